@@ -1,0 +1,93 @@
+"""ctypes binding of libfacl_b200.so (the C ABI declared in include/facl_b200.h).
+
+There is no CPU fallback: if the shared library is missing, importing a product module that needs it
+raises.  Build it with `python -c "import __graft_entry__ as g; g.build()"` or `make -C facl_b200/csrc`.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfacl_b200.so")
+
+_lib = None
+
+
+class FaclError(RuntimeError):
+    pass
+
+
+class Operand(C.Structure):
+    _fields_ = [("src0", C.c_void_p), ("src1", C.c_void_p), ("ld", C.c_longlong),
+                ("s0", C.c_void_p), ("s1", C.c_void_p), ("s2", C.c_void_p), ("lo", C.c_void_p)]
+
+
+class Gemm(C.Structure):
+    _fields_ = [("Md", C.c_int), ("Nd", C.c_int), ("Kd", C.c_int), ("nsplit", C.c_int),
+                ("a_mode", C.c_int), ("b_mode", C.c_int),
+                ("a_packed", C.c_void_p), ("a_packed_kblocks", C.c_int),
+                ("a", Operand), ("b", Operand),
+                ("ksplit", C.c_int),
+                ("bias", C.c_void_p), ("out_mode", C.c_int), ("out", C.c_void_p), ("ldo", C.c_longlong),
+                ("zin", C.c_void_p), ("ldz", C.c_longlong), ("zs0", C.c_void_p), ("zs2", C.c_void_p),
+                ("stats", C.c_void_p), ("pool", C.c_int), ("pool_sign", C.c_void_p), ("pool_out", C.c_void_p),
+                ("pool_arg", C.c_void_p), ("ldp", C.c_longlong)]
+
+
+_I, _LL, _P, _F, _SZ = C.c_int, C.c_longlong, C.c_void_p, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/facl_b200.h declares (tests check this)
+SIGNATURES = {
+    "facl_version": (C.c_char_p, []),
+    "facl_error_string": (C.c_char_p, [_I]),
+    "facl_fps": (_I, [_P, _I, _I, _I, _P, _I, _P, _P]),
+    "facl_fps_reorder": (_I, [_P, _I, _I, _I, _P, _I, _P, _P]),
+    "facl_group_points": (_I, [_P, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
+    "facl_packed_weight_bytes": (_SZ, [_I, _I]),
+    "facl_pack_weight": (_I, [_P, _LL, _LL, _I, _I, _P, _P]),
+    "facl_gemm_stat_partials": (_I, [_I, _I]),
+    "facl_gemm_tc": (_I, [C.POINTER(Gemm), _P]),
+}
+
+
+def lib():
+    """The loaded library (loads on first use; raises FaclError when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FaclError(
+                f"{LIB_PATH} not found: the CUDA library has not been built "
+                "(run `make -C facl_b200/csrc`); facl_b200 has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code, what=""):
+    if code != 0:
+        msg = lib().facl_error_string(int(code)).decode()
+        raise FaclError(f"{what or 'facl call'} failed: {msg} (cudaError {code})")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, name="tensor", dtype=torch.float32):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise FaclError(f"{name} must be a CUDA tensor: facl_b200 has no CPU path")
+    if dtype is not None and t.dtype != dtype:
+        raise FaclError(f"{name} must be {dtype}, got {t.dtype}")
+    return t

@@ -1,0 +1,33 @@
+// Shared host/device helpers for the facl_b200 CUDA library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FACL_CHECK(expr)                                   \
+    do {                                                   \
+        cudaError_t _e = (expr);                           \
+        if (_e != cudaSuccess) return (int)_e;             \
+    } while (0)
+
+#define FACL_CHECK_LAUNCH()                                \
+    do {                                                   \
+        cudaError_t _e = cudaGetLastError();               \
+        if (_e != cudaSuccess) return (int)_e;             \
+    } while (0)
+
+namespace facl {
+
+constexpr int kNumSMs = 148;
+
+// squared distance exactly as the reference evaluates it: ((dx*dx + dy*dy) + dz*dz), no FMA contraction
+// (utils_my.py:265-268 / cn3D_data_set.py:682-683)
+__device__ __forceinline__ float sqdist_ref(float px, float py, float pz, float cx, float cy, float cz) {
+    float dx = __fsub_rn(px, cx), dy = __fsub_rn(py, cy), dz = __fsub_rn(pz, cz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ int div_up_dev(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace facl
+
+static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

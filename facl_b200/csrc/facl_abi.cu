@@ -1,0 +1,58 @@
+// C-ABI shim: the only translation unit that defines exported symbols (see include/facl_b200.h).
+#include "../../include/facl_b200.h"
+#include "common.cuh"
+#include "facl_internal.h"
+#include "gemm_tc.cuh"
+
+using namespace facl;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* facl_version(void) { return "facl_b200 0.1 (sm_100a)"; }
+
+const char* facl_error_string(int code) { return cudaGetErrorString(static_cast<cudaError_t>(code)); }
+
+int facl_fps(const float* points, int V, int N, int D, const int* start_idx, int m, int* out_idx, void* stream) {
+    return fps_launch(points, V, N, D, start_idx, m, out_idx, S(stream));
+}
+
+int facl_fps_reorder(const float* points, int V, int N, int D, const int* picks, int m, float* out, void* stream) {
+    return fps_reorder_launch(points, V, N, D, picks, m, out, S(stream));
+}
+
+int facl_group_points(const float* points, int M, int N, int D, int Sc, int K, float r2, float* xt, int* idx, void* stream) {
+    return group_launch(points, M, N, D, Sc, K, r2, xt, idx, S(stream));
+}
+
+size_t facl_packed_weight_bytes(int rows, int cols) { return packed_weight_bytes(rows, cols); }
+
+int facl_pack_weight(const float* src, long long stride_m, long long stride_k, int rows, int cols, void* image, void* stream) {
+    return pack_weight_launch(src, stride_m, stride_k, rows, cols, image, S(stream));
+}
+
+static OperandSrc to_src(const facl_operand& o) {
+    OperandSrc s;
+    s.src0 = o.src0; s.src1 = o.src1; s.ld = o.ld; s.s0 = o.s0; s.s1 = o.s1; s.s2 = o.s2; s.lo = o.lo;
+    return s;
+}
+
+int facl_gemm_stat_partials(int Md, int Nd) { return gemm_tc_ctas_per_mtile(Md, Nd); }
+
+int facl_gemm_tc(const facl_gemm* d, void* stream) {
+    if (!d) return (int)cudaErrorInvalidValue;
+    GemmParams p;
+    p.Md = d->Md; p.Nd = d->Nd; p.Kd = d->Kd; p.nsplit = d->nsplit;
+    p.a_mode = d->a_mode; p.b_mode = d->b_mode;
+    p.a_packed = d->a_packed; p.a_packed_kblocks = d->a_packed_kblocks;
+    p.a = to_src(d->a); p.b = to_src(d->b);
+    p.ksplit = d->ksplit < 1 ? 1 : d->ksplit;
+    p.bias = d->bias; p.out_mode = d->out_mode; p.out = d->out; p.ldo = d->ldo;
+    p.zin = d->zin; p.ldz = d->ldz; p.zs0 = d->zs0; p.zs2 = d->zs2;
+    p.stats = d->stats; p.pool = d->pool; p.pool_sign = d->pool_sign; p.pool_out = d->pool_out;
+    p.pool_arg = d->pool_arg; p.ldp = d->ldp;
+    return launch_gemm_tc(p, S(stream));
+}
+
+}  // extern "C"

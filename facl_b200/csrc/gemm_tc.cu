@@ -1,0 +1,465 @@
+// Generic tcgen05 GEMM (see gemm_tc.cuh).  Warp-specialised, persistent over output tiles:
+//   warps 0-3  epilogue   (TMEM lanes 32w..32w+31 -> one output channel per thread)
+//   warps 4-7  producers  (fp32 global -> transform -> bf16 hi/lo -> swizzled K-major smem tiles)
+//   warp  8    MMA issuer (one lane issues tcgen05.mma; owns the TMEM allocation)
+//   warp  9    TMA        (one lane bulk-copies pre-packed weight tiles, cp.async.bulk + mbarrier tx)
+#include "gemm_tc.cuh"
+#include "umma.cuh"
+
+namespace facl {
+
+namespace {
+
+constexpr int M_TILE = 128;
+constexpr int N_TILE = 256;
+constexpr int K_BLK = 64;
+constexpr int A_TILE_BYTES = M_TILE * 128;
+constexpr int B_TILE_BYTES = N_TILE * 128;
+constexpr int NUM_PROD_WARPS = 4;
+constexpr int PROD_THREADS = NUM_PROD_WARPS * 32;
+constexpr int THREADS = 320;
+constexpr int NUM_SMS = 148;
+
+struct Work {
+    int mt, nt, kb0, kb1;
+};
+
+struct Schedule {
+    int numMT, numNT, KB, P;
+    int mt, nt, step, ks;
+    bool split;
+    __device__ Schedule(const GemmParams& p) {
+        numMT = (p.Md + M_TILE - 1) / M_TILE;
+        numNT = (p.Nd + N_TILE - 1) / N_TILE;
+        KB = (p.Kd + K_BLK - 1) / K_BLK;
+        split = p.ksplit > 1;
+        int b = blockIdx.x;
+        if (!split) {
+            P = gridDim.x / numMT;
+            mt = b % numMT;
+            nt = b / numMT;   // first n-tile; advance by P
+            step = P;
+            ks = 0;
+        } else {
+            P = 1;
+            mt = b % numMT;
+            nt = (b / numMT) % numNT;
+            ks = b / (numMT * numNT);
+            step = numNT;     // exactly one item
+        }
+    }
+    __device__ bool get(int it, const GemmParams& p, Work& w) const {
+        int n = nt + it * step;
+        if (n >= numNT) return false;
+        w.mt = mt;
+        w.nt = n;
+        if (!split) {
+            w.kb0 = 0;
+            w.kb1 = KB;
+        } else {
+            w.kb0 = (int)(((long long)ks * KB) / p.ksplit);
+            w.kb1 = (int)(((long long)(ks + 1) * KB) / p.ksplit);
+        }
+        return true;
+    }
+};
+
+__device__ __forceinline__ float xform(float a, float b, float s0, float s1, float s2, float lo) {
+    return fmaxf(fmaf(s0, a, fmaf(s1, b, s2)), lo);
+}
+
+__device__ __forceinline__ void store_chunk(uint8_t* hi, uint8_t* lo, int nhl, uint32_t row, uint32_t chunk, const float (&v)[8]) {
+    uint32_t off = sw128_offset(row, chunk);
+    if (nhl == 2) {
+        uint4 h, l;
+        split_bf16x8(v, h, l);
+        *reinterpret_cast<uint4*>(hi + off) = h;
+        *reinterpret_cast<uint4*>(lo + off) = l;
+    } else {
+        *reinterpret_cast<uint4*>(hi + off) = pack_bf16x8(v);
+    }
+}
+
+// fp32 source with K contiguous: rows of the tile are rows of the source; transform constants are per ROW.
+__device__ __forceinline__ void produce_rowmajor(const OperandSrc& s, uint8_t* hi, uint8_t* lo, int nhl, int nrows, int row0,
+                                                 int row_limit, int k0, int k_limit, int ptid) {
+    for (int task = ptid; task < nrows * 8; task += PROD_THREADS) {
+        int r = task >> 3, j = task & 7;
+        int grow = row0 + r;
+        int k = k0 + j * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (grow < row_limit && k < k_limit) {
+            float a[8], b[8];
+            const float* p0 = s.src0 + (long long)grow * s.ld + k;
+            bool full = (k + 8 <= k_limit);
+            if (full) {
+                float4 t0 = __ldg(reinterpret_cast<const float4*>(p0));
+                float4 t1 = __ldg(reinterpret_cast<const float4*>(p0) + 1);
+                a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] = (k + e < k_limit) ? __ldg(p0 + e) : 0.f;
+            }
+            if (s.src1) {
+                const float* p1 = s.src1 + (long long)grow * s.ld + k;
+                if (full) {
+                    float4 t0 = __ldg(reinterpret_cast<const float4*>(p1));
+                    float4 t1 = __ldg(reinterpret_cast<const float4*>(p1) + 1);
+                    b[0] = t0.x; b[1] = t0.y; b[2] = t0.z; b[3] = t0.w; b[4] = t1.x; b[5] = t1.y; b[6] = t1.z; b[7] = t1.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) b[e] = (k + e < k_limit) ? __ldg(p1 + e) : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) b[e] = 0.f;
+            }
+            float c0 = s.s0 ? __ldg(s.s0 + grow) : 1.f;
+            float c1 = s.s1 ? __ldg(s.s1 + grow) : 0.f;
+            float c2 = s.s2 ? __ldg(s.s2 + grow) : 0.f;
+            float cl = s.lo ? __ldg(s.lo + grow) : -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (k + e < k_limit) ? xform(a[e], b[e], c0, c1, c2, cl) : 0.f;
+        }
+        store_chunk(hi, lo, nhl, r, j, v);
+    }
+}
+
+// fp32 source stored channel-major [K][ld]: thread = tile row (coalesced along rows), transform constants are per K.
+__device__ __forceinline__ void produce_chmajor(const OperandSrc& s, uint8_t* hi, uint8_t* lo, int nhl, int nrows, int n0,
+                                                int n_limit, int k0, int k_limit, int pw, int lane) {
+#pragma unroll 1
+    for (int jj = 0; jj < 8 / NUM_PROD_WARPS; ++jj) {
+        int j = pw * (8 / NUM_PROD_WARPS) + jj;
+        int kb = k0 + j * 8;
+        float c0[8], c1[8], c2[8], cl[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            bool kv = kb + e < k_limit;
+            c0[e] = (kv && s.s0) ? __ldg(s.s0 + kb + e) : 1.f;
+            c1[e] = (kv && s.s1) ? __ldg(s.s1 + kb + e) : 0.f;
+            c2[e] = (kv && s.s2) ? __ldg(s.s2 + kb + e) : 0.f;
+            cl[e] = (kv && s.lo) ? __ldg(s.lo + kb + e) : -INFINITY;
+        }
+        for (int g = 0; g < (nrows + 31) / 32; ++g) {
+            int r = g * 32 + lane;
+            int n = n0 + r;
+            float v[8];
+            if (n < n_limit) {
+                float a[8], b[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] = (kb + e < k_limit) ? __ldg(s.src0 + (long long)(kb + e) * s.ld + n) : 0.f;
+                if (s.src1) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) b[e] = (kb + e < k_limit) ? __ldg(s.src1 + (long long)(kb + e) * s.ld + n) : 0.f;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) b[e] = 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = (kb + e < k_limit) ? xform(a[e], b[e], c0[e], c1[e], c2[e], cl[e]) : 0.f;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            }
+            if (r < N_TILE) store_chunk(hi, lo, nhl, r, j, v);
+        }
+    }
+}
+
+// grouped rows [Nd][4] (x - cx, y - cy, z - cz, feature): K = 4, zero-padded to one 16-wide MMA step.
+__device__ __forceinline__ void produce_xt4(const OperandSrc& s, uint8_t* hi, uint8_t* lo, int nhl, int nrows, int n0, int n_limit,
+                                            int ptid) {
+    for (int r = ptid; r < nrows; r += PROD_THREADS) {
+        int n = n0 + r;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (n < n_limit) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(s.src0) + n);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        }
+        store_chunk(hi, lo, nhl, r, 0, v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = 0.f;
+        store_chunk(hi, lo, nhl, r, 1, v);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nhl = (p.nsplit == 3) ? 2 : 1;
+    const int stage_bytes = (A_TILE_BYTES + B_TILE_BYTES) * nhl;
+    const int num_stages = (p.nsplit == 3) ? 2 : 4;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + num_stages * stage_bytes);
+    uint64_t* empty = full + num_stages;
+    uint64_t* acc_full = empty + num_stages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mma_n = (p.Nd >= N_TILE) ? N_TILE : ((p.Nd + 15) & ~15);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < num_stages; ++i) {
+            mbar_init(&full[i], NUM_PROD_WARPS + (p.a_mode == A_PACKED ? 1 : 0));
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 8) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    Schedule sched(p);
+    Work w;
+
+    if (warp < 4) {
+        // =============================== epilogue ===============================
+        const int c = sched.mt * M_TILE + warp * 32 + lane;
+        const bool cvalid = c < p.Md;
+        const float bias = (cvalid && p.bias) ? __ldg(p.bias + c) : 0.f;
+        const float zs0 = (cvalid && p.zs0) ? __ldg(p.zs0 + c) : 1.f;
+        const float zs2 = (cvalid && p.zs2) ? __ldg(p.zs2 + c) : 0.f;
+        const float psign = (cvalid && p.pool_sign) ? __ldg(p.pool_sign + c) : 1.f;
+        const bool keep_max = psign >= 0.f;
+        float stat0 = 0.f, stat1 = 0.f;
+        for (int it = 0; sched.get(it, p, w); ++it) {
+            const int buf = it & 1;
+            mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            tc_fence_after_sync();
+            float best = 0.f;
+            int barg = 0;
+            const int nchunks = (mma_n + 31) / 32;
+            for (int cc = 0; cc < nchunks; ++cc) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N_TILE + cc * 32), v);
+                tmem_ld_wait();
+                const int n0 = w.nt * N_TILE + cc * 32;
+                int nvalid = p.Nd - n0;
+                nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
+                if (cvalid && nvalid > 0) {
+                    float z[32];
+                    if (p.zin) {
+                        const float* zr = p.zin + (long long)c * p.ldz + n0;
+                        if (nvalid == 32 && ((p.ldz & 3) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                float4 t = __ldg(reinterpret_cast<const float4*>(zr) + q);
+                                z[4 * q] = t.x; z[4 * q + 1] = t.y; z[4 * q + 2] = t.z; z[4 * q + 3] = t.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) z[i] = (i < nvalid) ? __ldg(zr + i) : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float val = v[i] + bias;
+                        if (p.zin) {
+                            val = (fmaf(zs0, z[i], zs2) > 0.f) ? val : 0.f;
+                        }
+                        if (i < nvalid) {
+                            stat0 += val;
+                            stat1 = fmaf(val, p.zin ? z[i] : val, stat1);
+                        }
+                        v[i] = val;
+                    }
+                    if (p.pool) {
+                        const int pm = p.pool - 1;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (i < nvalid) {
+                                int pos = (cc * 32 + i) & pm;
+                                float sv = keep_max ? v[i] : -v[i];
+                                if (pos == 0 || sv > best) {
+                                    best = sv;
+                                    barg = pos;
+                                }
+                                if (pos == pm) {
+                                    long long gi = (long long)c * p.ldp + (n0 + i) / p.pool;
+                                    p.pool_out[gi] = keep_max ? best : -best;
+                                    if (p.pool_arg) p.pool_arg[gi] = (unsigned char)barg;
+                                }
+                            }
+                        }
+                    }
+                    if (p.out_mode == OUT_CHMAJOR) {
+                        float* o = p.out + (long long)c * p.ldo + n0;
+                        if (nvalid == 32 && ((p.ldo & 3) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nvalid) o[i] = v[i];
+                        }
+                    } else if (p.out_mode == OUT_ROWMAJOR) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nvalid) p.out[(long long)(n0 + i) * p.ldo + c] = v[i];
+                    } else if (p.out_mode == OUT_ATOMIC_CHMAJOR) {
+                        float* o = p.out + (long long)c * p.ldo + n0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nvalid) atomicAdd(o + i, v[i]);
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (p.stats && cvalid) {
+            int pidx = sched.split ? 0 : (blockIdx.x / sched.numMT);
+            float* st = p.stats + ((long long)pidx * p.Md + c) * 2;
+            st[0] = stat0;
+            st[1] = stat1;
+        }
+    } else if (warp < 8) {
+        // =============================== producers ===============================
+        const int pw = warp - 4;
+        const int ptid = threadIdx.x - 128;
+        int stage = 0, phase = 0;
+        for (int it = 0; sched.get(it, p, w); ++it) {
+            for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = smem + stage * stage_bytes;
+                uint8_t* a_hi = st;
+                uint8_t* a_lo = st + A_TILE_BYTES;
+                uint8_t* b_hi = st + A_TILE_BYTES * nhl;
+                uint8_t* b_lo = b_hi + B_TILE_BYTES;
+                if (p.a_mode == A_ROWMAJOR)
+                    produce_rowmajor(p.a, a_hi, a_lo, nhl, M_TILE, w.mt * M_TILE, p.Md, kb * K_BLK, p.Kd, ptid);
+                if (p.b_mode == B_ROWMAJOR)
+                    produce_rowmajor(p.b, b_hi, b_lo, nhl, mma_n, w.nt * N_TILE, p.Nd, kb * K_BLK, p.Kd, ptid);
+                else if (p.b_mode == B_CHMAJOR)
+                    produce_chmajor(p.b, b_hi, b_lo, nhl, mma_n, w.nt * N_TILE, p.Nd, kb * K_BLK, p.Kd, pw, lane);
+                else
+                    produce_xt4(p.b, b_hi, b_lo, nhl, mma_n, w.nt * N_TILE, p.Nd, ptid);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
+                if (++stage == num_stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // =============================== MMA issuer ===============================
+        const uint32_t idesc = umma_idesc_bf16(M_TILE, mma_n);
+        int stage = 0, phase = 0;
+        for (int it = 0; sched.get(it, p, w); ++it) {
+            const int buf = it & 1;
+            mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N_TILE);
+            for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after_sync();
+                if (lane == 0) {
+                    uint8_t* st = smem + stage * stage_bytes;
+                    const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_TILE_BYTES;
+                    const uint32_t b_hi = a_hi + A_TILE_BYTES * nhl, b_lo = b_hi + B_TILE_BYTES;
+                    int kleft = p.Kd - kb * K_BLK;
+                    int ksteps = kleft >= K_BLK ? 4 : (kleft + 15) / 16;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t acc = (kb > w.kb0 || ks > 0) ? 1u : 0u;
+                        const uint32_t ko = ks * 32;   // 16 bf16 = 32 bytes inside the 128-byte swizzled row
+                        umma_bf16_ss(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), idesc, acc);
+                        if (nhl == 2) {
+                            umma_bf16_ss(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), idesc, 1u);
+                            umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (kb == w.kb1 - 1) umma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+                if (++stage == num_stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // =============================== TMA (packed A) ===============================
+        if (p.a_mode == A_PACKED && lane == 0) {
+            int stage = 0, phase = 0;
+            const uint8_t* img = reinterpret_cast<const uint8_t*>(p.a_packed);
+            for (int it = 0; sched.get(it, p, w); ++it) {
+                for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* st = smem + stage * stage_bytes;
+                    const uint8_t* src = img + ((long long)w.mt * p.a_packed_kblocks + kb) * (2ll * A_TILE_BYTES);
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(A_TILE_BYTES * nhl));
+                    tma_bulk_g2s(st, src, A_TILE_BYTES, &full[stage]);
+                    if (nhl == 2) tma_bulk_g2s(st + A_TILE_BYTES, src + A_TILE_BYTES, A_TILE_BYTES, &full[stage]);
+                    if (++stage == num_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace
+
+int gemm_tc_ctas_per_mtile(int Md, int Nd) {
+    int numMT = (Md + M_TILE - 1) / M_TILE;
+    int numNT = (Nd + N_TILE - 1) / N_TILE;
+    int P = NUM_SMS / numMT;
+    if (P < 1) P = 1;
+    if (P > numNT) P = numNT;
+    return P;
+}
+
+int launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
+    static bool configured = false;
+    const int smem_bytes = 4 * (A_TILE_BYTES + B_TILE_BYTES) + 1024 + 256;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    if (p.Md <= 0 || p.Nd <= 0 || p.Kd <= 0) return (int)cudaErrorInvalidValue;
+    if (p.nsplit != 1 && p.nsplit != 3) return (int)cudaErrorInvalidValue;
+    if (p.pool && ((p.pool & (p.pool - 1)) != 0 || p.pool > N_TILE)) return (int)cudaErrorInvalidValue;
+    int numMT = (p.Md + M_TILE - 1) / M_TILE;
+    int numNT = (p.Nd + N_TILE - 1) / N_TILE;
+    int KB = (p.Kd + K_BLK - 1) / K_BLK;
+    int grid;
+    if (p.ksplit > 1) {
+        if (p.ksplit > KB || p.stats || p.pool) return (int)cudaErrorInvalidValue;
+        grid = numMT * numNT * p.ksplit;
+    } else {
+        grid = numMT * gemm_tc_ctas_per_mtile(p.Md, p.Nd);
+    }
+    gemm_tc_kernel<<<grid, THREADS, smem_bytes, stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace facl

@@ -1,0 +1,67 @@
+// Generic tcgen05 GEMM with fused operand prologues and reduction epilogues.
+//
+//   D[m, n] = sum_k A[m, k] * B[n, k]          m < Md ("channels", TMEM lanes), n < Nd ("rows", TMEM columns)
+//
+// Both operands are staged in shared memory as K-major bf16 tiles (128-byte rows, 128B swizzle) and
+// multiplied by tcgen05.mma (kind::f16, fp32 accumulators in TMEM).  nsplit = 3 runs the error-compensated
+// bf16x3 scheme (hi*hi + hi*lo + lo*hi), which is the "fp32" arithmetic mode of this library.
+//
+// Because the accumulator tile has output channels on TMEM lanes, an epilogue thread owns one channel and walks
+// its rows in registers: per-channel batch statistics, neighbourhood max-pooling and ReLU masks are in-thread
+// reductions -- no shuffles, no atomics.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace facl {
+
+// element transform applied while an fp32 source is converted into a bf16 operand tile:
+//     v = max(s0[ch] * src0 + s1[ch] * src1 + s2[ch], lo[ch])
+// null vectors mean s0 = 1, s1 = 0 (src1 unused), s2 = 0, lo = -inf.  `ch` is the K index for channel-major
+// sources and the tile-row index (m or n) for row-major sources.
+struct OperandSrc {
+    const float* src0;
+    const float* src1;
+    long long ld;        // leading dimension in elements
+    const float* s0;
+    const float* s1;
+    const float* s2;
+    const float* lo;
+};
+
+enum : int { A_PACKED = 0, A_ROWMAJOR = 1 };
+enum : int { B_ROWMAJOR = 1, B_CHMAJOR = 2, B_XT4 = 3 };
+enum : int { OUT_NONE = 0, OUT_CHMAJOR = 1, OUT_ROWMAJOR = 2, OUT_ATOMIC_CHMAJOR = 3 };
+
+struct GemmParams {
+    int Md, Nd, Kd;
+    int nsplit;                 // 1 (bf16) or 3 (bf16x3)
+    int a_mode, b_mode;
+    const void* a_packed;       // A_PACKED: [m_tile][k_blk][hi, lo][128 rows x 128 B], pre-swizzled
+    int a_packed_kblocks;       // k-blocks per m_tile in the packed image
+    OperandSrc a;               // A_ROWMAJOR: fp32 [Md][ld], K contiguous
+    OperandSrc b;               // B_ROWMAJOR: fp32 [Nd][ld]; B_CHMAJOR: fp32 [Kd][ld]; B_XT4: fp32 [Nd][4]
+    int ksplit;                 // 1: every CTA walks the whole K range; >1: split-K, one output tile per CTA
+    // ---- epilogue ----
+    const float* bias;          // [Md] or null
+    int out_mode;
+    float* out;
+    long long ldo;
+    const float* zin;           // optional fp32 [Md][ldz]: ReLU mask source and second statistic
+    long long ldz;
+    const float* zs0;           // mask = (zs0[c] * zin + zs2[c] > 0)
+    const float* zs2;
+    float* stats;               // optional [ctas_per_mtile][Md][2] partial sums: (sum v, sum v*v) or (sum v, sum v*zin)
+    int pool;                   // 0, or the number of consecutive columns max-pooled (divides 256)
+    const float* pool_sign;     // [Md]: >= 0 keep the max, < 0 keep the min (sign of the BN scale that follows)
+    float* pool_out;            // [Md][ldp] selected pre-activation value
+    unsigned char* pool_arg;    // [Md][ldp] position inside the group (first hit), or null
+    long long ldp;
+};
+
+// host launcher (gemm_tc.cu); returns cudaError_t as int
+int launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
+// CTAs that share one m-tile in the non-split schedule == number of stats partials per channel
+int gemm_tc_ctas_per_mtile(int Md, int Nd);
+
+}  // namespace facl

@@ -1,0 +1,145 @@
+"""CPU: the oracle must reproduce the fixtures the unmodified reference produced (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import torch
+
+import oracle
+from oracle.encoder import EncoderParams
+
+
+def _sorted_rows(a):
+    M, S, K, D = a.shape
+    flat = a.reshape(M * S, K, D)
+    out = np.empty_like(flat)
+    for i in range(flat.shape[0]):
+        r = flat[i]
+        out[i] = r[np.lexsort(r.T[::-1])]
+    return out.reshape(M, S, K, D)
+
+
+def test_fps_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "fps.npz"))
+    for i in range(int(z["n_cases"])):
+        got = oracle.farthest_point_sampling(z[f"pc_{i}"], int(z[f"m_{i}"]), int(z[f"start_{i}"]))
+        assert np.array_equal(got, z[f"idx_{i}"]), f"case {i}"
+        assert len(set(got.tolist())) == len(got)          # picks stay unique
+
+
+def test_fps_reorder():
+    pts = np.random.default_rng(0).random((2, 50, 4)).astype(np.float32)
+    out = oracle.fps_sample_data(pts, 8, [3, 7])
+    for v in range(2):
+        picks = oracle.farthest_point_sampling(pts[v, :, :3], 8, [3, 7][v])
+        assert np.array_equal(out[v, :8], pts[v, picks])
+        rest = np.setdiff1d(np.arange(50), picks)
+        assert np.array_equal(out[v, 8:], pts[v, rest])
+
+
+def test_grouping_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "group.npz"))
+    for name in z["names"]:
+        pts = torch.from_numpy(z[f"{name}_points"])
+        S, K = (int(v) for v in z[f"{name}_cfg"])
+        r2 = float(z[f"{name}_r2"])
+        xt, yt, idx = oracle.group_points(pts, S, K, r2)
+        rows = xt.permute(0, 2, 3, 1).contiguous().numpy()
+        assert np.array_equal(_sorted_rows(rows), z[f"{name}_rows_sorted"]), name
+        assert np.array_equal(np.sort(idx.numpy(), axis=2), z[f"{name}_idx_sorted"].astype(np.int32)), name
+        assert xt.shape == (pts.shape[0], 4, S, K) and yt.shape == (pts.shape[0], 3, S, 1)
+        assert torch.equal(yt[:, :, :, 0].permute(0, 2, 1), pts[:, :S, :3])
+
+
+def test_losses_match_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "losses.npz"))
+    for i in range(int(z["n_cases"])):
+        G, B, C = (int(v) for v in z[f"cfg_{i}"])
+        x = torch.from_numpy(z[f"x_{i}"]).requires_grad_(True)
+        xg = torch.from_numpy(z[f"xg_{i}"]).requires_grad_(True)
+        lg = oracle.global_contrast(G, xg, x, B)
+        lc = oracle.circle_contrast(G, x, B, z[f"order_{i}"])
+        (lg + lc).backward()
+        ref_g, ref_c = z[f"loss_{i}"]
+        assert abs(float(lg) - ref_g) <= 2e-5 * abs(ref_g) + 1e-4
+        assert abs(float(lc) - ref_c) <= 2e-5 * abs(ref_c) + 1e-4
+        for got, ref in ((x.grad, z[f"dx_{i}"]), (xg.grad, z[f"dxg_{i}"])):
+            ref = torch.from_numpy(ref)
+            assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-6
+
+
+def _load_step_fixture(golden_dir):
+    z = np.load(os.path.join(golden_dir, "train_step.npz"))
+    sd = oracle.init_state_dict(seed=int(z["seed_sd"]))
+    for k in list(sd):
+        if "sd0/" + k in z.files:
+            sd[k] = torch.from_numpy(z["sd0/" + k]).clone()
+    return z, sd
+
+
+def test_train_step_matches_reference(golden_dir):
+    z, sd = _load_step_fixture(golden_dir)
+    B, G, N, S, K = (int(v) for v in z["cfg"])
+    res = oracle.train_step(sd, torch.from_numpy(z["points"]), z["order"], S=S, K=K, r2=float(z["r2"]))
+
+    def rel2(a, b):
+        a = torch.as_tensor(a).double().reshape(-1)
+        b = torch.as_tensor(b).double().reshape(-1)
+        return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+    floor = rel2(z["x"], z["x64"])                         # the reference's own fp32-vs-fp64 deviation
+    assert rel2(res["x"], z["x"]) < 4 * floor + 1e-6
+    assert rel2(res["x_global"], z["x_global"]) < 4 * rel2(z["x_global"], z["x_global64"]) + 1e-6
+    assert abs(res["loss"] - z["loss"][0]) < 4 * abs(z["loss"][0] - z["loss64"][0]) + 1e-5 * abs(z["loss64"][0])
+    gscale = max(float(np.abs(z["grad64_val/" + k]).max()) for k in res["grads"])
+    for k, g in res["grads"].items():
+        pos = z["grad_pos/" + k]
+        got = g.reshape(-1).numpy()[pos]
+        ref64 = z["grad64_val/" + k]
+        noise = float(z["noise/" + k])
+        if noise > 1.0:                                    # mathematically-zero gradients (bias in front of a train-mode BN)
+            assert np.abs(got).max() < 1e-4 * gscale, k
+            continue
+        # sampled entries: error relative to the tensor's RMS magnitude, within the reference's rounding sensitivity
+        rms = float(z["grad64_norm/" + k]) / np.sqrt(g.numel())
+        if rms == 0.0:                                     # mapping.weight: feeds only the unused `code` output
+            assert np.abs(got).max() == 0.0, k
+            continue
+        err = np.sqrt(np.mean((got - ref64) ** 2)) / rms
+        assert err < 8 * noise + 1e-5, (k, err, noise)
+    # weights after the Adam step + BN running statistics
+    for k, v in sd.items():
+        if "sd1/" + k in z.files:
+            ref = torch.from_numpy(z["sd1/" + k])
+            if "running_" in k:
+                assert rel2(v, ref) < 1e-3, k
+            elif v.dtype.is_floating_point:
+                # first Adam step moves every entry by at most lr = 3e-4, in the direction of sign(grad): entries whose
+                # true gradient is 0 (biases in front of a train-mode BN) move by +-lr on rounding noise alone
+                assert float((v - ref).abs().max()) <= 2.5 * 3e-4, k
+            else:
+                assert int(v) == int(ref), k
+        elif "sd1_pos/" + k in z.files:
+            got = v.reshape(-1).numpy()[z["sd1_pos/" + k]]
+            assert np.allclose(got, z["sd1_val/" + k], rtol=0, atol=2.5 * 3e-4), k   # |delta| <= lr per Adam step
+
+
+def test_eval_forward_matches_reference(golden_dir):
+    z, sd = _load_step_fixture(golden_dir)
+    B, G, N, S, K = (int(v) for v in z["cfg"])
+    # the fixture's eval features were computed with the post-step weights: redo the step, then eval
+    oracle.train_step(sd, torch.from_numpy(z["points"]), z["order"], S=S, K=K, r2=float(z["r2"]))
+    clouds = torch.from_numpy(z["points"]).permute(1, 0, 2, 3).reshape(G * B, N, 4)
+    xt, yt, _ = oracle.group_points(clouds, S, K, float(z["r2"]))
+    with torch.no_grad():
+        x, _, _, xg = oracle.encoder_forward(EncoderParams(sd, training=False), xt, yt, gost=G)
+    feat = torch.cat([x, xg], 0)
+    ref = torch.from_numpy(z["eval_feat"])
+    assert float((feat - ref).norm() / ref.norm()) < 2e-3
+
+
+def test_info_nce_logits(golden_dir):
+    z, _ = _load_step_fixture(golden_dir)
+    B = int(z["cfg"][0])
+    logits, labels = oracle.info_nce_logits(torch.from_numpy(z["x"])[: 2 * B], B)
+    assert np.allclose(logits.numpy(), z["info_nce_logits"], rtol=1e-5, atol=1e-5)
+    assert labels.shape == (B,) and int(labels.sum()) == 0
