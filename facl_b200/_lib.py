@@ -35,6 +35,29 @@ class Gemm(C.Structure):
                 ("pool_arg", C.c_void_p), ("ldp", C.c_longlong)]
 
 
+NUM_BN_LAYERS = 7
+
+
+class Layer(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p)]
+
+
+class EncoderParams(C.Structure):
+    _fields_ = [("layer", Layer * NUM_BN_LAYERS), ("fc3_w", C.c_void_p), ("fc3_b", C.c_void_p), ("map_w", C.c_void_p)]
+
+
+class EncoderGrads(C.Structure):
+    _fields_ = [("dw", C.c_void_p * NUM_BN_LAYERS), ("db", C.c_void_p * NUM_BN_LAYERS),
+                ("dgamma", C.c_void_p * NUM_BN_LAYERS), ("dbeta", C.c_void_p * NUM_BN_LAYERS),
+                ("dfc3_w", C.c_void_p), ("dfc3_b", C.c_void_p)]
+
+
+class EncoderDims(C.Structure):
+    _fields_ = [("M", C.c_int), ("S", C.c_int), ("K", C.c_int), ("G", C.c_int), ("nsplit", C.c_int),
+                ("training", C.c_int)]
+
+
 _I, _LL, _P, _F, _SZ = C.c_int, C.c_longlong, C.c_void_p, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); must list every symbol include/facl_b200.h declares (tests check this)
@@ -48,6 +71,17 @@ SIGNATURES = {
     "facl_pack_weight": (_I, [_P, _LL, _LL, _I, _I, _P, _P]),
     "facl_gemm_stat_partials": (_I, [_I, _I]),
     "facl_gemm_tc": (_I, [C.POINTER(Gemm), _P]),
+    "facl_encoder_num_buffers": (_I, []),
+    "facl_encoder_buffer_name": (C.c_char_p, [_I]),
+    "facl_encoder_buffer_bytes": (_SZ, [_I, C.POINTER(EncoderDims)]),
+    "facl_encoder_buffer_backward_only": (_I, [_I]),
+    "facl_encoder_forward": (_I, [C.POINTER(EncoderDims), C.POINTER(EncoderParams), _P, _P, C.POINTER(C.c_void_p),
+                                  _P, _P, _P, _P, _P]),
+    "facl_encoder_backward": (_I, [C.POINTER(EncoderDims), C.POINTER(EncoderParams), _P, C.POINTER(C.c_void_p),
+                                   _P, _P, C.POINTER(EncoderGrads), _P]),
+    "facl_adam_step": (_I, [_P, _I, _F, _F, _F, _F, _I, _P]),
+    "facl_contrast_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "facl_contrast_losses": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
 }
 
 

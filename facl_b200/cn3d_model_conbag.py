@@ -1,0 +1,137 @@
+"""Drop-in for the reference module `training_code/cn3d_model_conbag.py`: PointNet_Plus and PointNet_Plus_fine.
+
+Same constructor signatures, attribute names and 52 state-dict keys as the reference
+(cn3d_model_conbag.py:22-91 and :141-210), so `load_state_dict(torch.load(...))` / `state_dict()` round-trip
+with reference checkpoints (extract_motion_feature.py:146, cn3d_train_motion_GL.py:341).  The nn.Conv2d /
+nn.BatchNorm2d / nn.Linear children are kept ONLY as parameter containers: forward() never calls them, it runs
+the sm_100a kernels of libfacl_b200.so (tcgen05 GEMMs with fused BatchNorm/ReLU/max-pool) and there is no CPU path.
+
+`precision`: "fp32" (default; bf16x3 error-compensated tensor-core products, fp32 accumulation) or "bf16".
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .encoder_rt import LAYER_PREFIXES, EncoderFunction, EncoderWorkspace
+
+nstates_plus_1 = [64, 64, 256]
+nstates_plus_2 = [128, 128, 256]
+nstates_plus_3 = [256, 512, 1024, 1024, 1024]
+
+
+class _EncoderBase(nn.Module):
+    def _build(self, opt, num_clusters, gost, dim, sample_num_level1, knn_K, normalize_input):
+        self.temperal_num = opt.temperal_num
+        self.knn_K = knn_K
+        self.ball_radius2 = opt.ball_radius2
+        self.sample_num_level1 = sample_num_level1
+        self.sample_num_level2 = opt.sample_num_level2
+        self.INPUT_FEATURE_NUM = opt.INPUT_FEATURE_NUM
+        self.num_outputs = opt.Num_Class
+        self.batch = opt.batchSize
+        self.dim = dim
+        self.num_clusters = num_clusters
+        self.gost = gost
+        self.normalize_input = normalize_input
+        self.pooling = opt.pooling
+        if self.pooling == 'concatenation':
+            self.dim_out = 1024
+        if self.INPUT_FEATURE_NUM != 4 or dim != 512 or num_clusters != 64:
+            raise _lib.FaclError("the sm_100a encoder is built for INPUT_FEATURE_NUM=4, dim=512, num_clusters=64")
+
+        def stack(cin, widths, pool):
+            mods = []
+            for w in widths:
+                mods += [nn.Conv2d(cin, w, kernel_size=(1, 1)), nn.BatchNorm2d(w), nn.ReLU(inplace=True)]
+                cin = w
+            if pool is not None:
+                mods.append(nn.MaxPool2d(pool, stride=1))
+            return nn.Sequential(*mods)
+
+        self.net3DV_1 = stack(self.INPUT_FEATURE_NUM, nstates_plus_1, (1, knn_K))
+        self.net3DV_3 = stack(3 + nstates_plus_2[2], nstates_plus_3[:3], None)
+        self.my_max_pool = nn.Sequential(nn.MaxPool2d((sample_num_level1, 1), stride=1))
+        self.gobaol_max_pool = nn.Sequential(nn.MaxPool2d((sample_num_level1 * gost, 1), stride=1))
+        self.netR_FC = nn.Sequential(
+            nn.Linear(self.dim_out, nstates_plus_3[4]),
+            nn.BatchNorm1d(nstates_plus_3[4]),
+            nn.ReLU(inplace=True),
+            nn.Linear(nstates_plus_3[4], self.dim),
+        )
+        self.mapping = nn.Linear(self.dim, self.num_clusters, bias=False)
+        self.precision = "fp32"
+        self._ws = None
+
+    # ---- plumbing -------------------------------------------------------------------------------------------
+    def _layers(self):
+        for name, ci, bi in LAYER_PREFIXES:
+            seq = getattr(self, name)
+            yield seq[ci], seq[bi]
+
+    def _param_list(self):
+        out = []
+        for conv, bn in self._layers():
+            out += [conv.weight, conv.bias, bn.weight, bn.bias]
+        out += [self.netR_FC[3].weight, self.netR_FC[3].bias, self.mapping.weight]
+        return out
+
+    def _bn_buffers(self):
+        out = []
+        for _, bn in self._layers():
+            out += [bn.running_mean, bn.running_var]
+        return out
+
+    def _workspace(self, dims, device, backward):
+        key = (dims.M, dims.S, dims.K, dims.G, bool(backward))
+        if self._ws is None or self._ws.key != key or next(iter(self._ws.tensors.values())).device != device:
+            self._ws = None          # release the old buffers before allocating the new set
+            self._ws = EncoderWorkspace(dims, device, backward)
+        return self._ws
+
+    def _run(self, xt, yt):
+        _lib.require_cuda(xt, "xt")
+        _lib.require_cuda(yt, "yt")
+        M, D, S, K = xt.shape
+        if D != 4 or S != self.sample_num_level1 or K != self.knn_K:
+            raise _lib.FaclError(f"xt must be (M,4,{self.sample_num_level1},{self.knn_K}), got {tuple(xt.shape)}")
+        if M % self.gost != 0:
+            raise _lib.FaclError(f"number of clouds {M} is not a multiple of gost={self.gost}")
+        rows = xt.permute(0, 2, 3, 1).contiguous()                       # no copy for group_points_* outputs
+        centres = yt.permute(0, 2, 1, 3).reshape(M * S, 3).contiguous()  # no copy for group_points_* outputs
+        params = self._param_list()
+        self._need_bwd = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        out = EncoderFunction.apply(rows, centres, self, *params)
+        if self.training:
+            with torch.no_grad():
+                for i, (_, bn) in enumerate(self._layers()):
+                    bn.num_batches_tracked += 2 if i == 6 else 1      # netR_FC runs on x and on x_global
+        return out
+
+
+class PointNet_Plus_fine(_EncoderBase):
+    """reference cn3d_model_conbag.py:141-234"""
+
+    def __init__(self, opt, num_clusters=64, gost=10, dim=512, sample_num_level1=32, knn_K=128, normalize_input=True):
+        super(PointNet_Plus_fine, self).__init__()
+        self._build(opt, num_clusters, gost, dim, sample_num_level1, knn_K, normalize_input)
+
+    def forward(self, xt, yt, loss_mode=0):
+        x, code, x_nor, x_global = self._run(xt, yt)
+        return x, code, x_nor, x_global
+
+
+class PointNet_Plus(_EncoderBase):
+    """reference cn3d_model_conbag.py:22-114.  The live reference forward returns x only (:114) although its
+    callers unpack four values (cn3d_train_motion_GL.py:234); set `return_all=True` for the 4-tuple of the
+    commented-out forward (:116-137), which is what PointNet_Plus_fine returns."""
+
+    def __init__(self, opt, num_clusters=64, gost=10, dim=512, normalize_input=True):
+        super(PointNet_Plus, self).__init__()
+        self._build(opt, num_clusters, gost, dim, opt.sample_num_level1, opt.knn_K, normalize_input)
+        self.return_all = False
+
+    def forward(self, xt, yt, loss_mode=0):
+        x, code, x_nor, x_global = self._run(xt, yt)
+        if self.return_all:
+            return x, code, x_nor, x_global
+        return x

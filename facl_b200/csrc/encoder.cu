@@ -1,0 +1,454 @@
+// Encoder forward / backward orchestration (generic-GEMM schedule).
+//
+// Replaces PointNet_Plus_fine.forward (reference training_code/cn3d_model_conbag.py:213-234) and its autograd
+// backward.  Every Conv2d(1x1)/Linear is a tcgen05 GEMM whose PROLOGUE applies the previous layer's
+// BatchNorm+ReLU while converting the fp32 activation to bf16 operand tiles, and whose EPILOGUE accumulates the
+// batch statistics the next BatchNorm needs (and, for the last layer of each stack, the max-pool).  Activations
+// are kept pre-BN ("z"), channel-major [C][rows], fp32.
+//
+// Train-mode BatchNorm + ReLU + max-pool identities used:
+//   max_k relu(a*z_k + b) = relu(a * (a >= 0 ? max_k z_k : min_k z_k) + b)            -> pool before BN
+//   dz = c0*dy + c1*z + c2   with c0 = g*rstd, c1 = -c0*rstd*dgamma/n, c2 = -c0*dbeta/n - c1*mean
+//   a conv/linear bias in front of a train-mode BN has zero gradient.
+#include <math.h>
+#include <string.h>
+
+#include "../../include/facl_b200.h"
+#include "common.cuh"
+#include "facl_internal.h"
+#include "gemm_tc.cuh"
+
+namespace facl {
+
+namespace {
+
+const int CIN[7] = {4, 64, 64, 259, 256, 512, 1024};
+const int COUT[7] = {64, 64, 256, 256, 512, 1024, 1024};
+const int C_EMB = 512, C_MAP = 64, C_FEAT = 1024;
+const float BN_EPS = 1e-5f, BN_MOM = 0.1f;
+
+enum Buf {
+    B_Z1, B_Z2, B_Z3, B_ARG3, B_PCAT, B_Z4, B_Z5, B_Z6, B_ARG6, B_PALL, B_ARGG, B_Z7, B_BN, B_VEC, B_STATS, B_WPACK,
+    B_DXT, B_DH7, B_DF, B_DY6, B_DH5, B_DH4, B_DP3, B_DY3, B_DH2, B_DH1, B_XTT, B_WPACKT,
+    NUM_BUFS
+};
+const char* BUF_NAMES[NUM_BUFS] = {"z1", "z2", "z3", "arg3", "pcat", "z4", "z5", "z6", "arg6", "pall", "argg", "z7", "bn", "vec",
+                                   "stats", "wpack", "dxt", "dh7", "df", "dy6", "dh5", "dh4", "dp3", "dy3", "dh2", "dh1", "xtt",
+                                   "wpackt"};
+const int FIRST_BWD_BUF = B_DXT;
+
+// forward weight images: layers 0..6, then fc3 (512x1024), then mapping (64x512)
+size_t wpack_offset(int idx) {
+    size_t off = 0;
+    for (int l = 0; l < idx; ++l) {
+        if (l < 7) off += packed_weight_bytes(COUT[l], CIN[l]);
+        else if (l == 7) off += packed_weight_bytes(C_EMB, C_FEAT);
+        else off += packed_weight_bytes(C_MAP, C_EMB);
+    }
+    return off;
+}
+// transposed images for the data-gradient GEMMs: layers 1..6 ([Cin'][Cout], layer 3 without its 3 xyz inputs), then fc3^T
+int tin(int l) { return l == 3 ? 256 : CIN[l]; }
+size_t wpackt_offset(int idx) {   // idx 1..6 layers, 7 = fc3^T, 8 = end
+    size_t off = 0;
+    for (int l = 1; l < idx; ++l) {
+        if (l < 7) off += packed_weight_bytes(tin(l), COUT[l]);
+        else off += packed_weight_bytes(C_FEAT, C_EMB);
+    }
+    return off;
+}
+
+size_t buffer_bytes(int i, const facl_encoder_dims* d) {
+    const size_t M = d->M, R3 = (size_t)d->M * d->S, R1 = R3 * d->K, B = d->M / d->G, MB = M + B, f = sizeof(float);
+    switch (i) {
+        case B_Z1: case B_Z2: case B_DH2: case B_DH1: return 64 * R1 * f;
+        case B_Z3: case B_DY3: return 256 * R1 * f;
+        case B_ARG3: return 256 * R3;
+        case B_PCAT: return 259 * R3 * f;
+        case B_Z4: case B_DH4: case B_DP3: return 256 * R3 * f;
+        case B_Z5: case B_DH5: return 512 * R3 * f;
+        case B_Z6: case B_DY6: return 1024 * R3 * f;
+        case B_ARG6: return 1024 * MB;
+        case B_PALL: case B_Z7: case B_DH7: case B_DF: return 1024 * MB * f;
+        case B_ARGG: return 1024 * B;
+        case B_BN: return 8 * 7 * 1024 * f;
+        case B_VEC: return 2048 * f;
+        case B_STATS: return 65536 * f;
+        case B_WPACK: return wpack_offset(9);
+        case B_DXT: return 512 * MB * f;
+        case B_XTT: return 4 * R1 * f;
+        case B_WPACKT: return wpackt_offset(8);
+    }
+    return 0;
+}
+
+struct Slot {
+    float *mean, *rstd, *scale, *shift, *c0, *c1, *c2;
+};
+Slot bn_slot(void* const* bufs, int i) {
+    float* base = reinterpret_cast<float*>(bufs[B_BN]) + (size_t)i * 7 * 1024;
+    float* vec = reinterpret_cast<float*>(bufs[B_VEC]);
+    Slot s{base, base + 1024, base + 2048, base + 3072, base + 4096, base + 5120, base + 6144};
+    if (i == 2) {   // BN of the last L1 layer feeds the 259-channel L3 input: its scale/shift live inside the input vectors
+        s.scale = vec + 3;
+        s.shift = vec + 320 + 3;
+    }
+    return s;
+}
+
+GemmParams gemm_base(int Md, int Nd, int Kd, int nsplit) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.Md = Md; p.Nd = Nd; p.Kd = Kd; p.nsplit = nsplit; p.ksplit = 1;
+    p.a_mode = A_PACKED; p.b_mode = B_CHMAJOR;
+    return p;
+}
+void set_packed_a(GemmParams& p, const void* img, int Kd) {
+    p.a_mode = A_PACKED;
+    p.a_packed = img;
+    p.a_packed_kblocks = (Kd + 63) / 64;
+}
+OperandSrc src1(const float* s, long long ld, const float* s0, const float* s2, const float* lo) {
+    OperandSrc o;
+    memset(&o, 0, sizeof(o));
+    o.src0 = s; o.ld = ld; o.s0 = s0; o.s2 = s2; o.lo = lo;
+    return o;
+}
+OperandSrc src2(const float* a, const float* b, long long ld, const float* c0, const float* c1, const float* c2) {
+    OperandSrc o;
+    memset(&o, 0, sizeof(o));
+    o.src0 = a; o.src1 = b; o.ld = ld; o.s0 = c0; o.s1 = c1; o.s2 = c2;
+    return o;
+}
+// Arithmetic mode per layer.  nsplit 3 ("fp32" mode) everywhere, or in "bf16" mode: single-pass bf16 for the layers
+// that carry the FLOPs (1..5) and the split scheme for the ones that are free -- the 4-wide first layer and the
+// head, which runs on M + B rows only and sits behind a small-batch BatchNorm1d that amplifies rounding.
+int layer_nsplit(int ns, int layer) {
+    if (ns == 3) return 3;
+    return (layer == 0 || layer >= 6) ? 3 : 1;
+}
+
+int pick_ksplit(int Md, int Nd, int Kd) {
+    int tiles = ((Md + 127) / 128) * ((Nd + 255) / 256);
+    int KB = (Kd + 63) / 64;
+    int ks = kNumSMs / tiles;
+    if (ks > KB) ks = KB;
+    return ks < 1 ? 1 : ks;
+}
+
+#define RUN(expr)                      \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != 0) return _rc;      \
+    } while (0)
+
+int check_dims(const facl_encoder_dims* d) {
+    if (!d || d->M <= 0 || d->G <= 0 || d->M % d->G != 0) return (int)cudaErrorInvalidValue;
+    if (d->K <= 0 || d->K > 256 || (d->K & (d->K - 1))) return (int)cudaErrorInvalidValue;
+    if (d->S <= 0 || d->S > 256 || (d->S & (d->S - 1))) return (int)cudaErrorInvalidValue;
+    if (d->nsplit != 1 && d->nsplit != 3) return (int)cudaErrorInvalidValue;
+    return 0;
+}
+
+}  // namespace
+
+int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, const float* xt, const float* centres,
+                    void* const* bufs, float* x, float* xg, float* x_nor, float* code, cudaStream_t st) {
+    RUN(check_dims(d));
+    const int M = d->M, S = d->S, K = d->K, G = d->G, B = M / G, ns = d->nsplit, tr = d->training;
+    const long long R3 = (long long)M * S, R1 = R3 * K, MB = M + B;
+    if (R1 > 2147483647LL) return (int)cudaErrorInvalidValue;
+    auto F = [&](int i) { return reinterpret_cast<float*>(bufs[i]); };
+    auto U = [&](int i) { return reinterpret_cast<unsigned char*>(bufs[i]); };
+    float* vec = F(B_VEC);
+    float* lo0 = vec + 960;
+    float* stats = tr ? F(B_STATS) : nullptr;
+    uint8_t* wp = reinterpret_cast<uint8_t*>(bufs[B_WPACK]);
+
+    // constant vectors: L3 input transform for the 3 centre-xyz channels (identity, no ReLU), zero lower bounds
+    RUN(fill_launch(vec, 3, 1.f, st));
+    RUN(fill_launch(vec + 320, 3, 0.f, st));
+    RUN(fill_launch(vec + 640, 3, -INFINITY, st));
+    RUN(fill_launch(vec + 643, 256, 0.f, st));
+    RUN(fill_launch(lo0, 1024, 0.f, st));
+    // operand images of the current weights
+    for (int l = 0; l < 7; ++l) RUN(pack_weight_launch(p->layer[l].w, CIN[l], 1, COUT[l], CIN[l], wp + wpack_offset(l), st));
+    RUN(pack_weight_launch(p->fc3_w, C_FEAT, 1, C_EMB, C_FEAT, wp + wpack_offset(7), st));
+    if (code) RUN(pack_weight_launch(p->map_w, C_EMB, 1, C_MAP, C_EMB, wp + wpack_offset(8), st));
+
+    auto finalize = [&](int layer, int slot_i, int Nd, double n) {
+        Slot s = bn_slot(bufs, slot_i);
+        const facl_layer& L = p->layer[layer];
+        return bn_finalize_launch(stats, gemm_tc_ctas_per_mtile(COUT[layer], Nd), COUT[layer], n, L.gamma, L.beta, L.running_mean,
+                                  L.running_var, BN_EPS, BN_MOM, tr, s.mean, s.rstd, s.scale, s.shift, st);
+    };
+
+    // ---- L1: 4 -> 64 -> 64 -> 256 over all M*S*K grouped rows, max over the K neighbours -------------------
+    {
+        GemmParams g = gemm_base(64, (int)R1, 4, layer_nsplit(ns, 0));
+        set_packed_a(g, wp + wpack_offset(0), 4);
+        g.b_mode = B_XT4;
+        g.b = src1(xt, 4, nullptr, nullptr, nullptr);
+        g.bias = p->layer[0].b;
+        g.out_mode = OUT_CHMAJOR; g.out = F(B_Z1); g.ldo = R1;
+        g.stats = stats;
+        RUN(launch_gemm_tc(g, st));
+        RUN(finalize(0, 0, (int)R1, (double)R1));
+    }
+    {
+        Slot s = bn_slot(bufs, 0);
+        GemmParams g = gemm_base(64, (int)R1, 64, ns);
+        set_packed_a(g, wp + wpack_offset(1), 64);
+        g.b = src1(F(B_Z1), R1, s.scale, s.shift, lo0);
+        g.bias = p->layer[1].b;
+        g.out_mode = OUT_CHMAJOR; g.out = F(B_Z2); g.ldo = R1;
+        g.stats = stats;
+        RUN(launch_gemm_tc(g, st));
+        RUN(finalize(1, 1, (int)R1, (double)R1));
+    }
+    {
+        Slot s = bn_slot(bufs, 1);
+        GemmParams g = gemm_base(256, (int)R1, 64, ns);
+        set_packed_a(g, wp + wpack_offset(2), 64);
+        g.b = src1(F(B_Z2), R1, s.scale, s.shift, lo0);
+        g.bias = p->layer[2].b;
+        if (tr) { g.out_mode = OUT_CHMAJOR; g.out = F(B_Z3); g.ldo = R1; }
+        g.stats = stats;
+        g.pool = K; g.pool_sign = p->layer[2].gamma; g.pool_out = F(B_PCAT) + 3 * R3; g.ldp = R3;
+        g.pool_arg = tr ? U(B_ARG3) : nullptr;
+        RUN(launch_gemm_tc(g, st));
+        RUN(finalize(2, 2, (int)R1, (double)R1));
+    }
+    // ---- L3: [centre xyz | pooled 256] -> 256 -> 512 -> 1024 over the M*S centres, max over the S centres ----
+    RUN(centres_to_chmajor_launch(centres, (int)R3, F(B_PCAT), R3, st));
+    {
+        GemmParams g = gemm_base(256, (int)R3, 259, ns);
+        set_packed_a(g, wp + wpack_offset(3), 259);
+        g.b = src1(F(B_PCAT), R3, vec, vec + 320, vec + 640);
+        g.bias = p->layer[3].b;
+        g.out_mode = OUT_CHMAJOR; g.out = F(B_Z4); g.ldo = R3;
+        g.stats = stats;
+        RUN(launch_gemm_tc(g, st));
+        RUN(finalize(3, 3, (int)R3, (double)R3));
+    }
+    {
+        Slot s = bn_slot(bufs, 3);
+        GemmParams g = gemm_base(512, (int)R3, 256, ns);
+        set_packed_a(g, wp + wpack_offset(4), 256);
+        g.b = src1(F(B_Z4), R3, s.scale, s.shift, lo0);
+        g.bias = p->layer[4].b;
+        g.out_mode = OUT_CHMAJOR; g.out = F(B_Z5); g.ldo = R3;
+        g.stats = stats;
+        RUN(launch_gemm_tc(g, st));
+        RUN(finalize(4, 4, (int)R3, (double)R3));
+    }
+    {
+        Slot s = bn_slot(bufs, 4);
+        GemmParams g = gemm_base(1024, (int)R3, 512, ns);
+        set_packed_a(g, wp + wpack_offset(5), 512);
+        g.b = src1(F(B_Z5), R3, s.scale, s.shift, lo0);
+        g.bias = p->layer[5].b;
+        if (tr) { g.out_mode = OUT_CHMAJOR; g.out = F(B_Z6); g.ldo = R3; }
+        g.stats = stats;
+        g.pool = S; g.pool_sign = p->layer[5].gamma; g.pool_out = F(B_PALL); g.ldp = MB;
+        g.pool_arg = tr ? U(B_ARG6) : nullptr;
+        RUN(launch_gemm_tc(g, st));
+        RUN(finalize(5, 5, (int)R3, (double)R3));
+    }
+    // ---- sequence aggregation: max over the G views (cn3d_model_conbag.py:225-226) ---------------------------
+    RUN(seq_pool_launch(F(B_PALL), MB, p->layer[5].gamma, C_FEAT, G, B, F(B_PALL) + M, MB, U(B_ARGG), st));
+    // ---- head netR_FC on the M cloud features, then on the B sequence features (two BN batches) --------------
+    for (int half = 0; half < 2; ++half) {
+        const int Nd = half == 0 ? M : B;
+        const long long off = half == 0 ? 0 : M;
+        Slot s5 = bn_slot(bufs, 5);
+        GemmParams g = gemm_base(1024, Nd, 1024, layer_nsplit(ns, 6));
+        set_packed_a(g, wp + wpack_offset(6), 1024);
+        g.b = src1(F(B_PALL) + off, MB, s5.scale, s5.shift, lo0);
+        g.bias = p->layer[6].b;
+        g.out_mode = OUT_CHMAJOR; g.out = F(B_Z7) + off; g.ldo = MB;
+        g.stats = stats;
+        RUN(launch_gemm_tc(g, st));
+        RUN(finalize(6, 6 + half, Nd, (double)Nd));
+        Slot s6 = bn_slot(bufs, 6 + half);
+        GemmParams h = gemm_base(C_EMB, Nd, 1024, layer_nsplit(ns, 7));
+        set_packed_a(h, wp + wpack_offset(7), 1024);
+        h.b = src1(F(B_Z7) + off, MB, s6.scale, s6.shift, lo0);
+        h.bias = p->fc3_b;
+        h.out_mode = OUT_ROWMAJOR; h.out = half == 0 ? x : xg; h.ldo = C_EMB;
+        RUN(launch_gemm_tc(h, st));
+    }
+    // ---- x_nor = normalize(x), code = mapping(x_nor) (cn3d_model_conbag.py:231-232) ---------------------------
+    if (x_nor) RUN(l2_normalize_launch(x, M, C_EMB, x_nor, st));
+    if (code) {
+        if (!x_nor) return (int)cudaErrorInvalidValue;
+        GemmParams g = gemm_base(C_MAP, M, C_EMB, layer_nsplit(ns, 8));
+        set_packed_a(g, wp + wpack_offset(8), C_EMB);
+        g.b_mode = B_ROWMAJOR;
+        g.b = src1(x_nor, C_EMB, nullptr, nullptr, nullptr);
+        g.out_mode = OUT_ROWMAJOR; g.out = code; g.ldo = C_MAP;
+        RUN(launch_gemm_tc(g, st));
+    }
+    return 0;
+}
+
+int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, const float* xt, void* const* bufs, const float* dx,
+                     const float* dxg, const facl_encoder_grads* gr, cudaStream_t st) {
+    RUN(check_dims(d));
+    if (!d->training) return (int)cudaErrorInvalidValue;
+    const int M = d->M, S = d->S, K = d->K, G = d->G, B = M / G, ns = d->nsplit;
+    const long long R3 = (long long)M * S, R1 = R3 * K, MB = M + B;
+    auto F = [&](int i) { return reinterpret_cast<float*>(bufs[i]); };
+    auto U = [&](int i) { return reinterpret_cast<unsigned char*>(bufs[i]); };
+    float* vec = F(B_VEC);
+    float* lo0 = vec + 960;
+    float* stats = F(B_STATS);
+    uint8_t* wt = reinterpret_cast<uint8_t*>(bufs[B_WPACKT]);
+
+    // transposed weight images for the data-gradient GEMMs
+    for (int l = 1; l < 7; ++l) {
+        const float* w = p->layer[l].w + (l == 3 ? 3 : 0);
+        RUN(pack_weight_launch(w, 1, CIN[l], tin(l), COUT[l], wt + wpackt_offset(l), st));
+    }
+    RUN(pack_weight_launch(p->fc3_w, 1, C_FEAT, C_FEAT, C_EMB, wt + wpackt_offset(7), st));
+    // weight gradients are accumulated with atomics (split-K): start from zero; biases in front of a BN get 0
+    for (int l = 0; l < 7; ++l) {
+        FACL_CHECK(cudaMemsetAsync(gr->dw[l], 0, sizeof(float) * COUT[l] * CIN[l], st));
+        FACL_CHECK(cudaMemsetAsync(gr->db[l], 0, sizeof(float) * COUT[l], st));
+    }
+    FACL_CHECK(cudaMemsetAsync(gr->dfc3_w, 0, sizeof(float) * C_EMB * C_FEAT, st));
+
+    // upstream gradients -> channel-major [512][M | B]
+    FACL_CHECK(cudaMemsetAsync(F(B_DXT), 0, sizeof(float) * C_EMB * MB, st));
+    if (dx) RUN(transpose_launch(dx, C_EMB, F(B_DXT), MB, M, C_EMB, st));
+    if (dxg) RUN(transpose_launch(dxg, C_EMB, F(B_DXT) + M, MB, B, C_EMB, st));
+    RUN(rowstats_launch(F(B_DXT), nullptr, MB, C_EMB, (int)MB, 0, gr->dfc3_b, st));   // netR_FC.3.bias: sum over both batches
+
+    auto wgrad = [&](int layer, int Md, int Nd, int Kd, const OperandSrc& a, const OperandSrc& b, float* out) {
+        GemmParams g = gemm_base(Md, Nd, Kd, layer_nsplit(ns, layer));
+        g.a_mode = A_ROWMAJOR; g.a = a;
+        g.b_mode = B_ROWMAJOR; g.b = b;
+        g.ksplit = pick_ksplit(Md, Nd, Kd);
+        g.out_mode = OUT_ATOMIC_CHMAJOR; g.out = out; g.ldo = Nd;
+        return launch_gemm_tc(g, st);
+    };
+    // dgrad: D[ci][r] = sum_co W^T[ci][co] * dz[co][r], masked by the ReLU of the layer below, + BN-backward sums
+    auto dgrad = [&](int layer, int Md, int Nd, int Kd, const void* wimg, const OperandSrc& b, const float* zin, long long ldz,
+                     const float* zs0, const float* zs2, float* out, long long ldo, bool want_stats) {
+        GemmParams g = gemm_base(Md, Nd, Kd, layer_nsplit(ns, layer));
+        set_packed_a(g, wimg, Kd);
+        g.b_mode = B_CHMAJOR; g.b = b;
+        g.zin = zin; g.ldz = ldz; g.zs0 = zs0; g.zs2 = zs2;
+        g.out_mode = OUT_CHMAJOR; g.out = out; g.ldo = ldo;
+        g.stats = want_stats ? stats : nullptr;
+        return launch_gemm_tc(g, st);
+    };
+    auto bwd_finalize = [&](int layer, int slot_i, int Md, int Nd, double n, int P, int accumulate) {
+        Slot s = bn_slot(bufs, slot_i);
+        (void)Md; (void)Nd;
+        return bn_bwd_finalize_launch(stats, P, COUT[layer], n, p->layer[layer].gamma, s.mean, s.rstd, gr->dgamma[layer],
+                                      gr->dbeta[layer], accumulate, s.c0, s.c1, s.c2, st);
+    };
+
+    // ---- head -------------------------------------------------------------------------------------------------
+    Slot s5 = bn_slot(bufs, 5);
+    for (int half = 0; half < 2; ++half) {
+        const int Nd = half == 0 ? M : B;
+        const long long off = half == 0 ? 0 : M;
+        Slot s6 = bn_slot(bufs, 6 + half);
+        // netR_FC.3: dW = dx^T-major * relu(bn(z7))
+        RUN(wgrad(7, C_EMB, C_FEAT, Nd, src1(F(B_DXT) + off, MB, nullptr, nullptr, nullptr),
+                  src1(F(B_Z7) + off, MB, s6.scale, s6.shift, lo0), gr->dfc3_w));
+        // grad wrt relu(bn(z7)), masked -> dh7, sums for BN(netR_FC.1)
+        RUN(dgrad(7, C_FEAT, Nd, C_EMB, wt + wpackt_offset(7), src1(F(B_DXT) + off, MB, nullptr, nullptr, nullptr), F(B_Z7) + off, MB,
+                  s6.scale, s6.shift, F(B_DH7) + off, MB, true));
+        RUN(bwd_finalize(6, 6 + half, C_FEAT, Nd, (double)Nd, gemm_tc_ctas_per_mtile(C_FEAT, Nd), half));
+        // netR_FC.0: dW = dz7 * relu(bn6(pooled))^T ; data grad masked by the pooled feature's ReLU
+        RUN(wgrad(6, C_FEAT, C_FEAT, Nd, src2(F(B_DH7) + off, F(B_Z7) + off, MB, s6.c0, s6.c1, s6.c2),
+                  src1(F(B_PALL) + off, MB, s5.scale, s5.shift, lo0), gr->dw[6]));
+        RUN(dgrad(6, C_FEAT, Nd, C_FEAT, wt + wpackt_offset(6), src2(F(B_DH7) + off, F(B_Z7) + off, MB, s6.c0, s6.c1, s6.c2),
+                  F(B_PALL) + off, MB, s5.scale, s5.shift, F(B_DF) + off, MB, false));
+    }
+    // sequence max -> the winning view's cloud; then the BN6 sums live on the pooled positions only
+    RUN(combine_pool_grads_launch(F(B_DF), MB, F(B_DF) + M, MB, U(B_ARGG), C_FEAT, G, B, st));
+    RUN(rowstats_launch(F(B_DF), F(B_PALL), MB, C_FEAT, M, 1, stats, st));
+    RUN(bwd_finalize(5, 5, C_FEAT, M, (double)R3, 1, 0));
+
+    // ---- L3 ---------------------------------------------------------------------------------------------------
+    FACL_CHECK(cudaMemsetAsync(F(B_DY6), 0, sizeof(float) * 1024 * R3, st));
+    RUN(pool_scatter_launch(F(B_DF), MB, U(B_ARG6), MB, C_FEAT, M, S, F(B_DY6), R3, st));
+    Slot s4 = bn_slot(bufs, 4), s3 = bn_slot(bufs, 3), s2 = bn_slot(bufs, 2), s1 = bn_slot(bufs, 1), s0 = bn_slot(bufs, 0);
+    {   // layer 5 (512 -> 1024)
+        OperandSrc dz = src2(F(B_DY6), F(B_Z6), R3, s5.c0, s5.c1, s5.c2);
+        RUN(wgrad(5, 1024, 512, (int)R3, dz, src1(F(B_Z5), R3, s4.scale, s4.shift, lo0), gr->dw[5]));
+        RUN(dgrad(5, 512, (int)R3, 1024, wt + wpackt_offset(5), dz, F(B_Z5), R3, s4.scale, s4.shift, F(B_DH5), R3, true));
+        RUN(bwd_finalize(4, 4, 512, (int)R3, (double)R3, gemm_tc_ctas_per_mtile(512, (int)R3), 0));
+    }
+    {   // layer 4 (256 -> 512)
+        OperandSrc dz = src2(F(B_DH5), F(B_Z5), R3, s4.c0, s4.c1, s4.c2);
+        RUN(wgrad(4, 512, 256, (int)R3, dz, src1(F(B_Z4), R3, s3.scale, s3.shift, lo0), gr->dw[4]));
+        RUN(dgrad(4, 256, (int)R3, 512, wt + wpackt_offset(4), dz, F(B_Z4), R3, s3.scale, s3.shift, F(B_DH4), R3, true));
+        RUN(bwd_finalize(3, 3, 256, (int)R3, (double)R3, gemm_tc_ctas_per_mtile(256, (int)R3), 0));
+    }
+    {   // layer 3 (259 -> 256): input = [centre xyz | relu(bn3(pooled))]; no gradient flows to the xyz channels
+        OperandSrc dz = src2(F(B_DH4), F(B_Z4), R3, s3.c0, s3.c1, s3.c2);
+        RUN(wgrad(3, 256, 259, (int)R3, dz, src1(F(B_PCAT), R3, vec, vec + 320, vec + 640), gr->dw[3]));
+        RUN(dgrad(3, 256, (int)R3, 256, wt + wpackt_offset(3), dz, F(B_PCAT) + 3 * R3, R3, s2.scale, s2.shift, F(B_DP3), R3, true));
+        RUN(bwd_finalize(2, 2, 256, (int)R3, (double)R1, gemm_tc_ctas_per_mtile(256, (int)R3), 0));
+    }
+    // ---- L1 ---------------------------------------------------------------------------------------------------
+    FACL_CHECK(cudaMemsetAsync(F(B_DY3), 0, sizeof(float) * 256 * R1, st));
+    RUN(pool_scatter_launch(F(B_DP3), R3, U(B_ARG3), R3, 256, (int)R3, K, F(B_DY3), R1, st));
+    {   // layer 2 (64 -> 256)
+        OperandSrc dz = src2(F(B_DY3), F(B_Z3), R1, s2.c0, s2.c1, s2.c2);
+        RUN(wgrad(2, 256, 64, (int)R1, dz, src1(F(B_Z2), R1, s1.scale, s1.shift, lo0), gr->dw[2]));
+        RUN(dgrad(2, 64, (int)R1, 256, wt + wpackt_offset(2), dz, F(B_Z2), R1, s1.scale, s1.shift, F(B_DH2), R1, true));
+        RUN(bwd_finalize(1, 1, 64, (int)R1, (double)R1, gemm_tc_ctas_per_mtile(64, (int)R1), 0));
+    }
+    {   // layer 1 (64 -> 64)
+        OperandSrc dz = src2(F(B_DH2), F(B_Z2), R1, s1.c0, s1.c1, s1.c2);
+        RUN(wgrad(1, 64, 64, (int)R1, dz, src1(F(B_Z1), R1, s0.scale, s0.shift, lo0), gr->dw[1]));
+        RUN(dgrad(1, 64, (int)R1, 64, wt + wpackt_offset(1), dz, F(B_Z1), R1, s0.scale, s0.shift, F(B_DH1), R1, true));
+        RUN(bwd_finalize(0, 0, 64, (int)R1, (double)R1, gemm_tc_ctas_per_mtile(64, (int)R1), 0));
+    }
+    {   // layer 0 (4 -> 64): only the weight gradient (the input points need none)
+        RUN(transpose_launch(xt, 4, F(B_XTT), R1, (int)R1, 4, st));
+        OperandSrc dz = src2(F(B_DH1), F(B_Z1), R1, s0.c0, s0.c1, s0.c2);
+        RUN(wgrad(0, 64, 4, (int)R1, dz, src1(F(B_XTT), R1, nullptr, nullptr, nullptr), gr->dw[0]));
+    }
+    return 0;
+}
+
+}  // namespace facl
+
+using namespace facl;
+
+extern "C" {
+
+int facl_encoder_num_buffers(void) { return NUM_BUFS; }
+const char* facl_encoder_buffer_name(int i) { return (i >= 0 && i < NUM_BUFS) ? BUF_NAMES[i] : ""; }
+size_t facl_encoder_buffer_bytes(int i, const facl_encoder_dims* dims) {
+    if (i < 0 || i >= NUM_BUFS || !dims || dims->G <= 0) return 0;
+    size_t b = buffer_bytes(i, dims);
+    return (b + 255) & ~(size_t)255;
+}
+int facl_encoder_buffer_backward_only(int i) { return i >= FIRST_BWD_BUF ? 1 : 0; }
+
+int facl_encoder_forward(const facl_encoder_dims* dims, const facl_encoder_params* params, const float* xt, const float* centres,
+                         void* const* buffers, float* x, float* x_global, float* x_nor, float* code, void* stream) {
+    if (!dims || !params || !xt || !centres || !buffers || !x || !x_global) return (int)cudaErrorInvalidValue;
+    return encoder_forward(dims, params, xt, centres, buffers, x, x_global, x_nor, code, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int facl_encoder_backward(const facl_encoder_dims* dims, const facl_encoder_params* params, const float* xt, void* const* buffers,
+                          const float* dx, const float* dx_global, const facl_encoder_grads* grads, void* stream) {
+    if (!dims || !params || !xt || !buffers || !grads) return (int)cudaErrorInvalidValue;
+    return encoder_backward(dims, params, xt, buffers, dx, dx_global, grads, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int facl_adam_step(const void* table_dev, int ntensors, float lr, float beta1, float beta2, float eps, int step, void* stream) {
+    if (!table_dev || ntensors <= 0 || step < 1) return (int)cudaErrorInvalidValue;
+    return adam_launch(table_dev, ntensors, lr, beta1, beta2, eps, step, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

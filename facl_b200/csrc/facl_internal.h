@@ -15,3 +15,24 @@ size_t packed_weight_bytes(int Md, int Kd);
 int pack_weight_launch(const float* src, long long stride_m, long long stride_k, int Md, int Kd, void* image, cudaStream_t st);
 
 }  // namespace facl
+
+namespace facl {
+// elementwise.cu
+int bn_finalize_launch(const float* partials, int P, int C, double n, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float eps, float momentum, int training, float* mean, float* rstd, float* scale,
+                       float* shift, cudaStream_t st);
+int bn_bwd_finalize_launch(const float* partials, int P, int C, double n, const float* gamma, const float* mean, const float* rstd,
+                           float* dgamma, float* dbeta, int accumulate, float* c0, float* c1, float* c2, cudaStream_t st);
+int rowstats_launch(const float* v, const float* z, long long ld, int C, int n, int pairs, float* out, cudaStream_t st);
+int transpose_launch(const float* in, long long ldi, float* out, long long ldo, int R, int C, cudaStream_t st);
+int seq_pool_launch(const float* pooled, long long ldp, const float* sign, int C, int G, int B, float* seq, long long lds,
+                    unsigned char* argg, cudaStream_t st);
+int combine_pool_grads_launch(float* dcloud, long long ldc, const float* dseq, long long lds, const unsigned char* argg, int C, int G,
+                              int B, cudaStream_t st);
+int pool_scatter_launch(const float* v, long long ldv, const unsigned char* arg, long long lda, int C, int groups, int pool,
+                        float* dense, long long ldd, cudaStream_t st);
+int centres_to_chmajor_launch(const float* c, int R, float* out, long long ldo, cudaStream_t st);
+int l2_normalize_launch(const float* x, int rows, int C, float* out, cudaStream_t st);
+int fill_launch(float* p, long long n, float v, cudaStream_t st);
+int adam_launch(const void* table_dev, int ntensors, float lr, float b1, float b2, float eps, int step, cudaStream_t st);
+}  // namespace facl

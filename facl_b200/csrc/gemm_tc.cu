@@ -93,7 +93,7 @@ __device__ __forceinline__ void produce_rowmajor(const OperandSrc& s, uint8_t* h
         if (grow < row_limit && k < k_limit) {
             float a[8], b[8];
             const float* p0 = s.src0 + (long long)grow * s.ld + k;
-            bool full = (k + 8 <= k_limit);
+            bool full = (k + 8 <= k_limit) && ((reinterpret_cast<uintptr_t>(p0) & 15) == 0);
             if (full) {
                 float4 t0 = __ldg(reinterpret_cast<const float4*>(p0));
                 float4 t1 = __ldg(reinterpret_cast<const float4*>(p0) + 1);
@@ -104,7 +104,7 @@ __device__ __forceinline__ void produce_rowmajor(const OperandSrc& s, uint8_t* h
             }
             if (s.src1) {
                 const float* p1 = s.src1 + (long long)grow * s.ld + k;
-                if (full) {
+                if (full && ((reinterpret_cast<uintptr_t>(p1) & 15) == 0)) {
                     float4 t0 = __ldg(reinterpret_cast<const float4*>(p1));
                     float4 t1 = __ldg(reinterpret_cast<const float4*>(p1) + 1);
                     b[0] = t0.x; b[1] = t0.y; b[2] = t0.z; b[3] = t0.w; b[4] = t1.x; b[5] = t1.y; b[6] = t1.z; b[7] = t1.w;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p)
                     float z[32];
                     if (p.zin) {
                         const float* zr = p.zin + (long long)c * p.ldz + n0;
-                        if (nvalid == 32 && ((p.ldz & 3) == 0)) {
+                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(zr) & 15) == 0)) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
                                 float4 t = __ldg(reinterpret_cast<const float4*>(zr) + q);
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p)
                     }
                     if (p.out_mode == OUT_CHMAJOR) {
                         float* o = p.out + (long long)c * p.ldo + n0;
-                        if (nvalid == 32 && ((p.ldo & 3) == 0)) {
+                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q)
                                 reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -311,6 +311,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p)
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             if (i < nvalid) p.out[(long long)(n0 + i) * p.ldo + c] = v[i];
+                    } else if (p.out_mode == OUT_ROWMAJOR_ACC) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nvalid) p.out[(long long)(n0 + i) * p.ldo + c] += v[i];
                     } else if (p.out_mode == OUT_ATOMIC_CHMAJOR) {
                         float* o = p.out + (long long)c * p.ldo + n0;
 #pragma unroll

@@ -1,0 +1,83 @@
+"""Host side of the contrastive losses: autograd.Function over the C ABI call facl_contrast_losses."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, stream_ptr
+
+_PRECISION = {"fp32": 3, "bf16": 1}
+precision = "fp32"      # module-level switch used by utils_my.global_contrast / circle_contrast
+
+_ws_cache = {}
+
+
+def _workspace(G, B, Cdim, device):
+    key = (G, B, Cdim, device)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        _ws_cache.clear()
+        ws = torch.empty(lib().facl_contrast_workspace_bytes(G, B, Cdim), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+class ContrastLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, x_global, G, B, order_dev, want_global, want_circle, nsplit):
+        x = x.contiguous()
+        M, Cdim = x.shape
+        if M != G * B:
+            raise _lib.FaclError(f"x has {M} rows, expected num_crop*batchSize = {G * B}")
+        dev = x.device
+        xg = x_global.contiguous() if x_global is not None else None
+        loss = torch.empty(2, dtype=torch.float32, device=dev)
+        dxg_part = torch.empty_like(x) if want_global else None
+        dxg = torch.empty((B, Cdim), dtype=torch.float32, device=dev) if want_global else None
+        dxc = torch.empty_like(x) if want_circle else None
+        ws = _workspace(G, B, Cdim, dev)
+        p = lambda t: None if t is None else t.data_ptr()
+        check(lib().facl_contrast_losses(p(x), p(xg), G, B, Cdim, p(order_dev), int(want_global), int(want_circle), nsplit,
+                                         ws.data_ptr(), loss.data_ptr(), p(dxg_part), p(dxg), p(dxc), stream_ptr()),
+              "facl_contrast_losses")
+        ctx.grads = (dxg_part, dxg, dxc)
+        ctx.has_xg = x_global is not None
+        return loss[0], loss[1]
+
+    @staticmethod
+    def backward(ctx, g_global, g_circle):
+        dxg_part, dxg, dxc = ctx.grads
+        dx = None
+        if dxg_part is not None and g_global is not None:
+            dx = dxg_part * g_global
+        if dxc is not None and g_circle is not None:
+            dx = dxc * g_circle if dx is None else dx + dxc * g_circle
+        dg = dxg * g_global if (dxg is not None and g_global is not None) else None
+        return dx, (dg if ctx.has_xg else None), None, None, None, None, None, None
+
+
+def contrast_losses(x, x_global, num_crop, batch_size, order=None, want_global=True, want_circle=True, prec=None):
+    """(loss_global, loss_circle) as 0-dim CUDA tensors with autograd (either may be a constant 0)."""
+    _lib.require_cuda(x, "x")
+    if want_global:
+        _lib.require_cuda(x_global, "x_global")
+    order_dev = None
+    if want_circle:
+        order_dev = torch.as_tensor(np.asarray(order, dtype=np.int32), device=x.device)
+    nsplit = _PRECISION[prec or precision]
+    return ContrastLossFunction.apply(x, x_global if want_global else None, int(num_crop), int(batch_size), order_dev,
+                                      bool(want_global), bool(want_circle), nsplit)
+
+
+def info_nce_logits_cuda(x, batch_size):
+    """Two-view logits of reference utils_my.py:200-213 (not on the live path; plain tensor algebra on the GPU)."""
+    _lib.require_cuda(x, "x")
+    B = batch_size
+    n = torch.arange(B, device=x.device)[:, None]
+    j = torch.arange(2 * B, device=x.device)[None, :]
+    mask = ((j % B) != n).to(x.dtype)
+    a, b = x[0:B], x[B:2 * B]
+    pos = (a * b).sum(dim=1, keepdim=True)
+    logits = torch.cat([pos, (a @ x.t()) * mask, (b @ x.t()) * mask], dim=1)
+    return logits, torch.zeros(B, dtype=torch.long, device=x.device)

@@ -1,0 +1,76 @@
+"""Drop-in for the reference module `training_code/utils_my.py` (the functions on the hot path).
+
+Same names, argument meaning, return shapes and `opt` side effects as the reference; the work is done by
+libfacl_b200.so on the GPU (no CPU path -- CPU tensors raise).
+
+  group_points_3DV / _2048 / _nums / group_points   reference utils_my.py:255-291 / :7-42 / :293-328 / :217-253
+  global_contrast / circle_contrast / Info_NCE      reference utils_my.py:53-83 / :85-116 / :200-213
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .losses import contrast_losses, info_nce_logits_cuda
+
+
+def _group(points, S, K, r2, N=None):
+    _lib.require_cuda(points, "points")
+    M = points.shape[0]
+    pts = points.reshape(M, -1, points.shape[-1]) if N is None else points.reshape(M, N, -1)
+    rows, _ = ops.group_points_raw(pts, S, K, r2, want_idx=False)
+    # reference return views (utils_my.py:283-284): xt (M,D,S,K) over the [M][S][K][D] buffer, yt (M,3,S,1)
+    inputs_level1 = rows.permute(0, 3, 1, 2)
+    centre = pts[:, 0:S, 0:3].contiguous()
+    inputs_level1_center = centre.view(-1, 1, S, 3).transpose(1, 3)
+    return inputs_level1, inputs_level1_center
+
+
+def group_points_3DV(points, opt):
+    """reference utils_my.py:255-291.  Side effects kept: overwrites opt.INPUT_FEATURE_NUM / knn_K / ball_radius
+    (:259-261), which makes the CLI radius and the per-step radius jitter of the train script dead."""
+    opt.INPUT_FEATURE_NUM = points.shape[-1]
+    opt.knn_K = 64
+    opt.ball_radius = 0.06
+    return _group(points, opt.sample_num_level1, opt.knn_K, opt.ball_radius, N=opt.SAMPLE_NUM)
+
+
+def group_points_3DV_2048(points, knn_K, sample_num_level1, SAMPLE_NUM=2048):
+    """reference utils_my.py:7-42 (squared radius hard-coded to 0.16, :13)."""
+    return _group(points, sample_num_level1, knn_K, 0.16)
+
+
+def group_points_3DV_nums(points, opt, sample_num_level1, knn_K):
+    """reference utils_my.py:293-328 (sets opt.ball_radius = 0.06, :299)."""
+    opt.INPUT_FEATURE_NUM = points.shape[-1]
+    opt.ball_radius = 0.06
+    return _group(points, sample_num_level1, knn_K, opt.ball_radius, N=opt.SAMPLE_NUM)
+
+
+def group_points(points, opt):
+    """reference utils_my.py:217-253 (sets opt.knn_K = 64, opt.ball_radius = 0.14)."""
+    opt.knn_K = 64
+    opt.ball_radius = 0.14
+    opt.INPUT_FEATURE_NUM = points.shape[-1]
+    return _group(points, opt.sample_num_level1, opt.knn_K, opt.ball_radius, N=opt.SAMPLE_NUM)
+
+
+def global_contrast(num_crop, x_global, x, opt, criterion=None):
+    """reference utils_my.py:53-83.  `criterion` must be CrossEntropyLoss with mean reduction (the only one the
+    reference passes, cn3d_train_motion_GL.py:179); it is accepted for signature parity and not called."""
+    loss_c, _ = contrast_losses(x, x_global, num_crop, opt.batchSize, order=None, want_global=True, want_circle=False)
+    return loss_c
+
+
+def circle_contrast(num_crop, x, batchSize, criterion=None, order=None):
+    """reference utils_my.py:85-116.  The view order is drawn like the reference does (np.random.shuffle of
+    arange(num_crop) from numpy's global RNG, :96-97) unless `order` is given."""
+    if order is None:
+        order = np.arange(0, num_crop, 1)
+        np.random.shuffle(order)
+    _, loss_circle = contrast_losses(x, None, num_crop, batchSize, order=order, want_global=False, want_circle=True)
+    return loss_circle
+
+
+def Info_NCE(x, opt):
+    """reference utils_my.py:200-213 (unused by the live scripts): logits (B, 1+4B) and zero labels."""
+    return info_nce_logits_cuda(x, opt.batchSize)

@@ -79,7 +79,7 @@ typedef struct facl_gemm {
     facl_operand a, b;
     int ksplit;              /* >1: split-K, use out_mode 3 (atomic accumulate) */
     const float* bias;       /* [Md] or NULL */
-    int out_mode;            /* 0 none, 1 out[m*ldo+n], 2 out[n*ldo+m], 3 atomicAdd out[m*ldo+n] */
+    int out_mode;            /* 0 none, 1 out[m*ldo+n], 2 out[n*ldo+m], 3 atomicAdd out[m*ldo+n], 4 out[n*ldo+m] += */
     float* out;
     long long ldo;
     const float* zin;        /* optional [Md][ldz]: v *= (zs0[m]*zin + zs2[m] > 0); 2nd statistic becomes sum v*zin */
@@ -96,6 +96,86 @@ typedef struct facl_gemm {
 
 FACL_API int facl_gemm_stat_partials(int Md, int Nd);
 FACL_API int facl_gemm_tc(const facl_gemm* desc, void* stream);
+
+/* ---- encoder: PointNet_Plus / PointNet_Plus_fine forward + backward ---------------------------------------
+ * replaces PointNet_Plus_fine.forward (reference training_code/cn3d_model_conbag.py:213-234; layers :162-210,
+ * identical in PointNet_Plus :43-91) and the autograd backward PyTorch derives for it.
+ *
+ * Layer table (index -> reference state-dict prefix): 0 net3DV_1.0/.1 (4->64)  1 net3DV_1.3/.4 (64->64)
+ * 2 net3DV_1.6/.7 (64->256)  3 net3DV_3.0/.1 (259->256)  4 net3DV_3.3/.4 (256->512)  5 net3DV_3.6/.7 (512->1024)
+ * 6 netR_FC.0/.1 (1024->1024).  Weights are the reference tensors themselves ([Cout][Cin] row-major fp32).    */
+#define FACL_NUM_BN_LAYERS 7
+
+typedef struct facl_layer {
+    const float* w;        /* conv / linear weight [Cout][Cin] */
+    const float* b;        /* bias [Cout] */
+    const float* gamma;    /* BatchNorm weight */
+    const float* beta;     /* BatchNorm bias */
+    float* running_mean;   /* updated in place in training mode (momentum 0.1, unbiased variance) */
+    float* running_var;
+} facl_layer;
+
+typedef struct facl_encoder_params {
+    facl_layer layer[FACL_NUM_BN_LAYERS];
+    const float* fc3_w;    /* netR_FC.3.weight [512][1024] */
+    const float* fc3_b;    /* netR_FC.3.bias   [512] */
+    const float* map_w;    /* mapping.weight   [64][512] */
+} facl_encoder_params;
+
+typedef struct facl_encoder_grads {   /* outputs of the backward; every pointer must be valid */
+    float* dw[FACL_NUM_BN_LAYERS];
+    float* db[FACL_NUM_BN_LAYERS];
+    float* dgamma[FACL_NUM_BN_LAYERS];
+    float* dbeta[FACL_NUM_BN_LAYERS];
+    float* dfc3_w;
+    float* dfc3_b;
+} facl_encoder_grads;
+
+typedef struct facl_encoder_dims {
+    int M;          /* clouds = G * B, G-major (row g*B + b), cn3d_train_motion_GL.py:225-226 */
+    int S;          /* centres per cloud (sample_num_level1) */
+    int K;          /* neighbours per centre (knn_K); power of two <= 256 */
+    int G;          /* views per sequence (the model's `gost`) */
+    int nsplit;     /* 1 = bf16 tensor-core operands, 3 = bf16x3 split (fp32-class accuracy) */
+    int training;   /* 1: batch statistics + running-stat update; 0: running statistics (extract_*_feature.py) */
+} facl_encoder_dims;
+
+/* Work buffers are owned by the caller: query the count / name / size, allocate each (256-byte aligned device
+ * memory) and pass the pointer table.  Buffers flagged "backward only" may be NULL for forward-only use. */
+FACL_API int facl_encoder_num_buffers(void);
+FACL_API const char* facl_encoder_buffer_name(int i);
+FACL_API size_t facl_encoder_buffer_bytes(int i, const facl_encoder_dims* dims);
+FACL_API int facl_encoder_buffer_backward_only(int i);
+
+/* xt [M*S*K][4] grouped rows (the physical layout of the reference's xt (M,4,S,K) view), centres [M*S][3]
+ * (the physical layout of yt (M,3,S,1)).  Outputs: x [M][512], x_global [M/G][512], x_nor [M][512],
+ * code [M][64] (x_nor / code may be NULL). */
+FACL_API int facl_encoder_forward(const facl_encoder_dims* dims, const facl_encoder_params* params, const float* xt,
+                                  const float* centres, void* const* buffers, float* x, float* x_global, float* x_nor,
+                                  float* code, void* stream);
+/* dx [M][512], dx_global [M/G][512]: gradients of the loss w.r.t. x / x_global (either may be NULL = zero).
+ * Must follow a training-mode forward on the same buffers. */
+FACL_API int facl_encoder_backward(const facl_encoder_dims* dims, const facl_encoder_params* params, const float* xt,
+                                   void* const* buffers, const float* dx, const float* dx_global,
+                                   const facl_encoder_grads* grads, void* stream);
+
+/* ---- optimiser: torch.optim.Adam(lr, betas, eps) step over a table of tensors (reference
+ * cn3d_train_motion_GL.py:180,332).  table_dev: device array of {float* p; const float* g; float* m; float* v;
+ * long long n} records; step is the 1-based step count used for bias correction. */
+FACL_API int facl_adam_step(const void* table_dev, int ntensors, float lr, float beta1, float beta2, float eps, int step,
+                            void* stream);
+
+/* ---- K6/K7: contrastive losses, forward + gradient -------------------------------------------------------
+ * replaces the inline "global" loss (reference training_code/cn3d_train_motion_GL.py:265-287 = utils_my.py:53-83
+ * global_contrast) and "circle" loss (:290-316 = utils_my.py:85-116 circle_contrast).
+ * x [G*B][C] (G-major rows), x_global [B][C]; order: device int32[G], the view permutation the reference draws
+ * with np.random.shuffle (:297-298).  loss[0] = global, loss[1] = circle (0 when not requested).
+ * Gradients for unit upstream weight: dx_global_part [G*B][C] and dx_global [B][C] (global loss),
+ * dx_circle_part [G*B][C] (circle loss).  C must be a multiple of 4. */
+FACL_API size_t facl_contrast_workspace_bytes(int G, int B, int C);
+FACL_API int facl_contrast_losses(const float* x, const float* x_global, int G, int B, int C, const int* order,
+                                  int want_global, int want_circle, int nsplit, void* workspace, float* loss,
+                                  float* dx_global_part, float* dx_global, float* dx_circle_part, void* stream);
 
 #ifdef __cplusplus
 }

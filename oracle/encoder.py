@@ -107,39 +107,62 @@ def _batchnorm(z, sd, key, training):
     return (z - mean) / torch.sqrt(var_b + BN_EPS) * gamma + beta
 
 
-def _shared_mlp(rows, sd, layers, training, taps=None):
+def _relu(y, routing, key):
+    """ReLU; with a routing table the activity pattern is imposed instead (see encoder_forward)."""
+    if routing is None or key not in routing:
+        return torch.relu(y)
+    return y * routing[key].to(y.dtype)
+
+
+def _shared_mlp(rows, sd, layers, training, taps=None, routing=None):
     h = rows
     for conv, bn, ci, co in layers:
         w = sd[conv + ".weight"].reshape(co, -1)
         z = h @ w.t() + sd[conv + ".bias"]
-        h = torch.relu(_batchnorm(z, sd, bn, training))
+        h = _relu(_batchnorm(z, sd, bn, training), routing, "relu:" + conv)
         if taps is not None:
             taps[conv] = z
     return h
 
 
-def _head(feat, sd, training):
+def _head(feat, sd, training, routing=None, key=None):
     z = feat @ sd["netR_FC.0.weight"].t() + sd["netR_FC.0.bias"]
-    h = torch.relu(_batchnorm(z, sd, "netR_FC.1", training))
+    h = _relu(_batchnorm(z, sd, "netR_FC.1", training), routing, key)
     return h @ sd["netR_FC.3.weight"].t() + sd["netR_FC.3.bias"]
 
 
-def encoder_forward(params, xt, yt, gost, taps=None):
+def _pool(h, dim, routing, key):
+    """max over `dim`; with a routing table the winner index is imposed instead (see encoder_forward)."""
+    if routing is None or key not in routing:
+        return h.max(dim=dim).values
+    idx = routing[key].to(torch.int64).unsqueeze(dim)
+    return h.gather(dim, idx).squeeze(dim)
+
+
+def encoder_forward(params, xt, yt, gost, taps=None, routing=None):
     """xt (M,D,S,K), yt (M,3,S,1) fp32; M = gost*B clouds, G-major.
-    Returns (x (M,512), code (M,64), x_nor (M,512), x_global (B,512))."""
+    Returns (x (M,512), code (M,64), x_nor (M,512), x_global (B,512)).
+
+    `routing` (tests only) imposes the network's discrete decisions instead of recomputing them, so that gradients
+    can be compared between two implementations whose forward values differ by rounding: the gradient of this
+    network is a discontinuous function of the activations (a near-tie in a max-pool flips where the gradient is
+    routed, an activation crossing 0 flips a ReLU), while for FIXED decisions it is smooth.  Keys: "k" (M*S,256)
+    winner among the K neighbours, "s" (M,1024) winner among the S centres, "g" (B,1024) winning view,
+    "relu:<conv key>" / "relu:head.x" / "relu:head.g" boolean activity patterns of the ReLUs."""
     sd, training = params.sd, params.training
     M, D, S, K = xt.shape
     rows = xt.permute(0, 2, 3, 1).reshape(M * S * K, D)
-    h = _shared_mlp(rows, sd, L1_LAYERS, training, taps)
-    pooled = h.reshape(M * S, K, -1).max(dim=1).values                 # max over the K neighbours
+    h = _shared_mlp(rows, sd, L1_LAYERS, training, taps, routing)
+    pooled = _pool(h.reshape(M * S, K, -1), 1, routing, "k")               # max over the K neighbours
     centre = yt.reshape(M, 3, S).permute(0, 2, 1).reshape(M * S, 3)
-    h = _shared_mlp(torch.cat([centre, pooled], dim=1), sd, L3_LAYERS, training, taps)
+    h = _shared_mlp(torch.cat([centre, pooled], dim=1), sd, L3_LAYERS, training, taps, routing)
     local = h.reshape(M, S, -1)                                        # xt_local, (M,S,1024)
-    feat = local.max(dim=1).values                                     # (M,1024)
+    feat = _pool(local, 1, routing, "s")                               # (M,1024)
     B = M // gost
-    feat_seq = local.reshape(gost, B, S, -1).max(dim=2).values.max(dim=0).values   # (B,1024)
-    x = _head(feat, sd, training)
-    x_global = _head(feat_seq, sd, training)
+    # max over all G*S positions of a sequence == max over the G per-cloud maxima
+    feat_seq = _pool(feat.reshape(gost, B, -1), 0, routing, "g")       # (B,1024)
+    x = _head(feat, sd, training, routing, "relu:head.x")
+    x_global = _head(feat_seq, sd, training, routing, "relu:head.g")
     x_nor = x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)
     code = x_nor @ sd["mapping.weight"].t()
     return x, code, x_nor, x_global

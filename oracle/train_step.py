@@ -29,7 +29,7 @@ def adam_update(sd, grads, state, lr=3e-4, betas=(0.5, 0.999), eps=1e-6):
 
 
 def train_step(sd, points_bgnd, order, S=64, K=64, r2=0.06, adam_state=None, lr=3e-4,
-               apply_update=True, dtype=torch.float32):
+               apply_update=True, dtype=torch.float32, routing=None):
     """points_bgnd (B,G,N,D) fp32.  Returns dict(loss, loss_global, loss_circle, grads, x, x_global).
     `sd` is updated in place (BN running stats always; weights when apply_update)."""
     B, G, N, D = points_bgnd.shape
@@ -40,7 +40,7 @@ def train_step(sd, points_bgnd, order, S=64, K=64, r2=0.06, adam_state=None, lr=
     leaves = params.trainable()
     for v in leaves.values():
         v.grad = None
-    x, code, x_nor, x_global = encoder_forward(params, xt, yt, gost=G)
+    x, code, x_nor, x_global = encoder_forward(params, xt, yt, gost=G, routing=routing)
     lg = global_contrast(G, x_global, x, B)
     lc = circle_contrast(G, x, B, order)
     loss = lc + lg
