@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Benchmark of the FACL hot path on B200: training sequences/s (grouping + encoder fwd + global/circle loss +
+backward + Adam) on synthetic NTU-shaped point-cloud sequences.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference ...                     # the reference algorithm on the host CPU (oracle port)
+
+Prints ONE JSON line (rank 0).  N=1 workload = BASELINE.json configs[1]: batch 64 x 20 views x 2048 points, fp32.
+For N>1 (torchrun) every rank keeps that per-GPU batch (weak scaling); embeddings are all-gathered for the
+contrastive losses and parameter gradients all-reduced.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+CFG2 = dict(B=64, G=20, N=2048, S=64, K=64, r2=0.16, precision="fp32")      # BASELINE.json configs[1]
+CPU_SAMPLE = dict(B=8, G=20, N=2048)                                          # bounded CPU sample of the same workload
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor_burst=p["bf16_tflops"], tensor_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle sampling during the timed region."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.stop_flag, self.rows = gpu_index, threading.Event(), []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=float(self.rows[0][1]) if self.rows else None,
+                    power_w_max=max(float(r[2]) for r in self.rows), samples=len(self.rows), reasons=reasons)
+
+
+def cpu_reference_step_time(B, G, N, steps, warmup, threads):
+    """The reference algorithm (oracle port: torch-CPU fp32 restatement of utils_my.group_points_3DV +
+    PointNet_Plus_fine + global/circle loss + autograd backward + Adam) on the host cores."""
+    import oracle
+    from facl_b200 import synth
+    torch.set_num_threads(threads)
+    sd = oracle.init_state_dict(seed=1)
+    pts = torch.from_numpy(synth.make_sequences(B, G, N, seed=1))
+    order = synth.view_order(G, 1)
+    state, times = {}, []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        res = oracle.train_step(sd, pts, order, S=64, K=64, r2=CFG2["r2"], adam_state=state)
+        state = res["adam_state"]
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), float(res["loss"])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    s = CPU_SAMPLE
+    sec, loss = cpu_reference_step_time(s["B"], s["G"], s["N"], max(1, min(args.steps, 3)), max(0, min(args.warmup, 1)), threads)
+    val = s["B"] / sec
+    line = dict(metric="train sequences/sec (encoder fwd+bwd+InfoNCE)", value=val, unit="sequences/s", n_gpus=args.gpus,
+                steps=max(1, min(args.steps, 3)), warmup=max(0, min(args.warmup, 1)), ms_per_step=sec * 1e3,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload="motion-stream contrastive training, 20 views x 2048 pts, fp32 (configs[1] shape)",
+                            global_batch=s["B"], note="bounded sample: batch 8 sequences per step on the host CPU"),
+                cpu_baseline=dict(value=val, unit="sequences/s", cores=threads, kind="port",
+                                  sample=f"oracle port, {s['B']} sequences x {s['G']} views x {s['N']} pts per step"),
+                e2e=dict(value=val, unit="sequences/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+TAG_NAMES = {27: "group_kernel", 28: "fps", 29: "pack_weight", 30: "bn_finalize", 31: "pool_misc", 32: "pool_scatter",
+             33: "loss_gemm", 34: "loss_misc", 35: "adam", 36: "transpose", 37: "memset"}
+CIN = [4, 64, 64, 259, 256, 512, 1024, 1024, 512]
+COUT = [64, 64, 256, 256, 512, 1024, 1024, 512, 64]
+
+
+def tag_name(t):
+    if t < 27:
+        return f"gemm_tc L{t // 3} {'fwd wgrad dgrad'.split()[t % 3]}"
+    return TAG_NAMES.get(t, str(t))
+
+
+def run_ours(args):
+    import ctypes as C
+    from facl_b200 import _lib, synth
+    from facl_b200.train import FusedTrainStep, TrainStep, default_opt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = dict(CFG2)
+    for k in ("B", "G", "N"):
+        if getattr(args, k) is not None:
+            cfg[k] = getattr(args, k)
+    if args.precision:
+        cfg["precision"] = args.precision
+    B, G, N = cfg["B"], cfg["G"], cfg["N"]
+    opt = default_opt(batchSize=B, SAMPLE_NUM=N)
+    tr = TrainStep(opt, num_crop=G, precision=cfg["precision"], radius2=cfg["r2"], device=f"cuda:{local_rank}", seed=1)
+    if world > 1:
+        from facl_b200.dist import DistributedFusedTrainStep
+        fused = DistributedFusedTrainStep(tr, B, G, N, r2=cfg["r2"])
+    else:
+        fused = FusedTrainStep(tr, B, G, N, r2=cfg["r2"])
+    nb = 2                                                           # distinct synthetic batches, cycled
+    host = [torch.from_numpy(synth.make_sequences(B, G, N, seed=100 + rank * 10 + i)).pin_memory() for i in range(nb)]
+    dev = [h.cuda(non_blocking=True) for h in host]
+    L = _lib.lib()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----------------------------------------------------------------------
+    for i in range(args.warmup):
+        fused.step(dev[i % nb])
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.facl_timing_enable(1 if rank == 0 else 0)
+    launches0 = L.facl_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        fused.step(dev[i % nb])
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = L.facl_launch_count() - launches0
+    L.facl_timing_enable(0)
+    ntags = 38
+    tms, tcnt = (C.c_float * ntags)(), (C.c_int * ntags)()
+    L.facl_timing_collect(tms, tcnt, ntags)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    loss_dev = float(fused.loss2[2])
+
+    # ---- end to end: pinned host batch in, loss back to the host, every step ------------------------------
+    e2e_steps = max(2, args.steps)
+    fused.step(host[0], want_host_loss=True)
+    sync_all()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(e2e_steps):
+        fused.step(host[i % nb], want_host_loss=True)
+        torch.cuda.current_stream().synchronize()                    # loss.item() of the reference loop (:335)
+        _ = float(fused.loss_host[0])
+    e1.record()
+    sync_all()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t)
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    M = G * B
+    R3, R1 = M * 64, M * 64 * 64
+    rows = [R1, R1, R1, R3, R3, R3, M + B, M + B, M]
+    per_tag = []
+    for t in range(ntags):
+        if tcnt[t] == 0:
+            continue
+        flops = None
+        if t < 27:
+            l = t // 3
+            flops = 2.0 * CIN[l] * COUT[l] * rows[l]                  # algorithmic FLOPs of one pass of this GEMM
+            if l == 3 and t % 3 == 2:
+                flops = 2.0 * 256 * 256 * rows[l]
+        per_tag.append(dict(tag=t, name=tag_name(t), ms_per_step=tms[t] / args.steps, launches_per_step=tcnt[t] / args.steps,
+                            flops=flops))
+    per_tag.sort(key=lambda d: -d["ms_per_step"])
+    kernel_ms = sum(d["ms_per_step"] for d in per_tag)
+    top = per_tag[0]
+    if top["flops"]:
+        achieved = top["flops"] * top["launches_per_step"] / (top["ms_per_step"] * 1e-3) / 1e12
+        roof = dict(kernel=top["name"], bound="tensor", achieved=achieved, peak=peaks["tensor_sustained"], unit="TFLOP/s",
+                    frac=achieved / peaks["tensor_sustained"], traffic=None, peak_source=peaks["source"] + ", sustained bf16",
+                    share_of_step=top["ms_per_step"] / (ms / args.steps))
+    else:
+        nbytes = {27: M * (16 * N + 16 * 64 * 64 + 12 * 64)}.get(top["tag"], 0)
+        achieved = nbytes / (top["ms_per_step"] * 1e-3) / 1e9
+        roof = dict(kernel=top["name"], bound="hbm", achieved=achieved, peak=peaks["hbm"], unit="GB/s",
+                    frac=achieved / peaks["hbm"], traffic=None, peak_source=peaks["source"],
+                    share_of_step=top["ms_per_step"] / (ms / args.steps))
+    # whole-step tensor roofline: 15.93 GFLOP per sequence against the sustained bf16 peak
+    step_flops = 796e6 * M
+    step_tf = step_flops / (ms / args.steps * 1e-3) / 1e12
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        s = CPU_SAMPLE
+        sec, _ = cpu_reference_step_time(s["B"], s["G"], s["N"], 2, 1, threads)
+        cpu = dict(value=s["B"] / sec, unit="sequences/s", cores=threads, kind="port",
+                   sample=f"oracle port (torch-CPU restatement of the reference step), {s['B']} sequences x {s['G']} views x "
+                          f"{s['N']} pts per step, 1 warm-up + 2 timed steps")
+    h2d = B * G * N * 4 * 4 + G * 4
+    line = dict(metric="train sequences/sec (encoder fwd+bwd+InfoNCE)", value=world * B * args.steps / (ms * 1e-3),
+                unit="sequences/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32 (bf16x3 split tensor-core products, fp32 accumulate)" if cfg["precision"] == "fp32" else
+                      "bf16 (fp32 accumulate, fp32 BN statistics / loss / master weights)",
+                data="synthetic",
+                config=dict(workload=f"motion-stream contrastive training, batch {B} x {G} views x {N} pts per GPU, "
+                                     f"S=K=64, r2={cfg['r2']}, {cfg['precision']} (BASELINE configs[1])",
+                            global_batch=world * B, parallelism=f"dp{world}", l2="working set (activations, >10 GB) >> 126 MB L2",
+                            loss_at_end=loss_dev),
+                e2e=dict(value=world * B * e2e_steps / (e2e_ms * 1e-3), unit="sequences/s", h2d_bytes_per_step=h2d,
+                         d2h_bytes_per_step=4, ms_per_step=e2e_ms / e2e_steps),
+                gpu_launches=int(launches), launches_per_step=launches / args.steps,
+                roofline=roof, step_tensor_tflops=step_tf, step_tensor_frac=step_tf / peaks["tensor_sustained"],
+                kernel_ms_per_step=kernel_ms, kernels=per_tag[:12], cpu_baseline=cpu, clocks=sampler.summary())
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--B", type=int, default=None)
+    ap.add_argument("--G", type=int, default=None)
+    ap.add_argument("--N", type=int, default=None)
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,17 @@ class EncoderDims(C.Structure):
                 ("training", C.c_int)]
 
 
+class TrainStepArgs(C.Structure):
+    _fields_ = [("dims", C.POINTER(EncoderDims)), ("params", C.POINTER(EncoderParams)), ("grads", C.POINTER(EncoderGrads)),
+                ("enc_buffers", C.POINTER(C.c_void_p)), ("N", C.c_int), ("r2", C.c_float),
+                ("points_bgnd", C.c_void_p), ("points_host", C.c_void_p), ("staging", C.c_void_p),
+                ("clouds", C.c_void_p), ("xt", C.c_void_p), ("centres", C.c_void_p), ("x", C.c_void_p),
+                ("x_global", C.c_void_p), ("order", C.c_void_p), ("loss_ws", C.c_void_p), ("loss2", C.c_void_p),
+                ("dx", C.c_void_p), ("dx_global", C.c_void_p), ("adam_table", C.c_void_p), ("adam_ntensors", C.c_int),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int),
+                ("loss_host", C.c_void_p)]
+
+
 _I, _LL, _P, _F, _SZ = C.c_int, C.c_longlong, C.c_void_p, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); must list every symbol include/facl_b200.h declares (tests check this)
@@ -80,6 +91,11 @@ SIGNATURES = {
     "facl_encoder_backward": (_I, [C.POINTER(EncoderDims), C.POINTER(EncoderParams), _P, C.POINTER(C.c_void_p),
                                    _P, _P, C.POINTER(EncoderGrads), _P]),
     "facl_adam_step": (_I, [_P, _I, _F, _F, _F, _F, _I, _P]),
+    "facl_gmajor": (_I, [_P, _P, _I, _I, _I, _P]),
+    "facl_train_step": (_I, [C.POINTER(TrainStepArgs), _P]),
+    "facl_timing_enable": (None, [_I]),
+    "facl_timing_collect": (_I, [_P, _P, _I]),
+    "facl_launch_count": (C.c_longlong, []),
     "facl_contrast_workspace_bytes": (_SZ, [_I, _I, _I]),
     "facl_contrast_losses": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
 }

@@ -104,10 +104,10 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__
     }
 }
 
-// out[c][r] = in[r][c]   (rows R, cols C), 32x32 tiles through shared memory
+// out[c][r] = in[r][c]   (rows R, cols C), 32x32 tiles through shared memory; blockIdx.x walks the rows (may be millions)
 __global__ void transpose_kernel(const float* __restrict__ in, long long ldi, float* __restrict__ out, long long ldo, int R, int C) {
     __shared__ float tile[32][33];
-    int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += 8) {
         int r = r0 + i, c = c0 + threadIdx.x;
         tile[i][threadIdx.x] = (r < R && c < C) ? in[(long long)r * ldi + c] : 0.f;
@@ -221,6 +221,8 @@ __global__ void adam_kernel(const AdamTensor* __restrict__ tab, int ntensors, fl
 int bn_finalize_launch(const float* partials, int P, int C, double n, const float* gamma, const float* beta, float* running_mean,
                        float* running_var, float eps, float momentum, int training, float* mean, float* rstd, float* scale,
                        float* shift, cudaStream_t st) {
+    ScopedTimer timer(TAG_BN, st);
+    count_launch();
     bn_finalize_kernel<<<div_up(C, 128), 128, 0, st>>>(partials, P, C, n, gamma, beta, running_mean, running_var, eps, momentum, training,
                                                        mean, rstd, scale, shift);
     return (int)cudaGetLastError();
@@ -228,56 +230,76 @@ int bn_finalize_launch(const float* partials, int P, int C, double n, const floa
 
 int bn_bwd_finalize_launch(const float* partials, int P, int C, double n, const float* gamma, const float* mean, const float* rstd,
                            float* dgamma, float* dbeta, int accumulate, float* c0, float* c1, float* c2, cudaStream_t st) {
+    ScopedTimer timer(TAG_BN, st);
+    count_launch();
     bn_bwd_finalize_kernel<<<div_up(C, 128), 128, 0, st>>>(partials, P, C, n, gamma, mean, rstd, dgamma, dbeta, accumulate, c0, c1, c2);
     return (int)cudaGetLastError();
 }
 
 int rowstats_launch(const float* v, const float* z, long long ld, int C, int n, int pairs, float* out, cudaStream_t st) {
+    ScopedTimer timer(TAG_POOLMISC, st);
+    count_launch();
     rowstats_kernel<<<C, 256, 0, st>>>(v, z, ld, n, pairs, out);
     return (int)cudaGetLastError();
 }
 
 int transpose_launch(const float* in, long long ldi, float* out, long long ldo, int R, int C, cudaStream_t st) {
-    dim3 grid(div_up(C, 32), div_up(R, 32)), block(32, 8);
+    ScopedTimer timer(TAG_TRANSPOSE, st);
+    count_launch();
+    dim3 grid(div_up(R, 32), div_up(C, 32)), block(32, 8);
     transpose_kernel<<<grid, block, 0, st>>>(in, ldi, out, ldo, R, C);
     return (int)cudaGetLastError();
 }
 
 int seq_pool_launch(const float* pooled, long long ldp, const float* sign, int C, int G, int B, float* seq, long long lds,
                     unsigned char* argg, cudaStream_t st) {
+    ScopedTimer timer(TAG_POOLMISC, st);
+    count_launch();
     seq_pool_kernel<<<div_up((long long)C * B, 256), 256, 0, st>>>(pooled, ldp, sign, C, G, B, seq, lds, argg);
     return (int)cudaGetLastError();
 }
 
 int combine_pool_grads_launch(float* dcloud, long long ldc, const float* dseq, long long lds, const unsigned char* argg, int C, int G,
                               int B, cudaStream_t st) {
+    ScopedTimer timer(TAG_POOLMISC, st);
+    count_launch();
     combine_pool_grads_kernel<<<div_up((long long)C * G * B, 256), 256, 0, st>>>(dcloud, ldc, dseq, lds, argg, C, G, B);
     return (int)cudaGetLastError();
 }
 
 int pool_scatter_launch(const float* v, long long ldv, const unsigned char* arg, long long lda, int C, int groups, int pool,
                         float* dense, long long ldd, cudaStream_t st) {
+    ScopedTimer timer(TAG_SCATTER, st);
+    count_launch();
     pool_scatter_kernel<<<div_up((long long)C * groups, 256), 256, 0, st>>>(v, ldv, arg, lda, C, groups, pool, dense, ldd);
     return (int)cudaGetLastError();
 }
 
 int centres_to_chmajor_launch(const float* c, int R, float* out, long long ldo, cudaStream_t st) {
+    ScopedTimer timer(TAG_POOLMISC, st);
+    count_launch();
     centres_to_chmajor_kernel<<<div_up(R, 256), 256, 0, st>>>(c, R, out, ldo);
     return (int)cudaGetLastError();
 }
 
 int l2_normalize_launch(const float* x, int rows, int C, float* out, cudaStream_t st) {
+    ScopedTimer timer(TAG_POOLMISC, st);
+    count_launch();
     l2_normalize_kernel<<<div_up((long long)rows * 32, 256), 256, 0, st>>>(x, rows, C, out);
     return (int)cudaGetLastError();
 }
 
 int fill_launch(float* p, long long n, float v, cudaStream_t st) {
     if (n <= 0) return 0;
+    ScopedTimer timer(TAG_MEMSET, st);
+    count_launch();
     fill_kernel<<<div_up(n, 256), 256, 0, st>>>(p, n, v);
     return (int)cudaGetLastError();
 }
 
 int adam_launch(const void* table_dev, int ntensors, float lr, float b1, float b2, float eps, int step, cudaStream_t st) {
+    ScopedTimer timer(TAG_ADAM, st);
+    count_launch();
     float bc1 = (float)(1.0 - pow((double)b1, (double)step));
     float bc2 = (float)sqrt(1.0 - pow((double)b2, (double)step));
     dim3 grid(64, ntensors < 64 ? ntensors : 64);

@@ -101,6 +101,7 @@ GemmParams gemm_base(int Md, int Nd, int Kd, int nsplit) {
     memset(&p, 0, sizeof(p));
     p.Md = Md; p.Nd = Nd; p.Kd = Kd; p.nsplit = nsplit; p.ksplit = 1;
     p.a_mode = A_PACKED; p.b_mode = B_CHMAJOR;
+    p.tag = -1;
     return p;
 }
 void set_packed_a(GemmParams& p, const void* img, int Kd) {
@@ -186,6 +187,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     // ---- L1: 4 -> 64 -> 64 -> 256 over all M*S*K grouped rows, max over the K neighbours -------------------
     {
         GemmParams g = gemm_base(64, (int)R1, 4, layer_nsplit(ns, 0));
+        g.tag = 0;
         set_packed_a(g, wp + wpack_offset(0), 4);
         g.b_mode = B_XT4;
         g.b = src1(xt, 4, nullptr, nullptr, nullptr);
@@ -198,6 +200,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     {
         Slot s = bn_slot(bufs, 0);
         GemmParams g = gemm_base(64, (int)R1, 64, ns);
+        g.tag = 3;
         set_packed_a(g, wp + wpack_offset(1), 64);
         g.b = src1(F(B_Z1), R1, s.scale, s.shift, lo0);
         g.bias = p->layer[1].b;
@@ -209,6 +212,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     {
         Slot s = bn_slot(bufs, 1);
         GemmParams g = gemm_base(256, (int)R1, 64, ns);
+        g.tag = 6;
         set_packed_a(g, wp + wpack_offset(2), 64);
         g.b = src1(F(B_Z2), R1, s.scale, s.shift, lo0);
         g.bias = p->layer[2].b;
@@ -223,6 +227,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     RUN(centres_to_chmajor_launch(centres, (int)R3, F(B_PCAT), R3, st));
     {
         GemmParams g = gemm_base(256, (int)R3, 259, ns);
+        g.tag = 9;
         set_packed_a(g, wp + wpack_offset(3), 259);
         g.b = src1(F(B_PCAT), R3, vec, vec + 320, vec + 640);
         g.bias = p->layer[3].b;
@@ -234,6 +239,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     {
         Slot s = bn_slot(bufs, 3);
         GemmParams g = gemm_base(512, (int)R3, 256, ns);
+        g.tag = 12;
         set_packed_a(g, wp + wpack_offset(4), 256);
         g.b = src1(F(B_Z4), R3, s.scale, s.shift, lo0);
         g.bias = p->layer[4].b;
@@ -245,6 +251,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     {
         Slot s = bn_slot(bufs, 4);
         GemmParams g = gemm_base(1024, (int)R3, 512, ns);
+        g.tag = 15;
         set_packed_a(g, wp + wpack_offset(5), 512);
         g.b = src1(F(B_Z5), R3, s.scale, s.shift, lo0);
         g.bias = p->layer[5].b;
@@ -263,6 +270,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
         const long long off = half == 0 ? 0 : M;
         Slot s5 = bn_slot(bufs, 5);
         GemmParams g = gemm_base(1024, Nd, 1024, layer_nsplit(ns, 6));
+        g.tag = 18;
         set_packed_a(g, wp + wpack_offset(6), 1024);
         g.b = src1(F(B_PALL) + off, MB, s5.scale, s5.shift, lo0);
         g.bias = p->layer[6].b;
@@ -272,6 +280,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
         RUN(finalize(6, 6 + half, Nd, (double)Nd));
         Slot s6 = bn_slot(bufs, 6 + half);
         GemmParams h = gemm_base(C_EMB, Nd, 1024, layer_nsplit(ns, 7));
+        h.tag = 21;
         set_packed_a(h, wp + wpack_offset(7), 1024);
         h.b = src1(F(B_Z7) + off, MB, s6.scale, s6.shift, lo0);
         h.bias = p->fc3_b;
@@ -283,6 +292,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     if (code) {
         if (!x_nor) return (int)cudaErrorInvalidValue;
         GemmParams g = gemm_base(C_MAP, M, C_EMB, layer_nsplit(ns, 8));
+        g.tag = 24;
         set_packed_a(g, wp + wpack_offset(8), C_EMB);
         g.b_mode = B_ROWMAJOR;
         g.b = src1(x_nor, C_EMB, nullptr, nullptr, nullptr);
@@ -326,6 +336,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
 
     auto wgrad = [&](int layer, int Md, int Nd, int Kd, const OperandSrc& a, const OperandSrc& b, float* out) {
         GemmParams g = gemm_base(Md, Nd, Kd, layer_nsplit(ns, layer));
+        g.tag = 3 * layer + 1;
         g.a_mode = A_ROWMAJOR; g.a = a;
         g.b_mode = B_ROWMAJOR; g.b = b;
         g.ksplit = pick_ksplit(Md, Nd, Kd);
@@ -336,6 +347,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
     auto dgrad = [&](int layer, int Md, int Nd, int Kd, const void* wimg, const OperandSrc& b, const float* zin, long long ldz,
                      const float* zs0, const float* zs2, float* out, long long ldo, bool want_stats) {
         GemmParams g = gemm_base(Md, Nd, Kd, layer_nsplit(ns, layer));
+        g.tag = 3 * layer + 2;
         set_packed_a(g, wimg, Kd);
         g.b_mode = B_CHMAJOR; g.b = b;
         g.zin = zin; g.ldz = ldz; g.zs0 = zs0; g.zs2 = zs2;
@@ -375,7 +387,10 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
     RUN(bwd_finalize(5, 5, C_FEAT, M, (double)R3, 1, 0));
 
     // ---- L3 ---------------------------------------------------------------------------------------------------
-    FACL_CHECK(cudaMemsetAsync(F(B_DY6), 0, sizeof(float) * 1024 * R3, st));
+    {
+        ScopedTimer timer(TAG_MEMSET, st);
+        FACL_CHECK(cudaMemsetAsync(F(B_DY6), 0, sizeof(float) * 1024 * R3, st));
+    }
     RUN(pool_scatter_launch(F(B_DF), MB, U(B_ARG6), MB, C_FEAT, M, S, F(B_DY6), R3, st));
     Slot s4 = bn_slot(bufs, 4), s3 = bn_slot(bufs, 3), s2 = bn_slot(bufs, 2), s1 = bn_slot(bufs, 1), s0 = bn_slot(bufs, 0);
     {   // layer 5 (512 -> 1024)
@@ -397,7 +412,10 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
         RUN(bwd_finalize(2, 2, 256, (int)R3, (double)R1, gemm_tc_ctas_per_mtile(256, (int)R3), 0));
     }
     // ---- L1 ---------------------------------------------------------------------------------------------------
-    FACL_CHECK(cudaMemsetAsync(F(B_DY3), 0, sizeof(float) * 256 * R1, st));
+    {
+        ScopedTimer timer(TAG_MEMSET, st);
+        FACL_CHECK(cudaMemsetAsync(F(B_DY3), 0, sizeof(float) * 256 * R1, st));
+    }
     RUN(pool_scatter_launch(F(B_DP3), R3, U(B_ARG3), R3, 256, (int)R3, K, F(B_DY3), R1, st));
     {   // layer 2 (64 -> 256)
         OperandSrc dz = src2(F(B_DY3), F(B_Z3), R1, s2.c0, s2.c1, s2.c2);

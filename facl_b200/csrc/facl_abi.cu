@@ -52,6 +52,7 @@ int facl_gemm_tc(const facl_gemm* d, void* stream) {
     p.zin = d->zin; p.ldz = d->ldz; p.zs0 = d->zs0; p.zs2 = d->zs2;
     p.stats = d->stats; p.pool = d->pool; p.pool_sign = d->pool_sign; p.pool_out = d->pool_out;
     p.pool_arg = d->pool_arg; p.ldp = d->ldp;
+    p.tag = -1;
     return launch_gemm_tc(p, S(stream));
 }
 

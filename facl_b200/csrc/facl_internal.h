@@ -36,3 +36,29 @@ int l2_normalize_launch(const float* x, int rows, int C, float* out, cudaStream_
 int fill_launch(float* p, long long n, float v, cudaStream_t st);
 int adam_launch(const void* table_dev, int ntensors, float lr, float b1, float b2, float eps, int step, cudaStream_t st);
 }  // namespace facl
+
+namespace facl {
+// profiler.cu
+void count_launch(int n = 1);
+struct ScopedTimer {
+    ScopedTimer(int tag, cudaStream_t st);
+    ~ScopedTimer();
+    int tag_;
+    cudaStream_t st_;
+    bool active_;
+    cudaEvent_t a_, b_;
+};
+// timing tags (facl_timing_collect index).  GEMM tags: 3*layer + kind (0 fwd, 1 wgrad, 2 dgrad), layer 0..8
+// (7 = netR_FC.3, 8 = mapping); then the non-GEMM kernels.
+enum TimingTag {
+    TAG_GEMM_BASE = 0,
+    TAG_GROUP = 27, TAG_FPS = 28, TAG_PACK = 29, TAG_BN = 30, TAG_POOLMISC = 31, TAG_SCATTER = 32, TAG_LOSS_GEMM = 33,
+    TAG_LOSS_MISC = 34, TAG_ADAM = 35, TAG_TRANSPOSE = 36, TAG_MEMSET = 37, NUM_TIMING_TAGS = 38
+};
+}  // namespace facl
+
+namespace facl {
+// train_step.cu
+int gmajor_launch(const float* in, float* out, int B, int G, int N, cudaStream_t st);
+int centres_launch(const float* clouds, int M, int N, int S, float* centres, cudaStream_t st);
+}  // namespace facl

@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(256) fps_reorder_kernel(const float* __restric
 
 template <int T, int PPT>
 static int launch_fps(const float* pts, int V, int N, int D, const int* start, int m, int* out, cudaStream_t st) {
+    ScopedTimer timer(TAG_FPS, st);
+    count_launch();
     fps_kernel<T, PPT><<<V, T, 0, st>>>(pts, N, D, start, m, out);
     return (int)cudaGetLastError();
 }
@@ -136,6 +138,8 @@ int fps_reorder_launch(const float* pts, int V, int N, int D, const int* picks, 
         cudaError_t e = cudaFuncSetAttribute(fps_reorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
+    ScopedTimer timer(TAG_FPS, st);
+    count_launch();
     fps_reorder_kernel<<<V, 256, smem, st>>>(pts, N, D, picks, m, out);
     return (int)cudaGetLastError();
 }

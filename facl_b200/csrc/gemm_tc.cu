@@ -4,6 +4,7 @@
 //   warp  8    MMA issuer (one lane issues tcgen05.mma; owns the TMEM allocation)
 //   warp  9    TMA        (one lane bulk-copies pre-packed weight tiles, cp.async.bulk + mbarrier tx)
 #include "gemm_tc.cuh"
+#include "facl_internal.h"
 #include "umma.cuh"
 
 namespace facl {
@@ -462,6 +463,8 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
     } else {
         grid = numMT * gemm_tc_ctas_per_mtile(p.Md, p.Nd);
     }
+    ScopedTimer timer(p.tag, stream);
+    count_launch();
     gemm_tc_kernel<<<grid, THREADS, smem_bytes, stream>>>(p);
     return (int)cudaGetLastError();
 }

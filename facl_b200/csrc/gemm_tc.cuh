@@ -57,6 +57,7 @@ struct GemmParams {
     float* pool_out;            // [Md][ldp] selected pre-activation value
     unsigned char* pool_arg;    // [Md][ldp] position inside the group (first hit), or null
     long long ldp;
+    int tag;                    // timing tag (profiler.cu), -1 = untimed
 };
 
 // host launcher (gemm_tc.cu); returns cudaError_t as int

@@ -221,6 +221,8 @@ int group_launch(const float* points, int M, int N, int D, int S, int K, float r
         configured = true;
     }
     dim3 grid((S + GW - 1) / GW, M);
+    ScopedTimer timer(TAG_GROUP, st);
+    count_launch();
     if (D == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0)
         group_kernel<true><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);
     else

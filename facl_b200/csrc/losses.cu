@@ -220,6 +220,7 @@ int contrast_losses(const float* x, const float* xg, int G, int B, int C, const 
     const int M = G * B, MB = M + B;
     LossWs w;
     loss_ws_layout(G, B, C, reinterpret_cast<uint8_t*>(workspace), &w);
+    count_launch(2 + 2 * (want_circle ? 2 : 0) + 2 * (want_global ? 1 : 0));   // the small loss kernels below
 
     auto sim = [&](const float* a, int rows, float* out) {   // out[rows][M] = a x^T
         GemmParams g;
@@ -228,6 +229,7 @@ int contrast_losses(const float* x, const float* xg, int G, int B, int C, const 
         g.a_mode = A_ROWMAJOR; g.a.src0 = a; g.a.ld = C;
         g.b_mode = B_ROWMAJOR; g.b.src0 = x; g.b.ld = C;
         g.out_mode = OUT_CHMAJOR; g.out = out; g.ldo = M;
+        g.tag = TAG_LOSS_GEMM;
         return launch_gemm_tc(g, st);
     };
     // out[rows of B-operand][C] (+)= dS-block * features, with the feature matrix as the packed "A" operand
@@ -238,6 +240,7 @@ int contrast_losses(const float* x, const float* xg, int G, int B, int C, const 
         g.a_mode = A_PACKED; g.a_packed = img; g.a_packed_kblocks = (Kd + 63) / 64;
         g.b_mode = b_mode; g.b.src0 = ds; g.b.ld = M;
         g.out_mode = accumulate ? OUT_ROWMAJOR_ACC : OUT_ROWMAJOR; g.out = out; g.ldo = C;
+        g.tag = TAG_LOSS_GEMM;
         return launch_gemm_tc(g, st);
     };
 
@@ -255,13 +258,8 @@ int contrast_losses(const float* x, const float* xg, int G, int B, int C, const 
     FACL_CHECK_LAUNCH();
     // feature matrices as packed A operands: A[m = c][k = row] = feat[row][c]
     RUN(pack_weight_launch(x, 1, C, C, M, w.img_x, st));
-    if (want_circle) {
-        loss_ds_kernel<<<div_up((long long)M * M, 256), 256, 0, st>>>(w.S, M, M, B, G, order, w.inv, 0, M, w.lcG, w.pgG, w.lcC, w.pgC);
-        FACL_CHECK_LAUNCH();
-        // dx[a] = sum_j dS[a][j] x[j]   and   dx[j] += sum_a dS[a][j] x[a]
-        RUN(dgemm(w.img_x, M, B_ROWMAJOR, w.S, M, dx_circle_part, 0));
-        RUN(dgemm(w.img_x, M, B_CHMAJOR, w.S, M, dx_circle_part, 1));
-    }
+    // When both gradients go to the same buffer (dx_circle_part == dx_global_part) the second one accumulates.
+    const bool one_buffer = want_global && want_circle && dx_circle_part == dx_global_part;
     if (want_global) {
         float* Sg = w.S + (size_t)M * M;
         loss_ds_kernel<<<div_up((long long)B * M, 256), 256, 0, st>>>(w.S, M, M, B, G, order, w.inv, M, B, w.lcG, w.pgG, w.lcC, w.pgC);
@@ -270,6 +268,13 @@ int contrast_losses(const float* x, const float* xg, int G, int B, int C, const 
         // dxg[n] = sum_j dS_g[n][j] x[j] ;  dx[j] = sum_n dS_g[n][j] xg[n]
         RUN(dgemm(w.img_x, M, B_ROWMAJOR, Sg, B, dxg, 0));
         RUN(dgemm(w.img_xall, B, B_CHMAJOR, Sg, M, dx_global_part, 0));
+    }
+    if (want_circle) {
+        loss_ds_kernel<<<div_up((long long)M * M, 256), 256, 0, st>>>(w.S, M, M, B, G, order, w.inv, 0, M, w.lcG, w.pgG, w.lcC, w.pgC);
+        FACL_CHECK_LAUNCH();
+        // dx[a] = sum_j dS[a][j] x[j]   and   dx[j] += sum_a dS[a][j] x[a]
+        RUN(dgemm(w.img_x, M, B_ROWMAJOR, w.S, M, dx_circle_part, one_buffer ? 1 : 0));
+        RUN(dgemm(w.img_x, M, B_CHMAJOR, w.S, M, dx_circle_part, 1));
     }
     return 0;
 }

@@ -41,6 +41,8 @@ int pack_weight_launch(const float* src, long long sm, long long sk, int Md, int
     if (Md <= 0 || Kd <= 0) return (int)cudaErrorInvalidValue;
     int numMT = (Md + 127) / 128, KBp = (Kd + 63) / 64;
     long long tasks = (long long)numMT * KBp * 1024;
+    ScopedTimer timer(TAG_PACK, st);
+    count_launch();
     pack_weight_kernel<<<div_up(tasks, 256), 256, 0, st>>>(src, sm, sk, Md, Kd, KBp, tasks, reinterpret_cast<uint8_t*>(image));
     return (int)cudaGetLastError();
 }

@@ -1,0 +1,88 @@
+// One whole training step behind a single C-ABI call: the loop body of reference
+// training_code/cn3d_train_motion_GL.py:224-335 (G-major flatten -> grouping -> encoder -> global + circle loss
+// -> backward -> Adam), optionally fed from a pinned HOST batch and returning the loss to a pinned host float.
+#include "../../include/facl_b200.h"
+#include "common.cuh"
+#include "facl_internal.h"
+
+namespace facl {
+
+namespace {
+// (B,G,N,4) -> (G*B,N,4): cloud g*B+b = view g of sample b (cn3d_train_motion_GL.py:225-226); float4 rows
+__global__ void gmajor_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int G, int N) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * G * N;
+    if (t >= total) return;
+    int n = (int)(t % N);
+    int m = (int)(t / N);
+    int g = m / B, b = m % B;
+    out[t] = in[((long long)b * G + g) * N + n];
+}
+__global__ void centres_kernel(const float* __restrict__ clouds, int M, int N, int S, float* __restrict__ centres) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M * S) return;
+    int m = t / S, s = t % S;
+    const float* p = clouds + ((long long)m * N + s) * 4;
+    centres[t * 3 + 0] = p[0];
+    centres[t * 3 + 1] = p[1];
+    centres[t * 3 + 2] = p[2];
+}
+__global__ void add2_kernel(const float* __restrict__ v, float* __restrict__ out) { out[0] = v[0] + v[1]; }
+}  // namespace
+
+int gmajor_launch(const float* in, float* out, int B, int G, int N, cudaStream_t st) {
+    ScopedTimer timer(TAG_TRANSPOSE, st);
+    count_launch();
+    long long total = (long long)B * G * N;
+    gmajor_kernel<<<div_up(total, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), B, G, N);
+    return (int)cudaGetLastError();
+}
+int centres_launch(const float* clouds, int M, int N, int S, float* centres, cudaStream_t st) {
+    ScopedTimer timer(TAG_POOLMISC, st);
+    count_launch();
+    centres_kernel<<<div_up((long long)M * S, 256), 256, 0, st>>>(clouds, M, N, S, centres);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace facl
+
+using namespace facl;
+
+extern "C" {
+
+int facl_gmajor(const float* points_bgnd, float* clouds, int B, int G, int N, void* stream) {
+    return gmajor_launch(points_bgnd, clouds, B, G, N, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int facl_train_step(const facl_train_step_args* a, void* stream) {
+    if (!a || !a->dims || !a->params || !a->grads || !a->enc_buffers) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const facl_encoder_dims* d = a->dims;
+    const int M = d->M, G = d->G, B = M / G, S = d->S, K = d->K, N = a->N;
+    const float* batch = a->points_bgnd;
+    if (a->points_host) {   // end-to-end path: the batch starts in pinned host memory
+        FACL_CHECK(cudaMemcpyAsync(a->staging, a->points_host, sizeof(float) * 4 * (size_t)M * N, cudaMemcpyHostToDevice, st));
+        batch = a->staging;
+    }
+    if (!batch) return (int)cudaErrorInvalidValue;
+    int rc;
+    if ((rc = gmajor_launch(batch, a->clouds, B, G, N, st))) return rc;
+    if ((rc = group_launch(a->clouds, M, N, 4, S, K, a->r2, a->xt, nullptr, st))) return rc;
+    if ((rc = centres_launch(a->clouds, M, N, S, a->centres, st))) return rc;
+    if ((rc = facl_encoder_forward(d, a->params, a->xt, a->centres, a->enc_buffers, a->x, a->x_global, nullptr, nullptr, stream)))
+        return rc;
+    if ((rc = facl_contrast_losses(a->x, a->x_global, G, B, 512, a->order, 1, 1, d->nsplit, a->loss_ws, a->loss2, a->dx,
+                                   a->dx_global, a->dx, stream)))
+        return rc;
+    if ((rc = facl_encoder_backward(d, a->params, a->xt, a->enc_buffers, a->dx, a->dx_global, a->grads, stream))) return rc;
+    if ((rc = facl_adam_step(a->adam_table, a->adam_ntensors, a->lr, a->beta1, a->beta2, a->eps, a->step, stream))) return rc;
+    {
+        count_launch();
+        add2_kernel<<<1, 1, 0, st>>>(a->loss2, a->loss2 + 2);
+        FACL_CHECK_LAUNCH();
+    }
+    if (a->loss_host) FACL_CHECK(cudaMemcpyAsync(a->loss_host, a->loss2 + 2, sizeof(float), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+}  // extern "C"

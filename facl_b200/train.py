@@ -1,0 +1,196 @@
+"""The training-step call sequence of the reference scripts, on the sm_100a library.
+
+`TrainStep` re-issues the loop body of reference training_code/cn3d_train_motion_GL.py:224-335
+(cn3d_train_apperance_GL.py is the same file up to three constants) through the reference-shaped API of this
+package -- group_points_3DV -> netR(xt, yt) -> global loss -> circle loss -> zero_grad / backward / Adam step --
+with synthetic batches standing in for the NTU DataLoader.
+"""
+import types
+
+import numpy as np
+import torch
+
+from . import cn3d_model_conbag as MODELL
+from . import losses as _losses
+from . import utils_my
+from .optim import Adam
+
+
+def default_opt(batchSize=64, SAMPLE_NUM=2048, sample_num_level1=64, knn_K=64):
+    """The argparse defaults of cn3d_train_motion_GL.py:77-135 that the hot path reads."""
+    return types.SimpleNamespace(batchSize=batchSize, INPUT_FEATURE_NUM=4, temperal_num=3, pooling="concatenation",
+                                 SAMPLE_NUM=SAMPLE_NUM, Num_Class=512, knn_K=knn_K, sample_num_level1=sample_num_level1,
+                                 sample_num_level2=64, ball_radius=0.16, ball_radius2=0.25, learning_rate=0.0003)
+
+
+class TrainStep:
+    """One object = model + optimiser + the per-step call sequence.
+
+    step(out_points, order=None):  out_points is the DataLoader tensor (B, G, N, 4) -- a CUDA tensor, or a (pinned)
+    host tensor that is copied to the device first (cn3d_train_motion_GL.py:228).  Returns the loss as a 0-dim CUDA
+    tensor; nothing synchronises unless the caller reads it."""
+
+    def __init__(self, opt=None, num_crop=10, precision="fp32", radius2=None, device="cuda", seed=1, model=None):
+        self.opt = opt or default_opt()
+        self.num_crop = num_crop
+        self.precision = precision
+        self.radius2 = radius2
+        self.device = torch.device(device)
+        if model is None:
+            torch.manual_seed(seed)                                   # cn3d_train_motion_GL.py:142-144
+            model = MODELL.PointNet_Plus_fine(self.opt, gost=num_crop, sample_num_level1=self.opt.sample_num_level1,
+                                              knn_K=self.opt.knn_K)
+        self.netR = model.to(self.device)
+        self.netR.precision = precision
+        self.netR.train()
+        self.optimizer = Adam(self.netR.parameters(), lr=self.opt.learning_rate, betas=(0.5, 0.999), eps=1e-06)
+        self.base_lr = self.opt.learning_rate
+        self.rng = np.random.RandomState(seed)
+
+    def set_epoch(self, epoch):
+        """StepLR(step_size=4, gamma=0.7) stepped with the epoch number (cn3d_train_motion_GL.py:181,333)."""
+        for g in self.optimizer.param_groups:
+            g["lr"] = self.base_lr * (0.7 ** (epoch // 4))
+
+    def group(self, data1):
+        if self.radius2 is None:
+            return utils_my.group_points_3DV(data1, self.opt)                                   # r2 = 0.06
+        return utils_my._group(data1, self.opt.sample_num_level1, self.opt.knn_K, self.radius2)  # e.g. 0.16 (_2048)
+
+    def step(self, out_points, order=None):
+        B, G, N, D = out_points.shape
+        if not out_points.is_cuda:
+            out_points = out_points.to(self.device, non_blocking=True)
+        # G-major flatten on the device (the reference permutes on the host, :225-226)
+        data1 = out_points.permute(1, 0, 2, 3).reshape(-1, N, D).to(torch.float32)
+        xt, yt = self.group(data1)
+        x, code, x_nor, x_global = self.netR(xt, yt, 1)
+        if order is None:
+            order = np.arange(0, G, 1)
+            self.rng.shuffle(order)                                                              # :297-298
+        loss_c, loss_circle = _losses.contrast_losses(x, x_global, G, B, order=order, prec=self.precision)
+        loss = loss_circle + loss_c                                                              # :329
+        self.optimizer.zero_grad(set_to_none=False)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+
+def extract_features(netR, opt, out_points, radius2=None):
+    """Forward-only feature extraction of extract_motion_feature.py:171-184,217-221: returns the (B, (G+1)*512)
+    array the reference writes per video (num_crop + 1 blocks of 512)."""
+    B, G, N, D = out_points.shape
+    netR.eval()
+    with torch.no_grad():
+        data1 = out_points.to(next(netR.parameters()).device).permute(1, 0, 2, 3).reshape(-1, N, D).to(torch.float32)
+        if radius2 is None:
+            xt, yt = utils_my.group_points_3DV(data1, opt)
+        else:
+            xt, yt = utils_my._group(data1, opt.sample_num_level1, opt.knn_K, radius2)
+        x, _, _, x_global = netR(xt, yt)
+        feat = torch.cat((x, x_global), dim=0)
+    return feat.reshape(G + 1, B, 512).permute(1, 0, 2).reshape(B, (G + 1) * 512)
+
+
+class FusedTrainStep:
+    """The same step as TrainStep.step, issued as ONE C-ABI call (facl_train_step) on persistent buffers: no torch
+    autograd graph, no per-step allocation, gradients written straight into the tensors bound to `p.grad`.
+    `step(batch)` takes the DataLoader-shaped (B, G, N, 4) fp32 batch either as a CUDA tensor or as a PINNED host
+    tensor (then the H2D copy is part of the call) and returns a device tensor [loss_global, loss_circle, loss]."""
+
+    def __init__(self, trainer, B, G, N, r2=0.06):
+        import ctypes as C
+        from . import _lib
+        from .encoder_rt import _dims, _params_struct
+        self.C, self._lib = C, _lib
+        self.tr = trainer
+        net = trainer.netR
+        dev = trainer.device
+        S, K = net.sample_num_level1, net.knn_K
+        M = G * B
+        self.shape = (B, G, N, 4)
+        self.dims = _dims(M, S, K, G, trainer.precision, True)
+        self.ws = net._workspace(self.dims, dev, True)
+        params = net._param_list()
+        self.params_struct = _params_struct([p.detach() for p in params], net._bn_buffers())
+        self.grads = [torch.zeros_like(p) for p in params[:30]]
+        for p, g in zip(params[:30], self.grads):
+            p.grad = g
+        gs = _lib.EncoderGrads()
+        for l in range(7):
+            gs.dw[l], gs.db[l], gs.dgamma[l], gs.dbeta[l] = (t.data_ptr() for t in self.grads[4 * l: 4 * l + 4])
+        gs.dfc3_w, gs.dfc3_b = self.grads[28].data_ptr(), self.grads[29].data_ptr()
+        self.grads_struct = gs
+        opt = trainer.optimizer
+        recs = []
+        import struct
+        for p, g in zip(params[:30], self.grads):
+            st = opt.state[p]
+            if not st:
+                st["exp_avg"] = torch.zeros_like(p)
+                st["exp_avg_sq"] = torch.zeros_like(p)
+            recs.append(struct.pack("<QQQQq", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
+                                    st["exp_avg_sq"].data_ptr(), p.numel()))
+        self.adam_table = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.staging = torch.empty((B, G, N, 4), **f32)
+        self.clouds = torch.empty((M, N, 4), **f32)
+        self.xt = torch.empty((M, S, K, 4), **f32)
+        self.centres = torch.empty((M * S, 3), **f32)
+        self.x = torch.empty((M, 512), **f32)
+        self.xg = torch.empty((B, 512), **f32)
+        self.dx = torch.empty((M, 512), **f32)
+        self.dxg = torch.empty((B, 512), **f32)
+        self.loss2 = torch.zeros(3, **f32)
+        self.loss_ws = torch.empty(_lib.lib().facl_contrast_workspace_bytes(G, B, 512), dtype=torch.uint8, device=dev)
+        self.order_dev = torch.zeros(G, dtype=torch.int32, device=dev)
+        self.order_ring = [torch.zeros(G, dtype=torch.int32).pin_memory() for _ in range(16)]
+        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.r2 = r2
+        self.pending_bn_steps = 0
+        a = _lib.TrainStepArgs()
+        a.dims, a.params, a.grads = C.pointer(self.dims), C.pointer(self.params_struct), C.pointer(self.grads_struct)
+        a.enc_buffers = self.ws.table
+        a.N, a.r2 = N, r2
+        a.staging, a.clouds, a.xt, a.centres = (t.data_ptr() for t in (self.staging, self.clouds, self.xt, self.centres))
+        a.x, a.x_global, a.order, a.loss_ws, a.loss2 = (t.data_ptr() for t in (self.x, self.xg, self.order_dev, self.loss_ws,
+                                                                                 self.loss2))
+        a.dx, a.dx_global = self.dx.data_ptr(), self.dxg.data_ptr()
+        a.adam_table, a.adam_ntensors = self.adam_table.data_ptr(), 30
+        a.beta1, a.beta2, a.eps = 0.5, 0.999, 1e-6
+        self.args = a
+
+    def step(self, batch, order=None, want_host_loss=False):
+        if tuple(batch.shape) != self.shape or batch.dtype != torch.float32:
+            raise self._lib.FaclError(f"batch must be float32 {self.shape}")
+        tr = self.tr
+        G = self.shape[1]
+        if order is None:
+            order = np.arange(0, G, 1)
+            tr.rng.shuffle(order)
+        opt = tr.optimizer
+        opt._step += 1
+        slot = self.order_ring[opt._step % len(self.order_ring)]
+        slot.copy_(torch.from_numpy(np.asarray(order, dtype=np.int32)))
+        self.order_dev.copy_(slot, non_blocking=True)
+        a = self.args
+        if batch.is_cuda:
+            a.points_bgnd, a.points_host = batch.data_ptr(), None
+        else:
+            if not batch.is_pinned():
+                raise self._lib.FaclError("host batches must be pinned (torch.Tensor.pin_memory)")
+            a.points_bgnd, a.points_host = None, batch.data_ptr()
+        a.lr = float(opt.param_groups[0]["lr"])
+        a.step = opt._step
+        a.loss_host = self.loss_host.data_ptr() if want_host_loss else None
+        self._lib.check(self._lib.lib().facl_train_step(self.C.byref(a), self._lib.stream_ptr()), "facl_train_step")
+        self.pending_bn_steps += 1
+        return self.loss2
+
+    def flush_counters(self):
+        """num_batches_tracked is bookkeeping only (momentum is fixed): applied lazily, off the hot path."""
+        if self.pending_bn_steps:
+            with torch.no_grad():
+                for i, (_, bn) in enumerate(self.tr.netR._layers()):
+                    bn.num_batches_tracked += (2 if i == 6 else 1) * self.pending_bn_steps
+            self.pending_bn_steps = 0

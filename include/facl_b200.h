@@ -177,6 +177,52 @@ FACL_API int facl_contrast_losses(const float* x, const float* x_global, int G, 
                                   int want_global, int want_circle, int nsplit, void* workspace, float* loss,
                                   float* dx_global_part, float* dx_global, float* dx_circle_part, void* stream);
 
+/* ---- instrumentation: per-kernel device timing and launch counting (used by bench.py) ---------------------
+ * facl_timing_enable(1): every tagged launch site is bracketed by CUDA events on its stream.
+ * facl_timing_collect: synchronises on the recorded events, returns total ms / launches per tag and resets.
+ * Tags: 3*layer + {0 forward, 1 weight-grad, 2 data-grad} for layer 0..8 (7 = netR_FC.3, 8 = mapping), then
+ * 27 grouping, 28 fps, 29 weight packing, 30 BN finalize, 31 pooling misc, 32 max-pool scatter, 33 loss GEMMs,
+ * 34 loss misc, 35 adam, 36 transposes, 37 memset/fill.  facl_launch_count: kernels launched so far. */
+#define FACL_NUM_TIMING_TAGS 38
+FACL_API void facl_timing_enable(int on);
+FACL_API int facl_timing_collect(float* ms_per_tag, int* count_per_tag, int ntags);
+FACL_API long long facl_launch_count(void);
+
+/* ---- one training step in one call -------------------------------------------------------------------------
+ * replaces the loop body of reference training_code/cn3d_train_motion_GL.py:224-335 (and the identical
+ * cn3d_train_apperance_GL.py): G-major flatten (:225-226) -> H2D (:228) -> group_points_3DV (:230) -> netR (:234)
+ * -> global loss (:265-287) -> circle loss (:290-316) -> backward + Adam step (:329-332) -> loss.item() (:335).
+ * All scratch is caller-owned.  loss2: device float[3] = {global, circle, total}. */
+typedef struct facl_train_step_args {
+    const facl_encoder_dims* dims;
+    const facl_encoder_params* params;
+    const facl_encoder_grads* grads;
+    void* const* enc_buffers;        /* facl_encoder_* work buffers, backward set included */
+    int N;                           /* points per cloud */
+    float r2;                        /* squared ball radius */
+    const float* points_bgnd;        /* device (B,G,N,4) batch, or NULL when points_host is given */
+    const float* points_host;        /* optional PINNED host (B,G,N,4) batch: copied into `staging` first */
+    float* staging;                  /* device (B,G,N,4), used with points_host */
+    float* clouds;                   /* device (G*B,N,4) scratch */
+    float* xt;                       /* device (G*B,S,K,4) scratch */
+    float* centres;                  /* device (G*B*S,3) scratch */
+    float* x;                        /* device (G*B,512) */
+    float* x_global;                 /* device (B,512) */
+    const int* order;                /* device int32[G]: view permutation of the circle loss */
+    void* loss_ws;                   /* facl_contrast_workspace_bytes(G,B,512) */
+    float* loss2;                    /* device float[3] */
+    float* dx;                       /* device (G*B,512) scratch */
+    float* dx_global;                /* device (B,512) scratch */
+    const void* adam_table;          /* see facl_adam_step */
+    int adam_ntensors;
+    float lr, beta1, beta2, eps;
+    int step;                        /* 1-based optimiser step */
+    float* loss_host;                /* optional PINNED host float: receives the total loss (async D2H) */
+} facl_train_step_args;
+
+FACL_API int facl_gmajor(const float* points_bgnd, float* clouds, int B, int G, int N, void* stream);
+FACL_API int facl_train_step(const facl_train_step_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -189,3 +189,64 @@ def test_pointnet_plus_returns_x_only(golden_dir):
     assert isinstance(x, torch.Tensor) and x.shape == (G * B, 512)
     assert rel2(x, z["x64"]) <= 1e-3
     assert sorted(net.module.state_dict().keys()) == sorted(oracle.STATE_KEYS)
+
+
+# ------------------------------------------------------------------------------------------------- whole step
+def test_fused_step_equals_api_step_and_oracle(golden_dir):
+    """facl_train_step (one C-ABI call) == the reference-shaped call sequence through torch autograd == oracle."""
+    from facl_b200.train import FusedTrainStep, TrainStep
+    z, sd0 = load_fixture(golden_dir)
+    B, G, N, S, K = (int(v) for v in z["cfg"])
+    pts = torch.from_numpy(z["points"])
+    order = z["order"]
+
+    def fresh():
+        opt = make_opt(B, N, S, K)
+        opt.learning_rate = 0.0003
+        net = MODELL.PointNet_Plus_fine(opt, gost=G, sample_num_level1=S, knn_K=K)
+        net.load_state_dict({k: v.clone() for k, v in sd0.items()})
+        return TrainStep(opt, num_crop=G, precision="fp32", model=net)
+
+    a = fresh()
+    loss_a = float(a.step(pts.to(DEV), order=order))
+    b = fresh()
+    fb = FusedTrainStep(b, B, G, N, r2=0.06)
+    loss_b = fb.step(pts.pin_memory(), order=order, want_host_loss=True)      # host batch in, loss out
+    torch.cuda.synchronize()
+    fb.flush_counters()
+    assert abs(float(fb.loss_host[0]) - float(loss_b[2])) == 0.0
+    assert abs(float(loss_b[2]) - loss_a) <= 1e-5 * abs(loss_a)
+    assert abs(loss_a - z["loss64"][0]) <= 1e-3 * abs(z["loss64"][0])
+    sa, sb = a.netR.state_dict(), b.netR.state_dict()
+    for k in sa:
+        if sa[k].dtype.is_floating_point:
+            # identical kernels and inputs; only summation order differs (atomics, dx_global + dx_circle).  Adam's first
+            # step moves an entry by lr * g / (|g| + eps), so entries with |g| ~ 0 may move by +-lr in either run
+            if "running_" in k:
+                assert rel2(sb[k], sa[k]) <= 1e-5, k
+            else:
+                assert float((sb[k] - sa[k]).abs().max()) <= 2.1 * 3e-4, k
+        else:
+            assert int(sa[k]) == int(sb[k]), k
+    # weights after the Adam step vs the reference fixture (|delta| <= lr per entry on the first step)
+    for k, v in sb.items():
+        if "sd1_pos/" + k in z.files:
+            got = v.reshape(-1).cpu().numpy()[z["sd1_pos/" + k]]
+            assert np.allclose(got, z["sd1_val/" + k], rtol=0, atol=2.5 * 3e-4), k
+    # a second step must run on the same buffers (persistent state, Adam step count 2)
+    fb.step(pts.to(DEV), order=order)
+    torch.cuda.synchronize()
+    assert np.isfinite(float(fb.loss2[2]))
+
+
+def test_extract_features_layout(golden_dir):
+    from facl_b200.train import extract_features
+    z, sd0 = load_fixture(golden_dir)
+    B, G, N, S, K = (int(v) for v in z["cfg"])
+    sd = {k: v.clone() for k, v in sd0.items()}
+    oracle.train_step(sd, torch.from_numpy(z["points"]), z["order"], S=S, K=K, r2=float(z["r2"]))
+    net, opt = _build(sd, B, G, N, S, K, "fp32")
+    feat = extract_features(net, opt, torch.from_numpy(z["points"]).to(DEV))
+    ref = z["eval_feat"].reshape(G + 1, B, 512).transpose(1, 0, 2).reshape(B, (G + 1) * 512)   # save_single_feature
+    assert feat.shape == (B, (G + 1) * 512)
+    assert rel2(feat, ref) <= 2e-3
