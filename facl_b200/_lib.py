@@ -66,7 +66,8 @@ class TrainStepArgs(C.Structure):
                 ("x_global", C.c_void_p), ("order", C.c_void_p), ("loss_ws", C.c_void_p), ("loss2", C.c_void_p),
                 ("dx", C.c_void_p), ("dx_global", C.c_void_p), ("adam_table", C.c_void_p), ("adam_ntensors", C.c_int),
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int),
-                ("loss_host", C.c_void_p)]
+                ("loss_host", C.c_void_p), ("phases", C.c_int), ("B_global", C.c_int), ("sample_offset", C.c_int),
+                ("keys", C.c_void_p), ("dkeys", C.c_void_p), ("dx_extra", C.c_void_p)]
 
 
 _I, _LL, _P, _F, _SZ = C.c_int, C.c_longlong, C.c_void_p, C.c_float, C.c_size_t
@@ -96,8 +97,8 @@ SIGNATURES = {
     "facl_timing_enable": (None, [_I]),
     "facl_timing_collect": (_I, [_P, _P, _I]),
     "facl_launch_count": (C.c_longlong, []),
-    "facl_contrast_workspace_bytes": (_SZ, [_I, _I, _I]),
-    "facl_contrast_losses": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "facl_contrast_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "facl_contrast_losses": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
 }
 
 

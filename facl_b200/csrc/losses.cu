@@ -26,16 +26,33 @@ namespace facl {
 
 namespace {
 
+// Index conventions (single- and multi-GPU).  The batch of B sequences is sharded over R ranks, Bl = B / R each.
+// Keys (the columns of S) are ALL ranks' view embeddings in rank-major order, which is what an all-gather of the
+// per-rank x (G-major inside a rank) produces:   key j = r*Ml + g*Bl + b   (Ml = G*Bl)  <->  view g of sample
+// n = r*Bl + b.  Anchors (the rows of S) are this rank's Ml view embeddings followed by its Bl sequence embeddings;
+// local anchor row a < Ml is view a / Bl of sample n0 + a % Bl, row Ml + b is sample n0 + b.  With R = 1 this is the
+// reference's own row order (g*B + n).
+struct Idx {
+    int G, B, Bl, Ml, Mk, n0;
+    __host__ __device__ int key_sample(int j) const {
+        int r = j / Ml, rem = j - r * Ml;
+        return r * Bl + (rem % Bl);
+    }
+    __host__ __device__ int key_view(int j) const { return (j % Ml) / Bl; }
+    __host__ __device__ int key_of(int g, int n) const { return (n / Bl) * Ml + g * Bl + (n % Bl); }
+    __host__ __device__ int anchor_sample(int a) const { return n0 + (a < Ml ? a % Bl : a - Ml); }
+};
+
 // one block per anchor row: m = max, e = sum exp(s - m) over the unmasked columns
-__global__ void __launch_bounds__(128) loss_rowstats_kernel(const float* __restrict__ Smat, long long ld, int M, int B, int row0,
-                                                            int nrows, float* __restrict__ rmax, float* __restrict__ rsum) {
+__global__ void __launch_bounds__(128) loss_rowstats_kernel(const float* __restrict__ Smat, Idx ix, int row0, int nrows,
+                                                            float* __restrict__ rmax, float* __restrict__ rsum) {
     int a = row0 + blockIdx.x;
     if (blockIdx.x >= nrows) return;
-    int n = (a < M) ? (a % B) : (a - M);
-    const float* row = Smat + (long long)a * ld;
+    int n = ix.anchor_sample(a);
+    const float* row = Smat + (long long)a * ix.Mk;
     float m = -INFINITY;
-    for (int j = threadIdx.x; j < M; j += 128)
-        if (j % B != n) m = fmaxf(m, row[j]);
+    for (int j = threadIdx.x; j < ix.Mk; j += 128)
+        if (ix.key_sample(j) != n) m = fmaxf(m, row[j]);
     __shared__ float sh[128];
     sh[threadIdx.x] = m;
     __syncthreads();
@@ -47,8 +64,8 @@ __global__ void __launch_bounds__(128) loss_rowstats_kernel(const float* __restr
     __syncthreads();
     float e = 0.f;
     if (m > -INFINITY)
-        for (int j = threadIdx.x; j < M; j += 128)
-            if (j % B != n) e += expf(row[j] - m);
+        for (int j = threadIdx.x; j < ix.Mk; j += 128)
+            if (ix.key_sample(j) != n) e += expf(row[j] - m);
     sh[threadIdx.x] = e;
     __syncthreads();
     for (int o = 64; o > 0; o >>= 1) {
@@ -70,62 +87,66 @@ __device__ __forceinline__ double lse3(double pos, double m, double e, double nz
     return mx + log(s);
 }
 
-// single block; thread per sample n.  Produces loss[0] = global, loss[1] = circle and the softmax coefficients:
-//   lcG[n] = log sum_g exp(-LSE_g,n)      pgG[n*G+g] = (exp(pos - LSE) - 1)/B       (global)
-//   lcC[n] = log sum_i exp(-LSE_i,n)      pgC[n*G+i] = (exp(pos - LSE) - 1)/B       (circle, i < G-1)
-__global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ Smat, long long ld, int M, int B, int G,
-                                                            const int* __restrict__ order, const float* __restrict__ rmax,
-                                                            const float* __restrict__ rsum, int want_global, int want_circle,
-                                                            float* __restrict__ loss, float* __restrict__ lcG, float* __restrict__ pgG,
+// single block; thread per LOCAL sample b.  Produces loss[0] = global, loss[1] = circle (this rank's anchors, already
+// divided by the global B) and the softmax coefficients:
+//   lcG[b] = log sum_g exp(-LSE_g,n)      pgG[b*G+g] = (exp(pos - LSE) - 1)/B       (global)
+//   lcC[b] = log sum_i exp(-LSE_i,n)      pgC[b*G+i] = (exp(pos - LSE) - 1)/B       (circle, i < G-1)
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ Smat, Idx ix, const int* __restrict__ order,
+                                                            const float* __restrict__ rmax, const float* __restrict__ rsum,
+                                                            int want_global, int want_circle, float* __restrict__ loss,
+                                                            float* __restrict__ lcG, float* __restrict__ pgG,
                                                             float* __restrict__ lcC, float* __restrict__ pgC) {
+    const int G = ix.G, B = ix.B;
+    const long long ld = ix.Mk;
     double accG = 0.0, accC = 0.0;
-    for (int n = threadIdx.x; n < B; n += 256) {
+    for (int b = threadIdx.x; b < ix.Bl; b += 256) {
+        const int n = ix.n0 + b;
         if (want_global) {
-            int a = M + n;
+            int a = ix.Ml + b;
             double m = rmax[a], e = rsum[a];
             double minL = 1e300;
             for (int g = 0; g < G; ++g) {
-                double pos = Smat[(long long)a * ld + (long long)g * B + n];
+                double pos = Smat[(long long)a * ld + ix.key_of(g, n)];
                 double L = lse3(pos, m, e, (double)G);
                 accG += L - pos;
-                pgG[n * G + g] = (float)((exp(pos - L) - 1.0) / B);
+                pgG[b * G + g] = (float)((exp(pos - L) - 1.0) / B);
                 minL = fmin(minL, L);
             }
             double s = 0.0;
             for (int g = 0; g < G; ++g) {
-                double pos = Smat[(long long)a * ld + (long long)g * B + n];
+                double pos = Smat[(long long)a * ld + ix.key_of(g, n)];
                 s += exp(minL - lse3(pos, m, e, (double)G));
             }
-            lcG[n] = (float)(-minL + log(s));
+            lcG[b] = (float)(-minL + log(s));
         }
         if (want_circle) {
             double mx = -INFINITY;
             for (int i = 0; i < G - 1; ++i) {
-                int a = order[i] * B + n;
+                int a = order[i] * ix.Bl + b;
                 if (rsum[a] > 0.f) mx = fmax(mx, (double)rmax[a]);
             }
             double e = 0.0;
             for (int i = 0; i < G - 1; ++i) {
-                int a = order[i] * B + n;
+                int a = order[i] * ix.Bl + b;
                 if (rsum[a] > 0.f) e += (double)rsum[a] * exp((double)rmax[a] - mx);
             }
             double nzero = (double)(G - 1) * G;
             double minL = 1e300;
             for (int i = 0; i < G - 1; ++i) {
-                int a = order[i] * B + n;
-                double pos = Smat[(long long)a * ld + (long long)order[i + 1] * B + n];
+                int a = order[i] * ix.Bl + b;
+                double pos = Smat[(long long)a * ld + ix.key_of(order[i + 1], n)];
                 double L = lse3(pos, mx, e, nzero);
                 accC += L - pos;
-                pgC[n * G + i] = (float)((exp(pos - L) - 1.0) / B);
+                pgC[b * G + i] = (float)((exp(pos - L) - 1.0) / B);
                 minL = fmin(minL, L);
             }
             double s = 0.0;
             for (int i = 0; i < G - 1; ++i) {
-                int a = order[i] * B + n;
-                double pos = Smat[(long long)a * ld + (long long)order[i + 1] * B + n];
+                int a = order[i] * ix.Bl + b;
+                double pos = Smat[(long long)a * ld + ix.key_of(order[i + 1], n)];
                 s += exp(minL - lse3(pos, mx, e, nzero));
             }
-            lcC[n] = (G > 1) ? (float)(-minL + log(s)) : -INFINITY;
+            lcC[b] = (G > 1) ? (float)(-minL + log(s)) : -INFINITY;
         }
     }
     __shared__ double sh[2][256];
@@ -146,23 +167,26 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restr
 }
 
 // S -> dL/dS in place (unit upstream gradient for each loss)
-__global__ void loss_ds_kernel(float* __restrict__ Smat, long long ld, int M, int B, int G, const int* __restrict__ order,
-                               const int* __restrict__ inv_order, int row0, int nrows, const float* __restrict__ lcG,
-                               const float* __restrict__ pgG, const float* __restrict__ lcC, const float* __restrict__ pgC) {
+__global__ void loss_ds_kernel(float* __restrict__ Smat, Idx ix, const int* __restrict__ order, const int* __restrict__ inv_order,
+                               int row0, int nrows, const float* __restrict__ lcG, const float* __restrict__ pgG,
+                               const float* __restrict__ lcC, const float* __restrict__ pgC) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)nrows * M) return;
-    int a = row0 + (int)(t / M), j = (int)(t % M);
-    float* s = Smat + (long long)a * ld + j;
+    if (t >= (long long)nrows * ix.Mk) return;
+    const int G = ix.G;
+    int a = row0 + (int)(t / ix.Mk), j = (int)(t % ix.Mk);
+    float* s = Smat + (long long)a * ix.Mk + j;
+    const int n = ix.anchor_sample(a);
+    const bool same = ix.key_sample(j) == n;
     float out;
-    if (a >= M) {
-        int n = a - M;
-        if (j % B == n) out = pgG[n * G + j / B];
-        else out = expf(*s + lcG[n]) / B;
+    if (a >= ix.Ml) {
+        int b = a - ix.Ml;
+        if (same) out = pgG[b * G + ix.key_view(j)];
+        else out = expf(*s + lcG[b]) / ix.B;
     } else {
-        int n = a % B, i = inv_order[a / B];
+        int b = a % ix.Bl, i = inv_order[a / ix.Bl];
         if (i >= G - 1) out = 0.f;                     // the last view in the chain is never an anchor
-        else if (j % B == n) out = (j / B == order[i + 1]) ? pgC[n * G + i] : 0.f;
-        else out = expf(*s + lcC[n]) / B;
+        else if (same) out = (ix.key_view(j) == order[i + 1]) ? pgC[b * G + i] : 0.f;
+        else out = expf(*s + lcC[b]) / ix.B;
     }
     *s = out;
 }
@@ -173,32 +197,32 @@ __global__ void invert_order_kernel(const int* __restrict__ order, int G, int* _
 }
 
 struct LossWs {
-    float *S, *xall, *rmax, *rsum, *lcG, *pgG, *lcC, *pgC;
+    float *S, *rmax, *rsum, *lcG, *pgG, *lcC, *pgC;
     int* inv;
-    uint8_t *img_x, *img_xall;
+    uint8_t *img_keys, *img_x, *img_xg;
 };
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-size_t loss_ws_layout(int G, int B, int C, uint8_t* base, LossWs* w) {
-    size_t M = (size_t)G * B, MB = M + B, off = 0;
+size_t loss_ws_layout(int G, int Bl, int R, int C, uint8_t* base, LossWs* w) {
+    size_t Ml = (size_t)G * Bl, Mk = Ml * R, rows = Ml + Bl, off = 0;
     auto take = [&](size_t bytes) {
         uint8_t* p = base ? base + off : nullptr;
         off += align256(bytes);
         return p;
     };
-    uint8_t* pS = take(MB * M * 4);
-    uint8_t* pX = take(MB * C * 4);
-    uint8_t* p1 = take(MB * 4);
-    uint8_t* p2 = take(MB * 4);
-    uint8_t* p3 = take((size_t)B * 4);
-    uint8_t* p4 = take((size_t)B * G * 4);
-    uint8_t* p5 = take((size_t)B * 4);
-    uint8_t* p6 = take((size_t)B * G * 4);
+    uint8_t* pS = take(rows * Mk * 4);
+    uint8_t* p1 = take(rows * 4);
+    uint8_t* p2 = take(rows * 4);
+    uint8_t* p3 = take((size_t)Bl * 4);
+    uint8_t* p4 = take((size_t)Bl * G * 4);
+    uint8_t* p5 = take((size_t)Bl * 4);
+    uint8_t* p6 = take((size_t)Bl * G * 4);
     uint8_t* p7 = take((size_t)G * 4);
-    uint8_t* p8 = take(packed_weight_bytes(C, (int)M));
-    uint8_t* p9 = take(packed_weight_bytes(C, (int)MB));
+    uint8_t* p8 = take(packed_weight_bytes(C, (int)Mk));
+    uint8_t* p9 = take(packed_weight_bytes(C, (int)Ml));
+    uint8_t* p10 = take(packed_weight_bytes(C, Bl));
     if (w) {
-        w->S = (float*)pS; w->xall = (float*)pX; w->rmax = (float*)p1; w->rsum = (float*)p2; w->lcG = (float*)p3;
-        w->pgG = (float*)p4; w->lcC = (float*)p5; w->pgC = (float*)p6; w->inv = (int*)p7; w->img_x = p8; w->img_xall = p9;
+        w->S = (float*)pS; w->rmax = (float*)p1; w->rsum = (float*)p2; w->lcG = (float*)p3; w->pgG = (float*)p4;
+        w->lcC = (float*)p5; w->pgC = (float*)p6; w->inv = (int*)p7; w->img_keys = p8; w->img_x = p9; w->img_xg = p10;
     }
     return off;
 }
@@ -211,71 +235,84 @@ size_t loss_ws_layout(int G, int B, int C, uint8_t* base, LossWs* w) {
 
 }  // namespace
 
-int contrast_losses(const float* x, const float* xg, int G, int B, int C, const int* order, int want_global, int want_circle,
-                    int nsplit, void* workspace, float* loss, float* dx_global_part, float* dxg, float* dx_circle_part,
-                    cudaStream_t st) {
-    if (G <= 0 || B <= 0 || C <= 0 || (C & 3) || !x || !workspace || !loss) return (int)cudaErrorInvalidValue;
-    if (want_global && (!xg || !dx_global_part || !dxg)) return (int)cudaErrorInvalidValue;
-    if (want_circle && (!order || !dx_circle_part || G < 2)) return (int)cudaErrorInvalidValue;
-    const int M = G * B, MB = M + B;
+// x [G*Bl][C], xg [Bl][C]: this rank's embeddings; keys [R*G*Bl][C]: every rank's x, rank-major (== x when R == 1).
+int contrast_losses(const float* x, const float* xg, const float* keys, int G, int B, int Bl, int n0, int C, const int* order,
+                    int want_global, int want_circle, int nsplit, void* workspace, float* loss, float* dx_anchor, float* dxg,
+                    float* dkeys, cudaStream_t st) {
+    if (G <= 0 || B <= 0 || Bl <= 0 || B % Bl != 0 || n0 < 0 || n0 + Bl > B || C <= 0 || (C & 3)) return (int)cudaErrorInvalidValue;
+    if (!x || !keys || !workspace || !loss || !dx_anchor || !dkeys) return (int)cudaErrorInvalidValue;
+    if (want_global && (!xg || !dxg)) return (int)cudaErrorInvalidValue;
+    if (want_circle && (!order || G < 2)) return (int)cudaErrorInvalidValue;
+    const int R = B / Bl, Ml = G * Bl, Mk = Ml * R;
+    Idx ix{G, B, Bl, Ml, Mk, n0};
     LossWs w;
-    loss_ws_layout(G, B, C, reinterpret_cast<uint8_t*>(workspace), &w);
+    loss_ws_layout(G, Bl, R, C, reinterpret_cast<uint8_t*>(workspace), &w);
     count_launch(2 + 2 * (want_circle ? 2 : 0) + 2 * (want_global ? 1 : 0));   // the small loss kernels below
 
-    auto sim = [&](const float* a, int rows, float* out) {   // out[rows][M] = a x^T
+    auto sim = [&](const float* a, int rows, float* out) {   // out[rows][Mk] = a keys^T
         GemmParams g;
         memset(&g, 0, sizeof(g));
-        g.Md = rows; g.Nd = M; g.Kd = C; g.nsplit = nsplit; g.ksplit = 1;
+        g.Md = rows; g.Nd = Mk; g.Kd = C; g.nsplit = nsplit; g.ksplit = 1;
         g.a_mode = A_ROWMAJOR; g.a.src0 = a; g.a.ld = C;
-        g.b_mode = B_ROWMAJOR; g.b.src0 = x; g.b.ld = C;
-        g.out_mode = OUT_CHMAJOR; g.out = out; g.ldo = M;
+        g.b_mode = B_ROWMAJOR; g.b.src0 = keys; g.b.ld = C;
+        g.out_mode = OUT_CHMAJOR; g.out = out; g.ldo = Mk;
         g.tag = TAG_LOSS_GEMM;
         return launch_gemm_tc(g, st);
     };
-    // out[rows of B-operand][C] (+)= dS-block * features, with the feature matrix as the packed "A" operand
+    // out[Nd rows][C] (+)= dS-block * features, with the feature matrix (transposed) as the packed "A" operand
     auto dgemm = [&](const uint8_t* img, int Kd, int b_mode, const float* ds, int Nd, float* out, int accumulate) {
         GemmParams g;
         memset(&g, 0, sizeof(g));
         g.Md = C; g.Nd = Nd; g.Kd = Kd; g.nsplit = nsplit; g.ksplit = 1;
         g.a_mode = A_PACKED; g.a_packed = img; g.a_packed_kblocks = (Kd + 63) / 64;
-        g.b_mode = b_mode; g.b.src0 = ds; g.b.ld = M;
+        g.b_mode = b_mode; g.b.src0 = ds; g.b.ld = Mk;
         g.out_mode = accumulate ? OUT_ROWMAJOR_ACC : OUT_ROWMAJOR; g.out = out; g.ldo = C;
         g.tag = TAG_LOSS_GEMM;
         return launch_gemm_tc(g, st);
     };
 
+    float* Sx = w.S;
+    float* Sg = w.S + (size_t)Ml * Mk;
     if (want_circle) {
-        RUN(sim(x, M, w.S));
+        RUN(sim(x, Ml, Sx));
         invert_order_kernel<<<1, 256, 0, st>>>(order, G, w.inv);
-        loss_rowstats_kernel<<<M, 128, 0, st>>>(w.S, M, M, B, 0, M, w.rmax, w.rsum);
+        loss_rowstats_kernel<<<Ml, 128, 0, st>>>(w.S, ix, 0, Ml, w.rmax, w.rsum);
     }
     if (want_global) {
-        RUN(sim(xg, B, w.S + (size_t)M * M));
-        loss_rowstats_kernel<<<B, 128, 0, st>>>(w.S, M, M, B, M, B, w.rmax, w.rsum);
+        RUN(sim(xg, Bl, Sg));
+        loss_rowstats_kernel<<<Bl, 128, 0, st>>>(w.S, ix, Ml, Bl, w.rmax, w.rsum);
     }
-    loss_finalize_kernel<<<1, 256, 0, st>>>(w.S, M, M, B, G, order, w.rmax, w.rsum, want_global, want_circle, loss, w.lcG, w.pgG,
-                                            w.lcC, w.pgC);
+    loss_finalize_kernel<<<1, 256, 0, st>>>(w.S, ix, order, w.rmax, w.rsum, want_global, want_circle, loss, w.lcG, w.pgG, w.lcC,
+                                            w.pgC);
     FACL_CHECK_LAUNCH();
     // feature matrices as packed A operands: A[m = c][k = row] = feat[row][c]
-    RUN(pack_weight_launch(x, 1, C, C, M, w.img_x, st));
-    // When both gradients go to the same buffer (dx_circle_part == dx_global_part) the second one accumulates.
-    const bool one_buffer = want_global && want_circle && dx_circle_part == dx_global_part;
+    RUN(pack_weight_launch(keys, 1, C, C, Mk, w.img_keys, st));
+    // dx_anchor and dkeys may be the same buffer (single GPU: keys == x): the later writers accumulate.
+    const bool one_buffer = dx_anchor == dkeys;
+    bool keys_written = false, anchor_written = false;
     if (want_global) {
-        float* Sg = w.S + (size_t)M * M;
-        loss_ds_kernel<<<div_up((long long)B * M, 256), 256, 0, st>>>(w.S, M, M, B, G, order, w.inv, M, B, w.lcG, w.pgG, w.lcC, w.pgC);
+        loss_ds_kernel<<<div_up((long long)Bl * Mk, 256), 256, 0, st>>>(w.S, ix, order, w.inv, Ml, Bl, w.lcG, w.pgG, w.lcC, w.pgC);
         FACL_CHECK_LAUNCH();
-        RUN(pack_weight_launch(xg, 1, C, C, B, w.img_xall, st));
-        // dxg[n] = sum_j dS_g[n][j] x[j] ;  dx[j] = sum_n dS_g[n][j] xg[n]
-        RUN(dgemm(w.img_x, M, B_ROWMAJOR, Sg, B, dxg, 0));
-        RUN(dgemm(w.img_xall, B, B_CHMAJOR, Sg, M, dx_global_part, 0));
+        RUN(pack_weight_launch(xg, 1, C, C, Bl, w.img_xg, st));
+        // dxg[b] = sum_j dS_g[b][j] keys[j] ;  dkeys[j] = sum_b dS_g[b][j] xg[b]
+        RUN(dgemm(w.img_keys, Mk, B_ROWMAJOR, Sg, Bl, dxg, 0));
+        RUN(dgemm(w.img_xg, Bl, B_CHMAJOR, Sg, Mk, dkeys, 0));
+        keys_written = true;
+        if (one_buffer) anchor_written = true;
     }
     if (want_circle) {
-        loss_ds_kernel<<<div_up((long long)M * M, 256), 256, 0, st>>>(w.S, M, M, B, G, order, w.inv, 0, M, w.lcG, w.pgG, w.lcC, w.pgC);
+        loss_ds_kernel<<<div_up((long long)Ml * Mk, 256), 256, 0, st>>>(w.S, ix, order, w.inv, 0, Ml, w.lcG, w.pgG, w.lcC, w.pgC);
         FACL_CHECK_LAUNCH();
-        // dx[a] = sum_j dS[a][j] x[j]   and   dx[j] += sum_a dS[a][j] x[a]
-        RUN(dgemm(w.img_x, M, B_ROWMAJOR, w.S, M, dx_circle_part, one_buffer ? 1 : 0));
-        RUN(dgemm(w.img_x, M, B_CHMAJOR, w.S, M, dx_circle_part, 1));
+        RUN(pack_weight_launch(x, 1, C, C, Ml, w.img_x, st));
+        // dx_anchor[a] = sum_j dS[a][j] keys[j]   and   dkeys[j] += sum_a dS[a][j] x[a]
+        RUN(dgemm(w.img_keys, Mk, B_ROWMAJOR, Sx, Ml, dx_anchor, anchor_written ? 1 : 0));
+        anchor_written = true;
+        if (one_buffer) keys_written = true;
+        RUN(dgemm(w.img_x, Ml, B_CHMAJOR, Sx, Mk, dkeys, keys_written ? 1 : 0));
+        keys_written = true;
     }
+    if (!anchor_written) FACL_CHECK(cudaMemsetAsync(dx_anchor, 0, sizeof(float) * (size_t)Ml * C, st));
+    if (!keys_written) FACL_CHECK(cudaMemsetAsync(dkeys, 0, sizeof(float) * (size_t)Mk * C, st));
     return 0;
 }
 
@@ -283,13 +320,15 @@ int contrast_losses(const float* x, const float* xg, int G, int B, int C, const 
 
 extern "C" {
 
-size_t facl_contrast_workspace_bytes(int G, int B, int C) { return facl::loss_ws_layout(G, B, C, nullptr, nullptr); }
+size_t facl_contrast_workspace_bytes(int G, int B_local, int world, int C) {
+    return facl::loss_ws_layout(G, B_local, world, C, nullptr, nullptr);
+}
 
-int facl_contrast_losses(const float* x, const float* x_global, int G, int B, int C, const int* order, int want_global,
-                         int want_circle, int nsplit, void* workspace, float* loss, float* dx_global_part, float* dx_global,
-                         float* dx_circle_part, void* stream) {
-    return facl::contrast_losses(x, x_global, G, B, C, order, want_global, want_circle, nsplit, workspace, loss, dx_global_part,
-                                 dx_global, dx_circle_part, reinterpret_cast<cudaStream_t>(stream));
+int facl_contrast_losses(const float* x, const float* x_global, const float* keys, int G, int B, int B_local, int sample_offset,
+                         int C, const int* order, int want_global, int want_circle, int nsplit, void* workspace, float* loss,
+                         float* dx_anchor, float* dx_global, float* dkeys, void* stream) {
+    return facl::contrast_losses(x, x_global, keys ? keys : x, G, B, B_local, sample_offset, C, order, want_global, want_circle,
+                                 nsplit, workspace, loss, dx_anchor, dx_global, dkeys, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

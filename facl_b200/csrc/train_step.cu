@@ -28,6 +28,10 @@ __global__ void centres_kernel(const float* __restrict__ clouds, int M, int N, i
     centres[t * 3 + 2] = p[2];
 }
 __global__ void add2_kernel(const float* __restrict__ v, float* __restrict__ out) { out[0] = v[0] + v[1]; }
+__global__ void axpy1_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
 }  // namespace
 
 int gmajor_launch(const float* in, float* out, int B, int G, int N, cudaStream_t st) {
@@ -58,30 +62,47 @@ int facl_train_step(const facl_train_step_args* a, void* stream) {
     if (!a || !a->dims || !a->params || !a->grads || !a->enc_buffers) return (int)cudaErrorInvalidValue;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const facl_encoder_dims* d = a->dims;
-    const int M = d->M, G = d->G, B = M / G, S = d->S, K = d->K, N = a->N;
-    const float* batch = a->points_bgnd;
-    if (a->points_host) {   // end-to-end path: the batch starts in pinned host memory
-        FACL_CHECK(cudaMemcpyAsync(a->staging, a->points_host, sizeof(float) * 4 * (size_t)M * N, cudaMemcpyHostToDevice, st));
-        batch = a->staging;
-    }
-    if (!batch) return (int)cudaErrorInvalidValue;
+    const int M = d->M, G = d->G, Bl = M / G, S = d->S, K = d->K, N = a->N;
+    const int phases = a->phases ? a->phases : FACL_PHASE_ALL;
+    const int Bglob = a->B_global > 0 ? a->B_global : Bl;
     int rc;
-    if ((rc = gmajor_launch(batch, a->clouds, B, G, N, st))) return rc;
-    if ((rc = group_launch(a->clouds, M, N, 4, S, K, a->r2, a->xt, nullptr, st))) return rc;
-    if ((rc = centres_launch(a->clouds, M, N, S, a->centres, st))) return rc;
-    if ((rc = facl_encoder_forward(d, a->params, a->xt, a->centres, a->enc_buffers, a->x, a->x_global, nullptr, nullptr, stream)))
-        return rc;
-    if ((rc = facl_contrast_losses(a->x, a->x_global, G, B, 512, a->order, 1, 1, d->nsplit, a->loss_ws, a->loss2, a->dx,
-                                   a->dx_global, a->dx, stream)))
-        return rc;
-    if ((rc = facl_encoder_backward(d, a->params, a->xt, a->enc_buffers, a->dx, a->dx_global, a->grads, stream))) return rc;
-    if ((rc = facl_adam_step(a->adam_table, a->adam_ntensors, a->lr, a->beta1, a->beta2, a->eps, a->step, stream))) return rc;
-    {
+    if (phases & FACL_PHASE_FORWARD) {
+        const float* batch = a->points_bgnd;
+        if (a->points_host) {   // end-to-end path: the batch starts in pinned host memory
+            FACL_CHECK(cudaMemcpyAsync(a->staging, a->points_host, sizeof(float) * 4 * (size_t)M * N, cudaMemcpyHostToDevice, st));
+            batch = a->staging;
+        }
+        if (!batch) return (int)cudaErrorInvalidValue;
+        if ((rc = gmajor_launch(batch, a->clouds, Bl, G, N, st))) return rc;
+        if ((rc = group_launch(a->clouds, M, N, 4, S, K, a->r2, a->xt, nullptr, st))) return rc;
+        if ((rc = centres_launch(a->clouds, M, N, S, a->centres, st))) return rc;
+        if ((rc = facl_encoder_forward(d, a->params, a->xt, a->centres, a->enc_buffers, a->x, a->x_global, nullptr, nullptr, stream)))
+            return rc;
+    }
+    if (phases & FACL_PHASE_LOSS) {
+        // single GPU: keys == x and both gradient roles are summed into dx; sharded: dkeys is a separate buffer that the
+        // caller sum-reduce-scatters and hands back as dx_extra
+        float* dkeys = a->keys ? a->dkeys : a->dx;
+        if ((rc = facl_contrast_losses(a->x, a->x_global, a->keys, G, Bglob, Bl, a->sample_offset, 512, a->order, 1, 1, d->nsplit,
+                                       a->loss_ws, a->loss2, a->dx, a->dx_global, dkeys, stream)))
+            return rc;
         count_launch();
         add2_kernel<<<1, 1, 0, st>>>(a->loss2, a->loss2 + 2);
         FACL_CHECK_LAUNCH();
     }
-    if (a->loss_host) FACL_CHECK(cudaMemcpyAsync(a->loss_host, a->loss2 + 2, sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (phases & FACL_PHASE_BACKWARD) {
+        if (a->dx_extra) {
+            long long n = (long long)M * 512;
+            count_launch();
+            axpy1_kernel<<<div_up(n, 256), 256, 0, st>>>(a->dx, a->dx_extra, n);
+            FACL_CHECK_LAUNCH();
+        }
+        if ((rc = facl_encoder_backward(d, a->params, a->xt, a->enc_buffers, a->dx, a->dx_global, a->grads, stream))) return rc;
+    }
+    if (phases & FACL_PHASE_UPDATE) {
+        if ((rc = facl_adam_step(a->adam_table, a->adam_ntensors, a->lr, a->beta1, a->beta2, a->eps, a->step, stream))) return rc;
+        if (a->loss_host) FACL_CHECK(cudaMemcpyAsync(a->loss_host, a->loss2 + 2, sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
     return 0;
 }
 

@@ -18,7 +18,7 @@ def _workspace(G, B, Cdim, device):
     ws = _ws_cache.get(key)
     if ws is None:
         _ws_cache.clear()
-        ws = torch.empty(lib().facl_contrast_workspace_bytes(G, B, Cdim), dtype=torch.uint8, device=device)
+        ws = torch.empty(lib().facl_contrast_workspace_bytes(G, B, 1, Cdim), dtype=torch.uint8, device=device)
         _ws_cache[key] = ws
     return ws
 
@@ -33,14 +33,28 @@ class ContrastLossFunction(torch.autograd.Function):
         dev = x.device
         xg = x_global.contiguous() if x_global is not None else None
         loss = torch.empty(2, dtype=torch.float32, device=dev)
-        dxg_part = torch.empty_like(x) if want_global else None
-        dxg = torch.empty((B, Cdim), dtype=torch.float32, device=dev) if want_global else None
-        dxc = torch.empty_like(x) if want_circle else None
+        # the two losses may receive different upstream gradients, so their x-gradients are kept apart: one call each
         ws = _workspace(G, B, Cdim, dev)
         p = lambda t: None if t is None else t.data_ptr()
-        check(lib().facl_contrast_losses(p(x), p(xg), G, B, Cdim, p(order_dev), int(want_global), int(want_circle), nsplit,
-                                         ws.data_ptr(), loss.data_ptr(), p(dxg_part), p(dxg), p(dxc), stream_ptr()),
-              "facl_contrast_losses")
+        dxg_part = dxg = dxc = None
+        if want_global:
+            dxg_part = torch.empty_like(x)
+            dxg = torch.empty((B, Cdim), dtype=torch.float32, device=dev)
+            lg = torch.empty(2, dtype=torch.float32, device=dev)
+            check(lib().facl_contrast_losses(p(x), p(xg), None, G, B, B, 0, Cdim, None, 1, 0, nsplit, ws.data_ptr(),
+                                             lg.data_ptr(), p(dxg_part), p(dxg), p(dxg_part), stream_ptr()),
+                  "facl_contrast_losses")
+            loss[0:1].copy_(lg[0:1])
+        else:
+            loss[0:1].zero_()
+        if want_circle:
+            dxc = torch.empty_like(x)
+            lc = torch.empty(2, dtype=torch.float32, device=dev)
+            check(lib().facl_contrast_losses(p(x), None, None, G, B, B, 0, Cdim, p(order_dev), 0, 1, nsplit, ws.data_ptr(),
+                                             lc.data_ptr(), p(dxc), None, p(dxc), stream_ptr()), "facl_contrast_losses")
+            loss[1:2].copy_(lc[1:2])
+        else:
+            loss[1:2].zero_()
         ctx.grads = (dxg_part, dxg, dxc)
         ctx.has_xg = x_global is not None
         return loss[0], loss[1]

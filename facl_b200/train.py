@@ -113,7 +113,13 @@ class FusedTrainStep:
         self.ws = net._workspace(self.dims, dev, True)
         params = net._param_list()
         self.params_struct = _params_struct([p.detach() for p in params], net._bn_buffers())
-        self.grads = [torch.zeros_like(p) for p in params[:30]]
+        # one flat gradient buffer (+ 4 trailing floats for the loss values): a single all-reduce covers it when sharded
+        sizes = [p.numel() for p in params[:30]]
+        self.flat = torch.zeros(sum(sizes) + 4, dtype=torch.float32, device=dev)
+        self.grads, off = [], 0
+        for p, n in zip(params[:30], sizes):
+            self.grads.append(self.flat[off: off + n].view_as(p))
+            off += n
         for p, g in zip(params[:30], self.grads):
             p.grad = g
         gs = _lib.EncoderGrads()
@@ -142,7 +148,7 @@ class FusedTrainStep:
         self.dx = torch.empty((M, 512), **f32)
         self.dxg = torch.empty((B, 512), **f32)
         self.loss2 = torch.zeros(3, **f32)
-        self.loss_ws = torch.empty(_lib.lib().facl_contrast_workspace_bytes(G, B, 512), dtype=torch.uint8, device=dev)
+        self.loss_ws = torch.empty(_lib.lib().facl_contrast_workspace_bytes(G, B, 1, 512), dtype=torch.uint8, device=dev)
         self.order_dev = torch.zeros(G, dtype=torch.int32, device=dev)
         self.order_ring = [torch.zeros(G, dtype=torch.int32).pin_memory() for _ in range(16)]
         self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()

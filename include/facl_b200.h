@@ -168,25 +168,21 @@ FACL_API int facl_adam_step(const void* table_dev, int ntensors, float lr, float
 /* ---- K6/K7: contrastive losses, forward + gradient -------------------------------------------------------
  * replaces the inline "global" loss (reference training_code/cn3d_train_motion_GL.py:265-287 = utils_my.py:53-83
  * global_contrast) and "circle" loss (:290-316 = utils_my.py:85-116 circle_contrast).
- * x [G*B][C] (G-major rows), x_global [B][C]; order: device int32[G], the view permutation the reference draws
- * with np.random.shuffle (:297-298).  loss[0] = global, loss[1] = circle (0 when not requested).
- * Gradients for unit upstream weight: dx_global_part [G*B][C] and dx_global [B][C] (global loss),
- * dx_circle_part [G*B][C] (circle loss).  C must be a multiple of 4. */
-FACL_API size_t facl_contrast_workspace_bytes(int G, int B, int C);
-FACL_API int facl_contrast_losses(const float* x, const float* x_global, int G, int B, int C, const int* order,
-                                  int want_global, int want_circle, int nsplit, void* workspace, float* loss,
-                                  float* dx_global_part, float* dx_global, float* dx_circle_part, void* stream);
-
-/* ---- instrumentation: per-kernel device timing and launch counting (used by bench.py) ---------------------
- * facl_timing_enable(1): every tagged launch site is bracketed by CUDA events on its stream.
- * facl_timing_collect: synchronises on the recorded events, returns total ms / launches per tag and resets.
- * Tags: 3*layer + {0 forward, 1 weight-grad, 2 data-grad} for layer 0..8 (7 = netR_FC.3, 8 = mapping), then
- * 27 grouping, 28 fps, 29 weight packing, 30 BN finalize, 31 pooling misc, 32 max-pool scatter, 33 loss GEMMs,
- * 34 loss misc, 35 adam, 36 transposes, 37 memset/fill.  facl_launch_count: kernels launched so far. */
-#define FACL_NUM_TIMING_TAGS 38
-FACL_API void facl_timing_enable(int on);
-FACL_API int facl_timing_collect(float* ms_per_tag, int* count_per_tag, int ntags);
-FACL_API long long facl_launch_count(void);
+ *
+ * Single GPU: B_local = B, sample_offset = 0, keys = NULL (= x).  x [G*B][C] (G-major rows), x_global [B][C];
+ * order: device int32[G], the view permutation the reference draws with np.random.shuffle (:297-298).
+ * loss[0] = global, loss[1] = circle (0 when not requested).  Gradients for unit upstream weight:
+ *   dx_anchor [G*B_local][C]  from x as the anchor (row) side,      dx_global [B_local][C],
+ *   dkeys     [world*G*B_local][C]  from x as the key (column) side; may alias dx_anchor when keys == x, the two
+ *   contributions are then summed into it.
+ * Multi GPU (batch of B sequences sharded, B_local per rank, this rank owns samples [sample_offset, +B_local)):
+ * keys = the all-gather of every rank's x, rank-major; losses are this rank's anchors' share (already divided by B);
+ * dkeys must be sum-reduce-scattered back to the ranks and added to dx_anchor.  C must be a multiple of 4. */
+FACL_API size_t facl_contrast_workspace_bytes(int G, int B_local, int world, int C);
+FACL_API int facl_contrast_losses(const float* x, const float* x_global, const float* keys, int G, int B, int B_local,
+                                  int sample_offset, int C, const int* order, int want_global, int want_circle, int nsplit,
+                                  void* workspace, float* loss, float* dx_anchor, float* dx_global, float* dkeys,
+                                  void* stream);
 
 /* ---- one training step in one call -------------------------------------------------------------------------
  * replaces the loop body of reference training_code/cn3d_train_motion_GL.py:224-335 (and the identical
@@ -218,10 +214,34 @@ typedef struct facl_train_step_args {
     float lr, beta1, beta2, eps;
     int step;                        /* 1-based optimiser step */
     float* loss_host;                /* optional PINNED host float: receives the total loss (async D2H) */
+    /* --- sharded (multi-GPU) operation: the step is issued in phases with the collectives in between --- */
+    int phases;                      /* bit mask of FACL_PHASE_*; 0 = all (single GPU) */
+    int B_global;                    /* sequences over all ranks (0 = this rank's batch) */
+    int sample_offset;               /* first global sample index owned by this rank */
+    const float* keys;               /* all-gathered x of every rank, rank-major (NULL = x) */
+    float* dkeys;                    /* (world*G*B_local,512): key-side gradient, to be sum-reduce-scattered */
+    const float* dx_extra;           /* (G*B_local,512): this rank's slice of the reduced dkeys, added to dx */
 } facl_train_step_args;
+
+#define FACL_PHASE_FORWARD 1         /* H2D, G-major flatten, grouping, encoder forward  -> x, x_global */
+#define FACL_PHASE_LOSS 2            /* losses + dL/dx (anchor side), dL/dx_global, dL/dkeys */
+#define FACL_PHASE_BACKWARD 4        /* dx += dx_extra; encoder backward -> parameter gradients */
+#define FACL_PHASE_UPDATE 8          /* Adam step, loss D2H */
+#define FACL_PHASE_ALL 15
 
 FACL_API int facl_gmajor(const float* points_bgnd, float* clouds, int B, int G, int N, void* stream);
 FACL_API int facl_train_step(const facl_train_step_args* args, void* stream);
+
+/* ---- instrumentation: per-kernel device timing and launch counting (used by bench.py) ---------------------
+ * facl_timing_enable(1): every tagged launch site is bracketed by CUDA events on its stream.
+ * facl_timing_collect: synchronises on the recorded events, returns total ms / launches per tag and resets.
+ * Tags: 3*layer + {0 forward, 1 weight-grad, 2 data-grad} for layer 0..8 (7 = netR_FC.3, 8 = mapping), then
+ * 27 grouping, 28 fps, 29 weight packing, 30 BN finalize, 31 pooling misc, 32 max-pool scatter, 33 loss GEMMs,
+ * 34 loss misc, 35 adam, 36 transposes, 37 memset/fill.  facl_launch_count: kernels launched so far. */
+#define FACL_NUM_TIMING_TAGS 38
+FACL_API void facl_timing_enable(int on);
+FACL_API int facl_timing_collect(float* ms_per_tag, int* count_per_tag, int ntags);
+FACL_API long long facl_launch_count(void);
 
 #ifdef __cplusplus
 }

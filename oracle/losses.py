@@ -19,17 +19,22 @@ def _same_sample_mask(B, cols, dtype):
     return ((j % B) != n).to(dtype)
 
 
-def global_contrast(num_crop, x_global, x, batch_size):
-    """sum_g mean_n CE([x_global[n].x[gB+n], (x_global @ x^T)[n,:] * mask], 0)."""
+def global_contrast(num_crop, x_global, x, batch_size, per_sample=False):
+    """sum_g mean_n CE([x_global[n].x[gB+n], (x_global @ x^T)[n,:] * mask], 0).
+    per_sample=True returns the (B,) vector of per-anchor-sample shares (they sum to the loss): the quantity a
+    rank that owns a slice of the batch contributes in the sharded multi-GPU scheme."""
     G, B = num_crop, batch_size
     xv = x.reshape(G, B, -1)
     pos = torch.einsum("nc,gnc->gn", x_global, xv)                    # (G,B)
     neg = (x_global @ x.t()) * _same_sample_mask(B, G * B, x.dtype)    # (B,GB), shared by every g
     logits = torch.cat([pos[:, :, None], neg[None].expand(G, B, G * B)], dim=2)
-    return (torch.logsumexp(logits, dim=2) - pos).mean(dim=1).sum()
+    terms = torch.logsumexp(logits, dim=2) - pos                       # (G,B)
+    if per_sample:
+        return terms.sum(dim=0) / B
+    return terms.mean(dim=1).sum()
 
 
-def circle_contrast(num_crop, x, batch_size, order):
+def circle_contrast(num_crop, x, batch_size, order, per_sample=False):
     """order: permutation of range(G) (the reference draws it with np.random.shuffle, :297-298).
     sum_{i<G-1} mean_n CE([x[o_i B+n].x[o_{i+1} B+n], concat_i' (x[o_i' B+n] @ x^T) * mask], 0)."""
     G, B = num_crop, batch_size
@@ -41,7 +46,10 @@ def circle_contrast(num_crop, x, batch_size, order):
     sims = torch.einsum("inc,kc->nik", anchors, x).reshape(B, (G - 1) * G * B)
     neg = sims * _same_sample_mask(B, (G - 1) * G * B, x.dtype)
     logits = torch.cat([pos[:, :, None], neg[None].expand(G - 1, B, neg.shape[1])], dim=2)
-    return (torch.logsumexp(logits, dim=2) - pos).mean(dim=1).sum()
+    terms = torch.logsumexp(logits, dim=2) - pos                       # (G-1,B)
+    if per_sample:
+        return terms.sum(dim=0) / B
+    return terms.mean(dim=1).sum()
 
 
 def info_nce_logits(x, batch_size):

@@ -250,3 +250,43 @@ def test_extract_features_layout(golden_dir):
     ref = z["eval_feat"].reshape(G + 1, B, 512).transpose(1, 0, 2).reshape(B, (G + 1) * 512)   # save_single_feature
     assert feat.shape == (B, (G + 1) * 512)
     assert rel2(feat, ref) <= 2e-3
+
+
+def test_sharded_losses_sum_to_global(golden_dir):
+    """Two emulated ranks (B=8 sharded 4+4) on one GPU: the per-rank loss shares and gradients of
+    facl_contrast_losses(keys=all-gather) add up to the single-rank result on the same global batch."""
+    import ctypes as C
+    from facl_b200 import _lib
+    from facl_b200.dist import key_index
+    z = np.load(os.path.join(golden_dir, "losses.npz"))
+    G, B, Cd = (int(v) for v in z["cfg_0"])
+    x_ref, xg = torch.from_numpy(z["x_0"]).to(DEV), torch.from_numpy(z["xg_0"]).to(DEV)
+    order = torch.as_tensor(np.asarray(z["order_0"], dtype=np.int32), device=DEV)
+    L = _lib.lib()
+    R, Bl = 2, B // 2
+    Ml, Mk = G * Bl, G * B
+    perm = torch.as_tensor([key_index(g, n, G, Bl) for g in range(G) for n in range(B)], device=DEV)   # ref row -> key row
+    keys = torch.empty_like(x_ref)
+    keys[perm] = x_ref
+    tot_loss = torch.zeros(2, device=DEV)
+    dkeys_sum = torch.zeros_like(keys)
+    dx_anchor_all = torch.zeros_like(keys)
+    dxg_all = torch.zeros_like(xg)
+    for r in range(R):
+        ws = torch.empty(L.facl_contrast_workspace_bytes(G, Bl, R, Cd), dtype=torch.uint8, device=DEV)
+        x_loc = keys[r * Ml:(r + 1) * Ml].contiguous()
+        xg_loc = xg[r * Bl:(r + 1) * Bl].contiguous()
+        loss = torch.zeros(2, device=DEV)
+        dxa, dxgl, dk = torch.empty_like(x_loc), torch.empty_like(xg_loc), torch.empty_like(keys)
+        _lib.check(L.facl_contrast_losses(x_loc.data_ptr(), xg_loc.data_ptr(), keys.data_ptr(), G, B, Bl, r * Bl, Cd,
+                                          order.data_ptr(), 1, 1, 3, ws.data_ptr(), loss.data_ptr(), dxa.data_ptr(),
+                                          dxgl.data_ptr(), dk.data_ptr(), _lib.stream_ptr()))
+        tot_loss += loss
+        dkeys_sum += dk                                    # == reduce-scatter + sum
+        dx_anchor_all[r * Ml:(r + 1) * Ml] = dxa
+        dxg_all[r * Bl:(r + 1) * Bl] = dxgl
+    dx_total = (dx_anchor_all + dkeys_sum)[perm]           # back to the reference row order
+    assert abs(float(tot_loss[0]) - z["loss_0"][0]) <= 1e-4 * z["loss_0"][0]
+    assert abs(float(tot_loss[1]) - z["loss_0"][1]) <= 1e-4 * z["loss_0"][1]
+    assert rel2(dx_total, z["dx_0"]) <= 1e-3
+    assert rel2(dxg_all, z["dxg_0"]) <= 1e-3
