@@ -55,7 +55,10 @@ class EncoderGrads(C.Structure):
 
 class EncoderDims(C.Structure):
     _fields_ = [("M", C.c_int), ("S", C.c_int), ("K", C.c_int), ("G", C.c_int), ("nsplit", C.c_int),
-                ("training", C.c_int)]
+                ("training", C.c_int), ("flags", C.c_int)]
+
+
+ENC_FUSED_L1 = 1
 
 
 class TrainStepArgs(C.Structure):

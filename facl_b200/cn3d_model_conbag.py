@@ -60,6 +60,7 @@ class _EncoderBase(nn.Module):
         )
         self.mapping = nn.Linear(self.dim, self.num_clusters, bias=False)
         self.precision = "fp32"
+        self.fused_l1 = True          # net3DV_1 as the fused kernels of csrc/l1_fused.cu
         self._ws = None
 
     # ---- plumbing -------------------------------------------------------------------------------------------
@@ -80,6 +81,13 @@ class _EncoderBase(nn.Module):
         for _, bn in self._layers():
             out += [bn.running_mean, bn.running_var]
         return out
+
+    def _flags(self, training, need_bwd):
+        from ._lib import ENC_FUSED_L1
+        fused = self.fused_l1 and (not need_bwd or self._fused_backward_ready)
+        return ENC_FUSED_L1 if fused else 0
+
+    _fused_backward_ready = False
 
     def _workspace(self, dims, device, backward):
         key = (dims.M, dims.S, dims.K, dims.G, bool(backward))

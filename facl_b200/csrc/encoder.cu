@@ -73,7 +73,7 @@ size_t buffer_bytes(int i, const facl_encoder_dims* d) {
         case B_ARGG: return 1024 * B;
         case B_BN: return 8 * 7 * 1024 * f;
         case B_VEC: return 2048 * f;
-        case B_STATS: return 65536 * f;
+        case B_STATS: return 131072 * f;
         case B_WPACK: return wpack_offset(9);
         case B_DXT: return 512 * MB * f;
         case B_XTT: return 4 * R1 * f;
@@ -184,6 +184,33 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
                                   L.running_var, BN_EPS, BN_MOM, tr, s.mean, s.rstd, s.scale, s.shift, st);
     };
 
+    if (d->flags & FACL_ENC_FUSED_L1) {
+        // ---- L1 fused: three launches, no per-row activation ever reaches HBM (l1_fused.cu) -------------------------
+        if ((R1 % 128) != 0 || 128 % K != 0) return (int)cudaErrorInvalidValue;
+        double* mom = reinterpret_cast<double*>(vec + 1984);
+        Slot s0 = bn_slot(bufs, 0), s1 = bn_slot(bufs, 1);
+        const facl_layer& L0 = p->layer[0];
+        if (tr) RUN(l1_moments_launch(xt, R1, mom, st));
+        RUN(l1_bn1_launch(mom, (double)R1, L0.w, L0.b, L0.gamma, L0.beta, L0.running_mean, L0.running_var, BN_EPS, BN_MOM, tr,
+                          s0.mean, s0.rstd, s0.scale, s0.shift, st));
+        const int grid = l1_fused_grid(R1);
+        if (tr)
+            RUN(l1_fwd_launch(false, xt, R1, K, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), p->layer[1].b, nullptr,
+                              nullptr, nullptr, nullptr, nullptr, stats, nullptr, 0, st));
+        {
+            const facl_layer& L = p->layer[1];
+            RUN(bn_finalize_launch(stats, 2 * grid, 64, (double)R1, L.gamma, L.beta, L.running_mean, L.running_var, BN_EPS, BN_MOM,
+                                   tr, s1.mean, s1.rstd, s1.scale, s1.shift, st));
+        }
+        RUN(l1_fwd_launch(true, xt, R1, K, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), p->layer[1].b, s1.scale,
+                          s1.shift, wp + wpack_offset(2), p->layer[2].b, p->layer[2].gamma, F(B_STATS), F(B_PCAT) + 3 * R3, R3, st));
+        {
+            Slot s2 = bn_slot(bufs, 2);
+            const facl_layer& L = p->layer[2];
+            RUN(bn_finalize_launch(F(B_STATS), grid, 256, (double)R1, L.gamma, L.beta, L.running_mean, L.running_var, BN_EPS, BN_MOM,
+                                   tr, s2.mean, s2.rstd, s2.scale, s2.shift, st));
+        }
+    } else {
     // ---- L1: 4 -> 64 -> 64 -> 256 over all M*S*K grouped rows, max over the K neighbours -------------------
     {
         GemmParams g = gemm_base(64, (int)R1, 4, layer_nsplit(ns, 0));
@@ -222,6 +249,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
         g.pool_arg = tr ? U(B_ARG3) : nullptr;
         RUN(launch_gemm_tc(g, st));
         RUN(finalize(2, 2, (int)R1, (double)R1));
+    }
     }
     // ---- L3: [centre xyz | pooled 256] -> 256 -> 512 -> 1024 over the M*S centres, max over the S centres ----
     RUN(centres_to_chmajor_launch(centres, (int)R3, F(B_PCAT), R3, st));
@@ -306,6 +334,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
                      const float* dxg, const facl_encoder_grads* gr, cudaStream_t st) {
     RUN(check_dims(d));
     if (!d->training) return (int)cudaErrorInvalidValue;
+    if (d->flags & FACL_ENC_FUSED_L1) return (int)cudaErrorNotSupported;   // fused backward: next
     const int M = d->M, S = d->S, K = d->K, G = d->G, B = M / G, ns = d->nsplit;
     const long long R3 = (long long)M * S, R1 = R3 * K, MB = M + B;
     auto F = [&](int i) { return reinterpret_cast<float*>(bufs[i]); };

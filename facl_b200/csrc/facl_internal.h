@@ -53,7 +53,8 @@ struct ScopedTimer {
 enum TimingTag {
     TAG_GEMM_BASE = 0,
     TAG_GROUP = 27, TAG_FPS = 28, TAG_PACK = 29, TAG_BN = 30, TAG_POOLMISC = 31, TAG_SCATTER = 32, TAG_LOSS_GEMM = 33,
-    TAG_LOSS_MISC = 34, TAG_ADAM = 35, TAG_TRANSPOSE = 36, TAG_MEMSET = 37, NUM_TIMING_TAGS = 38
+    TAG_LOSS_MISC = 34, TAG_ADAM = 35, TAG_TRANSPOSE = 36, TAG_MEMSET = 37, TAG_L1_MISC = 38, TAG_L1_PASS_A = 39,
+    TAG_L1_PASS_B = 40, TAG_L1_PASS_C = 41, TAG_L1_PASS_D = 42, NUM_TIMING_TAGS = 43
 };
 }  // namespace facl
 
@@ -61,4 +62,17 @@ namespace facl {
 // train_step.cu
 int gmajor_launch(const float* in, float* out, int B, int G, int N, cudaStream_t st);
 int centres_launch(const float* clouds, int M, int N, int S, float* centres, cudaStream_t st);
+}  // namespace facl
+
+namespace facl {
+// l1_fused.cu
+int l1_fused_grid(long long R);
+int l1_moments_launch(const float* xt, long long R, double* mom14, cudaStream_t st);
+int l1_bn1_launch(const double* mom14, double n, const float* w1, const float* b1, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float eps, float momentum, int training, float* mean, float* rstd,
+                  float* scale, float* shift, cudaStream_t st);
+int l1_fwd_launch(bool pass_b, const float* xt, long long R, int K, int nsplit, const float* w1, const float* b1, const float* scale1,
+                  const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
+                  const void* w3_img, const float* b3, const float* gamma3, float* stats, float* pooled, long long ldp,
+                  cudaStream_t st);
 }  // namespace facl

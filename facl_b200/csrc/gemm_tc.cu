@@ -170,6 +170,63 @@ __device__ __forceinline__ void produce_chmajor(const OperandSrc& s, uint8_t* hi
     }
 }
 
+// fp32 source stored channel-major [K][ld], staged as an MN-MAJOR operand tile: a task is (k, 8 consecutive rows), i.e.
+// two float4 loads and one 16-byte shared store -- no transposition anywhere.  Transform constants are per K.
+constexpr uint32_t B_MN_LBO = 8192, B_MN_SBO = 1024;   // 64-row blocks 8 KB apart, 8-k groups 1 KB apart (32 KB tile)
+__device__ __forceinline__ void produce_chmajor_mn(const OperandSrc& s, uint8_t* hi, uint8_t* lo, int nhl, int nrows, int n0,
+                                                   int n_limit, int k0, int k_limit, int ptid) {
+    const int chunks = (nrows + 7) >> 3;
+    for (int task = ptid; task < K_BLK * chunks; task += PROD_THREADS) {
+        int kk = task / chunks, c = task - kk * chunks;
+        int k = k0 + kk, n = n0 + c * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (k < k_limit && n < n_limit) {
+            float a[8], b[8];
+            const float* p0 = s.src0 + (long long)k * s.ld + n;
+            bool full = (n + 8 <= n_limit) && ((reinterpret_cast<uintptr_t>(p0) & 15) == 0);
+            if (full) {
+                float4 t0 = __ldg(reinterpret_cast<const float4*>(p0));
+                float4 t1 = __ldg(reinterpret_cast<const float4*>(p0) + 1);
+                a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] = (n + e < n_limit) ? __ldg(p0 + e) : 0.f;
+            }
+            if (s.src1) {
+                const float* p1 = s.src1 + (long long)k * s.ld + n;
+                if (full && ((reinterpret_cast<uintptr_t>(p1) & 15) == 0)) {
+                    float4 t0 = __ldg(reinterpret_cast<const float4*>(p1));
+                    float4 t1 = __ldg(reinterpret_cast<const float4*>(p1) + 1);
+                    b[0] = t0.x; b[1] = t0.y; b[2] = t0.z; b[3] = t0.w; b[4] = t1.x; b[5] = t1.y; b[6] = t1.z; b[7] = t1.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) b[e] = (n + e < n_limit) ? __ldg(p1 + e) : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) b[e] = 0.f;
+            }
+            float c0 = s.s0 ? __ldg(s.s0 + k) : 1.f;
+            float c1 = s.s1 ? __ldg(s.s1 + k) : 0.f;
+            float c2 = s.s2 ? __ldg(s.s2 + k) : 0.f;
+            float cl = s.lo ? __ldg(s.lo + k) : -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (n + e < n_limit) ? xform(a[e], b[e], c0, c1, c2, cl) : 0.f;
+        }
+        uint32_t off = mn_sw128_offset((uint32_t)kk, (uint32_t)c, B_MN_LBO, B_MN_SBO);
+        if (nhl == 2) {
+            uint4 h, l;
+            split_bf16x8(v, h, l);
+            *reinterpret_cast<uint4*>(hi + off) = h;
+            *reinterpret_cast<uint4*>(lo + off) = l;
+        } else {
+            *reinterpret_cast<uint4*>(hi + off) = pack_bf16x8(v);
+        }
+    }
+}
+
 // grouped rows [Nd][4] (x - cx, y - cy, z - cz, feature): K = 4, zero-padded to one 16-wide MMA step.
 __device__ __forceinline__ void produce_xt4(const OperandSrc& s, uint8_t* hi, uint8_t* lo, int nhl, int nrows, int n0, int n_limit,
                                             int ptid) {
@@ -352,6 +409,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p)
                 if (p.b_mode == B_ROWMAJOR)
                     produce_rowmajor(p.b, b_hi, b_lo, nhl, mma_n, w.nt * N_TILE, p.Nd, kb * K_BLK, p.Kd, ptid);
                 else if (p.b_mode == B_CHMAJOR)
+                    produce_chmajor_mn(p.b, b_hi, b_lo, nhl, mma_n, w.nt * N_TILE, p.Nd, kb * K_BLK, p.Kd, ptid);
+                else if (p.b_mode == B_CHMAJOR_GATHER)
                     produce_chmajor(p.b, b_hi, b_lo, nhl, mma_n, w.nt * N_TILE, p.Nd, kb * K_BLK, p.Kd, pw, lane);
                 else
                     produce_xt4(p.b, b_hi, b_lo, nhl, mma_n, w.nt * N_TILE, p.Nd, ptid);
@@ -366,7 +425,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p)
         }
     } else if (warp == 8) {
         // =============================== MMA issuer ===============================
-        const uint32_t idesc = umma_idesc_bf16(M_TILE, mma_n);
+        const bool b_mn = (p.b_mode == B_CHMAJOR);
+        const uint32_t idesc = umma_idesc_bf16(M_TILE, mma_n) | (b_mn ? UMMA_B_MN_MAJOR : 0u);
         int stage = 0, phase = 0;
         for (int it = 0; sched.get(it, p, w); ++it) {
             const int buf = it & 1;
@@ -385,10 +445,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p)
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const uint32_t acc = (kb > w.kb0 || ks > 0) ? 1u : 0u;
                         const uint32_t ko = ks * 32;   // 16 bf16 = 32 bytes inside the 128-byte swizzled row
-                        umma_bf16_ss(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), idesc, acc);
+                        // MN-major B: one k-step = two 8-k groups = 2 * SBO bytes
+                        const uint64_t bd_hi = b_mn ? umma_desc_mn_sw128(b_hi + ks * 2 * B_MN_SBO, B_MN_LBO, B_MN_SBO)
+                                                    : umma_desc_sw128(b_hi + ko);
+                        umma_bf16_ss(d_tmem, umma_desc_sw128(a_hi + ko), bd_hi, idesc, acc);
                         if (nhl == 2) {
-                            umma_bf16_ss(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), idesc, 1u);
-                            umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), idesc, 1u);
+                            const uint64_t bd_lo = b_mn ? umma_desc_mn_sw128(b_lo + ks * 2 * B_MN_SBO, B_MN_LBO, B_MN_SBO)
+                                                        : umma_desc_sw128(b_lo + ko);
+                            umma_bf16_ss(d_tmem, umma_desc_sw128(a_hi + ko), bd_lo, idesc, 1u);
+                            umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ko), bd_hi, idesc, 1u);
                         }
                     }
                     umma_commit(&empty[stage]);

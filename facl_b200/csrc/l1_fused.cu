@@ -1,0 +1,449 @@
+// K3: the first shared-MLP stack (net3DV_1: 4 -> 64 -> 64 -> 256, BN + ReLU after each, max over the K neighbours)
+// as fused tcgen05 kernels that never write a per-row activation to HBM.
+//
+// Replaces nn.Sequential net3DV_1 of reference training_code/cn3d_model_conbag.py:162-177 (= :43-58).
+//
+// Everything is laid out "channel on the TMEM lane / batch row on the TMEM column": accumulators are D[c][r], so an
+// epilogue thread owns ONE channel and sees its rows in registers -- BatchNorm statistics and the neighbourhood
+// max-pool are in-thread reductions, BN+ReLU constants are per-thread scalars, and a thread that has 8 consecutive rows
+// of its channel packs them into one 16-byte shared-memory store.  Activation tiles are therefore images of
+// [channel][64 consecutive rows] (128-byte rows, 128B swizzle), fed to the next tcgen05.mma as an MN-major B operand.
+//
+// Train-mode BatchNorm needs full-batch statistics before it can be applied, so the forward is three launches:
+//   l1_moments : sum x, sum x x^T over all rows  -> BN1 statistics in closed form (z1 is affine in the 4 inputs)
+//   pass A     : x -> h1 -> z2 (tensor core)     -> BN2 statistics
+//   pass B     : x -> h1 -> z2 -> h2 -> z3 (tensor core) -> BN3 statistics + max over K of the pre-BN value
+// (max_k relu(a z_k + b) = relu(a * (a >= 0 ? max z : min z) + b), so pooling can precede BN3.)
+#include "common.cuh"
+#include "facl_internal.h"
+#include "umma.cuh"
+
+namespace facl {
+
+namespace {
+
+constexpr int TILE = 128;                 // batch rows per tile
+constexpr uint32_t ACT_LBO = 8192;        // MN-major activation image: 64-row blocks 8 KB apart,
+constexpr uint32_t ACT_SBO = 1024;        //                            8-channel groups 1 KB apart (16 KB per half)
+constexpr int ACT_BYTES = 16384;
+constexpr int NTHREADS = 17 * 32;
+
+struct L1Params {
+    const float* xt;          // [R][4]
+    long long R;              // rows, multiple of TILE
+    int K;                    // neighbours per group (power of two, divides TILE)
+    int nhl;                  // 1: bf16, 2: bf16 hi+lo (fp32 mode)
+    const float* w1;          // [64][4]
+    const float* b1;          // [64]
+    const float* scale1;      // BN1 scale / shift (slot 0)
+    const float* shift1;
+    const uint8_t* w2_img;    // packed image of W2 (1 m-tile, 1 k-block)
+    const float* b2;
+    const float* scale2;      // BN2 (pass B only)
+    const float* shift2;
+    const uint8_t* w3_img;    // packed image of W3 (2 m-tiles, 1 k-block)
+    const float* b3;
+    const float* gamma3;      // sign decides max vs min
+    float* stats;             // pass A: [2*grid][64][2], pass B: [grid][256][2]
+    float* pooled;            // pass B: [256][ldp]  selected pre-BN value per (channel, group)
+    long long ldp;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// write 8 consecutive rows of one channel into an MN-major activation image (hi / hi+lo)
+__device__ __forceinline__ void store_act8(uint8_t* img, int nhl, int channel, int chunk, const float (&v)[8]) {
+    uint32_t off = mn_sw128_offset((uint32_t)channel, (uint32_t)chunk, ACT_LBO, ACT_SBO);
+    if (nhl == 2) {
+        uint4 h, l;
+        split_bf16x8(v, h, l);
+        *reinterpret_cast<uint4*>(img + off) = h;
+        *reinterpret_cast<uint4*>(img + ACT_BYTES + off) = l;
+    } else {
+        *reinterpret_cast<uint4*>(img + off) = pack_bf16x8(v);
+    }
+}
+
+// D[tmem] (+)= A (K-major weight image, 64-wide K) * B (MN-major activation image), all bf16 hi/lo combinations
+__device__ __forceinline__ void mma_weight_act(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_img, int nhl, uint32_t idesc) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ad = umma_desc_sw128(a_hi + ks * 32);
+        const uint64_t bd = umma_desc_mn_sw128(b_img + ks * 2 * ACT_SBO, ACT_LBO, ACT_SBO);
+        umma_bf16_ss(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        if (nhl == 2) {
+            umma_bf16_ss(d_tmem, ad, umma_desc_mn_sw128(b_img + ACT_BYTES + ks * 2 * ACT_SBO, ACT_LBO, ACT_SBO), idesc, 1u);
+            umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ks * 32), bd, idesc, 1u);
+        }
+    }
+}
+
+template <bool PASS_B>
+__global__ void __launch_bounds__(NTHREADS, 1) l1_fwd_kernel(const L1Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nhl = p.nhl;
+    // ---- shared-memory carve-up (all operand images 1 KB aligned) ----
+    uint8_t* w2s = smem;                                   // hi 8 KB | lo 8 KB (64 valid rows each)
+    uint8_t* w3s = w2s + 16384;                            // [half][hi 16 KB | lo 16 KB]      (pass B)
+    uint8_t* h1s = w3s + (PASS_B ? 65536 : 16384);         // pass A: leave 16 KB readable behind W2 (M=128 reads 128 rows)
+    uint8_t* h2s = h1s + 2 * 2 * ACT_BYTES;                // 2 stages x (hi|lo)
+    uint8_t* xs = h2s + (PASS_B ? 2 * 2 * ACT_BYTES : 0);  // 2 stages x 128 rows x 16 B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * TILE * 16);
+    uint64_t *h1_full = bars, *h1_empty = bars + 2, *d2_full = bars + 4, *d2_empty = bars + 6, *h2_full = bars + 8,
+             *h2_empty = bars + 10, *d3_full = bars + 12, *d3_empty = bars + 14, *w_bar = bars + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long ntiles = p.R / TILE;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&h1_full[i], 4);
+            mbar_init(&h1_empty[i], 1);
+            mbar_init(&d2_full[i], 1);
+            mbar_init(&d2_empty[i], 4);
+            mbar_init(&h2_full[i], 4);
+            mbar_init(&h2_empty[i], 1);
+            mbar_init(&d3_full[i], 1);
+            mbar_init(&d3_empty[i], 4);
+        }
+        mbar_init(w_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 16) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: D2[b] at 128*b (b = 0,1); D3[half] at 256 + 128*half
+    const uint32_t idesc = umma_idesc_bf16(128, TILE) | UMMA_B_MN_MAJOR;
+
+    if (warp == 16) {
+        // ======================= MMA issuer (one lane) =======================
+        if (lane == 0) {
+            // stage the weight images once (bulk TMA)
+            const uint32_t w2_bytes = 8192u * nhl, w3_bytes = PASS_B ? 32768u * nhl : 0u;
+            mbar_arrive_expect_tx(w_bar, w2_bytes + w3_bytes);
+            tma_bulk_g2s(w2s, p.w2_img, 8192, w_bar);
+            if (nhl == 2) tma_bulk_g2s(w2s + 8192, p.w2_img + 16384, 8192, w_bar);
+            if (PASS_B) {
+                for (int h = 0; h < 2; ++h) {
+                    tma_bulk_g2s(w3s + h * 32768, p.w3_img + h * 32768, 16384, w_bar);
+                    if (nhl == 2) tma_bulk_g2s(w3s + h * 32768 + 16384, p.w3_img + h * 32768 + 16384, 16384, w_bar);
+                }
+            }
+            mbar_wait(w_bar, 0);
+            const uint32_t w2_hi = smem_u32(w2s), w2_lo = w2_hi + 8192;
+            auto issue_mma2 = [&](int it) {
+                const int b = it & 1, u = (it >> 1) & 1;
+                mbar_wait(&h1_full[b], u);
+                mbar_wait(&d2_empty[b], u ^ 1);
+                tc_fence_after_sync();
+                mma_weight_act(tmem_base + 128 * b, w2_hi, w2_lo, smem_u32(h1s + b * 2 * ACT_BYTES), nhl, idesc);
+                umma_commit(&h1_empty[b]);
+                umma_commit(&d2_full[b]);
+            };
+            int it = 0;
+            long long t = blockIdx.x;
+            if (t < ntiles) issue_mma2(0);
+            for (; t < ntiles; t += gridDim.x, ++it) {
+                if (t + gridDim.x < ntiles) issue_mma2(it + 1);
+                if (PASS_B) {
+                    const int b = it & 1, u = (it >> 1) & 1;
+                    mbar_wait(&h2_full[b], u);
+                    for (int h = 0; h < 2; ++h) {
+                        mbar_wait(&d3_empty[h], (it & 1) ^ 1);
+                        tc_fence_after_sync();
+                        const uint32_t w3_hi = smem_u32(w3s + h * 32768);
+                        mma_weight_act(tmem_base + 256 + 128 * h, w3_hi, w3_hi + 16384, smem_u32(h2s + b * 2 * ACT_BYTES), nhl, idesc);
+                        umma_commit(&d3_full[h]);
+                    }
+                    umma_commit(&h2_empty[b]);
+                }
+            }
+        }
+    } else if (warp == 10 || warp == 11 || warp == 14 || warp == 15) {
+        // ======================= producers: x -> h1 = relu(bn1(W1 x + b1)), thread = channel =======================
+        const int pw = (warp == 10) ? 0 : (warp == 11) ? 1 : (warp == 14) ? 2 : 3;
+        const int ptid = pw * 32 + lane;          // 0..127
+        const int ch = ptid & 63, half = ptid >> 6;
+        // BN1 folded into the 4-wide layer: h1 = max(wf . x + bf, 0)
+        const float s1 = __ldg(p.scale1 + ch), t1 = __ldg(p.shift1 + ch);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + ch);
+        const float wx = s1 * w.x, wy = s1 * w.y, wz = s1 * w.z, ww = s1 * w.w;
+        const float bf = fmaf(s1, __ldg(p.b1 + ch), t1);
+        int it = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int b = it & 1, u = (it >> 1) & 1;
+            float4* xtile = reinterpret_cast<float4*>(xs + b * TILE * 16);
+            xtile[ptid] = __ldg(reinterpret_cast<const float4*>(p.xt) + t * TILE + ptid);
+            named_bar_sync(1, 128);
+            mbar_wait(&h1_empty[b], u ^ 1);
+            uint8_t* img = h1s + b * 2 * ACT_BYTES;
+#pragma unroll 2
+            for (int q = 0; q < 8; ++q) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float4 x = xtile[half * 64 + q * 8 + e];
+                    v[e] = fmaxf(fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf)))), 0.f);
+                }
+                store_act8(img, nhl, ch, half * 8 + q, v);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h1_full[b]);
+        }
+    } else if (warp == 8 || warp == 9 || warp == 12 || warp == 13) {
+        // ======================= z2 consumers, thread = channel j (lanes 0..63 of D2), two column halves =============
+        const int lg = warp & 1;                  // warps 8,12 -> TMEM lanes 0..31; 9,13 -> 32..63   (warp % 4 == lg)
+        const int colhalf = (warp >= 12) ? 1 : 0;
+        const int j = lg * 32 + lane;
+        const float b2 = __ldg(p.b2 + j);
+        float a2 = 0.f, c2 = 0.f;
+        if (PASS_B) {
+            a2 = __ldg(p.scale2 + j);
+            c2 = fmaf(a2, b2, __ldg(p.shift2 + j));
+        }
+        float s_acc = 0.f, q_acc = 0.f;
+        long long nrows = 0;
+        int it = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int b = it & 1, u = (it >> 1) & 1;
+            mbar_wait(&d2_full[b], u);
+            tc_fence_after_sync();
+            if (PASS_B) mbar_wait(&h2_empty[b], u ^ 1);
+            uint8_t* img = h2s + b * 2 * ACT_BYTES;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 * b + colhalf * 64 + q * 32), v);
+                tmem_ld_wait();
+                if (PASS_B) {
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        float h[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) h[e] = fmaxf(fmaf(a2, v[g8 * 8 + e], c2), 0.f);
+                        store_act8(img, nhl, j, colhalf * 8 + q * 4 + g8, h);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        s_acc += v[i];
+                        q_acc = fmaf(v[i], v[i], q_acc);
+                    }
+                }
+            }
+            nrows += 64;
+            tc_fence_before_sync();
+            if (PASS_B) fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (PASS_B) mbar_arrive(&h2_full[b]);
+                mbar_arrive(&d2_empty[b]);
+            }
+        }
+        if (!PASS_B) {
+            // statistics of z2 = acc + b2 from the sums of acc
+            const float n = (float)nrows;
+            float* st = p.stats + ((long long)(blockIdx.x * 2 + colhalf) * 64 + j) * 2;
+            st[0] = fmaf(n, b2, s_acc);
+            st[1] = q_acc + 2.f * b2 * s_acc + n * b2 * b2;
+        }
+    } else if (warp < 8) {
+        // ======================= z3 consumers (pass B), thread = channel c =======================
+        if (PASS_B) {
+            const int h = warp >> 2, lq = warp & 3;
+            const int c = h * 128 + lq * 32 + lane;
+            const float b3 = __ldg(p.b3 + c);
+            const float sgn = (__ldg(p.gamma3 + c) >= 0.f) ? 1.f : -1.f;
+            const int K = p.K, groups = TILE / K;
+            float s_acc = 0.f, q_acc = 0.f;
+            long long nrows = 0;
+            int it = 0;
+            for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                mbar_wait(&d3_full[h], it & 1);
+                tc_fence_after_sync();
+                float best = -INFINITY;
+#pragma unroll 1
+                for (int q = 0; q < TILE / 32; ++q) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(256 + 128 * h + q * 32), v);
+                    tmem_ld_wait();
+                    if (K >= 32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            s_acc += v[i];
+                            q_acc = fmaf(v[i], v[i], q_acc);
+                            best = fmaxf(best, v[i] * sgn);
+                        }
+                        if (((q + 1) * 32) % K == 0) {
+                            const long long g = t * groups + (q * 32) / K;
+                            p.pooled[(long long)c * p.ldp + g] = fmaf(best, sgn, b3);
+                            best = -INFINITY;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            s_acc += v[i];
+                            q_acc = fmaf(v[i], v[i], q_acc);
+                            best = fmaxf(best, v[i] * sgn);
+                            if (((i + 1) & (K - 1)) == 0) {
+                                const long long g = t * groups + (q * 32 + i) / K;
+                                p.pooled[(long long)c * p.ldp + g] = fmaf(best, sgn, b3);
+                                best = -INFINITY;
+                            }
+                        }
+                    }
+                }
+                nrows += TILE;
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d3_empty[h]);
+            }
+            const float n = (float)nrows;
+            float* st = p.stats + ((long long)blockIdx.x * 256 + c) * 2;
+            st[0] = fmaf(n, b3, s_acc);
+            st[1] = q_acc + 2.f * b3 * s_acc + n * b3 * b3;
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 16) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// sum x (4) and sum x x^T (10 unique) over all rows, in double
+__global__ void __launch_bounds__(256) l1_moments_kernel(const float4* __restrict__ xt, long long R, double* __restrict__ out) {
+    double s[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) s[i] = 0.0;
+    for (long long r = (long long)blockIdx.x * 256 + threadIdx.x; r < R; r += (long long)gridDim.x * 256) {
+        float4 x = __ldg(xt + r);
+        double a = x.x, b = x.y, c = x.z, d = x.w;
+        s[0] += a; s[1] += b; s[2] += c; s[3] += d;
+        s[4] += a * a; s[5] += a * b; s[6] += a * c; s[7] += a * d;
+        s[8] += b * b; s[9] += b * c; s[10] += b * d;
+        s[11] += c * c; s[12] += c * d; s[13] += d * d;
+    }
+    __shared__ double sh[14][8];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+        double v = s[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0) sh[i][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 14) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += sh[threadIdx.x][w];
+        atomicAdd(out + threadIdx.x, v);
+    }
+}
+
+// BN1 in closed form: z1 = W1 x + b1 is affine in x, so mean = w.mx + b, var = w^T Cov(x) w
+__global__ void l1_bn1_kernel(const double* __restrict__ mom, double n, const float* __restrict__ w1, const float* __restrict__ b1,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
+                              float eps, float momentum, int training, float* __restrict__ mean, float* __restrict__ rstd,
+                              float* __restrict__ scale, float* __restrict__ shift) {
+    int c = threadIdx.x;
+    if (c >= 64) return;
+    double mu, var;
+    if (training) {
+        double mx[4], cov[4][4];
+        for (int i = 0; i < 4; ++i) mx[i] = mom[i] / n;
+        const int idx[4][4] = {{4, 5, 6, 7}, {5, 8, 9, 10}, {6, 9, 11, 12}, {7, 10, 12, 13}};
+        for (int i = 0; i < 4; ++i)
+            for (int k = 0; k < 4; ++k) cov[i][k] = mom[idx[i][k]] / n - mx[i] * mx[k];
+        double w[4];
+        for (int i = 0; i < 4; ++i) w[i] = w1[c * 4 + i];
+        mu = b1[c];
+        for (int i = 0; i < 4; ++i) mu += w[i] * mx[i];
+        var = 0.0;
+        for (int i = 0; i < 4; ++i)
+            for (int k = 0; k < 4; ++k) var += w[i] * cov[i][k] * w[k];
+        if (var < 0.0) var = 0.0;
+        double unbiased = (n > 1.0) ? var * n / (n - 1.0) : var;
+        running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mu);
+        running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+    } else {
+        mu = running_mean[c];
+        var = running_var[c];
+    }
+    double r = 1.0 / sqrt(var + (double)eps), g = gamma[c];
+    mean[c] = (float)mu;
+    rstd[c] = (float)r;
+    scale[c] = (float)(g * r);
+    shift[c] = (float)((double)beta[c] - mu * g * r);
+}
+
+size_t l1_smem_bytes(bool pass_b) {
+    size_t b = 16384 + (pass_b ? 65536 : 16384) + 2 * 2 * ACT_BYTES + (pass_b ? 2 * 2 * ACT_BYTES : 0) + 2 * TILE * 16 + 256;
+    return b + 1024;
+}
+
+}  // namespace
+
+int l1_fused_grid(long long R) {
+    long long tiles = R / TILE;
+    return (int)(tiles < kNumSMs ? tiles : kNumSMs);
+}
+
+int l1_moments_launch(const float* xt, long long R, double* mom14, cudaStream_t st) {
+    FACL_CHECK(cudaMemsetAsync(mom14, 0, 14 * sizeof(double), st));
+    ScopedTimer timer(TAG_L1_MISC, st);
+    count_launch();
+    l1_moments_kernel<<<kNumSMs * 4, 256, 0, st>>>(reinterpret_cast<const float4*>(xt), R, mom14);
+    return (int)cudaGetLastError();
+}
+
+int l1_bn1_launch(const double* mom14, double n, const float* w1, const float* b1, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float eps, float momentum, int training, float* mean, float* rstd,
+                  float* scale, float* shift, cudaStream_t st) {
+    ScopedTimer timer(TAG_BN, st);
+    count_launch();
+    l1_bn1_kernel<<<1, 64, 0, st>>>(mom14, n, w1, b1, gamma, beta, running_mean, running_var, eps, momentum, training, mean, rstd,
+                                    scale, shift);
+    return (int)cudaGetLastError();
+}
+
+// pass A: statistics of z2 -> stats [2*grid][64][2];  pass B: pooled [256][ldp] + statistics of z3 -> stats [grid][256][2]
+int l1_fwd_launch(bool pass_b, const float* xt, long long R, int K, int nsplit, const float* w1, const float* b1, const float* scale1,
+                  const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
+                  const void* w3_img, const float* b3, const float* gamma3, float* stats, float* pooled, long long ldp,
+                  cudaStream_t st) {
+    if (R <= 0 || R % TILE != 0 || K <= 0 || (K & (K - 1)) || TILE % K != 0) return (int)cudaErrorInvalidValue;
+    static bool configured = false;
+    if (!configured) {
+        FACL_CHECK(cudaFuncSetAttribute(l1_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_smem_bytes(false)));
+        FACL_CHECK(cudaFuncSetAttribute(l1_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_smem_bytes(true)));
+        configured = true;
+    }
+    L1Params p;
+    p.xt = xt; p.R = R; p.K = K; p.nhl = (nsplit == 3) ? 2 : 1;
+    p.w1 = w1; p.b1 = b1; p.scale1 = scale1; p.shift1 = shift1;
+    p.w2_img = reinterpret_cast<const uint8_t*>(w2_img); p.b2 = b2; p.scale2 = scale2; p.shift2 = shift2;
+    p.w3_img = reinterpret_cast<const uint8_t*>(w3_img); p.b3 = b3; p.gamma3 = gamma3;
+    p.stats = stats; p.pooled = pooled; p.ldp = ldp;
+    const int grid = l1_fused_grid(R);
+    ScopedTimer timer(pass_b ? TAG_L1_PASS_B : TAG_L1_PASS_A, st);
+    count_launch();
+    if (pass_b)
+        l1_fwd_kernel<true><<<grid, NTHREADS, l1_smem_bytes(true), st>>>(p);
+    else
+        l1_fwd_kernel<false><<<grid, NTHREADS, l1_smem_bytes(false), st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace facl

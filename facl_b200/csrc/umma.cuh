@@ -85,6 +85,21 @@ __device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fe
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// Shared-memory descriptor for an MN-major operand with the 128-byte swizzle.  Canonical layout (16-byte units):
+// ((8, n), (8, k)) : ((1, LBO), (8, SBO)) -- a 128-byte row holds 64 consecutive MN elements of ONE k; 8 consecutive
+// k form a 1024-byte swizzle atom (chunk index XOR (k & 7)); the next 8 k are SBO bytes further, the next 64 MN
+// elements LBO bytes further.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// byte offset of the 16-byte chunk holding MN elements [8*chunk, 8*chunk+8) of row k in such a tile
+__device__ __forceinline__ uint32_t mn_sw128_offset(uint32_t k, uint32_t chunk, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (chunk >> 3) * lbo_bytes + (k >> 3) * sbo_bytes + (k & 7u) * 128u + (((chunk & 7u) ^ (k & 7u)) << 4);
+}
+constexpr uint32_t UMMA_B_MN_MAJOR = 1u << 16;   // instruction-descriptor bit: B operand is MN-major
+constexpr uint32_t UMMA_A_MN_MAJOR = 1u << 15;
+
 // Instruction descriptor, kind::f16 with BF16 A/B (both K-major), FP32 accumulate.
 //   [4,6) D fmt = 1 (F32)   [7,10) A fmt = 1 (BF16)   [10,13) B fmt = 1 (BF16)   [15] A major = 0   [16] B major = 0
 //   [17,23) N>>3   [24,29) M>>4

@@ -43,9 +43,9 @@ class EncoderWorkspace:
         return t[: numel * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
 
 
-def _dims(M, S, K, G, precision, training):
+def _dims(M, S, K, G, precision, training, flags=0):
     d = EncoderDims()
-    d.M, d.S, d.K, d.G, d.nsplit, d.training = M, S, K, G, NSPLIT[precision], int(bool(training))
+    d.M, d.S, d.K, d.G, d.nsplit, d.training, d.flags = M, S, K, G, NSPLIT[precision], int(bool(training)), int(flags)
     return d
 
 
@@ -70,7 +70,7 @@ class EncoderFunction(torch.autograd.Function):
         G = owner.gost
         training = owner.training
         need_bwd = owner._need_bwd        # decided by the caller: grad mode is always off inside Function.forward
-        dims = _dims(M, S, K, G, owner.precision, training)
+        dims = _dims(M, S, K, G, owner.precision, training, owner._flags(training, need_bwd))
         ws = owner._workspace(dims, rows.device, need_bwd)
         bufs = owner._bn_buffers()
         ps = _params_struct([p.detach() for p in params], bufs)

@@ -138,7 +138,10 @@ typedef struct facl_encoder_dims {
     int G;          /* views per sequence (the model's `gost`) */
     int nsplit;     /* 1 = bf16 tensor-core operands, 3 = bf16x3 split (fp32-class accuracy) */
     int training;   /* 1: batch statistics + running-stat update; 0: running statistics (extract_*_feature.py) */
+    int flags;      /* FACL_ENC_* */
 } facl_encoder_dims;
+
+#define FACL_ENC_FUSED_L1 1   /* net3DV_1 as the fused tcgen05 kernels (csrc/l1_fused.cu) instead of per-layer GEMMs */
 
 /* Work buffers are owned by the caller: query the count / name / size, allocate each (256-byte aligned device
  * memory) and pass the pointer table.  Buffers flagged "backward only" may be NULL for forward-only use. */
@@ -237,8 +240,9 @@ FACL_API int facl_train_step(const facl_train_step_args* args, void* stream);
  * facl_timing_collect: synchronises on the recorded events, returns total ms / launches per tag and resets.
  * Tags: 3*layer + {0 forward, 1 weight-grad, 2 data-grad} for layer 0..8 (7 = netR_FC.3, 8 = mapping), then
  * 27 grouping, 28 fps, 29 weight packing, 30 BN finalize, 31 pooling misc, 32 max-pool scatter, 33 loss GEMMs,
- * 34 loss misc, 35 adam, 36 transposes, 37 memset/fill.  facl_launch_count: kernels launched so far. */
-#define FACL_NUM_TIMING_TAGS 38
+ * 34 loss misc, 35 adam, 36 transposes, 37 memset/fill, 38 fused-L1 misc, 39..42 fused-L1 passes A, B, C, D.
+ * facl_launch_count: kernels launched so far. */
+#define FACL_NUM_TIMING_TAGS 43
 FACL_API void facl_timing_enable(int on);
 FACL_API int facl_timing_collect(float* ms_per_tag, int* count_per_tag, int ntags);
 FACL_API long long facl_launch_count(void);

@@ -290,3 +290,34 @@ def test_sharded_losses_sum_to_global(golden_dir):
     assert abs(float(tot_loss[1]) - z["loss_0"][1]) <= 1e-4 * z["loss_0"][1]
     assert rel2(dx_total, z["dx_0"]) <= 1e-3
     assert rel2(dxg_all, z["dxg_0"]) <= 1e-3
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_fused_l1_training_forward(golden_dir, prec):
+    """Training-mode forward through the fused net3DV_1 kernels (closed-form BN1 statistics, pass A, pass B): features
+    and running statistics against the fp64 reference fixture, and against the per-layer GEMM schedule."""
+    z, sd0 = load_fixture(golden_dir)
+    B, G, N, S, K = (int(v) for v in z["cfg"])
+    clouds = torch.from_numpy(z["points"]).permute(1, 0, 2, 3).reshape(-1, N, 4).to(DEV)
+    outs = {}
+    for fused in (True, False):
+        net, opt = _build(sd0, B, G, N, S, K, prec)
+        net.fused_l1 = fused
+        net.train()
+        with torch.no_grad():
+            xt, yt = utils_my.group_points_3DV(clouds, opt)
+            x, code, x_nor, xg = net(xt, yt, 1)
+        outs[fused] = (x, xg, {k: v.clone() for k, v in net.state_dict().items()})
+    x, xg, sd = outs[True]
+    ft = TOL_FEAT[prec]
+    assert rel2(x, z["x64"]) <= ft, rel2(x, z["x64"])
+    assert rel2(xg, z["x_global64"]) <= 2 * ft
+    assert rel2(x, outs[False][0]) <= ft
+    sd64 = {k: (v.clone().double() if v.dtype.is_floating_point else v.clone()) for k, v in sd0.items()}
+    oracle.train_step(sd64, torch.from_numpy(z["points"]), z["order"], S=S, K=K, r2=float(z["r2"]), apply_update=False,
+                      dtype=torch.float64)
+    for k, v in sd.items():
+        if "running_" in k:
+            assert rel2(v, sd64[k]) <= max(ft, 1e-3) * 2, (k, rel2(v, sd64[k]))
+        if "num_batches" in k:
+            assert int(v) == int(sd64[k])
