@@ -84,13 +84,12 @@ class _EncoderBase(nn.Module):
 
     def _flags(self, training, need_bwd):
         from ._lib import ENC_FUSED_L1
-        fused = self.fused_l1 and (not need_bwd or self._fused_backward_ready)
-        return ENC_FUSED_L1 if fused else 0
-
-    _fused_backward_ready = False
+        K, S = self.knn_K, self.sample_num_level1
+        ok = (S * K) % 128 == 0 and K in (8, 16, 32, 64)       # tile geometry of the fused kernels
+        return ENC_FUSED_L1 if (self.fused_l1 and ok) else 0
 
     def _workspace(self, dims, device, backward):
-        key = (dims.M, dims.S, dims.K, dims.G, bool(backward))
+        key = (dims.M, dims.S, dims.K, dims.G, bool(backward), dims.flags)
         if self._ws is None or self._ws.key != key or next(iter(self._ws.tensors.values())).device != device:
             self._ws = None          # release the old buffers before allocating the new set
             self._ws = EncoderWorkspace(dims, device, backward)

@@ -60,6 +60,13 @@ size_t wpackt_offset(int idx) {   // idx 1..6 layers, 7 = fc3^T, 8 = end
 
 size_t buffer_bytes(int i, const facl_encoder_dims* d) {
     const size_t M = d->M, R3 = (size_t)d->M * d->S, R1 = R3 * d->K, B = d->M / d->G, MB = M + B, f = sizeof(float);
+    if (d->flags & FACL_ENC_FUSED_L1) {   // no per-row activation is stored: only dh2 (pass C -> pass D) and small scratch
+        switch (i) {
+            case B_Z1: case B_Z2: case B_Z3: case B_ARG3: case B_DY3: case B_XTT: return 256;
+            case B_DH1: return (size_t)4 * kNumSMs * 64 * 4 * f;
+            default: break;
+        }
+    }
     switch (i) {
         case B_Z1: case B_Z2: case B_DH2: case B_DH1: return 64 * R1 * f;
         case B_Z3: case B_DY3: return 256 * R1 * f;
@@ -334,7 +341,6 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
                      const float* dxg, const facl_encoder_grads* gr, cudaStream_t st) {
     RUN(check_dims(d));
     if (!d->training) return (int)cudaErrorInvalidValue;
-    if (d->flags & FACL_ENC_FUSED_L1) return (int)cudaErrorNotSupported;   // fused backward: next
     const int M = d->M, S = d->S, K = d->K, G = d->G, B = M / G, ns = d->nsplit;
     const long long R3 = (long long)M * S, R1 = R3 * K, MB = M + B;
     auto F = [&](int i) { return reinterpret_cast<float*>(bufs[i]); };
@@ -439,6 +445,23 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
         RUN(wgrad(3, 256, 259, (int)R3, dz, src1(F(B_PCAT), R3, vec, vec + 320, vec + 640), gr->dw[3]));
         RUN(dgrad(3, 256, (int)R3, 256, wt + wpackt_offset(3), dz, F(B_PCAT) + 3 * R3, R3, s2.scale, s2.shift, F(B_DP3), R3, true));
         RUN(bwd_finalize(2, 2, 256, (int)R3, (double)R1, gemm_tc_ctas_per_mtile(256, (int)R3), 0));
+    }
+    if (d->flags & FACL_ENC_FUSED_L1) {
+        // ---- L1 fused backward: activations recomputed from the 16-byte input rows (l1_fused.cu) ------------------------
+        if ((R1 % 128) != 0 || 64 % K != 0) return (int)cudaErrorInvalidValue;
+        const uint8_t* wp = reinterpret_cast<const uint8_t*>(bufs[B_WPACK]);   // forward images of this step's weights
+        const double* mom = reinterpret_cast<const double*>(vec + 1984);
+        const facl_layer &L0 = p->layer[0], &L1 = p->layer[1], &L2 = p->layer[2];
+        const int P = 2 * l1_bwd_grid(R1);
+        RUN(l1_bwd_c_launch(xt, R1, K, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), L1.b, s1.scale, s1.shift,
+                            wp + wpack_offset(2), L2.b, L2.gamma, F(B_PCAT) + 3 * R3, F(B_DP3), R3, s2.c0, s2.c1, s2.c2, F(B_DH2),
+                            gr->dw[2], stats, st));
+        RUN(bwd_finalize(1, 1, 64, (int)R1, (double)R1, P, 0));
+        RUN(l1_bwd_d_launch(xt, R1, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), L1.b, s1.c0, s1.c1, s1.c2, F(B_DH2),
+                            gr->dw[1], F(B_DH1), stats, st));
+        RUN(bwd_finalize(0, 0, 64, (int)R1, (double)R1, P, 0));
+        RUN(l1_dw1_launch(F(B_DH1), P, mom, L0.w, L0.b, s0.c0, s0.c1, s0.c2, gr->dw[0], st));
+        return 0;
     }
     // ---- L1 ---------------------------------------------------------------------------------------------------
     {

@@ -67,6 +67,18 @@ int centres_launch(const float* clouds, int M, int N, int S, float* centres, cud
 namespace facl {
 // l1_fused.cu
 int l1_fused_grid(long long R);
+int l1_bwd_grid(long long R);
+void l1_set_debug_dump(unsigned char* mask1, unsigned char* mask2, unsigned char* arg);
+int l1_bwd_c_launch(const float* xt, long long R, int K, int nsplit, const float* w1, const float* b1, const float* scale1,
+                    const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
+                    const void* w3_img, const float* b3, const float* gamma3, const float* pooled, const float* dpooled,
+                    long long ldp, const float* c3_0, const float* c3_1, const float* c3_2, float* dh2, float* dw3, float* stats,
+                    cudaStream_t st);
+int l1_bwd_d_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1,
+                    const float* shift1, const void* w2_img, const float* b2, const float* c2_0, const float* c2_1,
+                    const float* c2_2, const float* dh2, float* dw2, float* amat, float* stats, cudaStream_t st);
+int l1_dw1_launch(const float* amat, int P, const double* mom14, const float* w1, const float* b1, const float* c0, const float* c1,
+                  const float* c2, float* dw1, cudaStream_t st);
 int l1_moments_launch(const float* xt, long long R, double* mom14, cudaStream_t st);
 int l1_bn1_launch(const double* mom14, double n, const float* w1, const float* b1, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, float eps, float momentum, int training, float* mean, float* rstd,

@@ -6,18 +6,60 @@ _CONVS = ["net3DV_1.0", "net3DV_1.3", "net3DV_1.6", "net3DV_3.0", "net3DV_3.3", 
 _COUT = [64, 64, 256, 256, 512, 1024]
 
 
-def routing_of_last_forward(net):
-    """-> dict understood by oracle.encoder_forward(routing=...); CPU tensors."""
+class L1DecisionDump:
+    """Context manager: asks the fused net3DV_1 backward to record its discrete decisions (see facl_debug_l1_dump)."""
+
+    def __init__(self, M, S, K, device="cuda"):
+        R1, R3 = M * S * K, M * S
+        self.shape = (M, S, K)
+        self.mask1 = torch.zeros(R1 * 64, dtype=torch.uint8, device=device)
+        self.mask2 = torch.zeros(R1 * 64, dtype=torch.uint8, device=device)
+        self.arg = torch.full((256, R3), 255, dtype=torch.uint8, device=device)
+
+    def __enter__(self):
+        from ._lib import lib
+        lib().facl_debug_l1_dump(self.mask1.data_ptr(), self.mask2.data_ptr(), self.arg.data_ptr())
+        return self
+
+    def __exit__(self, *exc):
+        from ._lib import lib
+        torch.cuda.synchronize()
+        lib().facl_debug_l1_dump(None, None, None)
+
+    def masks(self):
+        M, S, K = self.shape
+        R1 = M * S * K
+        m1 = self.mask1.view(R1 // 64, 64, 64).permute(0, 2, 1).reshape(R1, 64).bool().cpu()     # (row, channel)
+        m2 = self.mask2.view(R1 // 64, 64, 64).permute(0, 2, 1).reshape(R1, 64).bool().cpu()
+        return m1, m2, self.arg.t().long().cpu()                                              # arg: (M*S, 256)
+
+
+def routing_of_last_forward(net, l1_dump=None):
+    """-> dict understood by oracle.encoder_forward(routing=...); CPU tensors.  With the fused net3DV_1 kernels no
+    per-row activation exists in memory: pass the L1DecisionDump that was active during the backward."""
     ws = net._ws
-    M, S, K, G, _ = ws.key
+    M, S, K, G = ws.key[:4]
     B = M // G
     R3, R1, MB = M * S, M * S * K, M + B
     bn = ws.view("bn", (8, 7, 1024))
     vec = ws.view("vec", (2048,))
-    out = dict(k=ws.view("arg3", (256, R3), torch.uint8).t().long().cpu(),
-               s=ws.view("arg6", (1024, MB), torch.uint8)[:, :M].t().long().cpu(),
+    out = dict(s=ws.view("arg6", (1024, MB), torch.uint8)[:, :M].t().long().cpu(),
                g=ws.view("argg", (1024, B), torch.uint8).t().long().cpu())
+    if l1_dump is None:
+        out["k"] = ws.view("arg3", (256, R3), torch.uint8).t().long().cpu()
+    fused = l1_dump is not None
+    if fused:
+        m1, m2, arg = l1_dump.masks()
+        assert int((arg == 255).sum()) == 0, "a max-pool winner was not found by the recomputing backward"
+        out["k"] = arg
+        out["relu:net3DV_1.0"], out["relu:net3DV_1.3"] = m1, m2
+        # ReLU3 only matters on the winner rows: impose the pooled activation's sign on the whole group
+        pooled = ws.view("pcat", (259, R3))[3:]
+        act = ((pooled * vec[3:259][:, None] + vec[323:579][:, None]) > 0).t().cpu()            # (M*S, 256)
+        out["relu:net3DV_1.6"] = act[:, None, :].expand(R3, K, 256).reshape(R1, 256)
     for l, (conv, C) in enumerate(zip(_CONVS, _COUT)):
+        if fused and l < 3:
+            continue
         R = R1 if l < 3 else R3
         z = ws.view(f"z{l + 1}", (C, R))
         if l == 2:

@@ -19,7 +19,7 @@ class EncoderWorkspace:
 
     def __init__(self, dims, device, backward):
         L = lib()
-        self.key = (dims.M, dims.S, dims.K, dims.G, bool(backward))
+        self.key = (dims.M, dims.S, dims.K, dims.G, bool(backward), dims.flags)
         n = L.facl_encoder_num_buffers()
         self.tensors = {}
         self.table = (C.c_void_p * n)()

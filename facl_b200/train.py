@@ -109,7 +109,7 @@ class FusedTrainStep:
         S, K = net.sample_num_level1, net.knn_K
         M = G * B
         self.shape = (B, G, N, 4)
-        self.dims = _dims(M, S, K, G, trainer.precision, True)
+        self.dims = _dims(M, S, K, G, trainer.precision, True, net._flags(True, True))
         self.ws = net._workspace(self.dims, dev, True)
         params = net._param_list()
         self.params_struct = _params_struct([p.detach() for p in params], net._bn_buffers())

@@ -100,6 +100,7 @@ def test_train_step_vs_golden_and_oracle(golden_dir, prec):
     B, G, N, S, K = (int(v) for v in z["cfg"])
     tol = TOL[prec]
     net, opt = _build(sd0, B, G, N, S, K, prec)
+    net.fused_l1 = False          # per-layer schedule: keeps every pre-BN activation, so all discrete decisions can be read back
     net.train()
     pts = torch.from_numpy(z["points"])
     clouds = pts.permute(1, 0, 2, 3).reshape(-1, N, 4).type(torch.FloatTensor).to(DEV)
@@ -321,3 +322,40 @@ def test_fused_l1_training_forward(golden_dir, prec):
             assert rel2(v, sd64[k]) <= max(ft, 1e-3) * 2, (k, rel2(v, sd64[k]))
         if "num_batches" in k:
             assert int(v) == int(sd64[k])
+
+
+def test_fused_l1_backward(golden_dir):
+    """Gradients of the fused net3DV_1 path (activations recomputed in the backward, dW1 in closed form) against the
+    fp64 oracle under the SAME discrete decisions: the recomputing backward records its ReLU patterns and max-pool
+    winners through the facl_debug_l1_dump test hook."""
+    from facl_b200.debug import L1DecisionDump, routing_of_last_forward
+    z, sd0 = load_fixture(golden_dir)
+    B, G, N, S, K = (int(v) for v in z["cfg"])
+    pts = torch.from_numpy(z["points"])
+    clouds = pts.permute(1, 0, 2, 3).reshape(-1, N, 4).to(DEV)
+    net, opt = _build(sd0, B, G, N, S, K, "fp32")
+    assert net.fused_l1
+    net.train()
+    xt, yt = utils_my.group_points_3DV(clouds, opt)
+    x, code, x_nor, xg = net(xt, yt, 1)
+    lg, lc = facl_losses.contrast_losses(x, xg, G, B, order=z["order"], prec="fp32")
+    with L1DecisionDump(G * B, S, K) as dump:
+        (lg + lc).backward()
+    routing = routing_of_last_forward(net, l1_dump=dump)
+    sdr = {k: (v.clone().double() if v.dtype.is_floating_point else v.clone()) for k, v in sd0.items()}
+    ort = oracle.train_step(sdr, pts, z["order"], S=S, K=K, r2=float(z["r2"]), apply_update=False, dtype=torch.float64,
+                            routing=routing)
+    assert rel2(x, ort["x"]) <= 1e-3 and abs(float(lg + lc) - ort["loss"]) <= 1e-3 * abs(ort["loss"])
+    gscale = max(float(g.abs().max()) for g in ort["grads"].values())
+    report = []
+    for k, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        ref = ort["grads"][k].reshape(p.shape)
+        if float(ref.norm()) <= 1e-9 * gscale * ref.numel() ** 0.5:
+            assert float(p.grad.abs().max()) <= 1e-4 * gscale, k
+            continue
+        report.append((k, rel2(p.grad, ref)))
+    print("\n" + "\n".join(f"{k:24s} fused, matched decisions: err {a:.2e}" for k, a in report))
+    for k, a in report:
+        assert a <= TOL_GRAD["fp32"], (k, a)
