@@ -448,7 +448,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
     }
     if (d->flags & FACL_ENC_FUSED_L1) {
         // ---- L1 fused backward: activations recomputed from the 16-byte input rows (l1_fused.cu) ------------------------
-        if ((R1 % 128) != 0 || 64 % K != 0) return (int)cudaErrorInvalidValue;
+        if ((R1 % 128) != 0 || (K != 32 && K != 64)) return (int)cudaErrorInvalidValue;
         const uint8_t* wp = reinterpret_cast<const uint8_t*>(bufs[B_WPACK]);   // forward images of this step's weights
         const double* mom = reinterpret_cast<const double*>(vec + 1984);
         const facl_layer &L0 = p->layer[0], &L1 = p->layer[1], &L2 = p->layer[2];

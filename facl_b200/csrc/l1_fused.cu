@@ -425,12 +425,17 @@ __device__ __forceinline__ void produce_h1_tile64(const float4* xtile, uint8_t* 
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-// pass C
-// warps 0-7 : z3 consumers (thread = channel c)        warps 8,9,12,13 : z2 consumers / dh2 consumers (thread = channel j)
-// warps 10,11,14,15 : producers                         warp 16 : MMA issuer
+// pass C   (22 warps)
+// warps 0-7         : z3 consumers (thread = channel c)
+// warps 8,9,12,13   : z2 -> h2 image            warps 16,17,20,21 : dh2 consumers      (thread = channel j, TMEM lanes 0..63)
+// warps 10,11,14,15 : x -> h1 image producers   warp 18 : MMA issuer (warp 19 idles)
 // TMEM columns: D2[b] 0/64, D3[h] 128/192, DH2 256, DW3[h] 320/384
+// The MMA issue order is software-pipelined -- z3(it+1) is issued before the gradient GEMMs of tile it -- so the z3
+// consumers (the longest role) always have the next accumulator waiting.
 // --------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdParams p) {
+constexpr int C_THREADS = 22 * 32;
+
+__global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nhl = p.nhl;
@@ -448,13 +453,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = p.R / BT;
+    const int my_tiles = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA (grid <= ntiles)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&h1_full[i], 4);
             mbar_init(&h1_empty[i], 1);
             mbar_init(&d2_full[i], 1);
-            mbar_init(&d2_empty[i], 4);
+            mbar_init(&d2_empty[i], 8);        // h2 producers + dh2 consumers both read z2
             mbar_init(&h2_full[i], 4);
             mbar_init(&h2_empty[i], 1);
             mbar_init(&d3_full[i], 1);
@@ -468,7 +474,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
         mbar_init(fin_bar, 1);
         mbar_fence_init();
     }
-    if (warp == 16) {
+    if (warp == 18) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
@@ -480,7 +486,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
     const uint32_t idesc_dg = umma_idesc_bf16(128, BT) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;    // W3^T x dz3
     const uint32_t idesc_kk = umma_idesc_bf16(128, 64);                                        // reduction over rows
 
-    if (warp == 16) {
+    if (warp == 18) {
         if (lane == 0) {
             mbar_arrive_expect_tx(w_bar, 8192u * nhl + 32768u * nhl);
             tma_bulk_g2s(w2s, p.w2_img, 8192, w_bar);
@@ -492,7 +498,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
             mbar_wait(w_bar, 0);
             const uint32_t w2_hi = smem_u32(w2s), w2_lo = w2_hi + 8192;
             const uint32_t dz_hi = smem_u32(dzs), dz_lo = dz_hi + 32768;
-            auto issue_mma2 = [&](int it) {
+            auto issue_mma2 = [&](int it) {        // z2(it) = W2 h1(it)
                 const int b = it & 1, u = (it >> 1) & 1;
                 mbar_wait(&h1_full[b], u);
                 mbar_wait(&d2_empty[b], u ^ 1);
@@ -502,15 +508,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
                 umma_commit(&h1_empty[b]);
                 umma_commit(&d2_full[b]);
             };
-            int it = 0;
-            long long t = blockIdx.x;
-            if (t < ntiles) issue_mma2(0);
-            for (; t < ntiles; t += gridDim.x, ++it) {
+            auto issue_mma3 = [&](int it) {        // z3(it) = W3 h2(it)
                 const int b = it & 1, u = (it >> 1) & 1;
-                if (t + gridDim.x < ntiles) issue_mma2(it + 1);
-                // z3 = W3 h2
                 mbar_wait(&h2_full[b], u);
                 const uint32_t h2 = smem_u32(h2s + b * 2 * IMG64);
+#pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     mbar_wait(&d3_empty[h], (it & 1) ^ 1);
                     tc_fence_after_sync();
@@ -518,10 +520,21 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
                     mma_w_act64(tmem_base + 128 + 64 * h, w3_hi, w3_hi + 16384, h2, h2 + IMG64, nhl, idesc_mn);
                     umma_commit(&d3_full[h]);
                 }
-                // dh2 = W3^T dz3 (reduction over the 256 channels) and dW3 += dz3 h2^T (reduction over the 64 rows)
+            };
+            if (my_tiles > 0) issue_mma2(0);
+            if (my_tiles > 1) issue_mma2(1);
+            if (my_tiles > 0) issue_mma3(0);
+#pragma unroll 1
+            for (int it = 0; it < my_tiles; ++it) {
+                const int b = it & 1;
+                if (it + 2 < my_tiles) issue_mma2(it + 2);
+                if (it + 1 < my_tiles) issue_mma3(it + 1);
+                // dh2(it) = W3^T dz3(it) (reduction over the 256 channels); dW3 += dz3(it) h2(it)^T (reduction over the rows)
+                const uint32_t h2 = smem_u32(h2s + b * 2 * IMG64);
                 mbar_wait(dz_full, it & 1);
                 mbar_wait(dh_empty, (it & 1) ^ 1);
                 tc_fence_after_sync();
+#pragma unroll 1
                 for (int ks = 0; ks < 16; ++ks) {
                     const uint32_t wa = smem_u32(w3s + (ks >> 3) * 32768) + (ks & 7) * 2048;
                     const uint64_t a_hi = umma_desc_mn_sw128(wa, 16384, 1024), a_lo = umma_desc_mn_sw128(wa + 16384, 16384, 1024);
@@ -533,6 +546,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
                     }
                 }
                 umma_commit(dh_full);
+#pragma unroll 1
                 for (int h = 0; h < 2; ++h)
                     mma_rows64(tmem_base + 320 + 64 * h, dz_hi + h * 16384, dz_lo + h * 16384, h2, h2 + IMG64, nhl, idesc_kk, it == 0);
                 umma_commit(dz_empty);
@@ -548,6 +562,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
         const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + ch);
         const float wx = s1 * w.x, wy = s1 * w.y, wz = s1 * w.z, ww = s1 * w.w, bf = fmaf(s1, __ldg(p.b1 + ch), t1);
         int it = 0;
+#pragma unroll 1
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
             float4* xtile = reinterpret_cast<float4*>(xs + b * BT * 16);
@@ -567,13 +582,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
             }
         }
     } else if (warp == 8 || warp == 9 || warp == 12 || warp == 13) {
-        // ---- channel-j consumers: (1) z2 -> h2 image, (2) dh2 -> mask, statistics, HBM ----
+        // ---- z2 -> h2 = relu(bn2(z2)) image (thread = channel j) ----
         const int lg = warp & 1, colhalf = (warp >= 12) ? 1 : 0;
         const int j = lg * 32 + lane;
-        const float b2 = __ldg(p.b2 + j), a2 = __ldg(p.scale2 + j);
-        const float c2 = fmaf(a2, b2, __ldg(p.shift2 + j));
-        float s_acc = 0.f, q_acc = 0.f;
+        const float a2 = __ldg(p.scale2 + j);
+        const float c2 = fmaf(a2, __ldg(p.b2 + j), __ldg(p.shift2 + j));
         int it = 0;
+#pragma unroll 1
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
             mbar_wait(&d2_full[b], u);
@@ -596,7 +611,26 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&h2_full[b]);
-            // dh2
+        }
+    } else if (warp == 16 || warp == 17 || warp == 20 || warp == 21) {
+        // ---- dh2 consumers (thread = channel j): ReLU2 mask, BN2 backward sums, masked gradient -> HBM ----
+        const int lg = warp & 1, colhalf = (warp >= 20) ? 1 : 0;
+        const int j = lg * 32 + lane;
+        const float b2 = __ldg(p.b2 + j), a2 = __ldg(p.scale2 + j);
+        const float c2 = fmaf(a2, b2, __ldg(p.shift2 + j));
+        float s_acc = 0.f, q_acc = 0.f;
+        int it = 0;
+#pragma unroll 1
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int b = it & 1, u = (it >> 1) & 1;
+            mbar_wait(&d2_full[b], u);
+            tc_fence_after_sync();
+            float z[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(64 * b + colhalf * 32), z);
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d2_empty[b]);
             mbar_wait(dh_full, it & 1);
             tc_fence_after_sync();
             float g[32];
@@ -622,7 +656,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
         float* st = p.stats + ((long long)(blockIdx.x * 2 + colhalf) * 64 + j) * 2;
         st[0] = s_acc;
         st[1] = q_acc;
-    } else {
+    } else if (warp < 8) {
         // ---- z3 consumers (thread = channel c): locate the pool winner, build dz3, finally flush dW3 ----
         const int h = warp >> 2, lq = warp & 3;
         const int c = h * 128 + lq * 32 + lane;
@@ -630,41 +664,54 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
         const float sgn = (__ldg(p.gamma3 + c) >= 0.f) ? 1.f : -1.f;
         const float k0 = __ldg(p.c3_0 + c), k1 = __ldg(p.c3_1 + c);
         const float k2 = fmaf(k1, b3, __ldg(p.c3_2 + c));
-        const int K = p.K, groups = BT / K;
+        const int K = p.K;                         // 32 or 64: a 32-column chunk never straddles two groups
+        const int groups = BT / K;
         int it = 0;
+#pragma unroll 1
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            // the pooled value / its gradient of this tile's group(s): issue the loads before waiting for the accumulator
+            const long long g0 = (long long)c * p.ldp + t * groups;
+            const float pool0 = __ldg(p.pooled + g0), dp0 = k0 * __ldg(p.dpooled + g0);
+            float pool1 = pool0, dp1 = dp0;
+            if (groups == 2) {
+                pool1 = __ldg(p.pooled + g0 + 1);
+                dp1 = k0 * __ldg(p.dpooled + g0 + 1);
+            }
             mbar_wait(&d3_full[h], it & 1);
             tc_fence_after_sync();
-            float v[64];
-            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(128 + 64 * h), *reinterpret_cast<float(*)[32]>(&v[0]));
-            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(128 + 64 * h + 32), *reinterpret_cast<float(*)[32]>(&v[32]));
-            tmem_ld_wait();
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d3_empty[h]);
-            // dz3 = k1*z + k2 everywhere, + k0*dP at the first row whose value equals the pooled one
-            float pool = 0.f, dpv = 0.f;
-            bool found = true;
-#pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                if ((i & (K - 1)) == 0) {
-                    const long long g = t * groups + i / K;
-                    pool = __ldg(p.pooled + (long long)c * p.ldp + g);
-                    dpv = k0 * __ldg(p.dpooled + (long long)c * p.ldp + g);
-                    found = false;
+            bool found = false;
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(128 + 64 * h + q * 32), v);
+                tmem_ld_wait();
+                if (q == 1) {                      // both halves are in registers / consumed: release the accumulator
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d3_empty[h]);
                 }
-                const bool hit = !found && (fmaf(v[i] * sgn, sgn, b3) == pool);
-                found = found || hit;
-                if (hit && p.dbg_arg) p.dbg_arg[(long long)c * p.ldp + t * groups + i / K] = (unsigned char)(i & (K - 1));
-                v[i] = fmaf(k1, v[i], k2) + (hit ? dpv : 0.f);
-            }
-            mbar_wait(dz_empty, (it & 1) ^ 1);
+                const float pool = (q == 1 && groups == 2) ? pool1 : pool0;
+                const float dpv = (q == 1 && groups == 2) ? dp1 : dp0;
+                if (q == 1 && groups == 2) found = false;
+                int hit_at = -1;
+                // dz3 = k1*z + k2 everywhere, + k0*dP at the first row whose value equals the pooled one
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float w8[8];
+                for (int i = 0; i < 32; ++i) {
+                    const bool hit = !found && (fmaf(v[i] * sgn, sgn, b3) == pool);
+                    found = found || hit;
+                    hit_at = hit ? i : hit_at;
+                    v[i] = fmaf(k1, v[i], k2) + (hit ? dpv : 0.f);
+                }
+                if (p.dbg_arg && hit_at >= 0)
+                    p.dbg_arg[(long long)c * p.ldp + t * groups + (q * 32) / K] = (unsigned char)((q * 32 + hit_at) & (K - 1));
+                if (q == 0) mbar_wait(dz_empty, (it & 1) ^ 1);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) w8[e] = v[q * 8 + e];
-                store_img8(dzs, nhl, 32768, c, q, w8);
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    float w8[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) w8[e] = v[g8 * 8 + e];
+                    store_img8(dzs, nhl, 32768, c, q * 4 + g8, w8);
+                }
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -678,15 +725,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_c_kernel(const L1BwdPar
             float a[32];
             tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(320 + 64 * h + q * 32), a);
             tmem_ld_wait();
-            if (blockIdx.x < ntiles) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) atomicAdd(p.dw3 + c * 64 + q * 32 + i, a[i]);
-            }
+            for (int i = 0; i < 32; ++i) atomicAdd(p.dw3 + c * 64 + q * 32 + i, a[i]);
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 16) {
+    if (warp == 18) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 512);
     }
@@ -1072,7 +1117,7 @@ int l1_bwd_c_launch(const float* xt, long long R, int K, int nsplit, const float
                     const void* w3_img, const float* b3, const float* gamma3, const float* pooled, const float* dpooled,
                     long long ldp, const float* c3_0, const float* c3_1, const float* c3_2, float* dh2, float* dw3, float* stats,
                     cudaStream_t st) {
-    if (R <= 0 || R % BT != 0 || K <= 0 || (K & (K - 1)) || BT % K != 0) return (int)cudaErrorInvalidValue;
+    if (R <= 0 || R % BT != 0 || (K != 32 && K != 64)) return (int)cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
         FACL_CHECK(cudaFuncSetAttribute(l1_bwd_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_bwd_c_smem()));
@@ -1087,7 +1132,7 @@ int l1_bwd_c_launch(const float* xt, long long R, int K, int nsplit, const float
     p.dbg_mask1 = g_dbg_mask1; p.dbg_mask2 = g_dbg_mask2; p.dbg_arg = g_dbg_arg;
     ScopedTimer timer(TAG_L1_PASS_C, st);
     count_launch();
-    l1_bwd_c_kernel<<<l1_bwd_grid(R), BWD_THREADS, l1_bwd_c_smem(), st>>>(p);
+    l1_bwd_c_kernel<<<l1_bwd_grid(R), C_THREADS, l1_bwd_c_smem(), st>>>(p);
     return (int)cudaGetLastError();
 }
 
