@@ -1,8 +1,8 @@
 // Generic tcgen05 GEMM (see gemm_tc.cuh).  Warp-specialised, persistent over output tiles:
 //   warps 0-3  epilogue   (TMEM lanes 32w..32w+31 -> one output channel per thread)
-//   warps 4-7  producers  (fp32 global -> transform -> bf16 hi/lo -> swizzled K-major smem tiles)
-//   warp  8    MMA issuer (one lane issues tcgen05.mma; owns the TMEM allocation)
-//   warp  9    TMA        (one lane bulk-copies pre-packed weight tiles, cp.async.bulk + mbarrier tx)
+//   warps 4-9  producers  (fp32 global -> transform -> bf16 hi/lo -> swizzled smem tiles; loads batched 4 tasks deep)
+//   warp  10   MMA issuer (one lane issues tcgen05.mma; owns the TMEM allocation)
+//   warp  11   TMA        (one lane bulk-copies pre-packed weight tiles, cp.async.bulk + mbarrier tx)
 #include "gemm_tc.cuh"
 #include "facl_internal.h"
 #include "umma.cuh"
@@ -16,9 +16,9 @@ constexpr int N_TILE = 256;
 constexpr int K_BLK = 64;
 constexpr int A_TILE_BYTES = M_TILE * 128;
 constexpr int B_TILE_BYTES = N_TILE * 128;
-constexpr int NUM_PROD_WARPS = 4;
+constexpr int NUM_PROD_WARPS = 6;
 constexpr int PROD_THREADS = NUM_PROD_WARPS * 32;
-constexpr int THREADS = 320;
+constexpr int THREADS = 384;           // 4 epilogue + 6 producer + MMA + TMA warps
 constexpr int NUM_SMS = 148;
 
 struct Work {
@@ -81,91 +81,78 @@ __device__ __forceinline__ void store_chunk(uint8_t* hi, uint8_t* lo, int nhl, u
     }
 }
 
+// One producer task = 8 consecutive source floats (two 16-byte loads per source) -> one 16-byte chunk of an operand tile.
+// Loads of PBATCH tasks are issued back to back before any of them is consumed, so a thread keeps PBATCH * (2..4)
+// independent 16-byte requests in flight instead of paying the memory latency once per task.
+constexpr int PBATCH = 2;
+
+struct TaskData {
+    float a[8], b[8];
+    float c0, c1, c2, cl;
+    int nvalid;       // valid leading elements (0 = whole chunk is zero)
+};
+
+__device__ __forceinline__ void load_task(const OperandSrc& s, long long off, int nvalid, int ch, TaskData& t) {
+    t.nvalid = nvalid;
+    if (nvalid <= 0) return;
+    const float* p0 = s.src0 + off;
+    const bool vec = (nvalid == 8) && ((reinterpret_cast<uintptr_t>(p0) & 15) == 0);
+    if (vec) {
+        float4 t0 = __ldg(reinterpret_cast<const float4*>(p0));
+        float4 t1 = __ldg(reinterpret_cast<const float4*>(p0) + 1);
+        t.a[0] = t0.x; t.a[1] = t0.y; t.a[2] = t0.z; t.a[3] = t0.w; t.a[4] = t1.x; t.a[5] = t1.y; t.a[6] = t1.z; t.a[7] = t1.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t.a[e] = (e < nvalid) ? __ldg(p0 + e) : 0.f;
+    }
+    if (s.src1) {
+        const float* p1 = s.src1 + off;
+        if (vec && ((reinterpret_cast<uintptr_t>(p1) & 15) == 0)) {
+            float4 t0 = __ldg(reinterpret_cast<const float4*>(p1));
+            float4 t1 = __ldg(reinterpret_cast<const float4*>(p1) + 1);
+            t.b[0] = t0.x; t.b[1] = t0.y; t.b[2] = t0.z; t.b[3] = t0.w; t.b[4] = t1.x; t.b[5] = t1.y; t.b[6] = t1.z; t.b[7] = t1.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t.b[e] = (e < nvalid) ? __ldg(p1 + e) : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t.b[e] = 0.f;
+    }
+    t.c0 = s.s0 ? __ldg(s.s0 + ch) : 1.f;
+    t.c1 = s.s1 ? __ldg(s.s1 + ch) : 0.f;
+    t.c2 = s.s2 ? __ldg(s.s2 + ch) : 0.f;
+    t.cl = s.lo ? __ldg(s.lo + ch) : -INFINITY;
+}
+
+__device__ __forceinline__ void finish_task(const TaskData& t, float (&v)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (e < t.nvalid) ? xform(t.a[e], t.b[e], t.c0, t.c1, t.c2, t.cl) : 0.f;
+}
+
 // fp32 source with K contiguous: rows of the tile are rows of the source; transform constants are per ROW.
 __device__ __forceinline__ void produce_rowmajor(const OperandSrc& s, uint8_t* hi, uint8_t* lo, int nhl, int nrows, int row0,
                                                  int row_limit, int k0, int k_limit, int ptid) {
-    for (int task = ptid; task < nrows * 8; task += PROD_THREADS) {
-        int r = task >> 3, j = task & 7;
-        int grow = row0 + r;
-        int k = k0 + j * 8;
-        float v[8];
+    const int ntasks = nrows * 8;
+    for (int base = ptid; base < ntasks; base += PROD_THREADS * PBATCH) {
+        TaskData td[PBATCH];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        if (grow < row_limit && k < k_limit) {
-            float a[8], b[8];
-            const float* p0 = s.src0 + (long long)grow * s.ld + k;
-            bool full = (k + 8 <= k_limit) && ((reinterpret_cast<uintptr_t>(p0) & 15) == 0);
-            if (full) {
-                float4 t0 = __ldg(reinterpret_cast<const float4*>(p0));
-                float4 t1 = __ldg(reinterpret_cast<const float4*>(p0) + 1);
-                a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] = (k + e < k_limit) ? __ldg(p0 + e) : 0.f;
-            }
-            if (s.src1) {
-                const float* p1 = s.src1 + (long long)grow * s.ld + k;
-                if (full && ((reinterpret_cast<uintptr_t>(p1) & 15) == 0)) {
-                    float4 t0 = __ldg(reinterpret_cast<const float4*>(p1));
-                    float4 t1 = __ldg(reinterpret_cast<const float4*>(p1) + 1);
-                    b[0] = t0.x; b[1] = t0.y; b[2] = t0.z; b[3] = t0.w; b[4] = t1.x; b[5] = t1.y; b[6] = t1.z; b[7] = t1.w;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) b[e] = (k + e < k_limit) ? __ldg(p1 + e) : 0.f;
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) b[e] = 0.f;
-            }
-            float c0 = s.s0 ? __ldg(s.s0 + grow) : 1.f;
-            float c1 = s.s1 ? __ldg(s.s1 + grow) : 0.f;
-            float c2 = s.s2 ? __ldg(s.s2 + grow) : 0.f;
-            float cl = s.lo ? __ldg(s.lo + grow) : -INFINITY;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (k + e < k_limit) ? xform(a[e], b[e], c0, c1, c2, cl) : 0.f;
+        for (int u = 0; u < PBATCH; ++u) {
+            const int task = base + u * PROD_THREADS;
+            const int r = task >> 3, j = task & 7;
+            const int grow = row0 + r, k = k0 + j * 8;
+            int nv = (task < ntasks && grow < row_limit) ? (k_limit - k) : 0;
+            nv = nv > 8 ? 8 : nv;
+            load_task(s, (long long)grow * s.ld + k, nv, grow, td[u]);
         }
-        store_chunk(hi, lo, nhl, r, j, v);
-    }
-}
-
-// fp32 source stored channel-major [K][ld]: thread = tile row (coalesced along rows), transform constants are per K.
-__device__ __forceinline__ void produce_chmajor(const OperandSrc& s, uint8_t* hi, uint8_t* lo, int nhl, int nrows, int n0,
-                                                int n_limit, int k0, int k_limit, int pw, int lane) {
-#pragma unroll 1
-    for (int jj = 0; jj < 8 / NUM_PROD_WARPS; ++jj) {
-        int j = pw * (8 / NUM_PROD_WARPS) + jj;
-        int kb = k0 + j * 8;
-        float c0[8], c1[8], c2[8], cl[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            bool kv = kb + e < k_limit;
-            c0[e] = (kv && s.s0) ? __ldg(s.s0 + kb + e) : 1.f;
-            c1[e] = (kv && s.s1) ? __ldg(s.s1 + kb + e) : 0.f;
-            c2[e] = (kv && s.s2) ? __ldg(s.s2 + kb + e) : 0.f;
-            cl[e] = (kv && s.lo) ? __ldg(s.lo + kb + e) : -INFINITY;
-        }
-        for (int g = 0; g < (nrows + 31) / 32; ++g) {
-            int r = g * 32 + lane;
-            int n = n0 + r;
-            float v[8];
-            if (n < n_limit) {
-                float a[8], b[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] = (kb + e < k_limit) ? __ldg(s.src0 + (long long)(kb + e) * s.ld + n) : 0.f;
-                if (s.src1) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) b[e] = (kb + e < k_limit) ? __ldg(s.src1 + (long long)(kb + e) * s.ld + n) : 0.f;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) b[e] = 0.f;
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = (kb + e < k_limit) ? xform(a[e], b[e], c0[e], c1[e], c2[e], cl[e]) : 0.f;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        for (int u = 0; u < PBATCH; ++u) {
+            const int task = base + u * PROD_THREADS;
+            if (task < ntasks) {
+                float v[8];
+                finish_task(td[u], v);
+                store_chunk(hi, lo, nhl, task >> 3, task & 7, v);
             }
-            if (r < N_TILE) store_chunk(hi, lo, nhl, r, j, v);
         }
     }
 }
@@ -176,53 +163,35 @@ constexpr uint32_t B_MN_LBO = 8192, B_MN_SBO = 1024;   // 64-row blocks 8 KB apa
 __device__ __forceinline__ void produce_chmajor_mn(const OperandSrc& s, uint8_t* hi, uint8_t* lo, int nhl, int nrows, int n0,
                                                    int n_limit, int k0, int k_limit, int ptid) {
     const int chunks = (nrows + 7) >> 3;
-    for (int task = ptid; task < K_BLK * chunks; task += PROD_THREADS) {
-        int kk = task / chunks, c = task - kk * chunks;
-        int k = k0 + kk, n = n0 + c * 8;
-        float v[8];
+    const int ntasks = K_BLK * chunks;
+    for (int base = ptid; base < ntasks; base += PROD_THREADS * PBATCH) {
+        TaskData td[PBATCH];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        if (k < k_limit && n < n_limit) {
-            float a[8], b[8];
-            const float* p0 = s.src0 + (long long)k * s.ld + n;
-            bool full = (n + 8 <= n_limit) && ((reinterpret_cast<uintptr_t>(p0) & 15) == 0);
-            if (full) {
-                float4 t0 = __ldg(reinterpret_cast<const float4*>(p0));
-                float4 t1 = __ldg(reinterpret_cast<const float4*>(p0) + 1);
-                a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] = (n + e < n_limit) ? __ldg(p0 + e) : 0.f;
-            }
-            if (s.src1) {
-                const float* p1 = s.src1 + (long long)k * s.ld + n;
-                if (full && ((reinterpret_cast<uintptr_t>(p1) & 15) == 0)) {
-                    float4 t0 = __ldg(reinterpret_cast<const float4*>(p1));
-                    float4 t1 = __ldg(reinterpret_cast<const float4*>(p1) + 1);
-                    b[0] = t0.x; b[1] = t0.y; b[2] = t0.z; b[3] = t0.w; b[4] = t1.x; b[5] = t1.y; b[6] = t1.z; b[7] = t1.w;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) b[e] = (n + e < n_limit) ? __ldg(p1 + e) : 0.f;
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) b[e] = 0.f;
-            }
-            float c0 = s.s0 ? __ldg(s.s0 + k) : 1.f;
-            float c1 = s.s1 ? __ldg(s.s1 + k) : 0.f;
-            float c2 = s.s2 ? __ldg(s.s2 + k) : 0.f;
-            float cl = s.lo ? __ldg(s.lo + k) : -INFINITY;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (n + e < n_limit) ? xform(a[e], b[e], c0, c1, c2, cl) : 0.f;
+        for (int u = 0; u < PBATCH; ++u) {
+            const int task = base + u * PROD_THREADS;
+            const int kk = task / chunks, c = task - kk * chunks;
+            const int k = k0 + kk, n = n0 + c * 8;
+            int nv = (task < ntasks && k < k_limit) ? (n_limit - n) : 0;
+            nv = nv > 8 ? 8 : nv;
+            load_task(s, (long long)k * s.ld + n, nv, k, td[u]);
         }
-        uint32_t off = mn_sw128_offset((uint32_t)kk, (uint32_t)c, B_MN_LBO, B_MN_SBO);
-        if (nhl == 2) {
-            uint4 h, l;
-            split_bf16x8(v, h, l);
-            *reinterpret_cast<uint4*>(hi + off) = h;
-            *reinterpret_cast<uint4*>(lo + off) = l;
-        } else {
-            *reinterpret_cast<uint4*>(hi + off) = pack_bf16x8(v);
+#pragma unroll
+        for (int u = 0; u < PBATCH; ++u) {
+            const int task = base + u * PROD_THREADS;
+            if (task < ntasks) {
+                const int kk = task / chunks, c = task - kk * chunks;
+                float v[8];
+                finish_task(td[u], v);
+                uint32_t off = mn_sw128_offset((uint32_t)kk, (uint32_t)c, B_MN_LBO, B_MN_SBO);
+                if (nhl == 2) {
+                    uint4 h, l;
+                    split_bf16x8(v, h, l);
+                    *reinterpret_cast<uint4*>(hi + off) = h;
+                    *reinterpret_cast<uint4*>(lo + off) = l;
+                } else {
+                    *reinterpret_cast<uint4*>(hi + off) = pack_bf16x8(v);
+                }
+            }
         }
     }
 }
@@ -272,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p)
         }
         mbar_fence_init();
     }
-    if (warp == 8) {
+    if (warp == 10) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
@@ -391,9 +360,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p)
             st[0] = stat0;
             st[1] = stat1;
         }
-    } else if (warp < 8) {
+    } else if (warp < 10) {
         // =============================== producers ===============================
-        const int pw = warp - 4;
         const int ptid = threadIdx.x - 128;
         int stage = 0, phase = 0;
         for (int it = 0; sched.get(it, p, w); ++it) {
@@ -410,8 +378,6 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p)
                     produce_rowmajor(p.b, b_hi, b_lo, nhl, mma_n, w.nt * N_TILE, p.Nd, kb * K_BLK, p.Kd, ptid);
                 else if (p.b_mode == B_CHMAJOR)
                     produce_chmajor_mn(p.b, b_hi, b_lo, nhl, mma_n, w.nt * N_TILE, p.Nd, kb * K_BLK, p.Kd, ptid);
-                else if (p.b_mode == B_CHMAJOR_GATHER)
-                    produce_chmajor(p.b, b_hi, b_lo, nhl, mma_n, w.nt * N_TILE, p.Nd, kb * K_BLK, p.Kd, pw, lane);
                 else
                     produce_xt4(p.b, b_hi, b_lo, nhl, mma_n, w.nt * N_TILE, p.Nd, ptid);
                 fence_proxy_async_smem();
@@ -423,7 +389,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p)
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 10) {
         // =============================== MMA issuer ===============================
         const bool b_mn = (p.b_mode == B_CHMAJOR);
         const uint32_t idesc = umma_idesc_bf16(M_TILE, mma_n) | (b_mn ? UMMA_B_MN_MAJOR : 0u);
@@ -490,7 +456,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p)
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 10) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 512);
     }

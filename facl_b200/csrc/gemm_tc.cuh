@@ -30,7 +30,7 @@ struct OperandSrc {
 };
 
 enum : int { A_PACKED = 0, A_ROWMAJOR = 1 };
-enum : int { B_ROWMAJOR = 1, B_CHMAJOR = 2, B_XT4 = 3, B_CHMAJOR_GATHER = 5 };
+enum : int { B_ROWMAJOR = 1, B_CHMAJOR = 2, B_XT4 = 3 };
 enum : int { OUT_NONE = 0, OUT_CHMAJOR = 1, OUT_ROWMAJOR = 2, OUT_ATOMIC_CHMAJOR = 3, OUT_ROWMAJOR_ACC = 4 };
 
 struct GemmParams {
