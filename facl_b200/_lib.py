@@ -23,6 +23,10 @@ class Operand(C.Structure):
                 ("s0", C.c_void_p), ("s1", C.c_void_p), ("s2", C.c_void_p), ("lo", C.c_void_p)]
 
 
+class ActImage(C.Structure):
+    _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("cgs", C.c_int), ("rbs", C.c_int)]
+
+
 class Gemm(C.Structure):
     _fields_ = [("Md", C.c_int), ("Nd", C.c_int), ("Kd", C.c_int), ("nsplit", C.c_int),
                 ("a_mode", C.c_int), ("b_mode", C.c_int),
@@ -32,7 +36,7 @@ class Gemm(C.Structure):
                 ("bias", C.c_void_p), ("out_mode", C.c_int), ("out", C.c_void_p), ("ldo", C.c_longlong),
                 ("zin", C.c_void_p), ("ldz", C.c_longlong), ("zs0", C.c_void_p), ("zs2", C.c_void_p),
                 ("stats", C.c_void_p), ("pool", C.c_int), ("pool_sign", C.c_void_p), ("pool_out", C.c_void_p),
-                ("pool_arg", C.c_void_p), ("ldp", C.c_longlong)]
+                ("pool_arg", C.c_void_p), ("ldp", C.c_longlong), ("a_img", ActImage), ("b_img", ActImage)]
 
 
 NUM_BN_LAYERS = 7
@@ -86,6 +90,8 @@ SIGNATURES = {
     "facl_pack_weight": (_I, [_P, _LL, _LL, _I, _I, _P, _P]),
     "facl_gemm_stat_partials": (_I, [_I, _I]),
     "facl_gemm_tc": (_I, [C.POINTER(Gemm), _P]),
+    "facl_act_image_half_bytes": (_SZ, [_I, _LL]),
+    "facl_act_image": (_I, [C.POINTER(Operand), _LL, _I, _LL, _P, _I, _I, C.POINTER(ActImage), _P]),
     "facl_encoder_num_buffers": (_I, []),
     "facl_encoder_buffer_name": (C.c_char_p, [_I]),
     "facl_encoder_buffer_bytes": (_SZ, [_I, C.POINTER(EncoderDims)]),

@@ -29,12 +29,13 @@ const float BN_EPS = 1e-5f, BN_MOM = 0.1f;
 
 enum Buf {
     B_Z1, B_Z2, B_Z3, B_ARG3, B_PCAT, B_Z4, B_Z5, B_Z6, B_ARG6, B_PALL, B_ARGG, B_Z7, B_BN, B_VEC, B_STATS, B_WPACK,
-    B_DXT, B_DH7, B_DF, B_DY6, B_DH5, B_DH4, B_DP3, B_DY3, B_DH2, B_DH1, B_XTT, B_WPACKT,
+    B_IMG_H3, B_IMG_H4, B_IMG_H5,
+    B_DXT, B_DH7, B_DF, B_DY6, B_DH5, B_DH4, B_DP3, B_DY3, B_DH2, B_DH1, B_XTT, B_WPACKT, B_IMG_DZ,
     NUM_BUFS
 };
 const char* BUF_NAMES[NUM_BUFS] = {"z1", "z2", "z3", "arg3", "pcat", "z4", "z5", "z6", "arg6", "pall", "argg", "z7", "bn", "vec",
-                                   "stats", "wpack", "dxt", "dh7", "df", "dy6", "dh5", "dh4", "dp3", "dy3", "dh2", "dh1", "xtt",
-                                   "wpackt"};
+                                   "stats", "wpack", "img_h3", "img_h4", "img_h5", "dxt", "dh7", "df", "dy6", "dh5", "dh4", "dp3", "dy3", "dh2", "dh1", "xtt",
+                                   "wpackt", "img_dz"};
 const int FIRST_BWD_BUF = B_DXT;
 
 // forward weight images: layers 0..6, then fc3 (512x1024), then mapping (64x512)
@@ -58,6 +59,9 @@ size_t wpackt_offset(int idx) {   // idx 1..6 layers, 7 = fc3^T, 8 = end
     return off;
 }
 
+// net3DV_3 runs on pre-converted activation images (gemm_img.cu) whenever a pooling group is a whole number of chunks
+bool use_images(const facl_encoder_dims* d) { return d->S % 8 == 0; }
+
 size_t buffer_bytes(int i, const facl_encoder_dims* d) {
     const size_t M = d->M, R3 = (size_t)d->M * d->S, R1 = R3 * d->K, B = d->M / d->G, MB = M + B, f = sizeof(float);
     if (d->flags & FACL_ENC_FUSED_L1) {   // no per-row activation is stored: only dh2 (pass C -> pass D) and small scratch
@@ -74,7 +78,8 @@ size_t buffer_bytes(int i, const facl_encoder_dims* d) {
         case B_PCAT: return 259 * R3 * f;
         case B_Z4: case B_DH4: case B_DP3: return 256 * R3 * f;
         case B_Z5: case B_DH5: return 512 * R3 * f;
-        case B_Z6: case B_DY6: return 1024 * R3 * f;
+        case B_DY6: return use_images(d) ? 256 : 1024 * R3 * f;
+        case B_Z6: return 1024 * R3 * f;
         case B_ARG6: return 1024 * MB;
         case B_PALL: case B_Z7: case B_DH7: case B_DF: return 1024 * MB * f;
         case B_ARGG: return 1024 * B;
@@ -85,6 +90,10 @@ size_t buffer_bytes(int i, const facl_encoder_dims* d) {
         case B_DXT: return 512 * MB * f;
         case B_XTT: return 4 * R1 * f;
         case B_WPACKT: return wpackt_offset(8);
+        case B_IMG_H3: return use_images(d) ? 2 * act_image_half_bytes(259, (long long)R3) : 256;
+        case B_IMG_H4: return use_images(d) ? 2 * act_image_half_bytes(256, (long long)R3) : 256;
+        case B_IMG_H5: return use_images(d) ? 2 * act_image_half_bytes(512, (long long)R3) : 256;
+        case B_IMG_DZ: return use_images(d) ? 2 * act_image_half_bytes(1024, (long long)R3) : 256;
     }
     return 0;
 }
@@ -134,6 +143,17 @@ OperandSrc src2(const float* a, const float* b, long long ld, const float* c0, c
 int layer_nsplit(int ns, int layer) {
     if (ns == 3) return 3;
     return (layer == 0 || layer >= 6) ? 3 : 1;
+}
+
+int layer_nhl(int ns, int layer) { return layer_nsplit(ns, layer) == 3 ? 2 : 1; }
+
+ActImage image_of(void* const* bufs, int buf, int C, long long R) {
+    ActImage im;
+    im.hi = bufs[buf];
+    im.lo = reinterpret_cast<const uint8_t*>(bufs[buf]) + act_image_half_bytes(C, R);
+    im.cgs = ((C + 63) / 64) * 8;
+    im.rbs = (int)((R + 63) / 64);
+    return im;
 }
 
 int pick_ksplit(int Md, int Nd, int Kd) {
@@ -260,42 +280,40 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     }
     // ---- L3: [centre xyz | pooled 256] -> 256 -> 512 -> 1024 over the M*S centres, max over the S centres ----
     RUN(centres_to_chmajor_launch(centres, (int)R3, F(B_PCAT), R3, st));
-    {
-        GemmParams g = gemm_base(256, (int)R3, 259, ns);
-        g.tag = 9;
-        set_packed_a(g, wp + wpack_offset(3), 259);
-        g.b = src1(F(B_PCAT), R3, vec, vec + 320, vec + 640);
-        g.bias = p->layer[3].b;
-        g.out_mode = OUT_CHMAJOR; g.out = F(B_Z4); g.ldo = R3;
+    const bool img = use_images(d);
+    // one forward layer of net3DV_3: (image of the BN+ReLU'd input ->) GEMM with statistics (and max-pool) epilogue
+    auto l3_layer = [&](int layer, int img_buf, const OperandSrc& in, float* zout, bool pool) {
+        GemmParams g = gemm_base(COUT[layer], (int)R3, CIN[layer], layer_nsplit(ns, layer));
+        g.tag = 3 * layer;
+        set_packed_a(g, wp + wpack_offset(layer), CIN[layer]);
+        if (img) {
+            ActImage im = image_of(bufs, img_buf, CIN[layer], R3);
+            int rc = act_image_launch(in, 0, CIN[layer], R3, nullptr, 0, layer_nhl(ns, layer), im, TAG_IMAGE, st);
+            if (rc != 0) return rc;
+            g.b_mode = B_IMAGE_MN;
+            g.b_img = im;
+        } else {
+            g.b = in;
+        }
+        g.bias = p->layer[layer].b;
+        if (!pool || tr) { g.out_mode = OUT_CHMAJOR; g.out = zout; g.ldo = R3; }
         g.stats = stats;
-        RUN(launch_gemm_tc(g, st));
-        RUN(finalize(3, 3, (int)R3, (double)R3));
-    }
+        if (pool) {
+            g.pool = S; g.pool_sign = p->layer[layer].gamma; g.pool_out = F(B_PALL); g.ldp = MB;
+            g.pool_arg = tr ? U(B_ARG6) : nullptr;
+        }
+        int rc = launch_gemm_tc(g, st);
+        if (rc != 0) return rc;
+        return finalize(layer, layer, (int)R3, (double)R3);
+    };
+    RUN(l3_layer(3, B_IMG_H3, src1(F(B_PCAT), R3, vec, vec + 320, vec + 640), F(B_Z4), false));
     {
         Slot s = bn_slot(bufs, 3);
-        GemmParams g = gemm_base(512, (int)R3, 256, ns);
-        g.tag = 12;
-        set_packed_a(g, wp + wpack_offset(4), 256);
-        g.b = src1(F(B_Z4), R3, s.scale, s.shift, lo0);
-        g.bias = p->layer[4].b;
-        g.out_mode = OUT_CHMAJOR; g.out = F(B_Z5); g.ldo = R3;
-        g.stats = stats;
-        RUN(launch_gemm_tc(g, st));
-        RUN(finalize(4, 4, (int)R3, (double)R3));
+        RUN(l3_layer(4, B_IMG_H4, src1(F(B_Z4), R3, s.scale, s.shift, lo0), F(B_Z5), false));
     }
     {
         Slot s = bn_slot(bufs, 4);
-        GemmParams g = gemm_base(1024, (int)R3, 512, ns);
-        g.tag = 15;
-        set_packed_a(g, wp + wpack_offset(5), 512);
-        g.b = src1(F(B_Z5), R3, s.scale, s.shift, lo0);
-        g.bias = p->layer[5].b;
-        if (tr) { g.out_mode = OUT_CHMAJOR; g.out = F(B_Z6); g.ldo = R3; }
-        g.stats = stats;
-        g.pool = S; g.pool_sign = p->layer[5].gamma; g.pool_out = F(B_PALL); g.ldp = MB;
-        g.pool_arg = tr ? U(B_ARG6) : nullptr;
-        RUN(launch_gemm_tc(g, st));
-        RUN(finalize(5, 5, (int)R3, (double)R3));
+        RUN(l3_layer(5, B_IMG_H5, src1(F(B_Z5), R3, s.scale, s.shift, lo0), F(B_Z6), true));
     }
     // ---- sequence aggregation: max over the G views (cn3d_model_conbag.py:225-226) ---------------------------
     RUN(seq_pool_launch(F(B_PALL), MB, p->layer[5].gamma, C_FEAT, G, B, F(B_PALL) + M, MB, U(B_ARGG), st));
@@ -422,12 +440,47 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
     RUN(bwd_finalize(5, 5, C_FEAT, M, (double)R3, 1, 0));
 
     // ---- L3 ---------------------------------------------------------------------------------------------------
+    Slot s4 = bn_slot(bufs, 4), s3 = bn_slot(bufs, 3), s2 = bn_slot(bufs, 2), s1 = bn_slot(bufs, 1), s0 = bn_slot(bufs, 0);
+    if (use_images(d)) {
+        // dz_l = c0*dy + c1*z + c2 is converted ONCE into an image and read by both the weight- and the data-gradient GEMM;
+        // the forward input images (img_h*) are still there.  dy of layer 5 is the max-pool scatter of df, read through arg6.
+        auto l3_bwd = [&](int layer, const OperandSrc& dzsrc, long long ld1, const unsigned char* parg, int h_buf, const float* zin,
+                          const float* zs0, const float* zs2, float* dout, int slot_below, double n_below) {
+            const int Co = COUT[layer], Ci = CIN[layer];
+            ActImage dz = image_of(bufs, B_IMG_DZ, Co, R3);
+            int rc = act_image_launch(dzsrc, ld1, Co, R3, parg, parg ? S : 0, layer_nhl(ns, layer), dz, TAG_IMAGE, st);
+            if (rc != 0) return rc;
+            GemmParams g = gemm_base(Co, Ci, (int)R3, layer_nsplit(ns, layer));
+            g.tag = 3 * layer + 1;
+            g.a_mode = A_IMAGE; g.a_img = dz;
+            g.b_mode = B_IMAGE_K; g.b_img = image_of(bufs, h_buf, Ci, R3);
+            g.ksplit = pick_ksplit(Co, Ci, (int)R3);
+            g.out_mode = OUT_ATOMIC_CHMAJOR; g.out = gr->dw[layer]; g.ldo = Ci;
+            rc = launch_gemm_tc(g, st);
+            if (rc != 0) return rc;
+            GemmParams h = gemm_base(tin(layer), (int)R3, Co, layer_nsplit(ns, layer));
+            h.tag = 3 * layer + 2;
+            set_packed_a(h, wt + wpackt_offset(layer), Co);
+            h.b_mode = B_IMAGE_MN; h.b_img = dz;
+            h.zin = zin; h.ldz = R3; h.zs0 = zs0; h.zs2 = zs2;
+            h.out_mode = OUT_CHMAJOR; h.out = dout; h.ldo = R3;
+            h.stats = stats;
+            rc = launch_gemm_tc(h, st);
+            if (rc != 0) return rc;
+            return bwd_finalize(slot_below, slot_below, 0, 0, n_below, gemm_tc_ctas_per_mtile(tin(layer), (int)R3), 0);
+        };
+        RUN(l3_bwd(5, src2(F(B_DF), F(B_Z6), MB, s5.c0, s5.c1, s5.c2), R3, U(B_ARG6), B_IMG_H5, F(B_Z5), s4.scale, s4.shift, F(B_DH5),
+                   4, (double)R3));
+        RUN(l3_bwd(4, src2(F(B_DH5), F(B_Z5), R3, s4.c0, s4.c1, s4.c2), 0, nullptr, B_IMG_H4, F(B_Z4), s3.scale, s3.shift, F(B_DH4), 3,
+                   (double)R3));
+        RUN(l3_bwd(3, src2(F(B_DH4), F(B_Z4), R3, s3.c0, s3.c1, s3.c2), 0, nullptr, B_IMG_H3, F(B_PCAT) + 3 * R3, s2.scale, s2.shift,
+                   F(B_DP3), 2, (double)R1));
+    } else {
     {
         ScopedTimer timer(TAG_MEMSET, st);
         FACL_CHECK(cudaMemsetAsync(F(B_DY6), 0, sizeof(float) * 1024 * R3, st));
     }
     RUN(pool_scatter_launch(F(B_DF), MB, U(B_ARG6), MB, C_FEAT, M, S, F(B_DY6), R3, st));
-    Slot s4 = bn_slot(bufs, 4), s3 = bn_slot(bufs, 3), s2 = bn_slot(bufs, 2), s1 = bn_slot(bufs, 1), s0 = bn_slot(bufs, 0);
     {   // layer 5 (512 -> 1024)
         OperandSrc dz = src2(F(B_DY6), F(B_Z6), R3, s5.c0, s5.c1, s5.c2);
         RUN(wgrad(5, 1024, 512, (int)R3, dz, src1(F(B_Z5), R3, s4.scale, s4.shift, lo0), gr->dw[5]));
@@ -445,6 +498,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
         RUN(wgrad(3, 256, 259, (int)R3, dz, src1(F(B_PCAT), R3, vec, vec + 320, vec + 640), gr->dw[3]));
         RUN(dgrad(3, 256, (int)R3, 256, wt + wpackt_offset(3), dz, F(B_PCAT) + 3 * R3, R3, s2.scale, s2.shift, F(B_DP3), R3, true));
         RUN(bwd_finalize(2, 2, 256, (int)R3, (double)R1, gemm_tc_ctas_per_mtile(256, (int)R3), 0));
+    }
     }
     if (d->flags & FACL_ENC_FUSED_L1) {
         // ---- L1 fused backward: activations recomputed from the 16-byte input rows (l1_fused.cu) ------------------------

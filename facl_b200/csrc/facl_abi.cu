@@ -38,6 +38,12 @@ static OperandSrc to_src(const facl_operand& o) {
     return s;
 }
 
+static ActImage to_img(const facl_image& i) {
+    ActImage a;
+    a.hi = i.hi; a.lo = i.lo; a.cgs = i.cgs; a.rbs = i.rbs;
+    return a;
+}
+
 int facl_gemm_stat_partials(int Md, int Nd) { return gemm_tc_ctas_per_mtile(Md, Nd); }
 
 int facl_gemm_tc(const facl_gemm* d, void* stream) {
@@ -53,7 +59,17 @@ int facl_gemm_tc(const facl_gemm* d, void* stream) {
     p.stats = d->stats; p.pool = d->pool; p.pool_sign = d->pool_sign; p.pool_out = d->pool_out;
     p.pool_arg = d->pool_arg; p.ldp = d->ldp;
     p.tag = -1;
+    p.a_img = to_img(d->a_img);
+    p.b_img = to_img(d->b_img);
     return launch_gemm_tc(p, S(stream));
+}
+
+size_t facl_act_image_half_bytes(int C, long long R) { return act_image_half_bytes(C, R); }
+
+int facl_act_image(const facl_operand* src, long long ld1, int C, long long R, const unsigned char* pool_arg, int pool, int nsplit,
+                   const facl_image* img, void* stream) {
+    if (!src || !img || (nsplit != 1 && nsplit != 3)) return (int)cudaErrorInvalidValue;
+    return act_image_launch(to_src(*src), ld1, C, R, pool_arg, pool, nsplit == 3 ? 2 : 1, to_img(*img), -1, S(stream));
 }
 
 }  // extern "C"

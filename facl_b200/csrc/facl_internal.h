@@ -54,7 +54,7 @@ enum TimingTag {
     TAG_GEMM_BASE = 0,
     TAG_GROUP = 27, TAG_FPS = 28, TAG_PACK = 29, TAG_BN = 30, TAG_POOLMISC = 31, TAG_SCATTER = 32, TAG_LOSS_GEMM = 33,
     TAG_LOSS_MISC = 34, TAG_ADAM = 35, TAG_TRANSPOSE = 36, TAG_MEMSET = 37, TAG_L1_MISC = 38, TAG_L1_PASS_A = 39,
-    TAG_L1_PASS_B = 40, TAG_L1_PASS_C = 41, TAG_L1_PASS_D = 42, NUM_TIMING_TAGS = 43
+    TAG_L1_PASS_B = 40, TAG_L1_PASS_C = 41, TAG_L1_PASS_D = 42, TAG_IMAGE = 43, NUM_TIMING_TAGS = 44
 };
 }  // namespace facl
 

@@ -1,0 +1,402 @@
+// tcgen05 GEMM over PRE-CONVERTED activation images: every operand tile is staged by 1-D bulk TMA copies, no thread
+// touches an operand element.  Used for the net3DV_3 stack (reference training_code/cn3d_model_conbag.py:180-196),
+// whose three layers run on M*S rows -- few enough that converting each activation once (act_image_kernel: BN + ReLU
+// or the BN-backward affine map, fp32 -> bf16 hi/lo, written straight in UMMA tile layout) costs far less HBM time
+// than re-converting it inside every GEMM that reads it.
+//
+//   forward / data-gradient:  D[m][n] = sum_k W[m][k] * act[k][n]      A = packed weight image, B = image (MN-major)
+//   weight-gradient        :  D[m][n] = sum_r dz[m][r] * act[n][r]     A, B = images (K-major over rows), split-K
+//
+// Warp roles: warps 0-3 epilogue (TMEM lane = output channel), warp 4 MMA issuer, warp 5 TMA issuer.
+#include "gemm_tc.cuh"
+#include "common.cuh"
+#include "facl_internal.h"
+#include "umma.cuh"
+#include "gemm_sched.cuh"
+
+namespace facl {
+
+namespace {
+
+constexpr int IMG_THREADS = 192;
+constexpr uint32_t IMG_LBO = 8192, IMG_SBO = 1024;   // B tile as staged: 64-row blocks 8 KB apart, 8-channel atoms 1 KB apart
+
+template <int NHL>
+__global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int STAGE_BYTES = (A_TILE_BYTES + B_TILE_BYTES) * NHL;
+    constexpr int NUM_STAGES = (NHL == 2) ? 2 : 4;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * STAGE_BYTES);
+    uint64_t* empty = full + NUM_STAGES;
+    uint64_t* acc_full = empty + NUM_STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mma_n = (p.Nd >= N_TILE) ? N_TILE : ((p.Nd + 15) & ~15);
+    const bool wgrad = (p.a_mode == A_IMAGE);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NUM_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 4) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    Schedule sched(p);
+    Work w;
+
+    if (warp < 4) {
+        // =============================== epilogue ===============================
+        const int c = sched.mt * M_TILE + warp * 32 + lane;
+        const bool cvalid = c < p.Md;
+        const float bias = (cvalid && p.bias) ? __ldg(p.bias + c) : 0.f;
+        const float zs0 = (cvalid && p.zs0) ? __ldg(p.zs0 + c) : 1.f;
+        const float zs2 = (cvalid && p.zs2) ? __ldg(p.zs2 + c) : 0.f;
+        const float psign = (cvalid && p.pool_sign) ? __ldg(p.pool_sign + c) : 1.f;
+        const bool keep_max = psign >= 0.f;
+        float stat0 = 0.f, stat1 = 0.f;
+        for (int it = 0; sched.get(it, p, w); ++it) {
+            const int buf = it & 1;
+            mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            tc_fence_after_sync();
+            float best = 0.f;
+            int barg = 0;
+            const int nchunks = (mma_n + 31) / 32;
+            for (int cc = 0; cc < nchunks; ++cc) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N_TILE + cc * 32), v);
+                tmem_ld_wait();
+                const int n0 = w.nt * N_TILE + cc * 32;
+                int nvalid = p.Nd - n0;
+                nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
+                if (!cvalid || nvalid <= 0) continue;
+                if (p.out_mode == OUT_ATOMIC_CHMAJOR) {
+                    float* o = p.out + (long long)c * p.ldo + n0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nvalid) atomicAdd(o + i, v[i]);
+                    continue;
+                }
+                float z[32];
+                if (p.zin) {
+                    const float* zr = p.zin + (long long)c * p.ldz + n0;
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(zr) & 15) == 0)) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 t = __ldg(reinterpret_cast<const float4*>(zr) + q);
+                            z[4 * q] = t.x; z[4 * q + 1] = t.y; z[4 * q + 2] = t.z; z[4 * q + 3] = t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) z[i] = (i < nvalid) ? __ldg(zr + i) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float val = v[i] + bias;
+                    if (p.zin) val = (fmaf(zs0, z[i], zs2) > 0.f) ? val : 0.f;
+                    if (i < nvalid) {
+                        stat0 += val;
+                        stat1 = fmaf(val, p.zin ? z[i] : val, stat1);
+                    }
+                    v[i] = val;
+                }
+                if (p.pool) {
+                    const int pm = p.pool - 1;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (i < nvalid) {
+                            int pos = (cc * 32 + i) & pm;
+                            float sv = keep_max ? v[i] : -v[i];
+                            if (pos == 0 || sv > best) {
+                                best = sv;
+                                barg = pos;
+                            }
+                            if (pos == pm) {
+                                long long gi = (long long)c * p.ldp + (n0 + i) / p.pool;
+                                p.pool_out[gi] = keep_max ? best : -best;
+                                if (p.pool_arg) p.pool_arg[gi] = (unsigned char)barg;
+                            }
+                        }
+                    }
+                }
+                if (p.out_mode == OUT_CHMAJOR) {
+                    float* o = p.out + (long long)c * p.ldo + n0;
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nvalid) o[i] = v[i];
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (p.stats && cvalid) {
+            int pidx = sched.split ? 0 : (blockIdx.x / sched.numMT);
+            float* st = p.stats + ((long long)pidx * p.Md + c) * 2;
+            st[0] = stat0;
+            st[1] = stat1;
+        }
+    } else if (warp == 4) {
+        // =============================== MMA issuer ===============================
+        const uint32_t idesc = umma_idesc_bf16(M_TILE, mma_n) | (wgrad ? 0u : UMMA_B_MN_MAJOR);
+        int stage = 0, phase = 0;
+        for (int it = 0; sched.get(it, p, w); ++it) {
+            const int buf = it & 1;
+            mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N_TILE);
+            for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after_sync();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES), a_lo = a_hi + A_TILE_BYTES;
+                    const uint32_t b_hi = a_hi + A_TILE_BYTES * NHL, b_lo = b_hi + B_TILE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t acc = (kb > w.kb0 || ks > 0) ? 1u : 0u;
+                        const uint32_t ko = ks * 32;
+                        const uint64_t ad_hi = umma_desc_sw128(a_hi + ko);
+                        const uint64_t bd_hi = wgrad ? umma_desc_sw128(b_hi + ko)
+                                                     : umma_desc_mn_sw128(b_hi + ks * 2 * IMG_SBO, IMG_LBO, IMG_SBO);
+                        umma_bf16_ss(d_tmem, ad_hi, bd_hi, idesc, acc);
+                        if (NHL == 2) {
+                            const uint64_t bd_lo = wgrad ? umma_desc_sw128(b_lo + ko)
+                                                         : umma_desc_mn_sw128(b_lo + ks * 2 * IMG_SBO, IMG_LBO, IMG_SBO);
+                            umma_bf16_ss(d_tmem, ad_hi, bd_lo, idesc, 1u);
+                            umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ko), bd_hi, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (kb == w.kb1 - 1) umma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+                if (++stage == NUM_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (lane == 0) {
+        // =============================== TMA issuer ===============================
+        int stage = 0, phase = 0;
+        const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.a_packed);
+        const uint8_t* ai_hi = reinterpret_cast<const uint8_t*>(p.a_img.hi);
+        const uint8_t* ai_lo = reinterpret_cast<const uint8_t*>(p.a_img.lo);
+        const uint8_t* bi_hi = reinterpret_cast<const uint8_t*>(p.b_img.hi);
+        const uint8_t* bi_lo = reinterpret_cast<const uint8_t*>(p.b_img.lo);
+        for (int it = 0; sched.get(it, p, w); ++it) {
+            for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = smem + stage * STAGE_BYTES;
+                uint8_t* a_hi = st;
+                uint8_t* b_hi = st + A_TILE_BYTES * NHL;
+                uint8_t* b_lo = b_hi + B_TILE_BYTES;
+                if (!wgrad) {
+                    // A: one packed weight tile (hi | lo adjacent);  B: up to four 64-row blocks x 8 channel atoms
+                    const int rb0 = w.nt * (N_TILE / 64);
+                    int nrb = p.b_img.rbs - rb0;
+                    nrb = nrb > N_TILE / 64 ? N_TILE / 64 : nrb;
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(A_TILE_BYTES * NHL + nrb * 8192 * NHL));
+                    tma_bulk_g2s(a_hi, wimg + ((long long)w.mt * p.a_packed_kblocks + kb) * (2ll * A_TILE_BYTES), A_TILE_BYTES * NHL,
+                                 &full[stage]);
+                    for (int r = 0; r < nrb; ++r) {
+                        const long long off = ((long long)(rb0 + r) * p.b_img.cgs + kb * 8) * 1024;
+                        tma_bulk_g2s(b_hi + r * 8192, bi_hi + off, 8192, &full[stage]);
+                        if (NHL == 2) tma_bulk_g2s(b_lo + r * 8192, bi_lo + off, 8192, &full[stage]);
+                    }
+                } else {
+                    // reduction over the 64 rows of row block kb: A = 16 channel atoms, B = 32 channel atoms, both contiguous
+                    int na = p.a_img.cgs - w.mt * 16, nb = p.b_img.cgs - w.nt * 32;
+                    na = na > 16 ? 16 : na;
+                    nb = nb > 32 ? 32 : nb;
+                    const long long aoff = ((long long)kb * p.a_img.cgs + w.mt * 16) * 1024;
+                    const long long boff = ((long long)kb * p.b_img.cgs + w.nt * 32) * 1024;
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)((na + nb) * 1024 * NHL));
+                    tma_bulk_g2s(a_hi, ai_hi + aoff, na * 1024, &full[stage]);
+                    tma_bulk_g2s(b_hi, bi_hi + boff, nb * 1024, &full[stage]);
+                    if (NHL == 2) {
+                        tma_bulk_g2s(a_hi + A_TILE_BYTES, ai_lo + aoff, na * 1024, &full[stage]);
+                        tma_bulk_g2s(b_lo, bi_lo + boff, nb * 1024, &full[stage]);
+                    }
+                }
+                if (++stage == NUM_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fp32 channel-major activation -> bf16 hi/lo image.  Block = one 8-channel group x 256 rows; thread = (channel, 8 rows):
+// a warp reads 1 KB of one channel row per source and writes four full 128-byte swizzled rows.
+// ---------------------------------------------------------------------------------------------------------------------
+struct ImgParams {
+    OperandSrc s;
+    int C;
+    long long R;
+    const unsigned char* pool_arg;
+    int pool;
+    int nhl;
+    uint8_t* hi;
+    uint8_t* lo;
+    int cgs, rbs;
+    long long ld1;            // leading dimension of src1
+};
+
+__global__ void __launch_bounds__(256) act_image_kernel(const ImgParams q) {
+    const int cg = blockIdx.y;
+    const int c8 = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = cg * 8 + c8;
+    const long long r0 = ((long long)blockIdx.x * 32 + lane) * 8;           // first of this thread's 8 rows
+    const long long rb = r0 >> 6;
+    const int chunk = (int)((r0 >> 3) & 7);
+    if (rb >= q.rbs) return;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (c < q.C && r0 < q.R) {
+        const bool full8 = r0 + 8 <= q.R;
+        float a[8], b[8];
+        if (q.pool) {
+            // rows r0..r0+7 lie in one pooling group (pool is a multiple of 8)
+            const long long g = r0 / q.pool;
+            const int pos0 = (int)(r0 - g * q.pool);
+            const float dv = __ldg(q.s.src0 + (long long)c * q.s.ld + g);
+            const int arg = q.pool_arg[(long long)c * q.s.ld + g];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] = (arg == pos0 + e) ? dv : 0.f;
+        } else {
+            const float* p0 = q.s.src0 + (long long)c * q.s.ld + r0;
+            if (full8 && ((reinterpret_cast<uintptr_t>(p0) & 15) == 0)) {
+                float4 t0 = __ldg(reinterpret_cast<const float4*>(p0)), t1 = __ldg(reinterpret_cast<const float4*>(p0) + 1);
+                a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] = (r0 + e < q.R) ? __ldg(p0 + e) : 0.f;
+            }
+        }
+        if (q.s.src1) {
+            const float* p1 = q.s.src1 + (long long)c * q.ld1 + r0;
+            if (full8 && ((reinterpret_cast<uintptr_t>(p1) & 15) == 0)) {
+                float4 t0 = __ldg(reinterpret_cast<const float4*>(p1)), t1 = __ldg(reinterpret_cast<const float4*>(p1) + 1);
+                b[0] = t0.x; b[1] = t0.y; b[2] = t0.z; b[3] = t0.w; b[4] = t1.x; b[5] = t1.y; b[6] = t1.z; b[7] = t1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) b[e] = (r0 + e < q.R) ? __ldg(p1 + e) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) b[e] = 0.f;
+        }
+        const float s0 = q.s.s0 ? __ldg(q.s.s0 + c) : 1.f, s1 = q.s.s1 ? __ldg(q.s.s1 + c) : 0.f;
+        const float s2 = q.s.s2 ? __ldg(q.s.s2 + c) : 0.f, lo = q.s.lo ? __ldg(q.s.lo + c) : -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (r0 + e < q.R) ? fmaxf(fmaf(s0, a[e], fmaf(s1, b[e], s2)), lo) : 0.f;
+    }
+    const long long off = (rb * q.cgs + cg) * 1024 + sw128_offset((uint32_t)c8, (uint32_t)chunk);
+    if (q.nhl == 2) {
+        uint4 h, l;
+        split_bf16x8(v, h, l);
+        *reinterpret_cast<uint4*>(q.hi + off) = h;
+        *reinterpret_cast<uint4*>(q.lo + off) = l;
+    } else {
+        *reinterpret_cast<uint4*>(q.hi + off) = pack_bf16x8(v);
+    }
+}
+
+}  // namespace
+
+size_t act_image_half_bytes(int C, long long R) {
+    const size_t cgs = (size_t)((C + 63) / 64) * 8, rbs = (size_t)((R + 63) / 64);
+    return cgs * rbs * 1024;
+}
+
+int launch_gemm_img(const GemmParams& p, cudaStream_t stream) {
+    static bool configured = false;
+    const int smem_bytes = 4 * (A_TILE_BYTES + B_TILE_BYTES) + 1024 + 256;
+    if (!configured) {
+        FACL_CHECK(cudaFuncSetAttribute(gemm_img_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        FACL_CHECK(cudaFuncSetAttribute(gemm_img_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        configured = true;
+    }
+    const bool wgrad = p.a_mode == A_IMAGE;
+    if (wgrad != (p.b_mode == B_IMAGE_K)) return (int)cudaErrorInvalidValue;
+    if (!wgrad && (p.a_mode != A_PACKED || p.b_mode != B_IMAGE_MN)) return (int)cudaErrorInvalidValue;
+    if (p.Md <= 0 || p.Nd <= 0 || p.Kd <= 0 || (p.nsplit != 1 && p.nsplit != 3)) return (int)cudaErrorInvalidValue;
+    if (p.pool && ((p.pool & (p.pool - 1)) != 0 || p.pool > N_TILE)) return (int)cudaErrorInvalidValue;
+    if (!p.b_img.hi || (p.nsplit == 3 && !p.b_img.lo)) return (int)cudaErrorInvalidValue;
+    const int numMT = (p.Md + M_TILE - 1) / M_TILE, numNT = (p.Nd + N_TILE - 1) / N_TILE, KB = (p.Kd + K_BLK - 1) / K_BLK;
+    if (wgrad) {
+        // Kd = rows (a multiple of 64 after padding); every row block of both images is read
+        if (!p.a_img.hi || (p.nsplit == 3 && !p.a_img.lo) || p.a_img.rbs != KB || p.b_img.rbs != KB) return (int)cudaErrorInvalidValue;
+        if (p.a_img.cgs * 8 < p.Md || p.b_img.cgs * 8 < p.Nd) return (int)cudaErrorInvalidValue;
+        if (p.out_mode != OUT_ATOMIC_CHMAJOR || p.stats || p.pool) return (int)cudaErrorInvalidValue;
+    } else {
+        if (p.b_img.cgs < KB * 8 || (long long)p.b_img.rbs * 64 < p.Nd || p.a_packed_kblocks < KB) return (int)cudaErrorInvalidValue;
+        if (p.ksplit > 1) return (int)cudaErrorInvalidValue;
+    }
+    int grid;
+    if (p.ksplit > 1) {
+        if (p.ksplit > KB) return (int)cudaErrorInvalidValue;
+        grid = numMT * numNT * p.ksplit;
+    } else {
+        grid = numMT * gemm_tc_ctas_per_mtile(p.Md, p.Nd);
+    }
+    ScopedTimer timer(p.tag, stream);
+    count_launch();
+    if (p.nsplit == 3)
+        gemm_img_kernel<2><<<grid, IMG_THREADS, smem_bytes, stream>>>(p);
+    else
+        gemm_img_kernel<1><<<grid, IMG_THREADS, smem_bytes, stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+int act_image_launch(const OperandSrc& src, long long ld1, int C, long long R, const unsigned char* pool_arg, int pool, int nhl,
+                     const ActImage& img, int tag, cudaStream_t st) {
+    if (C <= 0 || R <= 0 || !src.src0 || !img.hi || (nhl == 2 && !img.lo)) return (int)cudaErrorInvalidValue;
+    if (pool && (pool % 8 != 0 || !pool_arg)) return (int)cudaErrorInvalidValue;
+    if (img.cgs * 8 < C || (long long)img.rbs * 64 < R || img.cgs % 8 != 0) return (int)cudaErrorInvalidValue;
+    ImgParams q;
+    q.s = src; q.C = C; q.R = R; q.pool_arg = pool_arg; q.pool = pool; q.nhl = nhl;
+    q.hi = reinterpret_cast<uint8_t*>(const_cast<void*>(img.hi));
+    q.lo = reinterpret_cast<uint8_t*>(const_cast<void*>(img.lo));
+    q.cgs = img.cgs; q.rbs = img.rbs; q.ld1 = ld1 ? ld1 : src.ld;
+    dim3 grid((unsigned)(img.rbs + 3) / 4, (unsigned)img.cgs);
+    ScopedTimer timer(tag, st);
+    count_launch();
+    act_image_kernel<<<grid, 256, 0, st>>>(q);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace facl

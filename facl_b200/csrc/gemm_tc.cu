@@ -6,64 +6,15 @@
 #include "gemm_tc.cuh"
 #include "facl_internal.h"
 #include "umma.cuh"
+#include "gemm_sched.cuh"
 
 namespace facl {
 
 namespace {
 
-constexpr int M_TILE = 128;
-constexpr int N_TILE = 256;
-constexpr int K_BLK = 64;
-constexpr int A_TILE_BYTES = M_TILE * 128;
-constexpr int B_TILE_BYTES = N_TILE * 128;
 constexpr int NUM_PROD_WARPS = 6;
 constexpr int PROD_THREADS = NUM_PROD_WARPS * 32;
 constexpr int THREADS = 384;           // 4 epilogue + 6 producer + MMA + TMA warps
-constexpr int NUM_SMS = 148;
-
-struct Work {
-    int mt, nt, kb0, kb1;
-};
-
-struct Schedule {
-    int numMT, numNT, KB, P;
-    int mt, nt, step, ks;
-    bool split;
-    __device__ Schedule(const GemmParams& p) {
-        numMT = (p.Md + M_TILE - 1) / M_TILE;
-        numNT = (p.Nd + N_TILE - 1) / N_TILE;
-        KB = (p.Kd + K_BLK - 1) / K_BLK;
-        split = p.ksplit > 1;
-        int b = blockIdx.x;
-        if (!split) {
-            P = gridDim.x / numMT;
-            mt = b % numMT;
-            nt = b / numMT;   // first n-tile; advance by P
-            step = P;
-            ks = 0;
-        } else {
-            P = 1;
-            mt = b % numMT;
-            nt = (b / numMT) % numNT;
-            ks = b / (numMT * numNT);
-            step = numNT;     // exactly one item
-        }
-    }
-    __device__ bool get(int it, const GemmParams& p, Work& w) const {
-        int n = nt + it * step;
-        if (n >= numNT) return false;
-        w.mt = mt;
-        w.nt = n;
-        if (!split) {
-            w.kb0 = 0;
-            w.kb1 = KB;
-        } else {
-            w.kb0 = (int)(((long long)ks * KB) / p.ksplit);
-            w.kb1 = (int)(((long long)(ks + 1) * KB) / p.ksplit);
-        }
-        return true;
-    }
-};
 
 __device__ __forceinline__ float xform(float a, float b, float s0, float s1, float s2, float lo) {
     return fmaxf(fmaf(s0, a, fmaf(s1, b, s2)), lo);
@@ -474,6 +425,7 @@ int gemm_tc_ctas_per_mtile(int Md, int Nd) {
 }
 
 int launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
+    if (p.a_mode == A_IMAGE || p.b_mode == B_IMAGE_MN || p.b_mode == B_IMAGE_K) return launch_gemm_img(p, stream);
     static bool configured = false;
     const int smem_bytes = 4 * (A_TILE_BYTES + B_TILE_BYTES) + 1024 + 256;
     if (!configured) {

@@ -29,8 +29,20 @@ struct OperandSrc {
     const float* lo;
 };
 
-enum : int { A_PACKED = 0, A_ROWMAJOR = 1 };
-enum : int { B_ROWMAJOR = 1, B_CHMAJOR = 2, B_XT4 = 3 };
+// A pre-converted bf16 activation image (gemm_img.cu).  Atoms of [8 channels][64 rows] bf16 = 1024 bytes with the
+// 128-byte swizzle (the 16-byte chunk holding rows 8j..8j+7 of channel c sits at chunk (j ^ (c & 7)) of the 128-byte row
+// c & 7); atom (rb, cg) = rows 64 rb.., channels 8 cg.. lives at ((rb * cgs) + cg) * 1024.  The SAME bytes are an
+// MN-major UMMA operand when the GEMM reduces over channels and a K-major operand when it reduces over rows.
+// Channels are padded with zeros to a multiple of 64 (cgs multiple of 8), rows to a multiple of 64.
+struct ActImage {
+    const void* hi;             // bf16(v)
+    const void* lo;             // bf16(v - hi), nsplit == 3 only
+    int cgs;                    // 8-channel groups per row block (padded channel count / 8)
+    int rbs;                    // 64-row blocks
+};
+
+enum : int { A_PACKED = 0, A_ROWMAJOR = 1, A_IMAGE = 2 };
+enum : int { B_ROWMAJOR = 1, B_CHMAJOR = 2, B_XT4 = 3, B_IMAGE_MN = 4, B_IMAGE_K = 5 };
 enum : int { OUT_NONE = 0, OUT_CHMAJOR = 1, OUT_ROWMAJOR = 2, OUT_ATOMIC_CHMAJOR = 3, OUT_ROWMAJOR_ACC = 4 };
 
 struct GemmParams {
@@ -58,7 +70,22 @@ struct GemmParams {
     unsigned char* pool_arg;    // [Md][ldp] position inside the group (first hit), or null
     long long ldp;
     int tag;                    // timing tag (profiler.cu), -1 = untimed
+    // ---- pre-converted activation images (gemm_img.cu): operands staged by bulk TMA only, no conversion warps ----
+    ActImage a_img;             // A_IMAGE: channels = m, reduction over the image's rows (weight-gradient GEMMs)
+    ActImage b_img;             // B_IMAGE_MN: channels = k, rows = n (forward / data-gradient GEMMs);
+                                // B_IMAGE_K: channels = n, reduction over rows
 };
+
+// bytes of one half (hi or lo) of an activation image of C channels x R rows
+size_t act_image_half_bytes(int C, long long R);
+// build an image from an fp32 channel-major source [C][ld] with the OperandSrc transform (per-channel constants).
+// pooled source (optional): src0 is then [C][ld] over GROUPS of `pool` rows and pool_arg [C][ld] the winner position
+// inside each group -- element (c, r) reads src0[c][r / pool] if pool_arg[c][r / pool] == r % pool, else 0.
+// ld1 = leading dimension of src.src1 (0: same as src.ld).
+int act_image_launch(const OperandSrc& src, long long ld1, int C, long long R, const unsigned char* pool_arg, int pool, int nhl,
+                     const ActImage& img, int tag, cudaStream_t st);
+// gemm_img.cu: the TMA-only kernel behind launch_gemm_tc for the *_IMAGE operand modes
+int launch_gemm_img(const GemmParams& p, cudaStream_t stream);
 
 // host launcher (gemm_tc.cu); returns cudaError_t as int
 int launch_gemm_tc(const GemmParams& p, cudaStream_t stream);

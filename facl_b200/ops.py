@@ -9,8 +9,8 @@ import torch
 from . import _lib
 from ._lib import Gemm, Operand, check, lib, ptr, require_cuda, stream_ptr
 
-A_PACKED, A_ROWMAJOR = 0, 1
-B_ROWMAJOR, B_CHMAJOR, B_XT4 = 1, 2, 3
+A_PACKED, A_ROWMAJOR, A_IMAGE = 0, 1, 2
+B_ROWMAJOR, B_CHMAJOR, B_XT4, B_IMAGE_MN, B_IMAGE_K = 1, 2, 3, 4, 5
 OUT_NONE, OUT_CHMAJOR, OUT_ROWMAJOR, OUT_ATOMIC = 0, 1, 2, 3
 
 
@@ -77,7 +77,27 @@ def stat_partials(Md, Nd):
     return lib().facl_gemm_stat_partials(Md, Nd)
 
 
-def gemm_tc(Md, Nd, Kd, *, nsplit, b_mode, b, a_packed=None, a=None, ksplit=1, bias=None, out_mode=OUT_NONE, out=None,
+class Image:
+    """A bf16 hi/lo activation image on the device (C ABI: facl_act_image); see include/facl_b200.h."""
+
+    def __init__(self, C_, R, device):
+        half = lib().facl_act_image_half_bytes(C_, R)
+        self.buf = torch.empty(2 * half, dtype=torch.uint8, device=device)
+        self.C, self.R = C_, R
+        self.struct = _lib.ActImage(self.buf.data_ptr(), self.buf.data_ptr() + half, ((C_ + 63) // 64) * 8, (R + 63) // 64)
+
+
+def act_image(C_, R, nsplit, *, ld1=0, pool_arg=None, pool=0, **operand):
+    """fp32 channel-major activation(s) -> Image (BN / ReLU / BN-backward transform applied on the way)."""
+    src = _operand(**operand)
+    dev = operand["src0"].device
+    img = Image(C_, R, dev)
+    check(lib().facl_act_image(C.byref(src), int(ld1), C_, R, _p(pool_arg), pool, nsplit, C.byref(img.struct), stream_ptr()),
+          "facl_act_image")
+    return img
+
+
+def gemm_tc(Md, Nd, Kd, *, nsplit, b_mode, b=None, a_packed=None, a=None, a_img=None, b_img=None, ksplit=1, bias=None, out_mode=OUT_NONE, out=None,
             ldo=0, zin=None, ldz=0, zs0=None, zs2=None, stats=None, pool=0, pool_sign=None, pool_out=None,
             pool_arg=None, ldp=0):
     """D[m,n] = sum_k A[m,k] B[n,k] on tcgen05 with fused prologue / epilogue (C ABI: facl_gemm_tc).
@@ -87,9 +107,13 @@ def gemm_tc(Md, Nd, Kd, *, nsplit, b_mode, b, a_packed=None, a=None, ksplit=1, b
     if a_packed is not None:
         g.a_mode, g.a_packed, g.a_packed_kblocks = A_PACKED, a_packed.data_ptr(), (Kd + 63) // 64
         g.a = _operand()
+    elif a_img is not None:
+        g.a_mode, g.a_img, g.a = A_IMAGE, a_img.struct, _operand()
     else:
         g.a_mode, g.a = A_ROWMAJOR, _operand(**a)
-    g.b_mode, g.b = b_mode, _operand(**b)
+    g.b_mode, g.b = b_mode, _operand(**(b or {}))
+    if b_img is not None:
+        g.b_img = b_img.struct
     g.ksplit = ksplit
     g.bias, g.out_mode, g.out, g.ldo = _p(bias), out_mode, _p(out), int(ldo)
     g.zin, g.ldz, g.zs0, g.zs2 = _p(zin), int(ldz), _p(zs0), _p(zs2)

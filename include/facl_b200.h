@@ -69,11 +69,30 @@ typedef struct facl_operand {
     const float* lo;
 } facl_operand;
 
+/* A pre-converted bf16 activation image: atoms of [8 channels][64 rows] bf16 (1024 bytes, 128-byte swizzle), atom
+ * (row block rb, channel group cg) at ((rb * cgs) + cg) * 1024; channels zero-padded to a multiple of 64, rows to a
+ * multiple of 64.  The same bytes are an MN-major UMMA operand (reduction over channels) and a K-major one (reduction
+ * over rows), so one conversion serves the forward, data-gradient and weight-gradient GEMMs (csrc/gemm_img.cu). */
+typedef struct facl_image {
+    void* hi;            /* bf16(v) */
+    void* lo;            /* bf16(v - hi); used when nsplit == 3 */
+    int cgs;             /* 8-channel groups per row block = padded channels / 8 */
+    int rbs;             /* 64-row blocks */
+} facl_image;
+
+FACL_API size_t facl_act_image_half_bytes(int C, long long R);
+/* image[c][r] = max(s0[c]*src0[c][r] + s1[c]*src1[c][r] + s2[c], lo[c]) from fp32 channel-major sources (src->ld, ld1 =
+ * leading dimension of src1, 0 = same).  pool > 0 (multiple of 8): src0 and pool_arg are [C][src->ld] over groups of
+ * `pool` rows and element (c, r) reads src0[c][r / pool] where pool_arg[c][r / pool] == r % pool, else 0 (the
+ * max-pool scatter of a pooled gradient).  Declared after facl_operand below. */
+
 typedef struct facl_gemm {
     int Md, Nd, Kd;          /* D[m,n] = sum_k A[m,k] * B[n,k] */
     int nsplit;              /* 1 = bf16 operands, 3 = bf16x3 split ("fp32" mode); fp32 accumulation either way */
-    int a_mode;              /* 0 packed image, 1 fp32 row-major [Md][ld] */
-    int b_mode;              /* 1 fp32 row-major [Nd][ld], 2 fp32 channel-major [Kd][ld], 3 grouped rows [Nd][4] */
+    int a_mode;              /* 0 packed image, 1 fp32 row-major [Md][ld], 2 activation image a_img (K = its rows) */
+    int b_mode;              /* 1 fp32 row-major [Nd][ld], 2 fp32 channel-major [Kd][ld], 3 grouped rows [Nd][4],
+                                4 activation image b_img, channels = k, rows = n (with a_mode 0),
+                                5 activation image b_img, channels = n, K = its rows (with a_mode 2, out_mode 3) */
     const void* a_packed;
     int a_packed_kblocks;
     facl_operand a, b;
@@ -92,7 +111,12 @@ typedef struct facl_gemm {
     float* pool_out;         /* [Md][ldp] */
     unsigned char* pool_arg; /* [Md][ldp] or NULL */
     long long ldp;
+    facl_image a_img;    /* a_mode 2 */
+    facl_image b_img;    /* b_mode 4 / 5 */
 } facl_gemm;
+
+FACL_API int facl_act_image(const facl_operand* src, long long ld1, int C, long long R, const unsigned char* pool_arg, int pool,
+                            int nsplit, const facl_image* img, void* stream);
 
 FACL_API int facl_gemm_stat_partials(int Md, int Nd);
 FACL_API int facl_gemm_tc(const facl_gemm* desc, void* stream);
@@ -240,9 +264,10 @@ FACL_API int facl_train_step(const facl_train_step_args* args, void* stream);
  * facl_timing_collect: synchronises on the recorded events, returns total ms / launches per tag and resets.
  * Tags: 3*layer + {0 forward, 1 weight-grad, 2 data-grad} for layer 0..8 (7 = netR_FC.3, 8 = mapping), then
  * 27 grouping, 28 fps, 29 weight packing, 30 BN finalize, 31 pooling misc, 32 max-pool scatter, 33 loss GEMMs,
- * 34 loss misc, 35 adam, 36 transposes, 37 memset/fill, 38 fused-L1 misc, 39..42 fused-L1 passes A, B, C, D.
+ * 34 loss misc, 35 adam, 36 transposes, 37 memset/fill, 38 fused-L1 misc, 39..42 fused-L1 passes A, B, C, D,
+ * 43 activation-image conversion.
  * facl_launch_count: kernels launched so far. */
-#define FACL_NUM_TIMING_TAGS 43
+#define FACL_NUM_TIMING_TAGS 44
 FACL_API void facl_timing_enable(int on);
 FACL_API int facl_timing_collect(float* ms_per_tag, int* count_per_tag, int ntags);
 FACL_API long long facl_launch_count(void);

@@ -245,3 +245,72 @@ def test_gemm_xt4(nsplit):
     torch.cuda.synchronize()
     want = (_bf16_round(W) @ _bf16_round(X).t()) if nsplit == 1 else W.double() @ X.double().t()
     _report("xt4", out, want, 2e-5 if nsplit == 1 else 1e-4)
+
+
+@pytest.mark.parametrize("nsplit", [1, 3])
+@pytest.mark.parametrize("Cout,Cin,R", [(256, 259, 1024), (512, 256, 640), (128, 64, 200)])
+def test_gemm_activation_images(nsplit, Cout, Cin, R):
+    """TMA-only GEMMs over pre-converted activation images (gemm_img.cu): forward (reduction over channels, with the
+    BN+ReLU transform, statistics and max-pool epilogue) and weight gradient (reduction over rows, split-K)."""
+    g = torch.Generator().manual_seed(Cout + Cin + R + nsplit)
+    W = torch.randn(Cout, Cin, generator=g) / Cin ** 0.5
+    z = torch.randn(Cin, R, generator=g)
+    s0, s2 = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g) * 0.3
+    lo = torch.zeros(Cin)
+    bias = torch.randn(Cout, generator=g)
+    h = torch.maximum(z.double() * s0.double()[:, None] + s2.double()[:, None], lo.double()[:, None])
+    hq = _bf16_round(h.float()) if nsplit == 1 else h
+    Wq = _bf16_round(W) if nsplit == 1 else W.double()
+    zd = z.to(DEV)
+    himg = ops.act_image(Cin, R, nsplit, src0=zd, ld=R, s0=s0.to(DEV), s2=s2.to(DEV), lo=lo.to(DEV))
+    wimg = ops.pack_weight(W.to(DEV), Cout, Cin, Cin, 1)
+    pool = 8
+    P = ops.stat_partials(Cout, R)
+    out = torch.full((Cout, R), float("nan"), device=DEV)
+    stats = torch.zeros((P, Cout, 2), device=DEV)
+    pooled = torch.full((Cout, R // pool), float("nan"), device=DEV)
+    parg = torch.zeros((Cout, R // pool), dtype=torch.uint8, device=DEV)
+    sign = torch.ones(Cout, device=DEV)
+    ops.gemm_tc(Cout, R, Cin, nsplit=nsplit, a_packed=wimg, b_mode=ops.B_IMAGE_MN, b_img=himg, bias=bias.to(DEV),
+                out_mode=ops.OUT_CHMAJOR, out=out, ldo=R, stats=stats, pool=pool, pool_sign=sign, pool_out=pooled,
+                pool_arg=parg, ldp=R // pool)
+    torch.cuda.synchronize()
+    want = Wq.double() @ hq.double() + bias.double()[:, None]
+    tol = 2e-5 if nsplit == 1 else 1e-4
+    _report("fwd", out, want, tol)
+    _report("stats0", stats.sum(0)[:, 0:1], want.sum(1, keepdim=True), 1e-4)
+    wp = want.reshape(Cout, R // pool, pool)
+    _report("pooled", pooled, wp.max(2).values, tol)
+    got_arg = parg.cpu().long()
+    picked = torch.gather(out.cpu().double().reshape(Cout, R // pool, pool), 2, got_arg[..., None])[..., 0]
+    assert torch.equal(picked.float(), pooled.cpu())
+    # weight gradient: dW[co][ci] = sum_r dz[co][r] h[ci][r], dz = c0*dy + c1*zz + c2 (two-source transform)
+    dy, zz = torch.randn(Cout, R, generator=g), torch.randn(Cout, R, generator=g)
+    c0, c1, c2 = (torch.randn(Cout, generator=g) for _ in range(3))
+    dz = dy.double() * c0.double()[:, None] + zz.double() * c1.double()[:, None] + c2.double()[:, None]
+    dzimg = ops.act_image(Cout, R, nsplit, src0=dy.to(DEV), src1=zz.to(DEV), ld=R, s0=c0.to(DEV), s1=c1.to(DEV), s2=c2.to(DEV))
+    dW = torch.zeros((Cout, Cin), device=DEV)
+    ops.gemm_tc(Cout, Cin, R, nsplit=nsplit, a_img=dzimg, b_mode=ops.B_IMAGE_K, b_img=himg, ksplit=min(3, (R + 63) // 64),
+                out_mode=ops.OUT_ATOMIC, out=dW, ldo=Cin)
+    torch.cuda.synchronize()
+    dzq = _bf16_round(dz.float()) if nsplit == 1 else dz
+    _report("wgrad", dW, dzq.double() @ hq.double().t(), tol * 5)
+
+
+def test_act_image_pooled_source():
+    """dz image of a max-pooled gradient read through the argmax table == image of the dense scatter."""
+    g = torch.Generator().manual_seed(5)
+    Cc, groups, pool = 64, 24, 16
+    R = groups * pool
+    df = torch.randn(Cc, groups, generator=g)
+    arg = torch.randint(0, pool, (Cc, groups), generator=g, dtype=torch.uint8)
+    z = torch.randn(Cc, R, generator=g)
+    c0, c1, c2 = (torch.randn(Cc, generator=g) for _ in range(3))
+    dense = torch.zeros(Cc, groups, pool)
+    dense.scatter_(2, arg.long()[..., None], df[..., None])
+    dense = dense.reshape(Cc, R)
+    kw = dict(s0=c0.to(DEV), s1=c1.to(DEV), s2=c2.to(DEV))
+    a = ops.act_image(Cc, R, 3, src0=df.to(DEV), src1=z.to(DEV), ld=groups, ld1=R, pool_arg=arg.to(DEV), pool=pool, **kw)
+    b = ops.act_image(Cc, R, 3, src0=dense.to(DEV), src1=z.to(DEV), ld=R, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(a.buf, b.buf)
