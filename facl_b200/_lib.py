@@ -106,7 +106,7 @@ SIGNATURES = {
     "facl_timing_enable": (None, [_I]),
     "facl_timing_collect": (_I, [_P, _P, _I]),
     "facl_launch_count": (C.c_longlong, []),
-    "facl_debug_l1_dump": (None, [_P, _P, _P]),
+    "facl_debug_l1_dump": (None, [_P, _P]),
     "facl_contrast_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "facl_contrast_losses": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
 }

@@ -85,7 +85,7 @@ class _EncoderBase(nn.Module):
     def _flags(self, training, need_bwd):
         from ._lib import ENC_FUSED_L1
         K, S = self.knn_K, self.sample_num_level1
-        ok = (S * K) % 128 == 0 and K in (32, 64)              # tile geometry of the fused kernels
+        ok = (S * K) % 128 == 0 and K == 64                    # tile geometry of the fused kernels (tile = max-pool group)
         return ENC_FUSED_L1 if (self.fused_l1 and ok) else 0
 
     def _workspace(self, dims, device, backward):

@@ -30,12 +30,12 @@ const float BN_EPS = 1e-5f, BN_MOM = 0.1f;
 enum Buf {
     B_Z1, B_Z2, B_Z3, B_ARG3, B_PCAT, B_Z4, B_Z5, B_Z6, B_ARG6, B_PALL, B_ARGG, B_Z7, B_BN, B_VEC, B_STATS, B_WPACK,
     B_IMG_H3, B_IMG_H4, B_IMG_H5,
-    B_DXT, B_DH7, B_DF, B_DY6, B_DH5, B_DH4, B_DP3, B_DY3, B_DH2, B_DH1, B_XTT, B_WPACKT, B_IMG_DZ,
+    B_DXT, B_DH7, B_DF, B_DY6, B_DH5, B_DH4, B_DP3, B_DY3, B_DH2, B_DH1, B_XTT, B_WPACKT, B_IMG_DZ, B_L1S,
     NUM_BUFS
 };
 const char* BUF_NAMES[NUM_BUFS] = {"z1", "z2", "z3", "arg3", "pcat", "z4", "z5", "z6", "arg6", "pall", "argg", "z7", "bn", "vec",
                                    "stats", "wpack", "img_h3", "img_h4", "img_h5", "dxt", "dh7", "df", "dy6", "dh5", "dh4", "dp3", "dy3", "dh2", "dh1", "xtt",
-                                   "wpackt", "img_dz"};
+                                   "wpackt", "img_dz", "l1s"};
 const int FIRST_BWD_BUF = B_DXT;
 
 // forward weight images: layers 0..6, then fc3 (512x1024), then mapping (64x512)
@@ -59,6 +59,11 @@ size_t wpackt_offset(int idx) {   // idx 1..6 layers, 7 = fc3^T, 8 = end
     return off;
 }
 
+// scratch of the fused net3DV_1 backward: 64x64 accumulators (floats), then three packed 64x64 operand images
+enum : int { L1S_H2 = 0, L1S_S2 = 4096, L1S_H1 = 4160, L1S_S1 = 8256, L1S_DW2S = 8320, L1S_ACC_END = 12416, L1S_Q3 = 12416,
+             L1S_Q2 = 12480 };
+const size_t L1S_IMG_OFF = 65536, L1S_BYTES = 65536 + 3 * 32768;
+
 // net3DV_3 runs on pre-converted activation images (gemm_img.cu) whenever a pooling group is a whole number of chunks
 bool use_images(const facl_encoder_dims* d) { return d->S % 8 == 0; }
 
@@ -66,7 +71,7 @@ size_t buffer_bytes(int i, const facl_encoder_dims* d) {
     const size_t M = d->M, R3 = (size_t)d->M * d->S, R1 = R3 * d->K, B = d->M / d->G, MB = M + B, f = sizeof(float);
     if (d->flags & FACL_ENC_FUSED_L1) {   // no per-row activation is stored: only dh2 (pass C -> pass D) and small scratch
         switch (i) {
-            case B_Z1: case B_Z2: case B_Z3: case B_ARG3: case B_DY3: case B_XTT: return 256;
+            case B_Z1: case B_Z2: case B_Z3: case B_DY3: case B_XTT: return 256;
             case B_DH1: return (size_t)4 * kNumSMs * 64 * 4 * f;
             default: break;
         }
@@ -94,6 +99,7 @@ size_t buffer_bytes(int i, const facl_encoder_dims* d) {
         case B_IMG_H4: return use_images(d) ? 2 * act_image_half_bytes(256, (long long)R3) : 256;
         case B_IMG_H5: return use_images(d) ? 2 * act_image_half_bytes(512, (long long)R3) : 256;
         case B_IMG_DZ: return use_images(d) ? 2 * act_image_half_bytes(1024, (long long)R3) : 256;
+        case B_L1S: return L1S_BYTES;
     }
     return 0;
 }
@@ -223,14 +229,15 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
         const int grid = l1_fused_grid(R1);
         if (tr)
             RUN(l1_fwd_launch(false, xt, R1, K, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), p->layer[1].b, nullptr,
-                              nullptr, nullptr, nullptr, nullptr, stats, nullptr, 0, st));
+                              nullptr, nullptr, nullptr, nullptr, stats, nullptr, nullptr, 0, st));
         {
             const facl_layer& L = p->layer[1];
             RUN(bn_finalize_launch(stats, 2 * grid, 64, (double)R1, L.gamma, L.beta, L.running_mean, L.running_var, BN_EPS, BN_MOM,
                                    tr, s1.mean, s1.rstd, s1.scale, s1.shift, st));
         }
         RUN(l1_fwd_launch(true, xt, R1, K, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), p->layer[1].b, s1.scale,
-                          s1.shift, wp + wpack_offset(2), p->layer[2].b, p->layer[2].gamma, F(B_STATS), F(B_PCAT) + 3 * R3, R3, st));
+                          s1.shift, wp + wpack_offset(2), p->layer[2].b, p->layer[2].gamma, F(B_STATS), F(B_PCAT) + 3 * R3,
+                          tr ? U(B_ARG3) : nullptr, R3, st));
         {
             Slot s2 = bn_slot(bufs, 2);
             const facl_layer& L = p->layer[2];
@@ -502,18 +509,25 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
     }
     if (d->flags & FACL_ENC_FUSED_L1) {
         // ---- L1 fused backward: activations recomputed from the 16-byte input rows (l1_fused.cu) ------------------------
-        if ((R1 % 128) != 0 || (K != 32 && K != 64)) return (int)cudaErrorInvalidValue;
+        if ((R1 % 64) != 0 || K != 64) return (int)cudaErrorInvalidValue;
         const uint8_t* wp = reinterpret_cast<const uint8_t*>(bufs[B_WPACK]);   // forward images of this step's weights
         const double* mom = reinterpret_cast<const double*>(vec + 1984);
         const facl_layer &L0 = p->layer[0], &L1 = p->layer[1], &L2 = p->layer[2];
         const int P = 2 * l1_bwd_grid(R1);
-        RUN(l1_bwd_c_launch(xt, R1, K, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), L1.b, s1.scale, s1.shift,
-                            wp + wpack_offset(2), L2.b, L2.gamma, F(B_PCAT) + 3 * R3, F(B_DP3), R3, s2.c0, s2.c1, s2.c2, F(B_DH2),
-                            gr->dw[2], stats, st));
+        float* acc = F(B_L1S);
+        uint8_t* imgs = reinterpret_cast<uint8_t*>(bufs[B_L1S]) + L1S_IMG_OFF;   // P3 | P2 | diag(e0) W2
+        FACL_CHECK(cudaMemsetAsync(acc, 0, sizeof(float) * L1S_ACC_END, st));
+        RUN(l1_prep_launch(L2.w, 256, s2.c1, L2.b, s2.c2, nullptr, imgs, acc + L1S_Q3, nullptr, st));
+        RUN(l1_bwd_c_launch(xt, R1, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), L1.b, s1.scale, s1.shift,
+                            wp + wpack_offset(2), imgs, acc + L1S_Q3, U(B_ARG3), F(B_DP3), R3, s2.c0, bufs[B_DH2], gr->dw[2],
+                            acc + L1S_H2, acc + L1S_S2, stats, st));
         RUN(bwd_finalize(1, 1, 64, (int)R1, (double)R1, P, 0));
-        RUN(l1_bwd_d_launch(xt, R1, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), L1.b, s1.c0, s1.c1, s1.c2, F(B_DH2),
-                            gr->dw[1], F(B_DH1), stats, st));
+        RUN(l1_fin_launch(L2.w, 256, s2.c1, L2.b, s2.c2, acc + L1S_H2, acc + L1S_S2, nullptr, nullptr, gr->dw[2], 1, st));
+        RUN(l1_prep_launch(L1.w, 64, s1.c1, L1.b, s1.c2, s1.c0, imgs + 32768, acc + L1S_Q2, imgs + 65536, st));
+        RUN(l1_bwd_d_launch(xt, R1, ns, L0.w, L0.b, s0.scale, s0.shift, imgs + 65536, imgs + 32768, acc + L1S_Q2, bufs[B_DH2],
+                            acc + L1S_DW2S, acc + L1S_H1, acc + L1S_S1, F(B_DH1), stats, st));
         RUN(bwd_finalize(0, 0, 64, (int)R1, (double)R1, P, 0));
+        RUN(l1_fin_launch(L1.w, 64, s1.c1, L1.b, s1.c2, acc + L1S_H1, acc + L1S_S1, s1.c0, acc + L1S_DW2S, gr->dw[1], 0, st));
         RUN(l1_dw1_launch(F(B_DH1), P, mom, L0.w, L0.b, s0.c0, s0.c1, s0.c2, gr->dw[0], st));
         return 0;
     }

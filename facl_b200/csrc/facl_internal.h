@@ -68,15 +68,19 @@ namespace facl {
 // l1_fused.cu
 int l1_fused_grid(long long R);
 int l1_bwd_grid(long long R);
-void l1_set_debug_dump(unsigned char* mask1, unsigned char* mask2, unsigned char* arg);
-int l1_bwd_c_launch(const float* xt, long long R, int K, int nsplit, const float* w1, const float* b1, const float* scale1,
+void l1_set_debug_dump(unsigned char* mask1, unsigned char* mask2);
+int l1_prep_launch(const float* W, int C, const float* d, const float* bias, const float* c2, const float* e0, void* p_img, float* q,
+                   void* e_img, cudaStream_t st);
+int l1_fin_launch(const float* W, int C, const float* d, const float* bias, const float* c2, const float* H, const float* s,
+                  const float* e0, const float* sparse, float* dW, int accumulate, cudaStream_t st);
+int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1,
                     const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
-                    const void* w3_img, const float* b3, const float* gamma3, const float* pooled, const float* dpooled,
-                    long long ldp, const float* c3_0, const float* c3_1, const float* c3_2, float* dh2, float* dw3, float* stats,
+                    const void* w3_img, const void* p3_img, const float* q3, const unsigned char* arg, const float* dpooled,
+                    long long ldp, const float* c3_0, void* dh2, float* dw3, float* gram, float* hsum, float* stats,
                     cudaStream_t st);
 int l1_bwd_d_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1,
-                    const float* shift1, const void* w2_img, const float* b2, const float* c2_0, const float* c2_1,
-                    const float* c2_2, const float* dh2, float* dw2, float* amat, float* stats, cudaStream_t st);
+                    const float* shift1, const void* e0w2_img, const void* p2_img, const float* q2, const void* dh2, float* dw2s,
+                    float* gram, float* hsum, float* amat, float* stats, cudaStream_t st);
 int l1_dw1_launch(const float* amat, int P, const double* mom14, const float* w1, const float* b1, const float* c0, const float* c1,
                   const float* c2, float* dw1, cudaStream_t st);
 int l1_moments_launch(const float* xt, long long R, double* mom14, cudaStream_t st);
@@ -85,6 +89,6 @@ int l1_bn1_launch(const double* mom14, double n, const float* w1, const float* b
                   float* scale, float* shift, cudaStream_t st);
 int l1_fwd_launch(bool pass_b, const float* xt, long long R, int K, int nsplit, const float* w1, const float* b1, const float* scale1,
                   const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
-                  const void* w3_img, const float* b3, const float* gamma3, float* stats, float* pooled, long long ldp,
-                  cudaStream_t st);
+                  const void* w3_img, const float* b3, const float* gamma3, float* stats, float* pooled, unsigned char* pool_arg,
+                  long long ldp, cudaStream_t st);
 }  // namespace facl

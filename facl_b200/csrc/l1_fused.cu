@@ -48,6 +48,7 @@ struct L1Params {
     const float* gamma3;      // sign decides max vs min
     float* stats;             // pass A: [2*grid][64][2], pass B: [grid][256][2]
     float* pooled;            // pass B: [256][ldp]  selected pre-BN value per (channel, group)
+    unsigned char* pool_arg;  // pass B: [256][ldp]  position of the winner inside its group (first hit), or null
     long long ldp;
 };
 
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l1_fwd_kernel(const L1Params p) {
                 mbar_wait(&d3_full[h], it & 1);
                 tc_fence_after_sync();
                 float best = -INFINITY;
+                int barg = 0;
 #pragma unroll 1
                 for (int q = 0; q < TILE / 32; ++q) {
                     float v[32];
@@ -284,23 +286,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) l1_fwd_kernel(const L1Params p) {
                         for (int i = 0; i < 32; ++i) {
                             s_acc += v[i];
                             q_acc = fmaf(v[i], v[i], q_acc);
-                            best = fmaxf(best, v[i] * sgn);
+                            const float sv = v[i] * sgn;
+                            barg = (sv > best) ? (q * 32 + i) : barg;
+                            best = fmaxf(best, sv);
                         }
                         if (((q + 1) * 32) % K == 0) {
                             const long long g = t * groups + (q * 32) / K;
                             p.pooled[(long long)c * p.ldp + g] = fmaf(best, sgn, b3);
+                            if (p.pool_arg) p.pool_arg[(long long)c * p.ldp + g] = (unsigned char)(barg & (K - 1));
                             best = -INFINITY;
+                            barg = (q + 1) * 32;
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             s_acc += v[i];
                             q_acc = fmaf(v[i], v[i], q_acc);
-                            best = fmaxf(best, v[i] * sgn);
+                            const float sv = v[i] * sgn;
+                            barg = (sv > best) ? i : barg;
+                            best = fmaxf(best, sv);
                             if (((i + 1) & (K - 1)) == 0) {
                                 const long long g = t * groups + (q * 32 + i) / K;
                                 p.pooled[(long long)c * p.ldp + g] = fmaf(best, sgn, b3);
+                                if (p.pool_arg) p.pool_arg[(long long)c * p.ldp + g] = (unsigned char)(barg & (K - 1));
                                 best = -INFINITY;
+                                barg = i + 1;
                             }
                         }
                     }
@@ -327,46 +337,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) l1_fwd_kernel(const L1Params p) {
 
 // =====================================================================================================================
 // Backward of net3DV_1.  Activations are RECOMPUTED from the 16-byte input rows (cheaper than storing 384 fp32 per row);
-// tiles are 64 batch rows.  All images are [channel][64 rows] (see above): the same bytes serve as an MN-major B
-// operand (reduction over channels: forward and data-gradient GEMMs) and as a K-major operand (reduction over rows:
-// weight-gradient GEMMs).
+// tiles are 64 batch rows = one max-pool group (K = 64).  All images are [channel][64 rows] (see above): the same bytes
+// serve as an MN-major B operand (reduction over channels) and as a K-major operand (reduction over rows).
 //
-//   pass C : x -> h1 -> z2 -> h2 -> z3;  dz3 = c0*dy3 + c1*z3 + c2 with dy3 = the pooled gradient placed at the max-pool
-//            winner (first row whose z3 equals the pooled value);  dW3 += dz3 h2^T (TMEM-resident over the whole
-//            kernel);  dh2 = W3^T dz3, masked by ReLU2 -> written to HBM (64 x R fp32, 64-row blocks) with the BN2
-//            backward sums.
-//   pass D : x -> h1 -> z2;  dz2 = c0*dh2' + c1*z2 + c2;  dW2 += dz2 h1^T (TMEM-resident);  dh1 = W2^T dz2 masked by
-//            ReLU1 -> BN1 backward sums and A = sum dh1' x^T (64x4); nothing per-row is written.
-//   dW1 follows in closed form from A and the input moments (z1 is affine in x).
+// The BatchNorm-backward map dz = c0*dy + c1*z + c2 is affine in z, and z is linear in the layer input, so the DENSE
+// part of every gradient collapses onto 64x64 matrices and never needs z3 (256 channels) again:
+//
+//   dz3 = k1 (.) z3 + k2 + Sp          Sp[c][r] = k0[c] dP[c][g] at the max-pool winner r = arg[c][g] (pass B records it)
+//   dh2 = W3^T dz3 = P3 h2 + q3 + W3^T Sp            P3 = W3^T diag(k1) W3,   q3 = W3^T (k1 (.) b3 + k2)
+//   dW3 = dz3 h2^T = diag(k1) W3 H2 + (k1 (.) b3 + k2) s2^T + Sp h2^T            H2 = sum h2 h2^T,  s2 = sum h2
+//   dz2 = e0 (.) dh2' + e1 (.) z2 + e2               dh2' = dh2 masked by ReLU2
+//   dh1 = W2^T dz2 = (diag(e0) W2)^T dh2' + P2 h1 + q2        P2 = W2^T diag(e1) W2,   q2 = W2^T (e1 (.) b2 + e2)
+//   dW2 = diag(e0) (dh2' h1^T) + diag(e1) (W2 H1 + b2 s1^T) + e2 s1^T            H1 = sum h1 h1^T,  s1 = sum h1
+//
+//   pass C : x -> h1 -> z2 -> h2;  Sp image (one non-zero per channel);  TMEM: dh2 = W3^T Sp + P3 h2,  dW3s += Sp h2^T,
+//            H2 += h2 h2^T;  dh2' -> HBM as a bf16 hi/lo image (+ the BN2-backward sums).
+//   pass D : x -> h1;  dh2' image by bulk TMA;  TMEM: dh1 = (E0 W2)^T dh2' + P2 h1,  dW2s += dh2' h1^T,  H1 += h1 h1^T;
+//            dh1 masked by ReLU1 -> BN1-backward sums and A = sum dh1' x^T (64x4); nothing per-row is written.
+//   l1_prep / l1_fin : the 64x64 matrix algebra around the passes;  dW1 follows in closed form from A and the moments.
 // =====================================================================================================================
 constexpr int BT = 64;                    // batch rows per backward tile
 constexpr int IMG64 = 8192;               // [64 ch][64 rows] bf16 image (one half)
-constexpr int BWD_THREADS = 17 * 32;
 
 struct L1BwdParams {
     const float* xt;
     long long R;
-    int K, nhl;
+    int nhl;
+    int tiles_per_cta;        // contiguous tile range per CTA (multiple of 4)
     const float* w1;  const float* b1;  const float* scale1;  const float* shift1;
-    const uint8_t* w2_img;  const float* b2;  const float* scale2;  const float* shift2;
-    const uint8_t* w3_img;  const float* b3;
     // pass C
-    const float* pooled;      // [256][ldp] forward max-pool values (selected z3)
+    const uint8_t* w2_img;  const float* b2;  const float* scale2;  const float* shift2;
+    const uint8_t* w3_img;
+    const uint8_t* p3_img;    // packed image of P3 (64x64)
+    const float* q3;          // [64]
+    const unsigned char* arg; // [256][ldp] max-pool winner inside its group (pass B)
     const float* dpooled;     // [256][ldp] gradient w.r.t. the pooled BN3 output, ReLU-masked
     long long ldp;
-    const float* c3_0; const float* c3_1; const float* c3_2;   // BN3 backward coefficients (slot 2)
-    const float* gamma3;
-    float* dh2;               // [R/64][64][64] masked gradient w.r.t. relu(bn2(z2))    (pass C out, pass D in)
-    float* dw3;               // [256][64]  += (atomic)
+    const float* c3_0;        // BN3 backward coefficient c0 (slot 2)
+    uint8_t* dh2;             // [R/64][hi 8 KB | lo 8 KB] image of the masked gradient w.r.t. relu(bn2(z2))  (C out, D in)
+    float* dw3;               // [256][64]  += Sp h2^T (atomic)
+    float* gram;              // [64][64]   += H2 (pass C) / H1 (pass D)
+    float* hsum;              // [64]       += s2 / s1
     // pass D
-    const float* c2_0; const float* c2_1; const float* c2_2;   // BN2 backward coefficients (slot 1)
-    float* dw2;               // [64][64] += (atomic)
-    float* amat;              // [grid][64][4] per-CTA sum dh1' x^T
-    float* stats;             // pass C: [2*grid][64][2] (sum dh2', sum dh2' z2); pass D: [2*grid][64][2] (sum dh1', sum dh1' z1)
-    // optional test hooks (pass C): the discrete decisions of the recomputed forward, so a checker can impose them
+    const uint8_t* e0w2_img;  // packed image of diag(e0) W2
+    const uint8_t* p2_img;    // packed image of P2
+    const float* q2;          // [64]
+    float* dw2s;              // [64][64] += dh2' h1^T (atomic)
+    float* amat;              // [2*grid][64][4] per-CTA sum dh1' x^T
+    float* stats;             // [2*grid][64][2]: pass C (sum dh2', sum dh2' z2); pass D (sum dh1', sum dh1' z1)
+    // optional test hooks (pass C): the ReLU decisions of the recomputed forward, so a checker can impose them
     unsigned char* dbg_mask1; // [R/64][64][64]  h1 > 0
     unsigned char* dbg_mask2; // [R/64][64][64]  h2 > 0
-    unsigned char* dbg_arg;   // [256][ldp]      max-pool winner inside its group
 };
 
 __device__ __forceinline__ void store_img8(uint8_t* img, int nhl, int img_bytes, int row, int chunk, const float (&v)[8]) {
@@ -383,12 +404,12 @@ __device__ __forceinline__ void store_img8(uint8_t* img, int nhl, int img_bytes,
 
 // D (+)= A(K-major weight image, 64-wide K) * B(MN-major [64 ch][64 rows] image): reduction over the 64 channels
 __device__ __forceinline__ void mma_w_act64(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int nhl,
-                                            uint32_t idesc) {
+                                            uint32_t idesc, bool first) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
         const uint64_t ad = umma_desc_sw128(a_hi + ks * 32);
         const uint64_t bd = umma_desc_mn_sw128(b_hi + ks * 2048, 8192, 1024);
-        umma_bf16_ss(d, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        umma_bf16_ss(d, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
         if (nhl == 2) {
             umma_bf16_ss(d, ad, umma_desc_mn_sw128(b_lo + ks * 2048, 8192, 1024), idesc, 1u);
             umma_bf16_ss(d, umma_desc_sw128(a_lo + ks * 32), bd, idesc, 1u);
@@ -408,10 +429,26 @@ __device__ __forceinline__ void mma_rows64(uint32_t d, uint32_t a_hi, uint32_t a
         }
     }
 }
+// D (+)= A^T (image [K ch][M], read MN-major) * B(MN-major [K ch][64 rows] image): reduction over `ksteps`*16 channels.
+// a_lbo = distance to the second 64 of M (garbage lanes 64..127 when the image has 64 columns).
+__device__ __forceinline__ void mma_t_act(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uint32_t b_hi, uint32_t b_lo,
+                                          int ksteps, int nhl, uint32_t idesc, bool first) {
+#pragma unroll 1
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t ad = umma_desc_mn_sw128(a_hi + ks * 2048, a_lbo, 1024);
+        const uint64_t bd = umma_desc_mn_sw128(b_hi + ks * 2048, 8192, 1024);
+        umma_bf16_ss(d, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+        if (nhl == 2) {
+            umma_bf16_ss(d, ad, umma_desc_mn_sw128(b_lo + ks * 2048, 8192, 1024), idesc, 1u);
+            umma_bf16_ss(d, umma_desc_mn_sw128(a_lo + ks * 2048, a_lbo, 1024), bd, idesc, 1u);
+        }
+    }
+}
 
-// producer shared by both backward passes: thread = channel (2 threads per channel, 32 rows each)
-__device__ __forceinline__ void produce_h1_tile64(const float4* xtile, uint8_t* img, int nhl, int ch, int half, float wx, float wy,
-                                                  float wz, float ww, float bf) {
+// producer shared by both backward passes: thread = channel (2 threads per channel, 32 rows each); returns sum of h1
+__device__ __forceinline__ float produce_h1_tile64(const float4* xtile, uint8_t* img, int nhl, int ch, int half, float wx, float wy,
+                                                   float wz, float ww, float bf) {
+    float acc = 0.f;
 #pragma unroll 2
     for (int q = 0; q < 4; ++q) {
         float v[8];
@@ -419,19 +456,21 @@ __device__ __forceinline__ void produce_h1_tile64(const float4* xtile, uint8_t* 
         for (int e = 0; e < 8; ++e) {
             float4 x = xtile[half * 32 + q * 8 + e];
             v[e] = fmaxf(fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf)))), 0.f);
+            acc += v[e];
         }
         store_img8(img, nhl, IMG64, ch, half * 4 + q, v);
     }
+    return acc;
 }
 
 // --------------------------------------------------------------------------------------------------------------------
 // pass C   (22 warps)
-// warps 0-7         : z3 consumers (thread = channel c)
-// warps 8,9,12,13   : z2 -> h2 image            warps 16,17,20,21 : dh2 consumers      (thread = channel j, TMEM lanes 0..63)
-// warps 10,11,14,15 : x -> h1 image producers   warp 18 : MMA issuer (warp 19 idles)
-// TMEM columns: D2[b] 0/64, D3[h] 128/192, DH2 256, DW3[h] 320/384
-// The MMA issue order is software-pipelined -- z3(it+1) is issued before the gradient GEMMs of tile it -- so the z3
-// consumers (the longest role) always have the next accumulator waiting.
+// warps 0-7         : Sp producers (thread = channel c): one bf16 hi/lo pair per tile; flush dW3s at the end
+// warps 8,9,12,13   : z2 -> h2 image (thread = channel j, TMEM lanes 0..63); flush H2 / s2 at the end
+// warps 10,11,14,15 : x -> h1 image producers
+// warps 16,17,20,21 : dh2 consumers (thread = channel j): + q3, ReLU2 mask, BN2-backward sums, image -> HBM
+// warp 18           : MMA issuer (warp 19 idles)
+// TMEM columns: D2[b] 0/64, DH2[b] 128/192, DW3s[h] 256/320, H2 384
 // --------------------------------------------------------------------------------------------------------------------
 constexpr int C_THREADS = 22 * 32;
 
@@ -441,39 +480,41 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     const int nhl = p.nhl;
     uint8_t* w2s = smem;                       // hi 8 KB | lo 8 KB
     uint8_t* w3s = w2s + 16384;                // [half][hi 16 KB | lo 16 KB]
-    uint8_t* h1s = w3s + 65536;                // 2 stages x (hi 8 KB | lo 8 KB)
-    uint8_t* h2s = h1s + 2 * 2 * IMG64;        // 2 stages x (hi | lo)
-    uint8_t* dzs = h2s + 2 * 2 * IMG64;        // [256 c][64 r]: hi 32 KB | lo 32 KB
-    uint8_t* xs = dzs + 65536;                 // 2 stages x 64 rows x 16 B
+    uint8_t* p3s = w3s + 65536;                // hi 8 KB | lo 8 KB
+    uint8_t* h1s = p3s + 16384;                // hi 8 KB | lo 8 KB (single stage)
+    uint8_t* h2s = h1s + 2 * IMG64;            // 2 stages x (hi | lo)
+    uint8_t* sps = h2s + 2 * 2 * IMG64;        // Sp [256 c][64 r]: hi 32 KB | lo 32 KB
+    uint8_t* xs = sps + 65536;                 // 2 stages x 64 rows x 16 B
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * BT * 16);
-    uint64_t *h1_full = bars, *h1_empty = bars + 2, *d2_full = bars + 4, *d2_empty = bars + 6, *h2_full = bars + 8,
-             *h2_empty = bars + 10, *d3_full = bars + 12, *d3_empty = bars + 14, *dz_full = bars + 16, *dz_empty = bars + 17,
-             *dh_full = bars + 18, *dh_empty = bars + 19, *w_bar = bars + 20, *fin_bar = bars + 21;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    uint64_t *h1_full = bars, *h1_empty = bars + 1, *d2_full = bars + 2, *d2_empty = bars + 4, *h2_full = bars + 6,
+             *h2_empty = bars + 8, *sp_full = bars + 10, *sp_empty = bars + 11, *dh_full = bars + 12, *dh_empty = bars + 14,
+             *w_bar = bars + 16, *fin_bar = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = p.R / BT;
-    const int my_tiles = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA (grid <= ntiles)
+    const long long t0 = (long long)blockIdx.x * p.tiles_per_cta;
+    const int my_tiles = (int)((ntiles - t0 < p.tiles_per_cta) ? (ntiles - t0) : p.tiles_per_cta);   // > 0 by the launch
 
     if (threadIdx.x == 0) {
+        mbar_init(h1_full, 4);
+        mbar_init(h1_empty, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&h1_full[i], 4);
-            mbar_init(&h1_empty[i], 1);
             mbar_init(&d2_full[i], 1);
             mbar_init(&d2_empty[i], 8);        // h2 producers + dh2 consumers both read z2
             mbar_init(&h2_full[i], 4);
             mbar_init(&h2_empty[i], 1);
-            mbar_init(&d3_full[i], 1);
-            mbar_init(&d3_empty[i], 4);
+            mbar_init(&dh_full[i], 1);
+            mbar_init(&dh_empty[i], 4);
         }
-        mbar_init(dz_full, 8);
-        mbar_init(dz_empty, 1);
-        mbar_init(dh_full, 1);
-        mbar_init(dh_empty, 4);
+        mbar_init(sp_full, 8);
+        mbar_init(sp_empty, 1);
         mbar_init(w_bar, 1);
         mbar_init(fin_bar, 1);
         mbar_fence_init();
     }
+    for (int i = threadIdx.x; i < 65536 / 16; i += C_THREADS) reinterpret_cast<uint4*>(sps)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
     if (warp == 18) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
@@ -483,113 +524,109 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc_mn = umma_idesc_bf16(128, BT) | UMMA_B_MN_MAJOR;                      // weights x activation image
-    const uint32_t idesc_dg = umma_idesc_bf16(128, BT) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;    // W3^T x dz3
+    const uint32_t idesc_dg = umma_idesc_bf16(128, BT) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;    // W3^T x Sp
     const uint32_t idesc_kk = umma_idesc_bf16(128, 64);                                        // reduction over rows
 
     if (warp == 18) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(w_bar, 8192u * nhl + 32768u * nhl);
+            mbar_arrive_expect_tx(w_bar, (8192u + 32768u + 8192u) * nhl);
             tma_bulk_g2s(w2s, p.w2_img, 8192, w_bar);
-            if (nhl == 2) tma_bulk_g2s(w2s + 8192, p.w2_img + 16384, 8192, w_bar);
+            tma_bulk_g2s(p3s, p.p3_img, 8192, w_bar);
+            if (nhl == 2) {
+                tma_bulk_g2s(w2s + 8192, p.w2_img + 16384, 8192, w_bar);
+                tma_bulk_g2s(p3s + 8192, p.p3_img + 16384, 8192, w_bar);
+            }
             for (int h = 0; h < 2; ++h) {
                 tma_bulk_g2s(w3s + h * 32768, p.w3_img + h * 32768, 16384, w_bar);
                 if (nhl == 2) tma_bulk_g2s(w3s + h * 32768 + 16384, p.w3_img + h * 32768 + 16384, 16384, w_bar);
             }
             mbar_wait(w_bar, 0);
             const uint32_t w2_hi = smem_u32(w2s), w2_lo = w2_hi + 8192;
-            const uint32_t dz_hi = smem_u32(dzs), dz_lo = dz_hi + 32768;
-            auto issue_mma2 = [&](int it) {        // z2(it) = W2 h1(it)
+            const uint32_t p3_hi = smem_u32(p3s), p3_lo = p3_hi + 8192;
+            const uint32_t h1 = smem_u32(h1s);
+            const uint32_t sp_hi = smem_u32(sps), sp_lo = sp_hi + 32768;
+            auto issue_z2 = [&](int it) {          // z2(it) = W2 h1(it)
                 const int b = it & 1, u = (it >> 1) & 1;
-                mbar_wait(&h1_full[b], u);
+                mbar_wait(h1_full, it & 1);
                 mbar_wait(&d2_empty[b], u ^ 1);
                 tc_fence_after_sync();
-                const uint32_t h1 = smem_u32(h1s + b * 2 * IMG64);
-                mma_w_act64(tmem_base + 64 * b, w2_hi, w2_lo, h1, h1 + IMG64, nhl, idesc_mn);
-                umma_commit(&h1_empty[b]);
+                mma_w_act64(tmem_base + 64 * b, w2_hi, w2_lo, h1, h1 + IMG64, nhl, idesc_mn, true);
+                umma_commit(h1_empty);
                 umma_commit(&d2_full[b]);
             };
-            auto issue_mma3 = [&](int it) {        // z3(it) = W3 h2(it)
-                const int b = it & 1, u = (it >> 1) & 1;
-                mbar_wait(&h2_full[b], u);
-                const uint32_t h2 = smem_u32(h2s + b * 2 * IMG64);
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    mbar_wait(&d3_empty[h], (it & 1) ^ 1);
-                    tc_fence_after_sync();
-                    const uint32_t w3_hi = smem_u32(w3s + h * 32768);
-                    mma_w_act64(tmem_base + 128 + 64 * h, w3_hi, w3_hi + 16384, h2, h2 + IMG64, nhl, idesc_mn);
-                    umma_commit(&d3_full[h]);
-                }
-            };
-            if (my_tiles > 0) issue_mma2(0);
-            if (my_tiles > 1) issue_mma2(1);
-            if (my_tiles > 0) issue_mma3(0);
+            issue_z2(0);
 #pragma unroll 1
             for (int it = 0; it < my_tiles; ++it) {
-                const int b = it & 1;
-                if (it + 2 < my_tiles) issue_mma2(it + 2);
-                if (it + 1 < my_tiles) issue_mma3(it + 1);
-                // dh2(it) = W3^T dz3(it) (reduction over the 256 channels); dW3 += dz3(it) h2(it)^T (reduction over the rows)
+                const int b = it & 1, u = (it >> 1) & 1;
+                if (it + 1 < my_tiles) issue_z2(it + 1);
                 const uint32_t h2 = smem_u32(h2s + b * 2 * IMG64);
-                mbar_wait(dz_full, it & 1);
-                mbar_wait(dh_empty, (it & 1) ^ 1);
+                mbar_wait(&h2_full[b], u);
+                mbar_wait(sp_full, it & 1);
+                mbar_wait(&dh_empty[b], u ^ 1);
                 tc_fence_after_sync();
+                // sparse products first, so the Sp image is free again while the dense ones run
 #pragma unroll 1
-                for (int ks = 0; ks < 16; ++ks) {
+                for (int ks = 0; ks < 16; ++ks) {   // dh2 = W3^T Sp: reduction over the 256 channels
                     const uint32_t wa = smem_u32(w3s + (ks >> 3) * 32768) + (ks & 7) * 2048;
                     const uint64_t a_hi = umma_desc_mn_sw128(wa, 16384, 1024), a_lo = umma_desc_mn_sw128(wa + 16384, 16384, 1024);
-                    const uint64_t b_hi = umma_desc_mn_sw128(dz_hi + ks * 2048, 8192, 1024);
-                    umma_bf16_ss(tmem_base + 256, a_hi, b_hi, idesc_dg, ks > 0 ? 1u : 0u);
+                    const uint64_t b_hi = umma_desc_mn_sw128(sp_hi + ks * 2048, 8192, 1024);
+                    umma_bf16_ss(tmem_base + 128 + 64 * b, a_hi, b_hi, idesc_dg, ks > 0 ? 1u : 0u);
                     if (nhl == 2) {
-                        umma_bf16_ss(tmem_base + 256, a_hi, umma_desc_mn_sw128(dz_lo + ks * 2048, 8192, 1024), idesc_dg, 1u);
-                        umma_bf16_ss(tmem_base + 256, a_lo, b_hi, idesc_dg, 1u);
+                        umma_bf16_ss(tmem_base + 128 + 64 * b, a_hi, umma_desc_mn_sw128(sp_lo + ks * 2048, 8192, 1024), idesc_dg, 1u);
+                        umma_bf16_ss(tmem_base + 128 + 64 * b, a_lo, b_hi, idesc_dg, 1u);
                     }
                 }
-                umma_commit(dh_full);
 #pragma unroll 1
-                for (int h = 0; h < 2; ++h)
-                    mma_rows64(tmem_base + 320 + 64 * h, dz_hi + h * 16384, dz_lo + h * 16384, h2, h2 + IMG64, nhl, idesc_kk, it == 0);
-                umma_commit(dz_empty);
+                for (int h = 0; h < 2; ++h)          // dW3s += Sp h2^T
+                    mma_rows64(tmem_base + 256 + 64 * h, sp_hi + h * 16384, sp_lo + h * 16384, h2, h2 + IMG64, nhl, idesc_kk, it == 0);
+                umma_commit(sp_empty);
+                mma_w_act64(tmem_base + 128 + 64 * b, p3_hi, p3_lo, h2, h2 + IMG64, nhl, idesc_mn, false);   // dh2 += P3 h2
+                umma_commit(&dh_full[b]);
+                mma_rows64(tmem_base + 384, h2, h2 + IMG64, h2, h2 + IMG64, nhl, idesc_kk, it == 0);           // H2 += h2 h2^T
                 umma_commit(&h2_empty[b]);
             }
             umma_commit(fin_bar);
         }
     } else if (warp == 10 || warp == 11 || warp == 14 || warp == 15) {
-        // ---- producers ----
+        // ---- x -> h1 producers ----
         const int pw = (warp == 10) ? 0 : (warp == 11) ? 1 : (warp == 14) ? 2 : 3;
         const int ptid = pw * 32 + lane, ch = ptid & 63, half = ptid >> 6;
         const float s1 = __ldg(p.scale1 + ch), t1 = __ldg(p.shift1 + ch);
         const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + ch);
         const float wx = s1 * w.x, wy = s1 * w.y, wz = s1 * w.z, ww = s1 * w.w, bf = fmaf(s1, __ldg(p.b1 + ch), t1);
-        int it = 0;
+        const float4* xg = reinterpret_cast<const float4*>(p.xt) + t0 * BT;
+        float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ptid < BT) xnext = __ldg(xg + ptid);
 #pragma unroll 1
-        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const int b = it & 1, u = (it >> 1) & 1;
-            float4* xtile = reinterpret_cast<float4*>(xs + b * BT * 16);
-            if (ptid < BT) xtile[ptid] = __ldg(reinterpret_cast<const float4*>(p.xt) + t * BT + ptid);
+        for (int it = 0; it < my_tiles; ++it) {
+            float4* xtile = reinterpret_cast<float4*>(xs + (it & 1) * BT * 16);
+            if (ptid < BT) {
+                xtile[ptid] = xnext;
+                if (it + 1 < my_tiles) xnext = __ldg(xg + (long long)(it + 1) * BT + ptid);
+            }
             named_bar_sync(1, 128);
-            mbar_wait(&h1_empty[b], u ^ 1);
-            produce_h1_tile64(xtile, h1s + b * 2 * IMG64, nhl, ch, half, wx, wy, wz, ww, bf);
+            mbar_wait(h1_empty, (it & 1) ^ 1);
+            produce_h1_tile64(xtile, h1s, nhl, ch, half, wx, wy, wz, ww, bf);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&h1_full[b]);
+            if (lane == 0) mbar_arrive(h1_full);
             if (p.dbg_mask1) {
                 for (int r = 0; r < 32; ++r) {
                     float4 x = xtile[half * 32 + r];
                     float v = fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf))));
-                    p.dbg_mask1[(t * 64 + ch) * 64 + half * 32 + r] = v > 0.f ? 1 : 0;
+                    p.dbg_mask1[((t0 + it) * 64 + ch) * 64 + half * 32 + r] = v > 0.f ? 1 : 0;
                 }
             }
         }
     } else if (warp == 8 || warp == 9 || warp == 12 || warp == 13) {
-        // ---- z2 -> h2 = relu(bn2(z2)) image (thread = channel j) ----
+        // ---- z2 -> h2 = relu(bn2(z2)) image (thread = channel j), s2 = sum h2 ----
         const int lg = warp & 1, colhalf = (warp >= 12) ? 1 : 0;
         const int j = lg * 32 + lane;
         const float a2 = __ldg(p.scale2 + j);
         const float c2 = fmaf(a2, __ldg(p.b2 + j), __ldg(p.shift2 + j));
-        int it = 0;
+        float hsum = 0.f;
 #pragma unroll 1
-        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
             mbar_wait(&d2_full[b], u);
             tc_fence_after_sync();
@@ -605,23 +642,38 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             for (int g8 = 0; g8 < 4; ++g8) {
                 float h[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) h[e] = fmaxf(fmaf(a2, z[g8 * 8 + e], c2), 0.f);
+                for (int e = 0; e < 8; ++e) {
+                    h[e] = fmaxf(fmaf(a2, z[g8 * 8 + e], c2), 0.f);
+                    hsum += h[e];
+                }
                 store_img8(img, nhl, IMG64, j, colhalf * 4 + g8, h);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&h2_full[b]);
+            if (p.dbg_mask2) {
+                for (int i = 0; i < 32; ++i)
+                    p.dbg_mask2[((t0 + it) * 64 + j) * 64 + colhalf * 32 + i] = fmaf(a2, z[i], c2) > 0.f ? 1 : 0;
+            }
         }
+        atomicAdd(p.hsum + j, hsum);
+        mbar_wait(fin_bar, 0);
+        tc_fence_after_sync();
+        float a[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(384 + colhalf * 32), a);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(p.gram + j * 64 + colhalf * 32 + i, a[i]);
     } else if (warp == 16 || warp == 17 || warp == 20 || warp == 21) {
-        // ---- dh2 consumers (thread = channel j): ReLU2 mask, BN2 backward sums, masked gradient -> HBM ----
+        // ---- dh2 consumers (thread = channel j): + q3, ReLU2 mask, BN2 backward sums, masked gradient image -> HBM ----
         const int lg = warp & 1, colhalf = (warp >= 20) ? 1 : 0;
         const int j = lg * 32 + lane;
         const float b2 = __ldg(p.b2 + j), a2 = __ldg(p.scale2 + j);
         const float c2 = fmaf(a2, b2, __ldg(p.shift2 + j));
+        const float q3 = __ldg(p.q3 + j);
         float s_acc = 0.f, q_acc = 0.f;
-        int it = 0;
 #pragma unroll 1
-        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
             mbar_wait(&d2_full[b], u);
             tc_fence_after_sync();
@@ -631,99 +683,81 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&d2_empty[b]);
-            mbar_wait(dh_full, it & 1);
+            mbar_wait(&dh_full[b], u);
             tc_fence_after_sync();
             float g[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + colhalf * 32), g);
+            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 + 64 * b + colhalf * 32), g);
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(dh_empty);
-            float* out = p.dh2 + (t * 64 + j) * 64 + colhalf * 32;
-            if (p.dbg_mask2) {
-                for (int i = 0; i < 32; ++i) p.dbg_mask2[(t * 64 + j) * 64 + colhalf * 32 + i] = fmaf(a2, z[i], c2) > 0.f ? 1 : 0;
-            }
+            if (lane == 0) mbar_arrive(&dh_empty[b]);
+            uint8_t* out = p.dh2 + (t0 + it) * (2 * IMG64);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float v = (fmaf(a2, z[i], c2) > 0.f) ? g[i] : 0.f;
-                s_acc += v;
-                q_acc = fmaf(v, z[i] + b2, q_acc);
-                g[i] = v;
-            }
+            for (int g8 = 0; g8 < 4; ++g8) {
+                float v8[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(out)[q] = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+                for (int e = 0; e < 8; ++e) {
+                    const int i = g8 * 8 + e;
+                    const float v = (fmaf(a2, z[i], c2) > 0.f) ? g[i] + q3 : 0.f;
+                    s_acc += v;
+                    q_acc = fmaf(v, z[i] + b2, q_acc);
+                    v8[e] = v;
+                }
+                store_img8(out, nhl, IMG64, j, colhalf * 4 + g8, v8);
+            }
         }
         float* st = p.stats + ((long long)(blockIdx.x * 2 + colhalf) * 64 + j) * 2;
         st[0] = s_acc;
         st[1] = q_acc;
     } else if (warp < 8) {
-        // ---- z3 consumers (thread = channel c): locate the pool winner, build dz3, finally flush dW3 ----
+        // ---- Sp producers (thread = channel c): k0 dP at the max-pool winner, everything else stays zero ----
         const int h = warp >> 2, lq = warp & 3;
         const int c = h * 128 + lq * 32 + lane;
-        const float b3 = __ldg(p.b3 + c);
-        const float sgn = (__ldg(p.gamma3 + c) >= 0.f) ? 1.f : -1.f;
-        const float k0 = __ldg(p.c3_0 + c), k1 = __ldg(p.c3_1 + c);
-        const float k2 = fmaf(k1, b3, __ldg(p.c3_2 + c));
-        const int K = p.K;                         // 32 or 64: a 32-column chunk never straddles two groups
-        const int groups = BT / K;
-        int it = 0;
+        const float k0 = __ldg(p.c3_0 + c);
+        const float* dpp = p.dpooled + (long long)c * p.ldp + t0;
+        const unsigned char* argp = p.arg + (long long)c * p.ldp + t0;
+        uint8_t* row_hi = sps + c * 128;
+        int prev = -1;
+        float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        uchar4 a4 = make_uchar4(0, 0, 0, 0);
 #pragma unroll 1
-        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            // the pooled value / its gradient of this tile's group(s): issue the loads before waiting for the accumulator
-            const long long g0 = (long long)c * p.ldp + t * groups;
-            const float pool0 = __ldg(p.pooled + g0), dp0 = k0 * __ldg(p.dpooled + g0);
-            float pool1 = pool0, dp1 = dp0;
-            if (groups == 2) {
-                pool1 = __ldg(p.pooled + g0 + 1);
-                dp1 = k0 * __ldg(p.dpooled + g0 + 1);
-            }
-            mbar_wait(&d3_full[h], it & 1);
-            tc_fence_after_sync();
-            bool found = false;
-#pragma unroll 1
-            for (int q = 0; q < 2; ++q) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(128 + 64 * h + q * 32), v);
-                tmem_ld_wait();
-                if (q == 1) {                      // both halves are in registers / consumed: release the accumulator
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&d3_empty[h]);
-                }
-                const float pool = (q == 1 && groups == 2) ? pool1 : pool0;
-                const float dpv = (q == 1 && groups == 2) ? dp1 : dp0;
-                if (q == 1 && groups == 2) found = false;
-                int hit_at = -1;
-                // dz3 = k1*z + k2 everywhere, + k0*dP at the first row whose value equals the pooled one
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const bool hit = !found && (fmaf(v[i] * sgn, sgn, b3) == pool);
-                    found = found || hit;
-                    hit_at = hit ? i : hit_at;
-                    v[i] = fmaf(k1, v[i], k2) + (hit ? dpv : 0.f);
-                }
-                if (p.dbg_arg && hit_at >= 0)
-                    p.dbg_arg[(long long)c * p.ldp + t * groups + (q * 32) / K] = (unsigned char)((q * 32 + hit_at) & (K - 1));
-                if (q == 0) mbar_wait(dz_empty, (it & 1) ^ 1);
-#pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                    float w8[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) w8[e] = v[g8 * 8 + e];
-                    store_img8(dzs, nhl, 32768, c, q * 4 + g8, w8);
+        for (int it = 0; it < my_tiles; ++it) {
+            if ((it & 3) == 0) {
+                if (it + 4 <= my_tiles) {
+                    d4 = __ldg(reinterpret_cast<const float4*>(dpp + it));
+                    a4 = __ldg(reinterpret_cast<const uchar4*>(argp + it));
+                } else {
+                    d4.x = __ldg(dpp + it);
+                    a4.x = __ldg(argp + it);
+                    if (it + 1 < my_tiles) { d4.y = __ldg(dpp + it + 1); a4.y = __ldg(argp + it + 1); }
+                    if (it + 2 < my_tiles) { d4.z = __ldg(dpp + it + 2); a4.z = __ldg(argp + it + 2); }
                 }
             }
+            const int sel = it & 3;
+            const float val = k0 * (sel == 0 ? d4.x : sel == 1 ? d4.y : sel == 2 ? d4.z : d4.w);
+            const int r = (sel == 0 ? a4.x : sel == 1 ? a4.y : sel == 2 ? a4.z : a4.w) & 63;
+            const __nv_bfloat16 vh = __float2bfloat16_rn(val);
+            const __nv_bfloat16 vl = __float2bfloat16_rn(val - __bfloat162float(vh));
+            const int off = ((((r >> 3) ^ (c & 7)) << 4) | ((r & 7) << 1));
+            mbar_wait(sp_empty, (it & 1) ^ 1);
+            if (prev >= 0) {
+                *reinterpret_cast<unsigned short*>(row_hi + prev) = 0;
+                *reinterpret_cast<unsigned short*>(row_hi + 32768 + prev) = 0;
+            }
+            *reinterpret_cast<unsigned short*>(row_hi + off) = __bfloat16_as_ushort(vh);
+            if (nhl == 2) *reinterpret_cast<unsigned short*>(row_hi + 32768 + off) = __bfloat16_as_ushort(vl);
+            prev = off;
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(dz_full);
+            if (lane == 0) mbar_arrive(sp_full);
         }
-        // dW3 of this CTA's rows sits in TMEM: add it to the global gradient
+        // dW3s of this CTA's rows sits in TMEM: add it to the global gradient
         mbar_wait(fin_bar, 0);
         tc_fence_after_sync();
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
             float a[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(320 + 64 * h + q * 32), a);
+            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(256 + 64 * h + q * 32), a);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) atomicAdd(p.dw3 + c * 64 + q * 32 + i, a[i]);
@@ -738,46 +772,51 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-// pass D
-// warps 0,1,4,5 : dh1 consumers (thread = channel i)    warps 8,9,12,13 : z2 consumers -> dz2 image (thread = channel j)
-// warps 10,11,14,15 : producers                          warp 16 : MMA issuer
-// TMEM columns: D2[b] 0/64, DH1[b] 128/192, DW2 256
+// pass D   (10 warps)
+// warps 0,1,4,5 : dh1 consumers (thread = channel i)      warps 2,3,6,7 : x -> h1 image producers
+// warp 8 : MMA issuer                                      warp 9 : bulk-TMA loader of the dh2' image tiles
+// TMEM columns: DH1[b] 0/64, DW2s 128, H1 192
 // --------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_d_kernel(const L1BwdParams p) {
+constexpr int D_THREADS = 10 * 32;
+constexpr int D_STAGES = 3;
+
+__global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nhl = p.nhl;
-    uint8_t* w2s = smem;                       // hi 8 KB | lo 8 KB, then 16 KB of slack (M=128 reads 128 rows)
-    uint8_t* h1s = w2s + 32768;                // 2 stages x (hi | lo)
-    uint8_t* dzs = h1s + 2 * 2 * IMG64;        // 2 stages x (hi | lo)   dz2 image [64 j][64 r]
-    uint8_t* xs = dzs + 2 * 2 * IMG64 + 16384; // slack behind the last image, then 2 stages x 64 rows x 16 B
+    uint8_t* ews = smem;                       // diag(e0) W2: hi 8 KB | lo 8 KB, then 16 KB of slack (M=128 reads 128 columns)
+    uint8_t* p2s = ews + 32768;                // hi 8 KB | lo 8 KB
+    uint8_t* h1s = p2s + 16384;                // 2 stages x (hi | lo)
+    uint8_t* dhs = h1s + 2 * 2 * IMG64;        // D_STAGES x (hi | lo)   dh2' image [64 j][64 r]
+    uint8_t* xs = dhs + D_STAGES * 2 * IMG64 + 16384;   // slack behind the last image, then 2 stages x 64 rows x 16 B
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * BT * 16);
-    uint64_t *h1_full = bars, *h1_empty = bars + 2, *d2_full = bars + 4, *d2_empty = bars + 6, *dz_full = bars + 8,
-             *dz_empty = bars + 10, *dh_full = bars + 12, *dh_empty = bars + 14, *x_free = bars + 16, *w_bar = bars + 18,
-             *fin_bar = bars + 19;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t *h1_full = bars, *h1_empty = bars + 2, *in_full = bars + 4, *in_empty = bars + 7, *dh_full = bars + 10,
+             *dh_empty = bars + 12, *x_free = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = p.R / BT;
+    const long long t0 = (long long)blockIdx.x * p.tiles_per_cta;
+    const int my_tiles = (int)((ntiles - t0 < p.tiles_per_cta) ? (ntiles - t0) : p.tiles_per_cta);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&h1_full[i], 4);
             mbar_init(&h1_empty[i], 1);
-            mbar_init(&d2_full[i], 1);
-            mbar_init(&d2_empty[i], 4);
-            mbar_init(&dz_full[i], 4);
-            mbar_init(&dz_empty[i], 1);
             mbar_init(&dh_full[i], 1);
             mbar_init(&dh_empty[i], 4);
             mbar_init(&x_free[i], 4);
+        }
+        for (int i = 0; i < D_STAGES; ++i) {
+            mbar_init(&in_full[i], 1);
+            mbar_init(&in_empty[i], 1);
         }
         mbar_init(w_bar, 1);
         mbar_init(fin_bar, 1);
         mbar_fence_init();
     }
-    if (warp == 16) {
-        tmem_alloc(tmem_slot, 512);
+    if (warp == 8) {
+        tmem_alloc(tmem_slot, 256);
         tmem_relinquish();
     }
     tc_fence_before_sync();
@@ -788,125 +827,95 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_d_kernel(const L1BwdPar
     const uint32_t idesc_dg = umma_idesc_bf16(128, BT) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;
     const uint32_t idesc_kk = umma_idesc_bf16(128, 64);
 
-    if (warp == 16) {
+    if (warp == 8) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(w_bar, 8192u * nhl);
-            tma_bulk_g2s(w2s, p.w2_img, 8192, w_bar);
-            if (nhl == 2) tma_bulk_g2s(w2s + 8192, p.w2_img + 16384, 8192, w_bar);
+            mbar_arrive_expect_tx(w_bar, 2 * 8192u * nhl);
+            tma_bulk_g2s(ews, p.e0w2_img, 8192, w_bar);
+            tma_bulk_g2s(p2s, p.p2_img, 8192, w_bar);
+            if (nhl == 2) {
+                tma_bulk_g2s(ews + 8192, p.e0w2_img + 16384, 8192, w_bar);
+                tma_bulk_g2s(p2s + 8192, p.p2_img + 16384, 8192, w_bar);
+            }
             mbar_wait(w_bar, 0);
-            const uint32_t w2_hi = smem_u32(w2s), w2_lo = w2_hi + 8192;
-            auto issue_mma2 = [&](int it) {
+            const uint32_t ew_hi = smem_u32(ews), ew_lo = ew_hi + 8192;
+            const uint32_t p2_hi = smem_u32(p2s), p2_lo = p2_hi + 8192;
+            int s = 0, ph = 0;
+#pragma unroll 1
+            for (int it = 0; it < my_tiles; ++it) {
                 const int b = it & 1, u = (it >> 1) & 1;
                 mbar_wait(&h1_full[b], u);
-                mbar_wait(&d2_empty[b], u ^ 1);
-                tc_fence_after_sync();
-                const uint32_t h1 = smem_u32(h1s + b * 2 * IMG64);
-                mma_w_act64(tmem_base + 64 * b, w2_hi, w2_lo, h1, h1 + IMG64, nhl, idesc_mn);
-                umma_commit(&d2_full[b]);
-            };
-            int it = 0;
-            long long t = blockIdx.x;
-            if (t < ntiles) issue_mma2(0);
-            for (; t < ntiles; t += gridDim.x, ++it) {
-                const int b = it & 1, u = (it >> 1) & 1;
-                if (t + gridDim.x < ntiles) issue_mma2(it + 1);
-                mbar_wait(&dz_full[b], u);
+                mbar_wait(&in_full[s], ph);
                 mbar_wait(&dh_empty[b], u ^ 1);
                 tc_fence_after_sync();
-                const uint32_t dz = smem_u32(dzs + b * 2 * IMG64), h1 = smem_u32(h1s + b * 2 * IMG64);
-                // dh1[i][r] = sum_j W2[j][i] dz2[j][r]: W2 image read as an MN-major A operand (M = i, K = j)
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t a_hi = umma_desc_mn_sw128(w2_hi + ks * 2048, 16384, 1024);
-                    const uint64_t a_lo = umma_desc_mn_sw128(w2_lo + ks * 2048, 16384, 1024);
-                    const uint64_t b_hi = umma_desc_mn_sw128(dz + ks * 2048, 8192, 1024);
-                    umma_bf16_ss(tmem_base + 128 + 64 * b, a_hi, b_hi, idesc_dg, ks > 0 ? 1u : 0u);
-                    if (nhl == 2) {
-                        umma_bf16_ss(tmem_base + 128 + 64 * b, a_hi, umma_desc_mn_sw128(dz + IMG64 + ks * 2048, 8192, 1024), idesc_dg, 1u);
-                        umma_bf16_ss(tmem_base + 128 + 64 * b, a_lo, b_hi, idesc_dg, 1u);
-                    }
-                }
+                const uint32_t dz = smem_u32(dhs + s * 2 * IMG64), h1 = smem_u32(h1s + b * 2 * IMG64);
+                // dh1[i][r] = sum_j (e0 W2)[j][i] dh2'[j][r] + sum_i' P2[i][i'] h1[i'][r]
+                mma_t_act(tmem_base + 64 * b, ew_hi, ew_lo, 16384, dz, dz + IMG64, 4, nhl, idesc_dg, true);
+                mma_w_act64(tmem_base + 64 * b, p2_hi, p2_lo, h1, h1 + IMG64, nhl, idesc_mn, false);
                 umma_commit(&dh_full[b]);
-                // dW2[j][i] += sum_r dz2[j][r] h1[i][r]
-                mma_rows64(tmem_base + 256, dz, dz + IMG64, h1, h1 + IMG64, nhl, idesc_kk, it == 0);
-                umma_commit(&dz_empty[b]);
+                mma_rows64(tmem_base + 128, dz, dz + IMG64, h1, h1 + IMG64, nhl, idesc_kk, it == 0);    // dW2s += dh2' h1^T
+                mma_rows64(tmem_base + 192, h1, h1 + IMG64, h1, h1 + IMG64, nhl, idesc_kk, it == 0);    // H1 += h1 h1^T
+                umma_commit(&in_empty[s]);
                 umma_commit(&h1_empty[b]);
+                if (++s == D_STAGES) { s = 0; ph ^= 1; }
             }
             umma_commit(fin_bar);
         }
-    } else if (warp == 10 || warp == 11 || warp == 14 || warp == 15) {
-        const int pw = (warp == 10) ? 0 : (warp == 11) ? 1 : (warp == 14) ? 2 : 3;
+    } else if (warp == 9) {
+        if (lane == 0) {
+            int s = 0, ph = 0;
+            const uint8_t* src = p.dh2 + t0 * (2 * IMG64);
+#pragma unroll 1
+            for (int it = 0; it < my_tiles; ++it) {
+                mbar_wait(&in_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&in_full[s], (uint32_t)(IMG64 * nhl));
+                tma_bulk_g2s(dhs + s * 2 * IMG64, src + (long long)it * (2 * IMG64), IMG64 * nhl, &in_full[s]);
+                if (++s == D_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 2 || warp == 3 || warp == 6 || warp == 7) {
+        const int pw = (warp == 2) ? 0 : (warp == 3) ? 1 : (warp == 6) ? 2 : 3;
         const int ptid = pw * 32 + lane, ch = ptid & 63, half = ptid >> 6;
         const float s1 = __ldg(p.scale1 + ch), t1 = __ldg(p.shift1 + ch);
         const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + ch);
         const float wx = s1 * w.x, wy = s1 * w.y, wz = s1 * w.z, ww = s1 * w.w, bf = fmaf(s1, __ldg(p.b1 + ch), t1);
-        int it = 0;
-        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const float4* xg = reinterpret_cast<const float4*>(p.xt) + t0 * BT;
+        float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ptid < BT) xnext = __ldg(xg + ptid);
+        float hsum = 0.f;
+#pragma unroll 1
+        for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
             float4* xtile = reinterpret_cast<float4*>(xs + b * BT * 16);
             mbar_wait(&x_free[b], u ^ 1);                         // the dh1 consumers of tile it-2 are done with this x tile
-            if (ptid < BT) xtile[ptid] = __ldg(reinterpret_cast<const float4*>(p.xt) + t * BT + ptid);
+            if (ptid < BT) {
+                xtile[ptid] = xnext;
+                if (it + 1 < my_tiles) xnext = __ldg(xg + (long long)(it + 1) * BT + ptid);
+            }
             named_bar_sync(1, 128);
             mbar_wait(&h1_empty[b], u ^ 1);
-            produce_h1_tile64(xtile, h1s + b * 2 * IMG64, nhl, ch, half, wx, wy, wz, ww, bf);
+            hsum += produce_h1_tile64(xtile, h1s + b * 2 * IMG64, nhl, ch, half, wx, wy, wz, ww, bf);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&h1_full[b]);
         }
-    } else if (warp == 8 || warp == 9 || warp == 12 || warp == 13) {
-        // ---- z2 consumers: dz2 = c0*dh2' + c1*z2 + c2 -> image ----
-        const int lg = warp & 1, colhalf = (warp >= 12) ? 1 : 0;
-        const int j = lg * 32 + lane;
-        const float b2 = __ldg(p.b2 + j);
-        const float k0 = __ldg(p.c2_0 + j), k1 = __ldg(p.c2_1 + j);
-        const float k2 = fmaf(k1, b2, __ldg(p.c2_2 + j));
-        int it = 0;
-        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const int b = it & 1, u = (it >> 1) & 1;
-            const float4* src = reinterpret_cast<const float4*>(p.dh2 + (t * 64 + j) * 64 + colhalf * 32);
-            float g[32];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float4 v4 = __ldg(src + q);
-                g[4 * q] = v4.x; g[4 * q + 1] = v4.y; g[4 * q + 2] = v4.z; g[4 * q + 3] = v4.w;
-            }
-            mbar_wait(&d2_full[b], u);
-            tc_fence_after_sync();
-            float z[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(64 * b + colhalf * 32), z);
-            tmem_ld_wait();
-            tc_fence_before_sync();
-            mbar_wait(&dz_empty[b], u ^ 1);
-            uint8_t* img = dzs + b * 2 * IMG64;
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-                float h[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) h[e] = fmaf(k0, g[g8 * 8 + e], fmaf(k1, z[g8 * 8 + e], k2));
-                store_img8(img, nhl, IMG64, j, colhalf * 4 + g8, h);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&dz_full[b]);
-                mbar_arrive(&d2_empty[b]);
-            }
-        }
+        atomicAdd(p.hsum + ch, hsum);
     } else if (warp == 0 || warp == 1 || warp == 4 || warp == 5) {
-        // ---- dh1 consumers (thread = channel i): ReLU1 mask by recomputation, BN1 backward sums, A = sum dh1' x^T ----
+        // ---- dh1 consumers (thread = channel i): + q2, ReLU1 mask by recomputation, BN1 backward sums, A = sum dh1' x^T ----
         const int lg = warp & 1, colhalf = (warp >= 4) ? 1 : 0;
         const int i = lg * 32 + lane;
         const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + i);
         const float b1 = __ldg(p.b1 + i), s1 = __ldg(p.scale1 + i), t1 = __ldg(p.shift1 + i);
         const float wx = s1 * w.x, wy = s1 * w.y, wz = s1 * w.z, ww = s1 * w.w, bf = fmaf(s1, b1, t1);   // as the producer folds BN1
+        const float q2 = __ldg(p.q2 + i);
         float s_acc = 0.f, q_acc = 0.f, ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
-        int it = 0;
-        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+#pragma unroll 1
+        for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
             const float4* xtile = reinterpret_cast<const float4*>(xs + b * BT * 16) + colhalf * 32;
             mbar_wait(&dh_full[b], u);
             tc_fence_after_sync();
             float g[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 + 64 * b + colhalf * 32), g);
+            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(64 * b + colhalf * 32), g);
             tmem_ld_wait();
             tc_fence_before_sync();
 #pragma unroll
@@ -914,7 +923,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_d_kernel(const L1BwdPar
                 const float4 x = xtile[r];
                 const float z1 = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, b1))));
                 const float zf = fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf))));
-                const float v = (zf > 0.f) ? g[r] : 0.f;
+                const float v = (zf > 0.f) ? g[r] + q2 : 0.f;
                 s_acc += v;
                 q_acc = fmaf(v, z1, q_acc);
                 ax = fmaf(v, x.x, ax); ay = fmaf(v, x.y, ay); az = fmaf(v, x.z, az); aw = fmaf(v, x.w, aw);
@@ -929,23 +938,79 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) l1_bwd_d_kernel(const L1BwdPar
         p.stats[slot * 2 + 0] = s_acc;
         p.stats[slot * 2 + 1] = q_acc;
         reinterpret_cast<float4*>(p.amat)[slot] = make_float4(ax, ay, az, aw);
-        // dW2 of this CTA's rows: TMEM -> global (lanes 0..63 = channel j, 64 columns = channel i)
+        // dW2s and H1 of this CTA's rows: TMEM -> global (lanes 0..63 = row index, 64 columns)
         mbar_wait(fin_bar, 0);
         tc_fence_after_sync();
         float a[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + colhalf * 32), a);
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 + colhalf * 32), a);
         tmem_ld_wait();
-        if (blockIdx.x < ntiles) {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) atomicAdd(p.dw2 + i * 64 + colhalf * 32 + q, a[q]);
-        }
+        for (int q = 0; q < 32; ++q) atomicAdd(p.dw2s + i * 64 + colhalf * 32 + q, a[q]);
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(192 + colhalf * 32), a);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) atomicAdd(p.gram + i * 64 + colhalf * 32 + q, a[q]);
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 16) {
+    if (warp == 8) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, 256);
     }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// The 64x64 algebra around the passes (one small block each).
+// l1_prep: P = W^T diag(d) W (64x64) and, optionally, E = diag(e0) W (C == 64), both as packed bf16 hi/lo operand images;
+//          q = W^T (d (.) bias + c2).   W is [C][64].
+// l1_fin : dW[c][j] (+)= d[c] (sum_j' W[c][j'] H[j'][j] + bias[c] s[j]) + c2[c] s[j] (+ e0[c] sparse[c][j])
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) l1_prep_kernel(const float* __restrict__ W, int C, const float* __restrict__ d,
+                                                      const float* __restrict__ bias, const float* __restrict__ c2,
+                                                      const float* __restrict__ e0, uint8_t* __restrict__ p_img, float* __restrict__ q,
+                                                      uint8_t* __restrict__ e_img) {
+    const int j = threadIdx.x >> 3, chunk = threadIdx.x & 7;
+    double acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0;
+    double qa = 0.0;
+    for (int c = 0; c < C; ++c) {
+        const double wd = (double)W[c * 64 + j] * (double)d[c];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += wd * (double)W[c * 64 + chunk * 8 + e];
+        if (chunk == 0) qa += (double)W[c * 64 + j] * ((double)d[c] * (double)bias[c] + (double)c2[c]);
+    }
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (float)acc[e];
+    uint4 hi, lo;
+    split_bf16x8(v, hi, lo);
+    const uint32_t off = sw128_offset((uint32_t)j, (uint32_t)chunk);
+    *reinterpret_cast<uint4*>(p_img + off) = hi;
+    *reinterpret_cast<uint4*>(p_img + 16384 + off) = lo;
+    if (chunk == 0) q[j] = (float)qa;
+    if (e_img) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = e0[j] * W[j * 64 + chunk * 8 + e];
+        split_bf16x8(v, hi, lo);
+        *reinterpret_cast<uint4*>(e_img + off) = hi;
+        *reinterpret_cast<uint4*>(e_img + 16384 + off) = lo;
+    }
+}
+
+__global__ void __launch_bounds__(256) l1_fin_kernel(const float* __restrict__ W, int C, const float* __restrict__ d,
+                                                     const float* __restrict__ bias, const float* __restrict__ c2,
+                                                     const float* __restrict__ H, const float* __restrict__ s,
+                                                     const float* __restrict__ e0, const float* __restrict__ sparse,
+                                                     float* __restrict__ dW, int accumulate) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= C * 64) return;
+    const int c = idx >> 6, j = idx & 63;
+    double acc = 0.0;
+    for (int k = 0; k < 64; ++k) acc += (double)W[c * 64 + k] * (double)H[k * 64 + j];
+    double out = (double)d[c] * (acc + (double)bias[c] * (double)s[j]) + (double)c2[c] * (double)s[j];
+    if (sparse) out += (double)e0[c] * (double)sparse[idx];
+    dW[idx] = accumulate ? dW[idx] + (float)out : (float)out;
 }
 
 // dW1[i][:] = c0_i * A_i + c1_i * (C w1_i + b1_i * sx) + c2_i * sx   with C = sum x x^T, sx = sum x (z1 is affine in x)
@@ -967,8 +1032,8 @@ __global__ void l1_dw1_kernel(const float* __restrict__ amat, int P, const doubl
     }
 }
 
-size_t l1_bwd_c_smem() { return 16384 + 65536 + 4 * IMG64 + 4 * IMG64 + 65536 + 2 * BT * 16 + 256 + 1024; }
-size_t l1_bwd_d_smem() { return 32768 + 4 * IMG64 + 4 * IMG64 + 16384 + 2 * BT * 16 + 256 + 1024; }
+size_t l1_bwd_c_smem() { return 16384 + 65536 + 16384 + 2 * IMG64 + 4 * IMG64 + 65536 + 2 * BT * 16 + 256 + 1024; }
+size_t l1_bwd_d_smem() { return 32768 + 16384 + 4 * IMG64 + D_STAGES * 2 * IMG64 + 16384 + 2 * BT * 16 + 256 + 1024; }
 
 // sum x (4) and sum x x^T (10 unique) over all rows, in double
 __global__ void __launch_bounds__(256) l1_moments_kernel(const float4* __restrict__ xt, long long R, double* __restrict__ out) {
@@ -1068,8 +1133,8 @@ int l1_bn1_launch(const double* mom14, double n, const float* w1, const float* b
 // pass A: statistics of z2 -> stats [2*grid][64][2];  pass B: pooled [256][ldp] + statistics of z3 -> stats [grid][256][2]
 int l1_fwd_launch(bool pass_b, const float* xt, long long R, int K, int nsplit, const float* w1, const float* b1, const float* scale1,
                   const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
-                  const void* w3_img, const float* b3, const float* gamma3, float* stats, float* pooled, long long ldp,
-                  cudaStream_t st) {
+                  const void* w3_img, const float* b3, const float* gamma3, float* stats, float* pooled, unsigned char* pool_arg,
+                  long long ldp, cudaStream_t st) {
     if (R <= 0 || R % TILE != 0 || K <= 0 || (K & (K - 1)) || TILE % K != 0) return (int)cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
@@ -1082,7 +1147,7 @@ int l1_fwd_launch(bool pass_b, const float* xt, long long R, int K, int nsplit, 
     p.w1 = w1; p.b1 = b1; p.scale1 = scale1; p.shift1 = shift1;
     p.w2_img = reinterpret_cast<const uint8_t*>(w2_img); p.b2 = b2; p.scale2 = scale2; p.shift2 = shift2;
     p.w3_img = reinterpret_cast<const uint8_t*>(w3_img); p.b3 = b3; p.gamma3 = gamma3;
-    p.stats = stats; p.pooled = pooled; p.ldp = ldp;
+    p.stats = stats; p.pooled = pooled; p.pool_arg = pool_arg; p.ldp = ldp;
     const int grid = l1_fused_grid(R);
     ScopedTimer timer(pass_b ? TAG_L1_PASS_B : TAG_L1_PASS_A, st);
     count_launch();
@@ -1093,53 +1158,77 @@ int l1_fwd_launch(bool pass_b, const float* xt, long long R, int K, int nsplit, 
     return (int)cudaGetLastError();
 }
 
-static unsigned char *g_dbg_mask1 = nullptr, *g_dbg_mask2 = nullptr, *g_dbg_arg = nullptr;
-void l1_set_debug_dump(unsigned char* mask1, unsigned char* mask2, unsigned char* arg) {
-    g_dbg_mask1 = mask1; g_dbg_mask2 = mask2; g_dbg_arg = arg;
+static unsigned char *g_dbg_mask1 = nullptr, *g_dbg_mask2 = nullptr;
+void l1_set_debug_dump(unsigned char* mask1, unsigned char* mask2) {
+    g_dbg_mask1 = mask1; g_dbg_mask2 = mask2;
 }
 
+// backward passes: every CTA owns a contiguous range of tiles (a multiple of 4, so the Sp producers can fetch four
+// groups' winners with one aligned vector load)
+static int bwd_tiles_per_cta(long long R) {
+    const long long tiles = R / BT;
+    long long per = (tiles + kNumSMs - 1) / kNumSMs;
+    per = (per + 3) & ~3LL;
+    return (int)per;
+}
 int l1_bwd_grid(long long R) {
-    long long tiles = R / BT;
-    return (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    const long long tiles = R / BT, per = bwd_tiles_per_cta(R);
+    return (int)((tiles + per - 1) / per);
 }
 
-static void fill_bwd_common(L1BwdParams& p, const float* xt, long long R, int K, int nsplit, const float* w1, const float* b1,
-                            const float* scale1, const float* shift1, const void* w2_img, const float* b2, const float* scale2,
-                            const float* shift2) {
-    p.xt = xt; p.R = R; p.K = K; p.nhl = (nsplit == 3) ? 2 : 1;
+static void fill_bwd_common(L1BwdParams& p, const float* xt, long long R, int nsplit, const float* w1, const float* b1,
+                            const float* scale1, const float* shift1) {
+    memset(&p, 0, sizeof(p));
+    p.xt = xt; p.R = R; p.nhl = (nsplit == 3) ? 2 : 1; p.tiles_per_cta = bwd_tiles_per_cta(R);
     p.w1 = w1; p.b1 = b1; p.scale1 = scale1; p.shift1 = shift1;
-    p.w2_img = reinterpret_cast<const uint8_t*>(w2_img); p.b2 = b2; p.scale2 = scale2; p.shift2 = shift2;
 }
 
-// pass C: needs dw3 zero-initialised by the caller (accumulated with atomics); stats [2*grid][64][2]
-int l1_bwd_c_launch(const float* xt, long long R, int K, int nsplit, const float* w1, const float* b1, const float* scale1,
+int l1_prep_launch(const float* W, int C, const float* d, const float* bias, const float* c2, const float* e0, void* p_img, float* q,
+                   void* e_img, cudaStream_t st) {
+    if (C <= 0 || (e_img && C != 64)) return (int)cudaErrorInvalidValue;
+    ScopedTimer timer(TAG_L1_MISC, st);
+    count_launch();
+    l1_prep_kernel<<<1, 512, 0, st>>>(W, C, d, bias, c2, e0, reinterpret_cast<uint8_t*>(p_img), q, reinterpret_cast<uint8_t*>(e_img));
+    return (int)cudaGetLastError();
+}
+
+int l1_fin_launch(const float* W, int C, const float* d, const float* bias, const float* c2, const float* H, const float* s,
+                  const float* e0, const float* sparse, float* dW, int accumulate, cudaStream_t st) {
+    ScopedTimer timer(TAG_L1_MISC, st);
+    count_launch();
+    l1_fin_kernel<<<(C * 64 + 255) / 256, 256, 0, st>>>(W, C, d, bias, c2, H, s, e0, sparse, dW, accumulate);
+    return (int)cudaGetLastError();
+}
+
+// pass C (K = 64): dw3 / gram / hsum are accumulated with atomics (zero-initialised by the caller); stats [2*grid][64][2]
+int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1,
                     const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
-                    const void* w3_img, const float* b3, const float* gamma3, const float* pooled, const float* dpooled,
-                    long long ldp, const float* c3_0, const float* c3_1, const float* c3_2, float* dh2, float* dw3, float* stats,
+                    const void* w3_img, const void* p3_img, const float* q3, const unsigned char* arg, const float* dpooled,
+                    long long ldp, const float* c3_0, void* dh2, float* dw3, float* gram, float* hsum, float* stats,
                     cudaStream_t st) {
-    if (R <= 0 || R % BT != 0 || (K != 32 && K != 64)) return (int)cudaErrorInvalidValue;
+    if (R <= 0 || R % BT != 0 || ldp % 4 != 0) return (int)cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
         FACL_CHECK(cudaFuncSetAttribute(l1_bwd_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_bwd_c_smem()));
         configured = true;
     }
     L1BwdParams p;
-    memset(&p, 0, sizeof(p));
-    fill_bwd_common(p, xt, R, K, nsplit, w1, b1, scale1, shift1, w2_img, b2, scale2, shift2);
-    p.w3_img = reinterpret_cast<const uint8_t*>(w3_img); p.b3 = b3; p.gamma3 = gamma3;
-    p.pooled = pooled; p.dpooled = dpooled; p.ldp = ldp; p.c3_0 = c3_0; p.c3_1 = c3_1; p.c3_2 = c3_2;
-    p.dh2 = dh2; p.dw3 = dw3; p.stats = stats;
-    p.dbg_mask1 = g_dbg_mask1; p.dbg_mask2 = g_dbg_mask2; p.dbg_arg = g_dbg_arg;
+    fill_bwd_common(p, xt, R, nsplit, w1, b1, scale1, shift1);
+    p.w2_img = reinterpret_cast<const uint8_t*>(w2_img); p.b2 = b2; p.scale2 = scale2; p.shift2 = shift2;
+    p.w3_img = reinterpret_cast<const uint8_t*>(w3_img); p.p3_img = reinterpret_cast<const uint8_t*>(p3_img); p.q3 = q3;
+    p.arg = arg; p.dpooled = dpooled; p.ldp = ldp; p.c3_0 = c3_0;
+    p.dh2 = reinterpret_cast<uint8_t*>(dh2); p.dw3 = dw3; p.gram = gram; p.hsum = hsum; p.stats = stats;
+    p.dbg_mask1 = g_dbg_mask1; p.dbg_mask2 = g_dbg_mask2;
     ScopedTimer timer(TAG_L1_PASS_C, st);
     count_launch();
     l1_bwd_c_kernel<<<l1_bwd_grid(R), C_THREADS, l1_bwd_c_smem(), st>>>(p);
     return (int)cudaGetLastError();
 }
 
-// pass D: dw2 zero-initialised by the caller; stats [2*grid][64][2]; amat [2*grid][64][4]
+// pass D: dw2s / gram / hsum accumulated with atomics (zero-initialised by the caller); stats [2*grid][64][2]; amat [2*grid][64][4]
 int l1_bwd_d_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1,
-                    const float* shift1, const void* w2_img, const float* b2, const float* c2_0, const float* c2_1,
-                    const float* c2_2, const float* dh2, float* dw2, float* amat, float* stats, cudaStream_t st) {
+                    const float* shift1, const void* e0w2_img, const void* p2_img, const float* q2, const void* dh2, float* dw2s,
+                    float* gram, float* hsum, float* amat, float* stats, cudaStream_t st) {
     if (R <= 0 || R % BT != 0) return (int)cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
@@ -1147,13 +1236,13 @@ int l1_bwd_d_launch(const float* xt, long long R, int nsplit, const float* w1, c
         configured = true;
     }
     L1BwdParams p;
-    memset(&p, 0, sizeof(p));
-    fill_bwd_common(p, xt, R, 64, nsplit, w1, b1, scale1, shift1, w2_img, b2, nullptr, nullptr);
-    p.c2_0 = c2_0; p.c2_1 = c2_1; p.c2_2 = c2_2;
-    p.dh2 = const_cast<float*>(dh2); p.dw2 = dw2; p.amat = amat; p.stats = stats;
+    fill_bwd_common(p, xt, R, nsplit, w1, b1, scale1, shift1);
+    p.e0w2_img = reinterpret_cast<const uint8_t*>(e0w2_img); p.p2_img = reinterpret_cast<const uint8_t*>(p2_img); p.q2 = q2;
+    p.dh2 = reinterpret_cast<uint8_t*>(const_cast<void*>(dh2)); p.dw2s = dw2s; p.gram = gram; p.hsum = hsum; p.amat = amat;
+    p.stats = stats;
     ScopedTimer timer(TAG_L1_PASS_D, st);
     count_launch();
-    l1_bwd_d_kernel<<<l1_bwd_grid(R), BWD_THREADS, l1_bwd_d_smem(), st>>>(p);
+    l1_bwd_d_kernel<<<l1_bwd_grid(R), D_THREADS, l1_bwd_d_smem(), st>>>(p);
     return (int)cudaGetLastError();
 }
 

@@ -76,8 +76,8 @@ int facl_timing_collect(float* ms_per_tag, int* count_per_tag, int ntags) {
 
 long long facl_launch_count(void) { return facl::g_launches; }
 
-void facl_debug_l1_dump(unsigned char* mask1, unsigned char* mask2, unsigned char* arg) {
-    facl::l1_set_debug_dump(mask1, mask2, arg);
+void facl_debug_l1_dump(unsigned char* mask1, unsigned char* mask2) {
+    facl::l1_set_debug_dump(mask1, mask2);
 }
 
 }  // extern "C"

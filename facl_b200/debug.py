@@ -14,24 +14,23 @@ class L1DecisionDump:
         self.shape = (M, S, K)
         self.mask1 = torch.zeros(R1 * 64, dtype=torch.uint8, device=device)
         self.mask2 = torch.zeros(R1 * 64, dtype=torch.uint8, device=device)
-        self.arg = torch.full((256, R3), 255, dtype=torch.uint8, device=device)
 
     def __enter__(self):
         from ._lib import lib
-        lib().facl_debug_l1_dump(self.mask1.data_ptr(), self.mask2.data_ptr(), self.arg.data_ptr())
+        lib().facl_debug_l1_dump(self.mask1.data_ptr(), self.mask2.data_ptr())
         return self
 
     def __exit__(self, *exc):
         from ._lib import lib
         torch.cuda.synchronize()
-        lib().facl_debug_l1_dump(None, None, None)
+        lib().facl_debug_l1_dump(None, None)
 
     def masks(self):
         M, S, K = self.shape
         R1 = M * S * K
         m1 = self.mask1.view(R1 // 64, 64, 64).permute(0, 2, 1).reshape(R1, 64).bool().cpu()     # (row, channel)
         m2 = self.mask2.view(R1 // 64, 64, 64).permute(0, 2, 1).reshape(R1, 64).bool().cpu()
-        return m1, m2, self.arg.t().long().cpu()                                              # arg: (M*S, 256)
+        return m1, m2
 
 
 def routing_of_last_forward(net, l1_dump=None):
@@ -45,13 +44,10 @@ def routing_of_last_forward(net, l1_dump=None):
     vec = ws.view("vec", (2048,))
     out = dict(s=ws.view("arg6", (1024, MB), torch.uint8)[:, :M].t().long().cpu(),
                g=ws.view("argg", (1024, B), torch.uint8).t().long().cpu())
-    if l1_dump is None:
-        out["k"] = ws.view("arg3", (256, R3), torch.uint8).t().long().cpu()
+    out["k"] = ws.view("arg3", (256, R3), torch.uint8).t().long().cpu()          # written by pass B when fused
     fused = l1_dump is not None
     if fused:
-        m1, m2, arg = l1_dump.masks()
-        assert int((arg == 255).sum()) == 0, "a max-pool winner was not found by the recomputing backward"
-        out["k"] = arg
+        m1, m2 = l1_dump.masks()
         out["relu:net3DV_1.0"], out["relu:net3DV_1.3"] = m1, m2
         # ReLU3 only matters on the winner rows: impose the pooled activation's sign on the whole group
         pooled = ws.view("pcat", (259, R3))[3:]

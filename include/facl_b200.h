@@ -271,10 +271,10 @@ FACL_API int facl_train_step(const facl_train_step_args* args, void* stream);
 FACL_API void facl_timing_enable(int on);
 FACL_API int facl_timing_collect(float* ms_per_tag, int* count_per_tag, int ntags);
 FACL_API long long facl_launch_count(void);
-/* test hook: when set (device pointers), the next fused net3DV_1 backward also records its discrete decisions --
- * mask1 / mask2 [R/64][64][64] bytes (ReLU1 / ReLU2 active, 64-row blocks x channel x row), arg [256][M*S] bytes
- * (max-pool winner inside its K-group; the slot of a group whose winner was not found is left untouched). */
-FACL_API void facl_debug_l1_dump(unsigned char* mask1, unsigned char* mask2, unsigned char* arg);
+/* test hook: when set (device pointers), the next fused net3DV_1 backward also records the ReLU decisions of its
+ * recomputed forward -- mask1 / mask2 [R/64][64][64] bytes (ReLU1 / ReLU2 active, 64-row blocks x channel x row).  The
+ * max-pool winners are in the encoder work buffer "arg3" ([256][M*S] bytes, position inside the K-group). */
+FACL_API void facl_debug_l1_dump(unsigned char* mask1, unsigned char* mask2);
 
 #ifdef __cplusplus
 }
