@@ -72,7 +72,7 @@ size_t buffer_bytes(int i, const facl_encoder_dims* d) {
     if (d->flags & FACL_ENC_FUSED_L1) {   // no per-row activation is stored: only dh2 (pass C -> pass D) and small scratch
         switch (i) {
             case B_Z1: case B_Z2: case B_Z3: case B_DY3: case B_XTT: return 256;
-            case B_DH1: return (size_t)4 * kNumSMs * 64 * 4 * f;
+            case B_DH1: return (size_t)4 * kNumSMs * 64 * 4 * f;   // pass D: [4 * grid][64][4]
             default: break;
         }
     }
@@ -526,9 +526,9 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
         RUN(l1_prep_launch(L1.w, 64, s1.c1, L1.b, s1.c2, s1.c0, imgs + 32768, acc + L1S_Q2, imgs + 65536, st));
         RUN(l1_bwd_d_launch(xt, R1, ns, L0.w, L0.b, s0.scale, s0.shift, imgs + 65536, imgs + 32768, acc + L1S_Q2, bufs[B_DH2],
                             acc + L1S_DW2S, acc + L1S_H1, acc + L1S_S1, F(B_DH1), stats, st));
-        RUN(bwd_finalize(0, 0, 64, (int)R1, (double)R1, P, 0));
+        RUN(bwd_finalize(0, 0, 64, (int)R1, (double)R1, 2 * P, 0));
         RUN(l1_fin_launch(L1.w, 64, s1.c1, L1.b, s1.c2, acc + L1S_H1, acc + L1S_S1, s1.c0, acc + L1S_DW2S, gr->dw[1], 0, st));
-        RUN(l1_dw1_launch(F(B_DH1), P, mom, L0.w, L0.b, s0.c0, s0.c1, s0.c2, gr->dw[0], st));
+        RUN(l1_dw1_launch(F(B_DH1), 2 * P, mom, L0.w, L0.b, s0.c0, s0.c1, s0.c2, gr->dw[0], st));
         return 0;
     }
     // ---- L1 ---------------------------------------------------------------------------------------------------

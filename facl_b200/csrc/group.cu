@@ -5,8 +5,9 @@
 // Python loop of S masked index writes.  Here the cloud tile is staged once into shared memory by a 1-D bulk
 // TMA copy, distances live in registers only, and the K nearest are selected exactly:
 //
-//   pass 1  every lane tracks its T = ceil(K/32) smallest distances; tau = max over lanes of the T-th one
-//           bounds the K-th smallest distance from above (32*T >= K of the points are <= tau);
+//   pass 1  every lane tracks its T = ceil(K/32) + 1 smallest distances; tau = the K-th smallest of those 32*T values
+//           (bitwise binary search with warp-wide counts) bounds the K-th smallest distance from above, tightly enough
+//           that only ~1.2 K points pass it;
 //   pass 2  points with d <= tau are compacted (ballot) into a per-warp candidate list of 64-bit keys
 //           (distance bits << 32 | index) -- distances are >= 0, so key order == (distance, index) order;
 //   rank    a candidate's output slot is the number of smaller keys; slots < K are written.
@@ -24,9 +25,9 @@ namespace facl {
 namespace {
 
 constexpr int GW = 8;             // warps (= centres) per block
-constexpr int CAP = 512;          // candidate slots per warp
-constexpr int TILE_PTS = 4096;    // points per shared-memory tile (64 KB as float4)
-constexpr int TMAX = 4;           // supports K <= 128
+constexpr int CAP = 256;          // candidate slots per warp
+constexpr int TILE_PTS = 4096;    // points per shared-memory tile (at most 64 KB as float4)
+constexpr int TMAX = 5;           // supports K <= 128 (T = ceil(K/32) + 1 tracked per lane)
 
 __device__ __forceinline__ void insert_smallest(float (&t)[TMAX], int T, float d) {
     // keep t[0] <= t[1] <= ... <= t[T-1] = the T smallest seen
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
                                                         float* __restrict__ xt, int* __restrict__ idx_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* tile = reinterpret_cast<float4*>(smem_raw);                                  // TILE_PTS x 16 B
-    unsigned long long* cand_all = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)TILE_PTS * 16);
+    unsigned long long* cand_all = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)(N < TILE_PTS ? N : TILE_PTS) * 16);
     __shared__ __align__(8) uint64_t bar;
 
     const int m = blockIdx.y;
@@ -63,8 +64,9 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
     const bool active = s < S;
     const float* cloud = points + (long long)m * N * D;
     unsigned long long* cand = cand_all + warp * CAP;
-    const int T = (K + 31) / 32;
+    const int T = (K + 31) / 32 + 1;
     const int ntiles = (N + TILE_PTS - 1) / TILE_PTS;
+    const int tile_pts = N < TILE_PTS ? N : TILE_PTS;
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -115,12 +117,23 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
             }
         }
     }
-    float tau = tsm[0];
+    // tau = K-th smallest of the 32*T tracked values (+inf where a lane saw fewer than T points): distances are >= 0, so
+    // their bit patterns order like unsigned integers; build the answer bit by bit from warp-wide counts.
+    unsigned tb[TMAX];
 #pragma unroll
-    for (int q = 1; q < TMAX; ++q)
-        if (q < T) tau = tsm[q];
-    // lanes that saw fewer than T points hold +inf, which keeps tau a valid upper bound
-    tau = __uint_as_float(__reduce_max_sync(0xFFFFFFFFu, __float_as_uint(tau)));
+    for (int q = 0; q < TMAX; ++q) tb[q] = (q < T) ? __float_as_uint(tsm[q]) : 0xFFFFFFFFu;
+    unsigned prefix = 0u;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const unsigned trial = prefix | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < TMAX; ++q) c += (tb[q] < trial) ? 1 : 0;
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
+        if (c < K) prefix = trial;            // fewer than K values below `trial`: the K-th smallest is >= trial
+    }
+    const float tau = __uint_as_float(prefix);
+    (void)tile_pts;
 
     // ---------------- pass 2: compact candidates with d <= tau ----------------
     int count = 0;
@@ -178,11 +191,28 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
     };
 
     if (count <= CAP) {
-        for (int i = lane; i < count; i += 32) {
-            unsigned long long key = cand[i];
-            int rank = 0;
-            for (int j = 0; j < count; ++j) rank += (cand[j] < key) ? 1 : 0;
-            if (rank < K) emit(rank, key);
+        // rank = number of smaller keys; four of this lane's keys stay in registers while one broadcast read per
+        // candidate serves all four comparisons
+        for (int base = 0; base < count; base += 128) {
+            unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull, k3 = ~0ull;
+            const int i0 = base + lane, i1 = i0 + 32, i2 = i0 + 64, i3 = i0 + 96;
+            if (i0 < count) k0 = cand[i0];
+            if (i1 < count) k1 = cand[i1];
+            if (i2 < count) k2 = cand[i2];
+            if (i3 < count) k3 = cand[i3];
+            int r0 = 0, r1 = 0, r2c = 0, r3 = 0;
+#pragma unroll 4
+            for (int j = 0; j < count; ++j) {
+                const unsigned long long c = cand[j];
+                r0 += (c < k0) ? 1 : 0;
+                r1 += (c < k1) ? 1 : 0;
+                r2c += (c < k2) ? 1 : 0;
+                r3 += (c < k3) ? 1 : 0;
+            }
+            if (i0 < count && r0 < K) emit(r0, k0);
+            if (i1 < count && r1 < K) emit(r1, k1);
+            if (i2 < count && r2c < K) emit(r2c, k2);
+            if (i3 < count && r3 < K) emit(r3, k3);
         }
     } else {
         // Rare (heavy duplication around the centre): K rounds of "smallest key greater than the last one",
@@ -213,11 +243,12 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
 
 int group_launch(const float* points, int M, int N, int D, int S, int K, float r2, float* xt, int* idx_out, cudaStream_t st) {
     if (M <= 0 || N <= 0 || D < 3 || S <= 0 || S > N || K <= 0 || K > N || K > 32 * TMAX) return (int)cudaErrorInvalidValue;
-    const size_t smem = (size_t)TILE_PTS * 16 + (size_t)GW * CAP * 8;
+    const size_t smem = (size_t)(N < TILE_PTS ? N : TILE_PTS) * 16 + (size_t)GW * CAP * 8;
     static bool configured = false;
     if (!configured) {
-        FACL_CHECK(cudaFuncSetAttribute(group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FACL_CHECK(cudaFuncSetAttribute(group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int max_smem = TILE_PTS * 16 + GW * CAP * 8;
+        FACL_CHECK(cudaFuncSetAttribute(group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        FACL_CHECK(cudaFuncSetAttribute(group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         configured = true;
     }
     dim3 grid((S + GW - 1) / GW, M);

@@ -772,26 +772,33 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-// pass D   (10 warps)
-// warps 0,1,4,5 : dh1 consumers (thread = channel i)      warps 2,3,6,7 : x -> h1 image producers
-// warp 8 : MMA issuer                                      warp 9 : bulk-TMA loader of the dh2' image tiles
-// TMEM columns: DH1[b] 0/64, DW2s 128, H1 192
+// pass D   (14 warps)
+// warps 0-7   : dh1 consumers: TMEM lane quarter = warp % 4, column half = warp / 4
+// warps 8-11  : x -> h1 image producers          warp 12 : MMA issuer          warp 13 : bulk-TMA loader of dh2' tiles
+// TMEM columns: DH1[b] 0/64, [dW2s ; H1] 128
+//
+// Every product here has only 64 real output rows, so the M = 128 instruction is fed STACKED operands instead of padding:
+//  * a weight image is stored [hi 64 rows | lo 64 rows]; read as one 128-row A tile, lanes 0..63 receive A_hi * B and lanes
+//    64..127 A_lo * B -- the bf16x3 scheme needs two instructions (B_hi, B_lo) instead of three, and because everything
+//    the consumers derive from dh1 is a SUM over rows, the two lane halves are simply reduced as separate partials;
+//  * dh2' and h1 of a tile sit next to each other in a stage ([dh2'_hi | h1_hi | dh2'_lo | h1_lo]), so one 128-row A tile
+//    against B = h1 yields dh2' h1^T (lanes 0..63) and h1 h1^T (lanes 64..127) at once.
 // --------------------------------------------------------------------------------------------------------------------
-constexpr int D_THREADS = 10 * 32;
+constexpr int D_THREADS = 14 * 32;
 constexpr int D_STAGES = 3;
+constexpr int D_STAGE_BYTES = 4 * IMG64;
 
 __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nhl = p.nhl;
-    uint8_t* ews = smem;                       // diag(e0) W2: hi 8 KB | lo 8 KB, then 16 KB of slack (M=128 reads 128 columns)
-    uint8_t* p2s = ews + 32768;                // hi 8 KB | lo 8 KB
-    uint8_t* h1s = p2s + 16384;                // 2 stages x (hi | lo)
-    uint8_t* dhs = h1s + 2 * 2 * IMG64;        // D_STAGES x (hi | lo)   dh2' image [64 j][64 r]
-    uint8_t* xs = dhs + D_STAGES * 2 * IMG64 + 16384;   // slack behind the last image, then 2 stages x 64 rows x 16 B
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * BT * 16);
-    uint64_t *h1_full = bars, *h1_empty = bars + 2, *in_full = bars + 4, *in_empty = bars + 7, *dh_full = bars + 10,
-             *dh_empty = bars + 12, *x_free = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17;
+    uint8_t* ews = smem;                       // diag(e0) W2: hi 8 KB | lo 8 KB
+    uint8_t* p2s = ews + 16384;                // P2:          hi 8 KB | lo 8 KB
+    uint8_t* stg = p2s + 16384;                // D_STAGES x [dh2'_hi | h1_hi | dh2'_lo | h1_lo]
+    uint8_t* xs = stg + D_STAGES * D_STAGE_BYTES;   // D_STAGES x 64 rows x 16 B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + D_STAGES * BT * 16);
+    uint64_t *h1_full = bars, *in_full = bars + 3, *st_empty = bars + 6, *dh_full = bars + 9, *dh_empty = bars + 11,
+             *x_free = bars + 13, *w_bar = bars + 16, *fin_bar = bars + 17;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -800,22 +807,21 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
     const int my_tiles = (int)((ntiles - t0 < p.tiles_per_cta) ? (ntiles - t0) : p.tiles_per_cta);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&h1_full[i], 4);
-            mbar_init(&h1_empty[i], 1);
-            mbar_init(&dh_full[i], 1);
-            mbar_init(&dh_empty[i], 4);
-            mbar_init(&x_free[i], 4);
-        }
         for (int i = 0; i < D_STAGES; ++i) {
+            mbar_init(&h1_full[i], 4);
             mbar_init(&in_full[i], 1);
-            mbar_init(&in_empty[i], 1);
+            mbar_init(&st_empty[i], 1);
+            mbar_init(&x_free[i], 8);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&dh_full[i], 1);
+            mbar_init(&dh_empty[i], 8);
         }
         mbar_init(w_bar, 1);
         mbar_init(fin_bar, 1);
         mbar_fence_init();
     }
-    if (warp == 8) {
+    if (warp == 12) {
         tmem_alloc(tmem_slot, 256);
         tmem_relinquish();
     }
@@ -827,7 +833,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
     const uint32_t idesc_dg = umma_idesc_bf16(128, BT) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;
     const uint32_t idesc_kk = umma_idesc_bf16(128, 64);
 
-    if (warp == 8) {
+    if (warp == 12) {
         if (lane == 0) {
             mbar_arrive_expect_tx(w_bar, 2 * 8192u * nhl);
             tma_bulk_g2s(ews, p.e0w2_img, 8192, w_bar);
@@ -837,44 +843,55 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
                 tma_bulk_g2s(p2s + 8192, p.p2_img + 16384, 8192, w_bar);
             }
             mbar_wait(w_bar, 0);
-            const uint32_t ew_hi = smem_u32(ews), ew_lo = ew_hi + 8192;
-            const uint32_t p2_hi = smem_u32(p2s), p2_lo = p2_hi + 8192;
+            const uint32_t ew = smem_u32(ews), p2 = smem_u32(p2s);
             int s = 0, ph = 0;
 #pragma unroll 1
             for (int it = 0; it < my_tiles; ++it) {
                 const int b = it & 1, u = (it >> 1) & 1;
-                mbar_wait(&h1_full[b], u);
+                mbar_wait(&h1_full[s], ph);
                 mbar_wait(&in_full[s], ph);
                 mbar_wait(&dh_empty[b], u ^ 1);
                 tc_fence_after_sync();
-                const uint32_t dz = smem_u32(dhs + s * 2 * IMG64), h1 = smem_u32(h1s + b * 2 * IMG64);
-                // dh1[i][r] = sum_j (e0 W2)[j][i] dh2'[j][r] + sum_i' P2[i][i'] h1[i'][r]
-                mma_t_act(tmem_base + 64 * b, ew_hi, ew_lo, 16384, dz, dz + IMG64, 4, nhl, idesc_dg, true);
-                mma_w_act64(tmem_base + 64 * b, p2_hi, p2_lo, h1, h1 + IMG64, nhl, idesc_mn, false);
+                const uint32_t dz = smem_u32(stg + s * D_STAGE_BYTES), h1 = dz + IMG64;   // lo halves 2 * IMG64 further
+                // dh1[i][r] = sum_j (e0 W2)[j][i] dh2'[j][r] + sum_i' P2[i][i'] h1[i'][r];  lanes 0..63 hi part, 64..127 lo part
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ad = umma_desc_mn_sw128(ew + ks * 2048, 8192, 1024);
+                    umma_bf16_ss(tmem_base + 64 * b, ad, umma_desc_mn_sw128(dz + ks * 2048, 8192, 1024), idesc_dg, ks > 0 ? 1u : 0u);
+                    if (nhl == 2)
+                        umma_bf16_ss(tmem_base + 64 * b, ad, umma_desc_mn_sw128(dz + 2 * IMG64 + ks * 2048, 8192, 1024), idesc_dg, 1u);
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ad = umma_desc_sw128(p2 + ks * 32);
+                    umma_bf16_ss(tmem_base + 64 * b, ad, umma_desc_mn_sw128(h1 + ks * 2048, 8192, 1024), idesc_mn, 1u);
+                    if (nhl == 2)
+                        umma_bf16_ss(tmem_base + 64 * b, ad, umma_desc_mn_sw128(h1 + 2 * IMG64 + ks * 2048, 8192, 1024), idesc_mn, 1u);
+                }
                 umma_commit(&dh_full[b]);
-                mma_rows64(tmem_base + 128, dz, dz + IMG64, h1, h1 + IMG64, nhl, idesc_kk, it == 0);    // dW2s += dh2' h1^T
-                mma_rows64(tmem_base + 192, h1, h1 + IMG64, h1, h1 + IMG64, nhl, idesc_kk, it == 0);    // H1 += h1 h1^T
-                umma_commit(&in_empty[s]);
-                umma_commit(&h1_empty[b]);
+                // [dW2s ; H1] += [dh2' ; h1] h1^T  (reduction over the 64 rows)
+                mma_rows64(tmem_base + 128, dz, dz + 2 * IMG64, h1, h1 + 2 * IMG64, nhl, idesc_kk, it == 0);
+                umma_commit(&st_empty[s]);
                 if (++s == D_STAGES) { s = 0; ph ^= 1; }
             }
             umma_commit(fin_bar);
         }
-    } else if (warp == 9) {
+    } else if (warp == 13) {
         if (lane == 0) {
             int s = 0, ph = 0;
             const uint8_t* src = p.dh2 + t0 * (2 * IMG64);
 #pragma unroll 1
             for (int it = 0; it < my_tiles; ++it) {
-                mbar_wait(&in_empty[s], ph ^ 1);
+                mbar_wait(&st_empty[s], ph ^ 1);
+                uint8_t* dst = stg + s * D_STAGE_BYTES;
                 mbar_arrive_expect_tx(&in_full[s], (uint32_t)(IMG64 * nhl));
-                tma_bulk_g2s(dhs + s * 2 * IMG64, src + (long long)it * (2 * IMG64), IMG64 * nhl, &in_full[s]);
+                tma_bulk_g2s(dst, src + (long long)it * (2 * IMG64), IMG64, &in_full[s]);
+                if (nhl == 2) tma_bulk_g2s(dst + 2 * IMG64, src + (long long)it * (2 * IMG64) + IMG64, IMG64, &in_full[s]);
                 if (++s == D_STAGES) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 2 || warp == 3 || warp == 6 || warp == 7) {
-        const int pw = (warp == 2) ? 0 : (warp == 3) ? 1 : (warp == 6) ? 2 : 3;
-        const int ptid = pw * 32 + lane, ch = ptid & 63, half = ptid >> 6;
+    } else if (warp >= 8) {
+        const int ptid = (warp - 8) * 32 + lane, ch = ptid & 63, half = ptid >> 6;
         const float s1 = __ldg(p.scale1 + ch), t1 = __ldg(p.shift1 + ch);
         const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + ch);
         const float wx = s1 * w.x, wy = s1 * w.y, wz = s1 * w.z, ww = s1 * w.w, bf = fmaf(s1, __ldg(p.b1 + ch), t1);
@@ -882,78 +899,97 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
         float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ptid < BT) xnext = __ldg(xg + ptid);
         float hsum = 0.f;
+        int s = 0, ph = 0;
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
-            const int b = it & 1, u = (it >> 1) & 1;
-            float4* xtile = reinterpret_cast<float4*>(xs + b * BT * 16);
-            mbar_wait(&x_free[b], u ^ 1);                         // the dh1 consumers of tile it-2 are done with this x tile
+            float4* xtile = reinterpret_cast<float4*>(xs + s * BT * 16);
+            mbar_wait(&x_free[s], ph ^ 1);                        // the dh1 consumers of the tile that used this x slot are done
             if (ptid < BT) {
                 xtile[ptid] = xnext;
                 if (it + 1 < my_tiles) xnext = __ldg(xg + (long long)(it + 1) * BT + ptid);
             }
             named_bar_sync(1, 128);
-            mbar_wait(&h1_empty[b], u ^ 1);
-            hsum += produce_h1_tile64(xtile, h1s + b * 2 * IMG64, nhl, ch, half, wx, wy, wz, ww, bf);
+            mbar_wait(&st_empty[s], ph ^ 1);
+            // h1 image of this stage: hi at +IMG64, lo at +3*IMG64
+            float acc = 0.f;
+            uint8_t* img = stg + s * D_STAGE_BYTES + IMG64;
+#pragma unroll 2
+            for (int q = 0; q < 4; ++q) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float4 x = xtile[half * 32 + q * 8 + e];
+                    v[e] = fmaxf(fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf)))), 0.f);
+                    acc += v[e];
+                }
+                store_img8(img, nhl, 2 * IMG64, ch, half * 4 + q, v);
+            }
+            hsum += acc;
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&h1_full[b]);
+            if (lane == 0) mbar_arrive(&h1_full[s]);
+            if (++s == D_STAGES) { s = 0; ph ^= 1; }
         }
         atomicAdd(p.hsum + ch, hsum);
-    } else if (warp == 0 || warp == 1 || warp == 4 || warp == 5) {
-        // ---- dh1 consumers (thread = channel i): + q2, ReLU1 mask by recomputation, BN1 backward sums, A = sum dh1' x^T ----
-        const int lg = warp & 1, colhalf = (warp >= 4) ? 1 : 0;
-        const int i = lg * 32 + lane;
+    } else {
+        // ---- dh1 consumers (thread = channel i, hi or lo part): + q2, ReLU1 mask by recomputation, BN1 backward sums,
+        //      A = sum dh1' x^T.  All of these are sums over rows, so the hi and lo parts are reduced as separate partials. ----
+        const int quarter = warp & 3, colhalf = warp >> 2;
+        const int part = quarter >> 1;                           // 0: lanes 0..63 (A_hi products), 1: lanes 64..127 (A_lo)
+        const int i = (quarter & 1) * 32 + lane;
         const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + i);
         const float b1 = __ldg(p.b1 + i), s1 = __ldg(p.scale1 + i), t1 = __ldg(p.shift1 + i);
         const float wx = s1 * w.x, wy = s1 * w.y, wz = s1 * w.z, ww = s1 * w.w, bf = fmaf(s1, b1, t1);   // as the producer folds BN1
-        const float q2 = __ldg(p.q2 + i);
+        const float q2 = part == 0 ? __ldg(p.q2 + i) : 0.f;
+        const bool live = (part == 0) || (nhl == 2);             // bf16 mode has no lo part: lanes 64..127 are meaningless
         float s_acc = 0.f, q_acc = 0.f, ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+        int s = 0;
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
-            const float4* xtile = reinterpret_cast<const float4*>(xs + b * BT * 16) + colhalf * 32;
+            const float4* xtile = reinterpret_cast<const float4*>(xs + s * BT * 16) + colhalf * 32;
             mbar_wait(&dh_full[b], u);
             tc_fence_after_sync();
             float g[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(64 * b + colhalf * 32), g);
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(64 * b + colhalf * 32), g);
             tmem_ld_wait();
             tc_fence_before_sync();
+            if (live) {
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                const float4 x = xtile[r];
-                const float z1 = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, b1))));
-                const float zf = fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf))));
-                const float v = (zf > 0.f) ? g[r] + q2 : 0.f;
-                s_acc += v;
-                q_acc = fmaf(v, z1, q_acc);
-                ax = fmaf(v, x.x, ax); ay = fmaf(v, x.y, ay); az = fmaf(v, x.z, az); aw = fmaf(v, x.w, aw);
+                for (int r = 0; r < 32; ++r) {
+                    const float4 x = xtile[r];
+                    const float z1 = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, b1))));
+                    const float zf = fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf))));
+                    const float v = (zf > 0.f) ? g[r] + q2 : 0.f;
+                    s_acc += v;
+                    q_acc = fmaf(v, z1, q_acc);
+                    ax = fmaf(v, x.x, ax); ay = fmaf(v, x.y, ay); az = fmaf(v, x.z, az); aw = fmaf(v, x.w, aw);
+                }
             }
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&dh_empty[b]);
-                mbar_arrive(&x_free[b]);
+                mbar_arrive(&x_free[s]);
             }
+            if (++s == D_STAGES) s = 0;
         }
-        const long long slot = (long long)(blockIdx.x * 2 + colhalf) * 64 + i;
+        const long long slot = (long long)(blockIdx.x * 4 + part * 2 + colhalf) * 64 + i;
         p.stats[slot * 2 + 0] = s_acc;
         p.stats[slot * 2 + 1] = q_acc;
         reinterpret_cast<float4*>(p.amat)[slot] = make_float4(ax, ay, az, aw);
-        // dW2s and H1 of this CTA's rows: TMEM -> global (lanes 0..63 = row index, 64 columns)
+        // [dW2s ; H1] of this CTA's rows: lanes 0..63 -> dW2s rows, lanes 64..127 -> H1 rows
         mbar_wait(fin_bar, 0);
         tc_fence_after_sync();
         float a[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 + colhalf * 32), a);
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 + colhalf * 32), a);
         tmem_ld_wait();
+        float* dst = (part == 0 ? p.dw2s : p.gram) + i * 64 + colhalf * 32;
 #pragma unroll
-        for (int q = 0; q < 32; ++q) atomicAdd(p.dw2s + i * 64 + colhalf * 32 + q, a[q]);
-        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(192 + colhalf * 32), a);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 32; ++q) atomicAdd(p.gram + i * 64 + colhalf * 32 + q, a[q]);
+        for (int q = 0; q < 32; ++q) atomicAdd(dst + q, a[q]);
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 12) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 256);
     }
@@ -965,20 +1001,39 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
 //          q = W^T (d (.) bias + c2).   W is [C][64].
 // l1_fin : dW[c][j] (+)= d[c] (sum_j' W[c][j'] H[j'][j] + bias[c] s[j]) + c2[c] s[j] (+ e0[c] sparse[c][j])
 // --------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) l1_prep_kernel(const float* __restrict__ W, int C, const float* __restrict__ d,
+// grid = 8 blocks (8 rows j each) x 256 threads = (4 slices of the reduction over c) x (8 rows) x (8 chunks of 8 columns)
+__global__ void __launch_bounds__(256) l1_prep_kernel(const float* __restrict__ W, int C, const float* __restrict__ d,
                                                       const float* __restrict__ bias, const float* __restrict__ c2,
                                                       const float* __restrict__ e0, uint8_t* __restrict__ p_img, float* __restrict__ q,
                                                       uint8_t* __restrict__ e_img) {
-    const int j = threadIdx.x >> 3, chunk = threadIdx.x & 7;
+    __shared__ double red[3][64][9];
+    const int slice = threadIdx.x >> 6, t = threadIdx.x & 63;
+    const int j = blockIdx.x * 8 + (t >> 3), chunk = t & 7;
     double acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.0;
     double qa = 0.0;
-    for (int c = 0; c < C; ++c) {
-        const double wd = (double)W[c * 64 + j] * (double)d[c];
+    for (int c = slice; c < C; c += 4) {
+        const double wj = (double)__ldg(W + c * 64 + j), dc = (double)__ldg(d + c);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + c * 64 + chunk * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + c * 64 + chunk * 8) + 1);
+        const double wd = wj * dc;
+        acc[0] += wd * w0.x; acc[1] += wd * w0.y; acc[2] += wd * w0.z; acc[3] += wd * w0.w;
+        acc[4] += wd * w1.x; acc[5] += wd * w1.y; acc[6] += wd * w1.z; acc[7] += wd * w1.w;
+        if (chunk == 0) qa += wj * (dc * (double)__ldg(bias + c) + (double)__ldg(c2 + c));
+    }
+    if (slice > 0) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += wd * (double)W[c * 64 + chunk * 8 + e];
-        if (chunk == 0) qa += (double)W[c * 64 + j] * ((double)d[c] * (double)bias[c] + (double)c2[c]);
+        for (int e = 0; e < 8; ++e) red[slice - 1][t][e] = acc[e];
+        red[slice - 1][t][8] = qa;
+    }
+    __syncthreads();
+    if (slice > 0) return;
+#pragma unroll
+    for (int sl = 0; sl < 3; ++sl) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += red[sl][t][e];
+        qa += red[sl][t][8];
     }
     float v[8];
 #pragma unroll
@@ -1033,7 +1088,7 @@ __global__ void l1_dw1_kernel(const float* __restrict__ amat, int P, const doubl
 }
 
 size_t l1_bwd_c_smem() { return 16384 + 65536 + 16384 + 2 * IMG64 + 4 * IMG64 + 65536 + 2 * BT * 16 + 256 + 1024; }
-size_t l1_bwd_d_smem() { return 32768 + 16384 + 4 * IMG64 + D_STAGES * 2 * IMG64 + 16384 + 2 * BT * 16 + 256 + 1024; }
+size_t l1_bwd_d_smem() { return 16384 + 16384 + D_STAGES * D_STAGE_BYTES + 16384 + D_STAGES * BT * 16 + 256 + 1024; }
 
 // sum x (4) and sum x x^T (10 unique) over all rows, in double
 __global__ void __launch_bounds__(256) l1_moments_kernel(const float4* __restrict__ xt, long long R, double* __restrict__ out) {
@@ -1188,7 +1243,7 @@ int l1_prep_launch(const float* W, int C, const float* d, const float* bias, con
     if (C <= 0 || (e_img && C != 64)) return (int)cudaErrorInvalidValue;
     ScopedTimer timer(TAG_L1_MISC, st);
     count_launch();
-    l1_prep_kernel<<<1, 512, 0, st>>>(W, C, d, bias, c2, e0, reinterpret_cast<uint8_t*>(p_img), q, reinterpret_cast<uint8_t*>(e_img));
+    l1_prep_kernel<<<8, 256, 0, st>>>(W, C, d, bias, c2, e0, reinterpret_cast<uint8_t*>(p_img), q, reinterpret_cast<uint8_t*>(e_img));
     return (int)cudaGetLastError();
 }
 
@@ -1225,7 +1280,7 @@ int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, c
     return (int)cudaGetLastError();
 }
 
-// pass D: dw2s / gram / hsum accumulated with atomics (zero-initialised by the caller); stats [2*grid][64][2]; amat [2*grid][64][4]
+// pass D: dw2s / gram / hsum accumulated with atomics (zero-initialised by the caller); stats [4*grid][64][2]; amat [4*grid][64][4]
 int l1_bwd_d_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1,
                     const float* shift1, const void* e0w2_img, const void* p2_img, const float* q2, const void* dh2, float* dw2s,
                     float* gram, float* hsum, float* amat, float* stats, cudaStream_t st) {
