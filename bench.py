@@ -266,7 +266,7 @@ def run_ours(args):
                          d2h_bytes_per_step=4, ms_per_step=e2e_ms / e2e_steps),
                 gpu_launches=int(launches), launches_per_step=launches / args.steps,
                 roofline=roof, step_tensor_tflops=step_tf, step_tensor_frac=step_tf / peaks["tensor_sustained"],
-                kernel_ms_per_step=kernel_ms, kernels=per_tag[:12], cpu_baseline=cpu, clocks=sampler.summary())
+                kernel_ms_per_step=kernel_ms, kernels=per_tag, cpu_baseline=cpu, clocks=sampler.summary())
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

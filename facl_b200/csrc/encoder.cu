@@ -29,13 +29,13 @@ const float BN_EPS = 1e-5f, BN_MOM = 0.1f;
 
 enum Buf {
     B_Z1, B_Z2, B_Z3, B_ARG3, B_PCAT, B_Z4, B_Z5, B_Z6, B_ARG6, B_PALL, B_ARGG, B_Z7, B_BN, B_VEC, B_STATS, B_WPACK,
-    B_IMG_H3, B_IMG_H4, B_IMG_H5,
-    B_DXT, B_DH7, B_DF, B_DY6, B_DH5, B_DH4, B_DP3, B_DY3, B_DH2, B_DH1, B_XTT, B_WPACKT, B_IMG_DZ, B_L1S,
+    B_IMG_H3, B_IMG_H4, B_IMG_H5, B_IMG_HD,
+    B_DXT, B_DH7, B_DF, B_DY6, B_DH5, B_DH4, B_DP3, B_DY3, B_DH2, B_DH1, B_XTT, B_WPACKT, B_IMG_DZ, B_L1S, B_IMG_HDB,
     NUM_BUFS
 };
 const char* BUF_NAMES[NUM_BUFS] = {"z1", "z2", "z3", "arg3", "pcat", "z4", "z5", "z6", "arg6", "pall", "argg", "z7", "bn", "vec",
-                                   "stats", "wpack", "img_h3", "img_h4", "img_h5", "dxt", "dh7", "df", "dy6", "dh5", "dh4", "dp3", "dy3", "dh2", "dh1", "xtt",
-                                   "wpackt", "img_dz", "l1s"};
+                                   "stats", "wpack", "img_h3", "img_h4", "img_h5", "img_hd", "dxt", "dh7", "df", "dy6", "dh5", "dh4", "dp3", "dy3", "dh2", "dh1", "xtt",
+                                   "wpackt", "img_dz", "l1s", "img_hdb"};
 const int FIRST_BWD_BUF = B_DXT;
 
 // forward weight images: layers 0..6, then fc3 (512x1024), then mapping (64x512)
@@ -100,6 +100,9 @@ size_t buffer_bytes(int i, const facl_encoder_dims* d) {
         case B_IMG_H5: return use_images(d) ? 2 * act_image_half_bytes(512, (long long)R3) : 256;
         case B_IMG_DZ: return use_images(d) ? 2 * act_image_half_bytes(1024, (long long)R3) : 256;
         case B_L1S: return L1S_BYTES;
+        case B_IMG_HD: return 2 * (2 * act_image_half_bytes(1024, (long long)M) + 2 * act_image_half_bytes(1024, (long long)B));
+        case B_IMG_HDB: return 2 * (act_image_half_bytes(512, (long long)M) + act_image_half_bytes(1024, (long long)M) +
+                                    act_image_half_bytes(512, (long long)B) + act_image_half_bytes(1024, (long long)B));
     }
     return 0;
 }
@@ -160,6 +163,36 @@ ActImage image_of(void* const* bufs, int buf, int C, long long R) {
     im.cgs = ((C + 63) / 64) * 8;
     im.rbs = (int)((R + 63) / 64);
     return im;
+}
+
+// head images: img_hd holds, per half (cloud rows / sequence rows), the inputs of netR_FC.0 and netR_FC.3;
+// img_hdb the two gradient images of the backward
+ActImage image_at(uint8_t* base, size_t& off, int C, long long R) {
+    ActImage im;
+    const size_t hb = act_image_half_bytes(C, R);
+    im.hi = base + off;
+    im.lo = base + off + hb;
+    im.cgs = ((C + 63) / 64) * 8;
+    im.rbs = (int)((R + 63) / 64);
+    off += 2 * hb;
+    return im;
+}
+struct HeadImages { ActImage h6, h7, dx, dz; };
+HeadImages head_images(void* const* bufs, int half, int M, int B) {
+    HeadImages hi{};
+    size_t off = 0, offb = 0;
+    uint8_t* f = reinterpret_cast<uint8_t*>(bufs[B_IMG_HD]);
+    uint8_t* b = reinterpret_cast<uint8_t*>(bufs[B_IMG_HDB]);
+    for (int h = 0; h <= half; ++h) {
+        const long long R = h == 0 ? M : B;
+        hi.h6 = image_at(f, off, 1024, R);
+        hi.h7 = image_at(f, off, 1024, R);
+        if (b) {
+            hi.dx = image_at(b, offb, 512, R);
+            hi.dz = image_at(b, offb, 1024, R);
+        }
+    }
+    return hi;
 }
 
 int pick_ksplit(int Md, int Nd, int Kd) {
@@ -329,20 +362,25 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
         const int Nd = half == 0 ? M : B;
         const long long off = half == 0 ? 0 : M;
         Slot s5 = bn_slot(bufs, 5);
+        HeadImages hi = head_images(bufs, half, M, B);
+        RUN(act_image_launch(src1(F(B_PALL) + off, MB, s5.scale, s5.shift, lo0), 0, 1024, Nd, nullptr, 0, layer_nhl(ns, 6), hi.h6,
+                             TAG_IMAGE, st));
         GemmParams g = gemm_base(1024, Nd, 1024, layer_nsplit(ns, 6));
         g.tag = 18;
         set_packed_a(g, wp + wpack_offset(6), 1024);
-        g.b = src1(F(B_PALL) + off, MB, s5.scale, s5.shift, lo0);
+        g.b_mode = B_IMAGE_MN; g.b_img = hi.h6;
         g.bias = p->layer[6].b;
         g.out_mode = OUT_CHMAJOR; g.out = F(B_Z7) + off; g.ldo = MB;
         g.stats = stats;
         RUN(launch_gemm_tc(g, st));
         RUN(finalize(6, 6 + half, Nd, (double)Nd));
         Slot s6 = bn_slot(bufs, 6 + half);
+        RUN(act_image_launch(src1(F(B_Z7) + off, MB, s6.scale, s6.shift, lo0), 0, 1024, Nd, nullptr, 0, layer_nhl(ns, 7), hi.h7,
+                             TAG_IMAGE, st));
         GemmParams h = gemm_base(C_EMB, Nd, 1024, layer_nsplit(ns, 7));
         h.tag = 21;
         set_packed_a(h, wp + wpack_offset(7), 1024);
-        h.b = src1(F(B_Z7) + off, MB, s6.scale, s6.shift, lo0);
+        h.b_mode = B_IMAGE_MN; h.b_img = hi.h7;
         h.bias = p->fc3_b;
         h.out_mode = OUT_ROWMAJOR; h.out = half == 0 ? x : xg; h.ldo = C_EMB;
         RUN(launch_gemm_tc(h, st));
@@ -428,18 +466,39 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
         const int Nd = half == 0 ? M : B;
         const long long off = half == 0 ? 0 : M;
         Slot s6 = bn_slot(bufs, 6 + half);
-        // netR_FC.3: dW = dx^T-major * relu(bn(z7))
-        RUN(wgrad(7, C_EMB, C_FEAT, Nd, src1(F(B_DXT) + off, MB, nullptr, nullptr, nullptr),
-                  src1(F(B_Z7) + off, MB, s6.scale, s6.shift, lo0), gr->dfc3_w));
+        HeadImages hi = head_images(bufs, half, M, B);
+        auto img_wgrad = [&](int layer, int Md, int Nd_, const ActImage& a, const ActImage& b, float* out) {
+            GemmParams g = gemm_base(Md, Nd_, Nd, layer_nsplit(ns, layer));
+            g.tag = 3 * layer + 1;
+            g.a_mode = A_IMAGE; g.a_img = a;
+            g.b_mode = B_IMAGE_K; g.b_img = b;
+            g.ksplit = pick_ksplit(Md, Nd_, Nd);
+            g.out_mode = OUT_ATOMIC_CHMAJOR; g.out = out; g.ldo = Nd_;
+            return launch_gemm_tc(g, st);
+        };
+        auto img_dgrad = [&](int layer, int Md, int Kd, const void* wimg, const ActImage& b, const float* zin, const float* zs0,
+                             const float* zs2, float* out, bool want_stats) {
+            GemmParams g = gemm_base(Md, Nd, Kd, layer_nsplit(ns, layer));
+            g.tag = 3 * layer + 2;
+            set_packed_a(g, wimg, Kd);
+            g.b_mode = B_IMAGE_MN; g.b_img = b;
+            g.zin = zin; g.ldz = MB; g.zs0 = zs0; g.zs2 = zs2;
+            g.out_mode = OUT_CHMAJOR; g.out = out; g.ldo = MB;
+            g.stats = want_stats ? stats : nullptr;
+            return launch_gemm_tc(g, st);
+        };
+        // netR_FC.3: dW = dx^T-major * relu(bn(z7))  (its input image is still there from the forward)
+        RUN(act_image_launch(src1(F(B_DXT) + off, MB, nullptr, nullptr, nullptr), 0, C_EMB, Nd, nullptr, 0, layer_nhl(ns, 7), hi.dx,
+                             TAG_IMAGE, st));
+        RUN(img_wgrad(7, C_EMB, C_FEAT, hi.dx, hi.h7, gr->dfc3_w));
         // grad wrt relu(bn(z7)), masked -> dh7, sums for BN(netR_FC.1)
-        RUN(dgrad(7, C_FEAT, Nd, C_EMB, wt + wpackt_offset(7), src1(F(B_DXT) + off, MB, nullptr, nullptr, nullptr), F(B_Z7) + off, MB,
-                  s6.scale, s6.shift, F(B_DH7) + off, MB, true));
+        RUN(img_dgrad(7, C_FEAT, C_EMB, wt + wpackt_offset(7), hi.dx, F(B_Z7) + off, s6.scale, s6.shift, F(B_DH7) + off, true));
         RUN(bwd_finalize(6, 6 + half, C_FEAT, Nd, (double)Nd, gemm_tc_ctas_per_mtile(C_FEAT, Nd), half));
         // netR_FC.0: dW = dz7 * relu(bn6(pooled))^T ; data grad masked by the pooled feature's ReLU
-        RUN(wgrad(6, C_FEAT, C_FEAT, Nd, src2(F(B_DH7) + off, F(B_Z7) + off, MB, s6.c0, s6.c1, s6.c2),
-                  src1(F(B_PALL) + off, MB, s5.scale, s5.shift, lo0), gr->dw[6]));
-        RUN(dgrad(6, C_FEAT, Nd, C_FEAT, wt + wpackt_offset(6), src2(F(B_DH7) + off, F(B_Z7) + off, MB, s6.c0, s6.c1, s6.c2),
-                  F(B_PALL) + off, MB, s5.scale, s5.shift, F(B_DF) + off, MB, false));
+        RUN(act_image_launch(src2(F(B_DH7) + off, F(B_Z7) + off, MB, s6.c0, s6.c1, s6.c2), 0, C_FEAT, Nd, nullptr, 0, layer_nhl(ns, 6),
+                             hi.dz, TAG_IMAGE, st));
+        RUN(img_wgrad(6, C_FEAT, C_FEAT, hi.dz, hi.h6, gr->dw[6]));
+        RUN(img_dgrad(6, C_FEAT, C_FEAT, wt + wpackt_offset(6), hi.dz, F(B_PALL) + off, s5.scale, s5.shift, F(B_DF) + off, false));
     }
     // sequence max -> the winning view's cloud; then the BN6 sums live on the pooled positions only
     RUN(combine_pool_grads_launch(F(B_DF), MB, F(B_DF) + M, MB, U(B_ARGG), C_FEAT, G, B, st));

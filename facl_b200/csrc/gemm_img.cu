@@ -116,7 +116,28 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                     }
                     v[i] = val;
                 }
-                if (p.pool) {
+                if (p.pool >= 32 && nvalid == 32) {
+                    // the whole 32-column chunk lies inside one pooling group: branch-free scan, one merge per chunk
+                    const float sg = keep_max ? 1.f : -1.f;
+                    float cb = -INFINITY;
+                    int ci = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float sv = v[i] * sg;
+                        ci = (sv > cb) ? i : ci;
+                        cb = fmaxf(cb, sv);
+                    }
+                    const int pos0 = (cc * 32) & (p.pool - 1);
+                    if (pos0 == 0 || cb > best) {
+                        best = cb;
+                        barg = pos0 + ci;
+                    }
+                    if (pos0 + 32 == p.pool) {
+                        const long long gi = (long long)c * p.ldp + n0 / p.pool;
+                        p.pool_out[gi] = best * sg;
+                        if (p.pool_arg) p.pool_arg[gi] = (unsigned char)barg;
+                    }
+                } else if (p.pool) {
                     const int pm = p.pool - 1;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
@@ -146,6 +167,10 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                         for (int i = 0; i < 32; ++i)
                             if (i < nvalid) o[i] = v[i];
                     }
+                } else if (p.out_mode == OUT_ROWMAJOR) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nvalid) p.out[(long long)(n0 + i) * p.ldo + c] = v[i];
                 }
             }
             tc_fence_before_sync();

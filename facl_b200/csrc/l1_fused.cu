@@ -28,7 +28,9 @@ constexpr int TILE = 128;                 // batch rows per tile
 constexpr uint32_t ACT_LBO = 8192;        // MN-major activation image: 64-row blocks 8 KB apart,
 constexpr uint32_t ACT_SBO = 1024;        //                            8-channel groups 1 KB apart (16 KB per half)
 constexpr int ACT_BYTES = 16384;
-constexpr int NTHREADS = 17 * 32;
+constexpr int NTHREADS_A = 17 * 32;        // pass A: warps 0-7 (idle z3 roles) are the h1 producers
+constexpr int NTHREADS_B = 21 * 32;        // pass B: warps 10,11,14,15 + 17..20 are the h1 producers
+constexpr int NPW = 8;                     // producer warps: 256 threads = 64 channels x 4 row quarters
 
 struct L1Params {
     const float* xt;          // [R][4]
@@ -84,7 +86,7 @@ __device__ __forceinline__ void mma_weight_act(uint32_t d_tmem, uint32_t a_hi, u
 }
 
 template <bool PASS_B>
-__global__ void __launch_bounds__(NTHREADS, 1) l1_fwd_kernel(const L1Params p) {
+__global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_kernel(const L1Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nhl = p.nhl;
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l1_fwd_kernel(const L1Params p) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&h1_full[i], 4);
+            mbar_init(&h1_full[i], NPW);
             mbar_init(&h1_empty[i], 1);
             mbar_init(&d2_full[i], 1);
             mbar_init(&d2_empty[i], 4);
@@ -171,33 +173,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) l1_fwd_kernel(const L1Params p) {
                 }
             }
         }
-    } else if (warp == 10 || warp == 11 || warp == 14 || warp == 15) {
-        // ======================= producers: x -> h1 = relu(bn1(W1 x + b1)), thread = channel =======================
-        const int pw = (warp == 10) ? 0 : (warp == 11) ? 1 : (warp == 14) ? 2 : 3;
-        const int ptid = pw * 32 + lane;          // 0..127
-        const int ch = ptid & 63, half = ptid >> 6;
+    } else if (PASS_B ? (warp == 10 || warp == 11 || warp == 14 || warp == 15 || warp >= 17) : (warp < 8)) {
+        // ======================= producers: x -> h1 = relu(bn1(W1 x + b1)), thread = (channel, row quarter) ===============
+        const int pw = !PASS_B ? warp : (warp >= 17) ? (warp - 13) : (warp == 10) ? 0 : (warp == 11) ? 1 : (warp == 14) ? 2 : 3;
+        const int ptid = pw * 32 + lane;          // 0..255
+        const int ch = ptid & 63, part = ptid >> 6;
         // BN1 folded into the 4-wide layer: h1 = max(wf . x + bf, 0)
         const float s1 = __ldg(p.scale1 + ch), t1 = __ldg(p.shift1 + ch);
         const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + ch);
         const float wx = s1 * w.x, wy = s1 * w.y, wz = s1 * w.z, ww = s1 * w.w;
         const float bf = fmaf(s1, __ldg(p.b1 + ch), t1);
         int it = 0;
+        float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ptid < TILE && (long long)blockIdx.x < ntiles) xnext = __ldg(reinterpret_cast<const float4*>(p.xt) + (long long)blockIdx.x * TILE + ptid);
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
             float4* xtile = reinterpret_cast<float4*>(xs + b * TILE * 16);
-            xtile[ptid] = __ldg(reinterpret_cast<const float4*>(p.xt) + t * TILE + ptid);
-            named_bar_sync(1, 128);
+            if (ptid < TILE) {
+                xtile[ptid] = xnext;
+                if (t + gridDim.x < ntiles) xnext = __ldg(reinterpret_cast<const float4*>(p.xt) + (t + gridDim.x) * TILE + ptid);
+            }
+            named_bar_sync(1, NPW * 32);
             mbar_wait(&h1_empty[b], u ^ 1);
             uint8_t* img = h1s + b * 2 * ACT_BYTES;
 #pragma unroll 2
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    float4 x = xtile[half * 64 + q * 8 + e];
+                    float4 x = xtile[part * 32 + q * 8 + e];
                     v[e] = fmaxf(fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf)))), 0.f);
                 }
-                store_act8(img, nhl, ch, half * 8 + q, v);
+                store_act8(img, nhl, ch, part * 4 + q, v);
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -260,9 +267,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) l1_fwd_kernel(const L1Params p) {
             st[0] = fmaf(n, b2, s_acc);
             st[1] = q_acc + 2.f * b2 * s_acc + n * b2 * b2;
         }
-    } else if (warp < 8) {
+    } else if (PASS_B && warp < 8) {
         // ======================= z3 consumers (pass B), thread = channel c =======================
-        if (PASS_B) {
+        {
             const int h = warp >> 2, lq = warp & 3;
             const int c = h * 128 + lq * 32 + lane;
             const float b3 = __ldg(p.b3 + c);
@@ -1207,9 +1214,9 @@ int l1_fwd_launch(bool pass_b, const float* xt, long long R, int K, int nsplit, 
     ScopedTimer timer(pass_b ? TAG_L1_PASS_B : TAG_L1_PASS_A, st);
     count_launch();
     if (pass_b)
-        l1_fwd_kernel<true><<<grid, NTHREADS, l1_smem_bytes(true), st>>>(p);
+        l1_fwd_kernel<true><<<grid, NTHREADS_B, l1_smem_bytes(true), st>>>(p);
     else
-        l1_fwd_kernel<false><<<grid, NTHREADS, l1_smem_bytes(false), st>>>(p);
+        l1_fwd_kernel<false><<<grid, NTHREADS_A, l1_smem_bytes(false), st>>>(p);
     return (int)cudaGetLastError();
 }
 

@@ -155,9 +155,9 @@ __device__ __forceinline__ void split_bf16x8(const float (&v)[8], uint4& hi, uin
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-        float r0 = v[2 * i] - __bfloat162float(h0), r1 = v[2 * i + 1] - __bfloat162float(h1);
-        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);                       // one packed convert for the pair
+        const float r0 = v[2 * i] - __uint_as_float(h[i] << 16);          // bf16 -> fp32 is a 16-bit shift
+        const float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u);
         l[i] = pack_bf16x2(r0, r1);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
