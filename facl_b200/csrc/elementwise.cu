@@ -10,19 +10,34 @@ namespace {
 // ---- BatchNorm forward: partial sums -> (mean, rstd, scale, shift), running-stat update -------------------
 // reference: nn.BatchNorm2d / nn.BatchNorm1d instantiated at cn3d_model_conbag.py:165,169,173,183,187,191,203
 // (eps 1e-5, momentum 0.1, biased variance for normalisation, unbiased for running_var).
+// one warp per channel: lanes stride over the P partial sums, then a shuffle reduction (in double)
+__device__ __forceinline__ void warp_sum_partials(const float* __restrict__ partials, int P, int C, int c, double& s, double& q) {
+    const int lane = threadIdx.x & 31;
+    s = 0.0;
+    q = 0.0;
+    for (int p = lane; p < P; p += 32) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(partials) + (long long)p * C + c);
+        s += (double)v.x;
+        q += (double)v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
+    }
+}
+
 __global__ void bn_finalize_kernel(const float* __restrict__ partials, int P, int C, double n, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* running_mean, float* running_var, float eps,
                                    float momentum, int training, float* __restrict__ mean, float* __restrict__ rstd,
                                    float* __restrict__ scale, float* __restrict__ shift) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     double mu, var;
+    double s = 0.0, q = 0.0;
+    if (training) warp_sum_partials(partials, P, C, c, s, q);
+    if ((threadIdx.x & 31) != 0) return;
     if (training) {
-        double s = 0.0, q = 0.0;
-        for (int p = 0; p < P; ++p) {
-            s += (double)partials[((long long)p * C + c) * 2 + 0];
-            q += (double)partials[((long long)p * C + c) * 2 + 1];
-        }
         mu = s / n;
         var = q / n - mu * mu;
         if (var < 0.0) var = 0.0;
@@ -46,13 +61,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int P, in
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int P, int C, double n, const float* __restrict__ gamma,
                                        const float* __restrict__ mean, const float* __restrict__ rstd, float* dgamma, float* dbeta,
                                        int accumulate, float* __restrict__ c0, float* __restrict__ c1, float* __restrict__ c2) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int p = 0; p < P; ++p) {
-        s += (double)partials[((long long)p * C + c) * 2 + 0];
-        q += (double)partials[((long long)p * C + c) * 2 + 1];
-    }
+    double s, q;
+    warp_sum_partials(partials, P, C, c, s, q);
+    if ((threadIdx.x & 31) != 0) return;
     double mu = mean[c], r = rstd[c], g = gamma[c];
     double dbe = s;
     double dga = r * (q - mu * s);
@@ -223,7 +236,7 @@ int bn_finalize_launch(const float* partials, int P, int C, double n, const floa
                        float* shift, cudaStream_t st) {
     ScopedTimer timer(TAG_BN, st);
     count_launch();
-    bn_finalize_kernel<<<div_up(C, 128), 128, 0, st>>>(partials, P, C, n, gamma, beta, running_mean, running_var, eps, momentum, training,
+    bn_finalize_kernel<<<div_up(C, 4), 128, 0, st>>>(partials, P, C, n, gamma, beta, running_mean, running_var, eps, momentum, training,
                                                        mean, rstd, scale, shift);
     return (int)cudaGetLastError();
 }
@@ -232,7 +245,7 @@ int bn_bwd_finalize_launch(const float* partials, int P, int C, double n, const 
                            float* dgamma, float* dbeta, int accumulate, float* c0, float* c1, float* c2, cudaStream_t st) {
     ScopedTimer timer(TAG_BN, st);
     count_launch();
-    bn_bwd_finalize_kernel<<<div_up(C, 128), 128, 0, st>>>(partials, P, C, n, gamma, mean, rstd, dgamma, dbeta, accumulate, c0, c1, c2);
+    bn_bwd_finalize_kernel<<<div_up(C, 4), 128, 0, st>>>(partials, P, C, n, gamma, mean, rstd, dgamma, dbeta, accumulate, c0, c1, c2);
     return (int)cudaGetLastError();
 }
 

@@ -239,9 +239,20 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     RUN(fill_launch(vec + 643, 256, 0.f, st));
     RUN(fill_launch(lo0, 1024, 0.f, st));
     // operand images of the current weights
-    for (int l = 0; l < 7; ++l) RUN(pack_weight_launch(p->layer[l].w, CIN[l], 1, COUT[l], CIN[l], wp + wpack_offset(l), st));
-    RUN(pack_weight_launch(p->fc3_w, C_FEAT, 1, C_EMB, C_FEAT, wp + wpack_offset(7), st));
-    if (code) RUN(pack_weight_launch(p->map_w, C_EMB, 1, C_MAP, C_EMB, wp + wpack_offset(8), st));
+    {
+        PackTable tbl;
+        for (int l = 0; l < 7; ++l) pack_table_add(tbl, p->layer[l].w, CIN[l], 1, COUT[l], CIN[l], wp + wpack_offset(l));
+        pack_table_add(tbl, p->fc3_w, C_FEAT, 1, C_EMB, C_FEAT, wp + wpack_offset(7));
+        if (code) pack_table_add(tbl, p->map_w, C_EMB, 1, C_MAP, C_EMB, wp + wpack_offset(8));
+        if (tr && bufs[B_WPACKT]) {
+            // transposed images for the data-gradient GEMMs of the backward that follows on these buffers
+            uint8_t* wt = reinterpret_cast<uint8_t*>(bufs[B_WPACKT]);
+            for (int l = 1; l < 7; ++l)
+                pack_table_add(tbl, p->layer[l].w + (l == 3 ? 3 : 0), 1, CIN[l], tin(l), COUT[l], wt + wpackt_offset(l));
+            pack_table_add(tbl, p->fc3_w, 1, C_FEAT, C_FEAT, C_EMB, wt + wpackt_offset(7));
+        }
+        RUN(pack_table_launch(tbl, st));
+    }
 
     auto finalize = [&](int layer, int slot_i, int Nd, double n) {
         Slot s = bn_slot(bufs, slot_i);
@@ -413,12 +424,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
     float* stats = F(B_STATS);
     uint8_t* wt = reinterpret_cast<uint8_t*>(bufs[B_WPACKT]);
 
-    // transposed weight images for the data-gradient GEMMs
-    for (int l = 1; l < 7; ++l) {
-        const float* w = p->layer[l].w + (l == 3 ? 3 : 0);
-        RUN(pack_weight_launch(w, 1, CIN[l], tin(l), COUT[l], wt + wpackt_offset(l), st));
-    }
-    RUN(pack_weight_launch(p->fc3_w, 1, C_FEAT, C_FEAT, C_EMB, wt + wpackt_offset(7), st));
+    // (the transposed weight images for the data-gradient GEMMs were packed by the training-mode forward)
     // weight gradients are accumulated with atomics (split-K): start from zero; biases in front of a BN get 0
     for (int l = 0; l < 7; ++l) {
         FACL_CHECK(cudaMemsetAsync(gr->dw[l], 0, sizeof(float) * COUT[l] * CIN[l], st));

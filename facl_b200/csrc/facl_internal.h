@@ -13,6 +13,20 @@ int group_launch(const float* points, int M, int N, int D, int S, int K, float r
 // pack.cu
 size_t packed_weight_bytes(int Md, int Kd);
 int pack_weight_launch(const float* src, long long stride_m, long long stride_k, int Md, int Kd, void* image, cudaStream_t st);
+struct PackJob {
+    const float* src;
+    long long sm, sk;
+    int Md, Kd, KBp;
+    long long task0;
+    uint8_t* img;
+};
+struct PackTable {
+    int n = 0;
+    long long total = 0;
+    PackJob job[20];
+};
+void pack_table_add(PackTable& tbl, const float* src, long long sm, long long sk, int Md, int Kd, void* image);
+int pack_table_launch(const PackTable& tbl, cudaStream_t st);
 
 }  // namespace facl
 

@@ -29,8 +29,7 @@ constexpr uint32_t ACT_LBO = 8192;        // MN-major activation image: 64-row b
 constexpr uint32_t ACT_SBO = 1024;        //                            8-channel groups 1 KB apart (16 KB per half)
 constexpr int ACT_BYTES = 16384;
 constexpr int NTHREADS_A = 17 * 32;        // pass A: warps 0-7 (idle z3 roles) are the h1 producers
-constexpr int NTHREADS_B = 21 * 32;        // pass B: warps 10,11,14,15 + 17..20 are the h1 producers
-constexpr int NPW = 8;                     // producer warps: 256 threads = 64 channels x 4 row quarters
+constexpr int NTHREADS_B = 17 * 32;        // pass B: warps 10,11,14,15 are the h1 producers (the z3 consumers own the issue slots)
 
 struct L1Params {
     const float* xt;          // [R][4]
@@ -90,6 +89,8 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nhl = p.nhl;
+    constexpr int NPW = PASS_B ? 4 : 8;        // producer warps: 64 channels x (2 | 4) row parts
+    constexpr int PROWS = TILE / (NPW / 2);    // rows per producer thread
     // ---- shared-memory carve-up (all operand images 1 KB aligned) ----
     uint8_t* w2s = smem;                                   // hi 8 KB | lo 8 KB (64 valid rows each)
     uint8_t* w3s = w2s + 16384;                            // [half][hi 16 KB | lo 16 KB]      (pass B)
@@ -173,10 +174,10 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                 }
             }
         }
-    } else if (PASS_B ? (warp == 10 || warp == 11 || warp == 14 || warp == 15 || warp >= 17) : (warp < 8)) {
+    } else if (PASS_B ? (warp == 10 || warp == 11 || warp == 14 || warp == 15) : (warp < 8)) {
         // ======================= producers: x -> h1 = relu(bn1(W1 x + b1)), thread = (channel, row quarter) ===============
-        const int pw = !PASS_B ? warp : (warp >= 17) ? (warp - 13) : (warp == 10) ? 0 : (warp == 11) ? 1 : (warp == 14) ? 2 : 3;
-        const int ptid = pw * 32 + lane;          // 0..255
+        const int pw = !PASS_B ? warp : (warp == 10) ? 0 : (warp == 11) ? 1 : (warp == 14) ? 2 : 3;
+        const int ptid = pw * 32 + lane;          // 0 .. 32 NPW - 1
         const int ch = ptid & 63, part = ptid >> 6;
         // BN1 folded into the 4-wide layer: h1 = max(wf . x + bf, 0)
         const float s1 = __ldg(p.scale1 + ch), t1 = __ldg(p.shift1 + ch);
@@ -197,14 +198,14 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             mbar_wait(&h1_empty[b], u ^ 1);
             uint8_t* img = h1s + b * 2 * ACT_BYTES;
 #pragma unroll 2
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < PROWS / 8; ++q) {
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    float4 x = xtile[part * 32 + q * 8 + e];
+                    float4 x = xtile[part * PROWS + q * 8 + e];
                     v[e] = fmaxf(fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf)))), 0.f);
                 }
-                store_act8(img, nhl, ch, part * 4 + q, v);
+                store_act8(img, nhl, ch, part * (PROWS / 8) + q, v);
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -1076,16 +1077,25 @@ __global__ void __launch_bounds__(256) l1_fin_kernel(const float* __restrict__ W
 }
 
 // dW1[i][:] = c0_i * A_i + c1_i * (C w1_i + b1_i * sx) + c2_i * sx   with C = sum x x^T, sx = sum x (z1 is affine in x)
-__global__ void l1_dw1_kernel(const float* __restrict__ amat, int P, const double* __restrict__ mom, const float* __restrict__ w1,
-                              const float* __restrict__ b1, const float* __restrict__ c0, const float* __restrict__ c1,
-                              const float* __restrict__ c2, float* __restrict__ dw1) {
-    int i = threadIdx.x;
-    if (i >= 64) return;
+__global__ void __launch_bounds__(1024) l1_dw1_kernel(const float* __restrict__ amat, int P, const double* __restrict__ mom,
+                                                      const float* __restrict__ w1, const float* __restrict__ b1,
+                                                      const float* __restrict__ c0, const float* __restrict__ c1,
+                                                      const float* __restrict__ c2, float* __restrict__ dw1) {
+    // 16 slices of the P partials x 64 channels, reduced through shared memory
+    __shared__ double red[16][64][4];
+    const int i = threadIdx.x & 63, slice = threadIdx.x >> 6;
     double a[4] = {0, 0, 0, 0};
-    for (int q = 0; q < P; ++q) {
-        float4 v = reinterpret_cast<const float4*>(amat)[(long long)q * 64 + i];
+    for (int q = slice; q < P; q += 16) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(amat) + (long long)q * 64 + i);
         a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
     }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) red[slice][i][d] = a[d];
+    __syncthreads();
+    if (slice > 0) return;
+    for (int sl = 1; sl < 16; ++sl)
+#pragma unroll
+        for (int d = 0; d < 4; ++d) a[d] += red[sl][i][d];
     const int idx[4][4] = {{4, 5, 6, 7}, {5, 8, 9, 10}, {6, 9, 11, 12}, {7, 10, 12, 13}};
     for (int d = 0; d < 4; ++d) {
         double zx = (double)b1[i] * mom[d];
@@ -1312,7 +1322,7 @@ int l1_dw1_launch(const float* amat, int P, const double* mom14, const float* w1
                   const float* c2, float* dw1, cudaStream_t st) {
     ScopedTimer timer(TAG_L1_MISC, st);
     count_launch();
-    l1_dw1_kernel<<<1, 64, 0, st>>>(amat, P, mom14, w1, b1, c0, c1, c2, dw1);
+    l1_dw1_kernel<<<1, 1024, 0, st>>>(amat, P, mom14, w1, b1, c0, c1, c2, dw1);
     return (int)cudaGetLastError();
 }
 

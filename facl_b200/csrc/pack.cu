@@ -30,7 +30,51 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, long long sm, 
     *reinterpret_cast<uint4*>(base + off) = hi;
     *reinterpret_cast<uint4*>(base + 16384 + off) = lo;
 }
+
+// several matrices in one launch (the per-step re-packing of all encoder weights): job table passed by value
+__global__ void pack_weights_batched_kernel(const PackTable tbl) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tbl.total) return;
+    int ji = 0;
+#pragma unroll 1
+    while (ji + 1 < tbl.n && t >= tbl.job[ji + 1].task0) ++ji;
+    const PackJob& jb = tbl.job[ji];
+    t -= jb.task0;
+    int j = (int)(t & 7);
+    int r = (int)((t >> 3) & 127);
+    long long tile = t >> 10;
+    int kb = (int)(tile % jb.KBp);
+    int mt = (int)(tile / jb.KBp);
+    int m = mt * 128 + r;
+    int k0 = kb * 64 + j * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        v[e] = (m < jb.Md && k0 + e < jb.Kd) ? __ldg(jb.src + (long long)m * jb.sm + (long long)(k0 + e) * jb.sk) : 0.f;
+    uint4 hi, lo;
+    split_bf16x8(v, hi, lo);
+    uint8_t* base = jb.img + tile * (2ll * 16384);
+    uint32_t off = sw128_offset((uint32_t)r, (uint32_t)j);
+    *reinterpret_cast<uint4*>(base + off) = hi;
+    *reinterpret_cast<uint4*>(base + 16384 + off) = lo;
+}
 }  // namespace
+
+void pack_table_add(PackTable& tbl, const float* src, long long sm, long long sk, int Md, int Kd, void* image) {
+    PackJob& jb = tbl.job[tbl.n++];
+    jb.src = src; jb.sm = sm; jb.sk = sk; jb.Md = Md; jb.Kd = Kd; jb.KBp = (Kd + 63) / 64;
+    jb.task0 = tbl.total;
+    jb.img = reinterpret_cast<uint8_t*>(image);
+    tbl.total += (long long)((Md + 127) / 128) * jb.KBp * 1024;
+}
+
+int pack_table_launch(const PackTable& tbl, cudaStream_t st) {
+    if (tbl.n <= 0) return 0;
+    ScopedTimer timer(TAG_PACK, st);
+    count_launch();
+    pack_weights_batched_kernel<<<div_up(tbl.total, 256), 256, 0, st>>>(tbl);
+    return (int)cudaGetLastError();
+}
 
 size_t packed_weight_bytes(int Md, int Kd) {
     size_t numMT = (Md + 127) / 128, KBp = (Kd + 63) / 64;
