@@ -6,6 +6,8 @@
 //
 //   forward / data-gradient:  D[m][n] = sum_k W[m][k] * act[k][n]      A = packed weight image, B = image (MN-major)
 //   weight-gradient        :  D[m][n] = sum_r dz[m][r] * act[n][r]     A, B = images (K-major over rows), split-K
+//   loss similarity / back :  the same two forms with the (row-major) embedding matrices read as images whose
+//                             "channels" are embedding rows, plus D[m][n] = sum_r W[m][r] * img[n][r] (packed A, image B)
 //
 // Warp roles: warps 0-3 epilogue (TMEM lane = output channel), warp 4 MMA issuer, warp 5 TMA issuer.
 #include "gemm_tc.cuh"
@@ -35,7 +37,8 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mma_n = (p.Nd >= N_TILE) ? N_TILE : ((p.Nd + 15) & ~15);
-    const bool wgrad = (p.a_mode == A_IMAGE);
+    const bool a_img = (p.a_mode == A_IMAGE);        // A = activation image, K = its rows (else: packed weight tiles)
+    const bool b_k = (p.b_mode == B_IMAGE_K);        // B image reduced over its rows (else over its channels, MN-major)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NUM_STAGES; ++i) {
@@ -171,6 +174,10 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (i < nvalid) p.out[(long long)(n0 + i) * p.ldo + c] = v[i];
+                } else if (p.out_mode == OUT_ROWMAJOR_ACC) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nvalid) p.out[(long long)(n0 + i) * p.ldo + c] += v[i];
                 }
             }
             tc_fence_before_sync();
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
         }
     } else if (warp == 4) {
         // =============================== MMA issuer ===============================
-        const uint32_t idesc = umma_idesc_bf16(M_TILE, mma_n) | (wgrad ? 0u : UMMA_B_MN_MAJOR);
+        const uint32_t idesc = umma_idesc_bf16(M_TILE, mma_n) | (b_k ? 0u : UMMA_B_MN_MAJOR);
         int stage = 0, phase = 0;
         for (int it = 0; sched.get(it, p, w); ++it) {
             const int buf = it & 1;
@@ -203,11 +210,11 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                         const uint32_t acc = (kb > w.kb0 || ks > 0) ? 1u : 0u;
                         const uint32_t ko = ks * 32;
                         const uint64_t ad_hi = umma_desc_sw128(a_hi + ko);
-                        const uint64_t bd_hi = wgrad ? umma_desc_sw128(b_hi + ko)
+                        const uint64_t bd_hi = b_k ? umma_desc_sw128(b_hi + ko)
                                                      : umma_desc_mn_sw128(b_hi + ks * 2 * IMG_SBO, IMG_LBO, IMG_SBO);
                         umma_bf16_ss(d_tmem, ad_hi, bd_hi, idesc, acc);
                         if (NHL == 2) {
-                            const uint64_t bd_lo = wgrad ? umma_desc_sw128(b_lo + ko)
+                            const uint64_t bd_lo = b_k ? umma_desc_sw128(b_lo + ko)
                                                          : umma_desc_mn_sw128(b_lo + ks * 2 * IMG_SBO, IMG_LBO, IMG_SBO);
                             umma_bf16_ss(d_tmem, ad_hi, bd_lo, idesc, 1u);
                             umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ko), bd_hi, idesc, 1u);
@@ -238,32 +245,46 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                 uint8_t* a_hi = st;
                 uint8_t* b_hi = st + A_TILE_BYTES * NHL;
                 uint8_t* b_lo = b_hi + B_TILE_BYTES;
-                if (!wgrad) {
-                    // A: one packed weight tile (hi | lo adjacent);  B: up to four 64-row blocks x 8 channel atoms
-                    const int rb0 = w.nt * (N_TILE / 64);
-                    int nrb = p.b_img.rbs - rb0;
+                uint32_t bytes = 0;
+                // ---- A ----
+                int na = 0;
+                if (a_img) {                         // 16 channel atoms of row block kb, contiguous
+                    na = p.a_img.cgs - w.mt * 16;
+                    na = na > 16 ? 16 : na;
+                    bytes += (uint32_t)(na * 1024 * NHL);
+                } else {
+                    bytes += (uint32_t)(A_TILE_BYTES * NHL);
+                }
+                // ---- B ----
+                int nb = 0, nrb = 0;
+                const int rb0 = w.nt * (N_TILE / 64);
+                if (b_k) {                           // 32 channel atoms of row block kb, contiguous
+                    nb = p.b_img.cgs - w.nt * 32;
+                    nb = nb > 32 ? 32 : nb;
+                    bytes += (uint32_t)(nb * 1024 * NHL);
+                } else {                             // up to four 64-row blocks x the 8 channel atoms of k-block kb
+                    nrb = p.b_img.rbs - rb0;
                     nrb = nrb > N_TILE / 64 ? N_TILE / 64 : nrb;
-                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(A_TILE_BYTES * NHL + nrb * 8192 * NHL));
+                    bytes += (uint32_t)(nrb * 8192 * NHL);
+                }
+                mbar_arrive_expect_tx(&full[stage], bytes);
+                if (a_img) {
+                    const long long aoff = ((long long)kb * p.a_img.cgs + w.mt * 16) * 1024;
+                    tma_bulk_g2s(a_hi, ai_hi + aoff, na * 1024, &full[stage]);
+                    if (NHL == 2) tma_bulk_g2s(a_hi + A_TILE_BYTES, ai_lo + aoff, na * 1024, &full[stage]);
+                } else {
                     tma_bulk_g2s(a_hi, wimg + ((long long)w.mt * p.a_packed_kblocks + kb) * (2ll * A_TILE_BYTES), A_TILE_BYTES * NHL,
                                  &full[stage]);
+                }
+                if (b_k) {
+                    const long long boff = ((long long)kb * p.b_img.cgs + w.nt * 32) * 1024;
+                    tma_bulk_g2s(b_hi, bi_hi + boff, nb * 1024, &full[stage]);
+                    if (NHL == 2) tma_bulk_g2s(b_lo, bi_lo + boff, nb * 1024, &full[stage]);
+                } else {
                     for (int r = 0; r < nrb; ++r) {
                         const long long off = ((long long)(rb0 + r) * p.b_img.cgs + kb * 8) * 1024;
                         tma_bulk_g2s(b_hi + r * 8192, bi_hi + off, 8192, &full[stage]);
                         if (NHL == 2) tma_bulk_g2s(b_lo + r * 8192, bi_lo + off, 8192, &full[stage]);
-                    }
-                } else {
-                    // reduction over the 64 rows of row block kb: A = 16 channel atoms, B = 32 channel atoms, both contiguous
-                    int na = p.a_img.cgs - w.mt * 16, nb = p.b_img.cgs - w.nt * 32;
-                    na = na > 16 ? 16 : na;
-                    nb = nb > 32 ? 32 : nb;
-                    const long long aoff = ((long long)kb * p.a_img.cgs + w.mt * 16) * 1024;
-                    const long long boff = ((long long)kb * p.b_img.cgs + w.nt * 32) * 1024;
-                    mbar_arrive_expect_tx(&full[stage], (uint32_t)((na + nb) * 1024 * NHL));
-                    tma_bulk_g2s(a_hi, ai_hi + aoff, na * 1024, &full[stage]);
-                    tma_bulk_g2s(b_hi, bi_hi + boff, nb * 1024, &full[stage]);
-                    if (NHL == 2) {
-                        tma_bulk_g2s(a_hi + A_TILE_BYTES, ai_lo + aoff, na * 1024, &full[stage]);
-                        tma_bulk_g2s(b_lo, bi_lo + boff, nb * 1024, &full[stage]);
                     }
                 }
                 if (++stage == NUM_STAGES) {
@@ -375,22 +396,24 @@ int launch_gemm_img(const GemmParams& p, cudaStream_t stream) {
         FACL_CHECK(cudaFuncSetAttribute(gemm_img_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured = true;
     }
-    const bool wgrad = p.a_mode == A_IMAGE;
-    if (wgrad != (p.b_mode == B_IMAGE_K)) return (int)cudaErrorInvalidValue;
-    if (!wgrad && (p.a_mode != A_PACKED || p.b_mode != B_IMAGE_MN)) return (int)cudaErrorInvalidValue;
+    const bool a_img = p.a_mode == A_IMAGE, b_k = p.b_mode == B_IMAGE_K;
+    if ((!a_img && p.a_mode != A_PACKED) || (!b_k && p.b_mode != B_IMAGE_MN) || (a_img && !b_k)) return (int)cudaErrorInvalidValue;
     if (p.Md <= 0 || p.Nd <= 0 || p.Kd <= 0 || (p.nsplit != 1 && p.nsplit != 3)) return (int)cudaErrorInvalidValue;
     if (p.pool && ((p.pool & (p.pool - 1)) != 0 || p.pool > N_TILE)) return (int)cudaErrorInvalidValue;
     if (!p.b_img.hi || (p.nsplit == 3 && !p.b_img.lo)) return (int)cudaErrorInvalidValue;
     const int numMT = (p.Md + M_TILE - 1) / M_TILE, numNT = (p.Nd + N_TILE - 1) / N_TILE, KB = (p.Kd + K_BLK - 1) / K_BLK;
-    if (wgrad) {
-        // Kd = rows (a multiple of 64 after padding); every row block of both images is read
-        if (!p.a_img.hi || (p.nsplit == 3 && !p.a_img.lo) || p.a_img.rbs != KB || p.b_img.rbs != KB) return (int)cudaErrorInvalidValue;
-        if (p.a_img.cgs * 8 < p.Md || p.b_img.cgs * 8 < p.Nd) return (int)cudaErrorInvalidValue;
-        if (p.out_mode != OUT_ATOMIC_CHMAJOR || p.stats || p.pool) return (int)cudaErrorInvalidValue;
-    } else {
-        if (p.b_img.cgs < KB * 8 || (long long)p.b_img.rbs * 64 < p.Nd || p.a_packed_kblocks < KB) return (int)cudaErrorInvalidValue;
-        if (p.ksplit > 1) return (int)cudaErrorInvalidValue;
+    if (a_img) {
+        // Kd = rows (a multiple of 64 after padding); every row block of the image is read
+        if (!p.a_img.hi || (p.nsplit == 3 && !p.a_img.lo) || p.a_img.rbs != KB || p.a_img.cgs * 8 < p.Md) return (int)cudaErrorInvalidValue;
+    } else if (!p.a_packed || p.a_packed_kblocks < KB) {
+        return (int)cudaErrorInvalidValue;
     }
+    if (b_k) {
+        if (p.b_img.rbs != KB || p.b_img.cgs * 8 < p.Nd) return (int)cudaErrorInvalidValue;
+    } else if (p.b_img.cgs < KB * 8 || (long long)p.b_img.rbs * 64 < p.Nd) {
+        return (int)cudaErrorInvalidValue;
+    }
+    if (p.ksplit > 1 && (p.out_mode != OUT_ATOMIC_CHMAJOR || p.stats || p.pool)) return (int)cudaErrorInvalidValue;
     int grid;
     if (p.ksplit > 1) {
         if (p.ksplit > KB) return (int)cudaErrorInvalidValue;

@@ -478,7 +478,13 @@ __device__ __forceinline__ float produce_h1_tile64(const float4* xtile, uint8_t*
 // warps 10,11,14,15 : x -> h1 image producers
 // warps 16,17,20,21 : dh2 consumers (thread = channel j): + q3, ReLU2 mask, BN2-backward sums, image -> HBM
 // warp 18           : MMA issuer (warp 19 idles)
-// TMEM columns: D2[b] 0/64, DH2[b] 128/192, DW3s[h] 256/320, H2 384
+// TMEM columns: D2[b] 0/64, DH2 128..255 ([hi | lo] column halves), DW3s[h] 256/320, H2 384
+//
+// tcgen05.mma time on these narrow tiles is set by the operand bytes it pulls from shared memory (the 4 KB A tile above
+// all), not by the math, so the bf16x3 scheme is issued as TWO instructions per k-step instead of three: the B images
+// are stored [hi | lo], and one N = 128 instruction against A_hi yields A_hi B_hi (columns 0..63) and A_hi B_lo (columns
+// 64..127); A_lo B_hi is added onto columns 0..63.  A consumer thread adds its two column halves in registers.  H2, whose
+// rows are only ever summed, uses the stacked-A form instead (h2 stage = [hi | lo] rows, see pass D).
 // --------------------------------------------------------------------------------------------------------------------
 constexpr int C_THREADS = 22 * 32;
 
@@ -495,7 +501,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     uint8_t* xs = sps + 65536;                 // 2 stages x 64 rows x 16 B
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * BT * 16);
     uint64_t *h1_full = bars, *h1_empty = bars + 1, *d2_full = bars + 2, *d2_empty = bars + 4, *h2_full = bars + 6,
-             *h2_empty = bars + 8, *sp_full = bars + 10, *sp_empty = bars + 11, *dh_full = bars + 12, *dh_empty = bars + 14,
+             *h2_empty = bars + 8, *sp_full = bars + 10, *sp_empty = bars + 11, *dh_full = bars + 12, *dh_empty = bars + 13,
              *w_bar = bars + 16, *fin_bar = bars + 17;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
@@ -510,10 +516,12 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         for (int i = 0; i < 2; ++i) {
             mbar_init(&d2_full[i], 1);
             mbar_init(&d2_empty[i], 8);        // h2 producers + dh2 consumers both read z2
+        }
+        mbar_init(dh_full, 1);
+        mbar_init(dh_empty, 4);
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&h2_full[i], 4);
             mbar_init(&h2_empty[i], 1);
-            mbar_init(&dh_full[i], 1);
-            mbar_init(&dh_empty[i], 4);
         }
         mbar_init(sp_full, 8);
         mbar_init(sp_empty, 1);
@@ -534,6 +542,9 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     const uint32_t idesc_mn = umma_idesc_bf16(128, BT) | UMMA_B_MN_MAJOR;                      // weights x activation image
     const uint32_t idesc_dg = umma_idesc_bf16(128, BT) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;    // W3^T x Sp
     const uint32_t idesc_kk = umma_idesc_bf16(128, 64);                                        // reduction over rows
+    const int nB = (nhl == 2) ? 2 * BT : BT;                                                   // [hi | lo] stacked B operand
+    const uint32_t idesc_mn2 = umma_idesc_bf16(128, nB) | UMMA_B_MN_MAJOR;
+    const uint32_t idesc_dg2 = umma_idesc_bf16(128, nB) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;
 
     if (warp == 18) {
         if (lane == 0) {
@@ -553,7 +564,16 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             const uint32_t p3_hi = smem_u32(p3s), p3_lo = p3_hi + 8192;
             const uint32_t h1 = smem_u32(h1s);
             const uint32_t sp_hi = smem_u32(sps), sp_lo = sp_hi + 32768;
-            auto issue_z2 = [&](int it) {          // z2(it) = W2 h1(it)
+            // D (+)= A B with B = [hi | lo] (MN-major, `b_lbo` bytes between the halves): A_hi x [B_hi | B_lo], then A_lo x B_hi
+            auto mma_w_b2 = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b, uint32_t b_lbo, bool first) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t bd = umma_desc_mn_sw128(b + ks * 2048, b_lbo, 1024);
+                    umma_bf16_ss(d, umma_desc_sw128(a_hi + ks * 32), bd, idesc_mn2, (first && ks == 0) ? 0u : 1u);
+                    if (nhl == 2) umma_bf16_ss(d, umma_desc_sw128(a_lo + ks * 32), bd, idesc_mn, 1u);
+                }
+            };
+            auto issue_z2 = [&](int it) {          // z2(it) = W2 h1(it): plain 3-term form, double-buffered accumulator
                 const int b = it & 1, u = (it >> 1) & 1;
                 mbar_wait(h1_full, it & 1);
                 mbar_wait(&d2_empty[b], u ^ 1);
@@ -566,31 +586,33 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
 #pragma unroll 1
             for (int it = 0; it < my_tiles; ++it) {
                 const int b = it & 1, u = (it >> 1) & 1;
-                if (it + 1 < my_tiles) issue_z2(it + 1);
                 const uint32_t h2 = smem_u32(h2s + b * 2 * IMG64);
                 mbar_wait(&h2_full[b], u);
                 mbar_wait(sp_full, it & 1);
-                mbar_wait(&dh_empty[b], u ^ 1);
                 tc_fence_after_sync();
-                // sparse products first, so the Sp image is free again while the dense ones run
-#pragma unroll 1
-                for (int ks = 0; ks < 16; ++ks) {   // dh2 = W3^T Sp: reduction over the 256 channels
-                    const uint32_t wa = smem_u32(w3s + (ks >> 3) * 32768) + (ks & 7) * 2048;
-                    const uint64_t a_hi = umma_desc_mn_sw128(wa, 16384, 1024), a_lo = umma_desc_mn_sw128(wa + 16384, 16384, 1024);
-                    const uint64_t b_hi = umma_desc_mn_sw128(sp_hi + ks * 2048, 8192, 1024);
-                    umma_bf16_ss(tmem_base + 128 + 64 * b, a_hi, b_hi, idesc_dg, ks > 0 ? 1u : 0u);
-                    if (nhl == 2) {
-                        umma_bf16_ss(tmem_base + 128 + 64 * b, a_hi, umma_desc_mn_sw128(sp_lo + ks * 2048, 8192, 1024), idesc_dg, 1u);
-                        umma_bf16_ss(tmem_base + 128 + 64 * b, a_lo, b_hi, idesc_dg, 1u);
-                    }
-                }
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h)          // dW3s += Sp h2^T
                     mma_rows64(tmem_base + 256 + 64 * h, sp_hi + h * 16384, sp_lo + h * 16384, h2, h2 + IMG64, nhl, idesc_kk, it == 0);
+                if (it + 1 < my_tiles) issue_z2(it + 1);
+                mbar_wait(dh_empty, (it & 1) ^ 1);
+                tc_fence_after_sync();
+#pragma unroll 1
+                for (int ks = 0; ks < 16; ++ks) {   // dh2 = W3^T Sp: reduction over the 256 channels
+                    const uint32_t wa = smem_u32(w3s + (ks >> 3) * 32768) + (ks & 7) * 2048;
+                    const uint64_t bd = umma_desc_mn_sw128(sp_hi + ks * 2048, 32768, 1024);
+                    umma_bf16_ss(tmem_base + 128, umma_desc_mn_sw128(wa, 16384, 1024), bd, idesc_dg2, ks > 0 ? 1u : 0u);
+                    if (nhl == 2) umma_bf16_ss(tmem_base + 128, umma_desc_mn_sw128(wa + 16384, 16384, 1024), bd, idesc_dg, 1u);
+                }
                 umma_commit(sp_empty);
-                mma_w_act64(tmem_base + 128 + 64 * b, p3_hi, p3_lo, h2, h2 + IMG64, nhl, idesc_mn, false);   // dh2 += P3 h2
-                umma_commit(&dh_full[b]);
-                mma_rows64(tmem_base + 384, h2, h2 + IMG64, h2, h2 + IMG64, nhl, idesc_kk, it == 0);           // H2 += h2 h2^T
+                mma_w_b2(tmem_base + 128, p3_hi, p3_lo, h2, 8192, false);                                       // dh2 += P3 h2
+                umma_commit(dh_full);
+                // H2 += h2 h2^T with the stage's [hi | lo] rows as one 128-row A tile: lanes 0..63 h2_hi (.), lanes 64..127 h2_lo (.)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ad = umma_desc_sw128(h2 + ks * 32);
+                    umma_bf16_ss(tmem_base + 384, ad, umma_desc_sw128(h2 + ks * 32), idesc_kk, (it == 0 && ks == 0) ? 0u : 1u);
+                    if (nhl == 2) umma_bf16_ss(tmem_base + 384, ad, umma_desc_sw128(h2 + IMG64 + ks * 32), idesc_kk, 1u);
+                }
                 umma_commit(&h2_empty[b]);
             }
             umma_commit(fin_bar);
@@ -625,6 +647,16 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                     p.dbg_mask1[((t0 + it) * 64 + ch) * 64 + half * 32 + r] = v > 0.f ? 1 : 0;
                 }
             }
+        }
+        if (nhl == 2) {     // these warps sit on TMEM lanes 64..127: the h2_lo rows of the stacked H2 accumulator
+            mbar_wait(fin_bar, 0);
+            tc_fence_after_sync();
+            const int lg = warp & 1, colhalf = (warp >= 14) ? 1 : 0, j = lg * 32 + lane;
+            float a[32];
+            tmem_ld32(tmem_base + ((uint32_t)(64 + lg * 32) << 16) + (uint32_t)(384 + colhalf * 32), a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(p.gram + j * 64 + colhalf * 32 + i, a[i]);
         }
     } else if (warp == 8 || warp == 9 || warp == 12 || warp == 13) {
         // ---- z2 -> h2 = relu(bn2(z2)) image (thread = channel j), s2 = sum h2 ----
@@ -685,20 +717,30 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             const int b = it & 1, u = (it >> 1) & 1;
             mbar_wait(&d2_full[b], u);
             tc_fence_after_sync();
-            float z[32];
+            float z[32], g[32];
             tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(64 * b + colhalf * 32), z);
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&d2_empty[b]);
-            mbar_wait(&dh_full[b], u);
+            mbar_wait(dh_full, it & 1);
             tc_fence_after_sync();
-            float g[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 + 64 * b + colhalf * 32), g);
-            tmem_ld_wait();
+            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 + colhalf * 32), g);
+            if (nhl == 2) {
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq) {       // the B_lo products (columns 64..127), 16 at a time to keep registers low
+                    float gl[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(192 + colhalf * 32 + hq * 16), gl);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) g[hq * 16 + i] += gl[i];
+                }
+            } else {
+                tmem_ld_wait();
+            }
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&dh_empty[b]);
+            if (lane == 0) mbar_arrive(dh_empty);
             uint8_t* out = p.dh2 + (t0 + it) * (2 * IMG64);
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
@@ -783,7 +825,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
 // pass D   (14 warps)
 // warps 0-7   : dh1 consumers: TMEM lane quarter = warp % 4, column half = warp / 4
 // warps 8-11  : x -> h1 image producers          warp 12 : MMA issuer          warp 13 : bulk-TMA loader of dh2' tiles
-// TMEM columns: DH1[b] 0/64, [dW2s ; H1] 128
+// TMEM columns: DH1[b] 0..127 / 128..255 (column halves = B_hi / B_lo products), [dW2s ; H1] 256
 //
 // Every product here has only 64 real output rows, so the M = 128 instruction is fed STACKED operands instead of padding:
 //  * a weight image is stored [hi 64 rows | lo 64 rows]; read as one 128-row A tile, lanes 0..63 receive A_hi * B and lanes
@@ -830,7 +872,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
         mbar_fence_init();
     }
     if (warp == 12) {
-        tmem_alloc(tmem_slot, 256);
+        tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
     tc_fence_before_sync();
@@ -840,6 +882,11 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
     const uint32_t idesc_mn = umma_idesc_bf16(128, BT) | UMMA_B_MN_MAJOR;
     const uint32_t idesc_dg = umma_idesc_bf16(128, BT) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;
     const uint32_t idesc_kk = umma_idesc_bf16(128, 64);
+    // B images are [hi | lo] (2 * IMG64 apart): one N = 128 instruction gives the products with both halves (columns 0..63 / 64..127)
+    const int nB = (nhl == 2) ? 2 * BT : BT;
+    const uint32_t idesc_mn2 = umma_idesc_bf16(128, nB) | UMMA_B_MN_MAJOR;
+    const uint32_t idesc_dg2 = umma_idesc_bf16(128, nB) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;
+    (void)idesc_mn; (void)idesc_dg;
 
     if (warp == 12) {
         if (lane == 0) {
@@ -863,22 +910,16 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
                 const uint32_t dz = smem_u32(stg + s * D_STAGE_BYTES), h1 = dz + IMG64;   // lo halves 2 * IMG64 further
                 // dh1[i][r] = sum_j (e0 W2)[j][i] dh2'[j][r] + sum_i' P2[i][i'] h1[i'][r];  lanes 0..63 hi part, 64..127 lo part
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t ad = umma_desc_mn_sw128(ew + ks * 2048, 8192, 1024);
-                    umma_bf16_ss(tmem_base + 64 * b, ad, umma_desc_mn_sw128(dz + ks * 2048, 8192, 1024), idesc_dg, ks > 0 ? 1u : 0u);
-                    if (nhl == 2)
-                        umma_bf16_ss(tmem_base + 64 * b, ad, umma_desc_mn_sw128(dz + 2 * IMG64 + ks * 2048, 8192, 1024), idesc_dg, 1u);
-                }
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16_ss(tmem_base + 128 * b, umma_desc_mn_sw128(ew + ks * 2048, 8192, 1024),
+                                 umma_desc_mn_sw128(dz + ks * 2048, 2 * IMG64, 1024), idesc_dg2, ks > 0 ? 1u : 0u);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t ad = umma_desc_sw128(p2 + ks * 32);
-                    umma_bf16_ss(tmem_base + 64 * b, ad, umma_desc_mn_sw128(h1 + ks * 2048, 8192, 1024), idesc_mn, 1u);
-                    if (nhl == 2)
-                        umma_bf16_ss(tmem_base + 64 * b, ad, umma_desc_mn_sw128(h1 + 2 * IMG64 + ks * 2048, 8192, 1024), idesc_mn, 1u);
-                }
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16_ss(tmem_base + 128 * b, umma_desc_sw128(p2 + ks * 32), umma_desc_mn_sw128(h1 + ks * 2048, 2 * IMG64, 1024),
+                                 idesc_mn2, 1u);
                 umma_commit(&dh_full[b]);
                 // [dW2s ; H1] += [dh2' ; h1] h1^T  (reduction over the 64 rows)
-                mma_rows64(tmem_base + 128, dz, dz + 2 * IMG64, h1, h1 + 2 * IMG64, nhl, idesc_kk, it == 0);
+                mma_rows64(tmem_base + 256, dz, dz + 2 * IMG64, h1, h1 + 2 * IMG64, nhl, idesc_kk, it == 0);
                 umma_commit(&st_empty[s]);
                 if (++s == D_STAGES) { s = 0; ph ^= 1; }
             }
@@ -959,8 +1000,16 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
             mbar_wait(&dh_full[b], u);
             tc_fence_after_sync();
             float g[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(64 * b + colhalf * 32), g);
-            tmem_ld_wait();
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 * b + colhalf * 32), g);
+            if (nhl == 2) {
+                float gl[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 * b + 64 + colhalf * 32), gl);
+                tmem_ld_wait();
+#pragma unroll
+                for (int r = 0; r < 32; ++r) g[r] += gl[r];
+            } else {
+                tmem_ld_wait();
+            }
             tc_fence_before_sync();
             if (live) {
 #pragma unroll
@@ -989,7 +1038,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
         mbar_wait(fin_bar, 0);
         tc_fence_after_sync();
         float a[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 + colhalf * 32), a);
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(256 + colhalf * 32), a);
         tmem_ld_wait();
         float* dst = (part == 0 ? p.dw2s : p.gram) + i * 64 + colhalf * 32;
 #pragma unroll
@@ -999,7 +1048,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
     __syncthreads();
     if (warp == 12) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 

@@ -200,6 +200,7 @@ struct LossWs {
     float *S, *rmax, *rsum, *lcG, *pgG, *lcC, *pgC;
     int* inv;
     uint8_t *img_keys, *img_x, *img_xg;
+    uint8_t *im_x, *im_xg, *im_keys, *im_ds;      // activation images (gemm_img.cu): embeddings [rows as channels][C], dS [rows][Mk]
 };
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 size_t loss_ws_layout(int G, int Bl, int R, int C, uint8_t* base, LossWs* w) {
@@ -220,7 +221,12 @@ size_t loss_ws_layout(int G, int Bl, int R, int C, uint8_t* base, LossWs* w) {
     uint8_t* p8 = take(packed_weight_bytes(C, (int)Mk));
     uint8_t* p9 = take(packed_weight_bytes(C, (int)Ml));
     uint8_t* p10 = take(packed_weight_bytes(C, Bl));
+    uint8_t* p11 = take(2 * act_image_half_bytes((int)Ml, C));
+    uint8_t* p12 = take(2 * act_image_half_bytes(Bl, C));
+    uint8_t* p13 = take(2 * act_image_half_bytes((int)Mk, C));
+    uint8_t* p14 = take(2 * act_image_half_bytes((int)Ml, (long long)Mk));
     if (w) {
+        w->im_x = p11; w->im_xg = p12; w->im_keys = p13; w->im_ds = p14;
         w->S = (float*)pS; w->rmax = (float*)p1; w->rsum = (float*)p2; w->lcG = (float*)p3; w->pgG = (float*)p4;
         w->lcC = (float*)p5; w->pgC = (float*)p6; w->inv = (int*)p7; w->img_keys = p8; w->img_x = p9; w->img_xg = p10;
     }
@@ -249,23 +255,42 @@ int contrast_losses(const float* x, const float* xg, const float* keys, int G, i
     loss_ws_layout(G, Bl, R, C, reinterpret_cast<uint8_t*>(workspace), &w);
     count_launch(2 + 2 * (want_circle ? 2 : 0) + 2 * (want_global ? 1 : 0));   // the small loss kernels below
 
-    auto sim = [&](const float* a, int rows, float* out) {   // out[rows][Mk] = a keys^T
+    const int nhl = nsplit == 3 ? 2 : 1;
+    auto image = [&](uint8_t* buf, int ch, long long rows) {
+        ActImage im;
+        im.hi = buf;
+        im.lo = buf + act_image_half_bytes(ch, rows);
+        im.cgs = ((ch + 63) / 64) * 8;
+        im.rbs = (int)((rows + 63) / 64);
+        return im;
+    };
+    // a row-major matrix [rows][ld] is the "channel-major" source of an image whose channels are its rows
+    auto make_image = [&](const float* src, int rows, long long cols, uint8_t* buf) {
+        OperandSrc o;
+        memset(&o, 0, sizeof(o));
+        o.src0 = src; o.ld = cols;
+        return act_image_launch(o, 0, rows, cols, nullptr, 0, nhl, image(buf, rows, cols), TAG_LOSS_MISC, st);
+    };
+    const bool keys_are_x = (keys == x) && (R == 1);     // single rank: one image serves as anchors and keys
+    const ActImage im_keys = image(keys_are_x ? w.im_x : w.im_keys, Mk, C);
+    auto sim = [&](const ActImage& a, int rows, float* out) {   // out[rows][Mk] = a keys^T  (reduction over the C "rows")
         GemmParams g;
         memset(&g, 0, sizeof(g));
         g.Md = rows; g.Nd = Mk; g.Kd = C; g.nsplit = nsplit; g.ksplit = 1;
-        g.a_mode = A_ROWMAJOR; g.a.src0 = a; g.a.ld = C;
-        g.b_mode = B_ROWMAJOR; g.b.src0 = keys; g.b.ld = C;
+        g.a_mode = A_IMAGE; g.a_img = a;
+        g.b_mode = B_IMAGE_K; g.b_img = im_keys;
         g.out_mode = OUT_CHMAJOR; g.out = out; g.ldo = Mk;
         g.tag = TAG_LOSS_GEMM;
         return launch_gemm_tc(g, st);
     };
-    // out[Nd rows][C] (+)= dS-block * features, with the feature matrix (transposed) as the packed "A" operand
-    auto dgemm = [&](const uint8_t* img, int Kd, int b_mode, const float* ds, int Nd, float* out, int accumulate) {
+    // out[Nd rows][C] (+)= dS-block * features, with the feature matrix (transposed) as the packed "A" operand and the
+    // dS block [rows][Mk] as an image: reduced over its rows-as-channels (b_mode MN) or over its Mk columns (b_mode K)
+    auto dgemm = [&](const uint8_t* img, int Kd, int b_mode, const ActImage& ds, int Nd, float* out, int accumulate) {
         GemmParams g;
         memset(&g, 0, sizeof(g));
         g.Md = C; g.Nd = Nd; g.Kd = Kd; g.nsplit = nsplit; g.ksplit = 1;
         g.a_mode = A_PACKED; g.a_packed = img; g.a_packed_kblocks = (Kd + 63) / 64;
-        g.b_mode = b_mode; g.b.src0 = ds; g.b.ld = Mk;
+        g.b_mode = b_mode; g.b_img = ds;
         g.out_mode = accumulate ? OUT_ROWMAJOR_ACC : OUT_ROWMAJOR; g.out = out; g.ldo = C;
         g.tag = TAG_LOSS_GEMM;
         return launch_gemm_tc(g, st);
@@ -273,13 +298,16 @@ int contrast_losses(const float* x, const float* xg, const float* keys, int G, i
 
     float* Sx = w.S;
     float* Sg = w.S + (size_t)Ml * Mk;
+    if (want_circle || keys_are_x) RUN(make_image(x, Ml, C, w.im_x));
+    if (!keys_are_x) RUN(make_image(keys, Mk, C, w.im_keys));
     if (want_circle) {
-        RUN(sim(x, Ml, Sx));
+        RUN(sim(image(w.im_x, Ml, C), Ml, Sx));
         invert_order_kernel<<<1, 256, 0, st>>>(order, G, w.inv);
         loss_rowstats_kernel<<<Ml, 128, 0, st>>>(w.S, ix, 0, Ml, w.rmax, w.rsum);
     }
     if (want_global) {
-        RUN(sim(xg, Bl, Sg));
+        RUN(make_image(xg, Bl, C, w.im_xg));
+        RUN(sim(image(w.im_xg, Bl, C), Bl, Sg));
         loss_rowstats_kernel<<<Bl, 128, 0, st>>>(w.S, ix, Ml, Bl, w.rmax, w.rsum);
     }
     loss_finalize_kernel<<<1, 256, 0, st>>>(w.S, ix, order, w.rmax, w.rsum, want_global, want_circle, loss, w.lcG, w.pgG, w.lcC,
@@ -295,8 +323,9 @@ int contrast_losses(const float* x, const float* xg, const float* keys, int G, i
         FACL_CHECK_LAUNCH();
         RUN(pack_weight_launch(xg, 1, C, C, Bl, w.img_xg, st));
         // dxg[b] = sum_j dS_g[b][j] keys[j] ;  dkeys[j] = sum_b dS_g[b][j] xg[b]
-        RUN(dgemm(w.img_keys, Mk, B_ROWMAJOR, Sg, Bl, dxg, 0));
-        RUN(dgemm(w.img_xg, Bl, B_CHMAJOR, Sg, Mk, dkeys, 0));
+        RUN(make_image(Sg, Bl, Mk, w.im_ds));
+        RUN(dgemm(w.img_keys, Mk, B_IMAGE_K, image(w.im_ds, Bl, Mk), Bl, dxg, 0));
+        RUN(dgemm(w.img_xg, Bl, B_IMAGE_MN, image(w.im_ds, Bl, Mk), Mk, dkeys, 0));
         keys_written = true;
         if (one_buffer) anchor_written = true;
     }
@@ -305,10 +334,11 @@ int contrast_losses(const float* x, const float* xg, const float* keys, int G, i
         FACL_CHECK_LAUNCH();
         RUN(pack_weight_launch(x, 1, C, C, Ml, w.img_x, st));
         // dx_anchor[a] = sum_j dS[a][j] keys[j]   and   dkeys[j] += sum_a dS[a][j] x[a]
-        RUN(dgemm(w.img_keys, Mk, B_ROWMAJOR, Sx, Ml, dx_anchor, anchor_written ? 1 : 0));
+        RUN(make_image(Sx, Ml, Mk, w.im_ds));
+        RUN(dgemm(w.img_keys, Mk, B_IMAGE_K, image(w.im_ds, Ml, Mk), Ml, dx_anchor, anchor_written ? 1 : 0));
         anchor_written = true;
         if (one_buffer) keys_written = true;
-        RUN(dgemm(w.img_x, Ml, B_CHMAJOR, Sx, Mk, dkeys, keys_written ? 1 : 0));
+        RUN(dgemm(w.img_x, Ml, B_IMAGE_MN, image(w.im_ds, Ml, Mk), Mk, dkeys, keys_written ? 1 : 0));
         keys_written = true;
     }
     if (!anchor_written) FACL_CHECK(cudaMemsetAsync(dx_anchor, 0, sizeof(float) * (size_t)Ml * C, st));
