@@ -213,6 +213,12 @@ def run_ours(args):
     M = G * B
     R3, R1 = M * 64, M * 64 * 64
     rows = [R1, R1, R1, R3, R3, R3, M + B, M + B, M]
+    # algorithmic FLOPs per launch of the fused net3DV_1 passes: A = layer-2 forward (statistics pass),
+    # B = layer-2 + layer-3 forward, C = layer-3 data + weight gradient, D = layer-2 data + weight gradient + layer-1 weight gradient
+    l1_flops = {39: 2.0 * 64 * 64 * R1, 40: 2.0 * (64 * 64 + 64 * 256) * R1, 41: 4.0 * 64 * 256 * R1,
+                42: (4.0 * 64 * 64 + 2.0 * 4 * 64) * R1}
+    # algorithmic HBM bytes per launch of the memory-bound kernels
+    hbm_bytes = {27: M * (16 * N + 16 * 64 * 64 + 12 * 64)}
     per_tag = []
     for t in range(ntags):
         if tcnt[t] == 0:
@@ -220,24 +226,34 @@ def run_ours(args):
         flops = None
         if t < 27:
             l = t // 3
-            flops = 2.0 * CIN[l] * COUT[l] * rows[l]                  # algorithmic FLOPs of one pass of this GEMM
+            flops = 2.0 * CIN[l] * COUT[l] * rows[l]                  # algorithmic FLOPs per step of this GEMM (head: both row sets)
             if l == 3 and t % 3 == 2:
                 flops = 2.0 * 256 * 256 * rows[l]
+        elif t in l1_flops:
+            flops = l1_flops[t]
         per_tag.append(dict(tag=t, name=tag_name(t), ms_per_step=tms[t] / args.steps, launches_per_step=tcnt[t] / args.steps,
                             flops=flops))
     per_tag.sort(key=lambda d: -d["ms_per_step"])
     kernel_ms = sum(d["ms_per_step"] for d in per_tag)
     top = per_tag[0]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and (B, G, N) == (CFG2["B"], CFG2["G"], CFG2["N"]) and cfg["precision"] == "fp32":
+        traffic = json.load(open(tpath)).get(top["name"])              # dram bytes per launch from the committed ncu --set full capture
+    split = 3.0 if cfg["precision"] == "fp32" else 1.0
     if top["flops"]:
-        achieved = top["flops"] * top["launches_per_step"] / (top["ms_per_step"] * 1e-3) / 1e12
+        achieved = top["flops"] / (top["ms_per_step"] * 1e-3) / 1e12   # per-step FLOPs of the tag / per-step time of the tag
         roof = dict(kernel=top["name"], bound="tensor", achieved=achieved, peak=peaks["tensor_sustained"], unit="TFLOP/s",
-                    frac=achieved / peaks["tensor_sustained"], traffic=None, peak_source=peaks["source"] + ", sustained bf16",
-                    share_of_step=top["ms_per_step"] / (ms / args.steps))
+                    frac=achieved / peaks["tensor_sustained"], traffic=traffic, peak_source=peaks["source"] + ", sustained bf16",
+                    share_of_step=top["ms_per_step"] / (ms / args.steps),
+                    note=f"algorithmic FLOPs; the {cfg['precision']} mode issues {split:.0f} bf16 products per FLOP, so its ceiling is "
+                         f"{peaks['tensor_sustained'] / split:.0f} TFLOP/s (frac_of_mode_ceiling)",
+                    frac_of_mode_ceiling=achieved * split / peaks["tensor_sustained"])
     else:
-        nbytes = {27: M * (16 * N + 16 * 64 * 64 + 12 * 64)}.get(top["tag"], 0)
+        nbytes = hbm_bytes.get(top["tag"], 0)
         achieved = nbytes / (top["ms_per_step"] * 1e-3) / 1e9
         roof = dict(kernel=top["name"], bound="hbm", achieved=achieved, peak=peaks["hbm"], unit="GB/s",
-                    frac=achieved / peaks["hbm"], traffic=None, peak_source=peaks["source"],
+                    frac=achieved / peaks["hbm"], traffic=traffic, peak_source=peaks["source"],
                     share_of_step=top["ms_per_step"] / (ms / args.steps))
     # whole-step tensor roofline: 15.93 GFLOP per sequence against the sustained bf16 peak
     step_flops = 796e6 * M
