@@ -156,14 +156,13 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident throughput ----------------------------------------------------------------------
+    # ---- device-resident throughput (per-kernel event timing OFF: it adds two event records per launch) ----------
     for i in range(args.warmup):
         fused.step(dev[i % nb])
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    L.facl_timing_enable(1 if rank == 0 else 0)
     launches0 = L.facl_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -173,15 +172,21 @@ def run_ours(args):
     sync_all()
     ms = ev0.elapsed_time(ev1)
     launches = L.facl_launch_count() - launches0
-    L.facl_timing_enable(0)
-    ntags = 44
-    tms, tcnt = (C.c_float * ntags)(), (C.c_int * ntags)()
-    L.facl_timing_collect(tms, tcnt, ntags)
     if dist is not None:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
     loss_dev = float(fused.loss2[2])
+    # ---- the same steps again with every launch site bracketed by CUDA events: per-kernel breakdown and roofline ----
+    ksteps = min(args.steps, 10)
+    L.facl_timing_enable(1 if rank == 0 else 0)
+    for i in range(ksteps):
+        fused.step(dev[i % nb])
+    sync_all()
+    L.facl_timing_enable(0)
+    ntags = 44
+    tms, tcnt = (C.c_float * ntags)(), (C.c_int * ntags)()
+    L.facl_timing_collect(tms, tcnt, ntags)
 
     # ---- end to end: pinned host batch in, loss back to the host, every step ------------------------------
     e2e_steps = max(2, args.steps)
@@ -231,7 +236,7 @@ def run_ours(args):
                 flops = 2.0 * 256 * 256 * rows[l]
         elif t in l1_flops:
             flops = l1_flops[t]
-        per_tag.append(dict(tag=t, name=tag_name(t), ms_per_step=tms[t] / args.steps, launches_per_step=tcnt[t] / args.steps,
+        per_tag.append(dict(tag=t, name=tag_name(t), ms_per_step=tms[t] / ksteps, launches_per_step=tcnt[t] / ksteps,
                             flops=flops))
     per_tag.sort(key=lambda d: -d["ms_per_step"])
     kernel_ms = sum(d["ms_per_step"] for d in per_tag)
