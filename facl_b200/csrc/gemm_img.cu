@@ -26,7 +26,7 @@ constexpr uint32_t IMG_LBO = 8192, IMG_SBO = 1024;   // B tile as staged: 64-row
 template <int NHL>
 __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
     constexpr int STAGE_BYTES = (A_TILE_BYTES + B_TILE_BYTES) * NHL;
     constexpr int NUM_STAGES = (NHL == 2) ? 2 : 4;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * STAGE_BYTES);

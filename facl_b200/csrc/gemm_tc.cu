@@ -168,7 +168,7 @@ __device__ __forceinline__ void produce_xt4(const OperandSrc& s, uint8_t* hi, ui
 
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
     const int nhl = (p.nsplit == 3) ? 2 : 1;
     const int stage_bytes = (A_TILE_BYTES + B_TILE_BYTES) * nhl;
     const int num_stages = (p.nsplit == 3) ? 2 : 4;

@@ -87,7 +87,7 @@ __device__ __forceinline__ void mma_weight_act(uint32_t d_tmem, uint32_t a_hi, u
 template <bool PASS_B>
 __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_kernel(const L1Params p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
     const int nhl = p.nhl;
     constexpr int NPW = PASS_B ? 4 : 8;        // producer warps: 64 channels x (2 | 4) row parts
     constexpr int PROWS = TILE / (NPW / 2);    // rows per producer thread
@@ -490,7 +490,7 @@ constexpr int C_THREADS = 22 * 32;
 
 __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
     const int nhl = p.nhl;
     uint8_t* w2s = smem;                       // hi 8 KB | lo 8 KB
     uint8_t* w3s = w2s + 16384;                // [half][hi 16 KB | lo 16 KB]
@@ -840,7 +840,7 @@ constexpr int D_STAGE_BYTES = 4 * IMG64;
 
 __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
     const int nhl = p.nhl;
     uint8_t* ews = smem;                       // diag(e0) W2: hi 8 KB | lo 8 KB
     uint8_t* p2s = ews + 16384;                // P2:          hi 8 KB | lo 8 KB
