@@ -190,13 +190,13 @@ def run_ours(args):
 
     # ---- end to end: pinned host batch in, loss back to the host, every step ------------------------------
     e2e_steps = max(2, args.steps)
-    fused.step(host[0], want_host_loss=True)
+    fused.step(host[0], want_host_loss=True, next_batch=host[1 % nb])    # the H2D of batch i+1 overlaps step i (prefetching loader)
     sync_all()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(e2e_steps):
-        fused.step(host[i % nb], want_host_loss=True)
+        fused.step(host[(i + 1) % nb], want_host_loss=True, next_batch=host[(i + 2) % nb])
         torch.cuda.current_stream().synchronize()                    # loss.item() of the reference loop (:335)
         _ = float(fused.loss_host[0])
     e1.record()

@@ -14,6 +14,7 @@
 //   pass A     : x -> h1 -> z2 (tensor core)     -> BN2 statistics
 //   pass B     : x -> h1 -> z2 -> h2 -> z3 (tensor core) -> BN3 statistics + max over K of the pre-BN value
 // (max_k relu(a z_k + b) = relu(a * (a >= 0 ? max z : min z) + b), so pooling can precede BN3.)
+#include <stdio.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -28,7 +29,7 @@ constexpr int TILE = 128;                 // batch rows per tile
 constexpr uint32_t ACT_LBO = 8192;        // MN-major activation image: 64-row blocks 8 KB apart,
 constexpr uint32_t ACT_SBO = 1024;        //                            8-channel groups 1 KB apart (16 KB per half)
 constexpr int ACT_BYTES = 16384;
-constexpr int NTHREADS_A = 17 * 32;        // pass A: warps 0-7 (idle z3 roles) are the h1 producers
+constexpr int NTHREADS_A = 25 * 32;        // pass A: warps 0-7 (idle z3 roles) and 17-24 are the h1 producers
 constexpr int NTHREADS_B = 17 * 32;        // pass B: warps 10,11,14,15 are the h1 producers (the z3 consumers own the issue slots)
 
 struct L1Params {
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
     const int nhl = p.nhl;
-    constexpr int NPW = PASS_B ? 4 : 8;        // producer warps: 64 channels x (2 | 4) row parts
+    constexpr int NPW = PASS_B ? 4 : 16;       // producer warps: 64 channels x (2 | 8) row parts
     constexpr int PROWS = TILE / (NPW / 2);    // rows per producer thread
     // ---- shared-memory carve-up (all operand images 1 KB aligned) ----
     uint8_t* w2s = smem;                                   // hi 8 KB | lo 8 KB (64 valid rows each)
@@ -174,9 +175,9 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                 }
             }
         }
-    } else if (PASS_B ? (warp == 10 || warp == 11 || warp == 14 || warp == 15) : (warp < 8)) {
+    } else if (PASS_B ? (warp == 10 || warp == 11 || warp == 14 || warp == 15) : (warp < 8 || warp >= 17)) {
         // ======================= producers: x -> h1 = relu(bn1(W1 x + b1)), thread = (channel, row quarter) ===============
-        const int pw = !PASS_B ? warp : (warp == 10) ? 0 : (warp == 11) ? 1 : (warp == 14) ? 2 : 3;
+        const int pw = !PASS_B ? (warp < 8 ? warp : warp - 9) : (warp == 10) ? 0 : (warp == 11) ? 1 : (warp == 14) ? 2 : 3;
         const int ptid = pw * 32 + lane;          // 0 .. 32 NPW - 1
         const int ch = ptid & 63, part = ptid >> 6;
         // BN1 folded into the 4-wide layer: h1 = max(wf . x + bf, 0)
@@ -185,6 +186,9 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
         const float wx = s1 * w.x, wy = s1 * w.y, wz = s1 * w.z, ww = s1 * w.w;
         const float bf = fmaf(s1, __ldg(p.b1 + ch), t1);
         int it = 0;
+#ifdef FACL_PROFILE_ROLES
+        long long prof_wait = 0, prof_comp = 0, prof_fence = 0;
+#endif
         float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ptid < TILE && (long long)blockIdx.x < ntiles) xnext = __ldg(reinterpret_cast<const float4*>(p.xt) + (long long)blockIdx.x * TILE + ptid);
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -194,8 +198,14 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                 xtile[ptid] = xnext;
                 if (t + gridDim.x < ntiles) xnext = __ldg(reinterpret_cast<const float4*>(p.xt) + (t + gridDim.x) * TILE + ptid);
             }
+#ifdef FACL_PROFILE_ROLES
+            long long c0 = clock64();
+#endif
             named_bar_sync(1, NPW * 32);
             mbar_wait(&h1_empty[b], u ^ 1);
+#ifdef FACL_PROFILE_ROLES
+            long long c1 = clock64();
+#endif
             uint8_t* img = h1s + b * 2 * ACT_BYTES;
 #pragma unroll 2
             for (int q = 0; q < PROWS / 8; ++q) {
@@ -207,10 +217,22 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                 }
                 store_act8(img, nhl, ch, part * (PROWS / 8) + q, v);
             }
+#ifdef FACL_PROFILE_ROLES
+            long long c2 = clock64();
+#endif
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&h1_full[b]);
+#ifdef FACL_PROFILE_ROLES
+            long long c3 = clock64();
+            prof_wait += c1 - c0; prof_comp += c2 - c1; prof_fence += c3 - c2;
+#endif
         }
+#ifdef FACL_PROFILE_ROLES
+        if (blockIdx.x == 0 && lane == 0 && (pw == 0 || pw == NPW - 1))
+            printf("fwd pass_b=%d producer warp %d: tiles %d wait %lld compute %lld fence %lld (cycles per tile)\n", (int)PASS_B, pw, it,
+                   prof_wait / it, prof_comp / it, prof_fence / it);
+#endif
     } else if (warp == 8 || warp == 9 || warp == 12 || warp == 13) {
         // ======================= z2 consumers, thread = channel j (lanes 0..63 of D2), two column halves =============
         const int lg = warp & 1;                  // warps 8,12 -> TMEM lanes 0..31; 9,13 -> 32..63   (warp % 4 == lg)

@@ -60,9 +60,10 @@ class DistributedFusedTrainStep(FusedTrainStep):
         self.args.phases = phases
         self._lib.check(self._lib.lib().facl_train_step(self.C.byref(self.args), self._lib.stream_ptr()), "facl_train_step")
 
-    def step(self, batch, order=None, want_host_loss=False):
-        if self.world == 1 and False:
-            return super().step(batch, order, want_host_loss)
+    def step(self, batch, order=None, want_host_loss=False, next_batch=None):
+        dev_copy, pf_slot = self._take_prefetched(batch)
+        if dev_copy is not None:
+            batch = dev_copy
         tr = self.tr
         G = self.shape[1]
         if order is None:                                   # same seed on every rank -> same permutation
@@ -96,5 +97,8 @@ class DistributedFusedTrainStep(FusedTrainStep):
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         self.loss2.copy_(self.flat[-4:-1])
         self._call(8)                                                          # Adam, loss D2H
+        self._release_prefetched(pf_slot)
+        if next_batch is not None:
+            self.prefetch(next_batch)
         self.pending_bn_steps += 1
         return self.loss2

@@ -154,6 +154,7 @@ class FusedTrainStep:
         self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         self.r2 = r2
         self.pending_bn_steps = 0
+        self._copy_stream, self._pf_bufs, self._pf_free, self._pending, self._pf_slot = None, None, None, None, 0
         a = _lib.TrainStepArgs()
         a.dims, a.params, a.grads = C.pointer(self.dims), C.pointer(self.params_struct), C.pointer(self.grads_struct)
         a.enc_buffers = self.ws.table
@@ -166,9 +167,48 @@ class FusedTrainStep:
         a.beta1, a.beta2, a.eps = 0.5, 0.999, 1e-6
         self.args = a
 
-    def step(self, batch, order=None, want_host_loss=False):
+    def prefetch(self, batch):
+        """Start the host->device copy of a PINNED (B, G, N, 4) batch on a side stream, so that it overlaps the step that is
+        running; the next step(batch) picks the device copy up (what a prefetching DataLoader wrapper does)."""
+        if batch.is_cuda:
+            return
+        if not batch.is_pinned():
+            raise self._lib.FaclError("host batches must be pinned (torch.Tensor.pin_memory)")
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.staging.device)
+            self._pf_bufs = [torch.empty_like(self.staging) for _ in range(2)]
+            self._pf_free = [None, None]
+        self._pf_slot ^= 1
+        slot = self._pf_slot
+        if self._pf_free[slot] is not None:                       # the step that last read this slot has been issued: wait for it
+            self._copy_stream.wait_event(self._pf_free[slot])
+        with torch.cuda.stream(self._copy_stream):
+            self._pf_bufs[slot].copy_(batch, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._pending = (batch.data_ptr(), slot, ev)
+
+    def _take_prefetched(self, batch):
+        """Device copy of `batch` if prefetch() was called for it, else None."""
+        if self._pending is None or batch.is_cuda or self._pending[0] != batch.data_ptr():
+            return None, None
+        _, slot, ev = self._pending
+        self._pending = None
+        torch.cuda.current_stream().wait_event(ev)
+        return self._pf_bufs[slot], slot
+
+    def _release_prefetched(self, slot):
+        if slot is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._pf_free[slot] = ev
+
+    def step(self, batch, order=None, want_host_loss=False, next_batch=None):
         if tuple(batch.shape) != self.shape or batch.dtype != torch.float32:
             raise self._lib.FaclError(f"batch must be float32 {self.shape}")
+        dev_copy, pf_slot = self._take_prefetched(batch)
+        if dev_copy is not None:
+            batch = dev_copy
         tr = self.tr
         G = self.shape[1]
         if order is None:
@@ -190,6 +230,9 @@ class FusedTrainStep:
         a.step = opt._step
         a.loss_host = self.loss_host.data_ptr() if want_host_loss else None
         self._lib.check(self._lib.lib().facl_train_step(self.C.byref(a), self._lib.stream_ptr()), "facl_train_step")
+        self._release_prefetched(pf_slot)
+        if next_batch is not None:
+            self.prefetch(next_batch)
         self.pending_bn_steps += 1
         return self.loss2
 

@@ -238,6 +238,16 @@ def test_fused_step_equals_api_step_and_oracle(golden_dir):
     fb.step(pts.to(DEV), order=order)
     torch.cuda.synchronize()
     assert np.isfinite(float(fb.loss2[2]))
+    # prefetched host batches (H2D of batch i+1 on a side stream during step i) give the same steps as device batches
+    c, d = fresh(), fresh()
+    fc, fd = FusedTrainStep(c, B, G, N, r2=0.06), FusedTrainStep(d, B, G, N, r2=0.06)
+    hosts = [pts.pin_memory(), (pts * 0.5).pin_memory()]
+    fc.prefetch(hosts[0])
+    for i in range(4):
+        lc = fc.step(hosts[i % 2], order=order, next_batch=hosts[(i + 1) % 2]).clone()
+        ld = fd.step(hosts[i % 2].to(DEV), order=order).clone()
+        # same kernels and inputs; atomic summation order differs between runs and Adam amplifies it step by step
+        assert float((lc - ld).abs().max()) <= 1e-5 * 10 ** i * float(ld.abs().max()), (i, lc, ld)
 
 
 def test_extract_features_layout(golden_dir):
