@@ -1009,16 +1009,16 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
         const int part = quarter >> 1;                           // 0: lanes 0..63 (A_hi products), 1: lanes 64..127 (A_lo)
         const int i = (quarter & 1) * 32 + lane;
         const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + i);
-        const float b1 = __ldg(p.b1 + i), s1 = __ldg(p.scale1 + i), t1 = __ldg(p.shift1 + i);
-        const float wx = s1 * w.x, wy = s1 * w.y, wz = s1 * w.z, ww = s1 * w.w, bf = fmaf(s1, b1, t1);   // as the producer folds BN1
+        const float b1 = __ldg(p.b1 + i);
         const float q2 = part == 0 ? __ldg(p.q2 + i) : 0.f;
         const bool live = (part == 0) || (nhl == 2);             // bf16 mode has no lo part: lanes 64..127 are meaningless
-        float s_acc = 0.f, q_acc = 0.f, ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+        float s_acc = 0.f, ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
         int s = 0;
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
             const float4* xtile = reinterpret_cast<const float4*>(xs + s * BT * 16) + colhalf * 32;
+            const uint8_t* h1img = stg + s * D_STAGE_BYTES + IMG64;      // bf16(h1) of this tile: non-zero <=> ReLU1 active
             mbar_wait(&dh_full[b], u);
             tc_fence_after_sync();
             float g[32];
@@ -1035,14 +1035,18 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
             tc_fence_before_sync();
             if (live) {
 #pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    const float4 x = xtile[r];
-                    const float z1 = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, b1))));
-                    const float zf = fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf))));
-                    const float v = (zf > 0.f) ? g[r] + q2 : 0.f;
-                    s_acc += v;
-                    q_acc = fmaf(v, z1, q_acc);
-                    ax = fmaf(v, x.x, ax); ay = fmaf(v, x.y, ay); az = fmaf(v, x.z, az); aw = fmaf(v, x.w, aw);
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 hb = *reinterpret_cast<const uint4*>(h1img + sw128_offset((uint32_t)i, (uint32_t)(colhalf * 4 + q)));
+                    const uint32_t hw[4] = {hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int r = q * 8 + e;
+                        const uint32_t bits = (e & 1) ? (hw[e >> 1] >> 16) : (hw[e >> 1] & 0xFFFFu);
+                        const float4 x = xtile[r];
+                        const float v = bits ? g[r] + q2 : 0.f;
+                        s_acc += v;
+                        ax = fmaf(v, x.x, ax); ay = fmaf(v, x.y, ay); az = fmaf(v, x.z, az); aw = fmaf(v, x.w, aw);
+                    }
                 }
             }
             __syncwarp();
@@ -1052,6 +1056,8 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
             }
             if (++s == D_STAGES) s = 0;
         }
+        // z1 = w.x + b1 is affine in x, so sum dh1' z1 follows from A = sum dh1' x^T and sum dh1'
+        const float q_acc = fmaf(w.x, ax, fmaf(w.y, ay, fmaf(w.z, az, fmaf(w.w, aw, b1 * s_acc))));
         const long long slot = (long long)(blockIdx.x * 4 + part * 2 + colhalf) * 64 + i;
         p.stats[slot * 2 + 0] = s_acc;
         p.stats[slot * 2 + 1] = q_acc;
