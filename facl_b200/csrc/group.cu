@@ -27,30 +27,21 @@ namespace {
 constexpr int GW = 8;             // warps (= centres) per block
 constexpr int CAP = 256;          // candidate slots per warp
 constexpr int TILE_PTS = 4096;    // points per shared-memory tile (at most 64 KB as float4)
-constexpr int TMAX = 5;           // supports K <= 128 (T = ceil(K/32) + 1 tracked per lane)
+constexpr int TMAX = 5;           // supports K <= 128 (T = ceil(K/32) + 1 tracked per lane, a template parameter)
 
-__device__ __forceinline__ void insert_smallest(float (&t)[TMAX], int T, float d) {
-    // keep t[0] <= t[1] <= ... <= t[T-1] = the T smallest seen
-    float last = t[0];
+// keep t[0] <= t[1] <= ... <= t[T-1] = the T smallest seen: a branch-free insertion network (2 min/max per level)
+template <int T>
+__device__ __forceinline__ void insert_smallest(float (&t)[T], float d) {
+    float carry = d;
 #pragma unroll
-    for (int q = 1; q < TMAX; ++q)
-        if (q < T) last = t[q];
-    if (d < last) {
-#pragma unroll
-        for (int q = 0; q < TMAX; ++q)
-            if (q == T - 1) t[q] = d;
-#pragma unroll
-        for (int q = TMAX - 1; q > 0; --q) {
-            if (q < T && t[q] < t[q - 1]) {
-                float tmp = t[q];
-                t[q] = t[q - 1];
-                t[q - 1] = tmp;
-            }
-        }
+    for (int q = 0; q < T; ++q) {
+        const float lo = fminf(t[q], carry);
+        carry = fmaxf(t[q], carry);
+        t[q] = lo;
     }
 }
 
-template <bool D4>
+template <bool D4, int T>
 __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict__ points, int N, int D, int S, int K, float r2,
                                                         float* __restrict__ xt, int* __restrict__ idx_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -64,7 +55,6 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
     const bool active = s < S;
     const float* cloud = points + (long long)m * N * D;
     unsigned long long* cand = cand_all + warp * CAP;
-    const int T = (K + 31) / 32 + 1;
     const int ntiles = (N + TILE_PTS - 1) / TILE_PTS;
     const int tile_pts = N < TILE_PTS ? N : TILE_PTS;
 
@@ -104,31 +94,31 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
     };
 
     // ---------------- pass 1: per-lane T smallest -> tau ----------------
-    float tsm[TMAX];
+    float tsm[T];
 #pragma unroll
-    for (int q = 0; q < TMAX; ++q) tsm[q] = INFINITY;
+    for (int q = 0; q < T; ++q) tsm[q] = INFINITY;
     for (int t = 0; t < ntiles; ++t) {
         if (t > 0) __syncthreads();           // everyone is done with the previous tile
         const int cnt = load_tile(t);
         if (active) {
             for (int i = lane; i < cnt; i += 32) {
                 float4 p = tile[i];
-                insert_smallest(tsm, T, sqdist_ref(p.x, p.y, p.z, cx, cy, cz));
+                insert_smallest<T>(tsm, sqdist_ref(p.x, p.y, p.z, cx, cy, cz));
             }
         }
     }
     // tau = K-th smallest of the 32*T tracked values (+inf where a lane saw fewer than T points): distances are >= 0, so
     // their bit patterns order like unsigned integers; build the answer bit by bit from warp-wide counts.
-    unsigned tb[TMAX];
+    unsigned tb[T];
 #pragma unroll
-    for (int q = 0; q < TMAX; ++q) tb[q] = (q < T) ? __float_as_uint(tsm[q]) : 0xFFFFFFFFu;
+    for (int q = 0; q < T; ++q) tb[q] = __float_as_uint(tsm[q]);
     unsigned prefix = 0u;
 #pragma unroll 1
     for (int bit = 31; bit >= 0; --bit) {
         const unsigned trial = prefix | (1u << bit);
         int c = 0;
 #pragma unroll
-        for (int q = 0; q < TMAX; ++q) c += (tb[q] < trial) ? 1 : 0;
+        for (int q = 0; q < T; ++q) c += (tb[q] < trial) ? 1 : 0;
         c = __reduce_add_sync(0xFFFFFFFFu, c);
         if (c < K) prefix = trial;            // fewer than K values below `trial`: the K-th smallest is >= trial
     }
@@ -157,6 +147,7 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
                     take = d <= tau;
                 }
                 unsigned bal = __ballot_sync(0xFFFFFFFFu, take);
+                if (bal == 0u) continue;               // ~96 % of the 32-point rows hold no candidate
                 if (take) {
                     int pos = count + __popc(bal & ((1u << lane) - 1u));
                     if (pos < CAP) cand[pos] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(n0 + i);
@@ -247,17 +238,30 @@ int group_launch(const float* points, int M, int N, int D, int S, int K, float r
     static bool configured = false;
     if (!configured) {
         const int max_smem = TILE_PTS * 16 + GW * CAP * 8;
-        FACL_CHECK(cudaFuncSetAttribute(group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        FACL_CHECK(cudaFuncSetAttribute(group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+#define FACL_GROUP_ATTR(TT)                                                                                              \
+        FACL_CHECK(cudaFuncSetAttribute(group_kernel<true, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));   \
+        FACL_CHECK(cudaFuncSetAttribute(group_kernel<false, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        FACL_GROUP_ATTR(2) FACL_GROUP_ATTR(3) FACL_GROUP_ATTR(4) FACL_GROUP_ATTR(5)
+#undef FACL_GROUP_ATTR
         configured = true;
     }
     dim3 grid((S + GW - 1) / GW, M);
     ScopedTimer timer(TAG_GROUP, st);
     count_launch();
-    if (D == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0)
-        group_kernel<true><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);
-    else
-        group_kernel<false><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);
+    const bool d4 = (D == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0);
+    const int T = (K + 31) / 32 + 1;           // smallest distances tracked per lane in pass 1
+#define FACL_GROUP_LAUNCH(TT)                                                                                     \
+    do {                                                                                                          \
+        if (d4) group_kernel<true, TT><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);         \
+        else group_kernel<false, TT><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);           \
+    } while (0)
+    switch (T) {
+        case 2: FACL_GROUP_LAUNCH(2); break;
+        case 3: FACL_GROUP_LAUNCH(3); break;
+        case 4: FACL_GROUP_LAUNCH(4); break;
+        default: FACL_GROUP_LAUNCH(5); break;
+    }
+#undef FACL_GROUP_LAUNCH
     return (int)cudaGetLastError();
 }
 
