@@ -213,18 +213,38 @@ struct AdamTensor {
     float* v;
     long long n;
 };
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float lr_c, float b1, float b2, float eps, float bc2_sqrt) {
+    m = b1 * m + (1.f - b1) * g;
+    v = b2 * v + (1.f - b2) * g * g;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    p -= lr_c * (m / denom);
+}
 __global__ void adam_kernel(const AdamTensor* __restrict__ tab, int ntensors, float lr, float b1, float b2, float eps, float bc1,
                             float bc2_sqrt) {
+    const float lr_c = lr / bc1;
     for (int t = blockIdx.y; t < ntensors; t += gridDim.y) {
         AdamTensor a = tab[t];
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
-            float g = a.g[i];
-            float m = b1 * a.m[i] + (1.f - b1) * g;
-            float v = b2 * a.v[i] + (1.f - b2) * g * g;
-            a.m[i] = m;
-            a.v[i] = v;
-            float denom = sqrtf(v) / bc2_sqrt + eps;
-            a.p[i] -= (lr / bc1) * (m / denom);
+        const bool vec = ((a.n & 3) == 0) && (((reinterpret_cast<uintptr_t>(a.p) | reinterpret_cast<uintptr_t>(a.g) |
+                                                reinterpret_cast<uintptr_t>(a.m) | reinterpret_cast<uintptr_t>(a.v)) & 15) == 0);
+        if (vec) {
+            const long long n4 = a.n >> 2;
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+                float4 p = reinterpret_cast<float4*>(a.p)[i], m = reinterpret_cast<float4*>(a.m)[i], v = reinterpret_cast<float4*>(a.v)[i];
+                const float4 g = reinterpret_cast<const float4*>(a.g)[i];
+                adam_one(p.x, g.x, m.x, v.x, lr_c, b1, b2, eps, bc2_sqrt);
+                adam_one(p.y, g.y, m.y, v.y, lr_c, b1, b2, eps, bc2_sqrt);
+                adam_one(p.z, g.z, m.z, v.z, lr_c, b1, b2, eps, bc2_sqrt);
+                adam_one(p.w, g.w, m.w, v.w, lr_c, b1, b2, eps, bc2_sqrt);
+                reinterpret_cast<float4*>(a.p)[i] = p;
+                reinterpret_cast<float4*>(a.m)[i] = m;
+                reinterpret_cast<float4*>(a.v)[i] = v;
+            }
+        } else {
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+                float p = a.p[i], m = a.m[i], v = a.v[i];
+                adam_one(p, a.g[i], m, v, lr_c, b1, b2, eps, bc2_sqrt);
+                a.p[i] = p; a.m[i] = m; a.v[i] = v;
+            }
         }
     }
 }
@@ -315,7 +335,7 @@ int adam_launch(const void* table_dev, int ntensors, float lr, float b1, float b
     count_launch();
     float bc1 = (float)(1.0 - pow((double)b1, (double)step));
     float bc2 = (float)sqrt(1.0 - pow((double)b2, (double)step));
-    dim3 grid(64, ntensors < 64 ? ntensors : 64);
+    dim3 grid(128, ntensors < 64 ? ntensors : 64);
     adam_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const AdamTensor*>(table_dev), ntensors, lr, b1, b2, eps, bc1, bc2);
     return (int)cudaGetLastError();
 }
