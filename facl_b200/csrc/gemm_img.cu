@@ -27,11 +27,18 @@ template <int NHL>
 __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
-    constexpr int STAGE_BYTES = (A_TILE_BYTES + B_TILE_BYTES) * NHL;
-    constexpr int NUM_STAGES = (NHL == 2) ? 2 : 4;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * STAGE_BYTES);
-    uint64_t* empty = full + NUM_STAGES;
-    uint64_t* acc_full = empty + NUM_STAGES;
+    // Two rings: A tiles (one per 64-wide k-block) and B HALF tiles (32 of the 64 k of a block when B is reduced over its
+    // channels, so that three half-stages of the large operand are in flight instead of one full stage; a pair of
+    // consecutive half slots forms one full K-major tile when B is reduced over its rows).
+    constexpr int A_SLOT = A_TILE_BYTES * NHL, B_SLOT = (B_TILE_BYTES / 2) * NHL;
+    constexpr int SA = (NHL == 2) ? 2 : 4, SB = (NHL == 2) ? 4 : 8;
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + SA * A_SLOT;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + SB * B_SLOT);
+    uint64_t* a_empty = a_full + SA;
+    uint64_t* b_full = a_empty + SA;
+    uint64_t* b_empty = b_full + SB;
+    uint64_t* acc_full = b_empty + SB;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -41,9 +48,13 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
     const bool b_k = (p.b_mode == B_IMAGE_K);        // B image reduced over its rows (else over its channels, MN-major)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NUM_STAGES; ++i) {
-            mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+        for (int i = 0; i < SA; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < SB; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
@@ -193,46 +204,75 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
     } else if (warp == 4) {
         // =============================== MMA issuer ===============================
         const uint32_t idesc = umma_idesc_bf16(M_TILE, mma_n) | (b_k ? 0u : UMMA_B_MN_MAJOR);
-        int stage = 0, phase = 0;
+        int sa = 0, pa = 0, sb = 0, pb = 0;
         for (int it = 0; sched.get(it, p, w); ++it) {
             const int buf = it & 1;
             mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N_TILE);
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
-                mbar_wait(&full[stage], phase);
-                tc_fence_after_sync();
-                if (lane == 0) {
-                    const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES), a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t b_hi = a_hi + A_TILE_BYTES * NHL, b_lo = b_hi + B_TILE_BYTES;
+                mbar_wait(&a_full[sa], pa);
+                const uint32_t a_hi = smem_u32(a_ring + sa * A_SLOT), a_lo = a_hi + A_TILE_BYTES;
+                if (b_k) {
+                    // one full K-major B tile in a pair of half slots: [hi | lo]
+                    mbar_wait(&b_full[sb], pb);
+                    tc_fence_after_sync();
+                    if (lane == 0) {
+                        const uint32_t b_hi = smem_u32(b_ring + sb * B_SLOT), b_lo = b_hi + B_TILE_BYTES;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t acc = (kb > w.kb0 || ks > 0) ? 1u : 0u;
-                        const uint32_t ko = ks * 32;
-                        const uint64_t ad_hi = umma_desc_sw128(a_hi + ko);
-                        const uint64_t bd_hi = b_k ? umma_desc_sw128(b_hi + ko)
-                                                     : umma_desc_mn_sw128(b_hi + ks * 2 * IMG_SBO, IMG_LBO, IMG_SBO);
-                        umma_bf16_ss(d_tmem, ad_hi, bd_hi, idesc, acc);
-                        if (NHL == 2) {
-                            const uint64_t bd_lo = b_k ? umma_desc_sw128(b_lo + ko)
-                                                         : umma_desc_mn_sw128(b_lo + ks * 2 * IMG_SBO, IMG_LBO, IMG_SBO);
-                            umma_bf16_ss(d_tmem, ad_hi, bd_lo, idesc, 1u);
-                            umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ko), bd_hi, idesc, 1u);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t acc = (kb > w.kb0 || ks > 0) ? 1u : 0u;
+                            const uint32_t ko = ks * 32;
+                            const uint64_t ad_hi = umma_desc_sw128(a_hi + ko), bd_hi = umma_desc_sw128(b_hi + ko);
+                            umma_bf16_ss(d_tmem, ad_hi, bd_hi, idesc, acc);
+                            if (NHL == 2) {
+                                umma_bf16_ss(d_tmem, ad_hi, umma_desc_sw128(b_lo + ko), idesc, 1u);
+                                umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ko), bd_hi, idesc, 1u);
+                            }
                         }
+                        umma_commit(&b_empty[sb]);
+                        umma_commit(&a_empty[sa]);
+                        if (kb == w.kb1 - 1) umma_commit(&acc_full[buf]);
                     }
-                    umma_commit(&empty[stage]);
-                    if (kb == w.kb1 - 1) umma_commit(&acc_full[buf]);
+                    __syncwarp();
+                    sb += 2;
+                    if (sb == SB) { sb = 0; pb ^= 1; }
+                } else {
+                    // two MN-major half tiles (32 channels each): slot = [hi 16 KB | lo 16 KB], 64-row blocks 4 KB apart
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        mbar_wait(&b_full[sb], pb);
+                        tc_fence_after_sync();
+                        if (lane == 0) {
+                            const uint32_t b_hi = smem_u32(b_ring + sb * B_SLOT), b_lo = b_hi + B_TILE_BYTES / 2;
+#pragma unroll
+                            for (int k2 = 0; k2 < 2; ++k2) {
+                                const int ks = 2 * h + k2;
+                                const uint32_t acc = (kb > w.kb0 || ks > 0) ? 1u : 0u;
+                                const uint64_t ad_hi = umma_desc_sw128(a_hi + ks * 32);
+                                const uint64_t bd_hi = umma_desc_mn_sw128(b_hi + k2 * 2 * IMG_SBO, IMG_LBO / 2, IMG_SBO);
+                                umma_bf16_ss(d_tmem, ad_hi, bd_hi, idesc, acc);
+                                if (NHL == 2) {
+                                    umma_bf16_ss(d_tmem, ad_hi, umma_desc_mn_sw128(b_lo + k2 * 2 * IMG_SBO, IMG_LBO / 2, IMG_SBO), idesc, 1u);
+                                    umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ks * 32), bd_hi, idesc, 1u);
+                                }
+                            }
+                            umma_commit(&b_empty[sb]);
+                            if (h == 1) {
+                                umma_commit(&a_empty[sa]);
+                                if (kb == w.kb1 - 1) umma_commit(&acc_full[buf]);
+                            }
+                        }
+                        __syncwarp();
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                    }
                 }
-                __syncwarp();
-                if (++stage == NUM_STAGES) {
-                    stage = 0;
-                    phase ^= 1;
-                }
+                if (++sa == SA) { sa = 0; pa ^= 1; }
             }
         }
     } else if (lane == 0) {
         // =============================== TMA issuer ===============================
-        int stage = 0, phase = 0;
+        int sa = 0, pa = 0, sb = 0, pb = 0;
         const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.a_packed);
         const uint8_t* ai_hi = reinterpret_cast<const uint8_t*>(p.a_img.hi);
         const uint8_t* ai_lo = reinterpret_cast<const uint8_t*>(p.a_img.lo);
@@ -240,56 +280,49 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
         const uint8_t* bi_lo = reinterpret_cast<const uint8_t*>(p.b_img.lo);
         for (int it = 0; sched.get(it, p, w); ++it) {
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t* st = smem + stage * STAGE_BYTES;
-                uint8_t* a_hi = st;
-                uint8_t* b_hi = st + A_TILE_BYTES * NHL;
-                uint8_t* b_lo = b_hi + B_TILE_BYTES;
-                uint32_t bytes = 0;
-                // ---- A ----
-                int na = 0;
+                // ---- A: one 128 x 64 tile ----
+                mbar_wait(&a_empty[sa], pa ^ 1);
+                uint8_t* a_hi = a_ring + sa * A_SLOT;
                 if (a_img) {                         // 16 channel atoms of row block kb, contiguous
-                    na = p.a_img.cgs - w.mt * 16;
+                    int na = p.a_img.cgs - w.mt * 16;
                     na = na > 16 ? 16 : na;
-                    bytes += (uint32_t)(na * 1024 * NHL);
-                } else {
-                    bytes += (uint32_t)(A_TILE_BYTES * NHL);
-                }
-                // ---- B ----
-                int nb = 0, nrb = 0;
-                const int rb0 = w.nt * (N_TILE / 64);
-                if (b_k) {                           // 32 channel atoms of row block kb, contiguous
-                    nb = p.b_img.cgs - w.nt * 32;
-                    nb = nb > 32 ? 32 : nb;
-                    bytes += (uint32_t)(nb * 1024 * NHL);
-                } else {                             // up to four 64-row blocks x the 8 channel atoms of k-block kb
-                    nrb = p.b_img.rbs - rb0;
-                    nrb = nrb > N_TILE / 64 ? N_TILE / 64 : nrb;
-                    bytes += (uint32_t)(nrb * 8192 * NHL);
-                }
-                mbar_arrive_expect_tx(&full[stage], bytes);
-                if (a_img) {
                     const long long aoff = ((long long)kb * p.a_img.cgs + w.mt * 16) * 1024;
-                    tma_bulk_g2s(a_hi, ai_hi + aoff, na * 1024, &full[stage]);
-                    if (NHL == 2) tma_bulk_g2s(a_hi + A_TILE_BYTES, ai_lo + aoff, na * 1024, &full[stage]);
-                } else {
+                    mbar_arrive_expect_tx(&a_full[sa], (uint32_t)(na * 1024 * NHL));
+                    tma_bulk_g2s(a_hi, ai_hi + aoff, na * 1024, &a_full[sa]);
+                    if (NHL == 2) tma_bulk_g2s(a_hi + A_TILE_BYTES, ai_lo + aoff, na * 1024, &a_full[sa]);
+                } else {                             // packed weight tile, hi | lo adjacent
+                    mbar_arrive_expect_tx(&a_full[sa], (uint32_t)(A_TILE_BYTES * NHL));
                     tma_bulk_g2s(a_hi, wimg + ((long long)w.mt * p.a_packed_kblocks + kb) * (2ll * A_TILE_BYTES), A_TILE_BYTES * NHL,
-                                 &full[stage]);
+                                 &a_full[sa]);
                 }
-                if (b_k) {
+                if (++sa == SA) { sa = 0; pa ^= 1; }
+                // ---- B ----
+                if (b_k) {                           // 32 channel atoms of row block kb, contiguous, into a pair of half slots
+                    int nb = p.b_img.cgs - w.nt * 32;
+                    nb = nb > 32 ? 32 : nb;
                     const long long boff = ((long long)kb * p.b_img.cgs + w.nt * 32) * 1024;
-                    tma_bulk_g2s(b_hi, bi_hi + boff, nb * 1024, &full[stage]);
-                    if (NHL == 2) tma_bulk_g2s(b_lo, bi_lo + boff, nb * 1024, &full[stage]);
-                } else {
-                    for (int r = 0; r < nrb; ++r) {
-                        const long long off = ((long long)(rb0 + r) * p.b_img.cgs + kb * 8) * 1024;
-                        tma_bulk_g2s(b_hi + r * 8192, bi_hi + off, 8192, &full[stage]);
-                        if (NHL == 2) tma_bulk_g2s(b_lo + r * 8192, bi_lo + off, 8192, &full[stage]);
+                    mbar_wait(&b_empty[sb], pb ^ 1);
+                    uint8_t* b_hi = b_ring + sb * B_SLOT;
+                    mbar_arrive_expect_tx(&b_full[sb], (uint32_t)(nb * 1024 * NHL));
+                    tma_bulk_g2s(b_hi, bi_hi + boff, nb * 1024, &b_full[sb]);
+                    if (NHL == 2) tma_bulk_g2s(b_hi + B_TILE_BYTES, bi_lo + boff, nb * 1024, &b_full[sb]);
+                    sb += 2;
+                    if (sb == SB) { sb = 0; pb ^= 1; }
+                } else {                             // per half: up to four 64-row blocks x 4 channel atoms (4 KB pieces)
+                    const int rb0 = w.nt * (N_TILE / 64);
+                    int nrb = p.b_img.rbs - rb0;
+                    nrb = nrb > N_TILE / 64 ? N_TILE / 64 : nrb;
+                    for (int h = 0; h < 2; ++h) {
+                        mbar_wait(&b_empty[sb], pb ^ 1);
+                        uint8_t* b_hi = b_ring + sb * B_SLOT;
+                        mbar_arrive_expect_tx(&b_full[sb], (uint32_t)(nrb * 4096 * NHL));
+                        for (int r = 0; r < nrb; ++r) {
+                            const long long off = ((long long)(rb0 + r) * p.b_img.cgs + kb * 8 + h * 4) * 1024;
+                            tma_bulk_g2s(b_hi + r * 4096, bi_hi + off, 4096, &b_full[sb]);
+                            if (NHL == 2) tma_bulk_g2s(b_hi + B_TILE_BYTES / 2 + r * 4096, bi_lo + off, 4096, &b_full[sb]);
+                        }
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
                     }
-                }
-                if (++stage == NUM_STAGES) {
-                    stage = 0;
-                    phase ^= 1;
                 }
             }
         }
