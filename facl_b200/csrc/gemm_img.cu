@@ -10,6 +10,7 @@
 //                             "channels" are embedding rows, plus D[m][n] = sum_r W[m][r] * img[n][r] (packed A, image B)
 //
 // Warp roles: warps 0-3 epilogue (TMEM lane = output channel), warp 4 MMA issuer, warp 5 TMA issuer.
+#include <stdio.h>
 #include "gemm_tc.cuh"
 #include "common.cuh"
 #include "facl_internal.h"
@@ -23,7 +24,7 @@ namespace {
 constexpr int IMG_THREADS = 192;
 constexpr uint32_t IMG_LBO = 8192, IMG_SBO = 1024;   // B tile as staged: 64-row blocks 8 KB apart, 8-channel atoms 1 KB apart
 
-template <int NHL>
+template <int NHL, int EPI>
 __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
@@ -41,6 +42,10 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
     uint64_t* acc_full = b_empty + SB;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    // per-epilogue-warp 32 x 36 float staging tiles: accumulator rows are (lane = channel, register = column), global rows
+    // are channels, so a direct store scatters 16-byte pieces over 32 lines per instruction; through this tile every store /
+    // load instruction moves four full 128-byte lines
+    float* xpose_all = reinterpret_cast<float*>(b_ring + SB * B_SLOT + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mma_n = (p.Nd >= N_TILE) ? N_TILE : ((p.Nd + 15) & ~15);
@@ -76,6 +81,13 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
 
     if (warp < 4) {
         // =============================== epilogue ===============================
+        // EPI selects a compile-time specialisation (the fully general body is ~150 KB of unrolled SASS and ran out of the
+        // instruction cache: "no_inst" stalls, 2-3 k cycles per 32-column chunk):
+        //   1  forward      : bias, statistics, optional max-pool, channel-major store          (full warps, aligned)
+        //   2  data-gradient: ReLU mask from zin, optional statistics, channel-major store        (full warps, aligned)
+        //   3  weight-grad  : atomic accumulate
+        //   0  everything else (row-major outputs, ragged shapes): runtime branches
+        constexpr bool GEN = (EPI == 0);
         const int c = sched.mt * M_TILE + warp * 32 + lane;
         const bool cvalid = c < p.Md;
         const float bias = (cvalid && p.bias) ? __ldg(p.bias + c) : 0.f;
@@ -84,38 +96,64 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
         const float psign = (cvalid && p.pool_sign) ? __ldg(p.pool_sign + c) : 1.f;
         const bool keep_max = psign >= 0.f;
         float stat0 = 0.f, stat1 = 0.f;
+        float* tb = xpose_all + warp * (32 * 36);
+        const int ch0 = sched.mt * M_TILE + warp * 32;                      // first channel of this warp
+        const int tch = lane >> 3, tcol = (lane & 7) * 4;                   // transposed access: 4 channels x 8 float4 per instruction
+        const bool has_zin = GEN ? (p.zin != nullptr) : (EPI == 2);
+        const bool has_pool = (GEN || EPI == 1) && p.pool != 0;
+        const bool has_stats = (EPI == 1) || ((GEN || EPI == 2) && p.stats != nullptr);
+#ifdef FACL_PROFILE_ROLES
+        long long pr_wait = 0, pr_work = 0, pr_t = clock64();
+        int pr_n = 0;
+#endif
         for (int it = 0; sched.get(it, p, w); ++it) {
             const int buf = it & 1;
             mbar_wait(&acc_full[buf], (it >> 1) & 1);
             tc_fence_after_sync();
+#ifdef FACL_PROFILE_ROLES
+            { long long t = clock64(); pr_wait += t - pr_t; pr_t = t; ++pr_n; }
+#endif
             float best = 0.f;
             int barg = 0;
             const int nchunks = (mma_n + 31) / 32;
+            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N_TILE);
+#pragma unroll 1
             for (int cc = 0; cc < nchunks; ++cc) {
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N_TILE + cc * 32), v);
+                tmem_ld32(trow + cc * 32, v);
                 tmem_ld_wait();
                 const int n0 = w.nt * N_TILE + cc * 32;
                 int nvalid = p.Nd - n0;
                 nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
-                if (!cvalid || nvalid <= 0) continue;
-                if (p.out_mode == OUT_ATOMIC_CHMAJOR) {
-                    float* o = p.out + (long long)c * p.ldo + n0;
+                if (EPI == 3 || (GEN && p.out_mode == OUT_ATOMIC_CHMAJOR)) {
+                    if (cvalid) {
+                        float* o = p.out + (long long)c * p.ldo + n0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (i < nvalid) atomicAdd(o + i, v[i]);
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nvalid) atomicAdd(o + i, v[i]);
+                    }
                     continue;
                 }
+                if (nvalid <= 0 || (GEN && !cvalid)) continue;     // nvalid is warp-uniform; specialised paths have full warps
                 float z[32];
-                if (p.zin) {
-                    const float* zr = p.zin + (long long)c * p.ldz + n0;
-                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(zr) & 15) == 0)) {
+                if (has_zin) {
+                    if (!GEN) {
+                        // coalesced: each instruction reads 4 channel rows x 128 bytes, then every thread picks up its own row
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            const int ch = 4 * t + tch;
+                            *reinterpret_cast<float4*>(tb + ch * 36 + tcol) =
+                                __ldg(reinterpret_cast<const float4*>(p.zin + (long long)(ch0 + ch) * p.ldz + n0 + tcol));
+                        }
+                        __syncwarp();
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            float4 t = __ldg(reinterpret_cast<const float4*>(zr) + q);
-                            z[4 * q] = t.x; z[4 * q + 1] = t.y; z[4 * q + 2] = t.z; z[4 * q + 3] = t.w;
+                            const float4 t4 = *reinterpret_cast<const float4*>(tb + lane * 36 + q * 4);
+                            z[4 * q] = t4.x; z[4 * q + 1] = t4.y; z[4 * q + 2] = t4.z; z[4 * q + 3] = t4.w;
                         }
+                        __syncwarp();
                     } else {
+                        const float* zr = p.zin + (long long)c * p.ldz + n0;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) z[i] = (i < nvalid) ? __ldg(zr + i) : 0.f;
                     }
@@ -123,14 +161,14 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     float val = v[i] + bias;
-                    if (p.zin) val = (fmaf(zs0, z[i], zs2) > 0.f) ? val : 0.f;
-                    if (i < nvalid) {
+                    if (has_zin) val = (fmaf(zs0, z[i], zs2) > 0.f) ? val : 0.f;
+                    if (has_stats && (!GEN || i < nvalid)) {
                         stat0 += val;
-                        stat1 = fmaf(val, p.zin ? z[i] : val, stat1);
+                        stat1 = fmaf(val, has_zin ? z[i] : val, stat1);
                     }
                     v[i] = val;
                 }
-                if (p.pool >= 32 && nvalid == 32) {
+                if (has_pool && p.pool >= 32 && nvalid == 32) {
                     // the whole 32-column chunk lies inside one pooling group: branch-free scan, one merge per chunk
                     const float sg = keep_max ? 1.f : -1.f;
                     float cb = -INFINITY;
@@ -151,7 +189,7 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                         p.pool_out[gi] = best * sg;
                         if (p.pool_arg) p.pool_arg[gi] = (unsigned char)barg;
                     }
-                } else if (p.pool) {
+                } else if (has_pool) {
                     const int pm = p.pool - 1;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
@@ -170,17 +208,25 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                         }
                     }
                 }
-                if (p.out_mode == OUT_CHMAJOR) {
-                    float* o = p.out + (long long)c * p.ldo + n0;
-                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                if (!GEN) {
+                    if (p.out_mode == OUT_CHMAJOR) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
-                            reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    } else {
+                            *reinterpret_cast<float4*>(tb + lane * 36 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        __syncwarp();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (i < nvalid) o[i] = v[i];
+                        for (int t = 0; t < 8; ++t) {
+                            const int ch = 4 * t + tch;
+                            *reinterpret_cast<float4*>(p.out + (long long)(ch0 + ch) * p.ldo + n0 + tcol) =
+                                *reinterpret_cast<const float4*>(tb + ch * 36 + tcol);
+                        }
+                        __syncwarp();
                     }
+                } else if (p.out_mode == OUT_CHMAJOR) {
+                    float* o = p.out + (long long)c * p.ldo + n0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nvalid) o[i] = v[i];
                 } else if (p.out_mode == OUT_ROWMAJOR) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
@@ -194,8 +240,16 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
+#ifdef FACL_PROFILE_ROLES
+            { long long t = clock64(); pr_work += t - pr_t; pr_t = t; }
+#endif
         }
-        if (p.stats && cvalid) {
+#ifdef FACL_PROFILE_ROLES
+        if (blockIdx.x == 0 && threadIdx.x == 0 && pr_n > 4)
+            printf("gemm_img<%d> Md %d Nd %d Kd %d: epilogue tiles %d wait_acc %lld work %lld (cycles/tile)\n", EPI, p.Md, p.Nd, p.Kd,
+                   pr_n, pr_wait / pr_n, pr_work / pr_n);
+#endif
+        if (has_stats && cvalid) {
             int pidx = sched.split ? 0 : (blockIdx.x / sched.numMT);
             float* st = p.stats + ((long long)pidx * p.Md + c) * 2;
             st[0] = stat0;
@@ -205,13 +259,27 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
         // =============================== MMA issuer ===============================
         const uint32_t idesc = umma_idesc_bf16(M_TILE, mma_n) | (b_k ? 0u : UMMA_B_MN_MAJOR);
         int sa = 0, pa = 0, sb = 0, pb = 0;
+#ifdef FACL_PROFILE_ROLES
+        long long pm_acc = 0, pm_ops = 0, pm_t = clock64(), pm_t0 = pm_t;
+        int pm_n = 0;
+#endif
         for (int it = 0; sched.get(it, p, w); ++it) {
             const int buf = it & 1;
             mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
             tc_fence_after_sync();
+#ifdef FACL_PROFILE_ROLES
+            { long long t = clock64(); pm_acc += t - pm_t; pm_t = t; ++pm_n; }
+#endif
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N_TILE);
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
+#ifdef FACL_PROFILE_ROLES
+                pm_t = clock64();
+#endif
                 mbar_wait(&a_full[sa], pa);
+                mbar_wait(&b_full[sb], pb);
+#ifdef FACL_PROFILE_ROLES
+                { long long t = clock64(); pm_ops += t - pm_t; pm_t = t; }
+#endif
                 const uint32_t a_hi = smem_u32(a_ring + sa * A_SLOT), a_lo = a_hi + A_TILE_BYTES;
                 if (b_k) {
                     // one full K-major B tile in a pair of half slots: [hi | lo]
@@ -270,6 +338,11 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                 if (++sa == SA) { sa = 0; pa ^= 1; }
             }
         }
+#ifdef FACL_PROFILE_ROLES
+        if (blockIdx.x == 0 && lane == 0 && pm_n > 4)
+            printf("gemm_img Md %d Nd %d Kd %d: mma tiles %d wait_acc_empty %lld wait_operands %lld total %lld (cycles/tile)\n", p.Md, p.Nd,
+                   p.Kd, pm_n, pm_acc / pm_n, pm_ops / pm_n, (clock64() - pm_t0) / pm_n);
+#endif
     } else if (lane == 0) {
         // =============================== TMA issuer ===============================
         int sa = 0, pa = 0, sb = 0, pb = 0;
@@ -423,10 +496,13 @@ size_t act_image_half_bytes(int C, long long R) {
 
 int launch_gemm_img(const GemmParams& p, cudaStream_t stream) {
     static bool configured = false;
-    const int smem_bytes = 4 * (A_TILE_BYTES + B_TILE_BYTES) + 1024 + 256;
+    const int smem_bytes = 4 * (A_TILE_BYTES + B_TILE_BYTES) + 1024 + 256 + 4 * 32 * 36 * 4;
     if (!configured) {
-        FACL_CHECK(cudaFuncSetAttribute(gemm_img_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        FACL_CHECK(cudaFuncSetAttribute(gemm_img_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+#define FACL_IMG_ATTR(N, E) \
+        FACL_CHECK(cudaFuncSetAttribute(gemm_img_kernel<N, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        FACL_IMG_ATTR(1, 0) FACL_IMG_ATTR(1, 1) FACL_IMG_ATTR(1, 2) FACL_IMG_ATTR(1, 3)
+        FACL_IMG_ATTR(2, 0) FACL_IMG_ATTR(2, 1) FACL_IMG_ATTR(2, 2) FACL_IMG_ATTR(2, 3)
+#undef FACL_IMG_ATTR
         configured = true;
     }
     const bool a_img = p.a_mode == A_IMAGE, b_k = p.b_mode == B_IMAGE_K;
@@ -454,12 +530,21 @@ int launch_gemm_img(const GemmParams& p, cudaStream_t stream) {
     } else {
         grid = numMT * gemm_tc_ctas_per_mtile(p.Md, p.Nd);
     }
+    // epilogue specialisation: the fast ones need full 32-channel warps, whole 32-column chunks and 16-byte aligned rows
+    const bool tidy = (p.Md % 32 == 0) && (p.Nd % 32 == 0) && p.out && (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    int epi = 0;
+    if (p.out_mode == OUT_ATOMIC_CHMAJOR) epi = 3;
+    else if (p.out_mode == OUT_CHMAJOR && tidy && !p.zin && p.stats) epi = 1;
+    else if (p.out_mode == OUT_CHMAJOR && tidy && p.zin && !p.pool && (p.ldz % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.zin) & 15) == 0)) epi = 2;
     ScopedTimer timer(p.tag, stream);
     count_launch();
-    if (p.nsplit == 3)
-        gemm_img_kernel<2><<<grid, IMG_THREADS, smem_bytes, stream>>>(p);
-    else
-        gemm_img_kernel<1><<<grid, IMG_THREADS, smem_bytes, stream>>>(p);
+#define FACL_IMG_LAUNCH(N, E) gemm_img_kernel<N, E><<<grid, IMG_THREADS, smem_bytes, stream>>>(p)
+    if (p.nsplit == 3) {
+        if (epi == 1) FACL_IMG_LAUNCH(2, 1); else if (epi == 2) FACL_IMG_LAUNCH(2, 2); else if (epi == 3) FACL_IMG_LAUNCH(2, 3); else FACL_IMG_LAUNCH(2, 0);
+    } else {
+        if (epi == 1) FACL_IMG_LAUNCH(1, 1); else if (epi == 2) FACL_IMG_LAUNCH(1, 2); else if (epi == 3) FACL_IMG_LAUNCH(1, 3); else FACL_IMG_LAUNCH(1, 0);
+    }
+#undef FACL_IMG_LAUNCH
     return (int)cudaGetLastError();
 }
 
