@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
         const int tch = lane >> 3, tcol = (lane & 7) * 4;                   // transposed access: 4 channels x 8 float4 per instruction
         const bool has_zin = GEN ? (p.zin != nullptr) : (EPI == 2);
         const bool has_pool = (GEN || EPI == 1) && p.pool != 0;
-        const bool has_stats = (EPI == 1) || ((GEN || EPI == 2) && p.stats != nullptr);
+        const bool has_stats = (EPI != 3) && p.stats != nullptr;
 #ifdef FACL_PROFILE_ROLES
         long long pr_wait = 0, pr_work = 0, pr_t = clock64();
         int pr_n = 0;
@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                     }
                     continue;
                 }
-                if (nvalid <= 0 || (GEN && !cvalid)) continue;     // nvalid is warp-uniform; specialised paths have full warps
+                // nvalid is warp-uniform; in the specialised paths a warp is either wholly inside Md or wholly outside (Md % 32 == 0)
+                if (nvalid <= 0 || !cvalid) continue;
                 float z[32];
                 if (has_zin) {
                     if (!GEN) {
@@ -534,7 +535,7 @@ int launch_gemm_img(const GemmParams& p, cudaStream_t stream) {
     const bool tidy = (p.Md % 32 == 0) && (p.Nd % 32 == 0) && p.out && (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     int epi = 0;
     if (p.out_mode == OUT_ATOMIC_CHMAJOR) epi = 3;
-    else if (p.out_mode == OUT_CHMAJOR && tidy && !p.zin && p.stats) epi = 1;
+    else if (p.out_mode == OUT_CHMAJOR && tidy && !p.zin) epi = 1;
     else if (p.out_mode == OUT_CHMAJOR && tidy && p.zin && !p.pool && (p.ldz % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.zin) & 15) == 0)) epi = 2;
     ScopedTimer timer(p.tag, stream);
     count_launch();

@@ -249,7 +249,7 @@ def test_gemm_xt4(nsplit):
 
 
 @pytest.mark.parametrize("nsplit", [1, 3])
-@pytest.mark.parametrize("Cout,Cin,R", [(256, 259, 1024), (512, 256, 640), (128, 64, 200)])
+@pytest.mark.parametrize("Cout,Cin,R", [(256, 259, 1024), (512, 256, 640), (128, 64, 200), (64, 128, 512), (96, 64, 256)])
 def test_gemm_activation_images(nsplit, Cout, Cin, R):
     """TMA-only GEMMs over pre-converted activation images (gemm_img.cu): forward (reduction over channels, with the
     BN+ReLU transform, statistics and max-pool epilogue) and weight gradient (reduction over rows, split-K)."""
