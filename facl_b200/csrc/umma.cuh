@@ -41,6 +41,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
+#ifdef FACL_WAIT_SLEEP_NS
+        __nanosleep(FACL_WAIT_SLEEP_NS);     // polling costs issue slots and shared-memory port time that the other roles need
+#endif
     }
 }
 
