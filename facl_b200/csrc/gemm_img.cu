@@ -159,26 +159,39 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                         for (int i = 0; i < 32; ++i) z[i] = (i < nvalid) ? __ldg(zr + i) : 0.f;
                     }
                 }
+                // four independent partial sums: one warp per scheduler has to hide its own FADD / FFMA latency
+                float s0p[4] = {0.f, 0.f, 0.f, 0.f}, s1p[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     float val = v[i] + bias;
                     if (has_zin) val = (fmaf(zs0, z[i], zs2) > 0.f) ? val : 0.f;
                     if (has_stats && (!GEN || i < nvalid)) {
-                        stat0 += val;
-                        stat1 = fmaf(val, has_zin ? z[i] : val, stat1);
+                        s0p[i & 3] += val;
+                        s1p[i & 3] = fmaf(val, has_zin ? z[i] : val, s1p[i & 3]);
                     }
                     v[i] = val;
                 }
+                stat0 += (s0p[0] + s0p[1]) + (s0p[2] + s0p[3]);
+                stat1 += (s1p[0] + s1p[1]) + (s1p[2] + s1p[3]);
                 if (has_pool && p.pool >= 32 && nvalid == 32) {
                     // the whole 32-column chunk lies inside one pooling group: branch-free scan, one merge per chunk
                     const float sg = keep_max ? 1.f : -1.f;
-                    float cb = -INFINITY;
-                    int ci = 0;
+                    // four interleaved scans (i = k mod 4), merged with the lowest index winning ties (first-hit rule)
+                    float cbk[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    int cik[4] = {0, 1, 2, 3};
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float sv = v[i] * sg;
-                        ci = (sv > cb) ? i : ci;
-                        cb = fmaxf(cb, sv);
+                        cik[i & 3] = (sv > cbk[i & 3]) ? i : cik[i & 3];
+                        cbk[i & 3] = fmaxf(cbk[i & 3], sv);
+                    }
+                    float cb = cbk[0];
+                    int ci = cik[0];
+#pragma unroll
+                    for (int k = 1; k < 4; ++k) {
+                        const bool take = (cbk[k] > cb) || (cbk[k] == cb && cik[k] < ci);
+                        ci = take ? cik[k] : ci;
+                        cb = take ? cbk[k] : cb;
                     }
                     const int pos0 = (cc * 32) & (p.pool - 1);
                     if (pos0 == 0 || cb > best) {
