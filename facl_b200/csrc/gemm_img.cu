@@ -249,6 +249,10 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (i < nvalid) p.out[(long long)(n0 + i) * p.ldo + c] += v[i];
+                } else if (p.out_mode == OUT_ATOMIC_ROWMAJOR) {   // split-K partial: lanes are consecutive m -> coalesced reductions
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nvalid) atomicAdd(p.out + (long long)(n0 + i) * p.ldo + c, v[i]);
                 }
             }
             tc_fence_before_sync();
@@ -536,7 +540,8 @@ int launch_gemm_img(const GemmParams& p, cudaStream_t stream) {
     } else if (p.b_img.cgs < KB * 8 || (long long)p.b_img.rbs * 64 < p.Nd) {
         return (int)cudaErrorInvalidValue;
     }
-    if (p.ksplit > 1 && (p.out_mode != OUT_ATOMIC_CHMAJOR || p.stats || p.pool)) return (int)cudaErrorInvalidValue;
+    if (p.ksplit > 1 && ((p.out_mode != OUT_ATOMIC_CHMAJOR && p.out_mode != OUT_ATOMIC_ROWMAJOR) || p.stats || p.pool))
+        return (int)cudaErrorInvalidValue;
     int grid;
     if (p.ksplit > 1) {
         if (p.ksplit > KB) return (int)cudaErrorInvalidValue;

@@ -43,7 +43,8 @@ struct ActImage {
 
 enum : int { A_PACKED = 0, A_ROWMAJOR = 1, A_IMAGE = 2 };
 enum : int { B_ROWMAJOR = 1, B_CHMAJOR = 2, B_XT4 = 3, B_IMAGE_MN = 4, B_IMAGE_K = 5 };
-enum : int { OUT_NONE = 0, OUT_CHMAJOR = 1, OUT_ROWMAJOR = 2, OUT_ATOMIC_CHMAJOR = 3, OUT_ROWMAJOR_ACC = 4 };
+enum : int { OUT_NONE = 0, OUT_CHMAJOR = 1, OUT_ROWMAJOR = 2, OUT_ATOMIC_CHMAJOR = 3, OUT_ROWMAJOR_ACC = 4,
+              OUT_ATOMIC_ROWMAJOR = 5 /* gemm_img.cu only: atomicAdd out[n*ldo + m], for split-K */ };
 
 struct GemmParams {
     int Md, Nd, Kd;

