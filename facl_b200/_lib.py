@@ -77,6 +77,24 @@ class TrainStepArgs(C.Structure):
                 ("keys", C.c_void_p), ("dkeys", C.c_void_p), ("dx_extra", C.c_void_p)]
 
 
+class PointSource(C.Structure):
+    _fields_ = [("rows", C.c_void_p), ("offsets", C.c_void_p), ("C", C.c_int)]
+
+
+class ViewRecipe(C.Structure):
+    _fields_ = [("source", C.c_int), ("channel", C.c_int), ("nonzero_only", C.c_int), ("jitter", C.c_int),
+                ("mirror", C.c_int), ("rotate", C.c_int)]
+
+
+class AugmentArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("G", C.c_int), ("N", C.c_int), ("n_sources", C.c_int),
+                ("sources", C.POINTER(PointSource)), ("recipes", C.POINTER(ViewRecipe)),
+                ("sigma", C.c_float), ("clip", C.c_float),
+                ("idx", C.c_void_p), ("noise", C.c_void_p), ("angle_u", C.c_void_p),
+                ("seed", C.c_ulonglong), ("step", C.c_ulonglong), ("g_major", C.c_int), ("max_rows", C.c_int),
+                ("out", C.c_void_p), ("out_rows", C.c_void_p)]
+
+
 _I, _LL, _P, _F, _SZ = C.c_int, C.c_longlong, C.c_void_p, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); must list every symbol include/facl_b200.h declares (tests check this)
@@ -86,6 +104,9 @@ SIGNATURES = {
     "facl_fps": (_I, [_P, _I, _I, _I, _P, _I, _P, _P]),
     "facl_fps_reorder": (_I, [_P, _I, _I, _I, _P, _I, _P, _P]),
     "facl_group_points": (_I, [_P, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
+    "facl_group_level2_scratch_bytes": (_SZ, [_I, _I, _I, _I]),
+    "facl_group_level2": (_I, [_P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "facl_augment_views": (_I, [C.POINTER(AugmentArgs), _P]),
     "facl_packed_weight_bytes": (_SZ, [_I, _I]),
     "facl_pack_weight": (_I, [_P, _LL, _LL, _I, _I, _P, _P]),
     "facl_gemm_stat_partials": (_I, [_I, _I]),

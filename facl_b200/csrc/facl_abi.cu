@@ -26,6 +26,31 @@ int facl_group_points(const float* points, int M, int N, int D, int Sc, int K, f
     return group_launch(points, M, N, D, Sc, K, r2, xt, idx, S(stream));
 }
 
+size_t facl_group_level2_scratch_bytes(int M, int N1, int S2, int K) { return group_level2_scratch_bytes(M, N1, S2, K); }
+
+int facl_group_level2(const float* feats, int M, int C, int N1, int S2, int K, float r2, float* out, int* idx, void* scratch,
+                      void* stream) {
+    return group_level2_launch(feats, M, C, N1, S2, K, r2, out, idx, scratch, S(stream));
+}
+
+int facl_augment_views(const facl_augment_args* a, void* stream) {
+    if (!a || !a->sources || !a->recipes || a->n_sources <= 0 || a->n_sources > AUGMENT_MAX_SOURCES || a->G <= 0 ||
+        a->G > AUGMENT_MAX_VIEWS)
+        return (int)cudaErrorInvalidValue;
+    AugmentParams p{};
+    p.B = a->B; p.G = a->G; p.N = a->N; p.n_sources = a->n_sources; p.g_major = a->g_major;
+    p.sigma = a->sigma; p.clip = a->clip;
+    for (int i = 0; i < a->n_sources; ++i) p.source[i] = AugmentSource{a->sources[i].rows, a->sources[i].offsets, a->sources[i].C};
+    for (int g = 0; g < a->G; ++g) {
+        const facl_view_recipe& r = a->recipes[g];
+        p.recipe[g] = AugmentRecipe{r.source, r.channel, r.nonzero_only, r.jitter, r.mirror, r.rotate};
+    }
+    p.idx = a->idx; p.noise = a->noise; p.angle_u = a->angle_u;
+    p.seed = a->seed; p.step = a->step;
+    p.out = a->out; p.out_rows = a->out_rows;
+    return augment_launch(p, a->max_rows, S(stream));
+}
+
 size_t facl_packed_weight_bytes(int rows, int cols) { return packed_weight_bytes(rows, cols); }
 
 int facl_pack_weight(const float* src, long long stride_m, long long stride_k, int rows, int cols, void* image, void* stream) {

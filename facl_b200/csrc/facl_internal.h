@@ -68,8 +68,39 @@ enum TimingTag {
     TAG_GEMM_BASE = 0,
     TAG_GROUP = 27, TAG_FPS = 28, TAG_PACK = 29, TAG_BN = 30, TAG_POOLMISC = 31, TAG_SCATTER = 32, TAG_LOSS_GEMM = 33,
     TAG_LOSS_MISC = 34, TAG_ADAM = 35, TAG_TRANSPOSE = 36, TAG_MEMSET = 37, TAG_L1_MISC = 38, TAG_L1_PASS_A = 39,
-    TAG_L1_PASS_B = 40, TAG_L1_PASS_C = 41, TAG_L1_PASS_D = 42, TAG_IMAGE = 43, NUM_TIMING_TAGS = 44
+    TAG_L1_PASS_B = 40, TAG_L1_PASS_C = 41, TAG_L1_PASS_D = 42, TAG_IMAGE = 43, TAG_AUGMENT = 44, TAG_GROUP2 = 45, NUM_TIMING_TAGS = 46
 };
+}  // namespace facl
+
+namespace facl {
+// augment.cu
+constexpr int AUGMENT_MAX_VIEWS = 32;
+constexpr int AUGMENT_MAX_SOURCES = 8;
+struct AugmentSource {
+    const float* rows;       // (total rows, C) row-major
+    const int* offsets;      // (B + 1) first row of each sequence
+    int C;
+};
+struct AugmentRecipe {
+    int source, channel, nonzero_only, jitter, mirror, rotate;
+};
+struct AugmentParams {
+    int B, G, N, n_sources, g_major;
+    float sigma, clip;
+    AugmentSource source[AUGMENT_MAX_SOURCES];
+    AugmentRecipe recipe[AUGMENT_MAX_VIEWS];
+    const int* idx;          // explicit draws (all three or none) ...
+    const double* noise;
+    const double* angle_u;
+    unsigned long long seed, step;   // ... else Philox4x32-10 keyed by (seed, step)
+    float* out;
+    int* out_rows;
+};
+int augment_launch(const AugmentParams& p, int max_rows, cudaStream_t st);
+// group2.cu
+size_t group_level2_scratch_bytes(int M, int N1, int S2, int K);
+int group_level2_launch(const float* feats, int M, int C, int N1, int S2, int K, float r2, float* out, int* idx, void* scratch,
+                        cudaStream_t st);
 }  // namespace facl
 
 namespace facl {

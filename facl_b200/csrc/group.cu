@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
     if (!active) return;
     __syncwarp();
 
-    float* xrow = xt + ((long long)m * S + s) * K * D;
+    float* xrow = xt ? xt + ((long long)m * S + s) * K * D : nullptr;      // nullptr: indices only (level-2 grouping)
     int* irow = idx_out ? idx_out + ((long long)m * S + s) * K : nullptr;
     const unsigned r2bits = __float_as_uint(r2);
 
@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
         int n = (int)(unsigned)(key & 0xFFFFFFFFu);
         if (dbits > r2bits) n = s;             // d > r2 (both >= 0): redirect to the centre itself
         if (irow) irow[slot] = n;
+        if (!xrow) return;
         const float* p = cloud + (long long)n * D;
         float* o = xrow + (long long)slot * D;
         if (D4) {

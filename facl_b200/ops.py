@@ -51,6 +51,20 @@ def group_points_raw(points, S, K, r2, want_idx=True):
     return rows, idx
 
 
+def group_level2(feats, S2, K, r2, want_idx=False):
+    """feats (M,C,N1) fp32 cuda channel-first -> out (M,C,S2,K), idx (M,S2,K) int32 | None.
+    C ABI: facl_group_level2 (replaces utils_my.py:332-381)."""
+    require_cuda(feats, "points")
+    feats = feats.contiguous()
+    M, Cc, N1 = feats.shape
+    out = torch.empty((M, Cc, S2, K), dtype=torch.float32, device=feats.device)
+    idx = torch.empty((M, S2, K), dtype=torch.int32, device=feats.device) if want_idx else None
+    scratch = torch.empty(lib().facl_group_level2_scratch_bytes(M, N1, S2, K), dtype=torch.uint8, device=feats.device)
+    check(lib().facl_group_level2(ptr(feats), M, Cc, N1, S2, K, float(r2), ptr(out), ptr(idx), ptr(scratch), stream_ptr()),
+          "facl_group_level2")
+    return out, idx
+
+
 def pack_weight(w, rows, cols, stride_m, stride_k, out=None):
     """fp32 matrix view A[m][k] = w.flat[m*stride_m + k*stride_k] -> bf16 hi/lo tile image (uint8 tensor)."""
     require_cuda(w, "w")

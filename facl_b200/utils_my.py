@@ -4,6 +4,7 @@ Same names, argument meaning, return shapes and `opt` side effects as the refere
 libfacl_b200.so on the GPU (no CPU path -- CPU tensors raise).
 
   group_points_3DV / _2048 / _nums / group_points   reference utils_my.py:255-291 / :7-42 / :293-328 / :217-253
+  group_points_2 / group_points_2_3DV               reference utils_my.py:332-356 / :358-381 (level-2 set abstraction)
   global_contrast / circle_contrast / Info_NCE      reference utils_my.py:53-83 / :85-116 / :200-213
 """
 import numpy as np
@@ -52,6 +53,20 @@ def group_points(points, opt):
     opt.ball_radius = 0.14
     opt.INPUT_FEATURE_NUM = points.shape[-1]
     return _group(points, opt.sample_num_level1, opt.knn_K, opt.ball_radius, N=opt.SAMPLE_NUM)
+
+
+def group_points_2(points, sample_num_level1, sample_num_level2, knn_K, ball_radius):
+    """reference utils_my.py:332-356.  points (B, 3+C, S1) channel-first.  As in the reference, knn_K is overridden
+    to 64 (:335) and `ball_radius` is compared against SQUARED distances as given (:345).
+    -> inputs_level2 (B, 3+C, S2, 64), inputs_level2_center (B, 3, S2, 1)."""
+    out, _ = ops.group_level2(points, sample_num_level2, 64, float(ball_radius))
+    return out, points[:, 0:3, 0:sample_num_level2].unsqueeze(3)
+
+
+def group_points_2_3DV(points, sample_num_level1, sample_num_level2, knn_K, ball_radius):
+    """reference utils_my.py:358-381: knn_K = 32 and ball_radius = 0.11 are hard-coded (:361-362)."""
+    out, _ = ops.group_level2(points, sample_num_level2, 32, 0.11)
+    return out, points[:, 0:3, 0:sample_num_level2].unsqueeze(3)
 
 
 def global_contrast(num_crop, x_global, x, opt, criterion=None):

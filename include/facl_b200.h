@@ -52,6 +52,62 @@ FACL_API int facl_fps_reorder(const float* points, int V, int N, int D, const in
  * idx (M,S,K) int32 or NULL: the chosen point index per slot, after the ball redirect.  K <= 128. */
 FACL_API int facl_group_points(const float* points, int M, int N, int D, int S, int K, float r2, float* xt, int* idx, void* stream);
 
+/* ---- level-2 set-abstraction grouping ------------------------------------------------------
+ * replaces group_points_2 / group_points_2_3DV, reference training_code/utils_my.py:332-356 / :358-381.
+ * feats (M,C,N1) fp32 CHANNEL-first, channels 0..2 = xyz; centres = the first S2 points of each cloud.
+ * The K nearest of the N1 points per centre (same selection rule as facl_group_points), slots with squared
+ * distance > r2 replaced by the centre; all C channels gathered:
+ * out (M,C,S2,K) fp32 channel-first, xyz minus the centre; idx (M,S2,K) int32 or NULL.
+ * scratch: facl_group_level2_scratch_bytes() bytes of device memory (xyz row image + neighbour table). */
+FACL_API size_t facl_group_level2_scratch_bytes(int M, int N1, int S2, int K);
+FACL_API int facl_group_level2(const float* feats, int M, int C, int N1, int S2, int K, float r2, float* out, int* idx,
+                               void* scratch, void* stream);
+
+/* ---- training-view augmentation on the device -------------------------------------------
+ * replaces NTU_RGBD_new.__getitem__ / get_data_train / get_temporal_augment_data and the helpers they call
+ * (reverse_transform, rotate_trans, jitter_point_cloud), reference training_code/cn3D_data_set.py:105-121,
+ * :285-350, :654-663, :708-713, :734-748, :765-776, plus the permute + float cast of cn3d_train_motion_GL.py:226-228.
+ * One launch turns the source clouds of B sequences into G views of N points each.
+ * A source is a ragged batch: rows (sum of P_b, C) fp32 row-major (x,y,z,channels...), offsets (B+1) int32.
+ * View g is described by recipes[g]:
+ *   source        which source is resampled (with replacement);
+ *   channel       the source column copied to output column 3;
+ *   nonzero_only  draw only among the rows whose `channel` column is != 0, in row order (:657-658);
+ *   jitter        xyz += clip(sigma * z, +-clip)                                  (:765-776)
+ *   mirror        round to f32, x = -x, jitter with a second set of normals, round (:708-713)
+ *   rotate        round to f32, (x,y,z) . Ry((u - 0.5) * 0.8 * pi), round        (:734-748)
+ * applied in that order, in f64 like numpy.  Random draws: either all three arrays are given (parity with a
+ * recorded numpy stream: idx (B,G,N) int32, noise (B,G,2,N,3) f64 standard normals, angle_u (B,G) f64 in [0,1)),
+ * or all three are NULL and the kernel draws them itself (Philox4x32-10 keyed by seed, step).
+ * out: (G,B,N,4) fp32 if g_major (what facl_group_points / facl_train_step consume) else (B,G,N,4);
+ * out_rows (B,G,N) int32 or NULL: the source row each output point came from.
+ * max_rows: the largest P_b of any source used with nonzero_only (sizes the compaction list; <= 51200).
+ * A view with nothing to draw from (numpy raises) is filled with NaN. */
+typedef struct {
+    const float* rows;
+    const int* offsets;
+    int C;
+} facl_point_source;
+typedef struct {
+    int source, channel, nonzero_only, jitter, mirror, rotate;
+} facl_view_recipe;
+typedef struct {
+    int B, G, N;
+    int n_sources;
+    const facl_point_source* sources;   /* host array [n_sources], <= 8 */
+    const facl_view_recipe* recipes;    /* host array [G], G <= 32 */
+    float sigma, clip;                  /* reference: 0.01, 0.05 */
+    const int* idx;
+    const double* noise;
+    const double* angle_u;
+    unsigned long long seed, step;
+    int g_major;
+    int max_rows;
+    float* out;
+    int* out_rows;
+} facl_augment_args;
+FACL_API int facl_augment_views(const facl_augment_args* args, void* stream);
+
 /* ---- tcgen05 GEMM building block (operand packing + fused GEMM), exposed for tests and for the Python-side
  * orchestration of the encoder layers (replaces the cuDNN/cuBLAS calls behind nn.Conv2d(1x1)/nn.Linear in
  * reference training_code/cn3d_model_conbag.py:162-207) ------------------------------------------------------ */
@@ -265,9 +321,9 @@ FACL_API int facl_train_step(const facl_train_step_args* args, void* stream);
  * Tags: 3*layer + {0 forward, 1 weight-grad, 2 data-grad} for layer 0..8 (7 = netR_FC.3, 8 = mapping), then
  * 27 grouping, 28 fps, 29 weight packing, 30 BN finalize, 31 pooling misc, 32 max-pool scatter, 33 loss GEMMs,
  * 34 loss misc, 35 adam, 36 transposes, 37 memset/fill, 38 fused-L1 misc, 39..42 fused-L1 passes A, B, C, D,
- * 43 activation-image conversion.
+ * 43 activation-image conversion, 44 view augmentation, 45 level-2 grouping (xyz image + channel gather).
  * facl_launch_count: kernels launched so far. */
-#define FACL_NUM_TIMING_TAGS 44
+#define FACL_NUM_TIMING_TAGS 46
 FACL_API void facl_timing_enable(int on);
 FACL_API int facl_timing_collect(float* ms_per_tag, int* count_per_tag, int ntags);
 FACL_API long long facl_launch_count(void);

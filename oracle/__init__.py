@@ -16,7 +16,7 @@ unmodified reference modules from /root/reference in the authoring container
 `tests/test_oracle_golden.py` re-checks the oracle against those fixtures on every CPU test run.
 """
 from .fps import farthest_point_sampling, fps_reorder_indices, fps_sample_data  # noqa: F401
-from .grouping import knn_ball_indices, group_points  # noqa: F401
+from .grouping import knn_ball_indices, group_points, group_points_level2  # noqa: F401
 from .encoder import EncoderParams, encoder_forward, init_state_dict, STATE_KEYS  # noqa: F401
 from .losses import global_contrast, circle_contrast, info_nce_logits  # noqa: F401
 from .train_step import train_step, adam_update  # noqa: F401

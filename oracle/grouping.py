@@ -58,3 +58,24 @@ def group_points(points, S, K, r2):
     xt = rows.permute(0, 3, 1, 2)                        # logical (M,D,S,K), physical [M][S][K][D]
     yt = centre.contiguous().permute(0, 2, 1)[..., None]  # (M,3,S,1)
     return xt, yt, idx
+
+
+def group_points_level2(feats, S2, K, r2):
+    """Level-2 set abstraction, reference utils_my.py:332-356 (`group_points_2`, K = 64 hard-coded at :335) and
+    :358-381 (`group_points_2_3DV`, K = 32, radius 0.11 hard-coded at :361-362).
+
+    feats (M, C, N1) float32 channel-first, channels 0..2 = xyz; centres = the first S2 points (:339, :353).
+    Same selection rule as level 1 (K smallest squared distances, slots with d > r2 redirected to the centre,
+    :342-348 -- note the reference compares the SQUARED distance with `ball_radius` as given), then every channel is
+    gathered (:350-351) and the centre subtracted from xyz (:354).
+    Returns (inputs_level2 (M,C,S2,K), centre (M,3,S2,1), idx (M,S2,K) int32 in ascending (d, n) order)."""
+    f = feats.detach().to(torch.float32).contiguous()
+    M, C, N1 = f.shape
+    rows = f[:, 0:3, :].permute(0, 2, 1).contiguous()                     # (M,N1,3)
+    idx_np, _ = knn_ball_indices(rows.numpy(), S2, K, r2)
+    idx = torch.from_numpy(idx_np)
+    flat = idx.view(M, 1, S2 * K).to(torch.int64).expand(M, C, S2 * K)
+    out = torch.gather(f, 2, flat).view(M, C, S2, K).clone()
+    centre = f[:, 0:3, 0:S2].unsqueeze(3)
+    out[:, 0:3] = out[:, 0:3] - centre
+    return out, centre, idx

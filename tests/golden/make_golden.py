@@ -13,6 +13,10 @@ What is executed from the reference, untouched:
   * training_code/cn3D_data_set.py:675-694 farthest_point_sampling_fast -- the module itself cannot be
                                       imported (imageio missing), so the method's source lines are
                                       exec'd from the file text at run time; nothing is copied here.
+  * training_code/cn3D_data_set.py:285-350, 654-663, 708-713, 734-748, 765-776 -- get_data_train,
+                                      get_temporal_augment_data, reverse_transform, rotate_trans,
+                                      jitter_point_cloud, lifted the same way and driven in the order of
+                                      NTU_RGBD_new.__getitem__ (:105-121) with np.random.seed(...)
   * torch.optim.Adam with the reference's hyper-parameters (cn3d_train_motion_GL.py:180).
 
 While writing each fixture the script also checks that `oracle/` reproduces it (the pin), and
@@ -339,7 +343,102 @@ def gen_losses():
     np.savez_compressed(os.path.join(HERE, "losses.npz"), **out)
 
 
+def sorted_cols(a):
+    """(M,C,S,K): sort the K columns of every (m,s) group lexicographically over the C channels."""
+    M, C, S, K = a.shape
+    rows = np.ascontiguousarray(a.transpose(0, 2, 3, 1)).reshape(M * S, K, C)
+    out = np.empty_like(rows)
+    for i in range(rows.shape[0]):
+        r = rows[i]
+        out[i] = r[np.lexsort(r.T[::-1])]
+    return out.reshape(M, S, K, C)
+
+
+def gen_group2():
+    """Level-2 grouping: utils_my.group_points_2 (K=64) and group_points_2_3DV (K=32, radius 0.11), run unmodified."""
+    out = {}
+    cases = [("l2", "group_points_2", 2, 9, 512, 128, 64, 0.02), ("l2_3dv", "group_points_2_3DV", 2, 11, 256, 64, 32, 0.11),
+             ("l2_small", "group_points_2", 2, 7, 96, 32, 64, 0.005)]
+    for ci, (name, fn, M, C, S1, S2, K, r2) in enumerate(cases):
+        g = torch.Generator().manual_seed(700 + ci)
+        xyz = torch.from_numpy(synth.make_sequences(M, 1, S1, seed=700 + ci)[:, 0, :, 0:3]).permute(0, 2, 1)
+        feats = torch.cat([xyz, torch.randn(M, C - 3, S1, generator=g)], 1).contiguous()
+        before = feats.clone()
+        xt, yt = getattr(ref_utils, fn)(feats, S1, S2, K, torch.tensor(r2))
+        assert torch.equal(before, feats)
+        assert xt.shape == (M, C, S2, K) and yt.shape == (M, 3, S2, 1)
+        oxt, oyt, oidx = oracle.group_points_level2(feats, S2, K, r2)
+        assert np.array_equal(sorted_cols(xt.numpy()), sorted_cols(oxt.numpy())), f"oracle level-2 grouping != reference ({name})"
+        assert torch.equal(oyt, yt)
+        red = float((oidx == torch.arange(S2)[None, :, None]).float().mean())
+        out[f"{name}_feats"] = feats.numpy()
+        out[f"{name}_cfg"] = np.array([S2, K], dtype=np.int64)
+        out[f"{name}_r2"] = np.array(r2, dtype=np.float64)
+        out[f"{name}_sorted"] = sorted_cols(xt.numpy())
+        print(f"group2 {name}: ok, {red:.3f} of the slots are the centre")
+    out["names"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(HERE, "group2.npz"), **out)
+
+
+def lift_reference_augment():
+    """A stand-in object carrying the reference's own augmentation methods (source text exec'd at run time)."""
+    text = open(os.path.join(REF, "cn3D_data_set.py")).read().split("\n")
+    ns = {"np": np, "NUM_POINT": 512}
+    for a, b in [(285, 350), (654, 663), (708, 713), (734, 748), (765, 776)]:
+        exec(textwrap.dedent("\n".join(text[a - 1:b])), ns)
+    cls = type("RefAug", (), {k: ns[k] for k in ("get_data_train", "get_temporal_augment_data", "reverse_transform",
+                                                  "rotate_trans", "jitter_point_cloud")})
+    return cls()
+
+
+def gen_augment():
+    from oracle import augment as oaug
+    ref = lift_reference_augment()
+    out = {}
+    cases = [(2048, 2048, 600, 200), (700, 512, 90, 33), (5000, 1500, 2048, 2048)]
+    for ci, (P, Pk, P1, P2) in enumerate(cases):
+        rng = np.random.default_rng(900 + ci)
+
+        def cloud(n, ch):
+            a = np.empty((n, ch), np.float32)
+            a[:, 0] = 0.45 * rng.uniform(-0.5, 0.5, n)
+            a[:, 1] = rng.uniform(-0.5, 0.5, n)
+            a[:, 2] = 0.30 * rng.uniform(-0.5, 0.5, n)
+            a[:, 3:] = rng.uniform(-0.5, 0.5, (n, ch - 3))
+            return a
+        points, key, res1, res2 = cloud(P, 8), cloud(Pk, 8), cloud(P1, 8), cloud(P2, 8)
+        points[rng.uniform(size=P) < 0.4, 4] = 0.0          # rows get_temporal_augment_data must skip
+        points[rng.uniform(size=P) < 0.7, 7] = 0.0
+        srcs64 = [a.astype(np.float64) for a in (points, key, res1, res2)]   # the dataset stores float64 (.npy)
+        np.random.seed(50 + ci)
+        p = srcs64[0]
+        t2 = ref.get_temporal_augment_data(p, 4)
+        t4 = ref.get_temporal_augment_data(p, 7)
+        views = ref.get_data_train(p[:, :4], srcs64[1][:, :4], t2[:, :4], t4[:, :4], srcs64[2][:, :4], srcs64[3][:, :4],
+                                   num_crop=10)
+        views = torch.from_numpy(views).type(torch.FloatTensor).numpy()      # cn3d_train_motion_GL.py:228
+        draws = oaug.record_draws(np.random.RandomState(50 + ci), srcs64, 512)
+        mine = oaug.make_views(srcs64, draws)
+        rot = [g for g, r in enumerate(oaug.GET_DATA_TRAIN) if r[5]]
+        exact = [g for g in range(10) if g not in rot]
+        assert np.array_equal(mine[exact], views[exact]), f"oracle augmentation != reference (case {ci})"
+        assert np.abs(mine[rot] - views[rot]).max() <= 6e-8, np.abs(mine[rot] - views[rot]).max()   # BLAS dot vs explicit sums
+        for k, a in zip(("points", "key", "res1", "res2"), (points, key, res1, res2)):
+            out[f"{k}_{ci}"] = a
+        out[f"idx_{ci}"], out[f"noise_{ci}"], out[f"angle_{ci}"] = draws.idx, draws.noise.astype(np.float64), draws.angle_u
+        out[f"views_{ci}"] = views
+        print(f"augment case {ci}: ok, max rot diff {np.abs(mine[rot] - views[rot]).max():.2e}")
+    out["n_cases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(HERE, "augment.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        sys.exit(0)
+    gen_augment()
+    gen_group2()
     gen_fps()
     gen_group()
     gen_losses()

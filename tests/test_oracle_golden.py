@@ -143,3 +143,41 @@ def test_info_nce_logits(golden_dir):
     logits, labels = oracle.info_nce_logits(torch.from_numpy(z["x"])[: 2 * B], B)
     assert np.allclose(logits.numpy(), z["info_nce_logits"], rtol=1e-5, atol=1e-5)
     assert labels.shape == (B,) and int(labels.sum()) == 0
+
+
+def test_augment_matches_reference(golden_dir):
+    """get_data_train + get_temporal_augment_data of the unmodified reference, driven by np.random.seed, against the
+    restatement fed with the same draws in the order the reference consumes them."""
+    from oracle import augment as oaug
+    z = np.load(os.path.join(golden_dir, "augment.npz"))
+    for i in range(int(z["n_cases"])):
+        srcs = [z[f"{k}_{i}"] for k in ("points", "key", "res1", "res2")]
+        draws = oaug.Draws(z[f"idx_{i}"], z[f"noise_{i}"], z[f"angle_{i}"])
+        # the recorded draws are what numpy's legacy RandomState yields in the reference's call order
+        again = oaug.record_draws(np.random.RandomState(50 + i), srcs, 512)
+        assert np.array_equal(again.idx, draws.idx) and np.array_equal(again.noise, draws.noise)
+        views = oaug.make_views(srcs, draws)
+        assert views.dtype == np.float32 and views.shape == (10, 512, 4)
+        assert np.array_equal(views, z[f"views_{i}"]), f"case {i}"
+        # temporal views only hold rows whose temporal channel is non-zero
+        assert np.all(views[6, :, 3] != 0) and np.all(views[7, :, 3] != 0)
+
+
+def _sorted_cols(a):
+    M, C, S, K = a.shape
+    rows = np.ascontiguousarray(a.transpose(0, 2, 3, 1)).reshape(M * S, K, C)
+    out = np.empty_like(rows)
+    for i in range(rows.shape[0]):
+        r = rows[i]
+        out[i] = r[np.lexsort(r.T[::-1])]
+    return out.reshape(M, S, K, C)
+
+
+def test_level2_grouping_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "group2.npz"))
+    for name in z["names"]:
+        feats = torch.from_numpy(z[f"{name}_feats"])
+        S2, K = (int(v) for v in z[f"{name}_cfg"])
+        out, centre, idx = oracle.group_points_level2(feats, S2, K, float(z[f"{name}_r2"]))
+        assert np.array_equal(_sorted_cols(out.numpy()), z[f"{name}_sorted"]), name
+        assert torch.equal(centre[..., 0], feats[:, 0:3, 0:S2])

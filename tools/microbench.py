@@ -69,6 +69,30 @@ def main():
         nbytes = V * (16 * N + 16 * S * K + 12 * S)
         print(json.dumps(dict(op="group", M=V, N=N, S=S, K=K, r2=r2, ms=ms, us_per_cloud=ms * 1e3 / V, algorithmic_GBs=nbytes / ms / 1e6,
                               hbm_frac=nbytes / ms / 1e6 / HBM, frac_slots_at_centre=redirected)), flush=True)
+    # ---------------- view augmentation ----------------
+    from facl_b200 import cn3D_data_set as ds
+    rng = np.random.default_rng(0)
+    for B, N, P in ([(64, 512, 2048)] if args.quick else [(64, 512, 2048), (64, 2048, 2048), (256, 2048, 4096)]):
+        srcs = []
+        for s in range(4):
+            a = rng.uniform(-0.5, 0.5, (B * P, 8)).astype(np.float32)
+            a[rng.uniform(size=B * P) < 0.5, 4] = 0
+            a[rng.uniform(size=B * P) < 0.5, 7] = 0
+            srcs.append(ds.Ragged(torch.from_numpy(a).cuda(), (torch.arange(B + 1, dtype=torch.int32) * P).cuda(), P))
+        aug = ds.ViewAugmenter(num_point=N)
+        ms = timed(lambda: aug.get_data_train(srcs))
+        G = len(ds.GET_DATA_TRAIN)
+        nbytes = B * G * N * (16 + 16) + 2 * B * P * 4      # gathered rows (xyz + channel) in, views out, temporal-channel scans
+        print(json.dumps(dict(op="augment_views", B=B, G=G, N=N, P=P, rng="philox", ms=ms, sequences_per_s=B / ms * 1e3,
+                              algorithmic_GBs=nbytes / ms / 1e6, hbm_frac=nbytes / ms / 1e6 / HBM)), flush=True)
+    # ---------------- level-2 grouping ----------------
+    for M, C, S1, S2, K in ([(256, 131, 512, 128, 64)] if args.quick else [(1280, 131, 512, 128, 64), (1280, 259, 64, 64, 32)]):
+        feats = torch.randn(M, C, S1, device=dev)
+        feats[:, :3] = torch.rand(M, 3, S1, device=dev) - 0.5
+        ms = timed(lambda: ops.group_level2(feats, S2, K, 0.02), iters=5)
+        nbytes = M * (4 * C * S1 + 4 * C * S2 * K)
+        print(json.dumps(dict(op="group_level2", M=M, C=C, S1=S1, S2=S2, K=K, ms=ms, us_per_cloud=ms * 1e3 / M,
+                              algorithmic_GBs=nbytes / ms / 1e6, hbm_frac=nbytes / ms / 1e6 / HBM)), flush=True)
     # ---------------- forward-only feature extraction (configs[4]) ----------------
     for G in ([10] if args.quick else [10, 20]):
         B, N = 64, 2048
