@@ -89,7 +89,7 @@ class ViewRecipe(C.Structure):
 class AugmentArgs(C.Structure):
     _fields_ = [("B", C.c_int), ("G", C.c_int), ("N", C.c_int), ("n_sources", C.c_int),
                 ("sources", C.POINTER(PointSource)), ("recipes", C.POINTER(ViewRecipe)),
-                ("sigma", C.c_float), ("clip", C.c_float),
+                ("sigma", C.c_double), ("clip", C.c_double),
                 ("idx", C.c_void_p), ("noise", C.c_void_p), ("angle_u", C.c_void_p),
                 ("seed", C.c_ulonglong), ("step", C.c_ulonglong), ("g_major", C.c_int), ("max_rows", C.c_int),
                 ("out", C.c_void_p), ("out_rows", C.c_void_p)]
@@ -106,6 +106,8 @@ SIGNATURES = {
     "facl_group_points": (_I, [_P, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
     "facl_group_level2_scratch_bytes": (_SZ, [_I, _I, _I, _I]),
     "facl_group_level2": (_I, [_P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "facl_l2_normalize": (_I, [_P, _I, _I, _P, _P]),
+    "facl_softmax_xent": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "facl_augment_views": (_I, [C.POINTER(AugmentArgs), _P]),
     "facl_packed_weight_bytes": (_SZ, [_I, _I]),
     "facl_pack_weight": (_I, [_P, _LL, _LL, _I, _I, _P, _P]),

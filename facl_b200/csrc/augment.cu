@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(THREADS) augment_kernel(const AugmentParams p)
                 }
             }
         }
-        const double sg = (double)p.sigma, cl = (double)p.clip;
+        const double sg = p.sigma, cl = p.clip;
         if (rc.jitter) {
             x = jit(x, z0[0], sg, cl);
             y = jit(y, z0[1], sg, cl);

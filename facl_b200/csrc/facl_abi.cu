@@ -26,6 +26,16 @@ int facl_group_points(const float* points, int M, int N, int D, int Sc, int K, f
     return group_launch(points, M, N, D, Sc, K, r2, xt, idx, S(stream));
 }
 
+int facl_l2_normalize(const float* x, int rows, int C, float* out, void* stream) {
+    if (!x || !out || rows <= 0 || C <= 0) return (int)cudaErrorInvalidValue;
+    return l2_normalize_launch(x, rows, C, out, S(stream));
+}
+
+int facl_softmax_xent(const float* logits, const int* labels, int rows, int C, float* loss, float* dlogits_t, float* dbias, int* hits,
+                      void* stream) {
+    return softmax_xent_launch(logits, labels, rows, C, loss, dlogits_t, dbias, hits, S(stream));
+}
+
 size_t facl_group_level2_scratch_bytes(int M, int N1, int S2, int K) { return group_level2_scratch_bytes(M, N1, S2, K); }
 
 int facl_group_level2(const float* feats, int M, int C, int N1, int S2, int K, float r2, float* out, int* idx, void* scratch,

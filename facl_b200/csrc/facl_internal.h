@@ -86,7 +86,7 @@ struct AugmentRecipe {
 };
 struct AugmentParams {
     int B, G, N, n_sources, g_major;
-    float sigma, clip;
+    double sigma, clip;
     AugmentSource source[AUGMENT_MAX_SOURCES];
     AugmentRecipe recipe[AUGMENT_MAX_VIEWS];
     const int* idx;          // explicit draws (all three or none) ...
@@ -97,6 +97,9 @@ struct AugmentParams {
     int* out_rows;
 };
 int augment_launch(const AugmentParams& p, int max_rows, cudaStream_t st);
+// probe.cu
+int softmax_xent_launch(const float* logits, const int* labels, int rows, int C, float* loss, float* dlogits_t, float* dbias, int* hits,
+                        cudaStream_t st);
 // group2.cu
 size_t group_level2_scratch_bytes(int M, int N1, int S2, int K);
 int group_level2_launch(const float* feats, int M, int C, int N1, int S2, int K, float r2, float* out, int* idx, void* scratch,

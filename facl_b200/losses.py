@@ -84,14 +84,43 @@ def contrast_losses(x, x_global, num_crop, batch_size, order=None, want_global=T
                                       bool(want_global), bool(want_circle), nsplit)
 
 
+class _SimilarityFunction(torch.autograd.Function):
+    """sims = x @ x.T on the tcgen05 GEMM (bf16x3 split, fp32 accumulation), differentiable."""
+
+    @staticmethod
+    def forward(ctx, x):
+        from . import ops
+        x = x.contiguous()
+        R, Cd = x.shape
+        out = torch.empty((R, R), dtype=torch.float32, device=x.device)
+        ops.gemm_tc(R, R, Cd, nsplit=3, a=dict(src0=x, ld=Cd), b_mode=ops.B_ROWMAJOR, b=dict(src0=x, ld=Cd),
+                    out_mode=ops.OUT_CHMAJOR, out=out, ldo=R)
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dsims):
+        from . import ops
+        (x,) = ctx.saved_tensors
+        R, Cd = x.shape
+        dsym = (dsims + dsims.t()).contiguous()
+        dx = torch.empty_like(x)
+        ops.gemm_tc(R, Cd, R, nsplit=3, a=dict(src0=dsym, ld=R), b_mode=ops.B_CHMAJOR, b=dict(src0=x, ld=Cd),
+                    out_mode=ops.OUT_CHMAJOR, out=dx, ldo=Cd)
+        return dx
+
+
 def info_nce_logits_cuda(x, batch_size):
-    """Two-view logits of reference utils_my.py:200-213 (not on the live path; plain tensor algebra on the GPU)."""
+    """Two-view logits of reference utils_my.py:200-213 (not on the live path): the similarity
+    GEMM (and its gradient) run on libfacl_b200's tensor-core kernel, the masking / concatenation is tensor plumbing."""
     _lib.require_cuda(x, "x")
     B = batch_size
+    if x.shape[0] != 2 * B:
+        raise _lib.FaclError(f"Info_NCE expects the two views of {B} samples, got {x.shape[0]} rows")   # :209-210 need (B, 2B)
     n = torch.arange(B, device=x.device)[:, None]
     j = torch.arange(2 * B, device=x.device)[None, :]
     mask = ((j % B) != n).to(x.dtype)
-    a, b = x[0:B], x[B:2 * B]
-    pos = (a * b).sum(dim=1, keepdim=True)
-    logits = torch.cat([pos, (a @ x.t()) * mask, (b @ x.t()) * mask], dim=1)
+    sims = _SimilarityFunction.apply(x)
+    pos = (x[0:B] * x[B:2 * B]).sum(dim=1, keepdim=True)
+    logits = torch.cat([pos, sims[0:B] * mask, sims[B:2 * B] * mask], dim=1)
     return logits, torch.zeros(B, dtype=torch.long, device=x.device)

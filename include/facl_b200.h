@@ -96,7 +96,7 @@ typedef struct {
     int n_sources;
     const facl_point_source* sources;   /* host array [n_sources], <= 8 */
     const facl_view_recipe* recipes;    /* host array [G], G <= 32 */
-    float sigma, clip;                  /* reference: 0.01, 0.05 */
+    double sigma, clip;                 /* reference: 0.01, 0.05 (f64 like numpy's arithmetic) */
     const int* idx;
     const double* noise;
     const double* angle_u;
@@ -314,6 +314,18 @@ typedef struct facl_train_step_args {
 
 FACL_API int facl_gmajor(const float* points_bgnd, float* clouds, int B, int G, int N, void* stream);
 FACL_API int facl_train_step(const facl_train_step_args* args, void* stream);
+
+/* ---- linear probe on the extracted features -------------------------------------------
+ * replaces the non-GEMM parts of Final_FC (reference linear_classify/fc_model.py:12-25: F.normalize(x, p=2, dim=1)
+ * then nn.Linear) and of the loop in linear_classify/linercls.py:106-124 (CrossEntropyLoss, top-1 accuracy); the
+ * logits and weight-gradient GEMMs go through facl_gemm_tc.
+ * facl_l2_normalize: out[r] = x[r] / max(|x[r]|_2, 1e-12), x and out (rows, C) fp32.
+ * facl_softmax_xent: logits (rows, C) fp32, labels (rows) int32.  Accumulates (memset first) the mean cross-entropy
+ * into *loss, d loss / d bias into dbias [C] and the number of top-1 hits into *hits; writes d loss / d logits
+ * TRANSPOSED into dlogits_t [C][rows] (the A operand of the weight-gradient GEMM).  Any output may be NULL. */
+FACL_API int facl_l2_normalize(const float* x, int rows, int C, float* out, void* stream);
+FACL_API int facl_softmax_xent(const float* logits, const int* labels, int rows, int C, float* loss, float* dlogits_t, float* dbias,
+                               int* hits, void* stream);
 
 /* ---- instrumentation: per-kernel device timing and launch counting (used by bench.py) ---------------------
  * facl_timing_enable(1): every tagged launch site is bracketed by CUDA events on its stream.

@@ -380,6 +380,69 @@ def gen_group2():
     np.savez_compressed(os.path.join(HERE, "group2.npz"), **out)
 
 
+def gen_probe():
+    """linear_classify: Final_FC (imported unmodified), the loop body of linercls.py:109-122 and its accuracy(),
+    plus save_single_feature of extract_motion_feature.py:217-221 (lifted; the script itself needs a GPU + dataset)."""
+    import importlib.util
+    import tempfile
+    from oracle import probe as oprobe
+    spec = importlib.util.spec_from_file_location("ref_fc_model", "/root/reference/linear_classify/fc_model.py")
+    fcm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fcm)
+    text = open("/root/reference/linear_classify/linercls.py").read().split("\n")
+    ns = {"torch": torch}
+    exec("\n".join(text[157:172]), ns)                       # accuracy(), :158-172
+    text = open(os.path.join(REF, "extract_motion_feature.py")).read().split("\n")
+    ns2 = {"np": np}
+    exec("\n".join(text[216:221]), ns2)                      # save_single_feature, :217-221
+    out = {}
+    # ---- feature files
+    rng = np.random.default_rng(5)
+    B, G = 3, 10
+    feat = rng.standard_normal(((G + 1) * B, 512)).astype(np.float32)
+    names = [f"S001C00{i}P001R001A00{i}" for i in range(B)]
+    with tempfile.TemporaryDirectory() as d:
+        ns2["save_single_feature"](feat, d + "/", names)
+        files = [open(os.path.join(d, n + ".npy"), "rb").read() for n in names]
+        rows = np.stack([np.load(os.path.join(d, n + ".npy")) for n in names])
+    assert np.array_equal(rows, oprobe.feature_rows(feat, G + 1))
+    out["feat"], out["feat_rows"] = feat, rows
+    out["file0"] = np.frombuffer(files[0], dtype=np.uint8)
+    # ---- probe training steps
+    torch.manual_seed(3)
+    net = fcm.Final_FC(input_dim=512, gost=2, num_class=20)         # 2 blocks / 20 classes instead of 22 / 120: small fixture
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    crit = torch.nn.CrossEntropyLoss()
+    optim = torch.optim.Adam(net.parameters(), lr=0.005, betas=(0.5, 0.999), eps=1e-06)
+    g = torch.Generator().manual_seed(9)
+    xs = torch.randn(3, 16, 2 * 512, generator=g) * torch.rand(3, 16, 1, generator=g) * 3
+    ys = torch.randint(0, 20, (3, 16), generator=g)
+    xs[0, 5] = 0                                                # F.normalize's eps branch
+    sd, state, losses, top1s = {k: v.clone() for k, v in sd0.items()}, {}, [], []
+    for it in range(3):
+        output = net(xs[it])
+        loss = crit(output, ys[it])
+        optim.zero_grad()
+        loss.backward()
+        if it == 0:
+            out["grad_w0"], out["grad_b0"] = net.fc.weight.grad.clone().numpy(), net.fc.bias.grad.clone().numpy()
+            out["logits0"] = output.detach().numpy()
+        optim.step()
+        acc1, _ = ns["accuracy"](output, ys[it], topk=(1, 1))
+        losses.append(float(loss.detach()))
+        top1s.append(float(acc1[0]))
+        o = oprobe.probe_step(sd, xs[it], ys[it], state)
+        assert abs(o["loss"] - float(loss)) <= 1e-5 and abs(o["top1"] - float(acc1[0])) < 1e-4, (o["loss"], float(loss))
+    for k in sd:
+        assert float((sd[k] - net.state_dict()[k]).abs().max()) <= 2e-6, k
+    out["x"], out["y"] = xs.numpy(), ys.numpy()
+    out["w0"], out["b0"] = sd0["fc.weight"].numpy(), sd0["fc.bias"].numpy()
+    out["w3"], out["b3"] = net.state_dict()["fc.weight"].numpy(), net.state_dict()["fc.bias"].numpy()
+    out["losses"], out["top1"] = np.array(losses), np.array(top1s)
+    print("probe:", losses, top1s)
+    np.savez_compressed(os.path.join(HERE, "probe.npz"), **out)
+
+
 def lift_reference_augment():
     """A stand-in object carrying the reference's own augmentation methods (source text exec'd at run time)."""
     text = open(os.path.join(REF, "cn3D_data_set.py")).read().split("\n")
@@ -439,6 +502,7 @@ if __name__ == "__main__":
         sys.exit(0)
     gen_augment()
     gen_group2()
+    gen_probe()
     gen_fps()
     gen_group()
     gen_losses()

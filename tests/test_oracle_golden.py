@@ -181,3 +181,23 @@ def test_level2_grouping_matches_reference(golden_dir):
         out, centre, idx = oracle.group_points_level2(feats, S2, K, float(z[f"{name}_r2"]))
         assert np.array_equal(_sorted_cols(out.numpy()), z[f"{name}_sorted"]), name
         assert torch.equal(centre[..., 0], feats[:, 0:3, 0:S2])
+
+
+def test_probe_and_feature_files_match_reference(golden_dir, tmp_path):
+    """Final_FC + CrossEntropy + Adam of linear_classify/, and save_single_feature's per-video file."""
+    from oracle import probe as oprobe
+    z = np.load(os.path.join(golden_dir, "probe.npz"))
+    rows = oprobe.feature_rows(z["feat"], 11)
+    assert np.array_equal(rows, z["feat_rows"])
+    np.save(tmp_path / "v.npy", rows[0])
+    assert np.array_equal(np.frombuffer(open(tmp_path / "v.npy", "rb").read(), dtype=np.uint8), z["file0"])
+    sd = {"fc.weight": torch.from_numpy(z["w0"]).clone(), "fc.bias": torch.from_numpy(z["b0"]).clone()}
+    state = {}
+    for it in range(3):
+        o = oprobe.probe_step(sd, torch.from_numpy(z["x"][it]), torch.from_numpy(z["y"][it]), state)
+        assert abs(o["loss"] - z["losses"][it]) <= 1e-5 and abs(o["top1"] - z["top1"][it]) < 1e-4
+        if it == 0:
+            assert np.abs(o["logits"].numpy() - z["logits0"]).max() <= 1e-6
+            assert np.abs(o["grads"]["fc.weight"].numpy() - z["grad_w0"]).max() <= 1e-7
+            assert np.abs(o["grads"]["fc.bias"].numpy() - z["grad_b0"]).max() <= 1e-7
+    assert np.abs(sd["fc.weight"].numpy() - z["w3"]).max() <= 2e-6 and np.abs(sd["fc.bias"].numpy() - z["b3"]).max() <= 2e-6
