@@ -87,52 +87,75 @@ __device__ __forceinline__ double lse3(double pos, double m, double e, double nz
     return mx + log(s);
 }
 
-// single block; thread per LOCAL sample b.  Produces loss[0] = global, loss[1] = circle (this rank's anchors, already
-// divided by the global B) and the softmax coefficients:
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+
+// single block of 16 warps; warp per LOCAL sample b, lanes over the views (the f64 exp / log chain per (b, view) is the
+// cost: spread over lanes it is ~10x shorter than a thread per sample).  Produces loss[0] = global, loss[1] = circle
+// (this rank's anchors, already divided by the global B) and the softmax coefficients:
 //   lcG[b] = log sum_g exp(-LSE_g,n)      pgG[b*G+g] = (exp(pos - LSE) - 1)/B       (global)
 //   lcC[b] = log sum_i exp(-LSE_i,n)      pgC[b*G+i] = (exp(pos - LSE) - 1)/B       (circle, i < G-1)
-__global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ Smat, Idx ix, const int* __restrict__ order,
-                                                            const float* __restrict__ rmax, const float* __restrict__ rsum,
-                                                            int want_global, int want_circle, float* __restrict__ loss,
-                                                            float* __restrict__ lcG, float* __restrict__ pgG,
-                                                            float* __restrict__ lcC, float* __restrict__ pgC) {
+constexpr int LF_THREADS = 512;
+__global__ void __launch_bounds__(LF_THREADS) loss_finalize_kernel(const float* __restrict__ Smat, Idx ix, const int* __restrict__ order,
+                                                                   const float* __restrict__ rmax, const float* __restrict__ rsum,
+                                                                   int want_global, int want_circle, float* __restrict__ loss,
+                                                                   float* __restrict__ lcG, float* __restrict__ pgG,
+                                                                   float* __restrict__ lcC, float* __restrict__ pgC) {
     const int G = ix.G, B = ix.B;
     const long long ld = ix.Mk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double accG = 0.0, accC = 0.0;
-    for (int b = threadIdx.x; b < ix.Bl; b += 256) {
+    for (int b = warp; b < ix.Bl; b += LF_THREADS / 32) {
         const int n = ix.n0 + b;
         if (want_global) {
-            int a = ix.Ml + b;
-            double m = rmax[a], e = rsum[a];
+            const int a = ix.Ml + b;
+            const double m = rmax[a], e = rsum[a];
             double minL = 1e300;
-            for (int g = 0; g < G; ++g) {
+            for (int g = lane; g < G; g += 32) {
                 double pos = Smat[(long long)a * ld + ix.key_of(g, n)];
                 double L = lse3(pos, m, e, (double)G);
                 accG += L - pos;
                 pgG[b * G + g] = (float)((exp(pos - L) - 1.0) / B);
                 minL = fmin(minL, L);
             }
+            minL = warp_min_d(minL);
             double s = 0.0;
-            for (int g = 0; g < G; ++g) {
+            for (int g = lane; g < G; g += 32) {
                 double pos = Smat[(long long)a * ld + ix.key_of(g, n)];
                 s += exp(minL - lse3(pos, m, e, (double)G));
             }
-            lcG[b] = (float)(-minL + log(s));
+            s = warp_sum_d(s);
+            if (lane == 0) lcG[b] = (float)(-minL + log(s));
         }
         if (want_circle) {
             double mx = -INFINITY;
-            for (int i = 0; i < G - 1; ++i) {
+            for (int i = lane; i < G - 1; i += 32) {
                 int a = order[i] * ix.Bl + b;
                 if (rsum[a] > 0.f) mx = fmax(mx, (double)rmax[a]);
             }
+            mx = warp_max_d(mx);
             double e = 0.0;
-            for (int i = 0; i < G - 1; ++i) {
+            for (int i = lane; i < G - 1; i += 32) {
                 int a = order[i] * ix.Bl + b;
                 if (rsum[a] > 0.f) e += (double)rsum[a] * exp((double)rmax[a] - mx);
             }
-            double nzero = (double)(G - 1) * G;
+            e = warp_sum_d(e);
+            const double nzero = (double)(G - 1) * G;
             double minL = 1e300;
-            for (int i = 0; i < G - 1; ++i) {
+            for (int i = lane; i < G - 1; i += 32) {
                 int a = order[i] * ix.Bl + b;
                 double pos = Smat[(long long)a * ld + ix.key_of(order[i + 1], n)];
                 double L = lse3(pos, mx, e, nzero);
@@ -140,29 +163,31 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restr
                 pgC[b * G + i] = (float)((exp(pos - L) - 1.0) / B);
                 minL = fmin(minL, L);
             }
+            minL = warp_min_d(minL);
             double s = 0.0;
-            for (int i = 0; i < G - 1; ++i) {
+            for (int i = lane; i < G - 1; i += 32) {
                 int a = order[i] * ix.Bl + b;
                 double pos = Smat[(long long)a * ld + ix.key_of(order[i + 1], n)];
                 s += exp(minL - lse3(pos, mx, e, nzero));
             }
-            lcC[b] = (G > 1) ? (float)(-minL + log(s)) : -INFINITY;
+            s = warp_sum_d(s);
+            if (lane == 0) lcC[b] = (G > 1) ? (float)(-minL + log(s)) : -INFINITY;
         }
     }
-    __shared__ double sh[2][256];
-    sh[0][threadIdx.x] = accG;
-    sh[1][threadIdx.x] = accC;
+    __shared__ double sh[2][LF_THREADS / 32];
+    accG = warp_sum_d(accG);
+    accC = warp_sum_d(accC);
+    if (lane == 0) {
+        sh[0][warp] = accG;
+        sh[1][warp] = accC;
+    }
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) {
-            sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
-            sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    if (warp == 0) {
+        double g = warp_sum_d(lane < LF_THREADS / 32 ? sh[0][lane] : 0.0), c = warp_sum_d(lane < LF_THREADS / 32 ? sh[1][lane] : 0.0);
+        if (lane == 0) {
+            loss[0] = want_global ? (float)(g / B) : 0.f;
+            loss[1] = want_circle ? (float)(c / B) : 0.f;
         }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        loss[0] = want_global ? (float)(sh[0][0] / B) : 0.f;
-        loss[1] = want_circle ? (float)(sh[1][0] / B) : 0.f;
     }
 }
 
@@ -315,7 +340,7 @@ int contrast_losses(const float* x, const float* xg, const float* keys, int G, i
         RUN(sim(image(w.im_xg, Bl, C), Bl, Sg));
         loss_rowstats_kernel<<<Bl, 128, 0, st>>>(w.S, ix, Ml, Bl, w.rmax, w.rsum);
     }
-    loss_finalize_kernel<<<1, 256, 0, st>>>(w.S, ix, order, w.rmax, w.rsum, want_global, want_circle, loss, w.lcG, w.pgG, w.lcC,
+    loss_finalize_kernel<<<1, LF_THREADS, 0, st>>>(w.S, ix, order, w.rmax, w.rsum, want_global, want_circle, loss, w.lcG, w.pgG, w.lcC,
                                             w.pgC);
     FACL_CHECK_LAUNCH();
     // feature matrices as packed A operands: A[m = c][k = row] = feat[row][c]

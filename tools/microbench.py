@@ -43,11 +43,16 @@ def clouds(V, N, seed):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated subset of: fps,group,augment,group2,probe,extract")
     args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+
+    def want(name):
+        return not only or name in only
     V = 256 if args.quick else 1280
     dev = torch.device("cuda")
     # ---------------- FPS (K1) ----------------
-    for N in ([2048] if args.quick else [1024, 2048, 4096, 8192, 16384]):
+    for N in ([2048] if args.quick else [1024, 2048, 4096, 8192, 16384]) if want("fps") else []:
         pts = clouds(V, N, seed=N)
         start = torch.zeros(V, dtype=torch.int32, device=dev)
         for m in ([64] if args.quick else [64, 128, 512]):
@@ -61,7 +66,7 @@ def main():
     combos = [(2048, 64, 0.16)] if args.quick else \
         [(N, 64, 0.16) for N in (1024, 2048, 4096, 8192, 16384)] + [(2048, K, 0.16) for K in (16, 32, 128)] + \
         [(2048, 64, r2) for r2 in (0.0025, 0.01, 0.06)]
-    for N, K, r2 in combos:
+    for N, K, r2 in combos if want("group") else []:
         pts = clouds(V, N, seed=N + K)
         ms = timed(lambda: ops.group_points_raw(pts, S, K, r2, want_idx=False))
         rows, idx = ops.group_points_raw(pts[:2].contiguous(), S, K, r2)
@@ -72,7 +77,7 @@ def main():
     # ---------------- view augmentation ----------------
     from facl_b200 import cn3D_data_set as ds
     rng = np.random.default_rng(0)
-    for B, N, P in ([(64, 512, 2048)] if args.quick else [(64, 512, 2048), (64, 2048, 2048), (256, 2048, 4096)]):
+    for B, N, P in ([(64, 512, 2048)] if args.quick else [(64, 512, 2048), (64, 2048, 2048), (256, 2048, 4096)]) if want("augment") else []:
         srcs = []
         for s in range(4):
             a = rng.uniform(-0.5, 0.5, (B * P, 8)).astype(np.float32)
@@ -86,15 +91,26 @@ def main():
         print(json.dumps(dict(op="augment_views", B=B, G=G, N=N, P=P, rng="philox", ms=ms, sequences_per_s=B / ms * 1e3,
                               algorithmic_GBs=nbytes / ms / 1e6, hbm_frac=nbytes / ms / 1e6 / HBM)), flush=True)
     # ---------------- level-2 grouping ----------------
-    for M, C, S1, S2, K in ([(256, 131, 512, 128, 64)] if args.quick else [(1280, 131, 512, 128, 64), (1280, 259, 64, 64, 32)]):
+    for M, C, S1, S2, K in ([(256, 131, 512, 128, 64)] if args.quick else [(1280, 131, 512, 128, 64), (1280, 259, 64, 64, 32)]) if want("group2") else []:
         feats = torch.randn(M, C, S1, device=dev)
         feats[:, :3] = torch.rand(M, 3, S1, device=dev) - 0.5
         ms = timed(lambda: ops.group_level2(feats, S2, K, 0.02), iters=5)
         nbytes = M * (4 * C * S1 + 4 * C * S2 * K)
         print(json.dumps(dict(op="group_level2", M=M, C=C, S1=S1, S2=S2, K=K, ms=ms, us_per_cloud=ms * 1e3 / M,
                               algorithmic_GBs=nbytes / ms / 1e6, hbm_frac=nbytes / ms / 1e6 / HBM)), flush=True)
+    # ---------------- linear probe step ----------------
+    if want("probe"):
+        from facl_b200 import linercls
+        for rows in ([64] if args.quick else [64, 1024]):
+            tr = linercls.ProbeTrainer()
+            x = torch.randn(rows, 22 * 512, device=dev)
+            y = torch.randint(0, 120, (rows,), device=dev)
+            ms = timed(lambda: tr.step(x, y), iters=20)
+            flops = 2 * 2 * rows * 22 * 512 * 120
+            print(json.dumps(dict(op="probe_step", rows=rows, features=22 * 512, classes=120, ms=ms, samples_per_s=rows / ms * 1e3,
+                                  algorithmic_TFLOPs=flops / ms / 1e9, loss=tr.pop_meters()[0] / 23)), flush=True)
     # ---------------- forward-only feature extraction (configs[4]) ----------------
-    for G in ([10] if args.quick else [10, 20]):
+    for G in ([10] if args.quick else [10, 20]) if want("extract") else []:
         B, N = 64, 2048
         opt = default_opt(batchSize=B, SAMPLE_NUM=N)
         tr = TrainStep(opt, num_crop=G, precision="fp32", radius2=0.16)
