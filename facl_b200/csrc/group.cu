@@ -41,7 +41,9 @@ __device__ __forceinline__ void insert_smallest(float (&t)[T], float d) {
     }
 }
 
-template <bool D4, int T>
+// NPL > 0: the cloud is exactly NPL * 32 points (one resident tile); every lane keeps its NPL distances in registers, so
+// the second pass is a compare + ballot per point instead of a reload and a recomputation.  NPL == 0: any N.
+template <bool D4, int T, int NPL>
 __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict__ points, int N, int D, int S, int K, float r2,
                                                         float* __restrict__ xt, int* __restrict__ idx_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -97,13 +99,26 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
     float tsm[T];
 #pragma unroll
     for (int q = 0; q < T; ++q) tsm[q] = INFINITY;
-    for (int t = 0; t < ntiles; ++t) {
-        if (t > 0) __syncthreads();           // everyone is done with the previous tile
-        const int cnt = load_tile(t);
+    float dreg[NPL > 0 ? NPL : 1];
+    if constexpr (NPL > 0) {
+        load_tile(0);
         if (active) {
-            for (int i = lane; i < cnt; i += 32) {
-                float4 p = tile[i];
-                insert_smallest<T>(tsm, sqdist_ref(p.x, p.y, p.z, cx, cy, cz));
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+                float4 p = tile[q * 32 + lane];
+                dreg[q] = sqdist_ref(p.x, p.y, p.z, cx, cy, cz);
+                insert_smallest<T>(tsm, dreg[q]);
+            }
+        }
+    } else {
+        for (int t = 0; t < ntiles; ++t) {
+            if (t > 0) __syncthreads();           // everyone is done with the previous tile
+            const int cnt = load_tile(t);
+            if (active) {
+                for (int i = lane; i < cnt; i += 32) {
+                    float4 p = tile[i];
+                    insert_smallest<T>(tsm, sqdist_ref(p.x, p.y, p.z, cx, cy, cz));
+                }
             }
         }
     }
@@ -127,32 +142,49 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
 
     // ---------------- pass 2: compact candidates with d <= tau ----------------
     int count = 0;
-    for (int t = 0; t < ntiles; ++t) {
-        int cnt;
-        if (ntiles > 1) {
-            __syncthreads();
-            cnt = load_tile(t);
-        } else {
-            cnt = N;                           // single tile: still resident
-        }
+    if constexpr (NPL > 0) {
         if (active) {
-            const int n0 = t * TILE_PTS;
-            for (int i0 = 0; i0 < cnt; i0 += 32) {
-                int i = i0 + lane;
-                bool take = false;
-                float d = 0.f;
-                if (i < cnt) {
-                    float4 p = tile[i];
-                    d = sqdist_ref(p.x, p.y, p.z, cx, cy, cz);
-                    take = d <= tau;
-                }
-                unsigned bal = __ballot_sync(0xFFFFFFFFu, take);
-                if (bal == 0u) continue;               // ~96 % of the 32-point rows hold no candidate
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+                const float d = dreg[q];
+                const bool take = d <= tau;
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, take);
+                if (bal == 0u) continue;
                 if (take) {
                     int pos = count + __popc(bal & ((1u << lane) - 1u));
-                    if (pos < CAP) cand[pos] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(n0 + i);
+                    if (pos < CAP) cand[pos] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(q * 32 + lane);
                 }
                 count += __popc(bal);
+            }
+        }
+    } else {
+        for (int t = 0; t < ntiles; ++t) {
+            int cnt;
+            if (ntiles > 1) {
+                __syncthreads();
+                cnt = load_tile(t);
+            } else {
+                cnt = N;                           // single tile: still resident
+            }
+            if (active) {
+                const int n0 = t * TILE_PTS;
+                for (int i0 = 0; i0 < cnt; i0 += 32) {
+                    int i = i0 + lane;
+                    bool take = false;
+                    float d = 0.f;
+                    if (i < cnt) {
+                        float4 p = tile[i];
+                        d = sqdist_ref(p.x, p.y, p.z, cx, cy, cz);
+                        take = d <= tau;
+                    }
+                    unsigned bal = __ballot_sync(0xFFFFFFFFu, take);
+                    if (bal == 0u) continue;               // ~96 % of the 32-point rows hold no candidate
+                    if (take) {
+                        int pos = count + __popc(bal & ((1u << lane) - 1u));
+                        if (pos < CAP) cand[pos] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(n0 + i);
+                    }
+                    count += __popc(bal);
+                }
             }
         }
     }
@@ -240,10 +272,12 @@ int group_launch(const float* points, int M, int N, int D, int S, int K, float r
     if (!configured) {
         const int max_smem = TILE_PTS * 16 + GW * CAP * 8;
 #define FACL_GROUP_ATTR(TT)                                                                                              \
-        FACL_CHECK(cudaFuncSetAttribute(group_kernel<true, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));   \
-        FACL_CHECK(cudaFuncSetAttribute(group_kernel<false, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        FACL_CHECK(cudaFuncSetAttribute(group_kernel<true, TT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));   \
+        FACL_CHECK(cudaFuncSetAttribute(group_kernel<false, TT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         FACL_GROUP_ATTR(2) FACL_GROUP_ATTR(3) FACL_GROUP_ATTR(4) FACL_GROUP_ATTR(5)
 #undef FACL_GROUP_ATTR
+        FACL_CHECK(cudaFuncSetAttribute(group_kernel<true, 3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        FACL_CHECK(cudaFuncSetAttribute(group_kernel<true, 3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         configured = true;
     }
     dim3 grid((S + GW - 1) / GW, M);
@@ -253,9 +287,15 @@ int group_launch(const float* points, int M, int N, int D, int S, int K, float r
     const int T = (K + 31) / 32 + 1;           // smallest distances tracked per lane in pass 1
 #define FACL_GROUP_LAUNCH(TT)                                                                                     \
     do {                                                                                                          \
-        if (d4) group_kernel<true, TT><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);         \
-        else group_kernel<false, TT><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);           \
+        if (d4) group_kernel<true, TT, 0><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);      \
+        else group_kernel<false, TT, 0><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);        \
     } while (0)
+    // the training shapes (K = 64; N = 2048 or 1024): distances stay in registers between the two passes
+    if (d4 && T == 3 && (N == 2048 || N == 1024)) {
+        if (N == 2048) group_kernel<true, 3, 64><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);
+        else group_kernel<true, 3, 32><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);
+        return (int)cudaGetLastError();
+    }
     switch (T) {
         case 2: FACL_GROUP_LAUNCH(2); break;
         case 3: FACL_GROUP_LAUNCH(3); break;

@@ -68,7 +68,8 @@ def test_group_golden(golden_dir):
 @pytest.mark.parametrize("N,S,K,r2,resample", [(2048, 64, 64, 0.16, False), (2048, 64, 64, 0.0025, False),
                                                (1024, 128, 32, 0.06, True), (8192, 64, 128, 0.01, False),
                                                (5000, 64, 16, 0.06, False), (200, 64, 64, 0.06, True),
-                                               (16384, 64, 64, 0.16, False), (4096, 64, 64, 0.01, False)])
+                                               (16384, 64, 64, 0.16, False), (4096, 64, 64, 0.01, False),
+                                               (1024, 64, 64, 0.06, False), (2048, 50, 64, 0.06, True)])
 def test_group_vs_oracle(N, S, K, r2, resample):
     M = 4
     pts = synth.make_sequences(M, 1, N, seed=N + K, skeleton=True, resample=resample)[:, 0]

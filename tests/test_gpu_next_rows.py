@@ -259,3 +259,43 @@ def test_info_nce_golden_and_gradient(golden_dir):
     torch.nn.functional.cross_entropy(logits, labels).backward()
     torch.nn.functional.cross_entropy(ol, olab).backward()
     assert float((xd.grad.cpu() - xo.grad).abs().max()) <= 1e-3 * float(xo.grad.abs().max())
+
+
+# ------------------------------------------------------------------------------------------- f1 -> the training step
+def test_augmented_views_feed_the_training_step():
+    """Loader-free pipeline: resident source clouds -> facl_augment_views -> facl_train_step; the loss equals the oracle's
+    step on the oracle's views (same recorded draws)."""
+    from facl_b200 import cn3d_model_conbag as MODELL
+    from facl_b200.train import FusedTrainStep, TrainStep
+    rng = np.random.default_rng(12)
+    B, G, N, S, K = 4, 10, 512, 64, 64
+
+    def cloud(n):
+        a = np.empty((n, 8), np.float32)
+        a[:, 0], a[:, 1], a[:, 2] = 0.45 * rng.uniform(-0.5, 0.5, n), rng.uniform(-0.5, 0.5, n), 0.3 * rng.uniform(-0.5, 0.5, n)
+        a[:, 3:] = rng.uniform(-0.5, 0.5, (n, 5))
+        a[rng.uniform(size=n) < 0.3, 4] = 0
+        a[rng.uniform(size=n) < 0.3, 7] = 0
+        return a
+    src_np = [[cloud(int(n)) for n in rng.integers(600, 2500, size=B)] for _ in range(4)]
+    draws_np = [oaug.record_draws(np.random.RandomState(100 + b), [src_np[s][b] for s in range(4)], N) for b in range(B)]
+    draws = ds.Draws(torch.from_numpy(np.stack([d.idx for d in draws_np])).to(DEV),
+                     torch.from_numpy(np.stack([d.noise for d in draws_np])).to(DEV),
+                     torch.from_numpy(np.stack([d.angle_u for d in draws_np])).to(DEV))
+    views = ds.ViewAugmenter(num_point=N).get_data_train([_ragged(s) for s in src_np], draws, g_major=False)      # (B,G,N,4)
+    oviews = np.stack([oaug.make_views([src_np[s][b] for s in range(4)], draws_np[b]) for b in range(B)])
+    assert np.abs(views.cpu().numpy() - oviews).max() <= 6e-8
+
+    sd0 = oracle.init_state_dict(seed=5)
+    opt = types.SimpleNamespace(temperal_num=3, knn_K=K, ball_radius=0.16, ball_radius2=0.25, sample_num_level1=S,
+                                sample_num_level2=64, INPUT_FEATURE_NUM=4, Num_Class=512, batchSize=B,
+                                pooling="concatenation", SAMPLE_NUM=N, learning_rate=0.0003)
+    net = MODELL.PointNet_Plus_fine(opt, gost=G, sample_num_level1=S, knn_K=K)
+    net.load_state_dict({k: v.clone() for k, v in sd0.items()})
+    step = FusedTrainStep(TrainStep(opt, num_crop=G, precision="fp32", model=net), B, G, N, r2=0.06)
+    order = np.arange(G)[::-1].copy()
+    loss = step.step(views, order=order)
+    torch.cuda.synchronize()
+    want = oracle.train_step({k: v.clone() for k, v in sd0.items()}, torch.from_numpy(oviews), order, S=S, K=K, r2=0.06,
+                             apply_update=False)
+    assert abs(float(loss[2]) - want["loss"]) <= 1e-3 * abs(want["loss"]), (float(loss[2]), want["loss"])
