@@ -273,15 +273,20 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
         const int grid = l1_fused_grid(R1);
         if (tr)
             RUN(l1_fwd_launch(false, xt, R1, K, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), p->layer[1].b, nullptr,
-                              nullptr, nullptr, nullptr, nullptr, stats, nullptr, nullptr, 0, st));
+                              nullptr, nullptr, nullptr, nullptr, 1, stats, nullptr, nullptr, nullptr, nullptr, 0, st));
         {
             const facl_layer& L = p->layer[1];
             RUN(bn_finalize_launch(stats, 2 * grid, 64, (double)R1, L.gamma, L.beta, L.running_mean, L.running_var, BN_EPS, BN_MOM,
                                    tr, s1.mean, s1.rstd, s1.scale, s1.shift, st));
         }
+        // training with the backward buffers present: pass B also accumulates H2 = sum h2 h2^T and s2 = sum h2 (tensor core), which
+        // the dense part of dW3 needs -- the backward then does not recompute them
+        float* l1s = (tr && bufs[B_L1S]) ? F(B_L1S) : nullptr;
+        if (l1s) FACL_CHECK(cudaMemsetAsync(l1s + L1S_H2, 0, sizeof(float) * (L1S_H1 - L1S_H2), st));
         RUN(l1_fwd_launch(true, xt, R1, K, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), p->layer[1].b, s1.scale,
-                          s1.shift, wp + wpack_offset(2), p->layer[2].b, p->layer[2].gamma, F(B_STATS), F(B_PCAT) + 3 * R3,
-                          tr ? U(B_ARG3) : nullptr, R3, st));
+                          s1.shift, wp + wpack_offset(2), p->layer[2].b, p->layer[2].gamma, tr ? 1 : 0, F(B_STATS),
+                          l1s ? l1s + L1S_H2 : nullptr, l1s ? l1s + L1S_S2 : nullptr, F(B_PCAT) + 3 * R3, tr ? U(B_ARG3) : nullptr, R3,
+                          st));
         {
             Slot s2 = bn_slot(bufs, 2);
             const facl_layer& L = p->layer[2];
@@ -581,11 +586,11 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
         const int P = 2 * l1_bwd_grid(R1);
         float* acc = F(B_L1S);
         uint8_t* imgs = reinterpret_cast<uint8_t*>(bufs[B_L1S]) + L1S_IMG_OFF;   // P3 | P2 | diag(e0) W2
-        FACL_CHECK(cudaMemsetAsync(acc, 0, sizeof(float) * L1S_ACC_END, st));
+        // H2 / s2 (acc + L1S_H2 .. L1S_H1) were accumulated by pass B of the forward on these buffers
+        FACL_CHECK(cudaMemsetAsync(acc + L1S_H1, 0, sizeof(float) * (L1S_ACC_END - L1S_H1), st));
         RUN(l1_prep_launch(L2.w, 256, s2.c1, L2.b, s2.c2, nullptr, imgs, acc + L1S_Q3, nullptr, st));
         RUN(l1_bwd_c_launch(xt, R1, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), L1.b, s1.scale, s1.shift,
-                            wp + wpack_offset(2), imgs, acc + L1S_Q3, U(B_ARG3), F(B_DP3), R3, s2.c0, bufs[B_DH2], gr->dw[2],
-                            acc + L1S_H2, acc + L1S_S2, stats, st));
+                            wp + wpack_offset(2), imgs, acc + L1S_Q3, U(B_ARG3), F(B_DP3), R3, s2.c0, bufs[B_DH2], gr->dw[2], stats, st));
         RUN(bwd_finalize(1, 1, 64, (int)R1, (double)R1, P, 0));
         RUN(l1_fin_launch(L2.w, 256, s2.c1, L2.b, s2.c2, acc + L1S_H2, acc + L1S_S2, nullptr, nullptr, gr->dw[2], 1, st));
         RUN(l1_prep_launch(L1.w, 64, s1.c1, L1.b, s1.c2, s1.c0, imgs + 32768, acc + L1S_Q2, imgs + 65536, st));

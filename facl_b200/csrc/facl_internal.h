@@ -124,8 +124,7 @@ int l1_fin_launch(const float* W, int C, const float* d, const float* bias, cons
 int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1,
                     const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
                     const void* w3_img, const void* p3_img, const float* q3, const unsigned char* arg, const float* dpooled,
-                    long long ldp, const float* c3_0, void* dh2, float* dw3, float* gram, float* hsum, float* stats,
-                    cudaStream_t st);
+                    long long ldp, const float* c3_0, void* dh2, float* dw3, float* stats, cudaStream_t st);
 int l1_bwd_d_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1,
                     const float* shift1, const void* e0w2_img, const void* p2_img, const float* q2, const void* dh2, float* dw2s,
                     float* gram, float* hsum, float* amat, float* stats, cudaStream_t st);
@@ -137,6 +136,6 @@ int l1_bn1_launch(const double* mom14, double n, const float* w1, const float* b
                   float* scale, float* shift, cudaStream_t st);
 int l1_fwd_launch(bool pass_b, const float* xt, long long R, int K, int nsplit, const float* w1, const float* b1, const float* scale1,
                   const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
-                  const void* w3_img, const float* b3, const float* gamma3, float* stats, float* pooled, unsigned char* pool_arg,
-                  long long ldp, cudaStream_t st);
+                  const void* w3_img, const float* b3, const float* gamma3, int stat_mode, float* stats, float* gram, float* hsum,
+                  float* pooled, unsigned char* pool_arg, long long ldp, cudaStream_t st);
 }  // namespace facl

@@ -49,6 +49,8 @@ struct L1Params {
     const float* b3;
     const float* gamma3;      // sign decides max vs min
     float* stats;             // pass A: [2*grid][64][2], pass B: [grid][256][2]
+    float* gram;              // pass B with GRAM: H2 += sum_r h2 h2^T [64][64], s2 += sum_r h2 [64] (atomics onto zeroed buffers)
+    float* hsum;
     float* pooled;            // pass B: [256][ldp]  selected pre-BN value per (channel, group)
     unsigned char* pool_arg;  // pass B: [256][ldp]  position of the winner inside its group (first hit), or null
     long long ldp;
@@ -59,33 +61,44 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // write 8 consecutive rows of one channel into an MN-major activation image (hi / hi+lo)
-__device__ __forceinline__ void store_act8(uint8_t* img, int nhl, int channel, int chunk, const float (&v)[8]) {
-    uint32_t off = mn_sw128_offset((uint32_t)channel, (uint32_t)chunk, ACT_LBO, ACT_SBO);
+// (lbo = distance between the 64-row blocks, lo_off = distance from a hi block to its lo block)
+__device__ __forceinline__ void store_act8(uint8_t* img, int nhl, int channel, int chunk, const float (&v)[8], uint32_t lbo = ACT_LBO,
+                                           uint32_t lo_off = ACT_BYTES) {
+    uint32_t off = mn_sw128_offset((uint32_t)channel, (uint32_t)chunk, lbo, ACT_SBO);
     if (nhl == 2) {
         uint4 h, l;
         split_bf16x8(v, h, l);
         *reinterpret_cast<uint4*>(img + off) = h;
-        *reinterpret_cast<uint4*>(img + ACT_BYTES + off) = l;
+        *reinterpret_cast<uint4*>(img + lo_off + off) = l;
     } else {
         *reinterpret_cast<uint4*>(img + off) = pack_bf16x8(v);
     }
 }
 
 // D[tmem] (+)= A (K-major weight image, 64-wide K) * B (MN-major activation image), all bf16 hi/lo combinations
-__device__ __forceinline__ void mma_weight_act(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_img, int nhl, uint32_t idesc) {
+__device__ __forceinline__ void mma_weight_act(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_img, int nhl, uint32_t idesc,
+                                               uint32_t lbo = ACT_LBO, uint32_t lo_off = ACT_BYTES) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
         const uint64_t ad = umma_desc_sw128(a_hi + ks * 32);
-        const uint64_t bd = umma_desc_mn_sw128(b_img + ks * 2 * ACT_SBO, ACT_LBO, ACT_SBO);
+        const uint64_t bd = umma_desc_mn_sw128(b_img + ks * 2 * ACT_SBO, lbo, ACT_SBO);
         umma_bf16_ss(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
         if (nhl == 2) {
-            umma_bf16_ss(d_tmem, ad, umma_desc_mn_sw128(b_img + ACT_BYTES + ks * 2 * ACT_SBO, ACT_LBO, ACT_SBO), idesc, 1u);
+            umma_bf16_ss(d_tmem, ad, umma_desc_mn_sw128(b_img + lo_off + ks * 2 * ACT_SBO, lbo, ACT_SBO), idesc, 1u);
             umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ks * 32), bd, idesc, 1u);
         }
     }
 }
 
-template <bool PASS_B>
+// STAT: 0 no statistics (eval), 1 per-channel sum / sum of squares of the layer output in the consumer threads.
+// GRAM (pass B, training with a backward to follow): H2 = sum h2 h2^T also accumulates on the tensor core and s2 = sum h2 in the
+// h2 producers -- the dense part of dW3 needs exactly these (see the backward below), and here the h2 tiles are already in
+// shared memory, so pass C does not have to spend tensor-pipe time on them.  (BN3 statistics are NOT derived from H2: the
+// closed form w^T (H2/n - m m^T) w amplifies the rounding of the long fp32 accumulation ~100x, measured 1e-3 on the gradients.)
+// pass B stage of h2: [block 0: hi 8 KB | lo 8 KB][block 1: hi | lo], so that a 64-row block is also a 128-row K-major A tile
+// [h2_hi ; h2_lo] (the stacked form of the Gram product).
+constexpr uint32_t H2_LBO = 16384, H2_LO = 8192;
+template <bool PASS_B, int STAT, bool GRAM>
 __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_kernel(const L1Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
@@ -100,8 +113,8 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
     uint8_t* xs = h2s + (PASS_B ? 2 * 2 * ACT_BYTES : 0);  // 2 stages x 128 rows x 16 B
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * TILE * 16);
     uint64_t *h1_full = bars, *h1_empty = bars + 2, *d2_full = bars + 4, *d2_empty = bars + 6, *h2_full = bars + 8,
-             *h2_empty = bars + 10, *d3_full = bars + 12, *d3_empty = bars + 14, *w_bar = bars + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+             *h2_empty = bars + 10, *d3_full = bars + 12, *d3_empty = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = p.R / TILE;
@@ -118,6 +131,7 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             mbar_init(&d3_empty[i], 4);
         }
         mbar_init(w_bar, 1);
+        mbar_init(fin_bar, 1);
         mbar_fence_init();
     }
     if (warp == 16) {
@@ -128,8 +142,10 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM columns: D2[b] at 128*b (b = 0,1); D3[half] at 256 + 128*half
+    // TMEM columns.  pass A: D2[b] at 128*b (b = 0,1).  pass B: D2 at 0 (single: its consumers copy it out at once), H2 Gram
+    // accumulator at 128..191 (lanes 0..63 h2_hi rows, 64..127 h2_lo rows), D3[half] at 256 + 128*half
     const uint32_t idesc = umma_idesc_bf16(128, TILE) | UMMA_B_MN_MAJOR;
+    const uint32_t idesc_kk = umma_idesc_bf16(128, 64);
 
     if (warp == 16) {
         // ======================= MMA issuer (one lane) =======================
@@ -150,9 +166,13 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             auto issue_mma2 = [&](int it) {
                 const int b = it & 1, u = (it >> 1) & 1;
                 mbar_wait(&h1_full[b], u);
-                mbar_wait(&d2_empty[b], u ^ 1);
+                if (PASS_B) {
+                    if (it > 0) mbar_wait(&d2_empty[(it - 1) & 1], ((it - 1) >> 1) & 1);      // the one D2 has been copied out
+                } else {
+                    mbar_wait(&d2_empty[b], u ^ 1);
+                }
                 tc_fence_after_sync();
-                mma_weight_act(tmem_base + 128 * b, w2_hi, w2_lo, smem_u32(h1s + b * 2 * ACT_BYTES), nhl, idesc);
+                mma_weight_act(tmem_base + (PASS_B ? 0 : 128 * b), w2_hi, w2_lo, smem_u32(h1s + b * 2 * ACT_BYTES), nhl, idesc);
                 umma_commit(&h1_empty[b]);
                 umma_commit(&d2_full[b]);
             };
@@ -168,12 +188,27 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                         mbar_wait(&d3_empty[h], (it & 1) ^ 1);
                         tc_fence_after_sync();
                         const uint32_t w3_hi = smem_u32(w3s + h * 32768);
-                        mma_weight_act(tmem_base + 256 + 128 * h, w3_hi, w3_hi + 16384, smem_u32(h2s + b * 2 * ACT_BYTES), nhl, idesc);
+                        mma_weight_act(tmem_base + 256 + 128 * h, w3_hi, w3_hi + 16384, smem_u32(h2s + b * 2 * ACT_BYTES), nhl, idesc,
+                                       H2_LBO, H2_LO);
                         umma_commit(&d3_full[h]);
+                    }
+                    if (GRAM) {
+                        // H2 += h2 h2^T, reduction over the tile's rows: per 64-row block one stacked A tile [hi ; lo] (.) hi, (.) lo
+#pragma unroll
+                        for (int blk = 0; blk < 2; ++blk) {
+                            const uint32_t hb = smem_u32(h2s + b * 2 * ACT_BYTES) + blk * H2_LBO;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t ad = umma_desc_sw128(hb + ks * 32);
+                                umma_bf16_ss(tmem_base + 128, ad, ad, idesc_kk, (it == 0 && blk == 0 && ks == 0) ? 0u : 1u);
+                                if (nhl == 2) umma_bf16_ss(tmem_base + 128, ad, umma_desc_sw128(hb + H2_LO + ks * 32), idesc_kk, 1u);
+                            }
+                        }
                     }
                     umma_commit(&h2_empty[b]);
                 }
             }
+            if (PASS_B && GRAM) umma_commit(fin_bar);
         }
     } else if (PASS_B ? (warp == 10 || warp == 11 || warp == 14 || warp == 15) : (warp < 8 || warp >= 17)) {
         // ======================= producers: x -> h1 = relu(bn1(W1 x + b1)), thread = (channel, row quarter) ===============
@@ -233,6 +268,17 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             printf("fwd pass_b=%d producer warp %d: tiles %d wait %lld compute %lld fence %lld (cycles per tile)\n", (int)PASS_B, pw, it,
                    prof_wait / it, prof_comp / it, prof_fence / it);
 #endif
+        if (PASS_B && GRAM && nhl == 2) {
+            // these warps sit on TMEM lanes 64..127: the h2_lo rows of the stacked Gram accumulator
+            mbar_wait(fin_bar, 0);
+            tc_fence_after_sync();
+            const int lg = warp & 1, colhalf = (warp >= 14) ? 1 : 0, j = lg * 32 + lane;
+            float a[32];
+            tmem_ld32(tmem_base + ((uint32_t)(64 + lg * 32) << 16) + (uint32_t)(128 + colhalf * 32), a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(p.gram + j * 64 + colhalf * 32 + i, a[i]);
+        }
     } else if (warp == 8 || warp == 9 || warp == 12 || warp == 13) {
         // ======================= z2 consumers, thread = channel j (lanes 0..63 of D2), two column halves =============
         const int lg = warp & 1;                  // warps 8,12 -> TMEM lanes 0..31; 9,13 -> 32..63   (warp % 4 == lg)
@@ -244,46 +290,69 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             a2 = __ldg(p.scale2 + j);
             c2 = fmaf(a2, b2, __ldg(p.shift2 + j));
         }
-        float s_acc = 0.f, q_acc = 0.f;
+        float s_acc = 0.f, q_acc = 0.f, hsum = 0.f;
         long long nrows = 0;
         int it = 0;
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
             mbar_wait(&d2_full[b], u);
             tc_fence_after_sync();
-            if (PASS_B) mbar_wait(&h2_empty[b], u ^ 1);
-            uint8_t* img = h2s + b * 2 * ACT_BYTES;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 * b + colhalf * 64 + q * 32), v);
+            if (PASS_B) {
+                // copy this thread's 64 rows out of the single D2 and hand it back before doing the arithmetic
+                float v[64];
+                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(colhalf * 64), *reinterpret_cast<float(*)[32]>(&v[0]));
+                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(colhalf * 64 + 32), *reinterpret_cast<float(*)[32]>(&v[32]));
                 tmem_ld_wait();
-                if (PASS_B) {
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d2_empty[b]);
+                mbar_wait(&h2_empty[b], u ^ 1);
+                uint8_t* img = h2s + b * 2 * ACT_BYTES;
 #pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8) {
-                        float h[8];
+                for (int g8 = 0; g8 < 8; ++g8) {
+                    float h[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) h[e] = fmaxf(fmaf(a2, v[g8 * 8 + e], c2), 0.f);
-                        store_act8(img, nhl, j, colhalf * 8 + q * 4 + g8, h);
+                    for (int e = 0; e < 8; ++e) {
+                        h[e] = fmaxf(fmaf(a2, v[g8 * 8 + e], c2), 0.f);
+                        if (GRAM) hsum += h[e];
                     }
-                } else {
+                    store_act8(img, nhl, j, colhalf * 8 + g8, h, H2_LBO, H2_LO);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&h2_full[b]);
+            } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        s_acc += v[i];
-                        q_acc = fmaf(v[i], v[i], q_acc);
+                for (int q = 0; q < 2; ++q) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 * b + colhalf * 64 + q * 32), v);
+                    tmem_ld_wait();
+                    if (STAT == 1) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            s_acc += v[i];
+                            q_acc = fmaf(v[i], v[i], q_acc);
+                        }
                     }
                 }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d2_empty[b]);
             }
             nrows += 64;
-            tc_fence_before_sync();
-            if (PASS_B) fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                if (PASS_B) mbar_arrive(&h2_full[b]);
-                mbar_arrive(&d2_empty[b]);
-            }
         }
-        if (!PASS_B) {
+        if (PASS_B && GRAM) {
+            atomicAdd(p.hsum + j, hsum);
+            // lanes 0..63 of the Gram accumulator: the h2_hi rows
+            mbar_wait(fin_bar, 0);
+            tc_fence_after_sync();
+            float a[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 + colhalf * 32), a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(p.gram + j * 64 + colhalf * 32 + i, a[i]);
+        }
+        if (!PASS_B && STAT == 1) {
             // statistics of z2 = acc + b2 from the sums of acc
             const float n = (float)nrows;
             float* st = p.stats + ((long long)(blockIdx.x * 2 + colhalf) * 64 + j) * 2;
@@ -314,8 +383,10 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                     if (K >= 32) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            s_acc += v[i];
-                            q_acc = fmaf(v[i], v[i], q_acc);
+                            if (STAT == 1) {
+                                s_acc += v[i];
+                                q_acc = fmaf(v[i], v[i], q_acc);
+                            }
                             const float sv = v[i] * sgn;
                             barg = (sv > best) ? (q * 32 + i) : barg;
                             best = fmaxf(best, sv);
@@ -330,8 +401,10 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            s_acc += v[i];
-                            q_acc = fmaf(v[i], v[i], q_acc);
+                            if (STAT == 1) {
+                                s_acc += v[i];
+                                q_acc = fmaf(v[i], v[i], q_acc);
+                            }
                             const float sv = v[i] * sgn;
                             barg = (sv > best) ? i : barg;
                             best = fmaxf(best, sv);
@@ -350,10 +423,12 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d3_empty[h]);
             }
-            const float n = (float)nrows;
-            float* st = p.stats + ((long long)blockIdx.x * 256 + c) * 2;
-            st[0] = fmaf(n, b3, s_acc);
-            st[1] = q_acc + 2.f * b3 * s_acc + n * b3 * b3;
+            if (STAT == 1) {
+                const float n = (float)nrows;
+                float* st = p.stats + ((long long)blockIdx.x * 256 + c) * 2;
+                st[0] = fmaf(n, b3, s_acc);
+                st[1] = q_acc + 2.f * b3 * s_acc + n * b3 * b3;
+            }
         }
     }
 
@@ -496,17 +571,17 @@ __device__ __forceinline__ float produce_h1_tile64(const float4* xtile, uint8_t*
 // --------------------------------------------------------------------------------------------------------------------
 // pass C   (22 warps)
 // warps 0-7         : Sp producers (thread = channel c): one bf16 hi/lo pair per tile; flush dW3s at the end
-// warps 8,9,12,13   : z2 -> h2 image (thread = channel j, TMEM lanes 0..63); flush H2 / s2 at the end
+// warps 8,9,12,13   : z2 -> h2 image (thread = channel j, TMEM lanes 0..63)
 // warps 10,11,14,15 : x -> h1 image producers
 // warps 16,17,20,21 : dh2 consumers (thread = channel j): + q3, ReLU2 mask, BN2-backward sums, image -> HBM
 // warp 18           : MMA issuer (warp 19 idles)
-// TMEM columns: D2[b] 0/64, DH2 128..255 ([hi | lo] column halves), DW3s[h] 256/320, H2 384
+// TMEM columns: D2[b] 0/64, DH2 128..255 ([hi | lo] column halves), DW3s[h] 256/320
+// (H2 = sum h2 h2^T and s2, which dW3 also needs, were accumulated by pass B of the forward)
 //
 // tcgen05.mma time on these narrow tiles is set by the operand bytes it pulls from shared memory (the 4 KB A tile above
 // all), not by the math, so the bf16x3 scheme is issued as TWO instructions per k-step instead of three: the B images
 // are stored [hi | lo], and one N = 128 instruction against A_hi yields A_hi B_hi (columns 0..63) and A_hi B_lo (columns
-// 64..127); A_lo B_hi is added onto columns 0..63.  A consumer thread adds its two column halves in registers.  H2, whose
-// rows are only ever summed, uses the stacked-A form instead (h2 stage = [hi | lo] rows, see pass D).
+// 64..127); A_lo B_hi is added onto columns 0..63.  A consumer thread adds its two column halves in registers.
 // --------------------------------------------------------------------------------------------------------------------
 constexpr int C_THREADS = 22 * 32;
 
@@ -628,13 +703,6 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 umma_commit(sp_empty);
                 mma_w_b2(tmem_base + 128, p3_hi, p3_lo, h2, 8192, false);                                       // dh2 += P3 h2
                 umma_commit(dh_full);
-                // H2 += h2 h2^T with the stage's [hi | lo] rows as one 128-row A tile: lanes 0..63 h2_hi (.), lanes 64..127 h2_lo (.)
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t ad = umma_desc_sw128(h2 + ks * 32);
-                    umma_bf16_ss(tmem_base + 384, ad, umma_desc_sw128(h2 + ks * 32), idesc_kk, (it == 0 && ks == 0) ? 0u : 1u);
-                    if (nhl == 2) umma_bf16_ss(tmem_base + 384, ad, umma_desc_sw128(h2 + IMG64 + ks * 32), idesc_kk, 1u);
-                }
                 umma_commit(&h2_empty[b]);
             }
             umma_commit(fin_bar);
@@ -670,23 +738,12 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 }
             }
         }
-        if (nhl == 2) {     // these warps sit on TMEM lanes 64..127: the h2_lo rows of the stacked H2 accumulator
-            mbar_wait(fin_bar, 0);
-            tc_fence_after_sync();
-            const int lg = warp & 1, colhalf = (warp >= 14) ? 1 : 0, j = lg * 32 + lane;
-            float a[32];
-            tmem_ld32(tmem_base + ((uint32_t)(64 + lg * 32) << 16) + (uint32_t)(384 + colhalf * 32), a);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(p.gram + j * 64 + colhalf * 32 + i, a[i]);
-        }
     } else if (warp == 8 || warp == 9 || warp == 12 || warp == 13) {
-        // ---- z2 -> h2 = relu(bn2(z2)) image (thread = channel j), s2 = sum h2 ----
+        // ---- z2 -> h2 = relu(bn2(z2)) image (thread = channel j) ----
         const int lg = warp & 1, colhalf = (warp >= 12) ? 1 : 0;
         const int j = lg * 32 + lane;
         const float a2 = __ldg(p.scale2 + j);
         const float c2 = fmaf(a2, __ldg(p.b2 + j), __ldg(p.shift2 + j));
-        float hsum = 0.f;
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
@@ -704,10 +761,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             for (int g8 = 0; g8 < 4; ++g8) {
                 float h[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    h[e] = fmaxf(fmaf(a2, z[g8 * 8 + e], c2), 0.f);
-                    hsum += h[e];
-                }
+                for (int e = 0; e < 8; ++e) h[e] = fmaxf(fmaf(a2, z[g8 * 8 + e], c2), 0.f);
                 store_img8(img, nhl, IMG64, j, colhalf * 4 + g8, h);
             }
             fence_proxy_async_smem();
@@ -718,14 +772,6 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                     p.dbg_mask2[((t0 + it) * 64 + j) * 64 + colhalf * 32 + i] = fmaf(a2, z[i], c2) > 0.f ? 1 : 0;
             }
         }
-        atomicAdd(p.hsum + j, hsum);
-        mbar_wait(fin_bar, 0);
-        tc_fence_after_sync();
-        float a[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(384 + colhalf * 32), a);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(p.gram + j * 64 + colhalf * 32 + i, a[i]);
     } else if (warp == 16 || warp == 17 || warp == 20 || warp == 21) {
         // ---- dh2 consumers (thread = channel j): + q3, ReLU2 mask, BN2 backward sums, masked gradient image -> HBM ----
         const int lg = warp & 1, colhalf = (warp >= 20) ? 1 : 0;
@@ -1279,16 +1325,22 @@ int l1_bn1_launch(const double* mom14, double n, const float* w1, const float* b
     return (int)cudaGetLastError();
 }
 
-// pass A: statistics of z2 -> stats [2*grid][64][2];  pass B: pooled [256][ldp] + statistics of z3 -> stats [grid][256][2]
+// pass A: statistics of z2 -> stats [2*grid][64][2];  pass B: pooled [256][ldp] (+ winners); stat_mode 1: statistics of z3 ->
+// stats [grid][256][2] (0: none, eval); gram / hsum non-null: H2 [64][64] and s2 [64] accumulated with atomics (zeroed by the caller)
 int l1_fwd_launch(bool pass_b, const float* xt, long long R, int K, int nsplit, const float* w1, const float* b1, const float* scale1,
                   const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
-                  const void* w3_img, const float* b3, const float* gamma3, float* stats, float* pooled, unsigned char* pool_arg,
-                  long long ldp, cudaStream_t st) {
+                  const void* w3_img, const float* b3, const float* gamma3, int stat_mode, float* stats, float* gram, float* hsum,
+                  float* pooled, unsigned char* pool_arg, long long ldp, cudaStream_t st) {
     if (R <= 0 || R % TILE != 0 || K <= 0 || (K & (K - 1)) || TILE % K != 0) return (int)cudaErrorInvalidValue;
+    if (stat_mode < 0 || stat_mode > 1 || (!pass_b && stat_mode != 1) || (stat_mode == 1 && !stats) || ((gram == nullptr) != (hsum == nullptr)) ||
+        (gram && (!pass_b || stat_mode != 1)))
+        return (int)cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
-        FACL_CHECK(cudaFuncSetAttribute(l1_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_smem_bytes(false)));
-        FACL_CHECK(cudaFuncSetAttribute(l1_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_smem_bytes(true)));
+        FACL_CHECK(cudaFuncSetAttribute(l1_fwd_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_smem_bytes(false)));
+        FACL_CHECK(cudaFuncSetAttribute(l1_fwd_kernel<true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_smem_bytes(true)));
+        FACL_CHECK(cudaFuncSetAttribute(l1_fwd_kernel<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_smem_bytes(true)));
+        FACL_CHECK(cudaFuncSetAttribute(l1_fwd_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_smem_bytes(true)));
         configured = true;
     }
     L1Params p;
@@ -1296,14 +1348,18 @@ int l1_fwd_launch(bool pass_b, const float* xt, long long R, int K, int nsplit, 
     p.w1 = w1; p.b1 = b1; p.scale1 = scale1; p.shift1 = shift1;
     p.w2_img = reinterpret_cast<const uint8_t*>(w2_img); p.b2 = b2; p.scale2 = scale2; p.shift2 = shift2;
     p.w3_img = reinterpret_cast<const uint8_t*>(w3_img); p.b3 = b3; p.gamma3 = gamma3;
-    p.stats = stats; p.pooled = pooled; p.pool_arg = pool_arg; p.ldp = ldp;
+    p.stats = stats; p.gram = gram; p.hsum = hsum; p.pooled = pooled; p.pool_arg = pool_arg; p.ldp = ldp;
     const int grid = l1_fused_grid(R);
     ScopedTimer timer(pass_b ? TAG_L1_PASS_B : TAG_L1_PASS_A, st);
     count_launch();
-    if (pass_b)
-        l1_fwd_kernel<true><<<grid, NTHREADS_B, l1_smem_bytes(true), st>>>(p);
+    if (!pass_b)
+        l1_fwd_kernel<false, 1, false><<<grid, NTHREADS_A, l1_smem_bytes(false), st>>>(p);
+    else if (stat_mode == 0)
+        l1_fwd_kernel<true, 0, false><<<grid, NTHREADS_B, l1_smem_bytes(true), st>>>(p);
+    else if (!gram)
+        l1_fwd_kernel<true, 1, false><<<grid, NTHREADS_B, l1_smem_bytes(true), st>>>(p);
     else
-        l1_fwd_kernel<false><<<grid, NTHREADS_A, l1_smem_bytes(false), st>>>(p);
+        l1_fwd_kernel<true, 1, true><<<grid, NTHREADS_B, l1_smem_bytes(true), st>>>(p);
     return (int)cudaGetLastError();
 }
 
@@ -1349,11 +1405,11 @@ int l1_fin_launch(const float* W, int C, const float* d, const float* bias, cons
     return (int)cudaGetLastError();
 }
 
-// pass C (K = 64): dw3 / gram / hsum are accumulated with atomics (zero-initialised by the caller); stats [2*grid][64][2]
+// pass C (K = 64): dw3 is accumulated with atomics (zero-initialised by the caller); stats [2*grid][64][2]
 int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1,
                     const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
                     const void* w3_img, const void* p3_img, const float* q3, const unsigned char* arg, const float* dpooled,
-                    long long ldp, const float* c3_0, void* dh2, float* dw3, float* gram, float* hsum, float* stats,
+                    long long ldp, const float* c3_0, void* dh2, float* dw3, float* stats,
                     cudaStream_t st) {
     if (R <= 0 || R % BT != 0 || ldp % 4 != 0) return (int)cudaErrorInvalidValue;
     static bool configured = false;
@@ -1366,7 +1422,7 @@ int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, c
     p.w2_img = reinterpret_cast<const uint8_t*>(w2_img); p.b2 = b2; p.scale2 = scale2; p.shift2 = shift2;
     p.w3_img = reinterpret_cast<const uint8_t*>(w3_img); p.p3_img = reinterpret_cast<const uint8_t*>(p3_img); p.q3 = q3;
     p.arg = arg; p.dpooled = dpooled; p.ldp = ldp; p.c3_0 = c3_0;
-    p.dh2 = reinterpret_cast<uint8_t*>(dh2); p.dw3 = dw3; p.gram = gram; p.hsum = hsum; p.stats = stats;
+    p.dh2 = reinterpret_cast<uint8_t*>(dh2); p.dw3 = dw3; p.gram = nullptr; p.hsum = nullptr; p.stats = stats;
     p.dbg_mask1 = g_dbg_mask1; p.dbg_mask2 = g_dbg_mask2;
     ScopedTimer timer(TAG_L1_PASS_C, st);
     count_launch();
