@@ -521,6 +521,38 @@ __device__ __forceinline__ void mma_w_act64(uint32_t d, uint32_t a_hi, uint32_t 
         }
     }
 }
+// A tiles in tensor memory.  tcgen05.mma on a 64-wide tile spends its time fetching the 4 KB A tile from shared memory (70
+// cycles per instruction against a 32-cycle math floor); the 64 x 64 weight matrices of the backward are constant for the whole
+// kernel, so they are copied ONCE into TMEM (32 columns per 128 x 64 bf16 tile; rows 64..127 zero) and the instructions that use
+// them read only their B tile from shared memory.
+// This warp's 32 lanes of one tile: `img` = K-major 128B-swizzled image (64 rows x 64 k) in shared memory, or nullptr for zeros.
+__device__ __forceinline__ void tmem_put_a_tile(uint32_t taddr, const uint8_t* img, int row) {
+    uint32_t u[32];
+    if (img) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 q = *reinterpret_cast<const uint4*>(img + sw128_offset((uint32_t)row, (uint32_t)c));
+            u[4 * c] = q.x; u[4 * c + 1] = q.y; u[4 * c + 2] = q.z; u[4 * c + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) u[c] = 0u;
+    }
+    tmem_st32(taddr, u);
+}
+// D (+)= A(TMEM tile, 64-wide K) * B(MN-major [64 ch][64 rows] image): the three bf16 hi/lo products, N = 64
+__device__ __forceinline__ void mma_t_act64(uint32_t d, uint32_t a_hi_t, uint32_t a_lo_t, uint32_t b_hi, uint32_t b_lo, int nhl,
+                                            uint32_t idesc, bool first) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t bd = umma_desc_mn_sw128(b_hi + ks * 2048, 8192, 1024);
+        umma_bf16_ts(d, a_hi_t + ks * 8, bd, idesc, (first && ks == 0) ? 0u : 1u);
+        if (nhl == 2) {
+            umma_bf16_ts(d, a_hi_t + ks * 8, umma_desc_mn_sw128(b_lo + ks * 2048, 8192, 1024), idesc, 1u);
+            umma_bf16_ts(d, a_lo_t + ks * 8, bd, idesc, 1u);
+        }
+    }
+}
 // D (+)= A(K-major image, rows = channels, K = 64 batch rows) * B(K-major image, K = 64 batch rows): reduction over rows
 __device__ __forceinline__ void mma_rows64(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int nhl,
                                            uint32_t idesc, bool first) {
@@ -575,7 +607,8 @@ __device__ __forceinline__ float produce_h1_tile64(const float4* xtile, uint8_t*
 // warps 10,11,14,15 : x -> h1 image producers
 // warps 16,17,20,21 : dh2 consumers (thread = channel j): + q3, ReLU2 mask, BN2-backward sums, image -> HBM
 // warp 18           : MMA issuer (warp 19 idles)
-// TMEM columns: D2[b] 0/64, DH2 128..255 ([hi | lo] column halves), DW3s[h] 256/320
+// TMEM columns: D2[b] 0/64, DH2 128..255 ([hi | lo] column halves), DW3s[h] 256/320, A tiles W2_hi / W2_lo / P3_hi / P3_lo at
+// 384 / 416 / 448 / 480
 // (H2 = sum h2 h2^T and s2, which dW3 also needs, were accumulated by pass B of the forward)
 //
 // tcgen05.mma time on these narrow tiles is set by the operand bytes it pulls from shared memory (the 4 KB A tile above
@@ -599,7 +632,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * BT * 16);
     uint64_t *h1_full = bars, *h1_empty = bars + 1, *d2_full = bars + 2, *d2_empty = bars + 4, *h2_full = bars + 6,
              *h2_empty = bars + 8, *sp_full = bars + 10, *sp_empty = bars + 11, *dh_full = bars + 12, *dh_empty = bars + 13,
-             *w_bar = bars + 16, *fin_bar = bars + 17;
+             *a_ready = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -622,6 +655,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         }
         mbar_init(sp_full, 8);
         mbar_init(sp_empty, 1);
+        mbar_init(a_ready, 4);
         mbar_init(w_bar, 1);
         mbar_init(fin_bar, 1);
         mbar_fence_init();
@@ -657,17 +691,19 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 if (nhl == 2) tma_bulk_g2s(w3s + h * 32768 + 16384, p.w3_img + h * 32768 + 16384, 16384, w_bar);
             }
             mbar_wait(w_bar, 0);
-            const uint32_t w2_hi = smem_u32(w2s), w2_lo = w2_hi + 8192;
-            const uint32_t p3_hi = smem_u32(p3s), p3_lo = p3_hi + 8192;
+            mbar_wait(a_ready, 0);                  // W2 / P3 A tiles are in tensor memory
+            tc_fence_after_sync();
+            const uint32_t w2_hi = tmem_base + 384, w2_lo = tmem_base + 416;
+            const uint32_t p3_hi = tmem_base + 448, p3_lo = tmem_base + 480;
             const uint32_t h1 = smem_u32(h1s);
             const uint32_t sp_hi = smem_u32(sps), sp_lo = sp_hi + 32768;
-            // D (+)= A B with B = [hi | lo] (MN-major, `b_lbo` bytes between the halves): A_hi x [B_hi | B_lo], then A_lo x B_hi
+            // D (+)= A B with A in TMEM and B = [hi | lo] (MN-major, `b_lbo` bytes between the halves): A_hi x [B_hi | B_lo], then A_lo x B_hi
             auto mma_w_b2 = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b, uint32_t b_lbo, bool first) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint64_t bd = umma_desc_mn_sw128(b + ks * 2048, b_lbo, 1024);
-                    umma_bf16_ss(d, umma_desc_sw128(a_hi + ks * 32), bd, idesc_mn2, (first && ks == 0) ? 0u : 1u);
-                    if (nhl == 2) umma_bf16_ss(d, umma_desc_sw128(a_lo + ks * 32), bd, idesc_mn, 1u);
+                    umma_bf16_ts(d, a_hi + ks * 8, bd, idesc_mn2, (first && ks == 0) ? 0u : 1u);
+                    if (nhl == 2) umma_bf16_ts(d, a_lo + ks * 8, bd, idesc_mn, 1u);
                 }
             };
             auto issue_z2 = [&](int it) {          // z2(it) = W2 h1(it): plain 3-term form, double-buffered accumulator
@@ -675,7 +711,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 mbar_wait(h1_full, it & 1);
                 mbar_wait(&d2_empty[b], u ^ 1);
                 tc_fence_after_sync();
-                mma_w_act64(tmem_base + 64 * b, w2_hi, w2_lo, h1, h1 + IMG64, nhl, idesc_mn, true);
+                mma_t_act64(tmem_base + 64 * b, w2_hi, w2_lo, h1, h1 + IMG64, nhl, idesc_mn, true);
                 umma_commit(h1_empty);
                 umma_commit(&d2_full[b]);
             };
@@ -709,6 +745,14 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         }
     } else if (warp == 10 || warp == 11 || warp == 14 || warp == 15) {
         // ---- x -> h1 producers ----
+        if (warp >= 14) {      // warps 14, 15 own TMEM lanes 64..127: the unused rows of the four A tiles are zero
+#pragma unroll 1
+            for (int tile = 0; tile < 4; ++tile) tmem_put_a_tile(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 384 + 32 * tile, nullptr, 0);
+            tmem_st_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+        }
         const int pw = (warp == 10) ? 0 : (warp == 11) ? 1 : (warp == 14) ? 2 : 3;
         const int ptid = pw * 32 + lane, ch = ptid & 63, half = ptid >> 6;
         const float s1 = __ldg(p.scale1 + ch), t1 = __ldg(p.shift1 + ch);
@@ -776,6 +820,19 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         // ---- dh2 consumers (thread = channel j): + q3, ReLU2 mask, BN2 backward sums, masked gradient image -> HBM ----
         const int lg = warp & 1, colhalf = (warp >= 20) ? 1 : 0;
         const int j = lg * 32 + lane;
+        if (warp < 18) {       // warps 16, 17 own TMEM lanes 0..63: rows of W2 (hi, lo) and P3 (hi, lo) -> A tiles at columns 384..511
+            mbar_wait(w_bar, 0);
+#pragma unroll 1
+            for (int tile = 0; tile < 4; ++tile) {
+                if (nhl == 1 && (tile & 1)) continue;
+                const uint8_t* img = (tile < 2 ? w2s : p3s) + (tile & 1) * 8192;
+                tmem_put_a_tile(tmem_base + ((uint32_t)(lg * 32) << 16) + 384 + 32 * tile, img, j);
+            }
+            tmem_st_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+        }
         const float b2 = __ldg(p.b2 + j), a2 = __ldg(p.scale2 + j);
         const float c2 = fmaf(a2, b2, __ldg(p.shift2 + j));
         const float q3 = __ldg(p.q3 + j);
