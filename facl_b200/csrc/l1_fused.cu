@@ -75,6 +75,38 @@ __device__ __forceinline__ void store_act8(uint8_t* img, int nhl, int channel, i
     }
 }
 
+// A tiles in tensor memory.  tcgen05.mma on a 64-wide tile spends its time fetching the 4 KB A tile from shared memory (70
+// cycles per instruction against a 32-cycle math floor); the 64 x 64 weight matrices of the backward are constant for the whole
+// kernel, so they are copied ONCE into TMEM (32 columns per 128 x 64 bf16 tile; rows 64..127 zero) and the instructions that use
+// them read only their B tile from shared memory.
+// This warp's 32 lanes of one tile: `img` = K-major 128B-swizzled image (64 rows x 64 k) in shared memory, or nullptr for zeros.
+__device__ __forceinline__ void tmem_put_a_tile(uint32_t taddr, const uint8_t* img, int row) {
+    uint32_t u[32];
+    if (img) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 q = *reinterpret_cast<const uint4*>(img + sw128_offset((uint32_t)row, (uint32_t)c));
+            u[4 * c] = q.x; u[4 * c + 1] = q.y; u[4 * c + 2] = q.z; u[4 * c + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) u[c] = 0u;
+    }
+    tmem_st32(taddr, u);
+}
+// D[tmem] (+)= A (TMEM tile, 64-wide K) * B (MN-major activation image), all bf16 hi/lo combinations
+__device__ __forceinline__ void mma_tmem_weight_act(uint32_t d_tmem, uint32_t a_hi_t, uint32_t a_lo_t, uint32_t b_img, int nhl,
+                                                    uint32_t idesc) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t bd = umma_desc_mn_sw128(b_img + ks * 2 * ACT_SBO, ACT_LBO, ACT_SBO);
+        umma_bf16_ts(d_tmem, a_hi_t + ks * 8, bd, idesc, ks > 0 ? 1u : 0u);
+        if (nhl == 2) {
+            umma_bf16_ts(d_tmem, a_hi_t + ks * 8, umma_desc_mn_sw128(b_img + ACT_BYTES + ks * 2 * ACT_SBO, ACT_LBO, ACT_SBO), idesc, 1u);
+            umma_bf16_ts(d_tmem, a_lo_t + ks * 8, bd, idesc, 1u);
+        }
+    }
+}
 // D[tmem] (+)= A (K-major weight image, 64-wide K) * B (MN-major activation image), all bf16 hi/lo combinations
 __device__ __forceinline__ void mma_weight_act(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_img, int nhl, uint32_t idesc,
                                                uint32_t lbo = ACT_LBO, uint32_t lo_off = ACT_BYTES) {
@@ -113,8 +145,9 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
     uint8_t* xs = h2s + (PASS_B ? 2 * 2 * ACT_BYTES : 0);  // 2 stages x 128 rows x 16 B
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * TILE * 16);
     uint64_t *h1_full = bars, *h1_empty = bars + 2, *d2_full = bars + 4, *d2_empty = bars + 6, *h2_full = bars + 8,
-             *h2_empty = bars + 10, *d3_full = bars + 12, *d3_empty = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+             *h2_empty = bars + 10, *d3_full = bars + 12, *d3_empty = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17,
+             *a_ready = bars + 18;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = p.R / TILE;
@@ -132,6 +165,7 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
         }
         mbar_init(w_bar, 1);
         mbar_init(fin_bar, 1);
+        mbar_init(a_ready, 4);
         mbar_fence_init();
     }
     if (warp == 16) {
@@ -142,10 +176,27 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM columns.  pass A: D2[b] at 128*b (b = 0,1).  pass B: D2 at 0 (single: its consumers copy it out at once), H2 Gram
-    // accumulator at 128..191 (lanes 0..63 h2_hi rows, 64..127 h2_lo rows), D3[half] at 256 + 128*half
+    // TMEM columns.  pass A: D2[b] at 128*b (b = 0,1), W2 A tiles (hi, lo) at 256 / 288.  pass B: D2 at 0 (single: its consumers
+    // copy it out at once), H2 Gram accumulator at 128..191 (lanes 0..63 h2_hi rows, 64..127 h2_lo rows), D3[half] at 256 + 128*half
     const uint32_t idesc = umma_idesc_bf16(128, TILE) | UMMA_B_MN_MAJOR;
     const uint32_t idesc_kk = umma_idesc_bf16(128, 64);
+    const uint32_t w2_t = tmem_base + 256;
+    // pass A: W2 is constant and becomes an A operand in tensor memory (see tmem_put_a_tile); warps 8, 9 own lanes 0..63, warps 10,
+    // 11 zero the unused lanes 64..127.  (Not in pass B: there the z3 consumers keep the TMEM read port busy, and A tiles read from
+    // TMEM made the pass 8 % slower, measured.)
+    constexpr bool W2_TMEM = !PASS_B;
+    if (W2_TMEM && warp >= 8 && warp < 12) {
+        if (warp < 10) mbar_wait(w_bar, 0);
+#pragma unroll 1
+        for (int tile = 0; tile < 2; ++tile) {
+            if (nhl == 1 && tile == 1) continue;
+            tmem_put_a_tile(w2_t + ((uint32_t)((warp & 3) * 32) << 16) + 32 * tile, warp < 10 ? w2s + tile * 8192 : nullptr, (warp & 1) * 32 + lane);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+    }
 
     if (warp == 16) {
         // ======================= MMA issuer (one lane) =======================
@@ -162,6 +213,10 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                 }
             }
             mbar_wait(w_bar, 0);
+            if (W2_TMEM) {
+                mbar_wait(a_ready, 0);
+                tc_fence_after_sync();
+            }
             const uint32_t w2_hi = smem_u32(w2s), w2_lo = w2_hi + 8192;
             auto issue_mma2 = [&](int it) {
                 const int b = it & 1, u = (it >> 1) & 1;
@@ -172,7 +227,10 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                     mbar_wait(&d2_empty[b], u ^ 1);
                 }
                 tc_fence_after_sync();
-                mma_weight_act(tmem_base + (PASS_B ? 0 : 128 * b), w2_hi, w2_lo, smem_u32(h1s + b * 2 * ACT_BYTES), nhl, idesc);
+                if (W2_TMEM)
+                    mma_tmem_weight_act(tmem_base + 128 * b, w2_t, w2_t + 32, smem_u32(h1s + b * 2 * ACT_BYTES), nhl, idesc);
+                else
+                    mma_weight_act(tmem_base, w2_hi, w2_lo, smem_u32(h1s + b * 2 * ACT_BYTES), nhl, idesc);
                 umma_commit(&h1_empty[b]);
                 umma_commit(&d2_full[b]);
             };
@@ -520,25 +578,6 @@ __device__ __forceinline__ void mma_w_act64(uint32_t d, uint32_t a_hi, uint32_t 
             umma_bf16_ss(d, umma_desc_sw128(a_lo + ks * 32), bd, idesc, 1u);
         }
     }
-}
-// A tiles in tensor memory.  tcgen05.mma on a 64-wide tile spends its time fetching the 4 KB A tile from shared memory (70
-// cycles per instruction against a 32-cycle math floor); the 64 x 64 weight matrices of the backward are constant for the whole
-// kernel, so they are copied ONCE into TMEM (32 columns per 128 x 64 bf16 tile; rows 64..127 zero) and the instructions that use
-// them read only their B tile from shared memory.
-// This warp's 32 lanes of one tile: `img` = K-major 128B-swizzled image (64 rows x 64 k) in shared memory, or nullptr for zeros.
-__device__ __forceinline__ void tmem_put_a_tile(uint32_t taddr, const uint8_t* img, int row) {
-    uint32_t u[32];
-    if (img) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 q = *reinterpret_cast<const uint4*>(img + sw128_offset((uint32_t)row, (uint32_t)c));
-            u[4 * c] = q.x; u[4 * c + 1] = q.y; u[4 * c + 2] = q.z; u[4 * c + 3] = q.w;
-        }
-    } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) u[c] = 0u;
-    }
-    tmem_st32(taddr, u);
 }
 // D (+)= A(TMEM tile, 64-wide K) * B(MN-major [64 ch][64 rows] image): the three bf16 hi/lo products, N = 64
 __device__ __forceinline__ void mma_t_act64(uint32_t d, uint32_t a_hi_t, uint32_t a_lo_t, uint32_t b_hi, uint32_t b_lo, int nhl,
