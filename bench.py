@@ -107,7 +107,7 @@ def run_reference(args):
 
 TAG_NAMES = {27: "group_kernel", 28: "fps", 29: "pack_weight", 30: "bn_finalize", 31: "pool_misc", 32: "pool_scatter",
              33: "loss_gemm", 34: "loss_misc", 35: "adam", 36: "transpose", 37: "memset", 38: "l1_misc", 39: "l1_pass_a",
-             40: "l1_pass_b", 41: "l1_pass_c", 42: "l1_pass_d", 43: "act_image"}
+             40: "l1_pass_b", 41: "l1_pass_c", 42: "l1_pass_d", 43: "act_image", 44: "augment_views", 45: "group_level2"}
 CIN = [4, 64, 64, 259, 256, 512, 1024, 1024, 512]
 COUT = [64, 64, 256, 256, 512, 1024, 1024, 512, 64]
 
