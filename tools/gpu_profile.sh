@@ -19,6 +19,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1; echo "ncu launch list rc=$?"
 timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:$KREGEX" -c 5 -f -o $OUT/${TAG}_hot \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_hot.log 2>&1; echo "ncu hot rc=$?"
-timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:gemm_tc_kernel" --launch-skip 21 --launch-count 21 -f -o $OUT/${TAG}_gemm \
+timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:gemm_img_kernel" --launch-skip 9 --launch-count 12 -f -o $OUT/${TAG}_gemm \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_gemm.log 2>&1; echo "ncu gemm rc=$?"
 ls -la $OUT | tail -12
