@@ -337,27 +337,20 @@ def test_fused_l1_training_forward(golden_dir, prec):
             assert int(v) == int(sd64[k])
 
 
-def test_fused_l1_backward(golden_dir):
-    """Gradients of the fused net3DV_1 path (activations recomputed in the backward, dW1 in closed form) against the
-    fp64 oracle under the SAME discrete decisions: the recomputing backward records its ReLU patterns and max-pool
-    winners through the facl_debug_l1_dump test hook."""
+def _check_fused_backward(pts, sd0, order, B, G, N, S, K, r2, tol):
     from facl_b200.debug import L1DecisionDump, routing_of_last_forward
-    z, sd0 = load_fixture(golden_dir)
-    B, G, N, S, K = (int(v) for v in z["cfg"])
-    pts = torch.from_numpy(z["points"])
     clouds = pts.permute(1, 0, 2, 3).reshape(-1, N, 4).to(DEV)
     net, opt = _build(sd0, B, G, N, S, K, "fp32")
     assert net.fused_l1
     net.train()
     xt, yt = utils_my.group_points_3DV(clouds, opt)
     x, code, x_nor, xg = net(xt, yt, 1)
-    lg, lc = facl_losses.contrast_losses(x, xg, G, B, order=z["order"], prec="fp32")
+    lg, lc = facl_losses.contrast_losses(x, xg, G, B, order=order, prec="fp32")
     with L1DecisionDump(G * B, S, K) as dump:
         (lg + lc).backward()
     routing = routing_of_last_forward(net, l1_dump=dump)
     sdr = {k: (v.clone().double() if v.dtype.is_floating_point else v.clone()) for k, v in sd0.items()}
-    ort = oracle.train_step(sdr, pts, z["order"], S=S, K=K, r2=float(z["r2"]), apply_update=False, dtype=torch.float64,
-                            routing=routing)
+    ort = oracle.train_step(sdr, pts, order, S=S, K=K, r2=r2, apply_update=False, dtype=torch.float64, routing=routing)
     assert rel2(x, ort["x"]) <= 1e-3 and abs(float(lg + lc) - ort["loss"]) <= 1e-3 * abs(ort["loss"])
     gscale = max(float(g.abs().max()) for g in ort["grads"].values())
     report = []
@@ -368,7 +361,79 @@ def test_fused_l1_backward(golden_dir):
         if float(ref.norm()) <= 1e-9 * gscale * ref.numel() ** 0.5:
             assert float(p.grad.abs().max()) <= 1e-4 * gscale, k
             continue
-        report.append((k, rel2(p.grad, ref)))
-    print("\n" + "\n".join(f"{k:24s} fused, matched decisions: err {a:.2e}" for k, a in report))
-    for k, a in report:
-        assert a <= TOL_GRAD["fp32"], (k, a)
+        rms_ref = float(ref.double().norm()) / ref.numel() ** 0.5
+        rms_err = float((p.grad.detach().double().cpu().reshape(-1) - ref.double().reshape(-1)).norm()) / ref.numel() ** 0.5
+        report.append((k, rel2(p.grad, ref), rms_ref / gscale, rms_err / gscale))
+    print("\n" + "\n".join(f"{k:24s} fused, matched decisions: err {a:.2e}  (rms/gscale: ref {r:.2e} err {e:.2e})" for k, a, r, e in report))
+    for k, a, r, e in report:
+        # A gradient that is structurally a near-zero residual (the BN beta in front of a layer whose own BatchNorm removes
+        # constants: its rms is 1e-5 of the largest gradient) is judged on its absolute error, which is the smallest of all.
+        assert a <= tol or e <= 1e-6, (k, a, r, e)
+
+
+def test_fused_l1_backward(golden_dir):
+    """Gradients of the fused net3DV_1 path (activations recomputed in the backward, dW1 in closed form) against the
+    fp64 oracle under the SAME discrete decisions: the recomputing backward records its ReLU patterns and max-pool
+    winners through the facl_debug_l1_dump test hook."""
+    z, sd0 = load_fixture(golden_dir)
+    B, G, N, S, K = (int(v) for v in z["cfg"])
+    _check_fused_backward(torch.from_numpy(z["points"]), sd0, z["order"], B, G, N, S, K, float(z["r2"]), TOL_GRAD["fp32"])
+
+
+def test_fused_l1_backward_long_accumulation():
+    """The same check at 8 sequences x 20 views x 2048 points (655 360 grouped rows: 35-70 tiles per CTA, so the TMEM-resident
+    Gram / weight-gradient accumulators and the per-thread BatchNorm sums run over thousands of steps) -- the largest size the
+    fp64 oracle finishes in seconds."""
+    from facl_b200 import synth
+    B, G, N, S, K = 8, 20, 2048, 64, 64
+    pts = torch.from_numpy(synth.make_sequences(B, G, N, seed=31))
+    _check_fused_backward(pts, oracle.init_state_dict(seed=12), synth.view_order(G, 5), B, G, N, S, K, 0.06, TOL_GRAD["fp32"])
+
+
+def test_full_size_fused_vs_per_layer_schedule():
+    """BASELINE configs[1] at FULL size (64 sequences x 20 views x 2048 points, fp32 mode): the fused net3DV_1 path (recompute,
+    closed-form BN1 / dW1, 64x64 backward algebra, Gram matrices accumulated over ~550 tiles per CTA, TMEM-resident weights)
+    against the per-layer GEMM schedule of the same library, which stores every activation and shares none of that algebra.
+    Both see the same weights and batch; loss, features, running statistics and every parameter gradient must agree.
+    (The oracle cannot run this size in seconds; it pins both schedules at the fixture size in the tests above.)"""
+    B, G, N, S, K = 64, 20, 2048, 64, 64
+    from facl_b200 import synth
+    sd0 = oracle.init_state_dict(seed=11)
+    clouds = torch.from_numpy(synth.make_sequences(B, G, N, seed=21)).permute(1, 0, 2, 3).reshape(-1, N, 4).contiguous().to(DEV)
+    order = synth.view_order(G, 3)
+    res = {}
+    for fused in (True, False):
+        net, opt = _build(sd0, B, G, N, S, K, "fp32")
+        net.fused_l1 = fused
+        net.train()
+        xt, yt = utils_my.group_points_3DV_2048(clouds, K, S)
+        x, code, x_nor, xg = net(xt, yt, 1)
+        lg, lc = facl_losses.contrast_losses(x, xg, G, B, order=order, prec="fp32")
+        (lg + lc).backward()
+        torch.cuda.synchronize()
+        res[fused] = dict(loss=float(lg + lc), x=x.detach().clone(), xg=xg.detach().clone(),
+                          grads={k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None},
+                          sd={k: v.detach().clone() for k, v in net.state_dict().items()})
+        del net, xt, yt, x, xg, lg, lc
+        torch.cuda.empty_cache()
+    a, b = res[True], res[False]
+    assert np.isfinite(a["loss"]) and abs(a["loss"] - b["loss"]) <= 1e-4 * abs(b["loss"]), (a["loss"], b["loss"])
+    assert rel2(a["x"], b["x"]) <= 1e-3 and rel2(a["xg"], b["xg"]) <= 1e-3
+    # Gradients: the two schedules round differently, so a few of the 5 M x 64 ReLU decisions and of the max-pool winners (over
+    # 64 neighbours, 64 centres, 20 views) flip between them, and each flip re-routes a gradient.  Measured at 8 sequences, where
+    # the fp64 oracle runs: fused vs oracle, per-layer vs oracle and fused vs per-layer ALL differ by 0.7-1.3e-2 (without
+    # matched decisions), while with matched decisions the fused path is within 1.5e-4 of the oracle (test_fused_l1_backward).
+    # This full-size check therefore bounds gross errors of scale (index overflow, accumulation blow-up), not rounding.
+    gscale = max(float(g.abs().max()) for g in b["grads"].values())
+    worst = []
+    for k, g in b["grads"].items():
+        if float(g.norm()) <= 1e-6 * gscale * g.numel() ** 0.5:            # zero by construction (conv bias in front of a BN)
+            assert float(a["grads"][k].abs().max()) <= 1e-4 * gscale, k
+            continue
+        worst.append((rel2(a["grads"][k], g), k))
+    print("\n" + "\n".join(f"{k:24s} fused vs per-layer, full size: {e:.2e}" for e, k in sorted(worst, reverse=True)[:8]))
+    for e, k in worst:
+        assert e <= 3e-2, (k, e)
+    for k, v in b["sd"].items():
+        if "running_" in k:
+            assert rel2(a["sd"][k], v) <= 1e-3, k
