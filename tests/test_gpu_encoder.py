@@ -380,12 +380,17 @@ def test_fused_l1_backward(golden_dir):
     _check_fused_backward(torch.from_numpy(z["points"]), sd0, z["order"], B, G, N, S, K, float(z["r2"]), TOL_GRAD["fp32"])
 
 
-def test_fused_l1_backward_long_accumulation():
-    """The same check at 8 sequences x 20 views x 2048 points (655 360 grouped rows: 35-70 tiles per CTA, so the TMEM-resident
-    Gram / weight-gradient accumulators and the per-thread BatchNorm sums run over thousands of steps) -- the largest size the
-    fp64 oracle finishes in seconds."""
+@pytest.mark.parametrize("B", [8, 64])
+def test_fused_l1_backward_long_accumulation(B):
+    """The same matched-decision check at B sequences x 20 views x 2048 points.  B = 64 is BASELINE configs[1] at FULL size
+    (5 242 880 grouped rows, ~550 tiles per CTA: the TMEM-resident Gram / weight-gradient accumulators and the per-thread
+    BatchNorm sums run over thousands of steps); the fp64 oracle needs ~40 s and ~100 GB of host memory for it, so that case is
+    skipped on hosts with less.  Measured on the 196 GB B200 box: every gradient within 1.7e-4 of the oracle (typically 5e-5)."""
+    import psutil
     from facl_b200 import synth
-    B, G, N, S, K = 8, 20, 2048, 64, 64
+    if B > 8 and psutil.virtual_memory().available < 150 * 2 ** 30:
+        pytest.skip("the fp64 oracle of the full-size step needs ~100 GB of host memory")
+    G, N, S, K = 20, 2048, 64, 64
     pts = torch.from_numpy(synth.make_sequences(B, G, N, seed=31))
     _check_fused_backward(pts, oracle.init_state_dict(seed=12), synth.view_order(G, 5), B, G, N, S, K, 0.06, TOL_GRAD["fp32"])
 
