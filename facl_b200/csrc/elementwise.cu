@@ -199,6 +199,20 @@ __global__ void l2_normalize_kernel(const float* __restrict__ x, int rows, int C
     for (int i = lane; i < C; i += 32) out[(long long)row * C + i] = xr[i] * inv;
 }
 
+// the constant vectors of the encoder's `vec` buffer in one launch: identity transform for the 3 centre-xyz channels of the
+// net3DV_3 input (scale 1 at 0, shift 0 at 320, lower bound -inf at 640), zero lower bounds (ReLU) for 256 channels at 643 and
+// 1024 zeros at 960
+__global__ void encoder_const_vectors_kernel(float* __restrict__ vec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3) {
+        vec[i] = 1.f;
+        vec[320 + i] = 0.f;
+        vec[640 + i] = -INFINITY;
+    }
+    if (i < 256) vec[643 + i] = 0.f;
+    if (i < 1024) vec[960 + i] = 0.f;
+}
+
 __global__ void fill_kernel(float* p, long long n, float v) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -319,6 +333,13 @@ int l2_normalize_launch(const float* x, int rows, int C, float* out, cudaStream_
     ScopedTimer timer(TAG_POOLMISC, st);
     count_launch();
     l2_normalize_kernel<<<div_up((long long)rows * 32, 256), 256, 0, st>>>(x, rows, C, out);
+    return (int)cudaGetLastError();
+}
+
+int encoder_const_vectors_launch(float* vec, cudaStream_t st) {
+    ScopedTimer timer(TAG_MEMSET, st);
+    count_launch();
+    encoder_const_vectors_kernel<<<4, 256, 0, st>>>(vec);
     return (int)cudaGetLastError();
 }
 

@@ -233,11 +233,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     uint8_t* wp = reinterpret_cast<uint8_t*>(bufs[B_WPACK]);
 
     // constant vectors: L3 input transform for the 3 centre-xyz channels (identity, no ReLU), zero lower bounds
-    RUN(fill_launch(vec, 3, 1.f, st));
-    RUN(fill_launch(vec + 320, 3, 0.f, st));
-    RUN(fill_launch(vec + 640, 3, -INFINITY, st));
-    RUN(fill_launch(vec + 643, 256, 0.f, st));
-    RUN(fill_launch(lo0, 1024, 0.f, st));
+    RUN(encoder_const_vectors_launch(vec, st));
     // operand images of the current weights
     {
         PackTable tbl;

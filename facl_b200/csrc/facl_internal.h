@@ -48,6 +48,7 @@ int pool_scatter_launch(const float* v, long long ldv, const unsigned char* arg,
 int centres_to_chmajor_launch(const float* c, int R, float* out, long long ldo, cudaStream_t st);
 int l2_normalize_launch(const float* x, int rows, int C, float* out, cudaStream_t st);
 int fill_launch(float* p, long long n, float v, cudaStream_t st);
+int encoder_const_vectors_launch(float* vec, cudaStream_t st);
 int adam_launch(const void* table_dev, int ntensors, float lr, float b1, float b2, float eps, int step, cudaStream_t st);
 }  // namespace facl
 

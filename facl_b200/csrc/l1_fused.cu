@@ -1228,19 +1228,20 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
 //          q = W^T (d (.) bias + c2).   W is [C][64].
 // l1_fin : dW[c][j] (+)= d[c] (sum_j' W[c][j'] H[j'][j] + bias[c] s[j]) + c2[c] s[j] (+ e0[c] sparse[c][j])
 // --------------------------------------------------------------------------------------------------------------------
-// grid = 8 blocks (8 rows j each) x 256 threads = (4 slices of the reduction over c) x (8 rows) x (8 chunks of 8 columns)
+// grid = 32 blocks (2 rows j each) x 256 threads = (16 slices of the reduction over c) x (2 rows) x (8 chunks of 8 columns)
+constexpr int PREP_SLICES = 16, PREP_ROWS = 2, PREP_BLOCKS = 64 / PREP_ROWS;
 __global__ void __launch_bounds__(256) l1_prep_kernel(const float* __restrict__ W, int C, const float* __restrict__ d,
                                                       const float* __restrict__ bias, const float* __restrict__ c2,
                                                       const float* __restrict__ e0, uint8_t* __restrict__ p_img, float* __restrict__ q,
                                                       uint8_t* __restrict__ e_img) {
-    __shared__ double red[3][64][9];
-    const int slice = threadIdx.x >> 6, t = threadIdx.x & 63;
-    const int j = blockIdx.x * 8 + (t >> 3), chunk = t & 7;
+    __shared__ double red[PREP_SLICES - 1][PREP_ROWS * 8][9];
+    const int slice = threadIdx.x / (PREP_ROWS * 8), t = threadIdx.x % (PREP_ROWS * 8);
+    const int j = blockIdx.x * PREP_ROWS + (t >> 3), chunk = t & 7;
     double acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.0;
     double qa = 0.0;
-    for (int c = slice; c < C; c += 4) {
+    for (int c = slice; c < C; c += PREP_SLICES) {
         const double wj = (double)__ldg(W + c * 64 + j), dc = (double)__ldg(d + c);
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + c * 64 + chunk * 8));
         const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + c * 64 + chunk * 8) + 1);
@@ -1256,8 +1257,8 @@ __global__ void __launch_bounds__(256) l1_prep_kernel(const float* __restrict__ 
     }
     __syncthreads();
     if (slice > 0) return;
-#pragma unroll
-    for (int sl = 0; sl < 3; ++sl) {
+#pragma unroll 1
+    for (int sl = 0; sl < PREP_SLICES - 1; ++sl) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] += red[sl][t][e];
         qa += red[sl][t][8];
@@ -1489,7 +1490,7 @@ int l1_prep_launch(const float* W, int C, const float* d, const float* bias, con
     if (C <= 0 || (e_img && C != 64)) return (int)cudaErrorInvalidValue;
     ScopedTimer timer(TAG_L1_MISC, st);
     count_launch();
-    l1_prep_kernel<<<8, 256, 0, st>>>(W, C, d, bias, c2, e0, reinterpret_cast<uint8_t*>(p_img), q, reinterpret_cast<uint8_t*>(e_img));
+    l1_prep_kernel<<<PREP_BLOCKS, 256, 0, st>>>(W, C, d, bias, c2, e0, reinterpret_cast<uint8_t*>(p_img), q, reinterpret_cast<uint8_t*>(e_img));
     return (int)cudaGetLastError();
 }
 
