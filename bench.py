@@ -184,7 +184,7 @@ def run_ours(args):
         fused.step(dev[i % nb])
     sync_all()
     L.facl_timing_enable(0)
-    ntags = 44
+    ntags = 46
     tms, tcnt = (C.c_float * ntags)(), (C.c_int * ntags)()
     L.facl_timing_collect(tms, tcnt, ntags)
 
