@@ -1064,12 +1064,28 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
             mbar_wait(w_bar, 0);
             const uint32_t ew = smem_u32(ews), p2 = smem_u32(p2s);
             int s = 0, ph = 0;
+#ifdef FACL_PROFILE_ROLES
+            long long pw_h1 = 0, pw_in = 0, pw_dh = 0, pw_issue = 0, pt0 = clock64();
+#endif
 #pragma unroll 1
             for (int it = 0; it < my_tiles; ++it) {
                 const int b = it & 1, u = (it >> 1) & 1;
+#ifdef FACL_PROFILE_ROLES
+                long long c0 = clock64();
+#endif
                 mbar_wait(&h1_full[s], ph);
+#ifdef FACL_PROFILE_ROLES
+                long long c1 = clock64();
+#endif
                 mbar_wait(&in_full[s], ph);
+#ifdef FACL_PROFILE_ROLES
+                long long c2 = clock64();
+#endif
                 mbar_wait(&dh_empty[b], u ^ 1);
+#ifdef FACL_PROFILE_ROLES
+                long long c3 = clock64();
+                pw_h1 += c1 - c0; pw_in += c2 - c1; pw_dh += c3 - c2;
+#endif
                 tc_fence_after_sync();
                 const uint32_t dz = smem_u32(stg + s * D_STAGE_BYTES), h1 = dz + IMG64;   // lo halves 2 * IMG64 further
                 // dh1[i][r] = sum_j (e0 W2)[j][i] dh2'[j][r] + sum_i' P2[i][i'] h1[i'][r];  lanes 0..63 hi part, 64..127 lo part
@@ -1086,7 +1102,15 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
                 mma_rows64(tmem_base + 256, dz, dz + 2 * IMG64, h1, h1 + 2 * IMG64, nhl, idesc_kk, it == 0);
                 umma_commit(&st_empty[s]);
                 if (++s == D_STAGES) { s = 0; ph ^= 1; }
+#ifdef FACL_PROFILE_ROLES
+                pw_issue += clock64() - c3;
+#endif
             }
+#ifdef FACL_PROFILE_ROLES
+            if (blockIdx.x == 0)      // measured: waits 68 / 51 / 94, issue 2013 of 2396 cycles per tile -- the issuing thread is back-pressured by the tensor pipe
+                printf("pass D mma warp: tiles %d, per tile: wait h1 %lld, wait dh2' TMA %lld, wait dh1 buffer %lld, issue %lld, total %lld\n",
+                       my_tiles, pw_h1 / my_tiles, pw_in / my_tiles, pw_dh / my_tiles, pw_issue / my_tiles, (clock64() - pt0) / my_tiles);
+#endif
             umma_commit(fin_bar);
         }
     } else if (warp == 13) {
