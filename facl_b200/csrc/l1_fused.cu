@@ -177,9 +177,10 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     // TMEM columns.  pass A: D2[b] at 128*b (b = 0,1), W2 A tiles (hi, lo) at 256 / 288.  pass B: D2 at 0 (single: its consumers
-    // copy it out at once), H2 Gram accumulator at 128..191 (lanes 0..63 h2_hi rows, 64..127 h2_lo rows), D3[half] at 256 + 128*half
+    // copy it out at once), H2 Gram accumulator at 128..255 (lanes 0..63 h2_hi rows, 64..127 h2_lo rows; columns 0..63 x h2_hi,
+    // 64..127 x h2_lo), D3[half] at 256 + 128*half
     const uint32_t idesc = umma_idesc_bf16(128, TILE) | UMMA_B_MN_MAJOR;
-    const uint32_t idesc_kk = umma_idesc_bf16(128, 64);
+    const uint32_t idesc_kk = umma_idesc_bf16(128, 64), idesc_kk2 = umma_idesc_bf16(128, 128);
     const uint32_t w2_t = tmem_base + 256;
     // pass A: W2 is constant and becomes an A operand in tensor memory (see tmem_put_a_tile); warps 8, 9 own lanes 0..63, warps 10,
     // 11 zero the unused lanes 64..127.  (Not in pass B: there the z3 consumers keep the TMEM read port busy, and A tiles read from
@@ -251,15 +252,16 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                         umma_commit(&d3_full[h]);
                     }
                     if (GRAM) {
-                        // H2 += h2 h2^T, reduction over the tile's rows: per 64-row block one stacked A tile [hi ; lo] (.) hi, (.) lo
+                        // H2 += h2 h2^T, reduction over the tile's rows.  A 64-row block [hi 64 ch ; lo 64 ch] is used as the 128-row A
+                        // tile AND as the 128-row B tile of ONE instruction per k-step: the accumulator's four 64 x 64 quadrants
+                        // are hi.hi, hi.lo, lo.hi, lo.lo, and H2 is their sum (taken when the accumulator is flushed)
 #pragma unroll
                         for (int blk = 0; blk < 2; ++blk) {
                             const uint32_t hb = smem_u32(h2s + b * 2 * ACT_BYTES) + blk * H2_LBO;
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 const uint64_t ad = umma_desc_sw128(hb + ks * 32);
-                                umma_bf16_ss(tmem_base + 128, ad, ad, idesc_kk, (it == 0 && blk == 0 && ks == 0) ? 0u : 1u);
-                                if (nhl == 2) umma_bf16_ss(tmem_base + 128, ad, umma_desc_sw128(hb + H2_LO + ks * 32), idesc_kk, 1u);
+                                umma_bf16_ss(tmem_base + 128, ad, ad, nhl == 2 ? idesc_kk2 : idesc_kk, (it == 0 && blk == 0 && ks == 0) ? 0u : 1u);
                             }
                         }
                     }
@@ -332,10 +334,12 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             tc_fence_after_sync();
             const int lg = warp & 1, colhalf = (warp >= 14) ? 1 : 0, j = lg * 32 + lane;
             float a[32];
+            float a2[32];
             tmem_ld32(tmem_base + ((uint32_t)(64 + lg * 32) << 16) + (uint32_t)(128 + colhalf * 32), a);
+            tmem_ld32(tmem_base + ((uint32_t)(64 + lg * 32) << 16) + (uint32_t)(192 + colhalf * 32), a2);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(p.gram + j * 64 + colhalf * 32 + i, a[i]);
+            for (int i = 0; i < 32; ++i) atomicAdd(p.gram + j * 64 + colhalf * 32 + i, a[i] + a2[i]);
         }
     } else if (warp == 8 || warp == 9 || warp == 12 || warp == 13) {
         // ======================= z2 consumers, thread = channel j (lanes 0..63 of D2), two column halves =============
@@ -406,7 +410,15 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             tc_fence_after_sync();
             float a[32];
             tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 + colhalf * 32), a);
-            tmem_ld_wait();
+            if (nhl == 2) {      // + the (.) h2_lo quadrant
+                float a2[32];
+                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(192 + colhalf * 32), a2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) a[i] += a2[i];
+            } else {
+                tmem_ld_wait();
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) atomicAdd(p.gram + j * 64 + colhalf * 32 + i, a[i]);
         }
