@@ -577,20 +577,6 @@ __device__ __forceinline__ void store_img8(uint8_t* img, int nhl, int img_bytes,
     }
 }
 
-// D (+)= A(K-major weight image, 64-wide K) * B(MN-major [64 ch][64 rows] image): reduction over the 64 channels
-__device__ __forceinline__ void mma_w_act64(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int nhl,
-                                            uint32_t idesc, bool first) {
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t ad = umma_desc_sw128(a_hi + ks * 32);
-        const uint64_t bd = umma_desc_mn_sw128(b_hi + ks * 2048, 8192, 1024);
-        umma_bf16_ss(d, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
-        if (nhl == 2) {
-            umma_bf16_ss(d, ad, umma_desc_mn_sw128(b_lo + ks * 2048, 8192, 1024), idesc, 1u);
-            umma_bf16_ss(d, umma_desc_sw128(a_lo + ks * 32), bd, idesc, 1u);
-        }
-    }
-}
 // D (+)= A(TMEM tile, 64-wide K) * B(MN-major [64 ch][64 rows] image): the three bf16 hi/lo products, N = 64
 __device__ __forceinline__ void mma_t_act64(uint32_t d, uint32_t a_hi_t, uint32_t a_lo_t, uint32_t b_hi, uint32_t b_lo, int nhl,
                                             uint32_t idesc, bool first) {
