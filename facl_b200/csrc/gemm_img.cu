@@ -106,8 +106,21 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
         long long pr_wait = 0, pr_work = 0, pr_t = clock64();
         int pr_n = 0;
 #endif
+        // EPI == 2: the zin rows of a chunk are fetched one chunk ahead (and the first chunk of a tile before the accumulator is
+        // waited for): with one epilogue warp per scheduler nothing else hides the ~1 k-cycle latency of these loads, which made this
+        // epilogue 21 k cycles per tile (3x the others) and the data-gradient GEMMs epilogue-bound
+        float4 zn[8];
+        auto zin_prefetch = [&](int nt, int cc) {
+            const int n0p = nt * N_TILE + cc * 32;
+            if (!cvalid || n0p >= p.Nd) return;
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                zn[t] = __ldg(reinterpret_cast<const float4*>(p.zin + (long long)(ch0 + 4 * t + tch) * p.ldz + n0p + tcol));
+        };
         for (int it = 0; sched.get(it, p, w); ++it) {
             const int buf = it & 1;
+            const int nchunks = (mma_n + 31) / 32;
+            if (!GEN && has_zin) zin_prefetch(w.nt, 0);
             mbar_wait(&acc_full[buf], (it >> 1) & 1);
             tc_fence_after_sync();
 #ifdef FACL_PROFILE_ROLES
@@ -115,7 +128,6 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
 #endif
             float best = 0.f;
             int barg = 0;
-            const int nchunks = (mma_n + 31) / 32;
             const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N_TILE);
 #pragma unroll 1
             for (int cc = 0; cc < nchunks; ++cc) {
@@ -139,13 +151,9 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                 float z[32];
                 if (has_zin) {
                     if (!GEN) {
-                        // coalesced: each instruction reads 4 channel rows x 128 bytes, then every thread picks up its own row
+                        // coalesced: each (prefetched) load covered 4 channel rows x 128 bytes; every thread now picks up its own row
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            const int ch = 4 * t + tch;
-                            *reinterpret_cast<float4*>(tb + ch * 36 + tcol) =
-                                __ldg(reinterpret_cast<const float4*>(p.zin + (long long)(ch0 + ch) * p.ldz + n0 + tcol));
-                        }
+                        for (int t = 0; t < 8; ++t) *reinterpret_cast<float4*>(tb + (4 * t + tch) * 36 + tcol) = zn[t];
                         __syncwarp();
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
@@ -153,6 +161,7 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                             z[4 * q] = t4.x; z[4 * q + 1] = t4.y; z[4 * q + 2] = t4.z; z[4 * q + 3] = t4.w;
                         }
                         __syncwarp();
+                        if (cc + 1 < nchunks) zin_prefetch(w.nt, cc + 1);
                     } else {
                         const float* zr = p.zin + (long long)c * p.ldz + n0;
 #pragma unroll
