@@ -50,7 +50,7 @@ def train_step(sd, points_bgnd, order, S=64, K=64, r2=0.06, adam_state=None, lr=
     for v in leaves.values():
         v.requires_grad_(False)
         v.grad = None
-    out = dict(loss=float(loss), loss_global=float(lg), loss_circle=float(lc), grads=grads,
+    out = dict(loss=float(loss.detach()), loss_global=float(lg.detach()), loss_circle=float(lc.detach()), grads=grads,
                x=x.detach(), x_global=x_global.detach())
     if apply_update:
         if adam_state is None:
