@@ -378,8 +378,39 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
         const uint8_t* ai_lo = reinterpret_cast<const uint8_t*>(p.a_img.lo);
         const uint8_t* bi_hi = reinterpret_cast<const uint8_t*>(p.b_img.hi);
         const uint8_t* bi_lo = reinterpret_cast<const uint8_t*>(p.b_img.lo);
+        // The activation images do not fit in L2 (168 MB for 512 channels x 81 920 rows), so a stage's bulk copies see HBM latency,
+        // and two 96 KB stages cannot cover it.  In the weight-gradient form (both operands are row blocks of images: 16-32 KB
+        // contiguous pieces that no other CTA reads) the pieces of the k-block PF_AHEAD steps ahead are requested into L2 while the
+        // ring is still busy (-3..-8 %).  Not in the weights x image form: there every piece is shared by the CTAs of all m-tiles
+        // and comes in 8 KB fragments; prefetching them made those GEMMs 30 % slower, also when only one CTA per column did it (measured).
+        constexpr int PF_AHEAD = 2;
+        auto prefetch_kblock = [&](const Work& wk, int kb) {
+            if (a_img) {
+                int na = p.a_img.cgs - wk.mt * 16;
+                na = na > 16 ? 16 : na;
+                const long long aoff = ((long long)kb * p.a_img.cgs + wk.mt * 16) * 1024;
+                tma_prefetch_l2(ai_hi + aoff, na * 1024);
+                if (NHL == 2) tma_prefetch_l2(ai_lo + aoff, na * 1024);
+            }
+            if (b_k) {
+                int nb = p.b_img.cgs - wk.nt * 32;
+                nb = nb > 32 ? 32 : nb;
+                const long long boff = ((long long)kb * p.b_img.cgs + wk.nt * 32) * 1024;
+                tma_prefetch_l2(bi_hi + boff, nb * 1024);
+                if (NHL == 2) tma_prefetch_l2(bi_lo + boff, nb * 1024);
+            }
+        };
         for (int it = 0; sched.get(it, p, w); ++it) {
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                if (b_k) {
+                    int pk = kb + PF_AHEAD;
+                    if (pk < w.kb1) {
+                        prefetch_kblock(w, pk);
+                    } else {
+                        Work wn;
+                        if (sched.get(it + 1, p, wn) && wn.kb0 + (pk - w.kb1) < wn.kb1) prefetch_kblock(wn, wn.kb0 + (pk - w.kb1));
+                    }
+                }
                 // ---- A: one 128 x 64 tile ----
                 mbar_wait(&a_empty[sa], pa ^ 1);
                 uint8_t* a_hi = a_ring + sa * A_SLOT;

@@ -62,6 +62,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
         : "memory");
 }
 
+// ask L2 to fetch a range that a later bulk copy will read (no shared memory, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMEM allocation (whole warp executes these)
 // ----------------------------------------------------------------------------------------------
