@@ -16,6 +16,8 @@
 // torch.topk(largest=False) returns whenever the K-th distance is not tied.  Slots whose
 // squared distance is > r2 (strict, utils_my.py:272) are redirected to the centre itself (:274-275).
 // Distances use ((dx*dx + dy*dy) + dz*dz) without FMA contraction -> bit-identical to the fp32 reference.
+#include <type_traits>
+
 #include "common.cuh"
 #include "facl_internal.h"
 #include "umma.cuh"
@@ -217,26 +219,32 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
     if (count <= CAP) {
         // rank = number of smaller keys; four of this lane's keys stay in registers while one broadcast read per
         // candidate serves all four comparisons
-        for (int base = 0; base < count; base += 128) {
-            unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull, k3 = ~0ull;
-            const int i0 = base + lane, i1 = i0 + 32, i2 = i0 + 64, i3 = i0 + 96;
-            if (i0 < count) k0 = cand[i0];
-            if (i1 < count) k1 = cand[i1];
-            if (i2 < count) k2 = cand[i2];
-            if (i3 < count) k3 = cand[i3];
-            int r0 = 0, r1 = 0, r2c = 0, r3 = 0;
+        // (the usual ~1.2 K = 77 candidates need three keys per lane, not four: the loop body is instantiated per key count)
+        auto rank_block = [&](auto nk_tag, int base) {
+            constexpr int NK = decltype(nk_tag)::value;
+            unsigned long long k[NK];
+            int r[NK];
+#pragma unroll
+            for (int q = 0; q < NK; ++q) {
+                const int i = base + lane + 32 * q;
+                k[q] = (i < count) ? cand[i] : ~0ull;
+                r[q] = 0;
+            }
 #pragma unroll 4
             for (int j = 0; j < count; ++j) {
                 const unsigned long long c = cand[j];
-                r0 += (c < k0) ? 1 : 0;
-                r1 += (c < k1) ? 1 : 0;
-                r2c += (c < k2) ? 1 : 0;
-                r3 += (c < k3) ? 1 : 0;
+#pragma unroll
+                for (int q = 0; q < NK; ++q) r[q] += (c < k[q]) ? 1 : 0;
             }
-            if (i0 < count && r0 < K) emit(r0, k0);
-            if (i1 < count && r1 < K) emit(r1, k1);
-            if (i2 < count && r2c < K) emit(r2c, k2);
-            if (i3 < count && r3 < K) emit(r3, k3);
+#pragma unroll
+            for (int q = 0; q < NK; ++q)
+                if (base + lane + 32 * q < count && r[q] < K) emit(r[q], k[q]);
+        };
+        for (int base = 0; base < count; base += 128) {
+            const int left = count - base;
+            if (left <= 64) rank_block(std::integral_constant<int, 2>{}, base);
+            else if (left <= 96) rank_block(std::integral_constant<int, 3>{}, base);
+            else rank_block(std::integral_constant<int, 4>{}, base);
         }
     } else {
         // Rare (heavy duplication around the centre): K rounds of "smallest key greater than the last one",
