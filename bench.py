@@ -3,7 +3,7 @@
 backward + Adam) on synthetic NTU-shaped point-cloud sequences.
 
     python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
-    python bench.py --impl reference ...                     # the reference algorithm on the host CPU (oracle port)
+    python bench.py --impl reference ...                     # the reference's own modules on the host CPU (oracle/_ref)
 
 Prints ONE JSON line (rank 0).  N=1 workload = BASELINE.json configs[1]: batch 64 x 20 views x 2048 points, fp32.
 For N>1 (torchrun) every rank keeps that per-GPU batch (weak scaling); embeddings are all-gathered for the
@@ -66,24 +66,58 @@ class ClockSampler(threading.Thread):
                     power_w_max=max(float(r[2]) for r in self.rows), samples=len(self.rows), reasons=reasons)
 
 
-def cpu_reference_step_time(B, G, N, steps, warmup, threads):
-    """The reference algorithm (oracle port: torch-CPU fp32 restatement of utils_my.group_points_3DV +
-    PointNet_Plus_fine + global/circle loss + autograd backward + Adam) on the host cores."""
-    import oracle
+def reference_leg(B, G, N, steps, warmup, threads):
+    """Times the reference's own CPU implementation of the step on the host cores.
+
+    kind "reference": the UNMODIFIED reference modules from oracle/_ref/ (tools/vendor_reference.sh): utils_my.group_points_3DV_2048
+    -> cn3d_model_conbag.PointNet_Plus_fine -> utils_my.global_contrast / circle_contrast -> autograd backward -> torch.optim.Adam,
+    the call sequence of cn3d_train_motion_GL.py:224-335.  kind "port": the oracle restatement, only when oracle/_ref is absent.
+    Must run in a process that does not use the GPU (the reference's hard-coded .cuda() calls are patched to identity)."""
     from facl_b200 import synth
+    from oracle import ref_step
     torch.set_num_threads(threads)
-    sd = oracle.init_state_dict(seed=1)
     pts = torch.from_numpy(synth.make_sequences(B, G, N, seed=1))
-    order = synth.view_order(G, 1)
-    state, times = {}, []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        res = oracle.train_step(sd, pts, order, S=64, K=64, r2=CFG2["r2"], adam_state=state)
-        state = res["adam_state"]
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    return sum(times) / len(times), float(res["loss"])
+    times, phases, loss = [], {}, float("nan")
+    if ref_step.available():
+        kind = "reference"
+        tr = ref_step.ReferenceTrainer(B, G, N, S=CFG2["S"], K=CFG2["K"], seed=1, threads=threads)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            loss, ph = tr.step(pts)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+                for k, v in ph.items():
+                    phases[k] = phases.get(k, 0.0) + v / steps
+    else:
+        import oracle
+        kind = "port"
+        sd = oracle.init_state_dict(seed=1)
+        order = synth.view_order(G, 1)
+        state = {}
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            res = oracle.train_step(sd, pts, order, S=CFG2["S"], K=CFG2["K"], r2=CFG2["r2"], adam_state=state)
+            state = res["adam_state"]
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            loss = float(res["loss"])
+    return sum(times) / len(times), loss, kind, phases
+
+
+def reference_batch(requested):
+    """Batch of the CPU arm: the configuration's own (64 sequences) when the host has the memory for the reference's
+    stored activations (~0.47 GB per sequence at 20 views x 2048 points, measured), else the largest power of two that fits."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        avail = 64.0
+    B = requested
+    while B > 4 and 0.5 * B + 4 > 0.8 * avail:
+        B //= 2
+    return B
 
 
 def run_reference(args):
@@ -91,18 +125,43 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    s = CPU_SAMPLE
-    sec, loss = cpu_reference_step_time(s["B"], s["G"], s["N"], max(1, min(args.steps, 3)), max(0, min(args.warmup, 1)), threads)
-    val = s["B"] / sec
+    G, N = args.G or CFG2["G"], args.N or CFG2["N"]
+    want = args.ref_batch or args.B or CFG2["B"]
+    B = reference_batch(want)
+    # one step of the full batch is ~15-40 s of CPU work: the K / W the driver passes are clamped so the run ends in minutes
+    steps, warmup = max(1, min(args.steps, 1 if B >= 32 else 2)), max(0, min(args.warmup, 1))
+    sec, loss, kind, phases = reference_leg(B, G, N, steps, warmup, threads)
+    val = B / sec
+    what = "unmodified reference modules (oracle/_ref: utils_my.group_points_3DV_2048, cn3d_model_conbag.PointNet_Plus_fine, " \
+           "utils_my.global_contrast / circle_contrast, torch.optim.Adam), torch CPU" if kind == "reference" else \
+           "oracle port (oracle/_ref absent: run tools/vendor_reference.sh where /root/reference exists)"
+    sample = f"{what}; {B} sequences x {G} views x {N} pts per step, {warmup} warm-up + {steps} timed step(s)"
+    full = args.B or CFG2["B"]
+    note = "the configuration's own global batch" if B == full else f"bounded sample: batch {B} of the configuration's {full} sequences per step"
     line = dict(metric="train sequences/sec (encoder fwd+bwd+InfoNCE)", value=val, unit="sequences/s", n_gpus=args.gpus,
-                steps=max(1, min(args.steps, 3)), warmup=max(0, min(args.warmup, 1)), ms_per_step=sec * 1e3,
+                steps=steps, warmup=warmup, ms_per_step=sec * 1e3,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="motion-stream contrastive training, 20 views x 2048 pts, fp32 (configs[1] shape)",
-                            global_batch=s["B"], note="bounded sample: batch 8 sequences per step on the host CPU"),
-                cpu_baseline=dict(value=val, unit="sequences/s", cores=threads, kind="port",
-                                  sample=f"oracle port, {s['B']} sequences x {s['G']} views x {s['N']} pts per step"),
+                config=dict(workload=f"motion-stream contrastive training, batch {B} x {G} views x {N} pts, S=K=64, r2={CFG2['r2']}, "
+                                     f"fp32 (BASELINE configs[1])", global_batch=B, parallelism="cpu", note=note, loss_at_end=loss),
+                cpu_baseline=dict(value=val, unit="sequences/s", cores=threads, kind=kind, sample=sample,
+                                  phase_seconds={k: round(v, 3) for k, v in phases.items()}),
                 e2e=dict(value=val, unit="sequences/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
+
+
+def cpu_baseline_subprocess(B, steps=2, warmup=1, timeout=600):
+    """The cpu_baseline leg of the GPU arm: the reference arm above on a bounded sample, in a CHILD process (the reference's
+    .cuda() patch must not leak into the process that drives the GPU)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-batch", str(B), "--steps", str(steps),
+           "--warmup", str(warmup)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        return line["cpu_baseline"]
+    except Exception as e:                                       # the baseline is a reported number, never a reason to lose the bench line
+        return dict(value=None, unit="sequences/s", cores=os.cpu_count() or 1, kind="unavailable", sample=f"failed: {e!r}")
 
 
 TAG_NAMES = {27: "group_kernel", 28: "fps", 29: "pack_weight", 30: "bn_finalize", 31: "pool_misc", 32: "pool_scatter",
@@ -266,12 +325,7 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        s = CPU_SAMPLE
-        sec, _ = cpu_reference_step_time(s["B"], s["G"], s["N"], 2, 1, threads)
-        cpu = dict(value=s["B"] / sec, unit="sequences/s", cores=threads, kind="port",
-                   sample=f"oracle port (torch-CPU restatement of the reference step), {s['B']} sequences x {s['G']} views x "
-                          f"{s['N']} pts per step, 1 warm-up + 2 timed steps")
+        cpu = cpu_baseline_subprocess(CPU_SAMPLE["B"])            # ~10 s of CPU work: 1 warm-up + 2 timed steps of 8 sequences
     h2d = B * G * N * 4 * 4 + G * 4
     line = dict(metric="train sequences/sec (encoder fwd+bwd+InfoNCE)", value=world * B * args.steps / (ms * 1e-3),
                 unit="sequences/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
@@ -304,6 +358,7 @@ def main():
     ap.add_argument("--N", type=int, default=None)
     ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=None, help="batch of the CPU reference arm (default: the configuration's 64)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -74,7 +74,8 @@ class TrainStepArgs(C.Structure):
                 ("dx", C.c_void_p), ("dx_global", C.c_void_p), ("adam_table", C.c_void_p), ("adam_ntensors", C.c_int),
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int),
                 ("loss_host", C.c_void_p), ("phases", C.c_int), ("B_global", C.c_int), ("sample_offset", C.c_int),
-                ("keys", C.c_void_p), ("dkeys", C.c_void_p), ("dx_extra", C.c_void_p)]
+                ("keys", C.c_void_p), ("dkeys", C.c_void_p), ("dx_extra", C.c_void_p),
+                ("order_by_value", C.c_int), ("order_vals", C.c_int * 256)]
 
 
 class PointSource(C.Structure):

@@ -31,3 +31,22 @@ __device__ __forceinline__ int div_up_dev(int a, int b) { return (a + b - 1) / b
 }  // namespace facl
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// One-time PER-DEVICE kernel configuration: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a property of the function on the
+// current device, so a process that touches a second GPU (a model moved to cuda:1, nn.DataParallel replicas) must configure
+// again there.  `need()` is true until `done()` has been called on the current device; a race between two host threads only
+// repeats an idempotent attribute call.
+#include <atomic>
+namespace facl {
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask{0ull};
+    int dev = 0;
+    bool need() {
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) { dev = -1; return true; }   // unknown device: configure every time
+        return ((mask.load(std::memory_order_acquire) >> dev) & 1ull) == 0ull;
+    }
+    void done() {
+        if (dev >= 0) mask.fetch_or(1ull << dev, std::memory_order_release);
+    }
+};
+}  // namespace facl

@@ -214,6 +214,7 @@ int check_dims(const facl_encoder_dims* d) {
     if (d->K <= 0 || d->K > 256 || (d->K & (d->K - 1))) return (int)cudaErrorInvalidValue;
     if (d->S <= 0 || d->S > 256 || (d->S & (d->S - 1))) return (int)cudaErrorInvalidValue;
     if (d->nsplit != 1 && d->nsplit != 3) return (int)cudaErrorInvalidValue;
+    if (d->G > 255) return (int)cudaErrorInvalidValue;   // the sequence max-pool records its winning view in one byte (seq_pool_kernel)
     return 0;
 }
 
@@ -412,10 +413,13 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     return 0;
 }
 
+// stages: 1 = head + net3DV_3 (every gradient except net3DV_1's is final afterwards), 2 = net3DV_1, 3 = both.  The split lets a
+// data-parallel caller start the all-reduce of the large gradients while the net3DV_1 backward (43 % of the step) still runs.
 int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, const float* xt, void* const* bufs, const float* dx,
-                     const float* dxg, const facl_encoder_grads* gr, cudaStream_t st) {
+                     const float* dxg, const facl_encoder_grads* gr, int stages, cudaStream_t st) {
     RUN(check_dims(d));
-    if (!d->training) return (int)cudaErrorInvalidValue;
+    if (!d->training || (stages & 3) == 0) return (int)cudaErrorInvalidValue;
+    const bool stage_hi = (stages & 1) != 0, stage_l1 = (stages & 2) != 0;
     const int M = d->M, S = d->S, K = d->K, G = d->G, B = M / G, ns = d->nsplit;
     const long long R3 = (long long)M * S, R1 = R3 * K, MB = M + B;
     auto F = [&](int i) { return reinterpret_cast<float*>(bufs[i]); };
@@ -425,6 +429,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
     float* stats = F(B_STATS);
     uint8_t* wt = reinterpret_cast<uint8_t*>(bufs[B_WPACKT]);
 
+    if (stage_hi) {
     // (the transposed weight images for the data-gradient GEMMs were packed by the training-mode forward)
     // weight gradients are accumulated with atomics (split-K): start from zero; biases in front of a BN get 0
     for (int l = 0; l < 7; ++l) {
@@ -439,6 +444,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
     if (dxg) RUN(transpose_launch(dxg, C_EMB, F(B_DXT) + M, MB, B, C_EMB, st));
     RUN(rowstats_launch(F(B_DXT), nullptr, MB, C_EMB, (int)MB, 0, gr->dfc3_b, st));   // netR_FC.3.bias: sum over both batches
 
+    }
     auto wgrad = [&](int layer, int Md, int Nd, int Kd, const OperandSrc& a, const OperandSrc& b, float* out) {
         GemmParams g = gemm_base(Md, Nd, Kd, layer_nsplit(ns, layer));
         g.tag = 3 * layer + 1;
@@ -469,7 +475,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
 
     // ---- head -------------------------------------------------------------------------------------------------
     Slot s5 = bn_slot(bufs, 5);
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < 2 && stage_hi; ++half) {
         const int Nd = half == 0 ? M : B;
         const long long off = half == 0 ? 0 : M;
         Slot s6 = bn_slot(bufs, 6 + half);
@@ -508,13 +514,17 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
         RUN(img_dgrad(6, C_FEAT, C_FEAT, wt + wpackt_offset(6), hi.dz, F(B_PALL) + off, s5.scale, s5.shift, F(B_DF) + off, false));
     }
     // sequence max -> the winning view's cloud; then the BN6 sums live on the pooled positions only
-    RUN(combine_pool_grads_launch(F(B_DF), MB, F(B_DF) + M, MB, U(B_ARGG), C_FEAT, G, B, st));
-    RUN(rowstats_launch(F(B_DF), F(B_PALL), MB, C_FEAT, M, 1, stats, st));
-    RUN(bwd_finalize(5, 5, C_FEAT, M, (double)R3, 1, 0));
+    if (stage_hi) {
+        RUN(combine_pool_grads_launch(F(B_DF), MB, F(B_DF) + M, MB, U(B_ARGG), C_FEAT, G, B, st));
+        RUN(rowstats_launch(F(B_DF), F(B_PALL), MB, C_FEAT, M, 1, stats, st));
+        RUN(bwd_finalize(5, 5, C_FEAT, M, (double)R3, 1, 0));
+    }
 
     // ---- L3 ---------------------------------------------------------------------------------------------------
     Slot s4 = bn_slot(bufs, 4), s3 = bn_slot(bufs, 3), s2 = bn_slot(bufs, 2), s1 = bn_slot(bufs, 1), s0 = bn_slot(bufs, 0);
-    if (use_images(d)) {
+    if (!stage_hi) {
+        // net3DV_3 and the head ran in an earlier call on these buffers
+    } else if (use_images(d)) {
         // dz_l = c0*dy + c1*z + c2 is converted ONCE into an image and read by both the weight- and the data-gradient GEMM;
         // the forward input images (img_h*) are still there.  dy of layer 5 is the max-pool scatter of df, read through arg6.
         auto l3_bwd = [&](int layer, const OperandSrc& dzsrc, long long ld1, const unsigned char* parg, int h_buf, const float* zin,
@@ -573,6 +583,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
         RUN(bwd_finalize(2, 2, 256, (int)R3, (double)R1, gemm_tc_ctas_per_mtile(256, (int)R3), 0));
     }
     }
+    if (!stage_l1) return 0;
     if (d->flags & FACL_ENC_FUSED_L1) {
         // ---- L1 fused backward: activations recomputed from the 16-byte input rows (l1_fused.cu) ------------------------
         if ((R1 % 64) != 0 || K != 64) return (int)cudaErrorInvalidValue;
@@ -647,7 +658,7 @@ int facl_encoder_forward(const facl_encoder_dims* dims, const facl_encoder_param
 int facl_encoder_backward(const facl_encoder_dims* dims, const facl_encoder_params* params, const float* xt, void* const* buffers,
                           const float* dx, const float* dx_global, const facl_encoder_grads* grads, void* stream) {
     if (!dims || !params || !xt || !buffers || !grads) return (int)cudaErrorInvalidValue;
-    return encoder_backward(dims, params, xt, buffers, dx, dx_global, grads, reinterpret_cast<cudaStream_t>(stream));
+    return encoder_backward(dims, params, xt, buffers, dx, dx_global, grads, 3, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int facl_adam_step(const void* table_dev, int ntensors, float lr, float beta1, float beta2, float eps, int step, void* stream) {

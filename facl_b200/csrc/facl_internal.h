@@ -107,7 +107,13 @@ int group_level2_launch(const float* feats, int M, int C, int N1, int S2, int K,
                         cudaStream_t st);
 }  // namespace facl
 
+struct facl_encoder_dims;
+struct facl_encoder_params;
+struct facl_encoder_grads;
 namespace facl {
+// encoder.cu
+int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, const float* xt, void* const* bufs, const float* dx,
+                     const float* dxg, const facl_encoder_grads* gr, int stages, cudaStream_t st);
 // train_step.cu
 int gmajor_launch(const float* in, float* out, int B, int G, int N, cudaStream_t st);
 int centres_launch(const float* clouds, int M, int N, int S, float* centres, cudaStream_t st);

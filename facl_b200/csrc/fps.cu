@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(T) fps_kernel(const float* __restrict__ pts, i
     __shared__ unsigned red_val[2][32];
     __shared__ unsigned red_idx[2][32];
     int cur = start[v];
+    cur = cur < 0 ? 0 : (cur >= N ? N - 1 : cur);          // an out-of-range seed would index past the cloud: clamped (documented in the header)
     if (tid == 0) out[(long long)v * m] = cur;
     int par = 0;
     for (int it = 1; it < m; ++it) {
@@ -70,7 +71,10 @@ __global__ void __launch_bounds__(T) fps_kernel(const float* __restrict__ pts, i
 }
 
 // rows [0,m) <- the picks in pick order, rows [m,N) <- the remaining points in ascending index order
-// (cn3D_data_set.py:669-671: concatenate(picks, setdiff1d(arange(N), picks)))
+// (cn3D_data_set.py:669-671: concatenate(picks, setdiff1d(arange(N), picks))[:N]).  FPS repeats an index once a cloud has fewer
+// than m distinct points (the loader resamples with replacement); the unpicked rows then number N - uniq > N - m and the
+// reference TRUNCATES the concatenation to N rows (`new_idx[:NUM_POINT]`, :671) -- so does the tail copy here.  Picks outside
+// [0, N) cannot be reported from the device without a synchronisation: they are clamped into the cloud.
 __global__ void __launch_bounds__(256) fps_reorder_kernel(const float* __restrict__ pts, int N, int D, const int* __restrict__ picks,
                                                           int m, float* __restrict__ out) {
     extern __shared__ unsigned char flag[];   // N bytes, then 256 ints
@@ -80,7 +84,11 @@ __global__ void __launch_bounds__(256) fps_reorder_kernel(const float* __restric
     float* dst = out + (long long)v * N * D;
     for (int i = tid; i < N; i += 256) flag[i] = 0;
     __syncthreads();
-    for (int j = tid; j < m; j += 256) flag[picks[(long long)v * m + j]] = 1;
+    for (int j = tid; j < m; j += 256) {
+        int i = picks[(long long)v * m + j];
+        i = i < 0 ? 0 : (i >= N ? N - 1 : i);
+        flag[i] = 1;
+    }
     __syncthreads();
     const int chunk = (N + 255) / 256;
     const int lo = tid * chunk, hi = min(N, lo + chunk);
@@ -98,7 +106,7 @@ __global__ void __launch_bounds__(256) fps_reorder_kernel(const float* __restric
     }
     __syncthreads();
     int pos = m + cnt[tid];
-    for (int i = lo; i < hi; ++i) {
+    for (int i = lo; i < hi && pos < N; ++i) {           // pos < N: the reference's truncation when picks repeat
         if (!flag[i]) {
             for (int d = 0; d < D; ++d) dst[(long long)pos * D + d] = src[(long long)i * D + d];
             ++pos;
@@ -106,6 +114,7 @@ __global__ void __launch_bounds__(256) fps_reorder_kernel(const float* __restric
     }
     for (int j = tid; j < m; j += 256) {
         int i = picks[(long long)v * m + j];
+        i = i < 0 ? 0 : (i >= N ? N - 1 : i);
         for (int d = 0; d < D; ++d) dst[(long long)j * D + d] = src[(long long)i * D + d];
     }
 }

@@ -553,15 +553,15 @@ size_t act_image_half_bytes(int C, long long R) {
 }
 
 int launch_gemm_img(const GemmParams& p, cudaStream_t stream) {
-    static bool configured = false;
+    static DeviceOnce configured;
     const int smem_bytes = 4 * (A_TILE_BYTES + B_TILE_BYTES) + 1024 + 256 + 4 * 32 * 36 * 4;
-    if (!configured) {
+    if (configured.need()) {
 #define FACL_IMG_ATTR(N, E) \
         FACL_CHECK(cudaFuncSetAttribute(gemm_img_kernel<N, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         FACL_IMG_ATTR(1, 0) FACL_IMG_ATTR(1, 1) FACL_IMG_ATTR(1, 2) FACL_IMG_ATTR(1, 3)
         FACL_IMG_ATTR(2, 0) FACL_IMG_ATTR(2, 1) FACL_IMG_ATTR(2, 2) FACL_IMG_ATTR(2, 3)
 #undef FACL_IMG_ATTR
-        configured = true;
+        configured.done();
     }
     const bool a_img = p.a_mode == A_IMAGE, b_k = p.b_mode == B_IMAGE_K;
     if ((!a_img && p.a_mode != A_PACKED) || (!b_k && p.b_mode != B_IMAGE_MN) || (a_img && !b_k)) return (int)cudaErrorInvalidValue;

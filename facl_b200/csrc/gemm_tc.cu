@@ -4,6 +4,7 @@
 //   warp  10   MMA issuer (one lane issues tcgen05.mma; owns the TMEM allocation)
 //   warp  11   TMA        (one lane bulk-copies pre-packed weight tiles, cp.async.bulk + mbarrier tx)
 #include "gemm_tc.cuh"
+#include "common.cuh"
 #include "facl_internal.h"
 #include "umma.cuh"
 #include "gemm_sched.cuh"
@@ -426,12 +427,12 @@ int gemm_tc_ctas_per_mtile(int Md, int Nd) {
 
 int launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
     if (p.a_mode == A_IMAGE || p.b_mode == B_IMAGE_MN || p.b_mode == B_IMAGE_K) return launch_gemm_img(p, stream);
-    static bool configured = false;
+    static DeviceOnce configured;
     const int smem_bytes = 4 * (A_TILE_BYTES + B_TILE_BYTES) + 1024 + 256;
-    if (!configured) {
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.done();
     }
     if (p.Md <= 0 || p.Nd <= 0 || p.Kd <= 0) return (int)cudaErrorInvalidValue;
     if (p.nsplit != 1 && p.nsplit != 3) return (int)cudaErrorInvalidValue;

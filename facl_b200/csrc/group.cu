@@ -276,8 +276,8 @@ __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict_
 int group_launch(const float* points, int M, int N, int D, int S, int K, float r2, float* xt, int* idx_out, cudaStream_t st) {
     if (M <= 0 || N <= 0 || D < 3 || S <= 0 || S > N || K <= 0 || K > N || K > 32 * TMAX) return (int)cudaErrorInvalidValue;
     const size_t smem = (size_t)(N < TILE_PTS ? N : TILE_PTS) * 16 + (size_t)GW * CAP * 8;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         const int max_smem = TILE_PTS * 16 + GW * CAP * 8;
 #define FACL_GROUP_ATTR(TT)                                                                                              \
         FACL_CHECK(cudaFuncSetAttribute(group_kernel<true, TT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));   \
@@ -286,7 +286,7 @@ int group_launch(const float* points, int M, int N, int D, int S, int K, float r
 #undef FACL_GROUP_ATTR
         FACL_CHECK(cudaFuncSetAttribute(group_kernel<true, 3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         FACL_CHECK(cudaFuncSetAttribute(group_kernel<true, 3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        configured = true;
+        configured.done();
     }
     dim3 grid((S + GW - 1) / GW, M);
     ScopedTimer timer(TAG_GROUP, st);

@@ -1454,13 +1454,13 @@ int l1_fwd_launch(bool pass_b, const float* xt, long long R, int K, int nsplit, 
     if (stat_mode < 0 || stat_mode > 1 || (!pass_b && stat_mode != 1) || (stat_mode == 1 && !stats) || ((gram == nullptr) != (hsum == nullptr)) ||
         (gram && (!pass_b || stat_mode != 1)))
         return (int)cudaErrorInvalidValue;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         FACL_CHECK(cudaFuncSetAttribute(l1_fwd_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_smem_bytes(false)));
         FACL_CHECK(cudaFuncSetAttribute(l1_fwd_kernel<true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_smem_bytes(true)));
         FACL_CHECK(cudaFuncSetAttribute(l1_fwd_kernel<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_smem_bytes(true)));
         FACL_CHECK(cudaFuncSetAttribute(l1_fwd_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_smem_bytes(true)));
-        configured = true;
+        configured.done();
     }
     L1Params p;
     p.xt = xt; p.R = R; p.K = K; p.nhl = (nsplit == 3) ? 2 : 1;
@@ -1531,10 +1531,10 @@ int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, c
                     long long ldp, const float* c3_0, void* dh2, float* dw3, float* stats,
                     cudaStream_t st) {
     if (R <= 0 || R % BT != 0 || ldp % 4 != 0) return (int)cudaErrorInvalidValue;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         FACL_CHECK(cudaFuncSetAttribute(l1_bwd_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_bwd_c_smem()));
-        configured = true;
+        configured.done();
     }
     L1BwdParams p;
     fill_bwd_common(p, xt, R, nsplit, w1, b1, scale1, shift1);
@@ -1554,10 +1554,10 @@ int l1_bwd_d_launch(const float* xt, long long R, int nsplit, const float* w1, c
                     const float* shift1, const void* e0w2_img, const void* p2_img, const float* q2, const void* dh2, float* dw2s,
                     float* gram, float* hsum, float* amat, float* stats, cudaStream_t st) {
     if (R <= 0 || R % BT != 0) return (int)cudaErrorInvalidValue;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         FACL_CHECK(cudaFuncSetAttribute(l1_bwd_d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_bwd_d_smem()));
-        configured = true;
+        configured.done();
     }
     L1BwdParams p;
     fill_bwd_common(p, xt, R, nsplit, w1, b1, scale1, shift1);

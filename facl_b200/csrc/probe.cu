@@ -33,10 +33,12 @@ __global__ void softmax_xent_kernel(const float* __restrict__ logits, const int*
     for (int c = lane; c < C; c += 32) se += __expf(z[c] - mx);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xFFFFFFFFu, se, o);
-    const int y = labels[row];
+    int y = labels[row];
+    const bool bad_label = y < 0 || y >= C;              // torch's CrossEntropyLoss device-asserts here; a kernel cannot raise, so the
+    y = bad_label ? 0 : y;                               // loss turns NaN (loud) instead of reading outside the logits row
     const float inv_rows = 1.f / (float)rows, lse = mx + __logf(se);
     if (lane == 0) {
-        if (loss) atomicAdd(loss, (lse - z[y]) * inv_rows);
+        if (loss) atomicAdd(loss, bad_label ? __int_as_float(0x7fc00000) : (lse - z[y]) * inv_rows);
         if (hits && arg == y) atomicAdd(hits, 1);
     }
     if (dlogits_t || dbias) {

@@ -27,6 +27,10 @@ __global__ void centres_kernel(const float* __restrict__ clouds, int M, int N, i
     centres[t * 3 + 1] = p[1];
     centres[t * 3 + 2] = p[2];
 }
+struct OrderVals { int v[FACL_MAX_VIEWS]; };
+__global__ void set_order_kernel(const OrderVals o, int G, int* __restrict__ order) {
+    if ((int)threadIdx.x < G) order[threadIdx.x] = o.v[threadIdx.x];
+}
 __global__ void add2_kernel(const float* __restrict__ v, float* __restrict__ out) { out[0] = v[0] + v[1]; }
 __global__ void axpy1_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,6 +87,20 @@ int facl_train_step(const facl_train_step_args* a, void* stream) {
         // single GPU: keys == x and both gradient roles are summed into dx; sharded: dkeys is a separate buffer that the
         // caller sum-reduce-scatters and hands back as dx_extra
         float* dkeys = a->keys ? a->dkeys : a->dx;
+        if (a->order_by_value) {
+            if (!a->order || G > FACL_MAX_VIEWS) return (int)cudaErrorInvalidValue;
+            OrderVals ov;
+            bool seen[FACL_MAX_VIEWS] = {false};
+            for (int i = 0; i < G; ++i) {          // must be a permutation of 0..G-1: the loss kernels index rows with it
+                const int o = a->order_vals[i];
+                if (o < 0 || o >= G || seen[o]) return (int)cudaErrorInvalidValue;
+                seen[o] = true;
+                ov.v[i] = o;
+            }
+            count_launch();
+            set_order_kernel<<<1, FACL_MAX_VIEWS, 0, st>>>(ov, G, a->order);
+            FACL_CHECK_LAUNCH();
+        }
         if ((rc = facl_contrast_losses(a->x, a->x_global, a->keys, G, Bglob, Bl, a->sample_offset, 512, a->order, 1, 1, d->nsplit,
                                        a->loss_ws, a->loss2, a->dx, a->dx_global, dkeys, stream)))
             return rc;
@@ -90,14 +108,21 @@ int facl_train_step(const facl_train_step_args* a, void* stream) {
         add2_kernel<<<1, 1, 0, st>>>(a->loss2, a->loss2 + 2);
         FACL_CHECK_LAUNCH();
     }
-    if (phases & FACL_PHASE_BACKWARD) {
+    if (phases & (FACL_PHASE_BACKWARD | FACL_PHASE_BACKWARD_HEAD)) {
         if (a->dx_extra) {
             long long n = (long long)M * 512;
             count_launch();
             axpy1_kernel<<<div_up(n, 256), 256, 0, st>>>(a->dx, a->dx_extra, n);
             FACL_CHECK_LAUNCH();
         }
-        if ((rc = facl_encoder_backward(d, a->params, a->xt, a->enc_buffers, a->dx, a->dx_global, a->grads, stream))) return rc;
+    }
+    {
+        // FACL_PHASE_BACKWARD = both stages; a sharded caller issues HEAD, starts the all-reduce of everything but net3DV_1's
+        // gradients on a side stream, and issues L1 -- the collective hides under passes C / D
+        int stages = (phases & FACL_PHASE_BACKWARD) ? 3 : 0;
+        if (phases & FACL_PHASE_BACKWARD_HEAD) stages |= 1;
+        if (phases & FACL_PHASE_BACKWARD_L1) stages |= 2;
+        if (stages && (rc = encoder_backward(d, a->params, a->xt, a->enc_buffers, a->dx, a->dx_global, a->grads, stages, st))) return rc;
     }
     if (phases & FACL_PHASE_UPDATE) {
         if ((rc = facl_adam_step(a->adam_table, a->adam_ntensors, a->lr, a->beta1, a->beta2, a->eps, a->step, stream))) return rc;

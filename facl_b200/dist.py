@@ -11,14 +11,18 @@ SURVEY.md section 8e:
     Every rank evaluates the two losses for ITS anchors against ALL keys (global negatives);
   * backward exchange: the key-side gradient dkeys (R*G*Bl, 512) is sum-reduce-scattered back to the owners, so the
     gradient flows through the gather (the reference's helper is @no_grad);
-  * parameter gradients (+ the two loss values) are summed by ONE all-reduce over a flat buffer, then every rank
-    applies the same Adam step.  BatchNorm running statistics stay rank-local; rank 0's are the ones to checkpoint.
+  * parameter gradients (+ the loss values) live in one flat buffer, reduced as TWO buckets: everything except
+    net3DV_1's gradients (99 % of the bytes) is all-reduced asynchronously as soon as the net3DV_3 backward has produced
+    it and hides under the net3DV_1 backward; the small rest follows.  Then every rank applies the same Adam step.
+    BatchNorm running statistics stay rank-local; rank 0's are the ones to checkpoint.
 """
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from .train import FusedTrainStep
+
+PHASE_FORWARD, PHASE_LOSS, PHASE_BACKWARD, PHASE_UPDATE, PHASE_BACKWARD_HEAD, PHASE_BACKWARD_L1 = 1, 2, 4, 8, 16, 32   # FACL_PHASE_*
 
 
 def key_index(g, n, G, Bl):
@@ -61,42 +65,31 @@ class DistributedFusedTrainStep(FusedTrainStep):
         self._lib.check(self._lib.lib().facl_train_step(self.C.byref(self.args), self._lib.stream_ptr()), "facl_train_step")
 
     def step(self, batch, order=None, want_host_loss=False, next_batch=None):
-        dev_copy, pf_slot = self._take_prefetched(batch)
-        if dev_copy is not None:
-            batch = dev_copy
-        tr = self.tr
-        G = self.shape[1]
-        if order is None:                                   # same seed on every rank -> same permutation
-            order = np.arange(0, G, 1)
-            tr.rng.shuffle(order)
-        opt = tr.optimizer
-        opt._step += 1
-        slot = self.order_ring[opt._step % len(self.order_ring)]
-        slot.copy_(torch.from_numpy(np.asarray(order, dtype=np.int32)))
-        self.order_dev.copy_(slot, non_blocking=True)
-        a = self.args
-        if batch.is_cuda:
-            a.points_bgnd, a.points_host = batch.data_ptr(), None
-        else:
-            a.points_bgnd, a.points_host = None, batch.data_ptr()
-        a.lr, a.step = float(opt.param_groups[0]["lr"]), opt._step
-        a.loss_host = self.loss_host.data_ptr() if want_host_loss else None
-        self._call(1)                                                          # forward
-        if self.world > 1:
+        pf_slot = self._begin_step(batch, order, want_host_loss)
+        multi = self.world > 1
+        self._call(PHASE_FORWARD)
+        if multi:
             dist.all_gather_into_tensor(self.keys, self.x)
         else:
             self.keys.copy_(self.x)
-        self._call(2)                                                          # losses, dx / dkeys
-        if self.world > 1:
+        self._call(PHASE_LOSS)                                                 # losses, dx / dkeys
+        if multi:
             dist.reduce_scatter_tensor(self.dkeys_loc, self.dkeys, op=dist.ReduceOp.SUM)
         else:
             self.dkeys_loc.copy_(self.dkeys)
-        self._call(4)                                                          # backward
-        self.flat[-4:-1].copy_(self.loss2)
-        if self.world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.loss2.copy_(self.flat[-4:-1])
-        self._call(8)                                                          # Adam, loss D2H
+        self.flat[0:3].copy_(self.loss2)                                        # this rank's loss shares ride in the small bucket
+        self._call(PHASE_BACKWARD_HEAD)                                         # head + net3DV_3: 99 % of the gradient bytes are final
+        big = None
+        if multi:
+            # asynchronous: NCCL's stream waits for the kernels issued so far and reduces the large bucket while the
+            # net3DV_1 backward (passes C / D, 2.7 ms) runs on the compute stream
+            big = dist.all_reduce(self.flat[self.flat_l1_end:], op=dist.ReduceOp.SUM, async_op=True)
+        self._call(PHASE_BACKWARD_L1)
+        if multi:
+            dist.all_reduce(self.flat[:self.flat_l1_end], op=dist.ReduceOp.SUM)   # loss values + net3DV_1 gradients (86 KB)
+            big.wait()                                                          # compute stream waits for the large bucket
+        self.loss2.copy_(self.flat[0:3])
+        self._call(PHASE_UPDATE)                                                # Adam, loss D2H
         self._release_prefetched(pf_slot)
         if next_batch is not None:
             self.prefetch(next_batch)

@@ -17,6 +17,22 @@ class Adam(torch.optim.Optimizer):
         self._table_key = None
         self._step = 0
 
+    # The step count lives in one Python int on the hot path (the fused train step increments it without touching the
+    # per-parameter state); state_dict() / load_state_dict() carry it as torch.optim.Adam does -- state[p]["step"], a
+    # float32 scalar tensor per parameter -- so a resumed run keeps its bias correction and the state is interchangeable
+    # with torch.optim.Adam(lr, betas, eps) (cn3d_train_motion_GL.py:180).
+    def state_dict(self):
+        for st in self.state.values():
+            if st:
+                st["step"] = torch.tensor(float(self._step), dtype=torch.float32)
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        steps = [int(st["step"]) for st in self.state.values() if st and "step" in st]
+        self._step = max(steps) if steps else 0
+        self._table_key = None              # the moment tensors were replaced: rebuild the device table
+
     @torch.no_grad()
     def step(self, closure=None):
         if closure is not None:

@@ -113,10 +113,13 @@ class FusedTrainStep:
         self.ws = net._workspace(self.dims, dev, True)
         params = net._param_list()
         self.params_struct = _params_struct([p.detach() for p in params], net._bn_buffers())
-        # one flat gradient buffer (+ 4 trailing floats for the loss values): a single all-reduce covers it when sharded
+        # one flat gradient buffer: [4 floats for the loss values | net3DV_1's gradients (12 tensors) | everything else], so a
+        # sharded run reduces it as two contiguous buckets (dist.py): the large tail as soon as the net3DV_3 backward is
+        # done, the small head after the net3DV_1 backward
         sizes = [p.numel() for p in params[:30]]
         self.flat = torch.zeros(sum(sizes) + 4, dtype=torch.float32, device=dev)
-        self.grads, off = [], 0
+        self.flat_l1_end = 4 + sum(sizes[:12])
+        self.grads, off = [], 4
         for p, n in zip(params[:30], sizes):
             self.grads.append(self.flat[off: off + n].view_as(p))
             off += n
@@ -127,17 +130,8 @@ class FusedTrainStep:
             gs.dw[l], gs.db[l], gs.dgamma[l], gs.dbeta[l] = (t.data_ptr() for t in self.grads[4 * l: 4 * l + 4])
         gs.dfc3_w, gs.dfc3_b = self.grads[28].data_ptr(), self.grads[29].data_ptr()
         self.grads_struct = gs
-        opt = trainer.optimizer
-        recs = []
-        import struct
-        for p, g in zip(params[:30], self.grads):
-            st = opt.state[p]
-            if not st:
-                st["exp_avg"] = torch.zeros_like(p)
-                st["exp_avg_sq"] = torch.zeros_like(p)
-            recs.append(struct.pack("<QQQQq", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
-                                    st["exp_avg_sq"].data_ptr(), p.numel()))
-        self.adam_table = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(dev)
+        self._params30 = params[:30]
+        self._adam_key = None
         f32 = dict(dtype=torch.float32, device=dev)
         self.staging = torch.empty((B, G, N, 4), **f32)
         self.clouds = torch.empty((M, N, 4), **f32)
@@ -150,7 +144,6 @@ class FusedTrainStep:
         self.loss2 = torch.zeros(3, **f32)
         self.loss_ws = torch.empty(_lib.lib().facl_contrast_workspace_bytes(G, B, 1, 512), dtype=torch.uint8, device=dev)
         self.order_dev = torch.zeros(G, dtype=torch.int32, device=dev)
-        self.order_ring = [torch.zeros(G, dtype=torch.int32).pin_memory() for _ in range(16)]
         self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         self.r2 = r2
         self.pending_bn_steps = 0
@@ -163,9 +156,69 @@ class FusedTrainStep:
         a.x, a.x_global, a.order, a.loss_ws, a.loss2 = (t.data_ptr() for t in (self.x, self.xg, self.order_dev, self.loss_ws,
                                                                                  self.loss2))
         a.dx, a.dx_global = self.dx.data_ptr(), self.dxg.data_ptr()
-        a.adam_table, a.adam_ntensors = self.adam_table.data_ptr(), 30
         a.beta1, a.beta2, a.eps = 0.5, 0.999, 1e-6
+        a.order_by_value = 1
         self.args = a
+        self._bind_adam_state()
+
+    def _bind_adam_state(self):
+        """(Re)build the device table of (param, grad, exp_avg, exp_avg_sq, numel) records.  The optimiser's moment tensors are
+        replaced by `optimizer.load_state_dict` (checkpoint resume): the table is rebuilt whenever they moved."""
+        import struct
+        opt = self.tr.optimizer
+        recs, key = [], []
+        for p, g in zip(self._params30, self.grads):
+            st = opt.state[p]
+            if "exp_avg" not in st:
+                st["exp_avg"] = torch.zeros_like(p)
+                st["exp_avg_sq"] = torch.zeros_like(p)
+            key.append((st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()))
+            recs.append(struct.pack("<QQQQq", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
+                                    st["exp_avg_sq"].data_ptr(), p.numel()))
+        self.adam_table = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(self.staging.device)
+        self._adam_key = key
+        self.args.adam_table, self.args.adam_ntensors = self.adam_table.data_ptr(), 30
+
+    def _adam_state_moved(self):
+        opt = self.tr.optimizer
+        for p, k in zip(self._params30, self._adam_key):
+            st = opt.state[p]
+            if "exp_avg" not in st or (st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()) != k:
+                return True
+        return False
+
+    def _begin_step(self, batch, order, want_host_loss):
+        """Argument block of one step: batch pointer, the view permutation BY VALUE, learning rate, step count."""
+        if tuple(batch.shape) != self.shape or batch.dtype != torch.float32:
+            raise self._lib.FaclError(f"batch must be float32 {self.shape}")
+        dev_copy, pf_slot = self._take_prefetched(batch)
+        if dev_copy is not None:
+            batch = dev_copy
+        tr = self.tr
+        G = self.shape[1]
+        if order is None:                                    # cn3d_train_motion_GL.py:297-298 (same seed on every rank -> same draw)
+            order = np.arange(0, G, 1)
+            tr.rng.shuffle(order)
+        order = [int(v) for v in order]
+        if sorted(order) != list(range(G)):
+            raise self._lib.FaclError(f"order must be a permutation of range({G})")
+        opt = tr.optimizer
+        if self._adam_state_moved():
+            self._bind_adam_state()
+        opt._step += 1
+        a = self.args
+        for i, v in enumerate(order):
+            a.order_vals[i] = v
+        if batch.is_cuda:
+            a.points_bgnd, a.points_host = batch.data_ptr(), None
+        else:
+            if not batch.is_pinned():
+                raise self._lib.FaclError("host batches must be pinned (torch.Tensor.pin_memory)")
+            a.points_bgnd, a.points_host = None, batch.data_ptr()
+        a.lr = float(opt.param_groups[0]["lr"])
+        a.step = opt._step
+        a.loss_host = self.loss_host.data_ptr() if want_host_loss else None
+        return pf_slot
 
     def prefetch(self, batch):
         """Start the host->device copy of a PINNED (B, G, N, 4) batch on a side stream, so that it overlaps the step that is
@@ -204,32 +257,9 @@ class FusedTrainStep:
             self._pf_free[slot] = ev
 
     def step(self, batch, order=None, want_host_loss=False, next_batch=None):
-        if tuple(batch.shape) != self.shape or batch.dtype != torch.float32:
-            raise self._lib.FaclError(f"batch must be float32 {self.shape}")
-        dev_copy, pf_slot = self._take_prefetched(batch)
-        if dev_copy is not None:
-            batch = dev_copy
-        tr = self.tr
-        G = self.shape[1]
-        if order is None:
-            order = np.arange(0, G, 1)
-            tr.rng.shuffle(order)
-        opt = tr.optimizer
-        opt._step += 1
-        slot = self.order_ring[opt._step % len(self.order_ring)]
-        slot.copy_(torch.from_numpy(np.asarray(order, dtype=np.int32)))
-        self.order_dev.copy_(slot, non_blocking=True)
-        a = self.args
-        if batch.is_cuda:
-            a.points_bgnd, a.points_host = batch.data_ptr(), None
-        else:
-            if not batch.is_pinned():
-                raise self._lib.FaclError("host batches must be pinned (torch.Tensor.pin_memory)")
-            a.points_bgnd, a.points_host = None, batch.data_ptr()
-        a.lr = float(opt.param_groups[0]["lr"])
-        a.step = opt._step
-        a.loss_host = self.loss_host.data_ptr() if want_host_loss else None
-        self._lib.check(self._lib.lib().facl_train_step(self.C.byref(a), self._lib.stream_ptr()), "facl_train_step")
+        pf_slot = self._begin_step(batch, order, want_host_loss)
+        self.args.phases = 0
+        self._lib.check(self._lib.lib().facl_train_step(self.C.byref(self.args), self._lib.stream_ptr()), "facl_train_step")
         self._release_prefetched(pf_slot)
         if next_batch is not None:
             self.prefetch(next_batch)

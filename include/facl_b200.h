@@ -272,6 +272,7 @@ FACL_API int facl_contrast_losses(const float* x, const float* x_global, const f
  * cn3d_train_apperance_GL.py): G-major flatten (:225-226) -> H2D (:228) -> group_points_3DV (:230) -> netR (:234)
  * -> global loss (:265-287) -> circle loss (:290-316) -> backward + Adam step (:329-332) -> loss.item() (:335).
  * All scratch is caller-owned.  loss2: device float[3] = {global, circle, total}. */
+#define FACL_MAX_VIEWS 256           /* G <= 255: the sequence max-pool records its winning view in one byte */
 typedef struct facl_train_step_args {
     const facl_encoder_dims* dims;
     const facl_encoder_params* params;
@@ -287,7 +288,7 @@ typedef struct facl_train_step_args {
     float* centres;                  /* device (G*B*S,3) scratch */
     float* x;                        /* device (G*B,512) */
     float* x_global;                 /* device (B,512) */
-    const int* order;                /* device int32[G]: view permutation of the circle loss */
+    int* order;                      /* device int32[G]: view permutation of the circle loss (read; written first when order_by_value) */
     void* loss_ws;                   /* facl_contrast_workspace_bytes(G,B,512) */
     float* loss2;                    /* device float[3] */
     float* dx;                       /* device (G*B,512) scratch */
@@ -304,6 +305,11 @@ typedef struct facl_train_step_args {
     const float* keys;               /* all-gathered x of every rank, rank-major (NULL = x) */
     float* dkeys;                    /* (world*G*B_local,512): key-side gradient, to be sum-reduce-scattered */
     const float* dx_extra;           /* (G*B_local,512): this rank's slice of the reduced dkeys, added to dx */
+    /* --- the view permutation passed BY VALUE: the reference draws it on the host every step (np.random.shuffle,
+     * cn3d_train_motion_GL.py:297-298); carried in the launch arguments it needs no host staging buffer whose reuse
+     * could race with a pending asynchronous copy --- */
+    int order_by_value;              /* non-zero: the LOSS phase first writes order_vals[0..G) into `order` */
+    int order_vals[FACL_MAX_VIEWS];
 } facl_train_step_args;
 
 #define FACL_PHASE_FORWARD 1         /* H2D, G-major flatten, grouping, encoder forward  -> x, x_global */
@@ -311,6 +317,8 @@ typedef struct facl_train_step_args {
 #define FACL_PHASE_BACKWARD 4        /* dx += dx_extra; encoder backward -> parameter gradients */
 #define FACL_PHASE_UPDATE 8          /* Adam step, loss D2H */
 #define FACL_PHASE_ALL 15
+#define FACL_PHASE_BACKWARD_HEAD 16  /* first half of BACKWARD: dx += dx_extra; head + net3DV_3 -> all gradients but net3DV_1's */
+#define FACL_PHASE_BACKWARD_L1 32    /* second half of BACKWARD: net3DV_1 (the all-reduce of the rest can run beside it) */
 
 FACL_API int facl_gmajor(const float* points_bgnd, float* clouds, int B, int G, int N, void* stream);
 FACL_API int facl_train_step(const facl_train_step_args* args, void* stream);

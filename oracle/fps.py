@@ -39,10 +39,12 @@ def farthest_point_sampling(pc, sample_num, start):
 
 
 def fps_reorder_indices(picks, n):
-    """Row permutation of cn3D_data_set.py:669-670: picks first, the rest ascending."""
+    """Row permutation of cn3D_data_set.py:669-671: picks first, the rest ascending, truncated to n rows
+    (`new_idx[:NUM_POINT]`: repeated picks -- a cloud with fewer than m distinct points -- leave more than
+    n - m unpicked rows)."""
     mask = np.ones(n, dtype=bool)
     mask[picks] = False
-    return np.concatenate([np.asarray(picks, dtype=np.int64), np.flatnonzero(mask)])
+    return np.concatenate([np.asarray(picks, dtype=np.int64), np.flatnonzero(mask)])[:n]
 
 
 def fps_sample_data(points, sample_num, starts):

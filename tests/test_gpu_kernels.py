@@ -52,6 +52,33 @@ def test_fps_vs_oracle_batched(N, m):
         assert np.array_equal(re[v], want), f"reorder cloud {v}"
 
 
+def test_fps_reorder_with_repeated_picks():
+    """Clouds with fewer than m distinct points (resampled with replacement, cn3D_data_set.py:287): picks repeat, the tail is
+    truncated at N rows like the reference's new_idx[:NUM_POINT] (:671); the LAST cloud of the batch must not write past the
+    output buffer and the following cloud must stay intact."""
+    rng = np.random.default_rng(5)
+    V, N, m = 3, 200, 64
+    pts = np.empty((V, N, 4), dtype=np.float32)
+    for v in range(V):
+        base = rng.random((7 + v, 4)).astype(np.float32)
+        pts[v] = base[rng.integers(0, base.shape[0], size=N)]
+    starts = np.array([0, 5, 199], dtype=np.int32)
+    dev = torch.from_numpy(pts).to(DEV)
+    picks = ops.fps(dev, m, torch.from_numpy(starts).to(DEV))
+    p = picks.cpu().numpy()
+    # guard rows behind the output: a tail overrun would land there
+    out_buf = torch.full((V * N + 64, 4), -7.0, device=DEV)
+    from facl_b200._lib import check, lib, ptr, stream_ptr
+    check(lib().facl_fps_reorder(ptr(dev), V, N, 4, ptr(picks), m, ptr(out_buf), stream_ptr()), "facl_fps_reorder")
+    got = out_buf.cpu().numpy()
+    assert np.all(got[V * N:] == -7.0)
+    for v in range(V):
+        want_p = oracle.farthest_point_sampling(pts[v, :, :3], m, int(starts[v]))
+        assert np.array_equal(p[v], want_p)
+        assert len(set(want_p.tolist())) < m
+        assert np.array_equal(got[v * N:(v + 1) * N], pts[v, oracle.fps_reorder_indices(want_p, N)]), f"cloud {v}"
+
+
 # ------------------------------------------------------------------------------------------------- grouping
 def test_group_golden(golden_dir):
     z = np.load(os.path.join(golden_dir, "group.npz"))

@@ -36,6 +36,22 @@ def test_fps_reorder():
         assert np.array_equal(out[v, 8:], pts[v, rest])
 
 
+def test_fps_reorder_fewer_distinct_points_than_picks():
+    """A cloud resampled with replacement from 5 distinct points: FPS repeats an index after 5 picks, and the
+    reference truncates concatenate(picks, setdiff1d(...)) to N rows (cn3D_data_set.py:669-671)."""
+    rng = np.random.default_rng(1)
+    base = rng.random((5, 4)).astype(np.float32)
+    pts = base[rng.integers(0, 5, size=40)][None]
+    picks = oracle.farthest_point_sampling(pts[0, :, :3], 16, 2)
+    assert len(set(picks.tolist())) < 16
+    idx = oracle.fps_reorder_indices(picks, 40)
+    other = np.setdiff1d(np.arange(40), picks.ravel())                 # the reference expression, verbatim semantics
+    want = np.concatenate((picks.ravel(), other))[:40]
+    assert idx.shape == (40,) and np.array_equal(idx, want)
+    out = oracle.fps_sample_data(pts, 16, [2])
+    assert out.shape == pts.shape and np.array_equal(out[0], pts[0, want])
+
+
 def test_grouping_matches_reference(golden_dir):
     z = np.load(os.path.join(golden_dir, "group.npz"))
     for name in z["names"]:
