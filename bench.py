@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 CFG2 = dict(B=64, G=20, N=2048, S=64, K=64, r2=0.16, precision="fp32")      # BASELINE.json configs[1]
+CFG3 = dict(B=256, G=20, N=2048, precision="bf16")                            # BASELINE.json configs[2] (global batch)
 CPU_SAMPLE = dict(B=8, G=20, N=2048)                                          # bounded CPU sample of the same workload
 
 
@@ -199,8 +200,8 @@ def run_ours(args):
     B, G, N = cfg["B"], cfg["G"], cfg["N"]
     opt = default_opt(batchSize=B, SAMPLE_NUM=N)
     tr = TrainStep(opt, num_crop=G, precision=cfg["precision"], radius2=cfg["r2"], device=f"cuda:{local_rank}", seed=1)
+    from facl_b200.dist import DistributedFusedTrainStep
     if world > 1:
-        from facl_b200.dist import DistributedFusedTrainStep
         fused = DistributedFusedTrainStep(tr, B, G, N, r2=cfg["r2"])
     else:
         fused = FusedTrainStep(tr, B, G, N, r2=cfg["r2"])
@@ -268,6 +269,85 @@ def run_ours(args):
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=2)
+
+    # ---- N > 1: is the sharded loss the loss of the global batch?  One more step with a known view order; the embeddings of
+    # every rank are gathered and rank 0 recomputes the losses through the world-size-1 facl_contrast_losses ----------------
+    dist_check = None
+    if dist is not None:
+        from facl_b200 import losses as facl_losses
+        from facl_b200.dist import reference_order_from_keys
+        order = synth.view_order(G, 9)
+        fused.step(dev[0], order=order)
+        sync_all()
+        xs = [torch.empty_like(fused.x) for _ in range(world)]
+        xgs = [torch.empty_like(fused.xg) for _ in range(world)]
+        dist.all_gather(xs, fused.x)
+        dist.all_gather(xgs, fused.xg)
+        if rank == 0:
+            x_ref = reference_order_from_keys(torch.cat(xs, 0), G, B * world, B)
+            lg, lc = facl_losses.contrast_losses(x_ref, torch.cat(xgs, 0), G, B * world, order=order)
+            single, sharded = float(lg) + float(lc), float(fused.loss2[2])
+            dist_check = dict(rel_err=abs(sharded - single) / abs(single), loss_sharded=sharded, loss_single_process=single,
+                              what="all-reduced loss of the sharded step vs facl_contrast_losses (world size 1) on the gathered embeddings")
+            del x_ref
+        del xs, xgs
+
+    # ---- the reference-shaped API path (N = 1): utils_my.group_points_3DV_2048 -> PointNet_Plus_fine -> contrast losses ->
+    # backward -> Adam through torch autograd, pinned host batch in, loss.item() out -- what a script gets after the two-line
+    # import swap of INTEGRATION.md, without the fused C-ABI step ------------------------------------------------------------
+    api_path = None
+    if dist is None and not args.no_api_path:
+        asteps = max(2, min(args.steps, 10))
+        order = synth.view_order(G, 9)
+        for i in range(2):
+            tr.step(host[i % nb], order=order)
+        sync_all()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ta = time.perf_counter()
+        a0.record()
+        for i in range(asteps):
+            _ = float(tr.step(host[i % nb], order=order))             # .item(): the reference loop's loss.item() (:335)
+        a1.record()
+        sync_all()
+        ams = max(a0.elapsed_time(a1), (time.perf_counter() - ta) * 1e3)
+        api_path = dict(value=B * asteps / (ams * 1e-3), unit="sequences/s", ms_per_step=ams / asteps, steps=asteps,
+                        what="TrainStep.step: reference-shaped module calls through torch autograd, host batch in, loss.item() out")
+
+    # ---- BASELINE configs[2]: appearance stream, bf16, GLOBAL batch 256 sharded over the N ranks (strong scaling) ---------------
+    cfg3 = None
+    if not args.no_cfg3 and (B, G, N) == (CFG2["B"], CFG2["G"], CFG2["N"]) and CFG3["B"] % world == 0:
+        del fused, tr, dev
+        torch.cuda.empty_cache()
+        Bl3 = CFG3["B"] // world
+        opt3 = default_opt(batchSize=Bl3, SAMPLE_NUM=N)
+        tr3 = TrainStep(opt3, num_crop=G, precision="bf16", radius2=cfg["r2"], device=f"cuda:{local_rank}", seed=1)
+        if world > 1:
+            f3 = DistributedFusedTrainStep(tr3, Bl3, G, N, r2=cfg["r2"])
+        else:
+            f3 = FusedTrainStep(tr3, Bl3, G, N, r2=cfg["r2"])
+        dev3 = [torch.from_numpy(synth.make_sequences(Bl3, G, N, seed=300 + rank * 10 + i)).cuda() for i in range(2)]
+        w3, s3 = max(3, min(args.warmup, 5)), max(3, min(args.steps, 10))
+        for i in range(w3):
+            f3.step(dev3[i % 2])
+        sync_all()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(s3):
+            f3.step(dev3[i % 2])
+        c1.record()
+        sync_all()
+        cms = c0.elapsed_time(c1)
+        if dist is not None:
+            t = torch.tensor([cms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cms = float(t)
+        cfg3 = dict(value=CFG3["B"] * s3 / (cms * 1e-3), unit="sequences/s", ms_per_step=cms / s3, steps=s3, warmup=w3,
+                    global_batch=CFG3["B"], per_gpu_batch=Bl3, n_gpus=world, scaling="strong",
+                    dtype="bf16 (fp32 accumulate, fp32 BN statistics / loss / master weights)",
+                    workload=f"appearance-stream contrastive training, global batch {CFG3['B']} x {G} views x {N} pts, bf16, "
+                             f"B sharded over {world} GPU(s), all-gathered negatives (BASELINE configs[2])",
+                    loss_at_end=float(f3.loss2[2]))
+        del f3, tr3, dev3
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -341,7 +421,8 @@ def run_ours(args):
                          d2h_bytes_per_step=4, ms_per_step=e2e_ms / e2e_steps),
                 gpu_launches=int(launches), launches_per_step=launches / args.steps,
                 roofline=roof, step_tensor_tflops=step_tf, step_tensor_frac=step_tf / peaks["tensor_sustained"],
-                kernel_ms_per_step=kernel_ms, kernels=per_tag, cpu_baseline=cpu, clocks=sampler.summary())
+                kernel_ms_per_step=kernel_ms, kernels=per_tag, cpu_baseline=cpu, clocks=sampler.summary(),
+                api_path=api_path, cfg3_strong=cfg3, dist_loss_check=dist_check)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -358,6 +439,8 @@ def main():
     ap.add_argument("--N", type=int, default=None)
     ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-api-path", action="store_true")
+    ap.add_argument("--no-cfg3", action="store_true")
     ap.add_argument("--ref-batch", type=int, default=None, help="batch of the CPU reference arm (default: the configuration's 64)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -61,6 +61,7 @@ class _EncoderBase(nn.Module):
         self.mapping = nn.Linear(self.dim, self.num_clusters, bias=False)
         self.precision = "fp32"
         self.fused_l1 = True          # net3DV_1 as the fused kernels of csrc/l1_fused.cu
+        self.bf16_split_layers = ()   # bf16 mode: layers (0..6 = the seven conv/linear+BN layers) that keep the bf16x3 products
         self._ws = None
 
     # ---- plumbing -------------------------------------------------------------------------------------------
@@ -85,8 +86,11 @@ class _EncoderBase(nn.Module):
     def _flags(self, training, need_bwd):
         from ._lib import ENC_FUSED_L1
         K, S = self.knn_K, self.sample_num_level1
-        ok = (S * K) % 128 == 0 and K == 64                    # tile geometry of the fused kernels (tile = max-pool group)
-        return ENC_FUSED_L1 if (self.fused_l1 and ok) else 0
+        ok = (S * K) % 128 == 0 and K in (64, 128)             # tile geometry of the fused kernels (max-pool group = 1 or 2 tiles)
+        flags = ENC_FUSED_L1 if (self.fused_l1 and ok) else 0
+        for l in self.bf16_split_layers:
+            flags |= 1 << (8 + int(l))                       # FACL_ENC_SPLIT_LAYER(l)
+        return flags
 
     def _workspace(self, dims, device, backward):
         key = (dims.M, dims.S, dims.K, dims.G, bool(backward), dims.flags)

@@ -149,10 +149,16 @@ OperandSrc src2(const float* a, const float* b, long long ld, const float* c0, c
 // Arithmetic mode per layer.  nsplit 3 ("fp32" mode) everywhere, or in "bf16" mode: single-pass bf16 for the layers
 // that carry the FLOPs (1..5) and the split scheme for the ones that are free -- the 4-wide first layer and the
 // head, which runs on M + B rows only and sits behind a small-batch BatchNorm1d that amplifies rounding.
+// `ns` carries d->nsplit in its low byte and, above it, the FACL_ENC_SPLIT_LAYER mask of layers that keep the split scheme in
+// bf16 mode (mode_of() below).
 int layer_nsplit(int ns, int layer) {
-    if (ns == 3) return 3;
+    if ((ns & 0xFF) == 3) return 3;
+    if ((ns >> 8) & (1 << layer)) return 3;
     return (layer == 0 || layer >= 6) ? 3 : 1;
 }
+int mode_of(const facl_encoder_dims* d) { return d->nsplit | (((d->flags >> 8) & 0x1FF) << 8); }
+// the fused net3DV_1 kernels take one arithmetic mode for layers 1 and 2 together
+int l1_nsplit(int ns) { return (layer_nsplit(ns, 1) == 3 || layer_nsplit(ns, 2) == 3) ? 3 : 1; }
 
 int layer_nhl(int ns, int layer) { return layer_nsplit(ns, layer) == 3 ? 2 : 1; }
 
@@ -223,7 +229,7 @@ int check_dims(const facl_encoder_dims* d) {
 int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, const float* xt, const float* centres,
                     void* const* bufs, float* x, float* xg, float* x_nor, float* code, cudaStream_t st) {
     RUN(check_dims(d));
-    const int M = d->M, S = d->S, K = d->K, G = d->G, B = M / G, ns = d->nsplit, tr = d->training;
+    const int M = d->M, S = d->S, K = d->K, G = d->G, B = M / G, ns = mode_of(d), tr = d->training;
     const long long R3 = (long long)M * S, R1 = R3 * K, MB = M + B;
     if (R1 > 2147483647LL) return (int)cudaErrorInvalidValue;
     auto F = [&](int i) { return reinterpret_cast<float*>(bufs[i]); };
@@ -269,7 +275,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
                           s0.mean, s0.rstd, s0.scale, s0.shift, st));
         const int grid = l1_fused_grid(R1);
         if (tr)
-            RUN(l1_fwd_launch(false, xt, R1, K, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), p->layer[1].b, nullptr,
+            RUN(l1_fwd_launch(false, xt, R1, K, l1_nsplit(ns), L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), p->layer[1].b, nullptr,
                               nullptr, nullptr, nullptr, nullptr, 1, stats, nullptr, nullptr, nullptr, nullptr, 0, st));
         {
             const facl_layer& L = p->layer[1];
@@ -280,7 +286,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
         // the dense part of dW3 needs -- the backward then does not recompute them
         float* l1s = (tr && bufs[B_L1S]) ? F(B_L1S) : nullptr;
         if (l1s) FACL_CHECK(cudaMemsetAsync(l1s + L1S_H2, 0, sizeof(float) * (L1S_H1 - L1S_H2), st));
-        RUN(l1_fwd_launch(true, xt, R1, K, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), p->layer[1].b, s1.scale,
+        RUN(l1_fwd_launch(true, xt, R1, K, l1_nsplit(ns), L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), p->layer[1].b, s1.scale,
                           s1.shift, wp + wpack_offset(2), p->layer[2].b, p->layer[2].gamma, tr ? 1 : 0, F(B_STATS),
                           l1s ? l1s + L1S_H2 : nullptr, l1s ? l1s + L1S_S2 : nullptr, F(B_PCAT) + 3 * R3, tr ? U(B_ARG3) : nullptr, R3,
                           st));
@@ -306,7 +312,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     }
     {
         Slot s = bn_slot(bufs, 0);
-        GemmParams g = gemm_base(64, (int)R1, 64, ns);
+        GemmParams g = gemm_base(64, (int)R1, 64, layer_nsplit(ns, 1));
         g.tag = 3;
         set_packed_a(g, wp + wpack_offset(1), 64);
         g.b = src1(F(B_Z1), R1, s.scale, s.shift, lo0);
@@ -318,7 +324,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     }
     {
         Slot s = bn_slot(bufs, 1);
-        GemmParams g = gemm_base(256, (int)R1, 64, ns);
+        GemmParams g = gemm_base(256, (int)R1, 64, layer_nsplit(ns, 2));
         g.tag = 6;
         set_packed_a(g, wp + wpack_offset(2), 64);
         g.b = src1(F(B_Z2), R1, s.scale, s.shift, lo0);
@@ -420,7 +426,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
     RUN(check_dims(d));
     if (!d->training || (stages & 3) == 0) return (int)cudaErrorInvalidValue;
     const bool stage_hi = (stages & 1) != 0, stage_l1 = (stages & 2) != 0;
-    const int M = d->M, S = d->S, K = d->K, G = d->G, B = M / G, ns = d->nsplit;
+    const int M = d->M, S = d->S, K = d->K, G = d->G, B = M / G, ns = mode_of(d);
     const long long R3 = (long long)M * S, R1 = R3 * K, MB = M + B;
     auto F = [&](int i) { return reinterpret_cast<float*>(bufs[i]); };
     auto U = [&](int i) { return reinterpret_cast<unsigned char*>(bufs[i]); };
@@ -586,7 +592,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
     if (!stage_l1) return 0;
     if (d->flags & FACL_ENC_FUSED_L1) {
         // ---- L1 fused backward: activations recomputed from the 16-byte input rows (l1_fused.cu) ------------------------
-        if ((R1 % 64) != 0 || K != 64) return (int)cudaErrorInvalidValue;
+        if ((R1 % 64) != 0 || (K != 64 && K != 128)) return (int)cudaErrorInvalidValue;
         const uint8_t* wp = reinterpret_cast<const uint8_t*>(bufs[B_WPACK]);   // forward images of this step's weights
         const double* mom = reinterpret_cast<const double*>(vec + 1984);
         const facl_layer &L0 = p->layer[0], &L1 = p->layer[1], &L2 = p->layer[2];
@@ -596,12 +602,12 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
         // H2 / s2 (acc + L1S_H2 .. L1S_H1) were accumulated by pass B of the forward on these buffers
         FACL_CHECK(cudaMemsetAsync(acc + L1S_H1, 0, sizeof(float) * (L1S_ACC_END - L1S_H1), st));
         RUN(l1_prep_launch(L2.w, 256, s2.c1, L2.b, s2.c2, nullptr, imgs, acc + L1S_Q3, nullptr, st));
-        RUN(l1_bwd_c_launch(xt, R1, ns, L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), L1.b, s1.scale, s1.shift,
-                            wp + wpack_offset(2), imgs, acc + L1S_Q3, U(B_ARG3), F(B_DP3), R3, s2.c0, bufs[B_DH2], gr->dw[2], stats, st));
+        RUN(l1_bwd_c_launch(xt, R1, l1_nsplit(ns), L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), L1.b, s1.scale, s1.shift,
+                            wp + wpack_offset(2), imgs, acc + L1S_Q3, U(B_ARG3), F(B_DP3), R3, s2.c0, bufs[B_DH2], gr->dw[2], stats, K, st));
         RUN(bwd_finalize(1, 1, 64, (int)R1, (double)R1, P, 0));
         RUN(l1_fin_launch(L2.w, 256, s2.c1, L2.b, s2.c2, acc + L1S_H2, acc + L1S_S2, nullptr, nullptr, gr->dw[2], 1, st));
         RUN(l1_prep_launch(L1.w, 64, s1.c1, L1.b, s1.c2, s1.c0, imgs + 32768, acc + L1S_Q2, imgs + 65536, st));
-        RUN(l1_bwd_d_launch(xt, R1, ns, L0.w, L0.b, s0.scale, s0.shift, imgs + 65536, imgs + 32768, acc + L1S_Q2, bufs[B_DH2],
+        RUN(l1_bwd_d_launch(xt, R1, l1_nsplit(ns), L0.w, L0.b, s0.scale, s0.shift, imgs + 65536, imgs + 32768, acc + L1S_Q2, bufs[B_DH2],
                             acc + L1S_DW2S, acc + L1S_H1, acc + L1S_S1, F(B_DH1), stats, st));
         RUN(bwd_finalize(0, 0, 64, (int)R1, (double)R1, 2 * P, 0));
         RUN(l1_fin_launch(L1.w, 64, s1.c1, L1.b, s1.c2, acc + L1S_H1, acc + L1S_S1, s1.c0, acc + L1S_DW2S, gr->dw[1], 0, st));

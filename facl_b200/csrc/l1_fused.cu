@@ -539,6 +539,7 @@ struct L1BwdParams {
     long long R;
     int nhl;
     int tiles_per_cta;        // contiguous tile range per CTA (multiple of 4)
+    int kshift;               // log2(K / 64): a max-pool group of K = 64 << kshift neighbours spans 1 << kshift consecutive tiles
     const float* w1;  const float* b1;  const float* scale1;  const float* shift1;
     // pass C
     const uint8_t* w2_img;  const float* b2;  const float* scale2;  const float* shift2;
@@ -926,28 +927,44 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         const int h = warp >> 2, lq = warp & 3;
         const int c = h * 128 + lq * 32 + lane;
         const float k0 = __ldg(p.c3_0 + c);
-        const float* dpp = p.dpooled + (long long)c * p.ldp + t0;
-        const unsigned char* argp = p.arg + (long long)c * p.ldp + t0;
+        // K = 64: group == tile.  K = 128 / 256: the group of tile t is t >> kshift and its winner (position 0..K-1 inside the
+        // group) lies in this tile iff (position >> 6) == (t & kmask); the other tiles of the group get a zero column
+        const int ksh = p.kshift, kmask = (1 << ksh) - 1;
+        const float* dpp = p.dpooled + (long long)c * p.ldp + (t0 >> ksh);
+        const unsigned char* argp = p.arg + (long long)c * p.ldp + (t0 >> ksh);
         uint8_t* row_hi = sps + c * 128;
         int prev = -1;
         float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
         uchar4 a4 = make_uchar4(0, 0, 0, 0);
+        float dcur = 0.f;
+        int acur = 0;
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
-            if ((it & 3) == 0) {
-                if (it + 4 <= my_tiles) {
-                    d4 = __ldg(reinterpret_cast<const float4*>(dpp + it));
-                    a4 = __ldg(reinterpret_cast<const uchar4*>(argp + it));
-                } else {
-                    d4.x = __ldg(dpp + it);
-                    a4.x = __ldg(argp + it);
-                    if (it + 1 < my_tiles) { d4.y = __ldg(dpp + it + 1); a4.y = __ldg(argp + it + 1); }
-                    if (it + 2 < my_tiles) { d4.z = __ldg(dpp + it + 2); a4.z = __ldg(argp + it + 2); }
+            float val;
+            int r;
+            if (ksh == 0) {
+                if ((it & 3) == 0) {
+                    if (it + 4 <= my_tiles) {
+                        d4 = __ldg(reinterpret_cast<const float4*>(dpp + it));
+                        a4 = __ldg(reinterpret_cast<const uchar4*>(argp + it));
+                    } else {
+                        d4.x = __ldg(dpp + it);
+                        a4.x = __ldg(argp + it);
+                        if (it + 1 < my_tiles) { d4.y = __ldg(dpp + it + 1); a4.y = __ldg(argp + it + 1); }
+                        if (it + 2 < my_tiles) { d4.z = __ldg(dpp + it + 2); a4.z = __ldg(argp + it + 2); }
+                    }
                 }
+                const int sel = it & 3;
+                val = k0 * (sel == 0 ? d4.x : sel == 1 ? d4.y : sel == 2 ? d4.z : d4.w);
+                r = (sel == 0 ? a4.x : sel == 1 ? a4.y : sel == 2 ? a4.z : a4.w) & 63;
+            } else {
+                if ((it & kmask) == 0) {
+                    dcur = __ldg(dpp + (it >> ksh));
+                    acur = __ldg(argp + (it >> ksh));
+                }
+                r = acur & 63;
+                val = ((acur >> 6) == (it & kmask)) ? k0 * dcur : 0.f;
             }
-            const int sel = it & 3;
-            const float val = k0 * (sel == 0 ? d4.x : sel == 1 ? d4.y : sel == 2 ? d4.z : d4.w);
-            const int r = (sel == 0 ? a4.x : sel == 1 ? a4.y : sel == 2 ? a4.z : a4.w) & 63;
             const __nv_bfloat16 vh = __float2bfloat16_rn(val);
             const __nv_bfloat16 vl = __float2bfloat16_rn(val - __bfloat162float(vh));
             const int off = ((((r >> 3) ^ (c & 7)) << 4) | ((r & 7) << 1));
@@ -1528,9 +1545,9 @@ int l1_fin_launch(const float* W, int C, const float* d, const float* bias, cons
 int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1,
                     const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
                     const void* w3_img, const void* p3_img, const float* q3, const unsigned char* arg, const float* dpooled,
-                    long long ldp, const float* c3_0, void* dh2, float* dw3, float* stats,
+                    long long ldp, const float* c3_0, void* dh2, float* dw3, float* stats, int K,
                     cudaStream_t st) {
-    if (R <= 0 || R % BT != 0 || ldp % 4 != 0) return (int)cudaErrorInvalidValue;
+    if (R <= 0 || R % BT != 0 || ldp % 4 != 0 || (K != 64 && K != 128 && K != 256) || R % K != 0) return (int)cudaErrorInvalidValue;
     static DeviceOnce configured;
     if (configured.need()) {
         FACL_CHECK(cudaFuncSetAttribute(l1_bwd_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l1_bwd_c_smem()));
@@ -1541,6 +1558,7 @@ int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, c
     p.w2_img = reinterpret_cast<const uint8_t*>(w2_img); p.b2 = b2; p.scale2 = scale2; p.shift2 = shift2;
     p.w3_img = reinterpret_cast<const uint8_t*>(w3_img); p.p3_img = reinterpret_cast<const uint8_t*>(p3_img); p.q3 = q3;
     p.arg = arg; p.dpooled = dpooled; p.ldp = ldp; p.c3_0 = c3_0;
+    p.kshift = K == 64 ? 0 : (K == 128 ? 1 : 2);
     p.dh2 = reinterpret_cast<uint8_t*>(dh2); p.dw3 = dw3; p.gram = nullptr; p.hsum = nullptr; p.stats = stats;
     p.dbg_mask1 = g_dbg_mask1; p.dbg_mask2 = g_dbg_mask2;
     ScopedTimer timer(TAG_L1_PASS_C, st);

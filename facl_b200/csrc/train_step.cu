@@ -101,7 +101,7 @@ int facl_train_step(const facl_train_step_args* a, void* stream) {
             set_order_kernel<<<1, FACL_MAX_VIEWS, 0, st>>>(ov, G, a->order);
             FACL_CHECK_LAUNCH();
         }
-        if ((rc = facl_contrast_losses(a->x, a->x_global, a->keys, G, Bglob, Bl, a->sample_offset, 512, a->order, 1, 1, d->nsplit,
+        if ((rc = facl_contrast_losses(a->x, a->x_global, a->keys, G, Bglob, Bl, a->sample_offset, 512, a->order, 1, 1, 3 /* the losses run the split products in both modes: see facl_contrast_losses */,
                                        a->loss_ws, a->loss2, a->dx, a->dx_global, dkeys, stream)))
             return rc;
         count_launch();

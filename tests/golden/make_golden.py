@@ -305,6 +305,70 @@ def gen_encoder_and_step():
     print("train_step.npz written")
 
 
+def gen_fine_geometry():
+    """PointNet_Plus_fine with its DEFAULT geometry (sample_num_level1=32, knn_K=128, cn3d_model_conbag.py:142): one training
+    step of the reference in fp32 and fp64 on a small batch grouped by utils_my.group_points_3DV_nums (:293-328).  Pins the
+    oracle -- and through it the CUDA path -- at a max-pool group that is not 64 wide."""
+    B, G, N, S, K = 2, 3, 256, 32, 128
+    r2 = 0.06
+    pts = synth.make_sequences(B, G, N, seed=310, skeleton=True)
+    order = synth.view_order(G, seed=2)
+    sd0 = oracle.init_state_dict(seed=13)
+    g = torch.Generator().manual_seed(6)
+    for k in sd0:
+        if k.endswith(".weight") and sd0[k].dim() == 1:
+            sd0[k] = 0.5 + torch.rand(sd0[k].shape, generator=g)
+            sd0[k][::5] *= -1.0
+        if k.endswith(".bias") and k.replace(".bias", ".running_mean") in sd0:
+            sd0[k] = 0.2 * (torch.rand(sd0[k].shape, generator=g) - 0.5)
+    opt = make_opt(B, N, S, K)
+    clouds = torch.from_numpy(pts).permute(1, 0, 2, 3).reshape(-1, N, 4).type(torch.FloatTensor)
+    xt, yt = ref_utils.group_points_3DV_nums(clouds, opt, S, K)
+    assert xt.shape == (G * B, 4, S, K) and opt.ball_radius == 0.06
+
+    def rel2(a, b):
+        a = a.double().reshape(-1)
+        b = b.double().reshape(-1)
+        return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+    def run_reference(dtype):
+        net = ref_model.PointNet_Plus_fine(opt, gost=G)                      # default sample_num_level1=32, knn_K=128
+        assert net.sample_num_level1 == S and net.knn_K == K
+        net.load_state_dict({k: v.clone() for k, v in sd0.items()})
+        net = net.to(dtype)
+        net.train()
+        x, code, x_nor, x_global = net(xt.to(dtype), yt.to(dtype), 1)
+        loss = oracle.circle_contrast(G, x, B, order) + oracle.global_contrast(G, x_global, x, B)   # pinned by gen_losses
+        loss.backward()
+        grads = {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in net.named_parameters()}
+        return dict(x=x.detach(), x_global=x_global.detach(), loss=float(loss), grads=grads)
+
+    r32, r64 = run_reference(torch.float32), run_reference(torch.float64)
+    osd = {k: (v.clone().double() if v.dtype.is_floating_point else v.clone()) for k, v in sd0.items()}
+    o64 = oracle.train_step(osd, torch.from_numpy(pts), order, S=S, K=K, r2=r2, dtype=torch.float64, apply_update=False)
+    assert rel2(o64["x"], r64["x"]) < 1e-9 and rel2(o64["x_global"], r64["x_global"]) < 1e-9
+    assert abs(o64["loss"] - r64["loss"]) < 1e-9 * abs(r64["loss"])
+    gscale = max(float(v.abs().max()) for v in r64["grads"].values())
+    out = dict(points=pts, order=order, cfg=np.array([B, G, N, S, K]), r2=np.array(r2), seed_sd=np.array(13),
+               x64=r64["x"].numpy(), x_global64=r64["x_global"].numpy(), loss64=np.array(r64["loss"]), loss=np.array(r32["loss"]))
+    for k, v in sd0.items():
+        if v.dim() <= 1:
+            out["sd0/" + k] = v.numpy()
+    for k, gref in r64["grads"].items():
+        og = o64["grads"][k].reshape(gref.shape)
+        if float(gref.norm()) < 1e-9 * gscale * gref.numel() ** 0.5:
+            assert float(og.abs().max()) < 1e-9 * gscale, k
+        else:
+            assert rel2(og, gref) < 1e-8, (k, rel2(og, gref))
+        pos = sample_positions(gref.shape, 256, seed=5)
+        out["grad_pos/" + k] = pos
+        out["grad64_val/" + k] = gref.reshape(-1).numpy()[pos]
+        out["grad64_norm/" + k] = np.array(float(gref.norm()))
+        out["noise/" + k] = np.array(rel2(r32["grads"][k], gref))
+    np.savez_compressed(os.path.join(HERE, "fine_geometry.npz"), **out)
+    print("fine_geometry.npz written; fp32 noise x", rel2(r32["x"], r64["x"]), "loss", r32["loss"], r64["loss"])
+
+
 def gen_losses():
     """Loss-only fixtures at a few (G,B,C) with larger magnitudes (values reach hundreds)."""
     out = {}
@@ -507,3 +571,4 @@ if __name__ == "__main__":
     gen_group()
     gen_losses()
     gen_encoder_and_step()
+    gen_fine_geometry()

@@ -28,8 +28,8 @@ DEV = "cuda"
 # (oracle.encoder_forward(routing=...)), where the comparison is smooth; the decisions themselves are validated by
 # the forward checks (a wrong winner or mask would show up in x / loss).
 TOL = {"fp32": 1e-3, "bf16": 2e-2}
-TOL_FEAT = {"fp32": 1e-3, "bf16": 5e-2}
-TOL_GRAD = {"fp32": 1e-3, "bf16": 1.5e-1}
+TOL_FEAT = {"fp32": 1e-3, "bf16": 2e-2}
+TOL_GRAD = {"fp32": 1e-3, "bf16": 2e-2}
 
 
 def make_opt(B, N, S=64, K=64):
@@ -107,6 +107,8 @@ def test_train_step_vs_golden_and_oracle(golden_dir, prec):
     xt, yt = utils_my.group_points_3DV(clouds, opt)
     assert xt.shape == (G * B, 4, S, K) and yt.shape == (G * B, 3, S, 1)
     x, code, x_nor, x_global = net(xt, yt, 1)
+    x.retain_grad()
+    x_global.retain_grad()
     lg, lc = facl_losses.contrast_losses(x, x_global, G, B, order=z["order"], prec=prec)
     loss = lc + lg
     loss.backward()
@@ -117,8 +119,15 @@ def test_train_step_vs_golden_and_oracle(golden_dir, prec):
     sd64 = {k: (v.clone().double() if v.dtype.is_floating_point else v.clone()) for k, v in sd0.items()}
     o64 = oracle.train_step(sd64, pts, z["order"], S=S, K=K, r2=float(z["r2"]), apply_update=False, dtype=torch.float64)
     sdr = {k: (v.clone().double() if v.dtype.is_floating_point else v.clone()) for k, v in sd0.items()}
+    # fp32 mode: the whole step is compared (loss gradient included).  bf16 mode: STAGE-WISE -- the oracle back-propagates the
+    # upstream gradient the CUDA path actually used.  The reference loss has temperature 1 on un-normalised dot products
+    # (logits of magnitude ~500, utils_my.py:72-82): a 1 % embedding error moves a logit by ~5 and a softmax weight by e^5, so
+    # gradients of the two END-TO-END runs cannot agree to 2e-2 in ANY 8-bit-mantissa arithmetic; what bf16 mode is held to
+    # is each stage within 2e-2 given identical inputs (the loss stage runs the split products in both modes and is checked
+    # against the reference fixture in test_losses_golden).
+    upstream = None if prec == "fp32" else (x.grad.detach().cpu(), x_global.grad.detach().cpu())
     ort = oracle.train_step(sdr, pts, z["order"], S=S, K=K, r2=float(z["r2"]), apply_update=False, dtype=torch.float64,
-                            routing=routing)
+                            routing=routing, upstream=upstream)
 
     # forward: features and loss, against the reference fixture (fp64 run of the reference) and the fp64 oracle
     ft = TOL_FEAT[prec]
@@ -154,6 +163,31 @@ def test_train_step_vs_golden_and_oracle(golden_dir, prec):
         worst = max(worst, err)
     print("\n" + "\n".join(f"{k:24s} matched-decisions err {e:.2e}   free-running err {f:.2e}" for k, e, f in report))
     assert worst <= TOL_GRAD[prec], report
+    if prec != "fp32":
+        return
+    # FREE-RUNNING gradients (no decisions imposed) against the reference's own fp64 gradients, held to the rule the fixture
+    # generator holds the CPU oracle to (tests/golden/make_golden.py: err < 6 * noise + 1e-5, noise = the reference's fp32-vs-
+    # fp64 deviation of that tensor, stored as noise/*): (i) whole tensors against the fp64 oracle, which reproduces the
+    # reference's fp64 gradients to 1e-8 (asserted when the fixture was written); (ii) the 256 sampled entries per tensor the
+    # fixture stores from the reference run itself (grad64_val/*), sampled-entry rule of tests/test_oracle_golden.py (8 * noise)
+    free = []
+    for k, p in net.named_parameters():
+        if k == "mapping.weight" or p.grad is None:
+            continue
+        noise = float(z["noise/" + k])
+        got = p.grad.detach().double().cpu().reshape(-1)
+        if noise > 1.0:                                    # mathematically-zero gradients (bias in front of a train-mode BN)
+            assert float(got.abs().max()) <= 1e-4 * gscale, k
+            continue
+        e_full = rel2(p.grad, o64["grads"][k].reshape(p.shape))
+        rms = float(z["grad64_norm/" + k]) / np.sqrt(got.numel())
+        e_samp = float(np.sqrt(np.mean((got.numpy()[z["grad_pos/" + k]] - z["grad64_val/" + k]) ** 2)) / rms)
+        free.append((k, e_full, e_samp, noise))
+    print("\n" + "\n".join(f"{k:24s} free-running: vs fp64 oracle {a:.2e}  vs reference samples {b:.2e}  (reference fp32 noise {n:.2e})"
+                           for k, a, b, n in free))
+    for k, a, b, n in free:
+        assert a < 6 * n + 1e-5, (k, a, n)
+        assert b < 8 * n + 1e-5, (k, b, n)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -337,21 +371,26 @@ def test_fused_l1_training_forward(golden_dir, prec):
             assert int(v) == int(sd64[k])
 
 
-def _check_fused_backward(pts, sd0, order, B, G, N, S, K, r2, tol):
+def _check_fused_backward(pts, sd0, order, B, G, N, S, K, r2, tol, prec="fp32"):
     from facl_b200.debug import L1DecisionDump, routing_of_last_forward
     clouds = pts.permute(1, 0, 2, 3).reshape(-1, N, 4).to(DEV)
-    net, opt = _build(sd0, B, G, N, S, K, "fp32")
-    assert net.fused_l1
+    net, opt = _build(sd0, B, G, N, S, K, prec)
+    assert net.fused_l1 and (net._flags(True, True) & 1), "this geometry must run the fused net3DV_1 kernels"
     net.train()
-    xt, yt = utils_my.group_points_3DV(clouds, opt)
+    xt, yt = utils_my._group(clouds, S, K, r2)
     x, code, x_nor, xg = net(xt, yt, 1)
-    lg, lc = facl_losses.contrast_losses(x, xg, G, B, order=order, prec="fp32")
+    x.retain_grad()
+    xg.retain_grad()
+    lg, lc = facl_losses.contrast_losses(x, xg, G, B, order=order, prec=prec)
     with L1DecisionDump(G * B, S, K) as dump:
         (lg + lc).backward()
     routing = routing_of_last_forward(net, l1_dump=dump)
     sdr = {k: (v.clone().double() if v.dtype.is_floating_point else v.clone()) for k, v in sd0.items()}
-    ort = oracle.train_step(sdr, pts, order, S=S, K=K, r2=r2, apply_update=False, dtype=torch.float64, routing=routing)
-    assert rel2(x, ort["x"]) <= 1e-3 and abs(float(lg + lc) - ort["loss"]) <= 1e-3 * abs(ort["loss"])
+    # bf16 mode is checked stage-wise (see test_train_step_vs_golden_and_oracle): the oracle back-propagates the CUDA path's own dL/dx
+    upstream = None if prec == "fp32" else (x.grad.detach().cpu(), xg.grad.detach().cpu())
+    ort = oracle.train_step(sdr, pts, order, S=S, K=K, r2=r2, apply_update=False, dtype=torch.float64, routing=routing,
+                            upstream=upstream)
+    assert rel2(x, ort["x"]) <= TOL_FEAT[prec] and abs(float(lg + lc) - ort["loss"]) <= TOL[prec] * abs(ort["loss"])
     gscale = max(float(g.abs().max()) for g in ort["grads"].values())
     report = []
     for k, p in net.named_parameters():
@@ -378,6 +417,65 @@ def test_fused_l1_backward(golden_dir):
     z, sd0 = load_fixture(golden_dir)
     B, G, N, S, K = (int(v) for v in z["cfg"])
     _check_fused_backward(torch.from_numpy(z["points"]), sd0, z["order"], B, G, N, S, K, float(z["r2"]), TOL_GRAD["fp32"])
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_fine_default_geometry(golden_dir, fused):
+    """PointNet_Plus_fine's DEFAULT geometry, sample_num_level1 = 32 and knn_K = 128 (cn3d_model_conbag.py:142): a max-pool group
+    spans two 64-row tiles of the fused net3DV_1 backward.  Features / loss against the reference's fp64 run (fixture
+    fine_geometry.npz), gradients against the fp64 oracle under the CUDA path's own discrete decisions; fused and per-layer."""
+    from facl_b200.debug import L1DecisionDump, routing_of_last_forward
+    z = np.load(os.path.join(golden_dir, "fine_geometry.npz"))
+    sd0 = oracle.init_state_dict(seed=int(z["seed_sd"]))
+    for k in list(sd0):
+        if "sd0/" + k in z.files:
+            sd0[k] = torch.from_numpy(z["sd0/" + k]).clone()
+    B, G, N, S, K = (int(v) for v in z["cfg"])
+    pts, order, r2 = torch.from_numpy(z["points"]), z["order"], float(z["r2"])
+    opt = make_opt(B, N, S, K)
+    net = MODELL.PointNet_Plus_fine(opt, gost=G)                               # default arguments: S1 = 32, K = 128
+    assert (net.sample_num_level1, net.knn_K) == (S, K) == (32, 128)
+    net.load_state_dict({k: v.clone() for k, v in sd0.items()})
+    net = net.to(DEV)
+    net.fused_l1 = fused
+    assert bool(net._flags(True, True) & 1) == fused
+    net.train()
+    clouds = pts.permute(1, 0, 2, 3).reshape(-1, N, 4).to(DEV)
+    xt, yt = utils_my.group_points_3DV_nums(clouds, opt, S, K)
+    x, code, x_nor, xg = net(xt, yt, 1)
+    lg, lc = facl_losses.contrast_losses(x, xg, G, B, order=order)
+    if fused:
+        with L1DecisionDump(G * B, S, K) as dump:
+            (lg + lc).backward()
+        routing = routing_of_last_forward(net, l1_dump=dump)
+    else:
+        (lg + lc).backward()
+        torch.cuda.synchronize()
+        routing = routing_of_last_forward(net)
+    assert rel2(x, z["x64"]) <= 1e-3 and rel2(xg, z["x_global64"]) <= 2e-3
+    assert abs(float(lg + lc) - float(z["loss64"])) <= 1e-3 * abs(float(z["loss64"]))
+    sdr = {k: (v.clone().double() if v.dtype.is_floating_point else v.clone()) for k, v in sd0.items()}
+    ort = oracle.train_step(sdr, pts, order, S=S, K=K, r2=r2, apply_update=False, dtype=torch.float64, routing=routing)
+    gscale = max(float(g.abs().max()) for g in ort["grads"].values())
+    for k, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        ref = ort["grads"][k].reshape(p.shape)
+        if float(ref.norm()) <= 1e-9 * gscale * ref.numel() ** 0.5:
+            assert float(p.grad.abs().max()) <= 1e-4 * gscale, k
+            continue
+        rms_err = float((p.grad.detach().double().cpu().reshape(-1) - ref.double().reshape(-1)).norm()) / ref.numel() ** 0.5
+        assert rel2(p.grad, ref) <= 1e-3 or rms_err / gscale <= 1e-6, (k, rel2(p.grad, ref))
+
+
+def test_fused_l1_backward_bf16_8x20x2048():
+    """bf16 mode (the arithmetic of BASELINE configs[2]) at 8 sequences x 20 views x 2048 points: features and loss within 2e-2 of
+    the fp64 oracle, every parameter gradient within 2e-2 of the oracle's back-propagation of the same upstream gradient under
+    the same discrete decisions."""
+    from facl_b200 import synth
+    B, G, N, S, K = 8, 20, 2048, 64, 64
+    pts = torch.from_numpy(synth.make_sequences(B, G, N, seed=31))
+    _check_fused_backward(pts, oracle.init_state_dict(seed=12), synth.view_order(G, 5), B, G, N, S, K, 0.06, TOL_GRAD["bf16"], prec="bf16")
 
 
 @pytest.mark.parametrize("B", [8, 64])

@@ -139,6 +139,31 @@ def test_train_step_matches_reference(golden_dir):
             assert np.allclose(got, z["sd1_val/" + k], rtol=0, atol=2.5 * 3e-4), k   # |delta| <= lr per Adam step
 
 
+def test_fine_geometry_matches_reference(golden_dir):
+    """PointNet_Plus_fine's default geometry (sample_num_level1=32, knn_K=128, cn3d_model_conbag.py:142): the oracle against the
+    reference's fp64 run of one step (tests/golden/make_golden.py: gen_fine_geometry)."""
+    z = np.load(os.path.join(golden_dir, "fine_geometry.npz"))
+    sd = oracle.init_state_dict(seed=int(z["seed_sd"]))
+    for k in list(sd):
+        if "sd0/" + k in z.files:
+            sd[k] = torch.from_numpy(z["sd0/" + k]).clone()
+    B, G, N, S, K = (int(v) for v in z["cfg"])
+    assert (S, K) == (32, 128)
+    sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    res = oracle.train_step(sd64, torch.from_numpy(z["points"]), z["order"], S=S, K=K, r2=float(z["r2"]), dtype=torch.float64,
+                            apply_update=False)
+    rel2 = lambda a, b: float((torch.as_tensor(a).double().reshape(-1) - torch.as_tensor(b).double().reshape(-1)).norm() /
+                              torch.as_tensor(b).double().norm())
+    assert rel2(res["x"], z["x64"]) < 1e-9 and rel2(res["x_global"], z["x_global64"]) < 1e-9
+    assert abs(res["loss"] - float(z["loss64"])) < 1e-9 * abs(float(z["loss64"]))
+    for k, g in res["grads"].items():
+        ref = z["grad64_val/" + k]
+        got = g.reshape(-1).numpy()[z["grad_pos/" + k]]
+        scale = max(float(np.abs(ref).max()), 1e-30)
+        if float(z["grad64_norm/" + k]) > 0:
+            assert np.abs(got - ref).max() <= 1e-7 * scale + 1e-12, k
+
+
 def test_eval_forward_matches_reference(golden_dir):
     z, sd = _load_step_fixture(golden_dir)
     B, G, N, S, K = (int(v) for v in z["cfg"])
