@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfacl_b200.so")
+# FACL_LIB_PATH: load a diagnostic build of the same library instead (e.g. libfacl_b200_prof.so, `make -C facl_b200/csrc prof`)
+LIB_PATH = os.environ.get("FACL_LIB_PATH") or os.path.join(_HERE, "libfacl_b200.so")
 
 _lib = None
 

@@ -25,6 +25,16 @@ namespace facl {
 
 namespace {
 
+// -DFACL_PROFILE_ROLES: clock64 accounting of where every warp role of the backward passes spends its tile period (waits on
+// each mbarrier vs work), printed by one warp per role of CTA 1.  Diagnostic builds only (tools/role_profile.sh).
+#ifdef FACL_PROFILE_ROLES
+#define PROF_DECL(n) long long prof_[n]; for (int pi_ = 0; pi_ < n; ++pi_) prof_[pi_] = 0; long long prof_t_ = clock64();
+#define PROF_MARK(i) { const long long pt_ = clock64(); prof_[i] += pt_ - prof_t_; prof_t_ = pt_; }
+#else
+#define PROF_DECL(n)
+#define PROF_MARK(i)
+#endif
+
 constexpr int TILE = 128;                 // batch rows per tile
 constexpr uint32_t ACT_LBO = 8192;        // MN-major activation image: 64-row blocks 8 KB apart,
 constexpr uint32_t ACT_SBO = 1024;        //                            8-channel groups 1 KB apart (16 KB per half)
@@ -744,14 +754,18 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                     if (nhl == 2) umma_bf16_ts(d, a_lo + ks * 8, bd, idesc_mn, 1u);
                 }
             };
+            PROF_DECL(8)
             auto issue_z2 = [&](int it) {          // z2(it) = W2 h1(it): plain 3-term form, double-buffered accumulator
                 const int b = it & 1, u = (it >> 1) & 1;
                 mbar_wait(h1_full, it & 1);
+                PROF_MARK(3)
                 mbar_wait(&d2_empty[b], u ^ 1);
+                PROF_MARK(4)
                 tc_fence_after_sync();
                 mma_t_act64(tmem_base + 64 * b, w2_hi, w2_lo, h1, h1 + IMG64, nhl, idesc_mn, true);
                 umma_commit(h1_empty);
                 umma_commit(&d2_full[b]);
+                PROF_MARK(5)
             };
             issue_z2(0);
 #pragma unroll 1
@@ -759,13 +773,17 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 const int b = it & 1, u = (it >> 1) & 1;
                 const uint32_t h2 = smem_u32(h2s + b * 2 * IMG64);
                 mbar_wait(&h2_full[b], u);
+                PROF_MARK(0)
                 mbar_wait(sp_full, it & 1);
+                PROF_MARK(1)
                 tc_fence_after_sync();
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h)          // dW3s += Sp h2^T
                     mma_rows64(tmem_base + 256 + 64 * h, sp_hi + h * 16384, sp_lo + h * 16384, h2, h2 + IMG64, nhl, idesc_kk, it == 0);
+                PROF_MARK(2)
                 if (it + 1 < my_tiles) issue_z2(it + 1);
                 mbar_wait(dh_empty, (it & 1) ^ 1);
+                PROF_MARK(6)
                 tc_fence_after_sync();
 #pragma unroll 1
                 for (int ks = 0; ks < 16; ++ks) {   // dh2 = W3^T Sp: reduction over the 256 channels
@@ -778,8 +796,15 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 mma_w_b2(tmem_base + 128, p3_hi, p3_lo, h2, 8192, false);                                       // dh2 += P3 h2
                 umma_commit(dh_full);
                 umma_commit(&h2_empty[b]);
+                PROF_MARK(7)
             }
             umma_commit(fin_bar);
+#ifdef FACL_PROFILE_ROLES
+            if (blockIdx.x == 1)
+                printf("pass C nhl=%d MMA thread, cycles/tile: wait h2_full %lld | wait sp_full %lld | issue SpH %lld | wait h1_full %lld | wait d2_empty %lld | "
+                       "issue z2 %lld | wait dh_empty %lld | issue WSp+P3h2 %lld\n", nhl, prof_[0] / my_tiles, prof_[1] / my_tiles, prof_[2] / my_tiles,
+                       prof_[3] / my_tiles, prof_[4] / my_tiles, prof_[5] / my_tiles, prof_[6] / my_tiles, prof_[7] / my_tiles);
+#endif
         }
     } else if (warp == 10 || warp == 11 || warp == 14 || warp == 15) {
         // ---- x -> h1 producers ----
@@ -799,6 +824,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         const float4* xg = reinterpret_cast<const float4*>(p.xt) + t0 * BT;
         float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ptid < BT) xnext = __ldg(xg + ptid);
+        PROF_DECL(4)
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             float4* xtile = reinterpret_cast<float4*>(xs + (it & 1) * BT * 16);
@@ -807,11 +833,15 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 if (it + 1 < my_tiles) xnext = __ldg(xg + (long long)(it + 1) * BT + ptid);
             }
             named_bar_sync(1, 128);
+            PROF_MARK(0)
             mbar_wait(h1_empty, (it & 1) ^ 1);
+            PROF_MARK(1)
             produce_h1_tile64(xtile, h1s, nhl, ch, half, wx, wy, wz, ww, bf);
+            PROF_MARK(2)
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(h1_full);
+            PROF_MARK(3)
             if (p.dbg_mask1) {
                 for (int r = 0; r < 32; ++r) {
                     float4 x = xtile[half * 32 + r];
@@ -820,16 +850,23 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 }
             }
         }
+#ifdef FACL_PROFILE_ROLES
+        if (blockIdx.x == 1 && ptid == 0)
+            printf("pass C h1 producer, cycles/tile: x tile + bar %lld | wait h1_empty %lld | produce %lld | fence+arrive %lld\n",
+                   prof_[0] / my_tiles, prof_[1] / my_tiles, prof_[2] / my_tiles, prof_[3] / my_tiles);
+#endif
     } else if (warp == 8 || warp == 9 || warp == 12 || warp == 13) {
         // ---- z2 -> h2 = relu(bn2(z2)) image (thread = channel j) ----
         const int lg = warp & 1, colhalf = (warp >= 12) ? 1 : 0;
         const int j = lg * 32 + lane;
         const float a2 = __ldg(p.scale2 + j);
         const float c2 = fmaf(a2, __ldg(p.b2 + j), __ldg(p.shift2 + j));
+        PROF_DECL(4)
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
             mbar_wait(&d2_full[b], u);
+            PROF_MARK(0)
             tc_fence_after_sync();
             float z[32];
             tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(64 * b + colhalf * 32), z);
@@ -837,7 +874,9 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&d2_empty[b]);
+            PROF_MARK(1)
             mbar_wait(&h2_empty[b], u ^ 1);
+            PROF_MARK(2)
             uint8_t* img = h2s + b * 2 * IMG64;
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
@@ -849,11 +888,17 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&h2_full[b]);
+            PROF_MARK(3)
             if (p.dbg_mask2) {
                 for (int i = 0; i < 32; ++i)
                     p.dbg_mask2[((t0 + it) * 64 + j) * 64 + colhalf * 32 + i] = fmaf(a2, z[i], c2) > 0.f ? 1 : 0;
             }
         }
+#ifdef FACL_PROFILE_ROLES
+        if (blockIdx.x == 1 && warp == 8 && lane == 0)
+            printf("pass C h2 producer, cycles/tile: wait d2_full %lld | ld z2 + arrive %lld | wait h2_empty %lld | compute+store+fence+arrive %lld\n",
+                   prof_[0] / my_tiles, prof_[1] / my_tiles, prof_[2] / my_tiles, prof_[3] / my_tiles);
+#endif
     } else if (warp == 16 || warp == 17 || warp == 20 || warp == 21) {
         // ---- dh2 consumers (thread = channel j): + q3, ReLU2 mask, BN2 backward sums, masked gradient image -> HBM ----
         const int lg = warp & 1, colhalf = (warp >= 20) ? 1 : 0;
@@ -875,10 +920,12 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         const float c2 = fmaf(a2, b2, __ldg(p.shift2 + j));
         const float q3 = __ldg(p.q3 + j);
         float s_acc = 0.f, q_acc = 0.f;
+        PROF_DECL(5)
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
             mbar_wait(&d2_full[b], u);
+            PROF_MARK(0)
             tc_fence_after_sync();
             float z[32], g[32];
             tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(64 * b + colhalf * 32), z);
@@ -886,7 +933,9 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&d2_empty[b]);
+            PROF_MARK(1)
             mbar_wait(dh_full, it & 1);
+            PROF_MARK(2)
             tc_fence_after_sync();
             tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 + colhalf * 32), g);
             if (nhl == 2) {
@@ -904,6 +953,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(dh_empty);
+            PROF_MARK(3)
             uint8_t* out = p.dh2 + (t0 + it) * (2 * IMG64);
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
@@ -918,7 +968,13 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 }
                 store_img8(out, nhl, IMG64, j, colhalf * 4 + g8, v8);
             }
+            PROF_MARK(4)
         }
+#ifdef FACL_PROFILE_ROLES
+        if (blockIdx.x == 1 && warp == 16 && lane == 0)
+            printf("pass C dh2 consumer, cycles/tile: wait d2_full %lld | ld z2 + arrive %lld | wait dh_full %lld | ld dh2 + arrive %lld | mask+sums+global store %lld\n",
+                   prof_[0] / my_tiles, prof_[1] / my_tiles, prof_[2] / my_tiles, prof_[3] / my_tiles, prof_[4] / my_tiles);
+#endif
         float* st = p.stats + ((long long)(blockIdx.x * 2 + colhalf) * 64 + j) * 2;
         st[0] = s_acc;
         st[1] = q_acc;
@@ -938,6 +994,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         uchar4 a4 = make_uchar4(0, 0, 0, 0);
         float dcur = 0.f;
         int acur = 0;
+        PROF_DECL(3)
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             float val;
@@ -968,7 +1025,9 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             const __nv_bfloat16 vh = __float2bfloat16_rn(val);
             const __nv_bfloat16 vl = __float2bfloat16_rn(val - __bfloat162float(vh));
             const int off = ((((r >> 3) ^ (c & 7)) << 4) | ((r & 7) << 1));
+            PROF_MARK(0)
             mbar_wait(sp_empty, (it & 1) ^ 1);
+            PROF_MARK(1)
             if (prev >= 0) {
                 *reinterpret_cast<unsigned short*>(row_hi + prev) = 0;
                 *reinterpret_cast<unsigned short*>(row_hi + 32768 + prev) = 0;
@@ -979,7 +1038,13 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(sp_full);
+            PROF_MARK(2)
         }
+#ifdef FACL_PROFILE_ROLES
+        if (blockIdx.x == 1 && warp == 0 && lane == 0)
+            printf("pass C Sp producer, cycles/tile: loads+convert %lld | wait sp_empty %lld | write+fence+arrive %lld\n", prof_[0] / my_tiles,
+                   prof_[1] / my_tiles, prof_[2] / my_tiles);
+#endif
         // dW3s of this CTA's rows sits in TMEM: add it to the global gradient
         mbar_wait(fin_bar, 0);
         tc_fence_after_sync();

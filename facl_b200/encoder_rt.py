@@ -10,7 +10,7 @@ from ._lib import EncoderDims, EncoderGrads, EncoderParams, check, lib, stream_p
 # order of the parameter tensors handed to the autograd.Function: 7 x (w, b, gamma, beta), fc3_w, fc3_b, map_w
 LAYER_PREFIXES = [("net3DV_1", 0, 1), ("net3DV_1", 3, 4), ("net3DV_1", 6, 7),
                   ("net3DV_3", 0, 1), ("net3DV_3", 3, 4), ("net3DV_3", 6, 7), ("netR_FC", 0, 1)]
-NSPLIT = {"fp32": 3, "bf16": 1}
+NSPLIT = {"fp32": 3, "bf16": 1, "bf16_fast": 1}
 
 
 class EncoderWorkspace:

@@ -9,7 +9,7 @@ from ._lib import check, lib, stream_ptr
 
 # The losses run the bf16x3 split products in BOTH modes: they are < 1 % of the step's FLOPs, and their logits are un-normalised
 # dot products of magnitude ~500 with temperature 1 (utils_my.py:72-82) -- single bf16 products would move a logit by > 1.
-_PRECISION = {"fp32": 3, "bf16": 3}
+_PRECISION = {"fp32": 3, "bf16": 3, "bf16_fast": 3}
 precision = "fp32"      # module-level switch used by utils_my.global_contrast / circle_contrast
 
 _ws_cache = {}

@@ -18,17 +18,21 @@ DEV = "cuda"
 
 # Tolerances, measured as ||a-b||_2 / ||b||_2 per tensor against the fp64 oracle:
 #   fp32 mode (bf16x3 split products, fp32 accumulate): features, loss, gradients <= 1e-3   (north_star: <= 1e-3)
-#   bf16 mode (bf16 operands, fp32 accumulate, fp32 BN statistics): loss <= 2e-2, features <= 5e-2.  Eight chained
-#     bf16 layers with a BatchNorm in between accumulate ~3e-2 on the final embedding (each layer adds ~2^-9 per
-#     operand); the north_star's 2e-2 is met for the loss, the per-layer activations stay below 1.5e-2.
+#   bf16 mode: features, loss <= 2e-2 (north_star: <= 2e-2); gradients <= 2e-2 stage-wise (see below).  "bf16" is the MIXED
+#     mode: single bf16 products for net3DV_3 layers 2-3, the split products for net3DV_1 and the first net3DV_3 layer.
+#     tools/bf16_layers.py measured why: with every layer in single bf16 products ("bf16_fast") the embedding error is
+#     3.1e-2 at the fixture size and 4.4e-2 at 8 x 20 x 2048, 71 % of its variance from net3DV_1 layers 1-2 and 25 % from
+#     the 259-wide layer (their errors are amplified ~12x by the BatchNorms / max-pools downstream); keeping those three on
+#     the split path gives 9e-3 / 8e-3.  A CPU emulation of the reference's modules with bf16-rounded operands (what
+#     autocast computes) reproduces the 3.1e-2, so it is a property of 8-bit mantissas on this network, not of the kernels.
 # Gradients: the gradient of this network is a DISCONTINUOUS function of the activations -- a near-tie in a max-pool
 # moves the routed gradient to another row, an activation crossing zero flips a ReLU.  The reference's own fp32 run
 # differs from its fp64 run by up to 3e-3 on these inputs for that reason alone (tests/golden `noise/*`).  Gradient
 # parity is therefore asserted against the oracle evaluated with the SAME discrete decisions the CUDA forward took
 # (oracle.encoder_forward(routing=...)), where the comparison is smooth; the decisions themselves are validated by
 # the forward checks (a wrong winner or mask would show up in x / loss).
-TOL = {"fp32": 1e-3, "bf16": 2e-2}
-TOL_FEAT = {"fp32": 1e-3, "bf16": 2e-2}
+TOL = {"fp32": 1e-3, "bf16": 2e-2, "bf16_fast": 2e-2}
+TOL_FEAT = {"fp32": 1e-3, "bf16": 2e-2, "bf16_fast": 5e-2}      # bf16_fast: outside the bound by design, see cn3d_model_conbag.py
 TOL_GRAD = {"fp32": 1e-3, "bf16": 2e-2}
 
 
@@ -340,7 +344,7 @@ def test_sharded_losses_sum_to_global(golden_dir):
     assert rel2(dxg_all, z["dxg_0"]) <= 1e-3
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16_fast"])
 def test_fused_l1_training_forward(golden_dir, prec):
     """Training-mode forward through the fused net3DV_1 kernels (closed-form BN1 statistics, pass A, pass B): features
     and running statistics against the fp64 reference fixture, and against the per-layer GEMM schedule."""

@@ -41,7 +41,7 @@ def run(name, pts, sd0, S, K, r2):
             net = MODELL.PointNet_Plus_fine(opt, gost=G, sample_num_level1=S, knn_K=K)
             net.load_state_dict({k: v.clone() for k, v in sd0.items()})
             net = net.cuda()
-            net.precision = "bf16"
+            net.precision = "bf16_fast"
             net.bf16_split_layers = layers
             net.train()
             with torch.no_grad():
