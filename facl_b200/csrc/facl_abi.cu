@@ -83,7 +83,7 @@ int facl_gemm_stat_partials(int Md, int Nd) { return gemm_tc_ctas_per_mtile(Md, 
 
 int facl_gemm_tc(const facl_gemm* d, void* stream) {
     if (!d) return (int)cudaErrorInvalidValue;
-    GemmParams p;
+    GemmParams p{};
     p.Md = d->Md; p.Nd = d->Nd; p.Kd = d->Kd; p.nsplit = d->nsplit;
     p.a_mode = d->a_mode; p.b_mode = d->b_mode;
     p.a_packed = d->a_packed; p.a_packed_kblocks = d->a_packed_kblocks;

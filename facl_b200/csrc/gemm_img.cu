@@ -117,6 +117,120 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
             for (int t = 0; t < 8; ++t)
                 zn[t] = __ldg(reinterpret_cast<const float4*>(p.zin + (long long)(ch0 + 4 * t + tch) * p.ldz + n0p + tcol));
         };
+        if (EPI == 4 || EPI == 5) {
+            // ===== contrastive-loss epilogues (see LossEpi): thread = anchor row, S never leaves the chip =====
+            const LossEpi& L = p.loss;
+            const int a = L.row0 + c;                                   // anchor index in [0, Ml + Bl)
+            const int bloc = (a < L.Ml) ? (a % L.Bl) : (a - L.Ml);      // local sample of the anchor
+            const int nsmp = L.n0 + bloc;                               // its global sample: keys of that sample are masked
+            const int nr = nsmp / L.Bl, nb = nsmp - nr * L.Bl;
+            float run_m = -INFINITY, run_e = 0.f;                       // EPI 4: online log-sum-exp state
+            // EPI 5: the row's softmax constants
+            float lc = 0.f, pgv = 0.f;
+            const float* pgrow = nullptr;
+            int nextv = -1;
+            bool dead = !cvalid;
+            const float invB = 1.f / (float)L.B;
+            if (EPI == 5 && cvalid) {
+                lc = __ldg(L.lc + bloc);
+                if (a >= L.Ml) {
+                    pgrow = L.pg + (long long)bloc * L.G;
+                } else {
+                    const int io = __ldg(L.inv_order + a / L.Bl);
+                    if (io >= L.G - 1) {
+                        dead = true;                                    // the last view of the chain is never an anchor
+                    } else {
+                        pgv = __ldg(L.pg + (long long)bloc * L.G + io);
+                        nextv = __ldg(L.order + io + 1);
+                    }
+                }
+            }
+            const int nchunks = (mma_n + 31) / 32;
+            for (int it = 0; sched.get(it, p, w); ++it) {
+                const int buf = it & 1;
+                mbar_wait(&acc_full[buf], (it >> 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N_TILE);
+#pragma unroll 1
+                for (int cc = 0; cc < nchunks; ++cc) {
+                    float v[32];
+                    tmem_ld32(trow + cc * 32, v);
+                    tmem_ld_wait();
+                    const int n0 = w.nt * N_TILE + cc * 32;
+                    int nvalid = p.Nd - n0;
+                    nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
+                    // key j = jr*Ml + jg*Bl + jb, advanced incrementally (one division per 32 columns instead of per element)
+                    int jr = n0 / L.Ml;
+                    const int jm = n0 - jr * L.Ml;
+                    int jg = jm / L.Bl, jb = jm - jg * L.Bl;
+                    if (EPI == 4) {
+                        if (!cvalid || nvalid <= 0) continue;
+                        float cm = -INFINITY;
+                        unsigned masked = 0u;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (i < nvalid) {
+                                if (jr == nr && jb == nb) {
+                                    masked |= 1u << i;
+                                    L.pos[(long long)a * L.G + jg] = v[i];      // G masked columns per row: the positives are among them
+                                } else {
+                                    cm = fmaxf(cm, v[i]);
+                                }
+                            }
+                            if (++jb == L.Bl) { jb = 0; if (++jg == L.G) { jg = 0; ++jr; } }
+                        }
+                        if (cm > -INFINITY) {
+                            const float nm = fmaxf(run_m, cm);
+                            float ssum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nvalid && !((masked >> i) & 1u)) ssum[i & 3] += expf(v[i] - nm);
+                            run_e = run_e * expf(run_m - nm) + ((ssum[0] + ssum[1]) + (ssum[2] + ssum[3]));   // exp(-inf) = 0 on the first chunk
+                            run_m = nm;
+                        }
+                    } else {
+                        const int rb = n0 >> 6;
+                        if (c >= L.ds_cgs * 8 || rb >= L.ds_rbs) continue;       // outside the (padded) image
+                        uint8_t* atom = reinterpret_cast<uint8_t*>(L.ds_hi) + ((long long)rb * L.ds_cgs + (c >> 3)) * 1024;
+                        uint8_t* atom_lo = reinterpret_cast<uint8_t*>(L.ds_lo) + ((long long)rb * L.ds_cgs + (c >> 3)) * 1024;
+                        const int chunk0 = (n0 & 63) >> 3;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float o[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int i = q * 8 + e;
+                                float out = 0.f;
+                                if (!dead && i < nvalid) {
+                                    if (jr == nr && jb == nb) out = pgrow ? __ldg(pgrow + jg) : (jg == nextv ? pgv : 0.f);
+                                    else out = expf(v[i] + lc) * invB;
+                                }
+                                o[e] = out;
+                                if (++jb == L.Bl) { jb = 0; if (++jg == L.G) { jg = 0; ++jr; } }
+                            }
+                            const uint32_t off = sw128_offset((uint32_t)(c & 7), (uint32_t)(chunk0 + q));
+                            if (NHL == 2) {
+                                uint4 h, l;
+                                split_bf16x8(o, h, l);
+                                *reinterpret_cast<uint4*>(atom + off) = h;
+                                *reinterpret_cast<uint4*>(atom_lo + off) = l;
+                            } else {
+                                *reinterpret_cast<uint4*>(atom + off) = pack_bf16x8(o);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+            if (EPI == 4 && cvalid) {
+                const int pidx = blockIdx.x / sched.numMT;
+                float* st = L.part + ((long long)pidx * p.Md + c) * 2;
+                st[0] = run_m;
+                st[1] = run_e;
+            }
+        } else
         for (int it = 0; sched.get(it, p, w); ++it) {
             const int buf = it & 1;
             const int nchunks = (mma_n + 31) / 32;
@@ -285,6 +399,8 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
     } else if (warp == 4) {
         // =============================== MMA issuer ===============================
         const uint32_t idesc = umma_idesc_bf16(M_TILE, mma_n) | (b_k ? 0u : UMMA_B_MN_MAJOR);
+        const UDesc a_kd = udesc_k(smem_u32(a_ring)), b_kd = udesc_k(smem_u32(b_ring));
+        const UDesc b_mnd = udesc_mn(smem_u32(b_ring), IMG_LBO / 2, IMG_SBO);
         int sa = 0, pa = 0, sb = 0, pb = 0;
 #ifdef FACL_PROFILE_ROLES
         long long pm_acc = 0, pm_ops = 0, pm_t = clock64(), pm_t0 = pm_t;
@@ -307,22 +423,21 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
 #ifdef FACL_PROFILE_ROLES
                 { long long t = clock64(); pm_ops += t - pm_t; pm_t = t; }
 #endif
-                const uint32_t a_hi = smem_u32(a_ring + sa * A_SLOT), a_lo = a_hi + A_TILE_BYTES;
+                // descriptors: ring bases built once (above); slot, hi/lo half and k-step are offsets in 16-byte units (umma.cuh, lean issue path)
+                const uint32_t ao = (uint32_t)sa * (A_SLOT / 16);
                 if (b_k) {
                     // one full K-major B tile in a pair of half slots: [hi | lo]
                     mbar_wait(&b_full[sb], pb);
                     tc_fence_after_sync();
-                    if (lane == 0) {
-                        const uint32_t b_hi = smem_u32(b_ring + sb * B_SLOT), b_lo = b_hi + B_TILE_BYTES;
+                    if (elect_one_sync()) {
+                        const uint32_t bo = (uint32_t)sb * (B_SLOT / 16);
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint32_t acc = (kb > w.kb0 || ks > 0) ? 1u : 0u;
-                            const uint32_t ko = ks * 32;
-                            const uint64_t ad_hi = umma_desc_sw128(a_hi + ko), bd_hi = umma_desc_sw128(b_hi + ko);
-                            umma_bf16_ss(d_tmem, ad_hi, bd_hi, idesc, acc);
+                            umma_ss(d_tmem, a_kd, ao + ks * 2, b_kd, bo + ks * 2, idesc, acc);
                             if (NHL == 2) {
-                                umma_bf16_ss(d_tmem, ad_hi, umma_desc_sw128(b_lo + ko), idesc, 1u);
-                                umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ko), bd_hi, idesc, 1u);
+                                umma_ss(d_tmem, a_kd, ao + ks * 2, b_kd, bo + B_TILE_BYTES / 16 + ks * 2, idesc, 1u);
+                                umma_ss(d_tmem, a_kd, ao + A_TILE_BYTES / 16 + ks * 2, b_kd, bo + ks * 2, idesc, 1u);
                             }
                         }
                         umma_commit(&b_empty[sb]);
@@ -338,18 +453,16 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                     for (int h = 0; h < 2; ++h) {
                         mbar_wait(&b_full[sb], pb);
                         tc_fence_after_sync();
-                        if (lane == 0) {
-                            const uint32_t b_hi = smem_u32(b_ring + sb * B_SLOT), b_lo = b_hi + B_TILE_BYTES / 2;
+                        if (elect_one_sync()) {
+                            const uint32_t bo = (uint32_t)sb * (B_SLOT / 16);
+                            const uint32_t ah = ao + h * 4;                      // k-steps 2h, 2h + 1 of the A tile
 #pragma unroll
                             for (int k2 = 0; k2 < 2; ++k2) {
-                                const int ks = 2 * h + k2;
-                                const uint32_t acc = (kb > w.kb0 || ks > 0) ? 1u : 0u;
-                                const uint64_t ad_hi = umma_desc_sw128(a_hi + ks * 32);
-                                const uint64_t bd_hi = umma_desc_mn_sw128(b_hi + k2 * 2 * IMG_SBO, IMG_LBO / 2, IMG_SBO);
-                                umma_bf16_ss(d_tmem, ad_hi, bd_hi, idesc, acc);
+                                const uint32_t acc = (kb > w.kb0 || h > 0 || k2 > 0) ? 1u : 0u;
+                                umma_ss(d_tmem, a_kd, ah + k2 * 2, b_mnd, bo + k2 * (2 * IMG_SBO / 16), idesc, acc);
                                 if (NHL == 2) {
-                                    umma_bf16_ss(d_tmem, ad_hi, umma_desc_mn_sw128(b_lo + k2 * 2 * IMG_SBO, IMG_LBO / 2, IMG_SBO), idesc, 1u);
-                                    umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ks * 32), bd_hi, idesc, 1u);
+                                    umma_ss(d_tmem, a_kd, ah + k2 * 2, b_mnd, bo + (B_TILE_BYTES / 2) / 16 + k2 * (2 * IMG_SBO / 16), idesc, 1u);
+                                    umma_ss(d_tmem, a_kd, ah + A_TILE_BYTES / 16 + k2 * 2, b_mnd, bo + k2 * (2 * IMG_SBO / 16), idesc, 1u);
                                 }
                             }
                             umma_commit(&b_empty[sb]);
@@ -370,8 +483,8 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
             printf("gemm_img Md %d Nd %d Kd %d: mma tiles %d wait_acc_empty %lld wait_operands %lld total %lld (cycles/tile)\n", p.Md, p.Nd,
                    p.Kd, pm_n, pm_acc / pm_n, pm_ops / pm_n, (clock64() - pm_t0) / pm_n);
 #endif
-    } else if (lane == 0) {
-        // =============================== TMA issuer ===============================
+    } else if (elect_one_sync()) {
+        // =============================== TMA issuer (warp 5, one elected lane) ===============================
         int sa = 0, pa = 0, sb = 0, pb = 0;
         const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.a_packed);
         const uint8_t* ai_hi = reinterpret_cast<const uint8_t*>(p.a_img.hi);
@@ -558,8 +671,8 @@ int launch_gemm_img(const GemmParams& p, cudaStream_t stream) {
     if (configured.need()) {
 #define FACL_IMG_ATTR(N, E) \
         FACL_CHECK(cudaFuncSetAttribute(gemm_img_kernel<N, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        FACL_IMG_ATTR(1, 0) FACL_IMG_ATTR(1, 1) FACL_IMG_ATTR(1, 2) FACL_IMG_ATTR(1, 3)
-        FACL_IMG_ATTR(2, 0) FACL_IMG_ATTR(2, 1) FACL_IMG_ATTR(2, 2) FACL_IMG_ATTR(2, 3)
+        FACL_IMG_ATTR(1, 0) FACL_IMG_ATTR(1, 1) FACL_IMG_ATTR(1, 2) FACL_IMG_ATTR(1, 3) FACL_IMG_ATTR(1, 4) FACL_IMG_ATTR(1, 5)
+        FACL_IMG_ATTR(2, 0) FACL_IMG_ATTR(2, 1) FACL_IMG_ATTR(2, 2) FACL_IMG_ATTR(2, 3) FACL_IMG_ATTR(2, 4) FACL_IMG_ATTR(2, 5)
 #undef FACL_IMG_ATTR
         configured.done();
     }
@@ -592,16 +705,26 @@ int launch_gemm_img(const GemmParams& p, cudaStream_t stream) {
     // epilogue specialisation: the fast ones need full 32-channel warps, whole 32-column chunks and 16-byte aligned rows
     const bool tidy = (p.Md % 32 == 0) && (p.Nd % 32 == 0) && p.out && (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     int epi = 0;
-    if (p.out_mode == OUT_ATOMIC_CHMAJOR) epi = 3;
+    if (p.loss.mode) {
+        const LossEpi& L = p.loss;
+        if (p.ksplit > 1 || p.stats || p.pool || L.G <= 0 || L.Bl <= 0 || L.Ml != L.G * L.Bl || L.B % L.Bl != 0 || p.Nd % L.Ml != 0)
+            return (int)cudaErrorInvalidValue;
+        if (L.mode == 1 && (!L.part || !L.pos)) return (int)cudaErrorInvalidValue;
+        if (L.mode == 2 && (!L.lc || !L.pg || !L.ds_hi || (p.nsplit == 3 && !L.ds_lo) || (L.row0 == 0 && (!L.order || !L.inv_order))))
+            return (int)cudaErrorInvalidValue;
+        epi = L.mode == 1 ? 4 : 5;
+    } else if (p.out_mode == OUT_ATOMIC_CHMAJOR) epi = 3;
     else if (p.out_mode == OUT_CHMAJOR && tidy && !p.zin) epi = 1;
     else if (p.out_mode == OUT_CHMAJOR && tidy && p.zin && !p.pool && (p.ldz % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.zin) & 15) == 0)) epi = 2;
     ScopedTimer timer(p.tag, stream);
     count_launch();
 #define FACL_IMG_LAUNCH(N, E) gemm_img_kernel<N, E><<<grid, IMG_THREADS, smem_bytes, stream>>>(p)
     if (p.nsplit == 3) {
-        if (epi == 1) FACL_IMG_LAUNCH(2, 1); else if (epi == 2) FACL_IMG_LAUNCH(2, 2); else if (epi == 3) FACL_IMG_LAUNCH(2, 3); else FACL_IMG_LAUNCH(2, 0);
+        if (epi == 1) FACL_IMG_LAUNCH(2, 1); else if (epi == 2) FACL_IMG_LAUNCH(2, 2); else if (epi == 3) FACL_IMG_LAUNCH(2, 3);
+        else if (epi == 4) FACL_IMG_LAUNCH(2, 4); else if (epi == 5) FACL_IMG_LAUNCH(2, 5); else FACL_IMG_LAUNCH(2, 0);
     } else {
-        if (epi == 1) FACL_IMG_LAUNCH(1, 1); else if (epi == 2) FACL_IMG_LAUNCH(1, 2); else if (epi == 3) FACL_IMG_LAUNCH(1, 3); else FACL_IMG_LAUNCH(1, 0);
+        if (epi == 1) FACL_IMG_LAUNCH(1, 1); else if (epi == 2) FACL_IMG_LAUNCH(1, 2); else if (epi == 3) FACL_IMG_LAUNCH(1, 3);
+        else if (epi == 4) FACL_IMG_LAUNCH(1, 4); else if (epi == 5) FACL_IMG_LAUNCH(1, 5); else FACL_IMG_LAUNCH(1, 0);
     }
 #undef FACL_IMG_LAUNCH
     return (int)cudaGetLastError();

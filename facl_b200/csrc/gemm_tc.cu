@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p)
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after_sync();
-                if (lane == 0) {
+                if (elect_one_sync()) {            // elect.sync: ptxas then emits the bare UTCHMMA / UTCBAR (umma.cuh, lean issue path)
                     uint8_t* st = smem + stage * stage_bytes;
                     const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_TILE_BYTES;
                     const uint32_t b_hi = a_hi + A_TILE_BYTES * nhl, b_lo = b_hi + B_TILE_BYTES;

@@ -46,6 +46,29 @@ enum : int { B_ROWMAJOR = 1, B_CHMAJOR = 2, B_XT4 = 3, B_IMAGE_MN = 4, B_IMAGE_K
 enum : int { OUT_NONE = 0, OUT_CHMAJOR = 1, OUT_ROWMAJOR = 2, OUT_ATOMIC_CHMAJOR = 3, OUT_ROWMAJOR_ACC = 4,
               OUT_ATOMIC_ROWMAJOR = 5 /* gemm_img.cu only: atomicAdd out[n*ldo + m], for split-K */ };
 
+// Contrastive-loss epilogues of the similarity GEMM S = anchors x keys^T (gemm_img.cu, losses.cu).  The GEMM's rows (TMEM lanes)
+// are anchors, its columns keys; S itself is never written.
+//   mode 1 (forward) : per anchor row an ONLINE log-sum-exp over the unmasked columns -- running (max, sum exp) kept in the
+//                      epilogue thread across all tiles of its CTA, one partial per (CTA, row) -> part[cta][Md][2]; the masked
+//                      columns (keys of the anchor's own sample: the positives among them) are stored to pos[row][view]
+//   mode 2 (backward): S is recomputed and turned into dL/dS in registers (softmax weight of the negatives, the stored
+//                      coefficient at the positive, 0 at the other masked columns), written as a bf16 hi/lo operand image
+// Index conventions as in losses.cu `Idx`: key j = r*Ml + g*Bl + b is view g of sample r*Bl + b.
+struct LossEpi {
+    int mode;                   // 0 none
+    int G, B, Bl, Ml, n0;       // views, global batch, local batch, G*Bl, first global sample of this rank
+    int row0;                   // anchor index of GEMM row 0: 0 for the view anchors (S_x), Ml for the sequence anchors (S_g)
+    float* part;                // mode 1: [ctas per m-tile][Md][2]
+    float* pos;                 // mode 1: [(Ml + Bl)][G]
+    const float* lc;            // mode 2: lcC (row0 == 0) or lcG (row0 == Ml), per local sample
+    const float* pg;            // mode 2: pgC / pgG  [Bl][G]
+    const int* order;           // mode 2, circle rows
+    const int* inv_order;
+    void* ds_hi;                // mode 2: dS image [Md channels][Nd rows]
+    void* ds_lo;
+    int ds_cgs, ds_rbs;
+};
+
 struct GemmParams {
     int Md, Nd, Kd;
     int nsplit;                 // 1 (bf16) or 3 (bf16x3)
@@ -75,6 +98,7 @@ struct GemmParams {
     ActImage a_img;             // A_IMAGE: channels = m, reduction over the image's rows (weight-gradient GEMMs)
     ActImage b_img;             // B_IMAGE_MN: channels = k, rows = n (forward / data-gradient GEMMs);
                                 // B_IMAGE_K: channels = n, reduction over rows
+    LossEpi loss;               // loss.mode != 0: contrastive-loss epilogue instead of an output matrix
 };
 
 // bytes of one half (hi or lo) of an activation image of C channels x R rows

@@ -104,30 +104,28 @@ __device__ __forceinline__ void tmem_put_a_tile(uint32_t taddr, const uint8_t* i
     }
     tmem_st32(taddr, u);
 }
-// D[tmem] (+)= A (TMEM tile, 64-wide K) * B (MN-major activation image), all bf16 hi/lo combinations
-__device__ __forceinline__ void mma_tmem_weight_act(uint32_t d_tmem, uint32_t a_hi_t, uint32_t a_lo_t, uint32_t b_img, int nhl,
-                                                    uint32_t idesc) {
+// D[tmem] (+)= A (TMEM tile, 64-wide K) * B (MN-major activation image), all bf16 hi/lo combinations.
+// b = descriptor of the stage-0 hi image; boff = stage offset, b_lo = distance to the lo image (16-byte units)
+__device__ __forceinline__ void mma_tmem_weight_act(uint32_t d_tmem, uint32_t a_hi_t, uint32_t a_lo_t, UDesc b, uint32_t boff, uint32_t b_lo,
+                                                    bool split, uint32_t idesc) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t bd = umma_desc_mn_sw128(b_img + ks * 2 * ACT_SBO, ACT_LBO, ACT_SBO);
-        umma_bf16_ts(d_tmem, a_hi_t + ks * 8, bd, idesc, ks > 0 ? 1u : 0u);
-        if (nhl == 2) {
-            umma_bf16_ts(d_tmem, a_hi_t + ks * 8, umma_desc_mn_sw128(b_img + ACT_BYTES + ks * 2 * ACT_SBO, ACT_LBO, ACT_SBO), idesc, 1u);
-            umma_bf16_ts(d_tmem, a_lo_t + ks * 8, bd, idesc, 1u);
+        umma_ts(d_tmem, a_hi_t + ks * 8, b, boff + ks * 128, idesc, ks > 0 ? 1u : 0u);
+        if (split) {
+            umma_ts(d_tmem, a_hi_t + ks * 8, b, boff + b_lo + ks * 128, idesc, 1u);
+            umma_ts(d_tmem, a_lo_t + ks * 8, b, boff + ks * 128, idesc, 1u);
         }
     }
 }
 // D[tmem] (+)= A (K-major weight image, 64-wide K) * B (MN-major activation image), all bf16 hi/lo combinations
-__device__ __forceinline__ void mma_weight_act(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_img, int nhl, uint32_t idesc,
-                                               uint32_t lbo = ACT_LBO, uint32_t lo_off = ACT_BYTES) {
+__device__ __forceinline__ void mma_weight_act(uint32_t d_tmem, UDesc a, uint32_t aoff, uint32_t a_lo, UDesc b, uint32_t boff, uint32_t b_lo,
+                                               bool split, uint32_t idesc) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t ad = umma_desc_sw128(a_hi + ks * 32);
-        const uint64_t bd = umma_desc_mn_sw128(b_img + ks * 2 * ACT_SBO, lbo, ACT_SBO);
-        umma_bf16_ss(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
-        if (nhl == 2) {
-            umma_bf16_ss(d_tmem, ad, umma_desc_mn_sw128(b_img + lo_off + ks * 2 * ACT_SBO, lbo, ACT_SBO), idesc, 1u);
-            umma_bf16_ss(d_tmem, umma_desc_sw128(a_lo + ks * 32), bd, idesc, 1u);
+        umma_ss(d_tmem, a, aoff + ks * 2, b, boff + ks * 128, idesc, ks > 0 ? 1u : 0u);
+        if (split) {
+            umma_ss(d_tmem, a, aoff + ks * 2, b, boff + b_lo + ks * 128, idesc, 1u);
+            umma_ss(d_tmem, a, aoff + a_lo + ks * 2, b, boff + ks * 128, idesc, 1u);
         }
     }
 }
@@ -210,8 +208,8 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
     }
 
     if (warp == 16) {
-        // ======================= MMA issuer (one lane) =======================
-        if (lane == 0) {
+        // ======================= MMA issuer (one elected lane: umma.cuh, lean issue path) =======================
+        if (elect_one_sync()) {
             // stage the weight images once (bulk TMA)
             const uint32_t w2_bytes = 8192u * nhl, w3_bytes = PASS_B ? 32768u * nhl : 0u;
             mbar_arrive_expect_tx(w_bar, w2_bytes + w3_bytes);
@@ -228,7 +226,13 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                 mbar_wait(a_ready, 0);
                 tc_fence_after_sync();
             }
-            const uint32_t w2_hi = smem_u32(w2s), w2_lo = w2_hi + 8192;
+            const bool split = nhl == 2;
+            const UDesc w2_k = udesc_k(smem_u32(w2s));                               // lo image 8 KB further
+            const UDesc w3_k = udesc_k(smem_u32(w3s));                               // half h 32 KB further, lo 16 KB further
+            const UDesc h1_mn = udesc_mn(smem_u32(h1s), ACT_LBO, ACT_SBO);           // stage b 32 KB further, lo 16 KB further
+            const UDesc h2_mn = udesc_mn(smem_u32(h2s), H2_LBO, ACT_SBO);            // stage b 32 KB further, lo 8 KB further
+            const UDesc h2_k = udesc_k(smem_u32(h2s));                               // a 64-row block [hi ; lo] as a K-major tile
+            constexpr uint32_t STAGE = 2 * ACT_BYTES / 16;
             auto issue_mma2 = [&](int it) {
                 const int b = it & 1, u = (it >> 1) & 1;
                 mbar_wait(&h1_full[b], u);
@@ -239,9 +243,9 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                 }
                 tc_fence_after_sync();
                 if (W2_TMEM)
-                    mma_tmem_weight_act(tmem_base + 128 * b, w2_t, w2_t + 32, smem_u32(h1s + b * 2 * ACT_BYTES), nhl, idesc);
+                    mma_tmem_weight_act(tmem_base + 128 * b, w2_t, w2_t + 32, h1_mn, b * STAGE, ACT_BYTES / 16, split, idesc);
                 else
-                    mma_weight_act(tmem_base, w2_hi, w2_lo, smem_u32(h1s + b * 2 * ACT_BYTES), nhl, idesc);
+                    mma_weight_act(tmem_base, w2_k, 0, 8192 / 16, h1_mn, b * STAGE, ACT_BYTES / 16, split, idesc);
                 umma_commit(&h1_empty[b]);
                 umma_commit(&d2_full[b]);
             };
@@ -256,9 +260,7 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                     for (int h = 0; h < 2; ++h) {
                         mbar_wait(&d3_empty[h], (it & 1) ^ 1);
                         tc_fence_after_sync();
-                        const uint32_t w3_hi = smem_u32(w3s + h * 32768);
-                        mma_weight_act(tmem_base + 256 + 128 * h, w3_hi, w3_hi + 16384, smem_u32(h2s + b * 2 * ACT_BYTES), nhl, idesc,
-                                       H2_LBO, H2_LO);
+                        mma_weight_act(tmem_base + 256 + 128 * h, w3_k, h * (32768 / 16), 16384 / 16, h2_mn, b * STAGE, H2_LO / 16, split, idesc);
                         umma_commit(&d3_full[h]);
                     }
                     if (GRAM) {
@@ -267,11 +269,10 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                         // are hi.hi, hi.lo, lo.hi, lo.lo, and H2 is their sum (taken when the accumulator is flushed)
 #pragma unroll
                         for (int blk = 0; blk < 2; ++blk) {
-                            const uint32_t hb = smem_u32(h2s + b * 2 * ACT_BYTES) + blk * H2_LBO;
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = umma_desc_sw128(hb + ks * 32);
-                                umma_bf16_ss(tmem_base + 128, ad, ad, nhl == 2 ? idesc_kk2 : idesc_kk, (it == 0 && blk == 0 && ks == 0) ? 0u : 1u);
+                                const uint32_t off = b * STAGE + blk * (H2_LBO / 16) + ks * 2;
+                                umma_ss(tmem_base + 128, h2_k, off, h2_k, off, split ? idesc_kk2 : idesc_kk, (it == 0 && blk == 0 && ks == 0) ? 0u : 1u);
                             }
                         }
                     }
@@ -588,48 +589,6 @@ __device__ __forceinline__ void store_img8(uint8_t* img, int nhl, int img_bytes,
     }
 }
 
-// D (+)= A(TMEM tile, 64-wide K) * B(MN-major [64 ch][64 rows] image): the three bf16 hi/lo products, N = 64
-__device__ __forceinline__ void mma_t_act64(uint32_t d, uint32_t a_hi_t, uint32_t a_lo_t, uint32_t b_hi, uint32_t b_lo, int nhl,
-                                            uint32_t idesc, bool first) {
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t bd = umma_desc_mn_sw128(b_hi + ks * 2048, 8192, 1024);
-        umma_bf16_ts(d, a_hi_t + ks * 8, bd, idesc, (first && ks == 0) ? 0u : 1u);
-        if (nhl == 2) {
-            umma_bf16_ts(d, a_hi_t + ks * 8, umma_desc_mn_sw128(b_lo + ks * 2048, 8192, 1024), idesc, 1u);
-            umma_bf16_ts(d, a_lo_t + ks * 8, bd, idesc, 1u);
-        }
-    }
-}
-// D (+)= A(K-major image, rows = channels, K = 64 batch rows) * B(K-major image, K = 64 batch rows): reduction over rows
-__device__ __forceinline__ void mma_rows64(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int nhl,
-                                           uint32_t idesc, bool first) {
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t ad = umma_desc_sw128(a_hi + ks * 32), bd = umma_desc_sw128(b_hi + ks * 32);
-        umma_bf16_ss(d, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
-        if (nhl == 2) {
-            umma_bf16_ss(d, ad, umma_desc_sw128(b_lo + ks * 32), idesc, 1u);
-            umma_bf16_ss(d, umma_desc_sw128(a_lo + ks * 32), bd, idesc, 1u);
-        }
-    }
-}
-// D (+)= A^T (image [K ch][M], read MN-major) * B(MN-major [K ch][64 rows] image): reduction over `ksteps`*16 channels.
-// a_lbo = distance to the second 64 of M (garbage lanes 64..127 when the image has 64 columns).
-__device__ __forceinline__ void mma_t_act(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uint32_t b_hi, uint32_t b_lo,
-                                          int ksteps, int nhl, uint32_t idesc, bool first) {
-#pragma unroll 1
-    for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t ad = umma_desc_mn_sw128(a_hi + ks * 2048, a_lbo, 1024);
-        const uint64_t bd = umma_desc_mn_sw128(b_hi + ks * 2048, 8192, 1024);
-        umma_bf16_ss(d, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
-        if (nhl == 2) {
-            umma_bf16_ss(d, ad, umma_desc_mn_sw128(b_lo + ks * 2048, 8192, 1024), idesc, 1u);
-            umma_bf16_ss(d, umma_desc_mn_sw128(a_lo + ks * 2048, a_lbo, 1024), bd, idesc, 1u);
-        }
-    }
-}
-
 // producer shared by both backward passes: thread = channel (2 threads per channel, 32 rows each); returns sum of h1
 __device__ __forceinline__ float produce_h1_tile64(const float4* xtile, uint8_t* img, int nhl, int ch, int half, float wx, float wy,
                                                    float wz, float ww, float bf) {
@@ -726,7 +685,8 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     const uint32_t idesc_dg2 = umma_idesc_bf16(128, nB) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;
 
     if (warp == 18) {
-        if (lane == 0) {
+        // one elected thread issues every bulk copy, tcgen05.mma and tcgen05.commit of the CTA (elect.sync: see umma.cuh, lean issue path)
+        if (elect_one_sync()) {
             mbar_arrive_expect_tx(w_bar, (8192u + 32768u + 8192u) * nhl);
             tma_bulk_g2s(w2s, p.w2_img, 8192, w_bar);
             tma_bulk_g2s(p3s, p.p3_img, 8192, w_bar);
@@ -743,17 +703,15 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             tc_fence_after_sync();
             const uint32_t w2_hi = tmem_base + 384, w2_lo = tmem_base + 416;
             const uint32_t p3_hi = tmem_base + 448, p3_lo = tmem_base + 480;
-            const uint32_t h1 = smem_u32(h1s);
-            const uint32_t sp_hi = smem_u32(sps), sp_lo = sp_hi + 32768;
-            // D (+)= A B with A in TMEM and B = [hi | lo] (MN-major, `b_lbo` bytes between the halves): A_hi x [B_hi | B_lo], then A_lo x B_hi
-            auto mma_w_b2 = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b, uint32_t b_lbo, bool first) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t bd = umma_desc_mn_sw128(b + ks * 2048, b_lbo, 1024);
-                    umma_bf16_ts(d, a_hi + ks * 8, bd, idesc_mn2, (first && ks == 0) ? 0u : 1u);
-                    if (nhl == 2) umma_bf16_ts(d, a_lo + ks * 8, bd, idesc_mn, 1u);
-                }
-            };
+            // operand descriptors, built once; all per-instruction offsets below are immediates in 16-byte units
+            const UDesc h1_mn = udesc_mn(smem_u32(h1s), 8192, 1024);            // h1 [64 ch][64 rows] as B of W2 h1 (reduction over channels)
+            const UDesc h2_k = udesc_k(smem_u32(h2s));                           // h2 stage 0, K-major: B of Sp h2^T (reduction over rows)
+            const UDesc h2_mn = udesc_mn(smem_u32(h2s), 8192, 1024);             // h2 stage 0, MN-major [hi | lo]: B of P3 h2
+            const UDesc sp_k = udesc_k(smem_u32(sps));                           // Sp K-major: A of Sp h2^T
+            const UDesc sp_mn = udesc_mn(smem_u32(sps), 32768, 1024);            // Sp MN-major [hi | lo]: B of W3^T Sp
+            const UDesc w3_mn = udesc_mn(smem_u32(w3s), 16384, 1024);            // W3 read transposed: A of W3^T Sp, [hi | lo] 16 KB apart
+            constexpr uint32_t LO64 = IMG64 / 16;                                // hi -> lo half of a [64][64] image
+            const bool split = nhl == 2;
             PROF_DECL(8)
             auto issue_z2 = [&](int it) {          // z2(it) = W2 h1(it): plain 3-term form, double-buffered accumulator
                 const int b = it & 1, u = (it >> 1) & 1;
@@ -762,7 +720,15 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 mbar_wait(&d2_empty[b], u ^ 1);
                 PROF_MARK(4)
                 tc_fence_after_sync();
-                mma_t_act64(tmem_base + 64 * b, w2_hi, w2_lo, h1, h1 + IMG64, nhl, idesc_mn, true);
+                const uint32_t d = tmem_base + 64 * b;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    umma_ts(d, w2_hi + ks * 8, h1_mn, ks * 128, idesc_mn, ks > 0 ? 1u : 0u);
+                    if (split) {
+                        umma_ts(d, w2_hi + ks * 8, h1_mn, LO64 + ks * 128, idesc_mn, 1u);
+                        umma_ts(d, w2_lo + ks * 8, h1_mn, ks * 128, idesc_mn, 1u);
+                    }
+                }
                 umma_commit(h1_empty);
                 umma_commit(&d2_full[b]);
                 PROF_MARK(5)
@@ -771,29 +737,42 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
 #pragma unroll 1
             for (int it = 0; it < my_tiles; ++it) {
                 const int b = it & 1, u = (it >> 1) & 1;
-                const uint32_t h2 = smem_u32(h2s + b * 2 * IMG64);
+                const uint32_t st = (uint32_t)b * (2 * IMG64 / 16);               // h2 stage offset
+                const uint32_t acc0 = it == 0 ? 0u : 1u;
                 mbar_wait(&h2_full[b], u);
                 PROF_MARK(0)
                 mbar_wait(sp_full, it & 1);
                 PROF_MARK(1)
                 tc_fence_after_sync();
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h)          // dW3s += Sp h2^T
-                    mma_rows64(tmem_base + 256 + 64 * h, sp_hi + h * 16384, sp_lo + h * 16384, h2, h2 + IMG64, nhl, idesc_kk, it == 0);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {        // dW3s += Sp h2^T   (A = Sp half h: 16 KB apart, lo 32 KB further)
+                    const uint32_t d = tmem_base + 256 + 64 * h;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        umma_ss(d, sp_k, h * 1024 + ks * 2, h2_k, st + ks * 2, idesc_kk, ks > 0 ? 1u : acc0);
+                        if (split) {
+                            umma_ss(d, sp_k, h * 1024 + ks * 2, h2_k, st + LO64 + ks * 2, idesc_kk, 1u);
+                            umma_ss(d, sp_k, 2048 + h * 1024 + ks * 2, h2_k, st + ks * 2, idesc_kk, 1u);
+                        }
+                    }
+                }
                 PROF_MARK(2)
                 if (it + 1 < my_tiles) issue_z2(it + 1);
                 mbar_wait(dh_empty, (it & 1) ^ 1);
                 PROF_MARK(6)
                 tc_fence_after_sync();
-#pragma unroll 1
+#pragma unroll
                 for (int ks = 0; ks < 16; ++ks) {   // dh2 = W3^T Sp: reduction over the 256 channels
-                    const uint32_t wa = smem_u32(w3s + (ks >> 3) * 32768) + (ks & 7) * 2048;
-                    const uint64_t bd = umma_desc_mn_sw128(sp_hi + ks * 2048, 32768, 1024);
-                    umma_bf16_ss(tmem_base + 128, umma_desc_mn_sw128(wa, 16384, 1024), bd, idesc_dg2, ks > 0 ? 1u : 0u);
-                    if (nhl == 2) umma_bf16_ss(tmem_base + 128, umma_desc_mn_sw128(wa + 16384, 16384, 1024), bd, idesc_dg, 1u);
+                    const uint32_t wa = (ks >> 3) * 2048 + (ks & 7) * 128;
+                    umma_ss(tmem_base + 128, w3_mn, wa, sp_mn, ks * 128, idesc_dg2, ks > 0 ? 1u : 0u);
+                    if (split) umma_ss(tmem_base + 128, w3_mn, wa + 1024, sp_mn, ks * 128, idesc_dg, 1u);
                 }
                 umma_commit(sp_empty);
-                mma_w_b2(tmem_base + 128, p3_hi, p3_lo, h2, 8192, false);                                       // dh2 += P3 h2
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {    // dh2 += P3 h2: A_hi x [h2_hi | h2_lo], then A_lo x h2_hi
+                    umma_ts(tmem_base + 128, p3_hi + ks * 8, h2_mn, st + ks * 128, idesc_mn2, 1u);
+                    if (split) umma_ts(tmem_base + 128, p3_lo + ks * 8, h2_mn, st + ks * 128, idesc_mn, 1u);
+                }
                 umma_commit(dh_full);
                 umma_commit(&h2_empty[b]);
                 PROF_MARK(7)
@@ -1133,7 +1112,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
     (void)idesc_mn; (void)idesc_dg;
 
     if (warp == 12) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_arrive_expect_tx(w_bar, 2 * 8192u * nhl);
             tma_bulk_g2s(ews, p.e0w2_img, 8192, w_bar);
             tma_bulk_g2s(p2s, p.p2_img, 8192, w_bar);
@@ -1142,7 +1121,12 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
                 tma_bulk_g2s(p2s + 8192, p.p2_img + 16384, 8192, w_bar);
             }
             mbar_wait(w_bar, 0);
-            const uint32_t ew = smem_u32(ews), p2 = smem_u32(p2s);
+            const bool split = nhl == 2;
+            const UDesc ew_mn = udesc_mn(smem_u32(ews), 8192, 1024);                 // (E0 W2) read transposed, [hi ; lo] rows stacked
+            const UDesc p2_k = udesc_k(smem_u32(p2s));                               // [P2_hi ; P2_lo] stacked
+            const UDesc stg_mn = udesc_mn(smem_u32(stg), 2 * IMG64, 1024);           // a stage image with its lo half as the second N block
+            const UDesc stg_k = udesc_k(smem_u32(stg));
+            constexpr uint32_t STG = D_STAGE_BYTES / 16, I64 = IMG64 / 16;
             int s = 0, ph = 0;
 #ifdef FACL_PROFILE_ROLES
             long long pw_h1 = 0, pw_in = 0, pw_dh = 0, pw_issue = 0, pt0 = clock64();
@@ -1167,19 +1151,22 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
                 pw_h1 += c1 - c0; pw_in += c2 - c1; pw_dh += c3 - c2;
 #endif
                 tc_fence_after_sync();
-                const uint32_t dz = smem_u32(stg + s * D_STAGE_BYTES), h1 = dz + IMG64;   // lo halves 2 * IMG64 further
+                const uint32_t so = (uint32_t)s * STG;            // stage: [dh2'_hi | h1_hi | dh2'_lo | h1_lo], 8 KB each
                 // dh1[i][r] = sum_j (e0 W2)[j][i] dh2'[j][r] + sum_i' P2[i][i'] h1[i'][r];  lanes 0..63 hi part, 64..127 lo part
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16_ss(tmem_base + 128 * b, umma_desc_mn_sw128(ew + ks * 2048, 8192, 1024),
-                                 umma_desc_mn_sw128(dz + ks * 2048, 2 * IMG64, 1024), idesc_dg2, ks > 0 ? 1u : 0u);
+                for (int ks = 0; ks < 4; ++ks) umma_ss(tmem_base + 128 * b, ew_mn, ks * 128, stg_mn, so + ks * 128, idesc_dg2, ks > 0 ? 1u : 0u);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16_ss(tmem_base + 128 * b, umma_desc_sw128(p2 + ks * 32), umma_desc_mn_sw128(h1 + ks * 2048, 2 * IMG64, 1024),
-                                 idesc_mn2, 1u);
+                for (int ks = 0; ks < 4; ++ks) umma_ss(tmem_base + 128 * b, p2_k, ks * 2, stg_mn, so + I64 + ks * 128, idesc_mn2, 1u);
                 umma_commit(&dh_full[b]);
-                // [dW2s ; H1] += [dh2' ; h1] h1^T  (reduction over the 64 rows)
-                mma_rows64(tmem_base + 256, dz, dz + 2 * IMG64, h1, h1 + 2 * IMG64, nhl, idesc_kk, it == 0);
+                // [dW2s ; H1] += [dh2' ; h1] h1^T  (reduction over the 64 rows): A = the 128-row tile at the stage start, B = h1
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    umma_ss(tmem_base + 256, stg_k, so + ks * 2, stg_k, so + I64 + ks * 2, idesc_kk, (it == 0 && ks == 0) ? 0u : 1u);
+                    if (split) {
+                        umma_ss(tmem_base + 256, stg_k, so + ks * 2, stg_k, so + 3 * I64 + ks * 2, idesc_kk, 1u);
+                        umma_ss(tmem_base + 256, stg_k, so + 2 * I64 + ks * 2, stg_k, so + I64 + ks * 2, idesc_kk, 1u);
+                    }
+                }
                 umma_commit(&st_empty[s]);
                 if (++s == D_STAGES) { s = 0; ph ^= 1; }
 #ifdef FACL_PROFILE_ROLES
@@ -1194,7 +1181,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
             umma_commit(fin_bar);
         }
     } else if (warp == 13) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int s = 0, ph = 0;
             const uint8_t* src = p.dh2 + t0 * (2 * IMG64);
 #pragma unroll 1

@@ -12,8 +12,11 @@
 // * the positives are themselves masked entries: global  pos[g][n] = S_g[n][g*B+n],
 //   circle pos[i][n] = S_x[o_i*B+n][o_{i+1}*B+n];
 // * circle: the G-1 anchor rows of sample n share one negative set (their union), utils_my.py:105-109.
-// A row pass computes (max, sum exp) over the unmasked entries, a finalize pass forms the log-sum-exps, the two
-// losses and the per-sample softmax coefficients; dS is then written in place and two GEMMs per loss give dX.
+// S is never materialised.  Forward: the similarity GEMM's TMEM epilogue keeps an ONLINE log-sum-exp per anchor row
+// (running max and sum of exponentials over the unmasked columns, merged across the CTAs that share a row) and stores only the
+// G masked entries of each row (the positives are among them); a finalize pass forms the log-sum-exps, the two losses and the
+// per-sample softmax coefficients.  Backward: the similarity GEMM runs again and its epilogue turns S into dL/dS in registers,
+// written directly as a bf16 hi/lo operand image; two GEMMs per loss then give dX.  (gemm_img.cu, LossEpi)
 #include <math.h>
 #include <string.h>
 
@@ -42,41 +45,6 @@ struct Idx {
     __host__ __device__ int key_of(int g, int n) const { return (n / Bl) * Ml + g * Bl + (n % Bl); }
     __host__ __device__ int anchor_sample(int a) const { return n0 + (a < Ml ? a % Bl : a - Ml); }
 };
-
-// one block per anchor row: m = max, e = sum exp(s - m) over the unmasked columns
-__global__ void __launch_bounds__(128) loss_rowstats_kernel(const float* __restrict__ Smat, Idx ix, int row0, int nrows,
-                                                            float* __restrict__ rmax, float* __restrict__ rsum) {
-    int a = row0 + blockIdx.x;
-    if (blockIdx.x >= nrows) return;
-    int n = ix.anchor_sample(a);
-    const float* row = Smat + (long long)a * ix.Mk;
-    float m = -INFINITY;
-    for (int j = threadIdx.x; j < ix.Mk; j += 128)
-        if (ix.key_sample(j) != n) m = fmaxf(m, row[j]);
-    __shared__ float sh[128];
-    sh[threadIdx.x] = m;
-    __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
-        if (threadIdx.x < o) sh[threadIdx.x] = fmaxf(sh[threadIdx.x], sh[threadIdx.x + o]);
-        __syncthreads();
-    }
-    m = sh[0];
-    __syncthreads();
-    float e = 0.f;
-    if (m > -INFINITY)
-        for (int j = threadIdx.x; j < ix.Mk; j += 128)
-            if (ix.key_sample(j) != n) e += expf(row[j] - m);
-    sh[threadIdx.x] = e;
-    __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
-        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        rmax[a] = m;
-        rsum[a] = sh[0];
-    }
-}
 
 __device__ __forceinline__ double lse3(double pos, double m, double e, double nzero) {
     // log(exp(pos) + e*exp(m) + nzero*exp(0)), with e possibly 0 (m = -inf)
@@ -109,14 +77,32 @@ __device__ __forceinline__ double warp_max_d(double v) {
 //   lcG[b] = log sum_g exp(-LSE_g,n)      pgG[b*G+g] = (exp(pos - LSE) - 1)/B       (global)
 //   lcC[b] = log sum_i exp(-LSE_i,n)      pgC[b*G+i] = (exp(pos - LSE) - 1)/B       (circle, i < G-1)
 constexpr int LF_THREADS = 512;
-__global__ void __launch_bounds__(LF_THREADS) loss_finalize_kernel(const float* __restrict__ Smat, Idx ix, const int* __restrict__ order,
-                                                                   const float* __restrict__ rmax, const float* __restrict__ rsum,
+__global__ void __launch_bounds__(LF_THREADS) loss_finalize_kernel(const float* __restrict__ pos, Idx ix, const int* __restrict__ order,
+                                                                   const float* __restrict__ partX, int PX, const float* __restrict__ partG,
+                                                                   int PG, float* rmax, float* rsum,
                                                                    int want_global, int want_circle, float* __restrict__ loss,
                                                                    float* __restrict__ lcG, float* __restrict__ pgG,
                                                                    float* __restrict__ lcC, float* __restrict__ pgC) {
     const int G = ix.G, B = ix.B;
-    const long long ld = ix.Mk;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // merge the per-CTA online log-sum-exp partials of every anchor row: m = max_p m_p, e = sum_p e_p exp(m_p - m)
+    for (int a = threadIdx.x; a < ix.Ml + ix.Bl; a += LF_THREADS) {
+        const bool seq = a >= ix.Ml;
+        if ((seq && !want_global) || (!seq && !want_circle)) continue;
+        const float* part = seq ? partG : partX;
+        const int P = seq ? PG : PX, Md = seq ? ix.Bl : ix.Ml, r = seq ? a - ix.Ml : a;
+        float m = -INFINITY;
+        for (int q = 0; q < P; ++q)
+            if (part[((long long)q * Md + r) * 2 + 1] > 0.f) m = fmaxf(m, part[((long long)q * Md + r) * 2]);
+        float e = 0.f;
+        for (int q = 0; q < P; ++q) {
+            const float eq = part[((long long)q * Md + r) * 2 + 1];
+            if (eq > 0.f) e += eq * expf(part[((long long)q * Md + r) * 2] - m);
+        }
+        rmax[a] = m;
+        rsum[a] = e;
+    }
+    __syncthreads();
     double accG = 0.0, accC = 0.0;
     for (int b = warp; b < ix.Bl; b += LF_THREADS / 32) {
         const int n = ix.n0 + b;
@@ -125,17 +111,17 @@ __global__ void __launch_bounds__(LF_THREADS) loss_finalize_kernel(const float* 
             const double m = rmax[a], e = rsum[a];
             double minL = 1e300;
             for (int g = lane; g < G; g += 32) {
-                double pos = Smat[(long long)a * ld + ix.key_of(g, n)];
-                double L = lse3(pos, m, e, (double)G);
-                accG += L - pos;
-                pgG[b * G + g] = (float)((exp(pos - L) - 1.0) / B);
+                double pos_v = pos[(long long)a * G + g];
+                double L = lse3(pos_v, m, e, (double)G);
+                accG += L - pos_v;
+                pgG[b * G + g] = (float)((exp(pos_v - L) - 1.0) / B);
                 minL = fmin(minL, L);
             }
             minL = warp_min_d(minL);
             double s = 0.0;
             for (int g = lane; g < G; g += 32) {
-                double pos = Smat[(long long)a * ld + ix.key_of(g, n)];
-                s += exp(minL - lse3(pos, m, e, (double)G));
+                double pos_v = pos[(long long)a * G + g];
+                s += exp(minL - lse3(pos_v, m, e, (double)G));
             }
             s = warp_sum_d(s);
             if (lane == 0) lcG[b] = (float)(-minL + log(s));
@@ -157,18 +143,18 @@ __global__ void __launch_bounds__(LF_THREADS) loss_finalize_kernel(const float* 
             double minL = 1e300;
             for (int i = lane; i < G - 1; i += 32) {
                 int a = order[i] * ix.Bl + b;
-                double pos = Smat[(long long)a * ld + ix.key_of(order[i + 1], n)];
-                double L = lse3(pos, mx, e, nzero);
-                accC += L - pos;
-                pgC[b * G + i] = (float)((exp(pos - L) - 1.0) / B);
+                double pos_v = pos[(long long)a * G + order[i + 1]];
+                double L = lse3(pos_v, mx, e, nzero);
+                accC += L - pos_v;
+                pgC[b * G + i] = (float)((exp(pos_v - L) - 1.0) / B);
                 minL = fmin(minL, L);
             }
             minL = warp_min_d(minL);
             double s = 0.0;
             for (int i = lane; i < G - 1; i += 32) {
                 int a = order[i] * ix.Bl + b;
-                double pos = Smat[(long long)a * ld + ix.key_of(order[i + 1], n)];
-                s += exp(minL - lse3(pos, mx, e, nzero));
+                double pos_v = pos[(long long)a * G + order[i + 1]];
+                s += exp(minL - lse3(pos_v, mx, e, nzero));
             }
             s = warp_sum_d(s);
             if (lane == 0) lcC[b] = (G > 1) ? (float)(-minL + log(s)) : -INFINITY;
@@ -191,38 +177,13 @@ __global__ void __launch_bounds__(LF_THREADS) loss_finalize_kernel(const float* 
     }
 }
 
-// S -> dL/dS in place (unit upstream gradient for each loss)
-__global__ void loss_ds_kernel(float* __restrict__ Smat, Idx ix, const int* __restrict__ order, const int* __restrict__ inv_order,
-                               int row0, int nrows, const float* __restrict__ lcG, const float* __restrict__ pgG,
-                               const float* __restrict__ lcC, const float* __restrict__ pgC) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)nrows * ix.Mk) return;
-    const int G = ix.G;
-    int a = row0 + (int)(t / ix.Mk), j = (int)(t % ix.Mk);
-    float* s = Smat + (long long)a * ix.Mk + j;
-    const int n = ix.anchor_sample(a);
-    const bool same = ix.key_sample(j) == n;
-    float out;
-    if (a >= ix.Ml) {
-        int b = a - ix.Ml;
-        if (same) out = pgG[b * G + ix.key_view(j)];
-        else out = expf(*s + lcG[b]) / ix.B;
-    } else {
-        int b = a % ix.Bl, i = inv_order[a / ix.Bl];
-        if (i >= G - 1) out = 0.f;                     // the last view in the chain is never an anchor
-        else if (same) out = (ix.key_view(j) == order[i + 1]) ? pgC[b * G + i] : 0.f;
-        else out = expf(*s + lcC[b]) / ix.B;
-    }
-    *s = out;
-}
-
 __global__ void invert_order_kernel(const int* __restrict__ order, int G, int* __restrict__ inv) {
     int i = threadIdx.x;
     if (i < G) inv[order[i]] = i;
 }
 
 struct LossWs {
-    float *S, *rmax, *rsum, *lcG, *pgG, *lcC, *pgC;
+    float *part, *pos, *rmax, *rsum, *lcG, *pgG, *lcC, *pgC;
     int* inv;
     uint8_t *img_keys, *img_x, *img_xg;
     uint8_t *im_x, *im_xg, *im_keys, *im_ds;      // activation images (gemm_img.cu): embeddings [rows as channels][C], dS [rows][Mk]
@@ -235,7 +196,8 @@ size_t loss_ws_layout(int G, int Bl, int R, int C, uint8_t* base, LossWs* w) {
         off += align256(bytes);
         return p;
     };
-    uint8_t* pS = take(rows * Mk * 4);
+    uint8_t* pS = take((size_t)kNumSMs * rows * 2 * 4);     // online log-sum-exp partials: at most one per (CTA, anchor row)
+    uint8_t* pP = take(rows * G * 4);                       // the G masked entries of every anchor row
     uint8_t* p1 = take(rows * 4);
     uint8_t* p2 = take(rows * 4);
     uint8_t* p3 = take((size_t)Bl * 4);
@@ -252,7 +214,7 @@ size_t loss_ws_layout(int G, int Bl, int R, int C, uint8_t* base, LossWs* w) {
     uint8_t* p14 = take(2 * act_image_half_bytes((int)Ml, (long long)Mk));
     if (w) {
         w->im_x = p11; w->im_xg = p12; w->im_keys = p13; w->im_ds = p14;
-        w->S = (float*)pS; w->rmax = (float*)p1; w->rsum = (float*)p2; w->lcG = (float*)p3; w->pgG = (float*)p4;
+        w->part = (float*)pS; w->pos = (float*)pP; w->rmax = (float*)p1; w->rsum = (float*)p2; w->lcG = (float*)p3; w->pgG = (float*)p4;
         w->lcC = (float*)p5; w->pgC = (float*)p6; w->inv = (int*)p7; w->img_keys = p8; w->img_x = p9; w->img_xg = p10;
     }
     return off;
@@ -278,7 +240,7 @@ int contrast_losses(const float* x, const float* xg, const float* keys, int G, i
     Idx ix{G, B, Bl, Ml, Mk, n0};
     LossWs w;
     loss_ws_layout(G, Bl, R, C, reinterpret_cast<uint8_t*>(workspace), &w);
-    count_launch(2 + 2 * (want_circle ? 2 : 0) + 2 * (want_global ? 1 : 0));   // the small loss kernels below
+    count_launch(1 + (want_circle ? 1 : 0));                                   // the small loss kernels below
 
     const int nhl = nsplit == 3 ? 2 : 1;
     auto image = [&](uint8_t* buf, int ch, long long rows) {
@@ -298,14 +260,29 @@ int contrast_losses(const float* x, const float* xg, const float* keys, int G, i
     };
     const bool keys_are_x = (keys == x) && (R == 1);     // single rank: one image serves as anchors and keys
     const ActImage im_keys = image(keys_are_x ? w.im_x : w.im_keys, Mk, C);
-    auto sim = [&](const ActImage& a, int rows, float* out) {   // out[rows][Mk] = a keys^T  (reduction over the C "rows")
+    // similarity GEMM S = a keys^T (reduction over the C "rows") with a contrastive-loss epilogue; S is never stored.
+    //   mode 1: online log-sum-exp partials + the masked entries;  mode 2: dL/dS written as the operand image `ds`
+    float* partX = w.part;
+    float* partG = w.part + (size_t)kNumSMs * Ml * 2;
+    auto sim = [&](const ActImage& a, int rows, int row0, int mode, const ActImage* ds) {
         GemmParams g;
         memset(&g, 0, sizeof(g));
         g.Md = rows; g.Nd = Mk; g.Kd = C; g.nsplit = nsplit; g.ksplit = 1;
         g.a_mode = A_IMAGE; g.a_img = a;
         g.b_mode = B_IMAGE_K; g.b_img = im_keys;
-        g.out_mode = OUT_CHMAJOR; g.out = out; g.ldo = Mk;
+        g.out_mode = OUT_NONE;
         g.tag = TAG_LOSS_GEMM;
+        LossEpi& L = g.loss;
+        L.mode = mode; L.G = G; L.B = B; L.Bl = Bl; L.Ml = Ml; L.n0 = n0; L.row0 = row0;
+        if (mode == 1) {
+            L.part = row0 == 0 ? partX : partG;
+            L.pos = w.pos;
+        } else {
+            L.lc = row0 == 0 ? w.lcC : w.lcG;
+            L.pg = row0 == 0 ? w.pgC : w.pgG;
+            L.order = order; L.inv_order = w.inv;
+            L.ds_hi = const_cast<void*>(ds->hi); L.ds_lo = const_cast<void*>(ds->lo); L.ds_cgs = ds->cgs; L.ds_rbs = ds->rbs;
+        }
         return launch_gemm_tc(g, st);
     };
     // out[Nd rows][C] (+)= dS-block * features, with the feature matrix (transposed) as the packed "A" operand and the
@@ -326,22 +303,19 @@ int contrast_losses(const float* x, const float* xg, const float* keys, int G, i
         return launch_gemm_tc(g, st);
     };
 
-    float* Sx = w.S;
-    float* Sg = w.S + (size_t)Ml * Mk;
     if (want_circle || keys_are_x) RUN(make_image(x, Ml, C, w.im_x));
     if (!keys_are_x) RUN(make_image(keys, Mk, C, w.im_keys));
     if (want_circle) {
-        RUN(sim(image(w.im_x, Ml, C), Ml, Sx));
+        RUN(sim(image(w.im_x, Ml, C), Ml, 0, 1, nullptr));
         invert_order_kernel<<<1, 256, 0, st>>>(order, G, w.inv);
-        loss_rowstats_kernel<<<Ml, 128, 0, st>>>(w.S, ix, 0, Ml, w.rmax, w.rsum);
     }
     if (want_global) {
         RUN(make_image(xg, Bl, C, w.im_xg));
-        RUN(sim(image(w.im_xg, Bl, C), Bl, Sg));
-        loss_rowstats_kernel<<<Bl, 128, 0, st>>>(w.S, ix, Ml, Bl, w.rmax, w.rsum);
+        RUN(sim(image(w.im_xg, Bl, C), Bl, Ml, 1, nullptr));
     }
-    loss_finalize_kernel<<<1, LF_THREADS, 0, st>>>(w.S, ix, order, w.rmax, w.rsum, want_global, want_circle, loss, w.lcG, w.pgG, w.lcC,
-                                            w.pgC);
+    loss_finalize_kernel<<<1, LF_THREADS, 0, st>>>(w.pos, ix, order, partX, gemm_tc_ctas_per_mtile(Ml, Mk), partG,
+                                                   gemm_tc_ctas_per_mtile(Bl, Mk), w.rmax, w.rsum, want_global, want_circle, loss, w.lcG,
+                                                   w.pgG, w.lcC, w.pgC);
     FACL_CHECK_LAUNCH();
     // feature matrices as packed A operands: A[m = c][k = row] = feat[row][c]
     RUN(pack_weight_launch(keys, 1, C, C, Mk, w.img_keys, st));
@@ -350,22 +324,21 @@ int contrast_losses(const float* x, const float* xg, const float* keys, int G, i
     if (dkeys != dx_anchor) FACL_CHECK(cudaMemsetAsync(dkeys, 0, sizeof(float) * (size_t)Mk * C, st));
     if (want_global) {
         FACL_CHECK(cudaMemsetAsync(dxg, 0, sizeof(float) * (size_t)Bl * C, st));
-        loss_ds_kernel<<<div_up((long long)Bl * Mk, 256), 256, 0, st>>>(w.S, ix, order, w.inv, Ml, Bl, w.lcG, w.pgG, w.lcC, w.pgC);
-        FACL_CHECK_LAUNCH();
         RUN(pack_weight_launch(xg, 1, C, C, Bl, w.img_xg, st));
+        // the similarity GEMM again, its epilogue writing dL/dS_g straight into the operand image
+        const ActImage ds = image(w.im_ds, Bl, Mk);
+        RUN(sim(image(w.im_xg, Bl, C), Bl, Ml, 2, &ds));
         // dxg[b] = sum_j dS_g[b][j] keys[j] ;  dkeys[j] += sum_b dS_g[b][j] xg[b]
-        RUN(make_image(Sg, Bl, Mk, w.im_ds));
-        RUN(dgemm(w.img_keys, Mk, B_IMAGE_K, image(w.im_ds, Bl, Mk), Bl, dxg));
-        RUN(dgemm(w.img_xg, Bl, B_IMAGE_MN, image(w.im_ds, Bl, Mk), Mk, dkeys));
+        RUN(dgemm(w.img_keys, Mk, B_IMAGE_K, ds, Bl, dxg));
+        RUN(dgemm(w.img_xg, Bl, B_IMAGE_MN, ds, Mk, dkeys));
     }
     if (want_circle) {
-        loss_ds_kernel<<<div_up((long long)Ml * Mk, 256), 256, 0, st>>>(w.S, ix, order, w.inv, 0, Ml, w.lcG, w.pgG, w.lcC, w.pgC);
-        FACL_CHECK_LAUNCH();
         RUN(pack_weight_launch(x, 1, C, C, Ml, w.img_x, st));
+        const ActImage ds = image(w.im_ds, Ml, Mk);
+        RUN(sim(image(w.im_x, Ml, C), Ml, 0, 2, &ds));
         // dx_anchor[a] += sum_j dS[a][j] keys[j]   and   dkeys[j] += sum_a dS[a][j] x[a]
-        RUN(make_image(Sx, Ml, Mk, w.im_ds));
-        RUN(dgemm(w.img_keys, Mk, B_IMAGE_K, image(w.im_ds, Ml, Mk), Ml, dx_anchor));
-        RUN(dgemm(w.img_x, Ml, B_IMAGE_MN, image(w.im_ds, Ml, Mk), Mk, dkeys));
+        RUN(dgemm(w.img_keys, Mk, B_IMAGE_K, ds, Ml, dx_anchor));
+        RUN(dgemm(w.img_x, Ml, B_IMAGE_MN, ds, Mk, dkeys));
     }
     return 0;
 }

@@ -134,6 +134,55 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ----------------------------------------------------------------------------------------------
+// Lean issue path.  Measured with clock64 role accounting (profiles/r2_role_profile.md): the ONE thread that issues the
+// tcgen05.mma stream of a fused kernel was bound by its own scalar instructions -- ~17 SASS instructions per MMA at ~6 cycles
+// each: (i) every 64-bit descriptor was rebuilt (shift, mask, or) from a byte address, (ii) under `if (lane == 0)` ptxas
+// cannot prove that a single thread is active and wraps every warp-level instruction (UTCHMMA, UTCBAR, UBLKCP) in an
+// ELECT / PLOP3 / BRA.U.ANY loop over the active threads.  Here a descriptor is a (lo, hi) pair of 32-bit words built once per
+// operand; a k-step or half-image offset is an immediate added to `lo` (the 14-bit address field counts 16-byte units and the
+// shared window is < 256 KB, so the sum never carries out of the field), and the issuing branch is taken through elect.sync,
+// after which ptxas emits the bare instruction: 1-3 SASS instructions per MMA.
+// ----------------------------------------------------------------------------------------------
+// true in exactly one lane of a fully converged warp (all 32 lanes must execute it)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+struct UDesc {
+    uint32_t lo, hi;
+};
+// K-major, 128-byte rows, 128B swizzle (same bits as umma_desc_sw128)
+__device__ __forceinline__ UDesc udesc_k(uint32_t smem_addr) {
+    return UDesc{((smem_addr >> 4) & 0x3FFFu) | (1u << 16), 64u | (1u << 14) | (2u << 29)};
+}
+// MN-major, 128B swizzle (same bits as umma_desc_mn_sw128)
+__device__ __forceinline__ UDesc udesc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return UDesc{((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16), ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29)};
+}
+// `off16`: byte offset / 16 added to the operand's start address (k-step, hi/lo half, stage)
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, UDesc a, uint32_t a_off16, UDesc b, uint32_t b_off16, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a.lo + a_off16), "r"(a.hi), "r"(b.lo + b_off16), "r"(b.hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, UDesc b, uint32_t b_off16, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b.lo + b_off16), "r"(b.hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Make the mbarrier track completion of all tcgen05.mma issued so far by this thread (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
