@@ -145,7 +145,10 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                     }
                 }
             }
-            const int nchunks = (mma_n + 31) / 32;
+            // EPI 5 writes whole 64-row blocks of the image (its padding columns must be zero): an even number of 32-column chunks
+            const int nchunks = (EPI == 5) ? ((mma_n + 63) / 64) * 2 : (mma_n + 31) / 32;
+            // the masked columns of this row are the G keys of its own sample: j = nr*Ml + g*Bl + nb, g = 0..G-1
+            const int jbase = nr * L.Ml + nb;
             for (int it = 0; sched.get(it, p, w); ++it) {
                 const int buf = it & 1;
                 mbar_wait(&acc_full[buf], (it >> 1) & 1);
@@ -159,33 +162,33 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                     const int n0 = w.nt * N_TILE + cc * 32;
                     int nvalid = p.Nd - n0;
                     nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
-                    // key j = jr*Ml + jg*Bl + jb, advanced incrementally (one division per 32 columns instead of per element)
-                    int jr = n0 / L.Ml;
-                    const int jm = n0 - jr * L.Ml;
-                    int jg = jm / L.Bl, jb = jm - jg * L.Bl;
+                    // bit i of `masked`: column n0 + i is a key of the anchor's own sample; mview = view of the lowest such column
+                    unsigned masked = 0u;
+                    int g0 = 0;
+                    if (cvalid && nvalid > 0) {
+                        int g = n0 > jbase ? (n0 - jbase + L.Bl - 1) / L.Bl : 0;          // first view whose key is >= n0
+                        g0 = g;
+                        for (int j = jbase + g * L.Bl; g < L.G && j < n0 + nvalid; ++g, j += L.Bl) masked |= 1u << (j - n0);
+                    }
                     if (EPI == 4) {
                         if (!cvalid || nvalid <= 0) continue;
                         float cm = -INFINITY;
-                        unsigned masked = 0u;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (i < nvalid) {
-                                if (jr == nr && jb == nb) {
-                                    masked |= 1u << i;
-                                    L.pos[(long long)a * L.G + jg] = v[i];      // G masked columns per row: the positives are among them
-                                } else {
-                                    cm = fmaxf(cm, v[i]);
-                                }
-                            }
-                            if (++jb == L.Bl) { jb = 0; if (++jg == L.G) { jg = 0; ++jr; } }
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nvalid && !((masked >> i) & 1u)) cm = fmaxf(cm, v[i]);
+                        if (masked) {                               // G masked columns per row: the positives are among them
+                            int g = g0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if ((masked >> i) & 1u) L.pos[(long long)a * L.G + g++] = v[i];
                         }
                         if (cm > -INFINITY) {
                             const float nm = fmaxf(run_m, cm);
                             float ssum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                             for (int i = 0; i < 32; ++i)
-                                if (i < nvalid && !((masked >> i) & 1u)) ssum[i & 3] += expf(v[i] - nm);
-                            run_e = run_e * expf(run_m - nm) + ((ssum[0] + ssum[1]) + (ssum[2] + ssum[3]));   // exp(-inf) = 0 on the first chunk
+                                ssum[i & 3] += (i < nvalid && !((masked >> i) & 1u)) ? __expf(v[i] - nm) : 0.f;
+                            run_e = run_e * __expf(run_m - nm) + ((ssum[0] + ssum[1]) + (ssum[2] + ssum[3]));   // exp(-inf) = 0 on the first chunk
                             run_m = nm;
                         }
                     } else {
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                         uint8_t* atom = reinterpret_cast<uint8_t*>(L.ds_hi) + ((long long)rb * L.ds_cgs + (c >> 3)) * 1024;
                         uint8_t* atom_lo = reinterpret_cast<uint8_t*>(L.ds_lo) + ((long long)rb * L.ds_cgs + (c >> 3)) * 1024;
                         const int chunk0 = (n0 & 63) >> 3;
+                        int g = g0;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             float o[8];
@@ -202,11 +206,14 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                                 const int i = q * 8 + e;
                                 float out = 0.f;
                                 if (!dead && i < nvalid) {
-                                    if (jr == nr && jb == nb) out = pgrow ? __ldg(pgrow + jg) : (jg == nextv ? pgv : 0.f);
-                                    else out = expf(v[i] + lc) * invB;
+                                    if ((masked >> i) & 1u) {
+                                        out = pgrow ? __ldg(pgrow + g) : (g == nextv ? pgv : 0.f);
+                                        ++g;
+                                    } else {
+                                        out = __expf(v[i] + lc) * invB;
+                                    }
                                 }
                                 o[e] = out;
-                                if (++jb == L.Bl) { jb = 0; if (++jg == L.G) { jg = 0; ++jr; } }
                             }
                             const uint32_t off = sw128_offset((uint32_t)(c & 7), (uint32_t)(chunk0 + q));
                             if (NHL == 2) {

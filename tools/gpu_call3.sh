@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 OUT=gpurun_out; TAG=${1:-r2c3}; mkdir -p $OUT
-timeout 1200 python -m pytest tests -m gpu -q -rf -x > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; grep -E "passed|failed|error" $OUT/${TAG}_tests.log | tail -3
+timeout 1200 python -m pytest tests -m gpu -q -rf > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; grep -E "passed|failed|error" $OUT/${TAG}_tests.log | tail -3
 grep -E "^FAILED|^ERROR" $OUT/${TAG}_tests.log | head -20
 bash tools/role_profile.sh $TAG 2>&1 | grep -v "pass D mma warp" | head -40
 for PREC in fp32 bf16 bf16_fast; do
