@@ -310,8 +310,22 @@ def run_ours(args):
         a1.record()
         sync_all()
         ams = max(a0.elapsed_time(a1), (time.perf_counter() - ta) * 1e3)
+        # the same loop fed through DevicePrefetcher (the H2D copy of batch i+1 under step i), the one-line change INTEGRATION.md shows
+        from facl_b200.train import DevicePrefetcher
+        sync_all()
+        tb = time.perf_counter()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for batch in DevicePrefetcher([host[i % nb] for i in range(asteps)], device=f"cuda:{local_rank}"):
+            _ = float(tr.step(batch, order=order))
+        b1.record()
+        sync_all()
+        bms = max(b0.elapsed_time(b1), (time.perf_counter() - tb) * 1e3)
         api_path = dict(value=B * asteps / (ams * 1e-3), unit="sequences/s", ms_per_step=ams / asteps, steps=asteps,
-                        what="TrainStep.step: reference-shaped module calls through torch autograd, host batch in, loss.item() out")
+                        what="TrainStep.step: reference-shaped module calls through torch autograd, host batch copied synchronously as "
+                             "the reference does (.cuda() at :228), loss.item() out",
+                        prefetched=dict(value=B * asteps / (bms * 1e-3), ms_per_step=bms / asteps,
+                                        what="same loop over facl_b200.train.DevicePrefetcher(loader): next batch's H2D under the current step"))
 
     # ---- BASELINE configs[2]: appearance stream, bf16, GLOBAL batch 256 sharded over the N ranks (strong scaling) ---------------
     cfg3 = None

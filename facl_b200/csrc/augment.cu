@@ -50,6 +50,7 @@ __device__ __forceinline__ double jit(double v, double z, double sigma, double c
 constexpr int THREADS = 256;
 
 __global__ void __launch_bounds__(THREADS) augment_kernel(const AugmentParams p) {
+    pdl_prologue();
     extern __shared__ int nz_list[];
     __shared__ int warp_cnt[THREADS / 32];
     const int view = blockIdx.x;                 // b * G + g
@@ -182,7 +183,7 @@ int augment_launch(const AugmentParams& p, int max_rows, cudaStream_t st) {
     }
     ScopedTimer timer(TAG_AUGMENT, st);
     count_launch();
-    augment_kernel<<<p.B * p.G, THREADS, smem, st>>>(p);
+    FACL_LAUNCH_OK(launch_pdl(augment_kernel, dim3(p.B * p.G), dim3(THREADS), smem, st, p));
     return (int)cudaGetLastError();
 }
 

@@ -32,6 +32,52 @@ __device__ __forceinline__ int div_up_dev(int a, int b) { return (a + b - 1) / b
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A training step is ~90 kernels on one stream, a third of them a few microseconds long; with
+// plain stream ordering every boundary costs the drain of the previous grid plus the launch of the next.  Every kernel of this
+// library starts with pdl_prologue(): `griddepcontrol.wait` returns only when the preceding grid has COMPLETED and its memory
+// is visible -- so no kernel body ever runs early -- and `griddepcontrol.launch_dependents` lets the next grid be scheduled
+// (its CTAs become resident and park in their own wait) while this one is still running.  Launches go through launch_pdl(),
+// which sets cudaLaunchAttributeProgrammaticStreamSerialization; FACL_PDL=0 in the environment disables it (A/B, debugging).
+// Without the attribute both instructions are no-ops.
+// ----------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+#include <cstdlib>
+#include <utility>
+namespace facl {
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("FACL_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+}  // namespace facl
+// a failed launch returns its error code from the enclosing launcher (all of them return the cudaError_t as int)
+#define FACL_LAUNCH_OK(expr)                                   \
+    do {                                                       \
+        cudaError_t _le = (expr);                              \
+        if (_le != cudaSuccess) return (int)_le;               \
+    } while (0)
+
 // One-time PER-DEVICE kernel configuration: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a property of the function on the
 // current device, so a process that touches a second GPU (a model moved to cuda:1, nn.DataParallel replicas) must configure
 // again there.  `need()` is true until `done()` has been called on the current device; a race between two host threads only

@@ -31,6 +31,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int P, in
                                    const float* __restrict__ beta, float* running_mean, float* running_var, float eps,
                                    float momentum, int training, float* __restrict__ mean, float* __restrict__ rstd,
                                    float* __restrict__ scale, float* __restrict__ shift) {
+    pdl_prologue();
     int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     double mu, var;
@@ -61,6 +62,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int P, in
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int P, int C, double n, const float* __restrict__ gamma,
                                        const float* __restrict__ mean, const float* __restrict__ rstd, float* dgamma, float* dbeta,
                                        int accumulate, float* __restrict__ c0, float* __restrict__ c1, float* __restrict__ c2) {
+    pdl_prologue();
     int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     double s, q;
@@ -87,6 +89,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int P
 // per-channel (sum v, sum v*z) over a channel-major matrix -> one "partial" (P = 1); block per channel
 __global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__ v, const float* __restrict__ z, long long ld, int n,
                                                        int pairs, float* __restrict__ out) {
+    pdl_prologue();
     int c = blockIdx.x;
     const float* vr = v + (long long)c * ld;
     const float* zr = z ? z + (long long)c * ld : nullptr;
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__
 
 // out[c][r] = in[r][c]   (rows R, cols C), 32x32 tiles through shared memory; blockIdx.x walks the rows (may be millions)
 __global__ void transpose_kernel(const float* __restrict__ in, long long ldi, float* __restrict__ out, long long ldo, int R, int C) {
+    pdl_prologue();
     __shared__ float tile[32][33];
     int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += 8) {
@@ -137,6 +141,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, long long ldi, fl
 // that follows is negative).  pooled [C][ldp] (first M = G*B columns) -> seq [C][lds] (B columns), argg [C][B].
 __global__ void seq_pool_kernel(const float* __restrict__ pooled, long long ldp, const float* __restrict__ sign, int C, int G, int B,
                                 float* __restrict__ seq, long long lds, unsigned char* __restrict__ argg) {
+    pdl_prologue();
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)C * B) return;
     int c = (int)(t / B), b = (int)(t % B);
@@ -160,6 +165,7 @@ __global__ void seq_pool_kernel(const float* __restrict__ pooled, long long ldp,
 // the sequence max) the grad from the sequence embedding
 __global__ void combine_pool_grads_kernel(float* __restrict__ dcloud, long long ldc, const float* __restrict__ dseq, long long lds,
                                           const unsigned char* __restrict__ argg, int C, int G, int B) {
+    pdl_prologue();
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int M = G * B;
     if (t >= (long long)C * M) return;
@@ -171,6 +177,7 @@ __global__ void combine_pool_grads_kernel(float* __restrict__ dcloud, long long 
 // max-pool backward: dense[c][grp*pool + arg[c][grp]] = v[c][grp]; dense must be zero-filled beforehand
 __global__ void pool_scatter_kernel(const float* __restrict__ v, long long ldv, const unsigned char* __restrict__ arg, long long lda,
                                     int C, int groups, int pool, float* __restrict__ dense, long long ldd) {
+    pdl_prologue();
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)C * groups) return;
     int c = (int)(t / groups), g = (int)(t % groups);
@@ -179,6 +186,7 @@ __global__ void pool_scatter_kernel(const float* __restrict__ v, long long ldv, 
 
 // centres [R][3] -> channel-major [3][R]
 __global__ void centres_to_chmajor_kernel(const float* __restrict__ c, int R, float* __restrict__ out, long long ldo) {
+    pdl_prologue();
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     out[r] = c[(long long)r * 3 + 0];
@@ -188,6 +196,7 @@ __global__ void centres_to_chmajor_kernel(const float* __restrict__ c, int R, fl
 
 // x_nor = x / max(||x||_2, 1e-12)  (F.normalize, cn3d_model_conbag.py:231); one warp per row
 __global__ void l2_normalize_kernel(const float* __restrict__ x, int rows, int C, float* __restrict__ out) {
+    pdl_prologue();
     int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* xr = x + (long long)row * C;
@@ -203,6 +212,7 @@ __global__ void l2_normalize_kernel(const float* __restrict__ x, int rows, int C
 // net3DV_3 input (scale 1 at 0, shift 0 at 320, lower bound -inf at 640), zero lower bounds (ReLU) for 256 channels at 643 and
 // 1024 zeros at 960
 __global__ void encoder_const_vectors_kernel(float* __restrict__ vec) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 3) {
         vec[i] = 1.f;
@@ -214,6 +224,7 @@ __global__ void encoder_const_vectors_kernel(float* __restrict__ vec) {
 }
 
 __global__ void fill_kernel(float* p, long long n, float v) {
+    pdl_prologue();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
@@ -235,6 +246,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 __global__ void adam_kernel(const AdamTensor* __restrict__ tab, int ntensors, float lr, float b1, float b2, float eps, float bc1,
                             float bc2_sqrt) {
+    pdl_prologue();
     const float lr_c = lr / bc1;
     for (int t = blockIdx.y; t < ntensors; t += gridDim.y) {
         AdamTensor a = tab[t];
@@ -270,8 +282,8 @@ int bn_finalize_launch(const float* partials, int P, int C, double n, const floa
                        float* shift, cudaStream_t st) {
     ScopedTimer timer(TAG_BN, st);
     count_launch();
-    bn_finalize_kernel<<<div_up(C, 4), 128, 0, st>>>(partials, P, C, n, gamma, beta, running_mean, running_var, eps, momentum, training,
-                                                       mean, rstd, scale, shift);
+    FACL_LAUNCH_OK(launch_pdl(bn_finalize_kernel, dim3(div_up(C, 4)), dim3(128), 0, st, partials, P, C, n, gamma, beta, running_mean, running_var, eps, momentum, training,
+                                                       mean, rstd, scale, shift));
     return (int)cudaGetLastError();
 }
 
@@ -279,14 +291,14 @@ int bn_bwd_finalize_launch(const float* partials, int P, int C, double n, const 
                            float* dgamma, float* dbeta, int accumulate, float* c0, float* c1, float* c2, cudaStream_t st) {
     ScopedTimer timer(TAG_BN, st);
     count_launch();
-    bn_bwd_finalize_kernel<<<div_up(C, 4), 128, 0, st>>>(partials, P, C, n, gamma, mean, rstd, dgamma, dbeta, accumulate, c0, c1, c2);
+    FACL_LAUNCH_OK(launch_pdl(bn_bwd_finalize_kernel, dim3(div_up(C, 4)), dim3(128), 0, st, partials, P, C, n, gamma, mean, rstd, dgamma, dbeta, accumulate, c0, c1, c2));
     return (int)cudaGetLastError();
 }
 
 int rowstats_launch(const float* v, const float* z, long long ld, int C, int n, int pairs, float* out, cudaStream_t st) {
     ScopedTimer timer(TAG_POOLMISC, st);
     count_launch();
-    rowstats_kernel<<<C, 256, 0, st>>>(v, z, ld, n, pairs, out);
+    FACL_LAUNCH_OK(launch_pdl(rowstats_kernel, dim3(C), dim3(256), 0, st, v, z, ld, n, pairs, out));
     return (int)cudaGetLastError();
 }
 
@@ -294,7 +306,7 @@ int transpose_launch(const float* in, long long ldi, float* out, long long ldo, 
     ScopedTimer timer(TAG_TRANSPOSE, st);
     count_launch();
     dim3 grid(div_up(R, 32), div_up(C, 32)), block(32, 8);
-    transpose_kernel<<<grid, block, 0, st>>>(in, ldi, out, ldo, R, C);
+    FACL_LAUNCH_OK(launch_pdl(transpose_kernel, dim3(grid), dim3(block), 0, st, in, ldi, out, ldo, R, C));
     return (int)cudaGetLastError();
 }
 
@@ -302,7 +314,7 @@ int seq_pool_launch(const float* pooled, long long ldp, const float* sign, int C
                     unsigned char* argg, cudaStream_t st) {
     ScopedTimer timer(TAG_POOLMISC, st);
     count_launch();
-    seq_pool_kernel<<<div_up((long long)C * B, 256), 256, 0, st>>>(pooled, ldp, sign, C, G, B, seq, lds, argg);
+    FACL_LAUNCH_OK(launch_pdl(seq_pool_kernel, dim3(div_up((long long)C * B, 256)), dim3(256), 0, st, pooled, ldp, sign, C, G, B, seq, lds, argg));
     return (int)cudaGetLastError();
 }
 
@@ -310,7 +322,7 @@ int combine_pool_grads_launch(float* dcloud, long long ldc, const float* dseq, l
                               int B, cudaStream_t st) {
     ScopedTimer timer(TAG_POOLMISC, st);
     count_launch();
-    combine_pool_grads_kernel<<<div_up((long long)C * G * B, 256), 256, 0, st>>>(dcloud, ldc, dseq, lds, argg, C, G, B);
+    FACL_LAUNCH_OK(launch_pdl(combine_pool_grads_kernel, dim3(div_up((long long)C * G * B, 256)), dim3(256), 0, st, dcloud, ldc, dseq, lds, argg, C, G, B));
     return (int)cudaGetLastError();
 }
 
@@ -318,28 +330,28 @@ int pool_scatter_launch(const float* v, long long ldv, const unsigned char* arg,
                         float* dense, long long ldd, cudaStream_t st) {
     ScopedTimer timer(TAG_SCATTER, st);
     count_launch();
-    pool_scatter_kernel<<<div_up((long long)C * groups, 256), 256, 0, st>>>(v, ldv, arg, lda, C, groups, pool, dense, ldd);
+    FACL_LAUNCH_OK(launch_pdl(pool_scatter_kernel, dim3(div_up((long long)C * groups, 256)), dim3(256), 0, st, v, ldv, arg, lda, C, groups, pool, dense, ldd));
     return (int)cudaGetLastError();
 }
 
 int centres_to_chmajor_launch(const float* c, int R, float* out, long long ldo, cudaStream_t st) {
     ScopedTimer timer(TAG_POOLMISC, st);
     count_launch();
-    centres_to_chmajor_kernel<<<div_up(R, 256), 256, 0, st>>>(c, R, out, ldo);
+    FACL_LAUNCH_OK(launch_pdl(centres_to_chmajor_kernel, dim3(div_up(R, 256)), dim3(256), 0, st, c, R, out, ldo));
     return (int)cudaGetLastError();
 }
 
 int l2_normalize_launch(const float* x, int rows, int C, float* out, cudaStream_t st) {
     ScopedTimer timer(TAG_POOLMISC, st);
     count_launch();
-    l2_normalize_kernel<<<div_up((long long)rows * 32, 256), 256, 0, st>>>(x, rows, C, out);
+    FACL_LAUNCH_OK(launch_pdl(l2_normalize_kernel, dim3(div_up((long long)rows * 32, 256)), dim3(256), 0, st, x, rows, C, out));
     return (int)cudaGetLastError();
 }
 
 int encoder_const_vectors_launch(float* vec, cudaStream_t st) {
     ScopedTimer timer(TAG_MEMSET, st);
     count_launch();
-    encoder_const_vectors_kernel<<<4, 256, 0, st>>>(vec);
+    FACL_LAUNCH_OK(launch_pdl(encoder_const_vectors_kernel, dim3(4), dim3(256), 0, st, vec));
     return (int)cudaGetLastError();
 }
 
@@ -347,7 +359,7 @@ int fill_launch(float* p, long long n, float v, cudaStream_t st) {
     if (n <= 0) return 0;
     ScopedTimer timer(TAG_MEMSET, st);
     count_launch();
-    fill_kernel<<<div_up(n, 256), 256, 0, st>>>(p, n, v);
+    FACL_LAUNCH_OK(launch_pdl(fill_kernel, dim3(div_up(n, 256)), dim3(256), 0, st, p, n, v));
     return (int)cudaGetLastError();
 }
 
@@ -357,7 +369,7 @@ int adam_launch(const void* table_dev, int ntensors, float lr, float b1, float b
     float bc1 = (float)(1.0 - pow((double)b1, (double)step));
     float bc2 = (float)sqrt(1.0 - pow((double)b2, (double)step));
     dim3 grid(128, ntensors < 64 ? ntensors : 64);
-    adam_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const AdamTensor*>(table_dev), ntensors, lr, b1, b2, eps, bc1, bc2);
+    FACL_LAUNCH_OK(launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const AdamTensor*>(table_dev), ntensors, lr, b1, b2, eps, bc1, bc2));
     return (int)cudaGetLastError();
 }
 

@@ -15,6 +15,7 @@ namespace facl {
 template <int T, int PPT>
 __global__ void __launch_bounds__(T) fps_kernel(const float* __restrict__ pts, int N, int D, const int* __restrict__ start, int m,
                                                 int* __restrict__ out) {
+    pdl_prologue();
     const int v = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = T / 32;
     const float* base = pts + (long long)v * N * D;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(T) fps_kernel(const float* __restrict__ pts, i
 // [0, N) cannot be reported from the device without a synchronisation: they are clamped into the cloud.
 __global__ void __launch_bounds__(256) fps_reorder_kernel(const float* __restrict__ pts, int N, int D, const int* __restrict__ picks,
                                                           int m, float* __restrict__ out) {
+    pdl_prologue();
     extern __shared__ unsigned char flag[];   // N bytes, then 256 ints
     int* cnt = reinterpret_cast<int*>(flag + ((N + 15) & ~15));
     const int v = blockIdx.x, tid = threadIdx.x;
@@ -123,7 +125,7 @@ template <int T, int PPT>
 static int launch_fps(const float* pts, int V, int N, int D, const int* start, int m, int* out, cudaStream_t st) {
     ScopedTimer timer(TAG_FPS, st);
     count_launch();
-    fps_kernel<T, PPT><<<V, T, 0, st>>>(pts, N, D, start, m, out);
+    FACL_LAUNCH_OK(launch_pdl(fps_kernel<T, PPT>, dim3(V), dim3(T), 0, st, pts, N, D, start, m, out));
     return (int)cudaGetLastError();
 }
 
@@ -149,7 +151,7 @@ int fps_reorder_launch(const float* pts, int V, int N, int D, const int* picks, 
     }
     ScopedTimer timer(TAG_FPS, st);
     count_launch();
-    fps_reorder_kernel<<<V, 256, smem, st>>>(pts, N, D, picks, m, out);
+    FACL_LAUNCH_OK(launch_pdl(fps_reorder_kernel, dim3(V), dim3(256), smem, st, pts, N, D, picks, m, out));
     return (int)cudaGetLastError();
 }
 

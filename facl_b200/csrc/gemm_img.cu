@@ -26,6 +26,7 @@ constexpr uint32_t IMG_LBO = 8192, IMG_SBO = 1024;   // B tile as staged: 64-row
 
 template <int NHL, int EPI>
 __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmParams p) {
+    pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
     // Two rings: A tiles (one per 64-wide k-block) and B HALF tiles (32 of the 64 k of a block when B is reduced over its
@@ -605,6 +606,7 @@ struct ImgParams {
 };
 
 __global__ void __launch_bounds__(256) act_image_kernel(const ImgParams q) {
+    pdl_prologue();
     const int cg = blockIdx.y;
     const int c8 = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = cg * 8 + c8;
@@ -725,7 +727,7 @@ int launch_gemm_img(const GemmParams& p, cudaStream_t stream) {
     else if (p.out_mode == OUT_CHMAJOR && tidy && p.zin && !p.pool && (p.ldz % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.zin) & 15) == 0)) epi = 2;
     ScopedTimer timer(p.tag, stream);
     count_launch();
-#define FACL_IMG_LAUNCH(N, E) gemm_img_kernel<N, E><<<grid, IMG_THREADS, smem_bytes, stream>>>(p)
+#define FACL_IMG_LAUNCH(N, E) FACL_LAUNCH_OK(launch_pdl(gemm_img_kernel<N, E>, dim3(grid), dim3(IMG_THREADS), smem_bytes, stream, p))
     if (p.nsplit == 3) {
         if (epi == 1) FACL_IMG_LAUNCH(2, 1); else if (epi == 2) FACL_IMG_LAUNCH(2, 2); else if (epi == 3) FACL_IMG_LAUNCH(2, 3);
         else if (epi == 4) FACL_IMG_LAUNCH(2, 4); else if (epi == 5) FACL_IMG_LAUNCH(2, 5); else FACL_IMG_LAUNCH(2, 0);
@@ -750,7 +752,7 @@ int act_image_launch(const OperandSrc& src, long long ld1, int C, long long R, c
     dim3 grid((unsigned)(img.rbs + 3) / 4, (unsigned)img.cgs);
     ScopedTimer timer(tag, st);
     count_launch();
-    act_image_kernel<<<grid, 256, 0, st>>>(q);
+    FACL_LAUNCH_OK(launch_pdl(act_image_kernel, grid, dim3(256), 0, st, q));
     return (int)cudaGetLastError();
 }
 

@@ -168,6 +168,7 @@ __device__ __forceinline__ void produce_xt4(const OperandSrc& s, uint8_t* hi, ui
 }
 
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmParams p) {
+    pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
     const int nhl = (p.nsplit == 3) ? 2 : 1;
@@ -449,7 +450,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t stream) {
     }
     ScopedTimer timer(p.tag, stream);
     count_launch();
-    gemm_tc_kernel<<<grid, THREADS, smem_bytes, stream>>>(p);
+    FACL_LAUNCH_OK(launch_pdl(gemm_tc_kernel, dim3(grid), dim3(THREADS), smem_bytes, stream, p));
     return (int)cudaGetLastError();
 }
 

@@ -48,6 +48,7 @@ __device__ __forceinline__ void insert_smallest(float (&t)[T], float d) {
 template <bool D4, int T, int NPL>
 __global__ void __launch_bounds__(GW * 32) group_kernel(const float* __restrict__ points, int N, int D, int S, int K, float r2,
                                                         float* __restrict__ xt, int* __restrict__ idx_out) {
+    pdl_prologue();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* tile = reinterpret_cast<float4*>(smem_raw);                                  // TILE_PTS x 16 B
     unsigned long long* cand_all = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)(N < TILE_PTS ? N : TILE_PTS) * 16);
@@ -295,13 +296,13 @@ int group_launch(const float* points, int M, int N, int D, int S, int K, float r
     const int T = (K + 31) / 32 + 1;           // smallest distances tracked per lane in pass 1
 #define FACL_GROUP_LAUNCH(TT)                                                                                     \
     do {                                                                                                          \
-        if (d4) group_kernel<true, TT, 0><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);      \
-        else group_kernel<false, TT, 0><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);        \
+        if (d4) FACL_LAUNCH_OK(launch_pdl(group_kernel<true, TT, 0>, dim3(grid), dim3(GW * 32), smem, st, points, N, D, S, K, r2, xt, idx_out));      \
+        else FACL_LAUNCH_OK(launch_pdl(group_kernel<false, TT, 0>, dim3(grid), dim3(GW * 32), smem, st, points, N, D, S, K, r2, xt, idx_out));        \
     } while (0)
     // the training shapes (K = 64; N = 2048 or 1024): distances stay in registers between the two passes
     if (d4 && T == 3 && (N == 2048 || N == 1024)) {
-        if (N == 2048) group_kernel<true, 3, 64><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);
-        else group_kernel<true, 3, 32><<<grid, GW * 32, smem, st>>>(points, N, D, S, K, r2, xt, idx_out);
+        if (N == 2048) FACL_LAUNCH_OK(launch_pdl(group_kernel<true, 3, 64>, dim3(grid), dim3(GW * 32), smem, st, points, N, D, S, K, r2, xt, idx_out));
+        else FACL_LAUNCH_OK(launch_pdl(group_kernel<true, 3, 32>, dim3(grid), dim3(GW * 32), smem, st, points, N, D, S, K, r2, xt, idx_out));
         return (int)cudaGetLastError();
     }
     switch (T) {

@@ -15,6 +15,7 @@ namespace facl {
 namespace {
 
 __global__ void xyz_rows_kernel(const float* __restrict__ feats, int C, int N1, float4* __restrict__ rows, long long total) {
+    pdl_prologue();
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     long long m = t / N1;
@@ -28,6 +29,7 @@ constexpr int GT = 256;
 
 __global__ void __launch_bounds__(GT) gather_channels_kernel(const float* __restrict__ feats, const int* __restrict__ idx, int C, int N1,
                                                              int S2, int K, float* __restrict__ out) {
+    pdl_prologue();
     extern __shared__ float rows[];                 // [CH][N1]
     const int m = blockIdx.y, c0 = blockIdx.x * CH;
     const int nch = min(CH, C - c0);
@@ -66,7 +68,7 @@ int group_level2_launch(const float* feats, int M, int C, int N1, int S2, int K,
     {
         ScopedTimer timer(TAG_GROUP2, st);
         count_launch();
-        xyz_rows_kernel<<<div_up(total, 256), 256, 0, st>>>(feats, C, N1, xyz, total);
+        FACL_LAUNCH_OK(launch_pdl(xyz_rows_kernel, dim3(div_up(total, 256)), dim3(256), 0, st, feats, C, N1, xyz, total));
         FACL_CHECK(cudaGetLastError());
     }
     int e = group_launch(reinterpret_cast<const float*>(xyz), M, N1, 4, S2, K, r2, nullptr, nbr, st);
@@ -75,7 +77,7 @@ int group_level2_launch(const float* feats, int M, int C, int N1, int S2, int K,
     if (smem > 48 * 1024) FACL_CHECK(cudaFuncSetAttribute(gather_channels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ScopedTimer timer(TAG_GROUP2, st);
     count_launch();
-    gather_channels_kernel<<<dim3((C + CH - 1) / CH, M), GT, smem, st>>>(feats, nbr, C, N1, S2, K, out);
+    FACL_LAUNCH_OK(launch_pdl(gather_channels_kernel, dim3(dim3((C + CH - 1) / CH, M)), dim3(GT), smem, st, feats, nbr, C, N1, S2, K, out));
     return (int)cudaGetLastError();
 }
 

@@ -140,6 +140,7 @@ __device__ __forceinline__ void mma_weight_act(uint32_t d_tmem, UDesc a, uint32_
 constexpr uint32_t H2_LBO = 16384, H2_LO = 8192;
 template <bool PASS_B, int STAT, bool GRAM>
 __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_kernel(const L1Params p) {
+    pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
     const int nhl = p.nhl;
@@ -626,6 +627,7 @@ __device__ __forceinline__ float produce_h1_tile64(const float4* xtile, uint8_t*
 constexpr int C_THREADS = 22 * 32;
 
 __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParams p) {
+    pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
     const int nhl = p.nhl;
@@ -1062,6 +1064,7 @@ constexpr int D_STAGES = 3;
 constexpr int D_STAGE_BYTES = 4 * IMG64;
 
 __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParams p) {
+    pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
     const int nhl = p.nhl;
@@ -1325,6 +1328,7 @@ __global__ void __launch_bounds__(256) l1_prep_kernel(const float* __restrict__ 
                                                       const float* __restrict__ bias, const float* __restrict__ c2,
                                                       const float* __restrict__ e0, uint8_t* __restrict__ p_img, float* __restrict__ q,
                                                       uint8_t* __restrict__ e_img) {
+    pdl_prologue();
     __shared__ double red[PREP_SLICES - 1][PREP_ROWS * 8][9];
     const int slice = threadIdx.x / (PREP_ROWS * 8), t = threadIdx.x % (PREP_ROWS * 8);
     const int j = blockIdx.x * PREP_ROWS + (t >> 3), chunk = t & 7;
@@ -1377,6 +1381,7 @@ __global__ void __launch_bounds__(256) l1_fin_kernel(const float* __restrict__ W
                                                      const float* __restrict__ H, const float* __restrict__ s,
                                                      const float* __restrict__ e0, const float* __restrict__ sparse,
                                                      float* __restrict__ dW, int accumulate) {
+    pdl_prologue();
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= C * 64) return;
     const int c = idx >> 6, j = idx & 63;
@@ -1392,6 +1397,7 @@ __global__ void __launch_bounds__(1024) l1_dw1_kernel(const float* __restrict__ 
                                                       const float* __restrict__ w1, const float* __restrict__ b1,
                                                       const float* __restrict__ c0, const float* __restrict__ c1,
                                                       const float* __restrict__ c2, float* __restrict__ dw1) {
+    pdl_prologue();
     // 16 slices of the P partials x 64 channels, reduced through shared memory
     __shared__ double red[16][64][4];
     const int i = threadIdx.x & 63, slice = threadIdx.x >> 6;
@@ -1420,6 +1426,7 @@ size_t l1_bwd_d_smem() { return 16384 + 16384 + D_STAGES * D_STAGE_BYTES + 16384
 
 // sum x (4) and sum x x^T (10 unique) over all rows, in double
 __global__ void __launch_bounds__(256) l1_moments_kernel(const float4* __restrict__ xt, long long R, double* __restrict__ out) {
+    pdl_prologue();
     double s[14];
 #pragma unroll
     for (int i = 0; i < 14; ++i) s[i] = 0.0;
@@ -1452,6 +1459,7 @@ __global__ void l1_bn1_kernel(const double* __restrict__ mom, double n, const fl
                               const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
                               float eps, float momentum, int training, float* __restrict__ mean, float* __restrict__ rstd,
                               float* __restrict__ scale, float* __restrict__ shift) {
+    pdl_prologue();
     int c = threadIdx.x;
     if (c >= 64) return;
     double mu, var;
@@ -1499,7 +1507,7 @@ int l1_moments_launch(const float* xt, long long R, double* mom14, cudaStream_t 
     FACL_CHECK(cudaMemsetAsync(mom14, 0, 14 * sizeof(double), st));
     ScopedTimer timer(TAG_L1_MISC, st);
     count_launch();
-    l1_moments_kernel<<<kNumSMs * 4, 256, 0, st>>>(reinterpret_cast<const float4*>(xt), R, mom14);
+    FACL_LAUNCH_OK(launch_pdl(l1_moments_kernel, dim3(kNumSMs * 4), dim3(256), 0, st, reinterpret_cast<const float4*>(xt), R, mom14));
     return (int)cudaGetLastError();
 }
 
@@ -1508,8 +1516,8 @@ int l1_bn1_launch(const double* mom14, double n, const float* w1, const float* b
                   float* scale, float* shift, cudaStream_t st) {
     ScopedTimer timer(TAG_BN, st);
     count_launch();
-    l1_bn1_kernel<<<1, 64, 0, st>>>(mom14, n, w1, b1, gamma, beta, running_mean, running_var, eps, momentum, training, mean, rstd,
-                                    scale, shift);
+    FACL_LAUNCH_OK(launch_pdl(l1_bn1_kernel, dim3(1), dim3(64), 0, st, mom14, n, w1, b1, gamma, beta, running_mean, running_var, eps, momentum, training, mean, rstd,
+                                    scale, shift));
     return (int)cudaGetLastError();
 }
 
@@ -1541,13 +1549,13 @@ int l1_fwd_launch(bool pass_b, const float* xt, long long R, int K, int nsplit, 
     ScopedTimer timer(pass_b ? TAG_L1_PASS_B : TAG_L1_PASS_A, st);
     count_launch();
     if (!pass_b)
-        l1_fwd_kernel<false, 1, false><<<grid, NTHREADS_A, l1_smem_bytes(false), st>>>(p);
+        FACL_LAUNCH_OK(launch_pdl(l1_fwd_kernel<false, 1, false>, dim3(grid), dim3(NTHREADS_A), l1_smem_bytes(false), st, p));
     else if (stat_mode == 0)
-        l1_fwd_kernel<true, 0, false><<<grid, NTHREADS_B, l1_smem_bytes(true), st>>>(p);
+        FACL_LAUNCH_OK(launch_pdl(l1_fwd_kernel<true, 0, false>, dim3(grid), dim3(NTHREADS_B), l1_smem_bytes(true), st, p));
     else if (!gram)
-        l1_fwd_kernel<true, 1, false><<<grid, NTHREADS_B, l1_smem_bytes(true), st>>>(p);
+        FACL_LAUNCH_OK(launch_pdl(l1_fwd_kernel<true, 1, false>, dim3(grid), dim3(NTHREADS_B), l1_smem_bytes(true), st, p));
     else
-        l1_fwd_kernel<true, 1, true><<<grid, NTHREADS_B, l1_smem_bytes(true), st>>>(p);
+        FACL_LAUNCH_OK(launch_pdl(l1_fwd_kernel<true, 1, true>, dim3(grid), dim3(NTHREADS_B), l1_smem_bytes(true), st, p));
     return (int)cudaGetLastError();
 }
 
@@ -1581,7 +1589,7 @@ int l1_prep_launch(const float* W, int C, const float* d, const float* bias, con
     if (C <= 0 || (e_img && C != 64)) return (int)cudaErrorInvalidValue;
     ScopedTimer timer(TAG_L1_MISC, st);
     count_launch();
-    l1_prep_kernel<<<PREP_BLOCKS, 256, 0, st>>>(W, C, d, bias, c2, e0, reinterpret_cast<uint8_t*>(p_img), q, reinterpret_cast<uint8_t*>(e_img));
+    FACL_LAUNCH_OK(launch_pdl(l1_prep_kernel, dim3(PREP_BLOCKS), dim3(256), 0, st, W, C, d, bias, c2, e0, reinterpret_cast<uint8_t*>(p_img), q, reinterpret_cast<uint8_t*>(e_img)));
     return (int)cudaGetLastError();
 }
 
@@ -1589,7 +1597,7 @@ int l1_fin_launch(const float* W, int C, const float* d, const float* bias, cons
                   const float* e0, const float* sparse, float* dW, int accumulate, cudaStream_t st) {
     ScopedTimer timer(TAG_L1_MISC, st);
     count_launch();
-    l1_fin_kernel<<<(C * 64 + 255) / 256, 256, 0, st>>>(W, C, d, bias, c2, H, s, e0, sparse, dW, accumulate);
+    FACL_LAUNCH_OK(launch_pdl(l1_fin_kernel, dim3((C * 64 + 255) / 256), dim3(256), 0, st, W, C, d, bias, c2, H, s, e0, sparse, dW, accumulate));
     return (int)cudaGetLastError();
 }
 
@@ -1615,7 +1623,7 @@ int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, c
     p.dbg_mask1 = g_dbg_mask1; p.dbg_mask2 = g_dbg_mask2;
     ScopedTimer timer(TAG_L1_PASS_C, st);
     count_launch();
-    l1_bwd_c_kernel<<<l1_bwd_grid(R), C_THREADS, l1_bwd_c_smem(), st>>>(p);
+    FACL_LAUNCH_OK(launch_pdl(l1_bwd_c_kernel, dim3(l1_bwd_grid(R)), dim3(C_THREADS), l1_bwd_c_smem(), st, p));
     return (int)cudaGetLastError();
 }
 
@@ -1636,7 +1644,7 @@ int l1_bwd_d_launch(const float* xt, long long R, int nsplit, const float* w1, c
     p.stats = stats;
     ScopedTimer timer(TAG_L1_PASS_D, st);
     count_launch();
-    l1_bwd_d_kernel<<<l1_bwd_grid(R), D_THREADS, l1_bwd_d_smem(), st>>>(p);
+    FACL_LAUNCH_OK(launch_pdl(l1_bwd_d_kernel, dim3(l1_bwd_grid(R)), dim3(D_THREADS), l1_bwd_d_smem(), st, p));
     return (int)cudaGetLastError();
 }
 
@@ -1644,7 +1652,7 @@ int l1_dw1_launch(const float* amat, int P, const double* mom14, const float* w1
                   const float* c2, float* dw1, cudaStream_t st) {
     ScopedTimer timer(TAG_L1_MISC, st);
     count_launch();
-    l1_dw1_kernel<<<1, 1024, 0, st>>>(amat, P, mom14, w1, b1, c0, c1, c2, dw1);
+    FACL_LAUNCH_OK(launch_pdl(l1_dw1_kernel, dim3(1), dim3(1024), 0, st, amat, P, mom14, w1, b1, c0, c1, c2, dw1));
     return (int)cudaGetLastError();
 }
 

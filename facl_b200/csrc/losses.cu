@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(LF_THREADS) loss_finalize_kernel(const float* 
                                                                    int want_global, int want_circle, float* __restrict__ loss,
                                                                    float* __restrict__ lcG, float* __restrict__ pgG,
                                                                    float* __restrict__ lcC, float* __restrict__ pgC) {
+    pdl_prologue();
     const int G = ix.G, B = ix.B;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // merge the per-CTA online log-sum-exp partials of every anchor row: m = max_p m_p, e = sum_p e_p exp(m_p - m)
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(LF_THREADS) loss_finalize_kernel(const float* 
 }
 
 __global__ void invert_order_kernel(const int* __restrict__ order, int G, int* __restrict__ inv) {
+    pdl_prologue();
     int i = threadIdx.x;
     if (i < G) inv[order[i]] = i;
 }
@@ -307,15 +309,15 @@ int contrast_losses(const float* x, const float* xg, const float* keys, int G, i
     if (!keys_are_x) RUN(make_image(keys, Mk, C, w.im_keys));
     if (want_circle) {
         RUN(sim(image(w.im_x, Ml, C), Ml, 0, 1, nullptr));
-        invert_order_kernel<<<1, 256, 0, st>>>(order, G, w.inv);
+        FACL_LAUNCH_OK(launch_pdl(invert_order_kernel, dim3(1), dim3(256), 0, st, order, G, w.inv));
     }
     if (want_global) {
         RUN(make_image(xg, Bl, C, w.im_xg));
         RUN(sim(image(w.im_xg, Bl, C), Bl, Ml, 1, nullptr));
     }
-    loss_finalize_kernel<<<1, LF_THREADS, 0, st>>>(w.pos, ix, order, partX, gemm_tc_ctas_per_mtile(Ml, Mk), partG,
+    FACL_LAUNCH_OK(launch_pdl(loss_finalize_kernel, dim3(1), dim3(LF_THREADS), 0, st, w.pos, ix, order, partX, gemm_tc_ctas_per_mtile(Ml, Mk), partG,
                                                    gemm_tc_ctas_per_mtile(Bl, Mk), w.rmax, w.rsum, want_global, want_circle, loss, w.lcG,
-                                                   w.pgG, w.lcC, w.pgC);
+                                                   w.pgG, w.lcC, w.pgC));
     FACL_CHECK_LAUNCH();
     // feature matrices as packed A operands: A[m = c][k = row] = feat[row][c]
     RUN(pack_weight_launch(keys, 1, C, C, Mk, w.img_keys, st));

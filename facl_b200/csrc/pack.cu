@@ -11,6 +11,7 @@ namespace facl {
 namespace {
 __global__ void pack_weight_kernel(const float* __restrict__ src, long long sm, long long sk, int Md, int Kd, int KBp, long long tasks,
                                    uint8_t* __restrict__ img) {
+    pdl_prologue();
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= tasks) return;
     int j = (int)(t & 7);
@@ -33,6 +34,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, long long sm, 
 
 // several matrices in one launch (the per-step re-packing of all encoder weights): job table passed by value
 __global__ void pack_weights_batched_kernel(const PackTable tbl) {
+    pdl_prologue();
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= tbl.total) return;
     int ji = 0;
@@ -72,7 +74,7 @@ int pack_table_launch(const PackTable& tbl, cudaStream_t st) {
     if (tbl.n <= 0) return 0;
     ScopedTimer timer(TAG_PACK, st);
     count_launch();
-    pack_weights_batched_kernel<<<div_up(tbl.total, 256), 256, 0, st>>>(tbl);
+    FACL_LAUNCH_OK(launch_pdl(pack_weights_batched_kernel, dim3(div_up(tbl.total, 256)), dim3(256), 0, st, tbl));
     return (int)cudaGetLastError();
 }
 
@@ -87,7 +89,7 @@ int pack_weight_launch(const float* src, long long sm, long long sk, int Md, int
     long long tasks = (long long)numMT * KBp * 1024;
     ScopedTimer timer(TAG_PACK, st);
     count_launch();
-    pack_weight_kernel<<<div_up(tasks, 256), 256, 0, st>>>(src, sm, sk, Md, Kd, KBp, tasks, reinterpret_cast<uint8_t*>(image));
+    FACL_LAUNCH_OK(launch_pdl(pack_weight_kernel, dim3(div_up(tasks, 256)), dim3(256), 0, st, src, sm, sk, Md, Kd, KBp, tasks, reinterpret_cast<uint8_t*>(image)));
     return (int)cudaGetLastError();
 }
 

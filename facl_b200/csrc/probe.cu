@@ -14,6 +14,7 @@ namespace {
 __global__ void softmax_xent_kernel(const float* __restrict__ logits, const int* __restrict__ labels, int rows, int C,
                                     float* __restrict__ loss, float* __restrict__ dlogits_t, float* __restrict__ dbias,
                                     int* __restrict__ hits) {
+    pdl_prologue();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* z = logits + (long long)row * C;
@@ -57,7 +58,7 @@ int softmax_xent_launch(const float* logits, const int* labels, int rows, int C,
     if (!logits || !labels || rows <= 0 || C <= 0) return (int)cudaErrorInvalidValue;
     ScopedTimer timer(TAG_LOSS_MISC, st);
     count_launch();
-    softmax_xent_kernel<<<div_up((long long)rows * 32, 256), 256, 0, st>>>(logits, labels, rows, C, loss, dlogits_t, dbias, hits);
+    FACL_LAUNCH_OK(launch_pdl(softmax_xent_kernel, dim3(div_up((long long)rows * 32, 256)), dim3(256), 0, st, logits, labels, rows, C, loss, dlogits_t, dbias, hits));
     return (int)cudaGetLastError();
 }
 

@@ -10,6 +10,7 @@ namespace facl {
 namespace {
 // (B,G,N,4) -> (G*B,N,4): cloud g*B+b = view g of sample b (cn3d_train_motion_GL.py:225-226); float4 rows
 __global__ void gmajor_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int G, int N) {
+    pdl_prologue();
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * G * N;
     if (t >= total) return;
@@ -19,6 +20,7 @@ __global__ void gmajor_kernel(const float4* __restrict__ in, float4* __restrict_
     out[t] = in[((long long)b * G + g) * N + n];
 }
 __global__ void centres_kernel(const float* __restrict__ clouds, int M, int N, int S, float* __restrict__ centres) {
+    pdl_prologue();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= M * S) return;
     int m = t / S, s = t % S;
@@ -29,10 +31,13 @@ __global__ void centres_kernel(const float* __restrict__ clouds, int M, int N, i
 }
 struct OrderVals { int v[FACL_MAX_VIEWS]; };
 __global__ void set_order_kernel(const OrderVals o, int G, int* __restrict__ order) {
+    pdl_prologue();
     if ((int)threadIdx.x < G) order[threadIdx.x] = o.v[threadIdx.x];
 }
-__global__ void add2_kernel(const float* __restrict__ v, float* __restrict__ out) { out[0] = v[0] + v[1]; }
+__global__ void add2_kernel(const float* __restrict__ v, float* __restrict__ out) {
+    pdl_prologue(); out[0] = v[0] + v[1]; }
 __global__ void axpy1_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
+    pdl_prologue();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] += x[i];
 }
@@ -42,13 +47,13 @@ int gmajor_launch(const float* in, float* out, int B, int G, int N, cudaStream_t
     ScopedTimer timer(TAG_TRANSPOSE, st);
     count_launch();
     long long total = (long long)B * G * N;
-    gmajor_kernel<<<div_up(total, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), B, G, N);
+    FACL_LAUNCH_OK(launch_pdl(gmajor_kernel, dim3(div_up(total, 256)), dim3(256), 0, st, reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), B, G, N));
     return (int)cudaGetLastError();
 }
 int centres_launch(const float* clouds, int M, int N, int S, float* centres, cudaStream_t st) {
     ScopedTimer timer(TAG_POOLMISC, st);
     count_launch();
-    centres_kernel<<<div_up((long long)M * S, 256), 256, 0, st>>>(clouds, M, N, S, centres);
+    FACL_LAUNCH_OK(launch_pdl(centres_kernel, dim3(div_up((long long)M * S, 256)), dim3(256), 0, st, clouds, M, N, S, centres));
     return (int)cudaGetLastError();
 }
 
@@ -98,21 +103,21 @@ int facl_train_step(const facl_train_step_args* a, void* stream) {
                 ov.v[i] = o;
             }
             count_launch();
-            set_order_kernel<<<1, FACL_MAX_VIEWS, 0, st>>>(ov, G, a->order);
+            FACL_LAUNCH_OK(launch_pdl(set_order_kernel, dim3(1), dim3(FACL_MAX_VIEWS), 0, st, ov, G, a->order));
             FACL_CHECK_LAUNCH();
         }
         if ((rc = facl_contrast_losses(a->x, a->x_global, a->keys, G, Bglob, Bl, a->sample_offset, 512, a->order, 1, 1, 3 /* the losses run the split products in both modes: see facl_contrast_losses */,
                                        a->loss_ws, a->loss2, a->dx, a->dx_global, dkeys, stream)))
             return rc;
         count_launch();
-        add2_kernel<<<1, 1, 0, st>>>(a->loss2, a->loss2 + 2);
+        FACL_LAUNCH_OK(launch_pdl(add2_kernel, dim3(1), dim3(1), 0, st, a->loss2, a->loss2 + 2));
         FACL_CHECK_LAUNCH();
     }
     if (phases & (FACL_PHASE_BACKWARD | FACL_PHASE_BACKWARD_HEAD)) {
         if (a->dx_extra) {
             long long n = (long long)M * 512;
             count_launch();
-            axpy1_kernel<<<div_up(n, 256), 256, 0, st>>>(a->dx, a->dx_extra, n);
+            FACL_LAUNCH_OK(launch_pdl(axpy1_kernel, dim3(div_up(n, 256)), dim3(256), 0, st, a->dx, a->dx_extra, n));
             FACL_CHECK_LAUNCH();
         }
     }
