@@ -313,10 +313,13 @@ def run_ours(args):
         # the same loop fed through DevicePrefetcher (the H2D copy of batch i+1 under step i), the one-line change INTEGRATION.md shows
         from facl_b200.train import DevicePrefetcher
         sync_all()
-        tb = time.perf_counter()
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for batch in DevicePrefetcher([host[i % nb] for i in range(asteps)], device=f"cuda:{local_rank}"):
+        tb = None
+        for i, batch in enumerate(DevicePrefetcher([host[i % nb] for i in range(asteps + 2)], device=f"cuda:{local_rank}")):
+            if i == 2:                                                # two untimed steps: the prefetcher allocates its two device slots
+                sync_all()
+                tb = time.perf_counter()
+                b0.record()
             _ = float(tr.step(batch, order=order))
         b1.record()
         sync_all()

@@ -132,6 +132,8 @@ int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, c
                     const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
                     const void* w3_img, const void* p3_img, const float* q3, const unsigned char* arg, const float* dpooled,
                     long long ldp, const float* c3_0, void* dh2, float* dw3, float* stats, int K, cudaStream_t st);
+int l1_gamma0_fix_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1, const float* shift1,
+                         const float* w2, const float* b2, const float* scale2, const void* dh2, float* stats, cudaStream_t st);
 int l1_bwd_d_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1,
                     const float* shift1, const void* e0w2_img, const void* p2_img, const float* q2, const void* dh2, float* dw2s,
                     float* gram, float* hsum, float* amat, float* stats, cudaStream_t st);

@@ -654,13 +654,13 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         mbar_init(h1_empty, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&d2_full[i], 1);
-            mbar_init(&d2_empty[i], 8);        // h2 producers + dh2 consumers both read z2
+            mbar_init(&d2_empty[i], 4);        // the h2 producers read z2 (the dh2 consumers take mask and z2 from the h2 image)
         }
         mbar_init(dh_full, 1);
         mbar_init(dh_empty, 4);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&h2_full[i], 4);
-            mbar_init(&h2_empty[i], 1);
+            mbar_init(&h2_empty[i], 5);        // tcgen05.commit of the MMAs that read the stage + the four dh2 consumer warps
         }
         mbar_init(sp_full, 8);
         mbar_init(sp_empty, 1);
@@ -900,34 +900,28 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         const float b2 = __ldg(p.b2 + j), a2 = __ldg(p.scale2 + j);
         const float c2 = fmaf(a2, b2, __ldg(p.shift2 + j));
         const float q3 = __ldg(p.q3 + j);
+        // The ReLU2 mask and z2 come from the h2 image the producers left in shared memory, not from the z2 accumulator: under the
+        // MMA stream's TMEM traffic a tcgen05.ld round trip costs ~500 cycles (role profile), and the SINGLE dh2 accumulator is held
+        // for as long as this role's loads take.  With no z2 in registers both halves of dh2 are loaded under one wait (1500 -> 500
+        // cycles of hold per tile).  h2 = a2 z + c2 > 0 on the active rows, so z2 + b2 = (h2 - c2) / a2 + b2 there, and only active
+        // rows contribute to sum dh2' (z2 + b2):  q = sum dh2' (h2 - c2),  sum dh2' (z2 + b2) = q / a2 + b2 sum dh2'.
+        // (a2 == 0, a BatchNorm weight that is exactly zero: l1_gamma0_fix_kernel recomputes that channel's sum from the inputs.)
         float s_acc = 0.f, q_acc = 0.f;
         PROF_DECL(5)
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
-            const int b = it & 1, u = (it >> 1) & 1;
-            mbar_wait(&d2_full[b], u);
-            PROF_MARK(0)
-            tc_fence_after_sync();
-            float z[32], g[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(64 * b + colhalf * 32), z);
-            tmem_ld_wait();
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d2_empty[b]);
-            PROF_MARK(1)
-            mbar_wait(dh_full, it & 1);
+            const int b = it & 1;
+            mbar_wait(dh_full, it & 1);                 // implies h2(it) is complete in stage b (the MMAs that read it have run)
             PROF_MARK(2)
             tc_fence_after_sync();
+            float g[32];
             tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 + colhalf * 32), g);
             if (nhl == 2) {
+                float gl[32];                          // the B_lo products (columns 64..127)
+                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(192 + colhalf * 32), gl);
+                tmem_ld_wait();
 #pragma unroll
-                for (int hq = 0; hq < 2; ++hq) {       // the B_lo products (columns 64..127), 16 at a time to keep registers low
-                    float gl[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(192 + colhalf * 32 + hq * 16), gl);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) g[hq * 16 + i] += gl[i];
-                }
+                for (int i = 0; i < 32; ++i) g[i] += gl[i];
             } else {
                 tmem_ld_wait();
             }
@@ -935,16 +929,33 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             __syncwarp();
             if (lane == 0) mbar_arrive(dh_empty);
             PROF_MARK(3)
+            // this thread's 32 rows of h2 (4 chunks of 8, hi and lo) into registers at once, so that the stage can be handed back to
+            // the h2 producers before the arithmetic and the global stores below (holding it through them stalled the producers of
+            // tile it + 2, measured)
+            const uint8_t* h2img = h2s + b * 2 * IMG64;
+            uint4 hh[4], hl[4];
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+                const uint32_t hoff = sw128_offset((uint32_t)j, (uint32_t)(colhalf * 4 + g8));
+                hh[g8] = *reinterpret_cast<const uint4*>(h2img + hoff);
+                hl[g8] = (nhl == 2) ? *reinterpret_cast<const uint4*>(h2img + IMG64 + hoff) : make_uint4(0u, 0u, 0u, 0u);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h2_empty[b]);   // the h2 stage may be refilled: the MMA stream and these four warps have read it
             uint8_t* out = p.dh2 + (t0 + it) * (2 * IMG64);
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
+                const uint32_t hw[4] = {hh[g8].x, hh[g8].y, hh[g8].z, hh[g8].w}, lw[4] = {hl[g8].x, hl[g8].y, hl[g8].z, hl[g8].w};
                 float v8[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int i = g8 * 8 + e;
-                    const float v = (fmaf(a2, z[i], c2) > 0.f) ? g[i] + q3 : 0.f;
+                    const uint32_t hb = (e & 1) ? (hw[e >> 1] & 0xFFFF0000u) : (hw[e >> 1] << 16);     // bf16 -> fp32 bits
+                    const uint32_t lb = (e & 1) ? (lw[e >> 1] & 0xFFFF0000u) : (lw[e >> 1] << 16);
+                    const float h2v = __uint_as_float(hb) + __uint_as_float(lb);
+                    const float v = hb ? g[i] + q3 : 0.f;                    // bf16(h2) != 0  <=>  ReLU2 active
                     s_acc += v;
-                    q_acc = fmaf(v, z[i] + b2, q_acc);
+                    q_acc = fmaf(v, h2v - c2, q_acc);
                     v8[e] = v;
                 }
                 store_img8(out, nhl, IMG64, j, colhalf * 4 + g8, v8);
@@ -953,9 +964,10 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         }
 #ifdef FACL_PROFILE_ROLES
         if (blockIdx.x == 1 && warp == 16 && lane == 0)
-            printf("pass C dh2 consumer, cycles/tile: wait d2_full %lld | ld z2 + arrive %lld | wait dh_full %lld | ld dh2 + arrive %lld | mask+sums+global store %lld\n",
-                   prof_[0] / my_tiles, prof_[1] / my_tiles, prof_[2] / my_tiles, prof_[3] / my_tiles, prof_[4] / my_tiles);
+            printf("pass C dh2 consumer, cycles/tile: wait dh_full %lld | ld dh2 + arrive %lld | mask+sums+global store %lld\n",
+                   prof_[2] / my_tiles, prof_[3] / my_tiles, prof_[4] / my_tiles);
 #endif
+        q_acc = (a2 != 0.f) ? q_acc / a2 + b2 * s_acc : 0.f;
         float* st = p.stats + ((long long)(blockIdx.x * 2 + colhalf) * 64 + j) * 2;
         st[0] = s_acc;
         st[1] = q_acc;
@@ -1421,6 +1433,55 @@ __global__ void __launch_bounds__(1024) l1_dw1_kernel(const float* __restrict__ 
     }
 }
 
+// Degenerate BatchNorm weight.  Pass C derives sum dh2' (z2 + b2) from the h2 image as q / a2 + b2 sum dh2' (a2 = gamma2 rstd2), which is
+// undefined for a channel whose gamma2 is EXACTLY zero (h2 is then constant and carries no z2).  Such a channel gets 0 from pass C and
+// its sum from here: z2 recomputed from the 16-byte input rows on CUDA cores, dh2' read back from the image pass C wrote.  One block; it
+// returns after reading the 64 scales when no channel is degenerate (the normal case).
+__global__ void __launch_bounds__(1024) l1_gamma0_fix_kernel(const float4* __restrict__ xt, long long R, const float* __restrict__ w1,
+                                                             const float* __restrict__ b1, const float* __restrict__ scale1,
+                                                             const float* __restrict__ shift1, const float* __restrict__ w2,
+                                                             const float* __restrict__ b2, const float* __restrict__ scale2,
+                                                             const uint8_t* __restrict__ dh2, int nhl, float* __restrict__ stats) {
+    pdl_prologue();
+    __shared__ int any;
+    __shared__ double red[32];
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    if (threadIdx.x < 64 && scale2[threadIdx.x] == 0.f) any = 1;
+    __syncthreads();
+    if (!any) return;
+    for (int j = 0; j < 64; ++j) {
+        if (scale2[j] != 0.f) continue;
+        double acc = 0.0;
+        for (long long r = threadIdx.x; r < R; r += 1024) {
+            const float4 x = __ldg(xt + r);
+            float z = 0.f;
+            for (int i = 0; i < 64; ++i) {
+                const float s1 = scale1[i];
+                const float h = fmaxf(fmaf(s1 * w1[4 * i], x.x, fmaf(s1 * w1[4 * i + 1], x.y, fmaf(s1 * w1[4 * i + 2], x.z,
+                                      fmaf(s1 * w1[4 * i + 3], x.w, fmaf(s1, b1[i], shift1[i]))))), 0.f);
+                z = fmaf(w2[j * 64 + i], h, z);
+            }
+            const long long tile = r >> 6;
+            const int rr = (int)(r & 63);
+            const uint8_t* at = dh2 + tile * (2 * IMG64) + sw128_offset((uint32_t)j, (uint32_t)(rr >> 3)) + (rr & 7) * 2;
+            float g = __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(at)) << 16);
+            if (nhl == 2) g += __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(at + IMG64)) << 16);
+            acc += (double)g * (double)(z + b2[j]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 32; ++w) t += red[w];
+            stats[(0 * 64 + j) * 2 + 1] += (float)t;          // partial 0 of channel j (pass C left 0 in every partial)
+        }
+        __syncthreads();
+    }
+}
+
 size_t l1_bwd_c_smem() { return 16384 + 65536 + 16384 + 2 * IMG64 + 4 * IMG64 + 65536 + 2 * BT * 16 + 256 + 1024; }
 size_t l1_bwd_d_smem() { return 16384 + 16384 + D_STAGES * D_STAGE_BYTES + 16384 + D_STAGES * BT * 16 + 256 + 1024; }
 
@@ -1624,6 +1685,15 @@ int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, c
     ScopedTimer timer(TAG_L1_PASS_C, st);
     count_launch();
     FACL_LAUNCH_OK(launch_pdl(l1_bwd_c_kernel, dim3(l1_bwd_grid(R)), dim3(C_THREADS), l1_bwd_c_smem(), st, p));
+    return (int)cudaGetLastError();
+}
+
+int l1_gamma0_fix_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1, const float* shift1,
+                         const float* w2, const float* b2, const float* scale2, const void* dh2, float* stats, cudaStream_t st) {
+    ScopedTimer timer(TAG_L1_MISC, st);
+    count_launch();
+    FACL_LAUNCH_OK(launch_pdl(l1_gamma0_fix_kernel, dim3(1), dim3(1024), 0, st, reinterpret_cast<const float4*>(xt), R, w1, b1, scale1, shift1, w2,
+                              b2, scale2, reinterpret_cast<const uint8_t*>(dh2), (nsplit == 3) ? 2 : 1, stats));
     return (int)cudaGetLastError();
 }
 

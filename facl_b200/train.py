@@ -101,32 +101,48 @@ class DevicePrefetcher:
     def __init__(self, loader, device="cuda"):
         self.loader, self.device = loader, torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = None                 # two persistent device buffers: no allocator traffic on the hot path
+        self.free = [None, None]          # event after the last compute-stream use of each slot
 
-    def _start(self, item):
+    def _start(self, item, k):
         batch = item[0] if isinstance(item, (tuple, list)) else item
-        if not batch.is_cuda and not batch.is_pinned():
+        if batch.is_cuda:
+            return item, batch.to(torch.float32), None
+        if not batch.is_pinned():
             batch = batch.pin_memory()
+        if self.slots is None or self.slots[0].shape != batch.shape:
+            self.slots = [torch.empty(batch.shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self.free = [None, None]
         with torch.cuda.stream(self.stream):
-            dev = batch.to(self.device, dtype=torch.float32, non_blocking=True)
+            if self.free[k] is not None:
+                self.stream.wait_event(self.free[k])
+            self.slots[k].copy_(batch, non_blocking=True)      # converts float64 loader tensors on the fly (:228)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return item, dev, ev
+        return item, self.slots[k], ev
 
     def __iter__(self):
         it = iter(self.loader)
+        k = 0
         try:
-            nxt = self._start(next(it))
+            nxt = self._start(next(it), k)
         except StopIteration:
             return
         while nxt is not None:
             item, dev, ev = nxt
+            cur_slot = k
+            k ^= 1
             try:
-                nxt = self._start(next(it))
+                nxt = self._start(next(it), k)
             except StopIteration:
                 nxt = None
-            torch.cuda.current_stream().wait_event(ev)
-            dev.record_stream(torch.cuda.current_stream())
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
             yield (dev, *item[1:]) if isinstance(item, (tuple, list)) else dev
+            # the consumer has issued its work on `dev`: the slot may be overwritten once that work has run
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream())
+            self.free[cur_slot] = done
 
 
 class FusedTrainStep:

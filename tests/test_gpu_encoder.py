@@ -472,6 +472,22 @@ def test_fine_default_geometry(golden_dir, fused):
         assert rel2(p.grad, ref) <= 1e-3 or rms_err / gscale <= 1e-6, (k, rel2(p.grad, ref))
 
 
+def test_fused_l1_backward_zero_bn_weight(golden_dir):
+    """A BatchNorm weight that is EXACTLY zero in net3DV_1's second layer: the fused backward cannot derive that channel's
+    sum dh2' z2 from the (constant) activation and recomputes it from the inputs (l1_gamma0_fix_kernel); a zero gamma in the first
+    and third layer exercises the sign / max-vs-min selection of the pooled layer.  Same matched-decision check as above."""
+    z, sd0 = load_fixture(golden_dir)
+    B, G, N, S, K = (int(v) for v in z["cfg"])
+    sd0 = {k: v.clone() for k, v in sd0.items()}
+    sd0["net3DV_1.4.weight"][5] = 0.0
+    sd0["net3DV_1.4.weight"][40] = 0.0
+    sd0["net3DV_1.4.bias"][40] = -0.3            # one degenerate channel inactive everywhere, one active everywhere
+    sd0["net3DV_1.4.bias"][5] = 0.25
+    sd0["net3DV_1.1.weight"][7] = 0.0
+    sd0["net3DV_1.7.weight"][9] = 0.0
+    _check_fused_backward(torch.from_numpy(z["points"]), sd0, z["order"], B, G, N, S, K, float(z["r2"]), TOL_GRAD["fp32"])
+
+
 def test_fused_l1_backward_bf16_8x20x2048():
     """bf16 mode (the arithmetic of BASELINE configs[2]) at 8 sequences x 20 views x 2048 points: features and loss within 2e-2 of
     the fp64 oracle, every parameter gradient within 2e-2 of the oracle's back-propagation of the same upstream gradient under
