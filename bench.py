@@ -398,16 +398,18 @@ def run_ours(args):
     per_tag.sort(key=lambda d: -d["ms_per_step"])
     kernel_ms = sum(d["ms_per_step"] for d in per_tag)
     top = per_tag[0]
-    traffic = None
+    traffic, traffic_source = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and (B, G, N) == (CFG2["B"], CFG2["G"], CFG2["N"]) and cfg["precision"] == "fp32":
-        traffic = json.load(open(tpath)).get(top["name"])              # dram bytes per launch from the committed ncu --set full capture
+        tj = json.load(open(tpath))
+        traffic = tj.get(top["name"])                                   # dram bytes per launch from the committed ncu --set full capture
+        traffic_source = tj.get("_source")
     # bf16 (the 2e-2 mode) keeps the split products in net3DV_1, where every roofline kernel lives; only bf16_fast issues single products there
     split = 1.0 if cfg["precision"] == "bf16_fast" else 3.0
     if top["flops"]:
         achieved = top["flops"] / (top["ms_per_step"] * 1e-3) / 1e12   # per-step FLOPs of the tag / per-step time of the tag
         roof = dict(kernel=top["name"], bound="tensor", achieved=achieved, peak=peaks["tensor_sustained"], unit="TFLOP/s",
-                    frac=achieved / peaks["tensor_sustained"], traffic=traffic, peak_source=peaks["source"] + ", sustained bf16",
+                    frac=achieved / peaks["tensor_sustained"], traffic=traffic, traffic_source=traffic_source, peak_source=peaks["source"] + ", sustained bf16",
                     share_of_step=top["ms_per_step"] / (ms / args.steps),
                     note=f"algorithmic FLOPs; the {cfg['precision']} mode issues {split:.0f} bf16 products per FLOP, so its ceiling is "
                          f"{peaks['tensor_sustained'] / split:.0f} TFLOP/s (frac_of_mode_ceiling)",
@@ -416,7 +418,7 @@ def run_ours(args):
         nbytes = hbm_bytes.get(top["tag"], 0)
         achieved = nbytes / (top["ms_per_step"] * 1e-3) / 1e9
         roof = dict(kernel=top["name"], bound="hbm", achieved=achieved, peak=peaks["hbm"], unit="GB/s",
-                    frac=achieved / peaks["hbm"], traffic=traffic, peak_source=peaks["source"],
+                    frac=achieved / peaks["hbm"], traffic=traffic, traffic_source=traffic_source, peak_source=peaks["source"],
                     share_of_step=top["ms_per_step"] / (ms / args.steps))
     # whole-step tensor roofline: 15.93 GFLOP per sequence against the sustained bf16 peak
     step_flops = 796e6 * M
