@@ -273,6 +273,26 @@ def run_ours(args):
     # ---- N > 1: is the sharded loss the loss of the global batch?  One more step with a known view order; the embeddings of
     # every rank are gathered and rank 0 recomputes the losses through the world-size-1 facl_contrast_losses ----------------
     dist_check = None
+    dist_timeline = None
+    if dist is not None and args.dist_timeline:
+        # where a sharded step spends its time: CUDA events at every phase / collective boundary, 10 steps, max over ranks
+        res = {}
+        for mode, ov in (("bucketed_overlapped", True), ("single_allreduce", False)):
+            fused.overlap = ov
+            for i in range(3):
+                fused.step(dev[i % nb])
+            sync_all()
+            fused.enable_timeline(True)
+            for i in range(10):
+                fused.step(dev[i % nb])
+            tl = fused.timeline_ms()
+            fused.enable_timeline(False)
+            t = torch.tensor(list(tl.values()), device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[mode] = {k: round(float(v), 4) for k, v in zip(tl.keys(), t)}
+            res[mode]["sum"] = round(float(t.sum()), 4)
+        fused.overlap = True
+        dist_timeline = res
     if dist is not None:
         from facl_b200 import losses as facl_losses
         from facl_b200.dist import reference_order_from_keys
@@ -443,7 +463,7 @@ def run_ours(args):
                 gpu_launches=int(launches), launches_per_step=launches / args.steps,
                 roofline=roof, step_tensor_tflops=step_tf, step_tensor_frac=step_tf / peaks["tensor_sustained"],
                 kernel_ms_per_step=kernel_ms, kernels=per_tag, cpu_baseline=cpu, clocks=sampler.summary(),
-                api_path=api_path, cfg3_strong=cfg3, dist_loss_check=dist_check)
+                api_path=api_path, cfg3_strong=cfg3, dist_loss_check=dist_check, dist_timeline=dist_timeline)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -462,6 +482,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api-path", action="store_true")
     ap.add_argument("--no-cfg3", action="store_true")
+    ap.add_argument("--dist-timeline", action="store_true", help="N > 1: per-phase / per-collective milliseconds of the sharded step")
     ap.add_argument("--ref-batch", type=int, default=None, help="batch of the CPU reference arm (default: the configuration's 64)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -42,6 +42,8 @@ class DistributedFusedTrainStep(FusedTrainStep):
 
     def __init__(self, trainer, B, G, N, r2=0.06):
         super().__init__(trainer, B, G, N, r2=r2)
+        self.overlap = True          # bucketed all-reduce, large bucket under the net3DV_1 backward (False: one all-reduce at the end)
+        self._tl = None
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         M = G * B
@@ -60,6 +62,29 @@ class DistributedFusedTrainStep(FusedTrainStep):
             for p in trainer.netR.parameters():
                 dist.broadcast(p.data, src=0)
 
+    # ---- optional timeline: CUDA events on the compute stream at every phase / collective boundary (bench.py --dist-timeline) ----
+    PHASE_NAMES = ["forward", "all_gather(x)", "losses", "reduce_scatter(dkeys)", "backward head+net3DV_3", "backward net3DV_1",
+                   "all_reduce(small) + wait(big)", "adam + loss D2H"]
+
+    def enable_timeline(self, on=True):
+        self._tl = [] if on else None
+
+    def _mark(self):
+        if getattr(self, "_tl", None) is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._cur.append(ev)
+
+    def timeline_ms(self):
+        """Average milliseconds per phase over the recorded steps (synchronises)."""
+        torch.cuda.synchronize()
+        n = len(self._tl)
+        acc = [0.0] * len(self.PHASE_NAMES)
+        for evs in self._tl:
+            for i in range(len(self.PHASE_NAMES)):
+                acc[i] += evs[i].elapsed_time(evs[i + 1])
+        return {name: acc[i] / max(n, 1) for i, name in enumerate(self.PHASE_NAMES)}
+
     def _call(self, phases):
         self.args.phases = phases
         self._lib.check(self._lib.lib().facl_train_step(self.C.byref(self.args), self._lib.stream_ptr()), "facl_train_step")
@@ -67,29 +92,44 @@ class DistributedFusedTrainStep(FusedTrainStep):
     def step(self, batch, order=None, want_host_loss=False, next_batch=None):
         pf_slot = self._begin_step(batch, order, want_host_loss)
         multi = self.world > 1
+        self._cur = []
+        self._mark()
         self._call(PHASE_FORWARD)
+        self._mark()
         if multi:
             dist.all_gather_into_tensor(self.keys, self.x)
         else:
             self.keys.copy_(self.x)
+        self._mark()
         self._call(PHASE_LOSS)                                                 # losses, dx / dkeys
+        self._mark()
         if multi:
             dist.reduce_scatter_tensor(self.dkeys_loc, self.dkeys, op=dist.ReduceOp.SUM)
         else:
             self.dkeys_loc.copy_(self.dkeys)
         self.flat[0:3].copy_(self.loss2)                                        # this rank's loss shares ride in the small bucket
+        self._mark()
         self._call(PHASE_BACKWARD_HEAD)                                         # head + net3DV_3: 99 % of the gradient bytes are final
         big = None
-        if multi:
+        if multi and self.overlap:
             # asynchronous: NCCL's stream waits for the kernels issued so far and reduces the large bucket while the
-            # net3DV_1 backward (passes C / D, 2.7 ms) runs on the compute stream
+            # net3DV_1 backward (passes C / D, 2.2 ms) runs on the compute stream
             big = dist.all_reduce(self.flat[self.flat_l1_end:], op=dist.ReduceOp.SUM, async_op=True)
+        self._mark()
         self._call(PHASE_BACKWARD_L1)
+        self._mark()
         if multi:
-            dist.all_reduce(self.flat[:self.flat_l1_end], op=dist.ReduceOp.SUM)   # loss values + net3DV_1 gradients (86 KB)
-            big.wait()                                                          # compute stream waits for the large bucket
+            if big is not None:
+                dist.all_reduce(self.flat[:self.flat_l1_end], op=dist.ReduceOp.SUM)   # loss values + net3DV_1 gradients (86 KB)
+                big.wait()                                                      # compute stream waits for the large bucket
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)                # one bucket, after the whole backward
         self.loss2.copy_(self.flat[0:3])
+        self._mark()
         self._call(PHASE_UPDATE)                                                # Adam, loss D2H
+        self._mark()
+        if getattr(self, "_tl", None) is not None:
+            self._tl.append(self._cur)
         self._release_prefetched(pf_slot)
         if next_batch is not None:
             self.prefetch(next_batch)
