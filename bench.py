@@ -226,8 +226,10 @@ def run_ours(args):
     launches0 = L.facl_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    th0 = time.perf_counter()
     for i in range(args.steps):
         fused.step(dev[i % nb])
+    host_issue_ms = (time.perf_counter() - th0) * 1e3 / args.steps      # host time to ISSUE a step (no synchronisation inside)
     ev1.record()
     sync_all()
     ms = ev0.elapsed_time(ev1)
@@ -460,7 +462,7 @@ def run_ours(args):
                             loss_at_end=loss_dev),
                 e2e=dict(value=world * B * e2e_steps / (e2e_ms * 1e-3), unit="sequences/s", h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=4, ms_per_step=e2e_ms / e2e_steps),
-                gpu_launches=int(launches), launches_per_step=launches / args.steps,
+                gpu_launches=int(launches), launches_per_step=launches / args.steps, host_issue_ms_per_step=host_issue_ms,
                 roofline=roof, step_tensor_tflops=step_tf, step_tensor_frac=step_tf / peaks["tensor_sustained"],
                 kernel_ms_per_step=kernel_ms, kernels=per_tag, cpu_baseline=cpu, clocks=sampler.summary(),
                 api_path=api_path, cfg3_strong=cfg3, dist_loss_check=dist_check, dist_timeline=dist_timeline)

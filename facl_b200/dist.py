@@ -44,6 +44,9 @@ class DistributedFusedTrainStep(FusedTrainStep):
         super().__init__(trainer, B, G, N, r2=r2)
         self.overlap = True          # bucketed all-reduce, large bucket under the net3DV_1 backward (False: one all-reduce at the end)
         self._tl = None
+        import os
+        self.max_ahead = int(os.environ.get("FACL_MAX_AHEAD", "2"))   # steps the host may run ahead of the GPU (0: unbounded)
+        self._inflight = []
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         M = G * B
@@ -90,8 +93,14 @@ class DistributedFusedTrainStep(FusedTrainStep):
         self._lib.check(self._lib.lib().facl_train_step(self.C.byref(self.args), self._lib.stream_ptr()), "facl_train_step")
 
     def step(self, batch, order=None, want_host_loss=False, next_batch=None):
-        pf_slot = self._begin_step(batch, order, want_host_loss)
         multi = self.world > 1
+        if multi and self.max_ahead > 0:
+            # bounded run-ahead: the host may be at most `max_ahead` steps in front of the GPU.  Measured on 8 GPUs: a free-running
+            # host loop (every rank's Python thread issuing NCCL calls and ~100 launches per step without ever blocking) made the
+            # step 0.3 ms SLOWER than a loop that reads the loss back every step; NCCL's host-side threads compete with it.
+            while len(self._inflight) >= self.max_ahead:
+                self._inflight.pop(0).synchronize()
+        pf_slot = self._begin_step(batch, order, want_host_loss)
         self._cur = []
         self._mark()
         self._call(PHASE_FORWARD)
@@ -130,6 +139,10 @@ class DistributedFusedTrainStep(FusedTrainStep):
         self._mark()
         if getattr(self, "_tl", None) is not None:
             self._tl.append(self._cur)
+        if multi and self.max_ahead > 0:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._inflight.append(ev)
         self._release_prefetched(pf_slot)
         if next_batch is not None:
             self.prefetch(next_batch)
