@@ -111,6 +111,9 @@ SIGNATURES = {
     "facl_l2_normalize": (_I, [_P, _I, _I, _P, _P]),
     "facl_softmax_xent": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "facl_augment_views": (_I, [C.POINTER(AugmentArgs), _P]),
+    "facl_sinkhorn": (_I, [_P, _I, _I, _I, _P, _P]),
+    "facl_soft_xent": (_I, [_P, _P, _I, _I, _F, _P, _P, _P]),
+    "facl_kmeans": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "facl_packed_weight_bytes": (_SZ, [_I, _I]),
     "facl_pack_weight": (_I, [_P, _LL, _LL, _I, _I, _P, _P]),
     "facl_gemm_stat_partials": (_I, [_I, _I]),

@@ -21,6 +21,7 @@ import torch.nn as nn
 
 from . import _lib
 from .encoder_rt import LAYER_PREFIXES, EncoderFunction, EncoderWorkspace
+from .heads import distributed_sinkhorn, shoot_infs  # noqa: F401  (reference cn3d_model_conbag.py:391-425)
 
 nstates_plus_1 = [64, 64, 256]
 nstates_plus_2 = [128, 128, 256]

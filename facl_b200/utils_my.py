@@ -6,12 +6,14 @@ libfacl_b200.so on the GPU (no CPU path -- CPU tensors raise).
   group_points_3DV / _2048 / _nums / group_points   reference utils_my.py:255-291 / :7-42 / :293-328 / :217-253
   group_points_2 / group_points_2_3DV               reference utils_my.py:332-356 / :358-381 (level-2 set abstraction)
   global_contrast / circle_contrast / Info_NCE      reference utils_my.py:53-83 / :85-116 / :200-213
+  CLD_Loss / grouping / KMeans                      reference utils_my.py:152-198 (facl_b200/heads.py)
 """
 import numpy as np
 import torch
 
 from . import _lib, ops
 from .losses import contrast_losses, info_nce_logits_cuda
+from .heads import CLD_Loss, KMeans, grouping  # noqa: F401  (reference utils_my.py:152-198; disabled in the scripts by cld_if = 0)
 
 
 def _group(points, S, K, r2, N=None):

@@ -336,6 +336,19 @@ FACL_API int facl_l2_normalize(const float* x, int rows, int C, float* out, void
 FACL_API int facl_softmax_xent(const float* logits, const int* labels, int rows, int C, float* loss, float* dlogits_t, float* dbias,
                                int* hits, void* stream);
 
+/* ---- the loss heads the reference scripts disable by constants ------------------------------------------
+ * facl_sinkhorn replaces distributed_sinkhorn + shoot_infs (reference training_code/cn3d_model_conbag.py:391-425): q [K][B] fp32
+ * (K prototypes x B samples, already exponentiated as at cn3d_train_motion_GL.py:254-255) -> out [B][K], the rows of the
+ * Sinkhorn-Knopp normalised assignment (`(Q / sum_k Q).t()`); infinities are replaced by the maximum of the finite entries.
+ * facl_soft_xent replaces the inner SwAV term `-mean(sum(q * log(softmax(code / 0.1)), dim=1))` (cn3d_train_motion_GL.py:258-260):
+ * logits, q [rows][K]; accumulates the loss into *loss (memset first) and writes d loss / d logits [rows][K]; either may be NULL.
+ * facl_kmeans replaces KMeans (reference training_code/utils_my.py:180-198 = cn3d_train_motion_GL.py:52-70): x [N][D] fp32, centroids
+ * initialised to the first K rows, `iters` rounds of (assign to the FIRST nearest centroid, replace centroids by member means, empty
+ * clusters divide by 1) -> labels [N] int32 of the last assignment, centroids [K][D], counts [K] int32 (the divisors; may be NULL). */
+FACL_API int facl_sinkhorn(const float* q, int K, int B, int iters, float* out, void* stream);
+FACL_API int facl_soft_xent(const float* logits, const float* q, int rows, int K, float scale, float* loss, float* dlogits, void* stream);
+FACL_API int facl_kmeans(const float* x, int N, int D, int K, int iters, int* labels, float* centroids, int* counts, void* stream);
+
 /* ---- instrumentation: per-kernel device timing and launch counting (used by bench.py) ---------------------
  * facl_timing_enable(1): every tagged launch site is bracketed by CUDA events on its stream.
  * facl_timing_collect: synchronises on the recorded events, returns total ms / launches per tag and resets.

@@ -19,4 +19,5 @@ from .fps import farthest_point_sampling, fps_reorder_indices, fps_sample_data  
 from .grouping import knn_ball_indices, group_points, group_points_level2  # noqa: F401
 from .encoder import EncoderParams, encoder_forward, init_state_dict, STATE_KEYS  # noqa: F401
 from .losses import global_contrast, circle_contrast, info_nce_logits  # noqa: F401
+from . import heads  # noqa: F401
 from .train_step import train_step, train_step_sharded, adam_update  # noqa: F401

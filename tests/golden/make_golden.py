@@ -369,6 +369,75 @@ def gen_fine_geometry():
     print("fine_geometry.npz written; fp32 noise x", rel2(r32["x"], r64["x"]), "loss", r32["loss"], r64["loss"])
 
 
+def gen_heads():
+    """The disabled loss heads, from the reference functions themselves: distributed_sinkhorn (cn3d_model_conbag.py:391-406, also
+    with an overflowed entry for shoot_infs), the inline SwAV block of cn3d_train_motion_GL.py:240-261 (re-issued here line by line
+    around the reference's distributed_sinkhorn, queue = None), utils_my.KMeans / grouping / CLD_Loss (:152-198)."""
+    from oracle import heads as oh
+    out = {}
+    g = torch.Generator().manual_seed(77)
+    # ---- Sinkhorn
+    for i, (K, B, scale, inf) in enumerate([(64, 8, 1.0, False), (64, 64, 3.0, False), (16, 5, 1.0, True)]):
+        Q = torch.exp(torch.randn(K, B, generator=g) * scale)
+        if inf:
+            Q[3, 2] = float("inf")
+        ref = ref_model.distributed_sinkhorn(Q.clone(), 3)
+        mine = oh.distributed_sinkhorn(Q.clone(), 3)
+        assert torch.allclose(ref, mine, rtol=1e-5, atol=1e-7), i
+        out[f"sk_q_{i}"], out[f"sk_out_{i}"] = Q.numpy(), ref.numpy()
+    out["sk_n"] = np.array(3)
+    # ---- SwAV block (num_crop views of B samples, 64 prototypes)
+    G, B = 5, 8
+    x = torch.randn(G * B, 512, generator=g)
+    W = torch.randn(64, 512, generator=g) * 0.05
+    xr = x.clone().requires_grad_(True)
+    Wr = W.clone().requires_grad_(True)
+    x_nor = torch.nn.functional.normalize(xr, dim=1, p=2)          # cn3d_model_conbag.py:231
+    code = x_nor @ Wr.t()                                          # :232 (mapping, bias-free)
+    softmax = torch.nn.Softmax(dim=1)
+    loss_swa = 0
+    for crop_id in range(G - 1):                                   # cn3d_train_motion_GL.py:240-261, queue is None
+        with torch.no_grad():
+            po = code[B * crop_id:B * (crop_id + 1), :]
+            po = po / 0.03
+            po = torch.exp(po).t()
+            q = ref_model.distributed_sinkhorn(po, 3)[-B:]
+        subloss = 0
+        for v in np.delete(np.arange(G - 1), crop_id):
+            p = softmax(code[B * v: B * (v + 1)] / 0.1)
+            subloss = subloss - torch.mean(torch.sum(q * torch.log(p), dim=1))
+        loss_swa = loss_swa + subloss
+    loss_swa = loss_swa / (G - 1)
+    loss_swa.backward()
+    x2, W2 = x.clone().requires_grad_(True), W.clone().requires_grad_(True)
+    code2 = torch.nn.functional.normalize(x2, dim=1, p=2) @ W2.t()
+    mine = oh.swav_loss(code2, G, B)
+    mine.backward()
+    assert abs(float(mine) - float(loss_swa)) < 1e-5 * abs(float(loss_swa)) and torch.allclose(x2.grad, xr.grad, rtol=1e-4, atol=1e-7)
+    out.update(swav_x=x.numpy(), swav_w=W.numpy(), swav_cfg=np.array([G, B]), swav_loss=np.array(float(loss_swa)),
+               swav_dx=xr.grad.numpy(), swav_dw=Wr.grad.numpy(), swav_code=code.detach().numpy())
+    # ---- k-means / CLD on clustered unit vectors (assignments stable under rounding)
+    G, B = 6, 32
+    centers = torch.nn.functional.normalize(torch.randn(12, 512, generator=g), dim=1)
+    pick = torch.randint(0, 12, (G * B,), generator=g)
+    feats = torch.nn.functional.normalize(centers[pick] + 0.05 * torch.randn(G * B, 512, generator=g), dim=1)
+    fr = feats.clone().requires_grad_(True)
+    cl, c = ref_utils.KMeans(fr[: 3 * B], 60, 5)
+    ol, oc = oh.kmeans(feats[: 3 * B], 60, 5)
+    assert torch.equal(cl, ol) and torch.allclose(c, oc, rtol=1e-5, atol=1e-6)
+    opt = make_opt(B, 128)
+    loss_cld = ref_utils.CLD_Loss(0, G, fr, opt)
+    loss_cld.backward()
+    f2 = feats.clone().requires_grad_(True)
+    mine = oh.cld_loss(G, f2, B)
+    mine.backward()
+    assert abs(float(mine) - float(loss_cld)) < 1e-5 * abs(float(loss_cld)) and torch.allclose(f2.grad, fr.grad, rtol=1e-3, atol=1e-6)
+    out.update(cld_x=feats.numpy(), cld_cfg=np.array([G, B]), cld_loss=np.array(float(loss_cld)), cld_dx=fr.grad.numpy(),
+               km_labels=cl.numpy(), km_centroids=c.detach().numpy())
+    np.savez_compressed(os.path.join(HERE, "heads.npz"), **out)
+    print("heads.npz written: swav", float(loss_swa), "cld", float(loss_cld))
+
+
 def gen_losses():
     """Loss-only fixtures at a few (G,B,C) with larger magnitudes (values reach hundreds)."""
     out = {}
@@ -572,3 +641,4 @@ if __name__ == "__main__":
     gen_losses()
     gen_encoder_and_step()
     gen_fine_geometry()
+    gen_heads()

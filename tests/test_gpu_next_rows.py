@@ -299,3 +299,45 @@ def test_augmented_views_feed_the_training_step():
     want = oracle.train_step({k: v.clone() for k, v in sd0.items()}, torch.from_numpy(oviews), order, S=S, K=K, r2=0.06,
                              apply_update=False)
     assert abs(float(loss[2]) - want["loss"]) <= 1e-3 * abs(want["loss"]), (float(loss[2]), want["loss"])
+
+
+# ------------------------------------------------------------------------------------------------- disabled loss heads (f4)
+def test_sinkhorn_swav_cld_heads_match_reference(golden_dir):
+    """distributed_sinkhorn / shoot_infs (cn3d_model_conbag.py:391-425), the SwAV block of
+    cn3d_train_motion_GL.py:236-262 and utils_my.CLD_Loss / grouping / KMeans (:152-198) on the GPU, against outputs of the reference
+    functions themselves (heads.npz).  k-means labels are index work: bit-exact."""
+    import types
+    from facl_b200 import cn3d_model_conbag as MODELL, heads, utils_my
+    z = np.load(os.path.join(golden_dir, "heads.npz"))
+
+    def rel2(a, b):
+        a = torch.as_tensor(a).detach().double().cpu().reshape(-1)
+        b = torch.as_tensor(b).double().reshape(-1)
+        return float((a - b).norm() / b.norm())
+
+    for i in range(int(z["sk_n"])):
+        q = torch.from_numpy(z[f"sk_q_{i}"]).to(DEV)
+        got = MODELL.distributed_sinkhorn(q, 3)
+        assert np.allclose(got.cpu().numpy(), z[f"sk_out_{i}"], rtol=2e-5, atol=1e-7), i
+    t = torch.tensor([1.0, float("inf"), 3.0, -float("inf")], device=DEV)
+    assert MODELL.shoot_infs(t).tolist() == [1.0, 3.0, 3.0, 3.0]
+    # SwAV: x -> normalize -> mapping -> Sinkhorn targets / soft cross-entropy, gradients to x and mapping.weight
+    G, B = (int(v) for v in z["swav_cfg"])
+    x = torch.from_numpy(z["swav_x"]).to(DEV).requires_grad_(True)
+    w = torch.from_numpy(z["swav_w"]).to(DEV).requires_grad_(True)
+    x_nor, code = heads.normalized_code(x, w)
+    assert rel2(code, z["swav_code"]) <= 1e-4
+    loss = heads.swav_loss(code, G, B)
+    loss.backward()
+    assert abs(float(loss) - float(z["swav_loss"])) <= 1e-3 * abs(float(z["swav_loss"]))
+    assert rel2(x.grad, z["swav_dx"]) <= 2e-3 and rel2(w.grad, z["swav_dw"]) <= 2e-3
+    # CLD
+    G, B = (int(v) for v in z["cld_cfg"])
+    f = torch.from_numpy(z["cld_x"]).to(DEV).requires_grad_(True)
+    labels, cent = utils_my.KMeans(f.detach()[: 3 * B], 60, 5)
+    assert np.array_equal(labels.cpu().numpy(), z["km_labels"])
+    assert np.allclose(cent.cpu().numpy(), z["km_centroids"], rtol=1e-5, atol=1e-6)
+    loss = utils_my.CLD_Loss(0, G, f, types.SimpleNamespace(batchSize=B))
+    loss.backward()
+    assert abs(float(loss) - float(z["cld_loss"])) <= 1e-3 * abs(float(z["cld_loss"]))
+    assert rel2(f.grad, z["cld_dx"]) <= 2e-3

@@ -164,6 +164,31 @@ def test_fine_geometry_matches_reference(golden_dir):
             assert np.abs(got - ref).max() <= 1e-7 * scale + 1e-12, k
 
 
+def test_disabled_heads_match_reference(golden_dir):
+    """Sinkhorn, the SwAV block and the CLD k-means loss (disabled in the reference scripts by constants) against outputs of the
+    reference functions (tests/golden/make_golden.py: gen_heads)."""
+    from oracle import heads as oh
+    z = np.load(os.path.join(golden_dir, "heads.npz"))
+    for i in range(int(z["sk_n"])):
+        got = oh.distributed_sinkhorn(torch.from_numpy(z[f"sk_q_{i}"]), 3)
+        assert np.allclose(got.numpy(), z[f"sk_out_{i}"], rtol=1e-5, atol=1e-7), i
+    G, B = (int(v) for v in z["swav_cfg"])
+    x = torch.from_numpy(z["swav_x"]).requires_grad_(True)
+    w = torch.from_numpy(z["swav_w"]).requires_grad_(True)
+    loss = oh.swav_loss(torch.nn.functional.normalize(x, dim=1) @ w.t(), G, B)
+    loss.backward()
+    assert abs(float(loss) - float(z["swav_loss"])) < 1e-5 * abs(float(z["swav_loss"]))
+    assert np.allclose(x.grad.numpy(), z["swav_dx"], rtol=1e-4, atol=1e-7) and np.allclose(w.grad.numpy(), z["swav_dw"], rtol=1e-4, atol=1e-6)
+    G, B = (int(v) for v in z["cld_cfg"])
+    f = torch.from_numpy(z["cld_x"]).requires_grad_(True)
+    labels, cent = oh.kmeans(f.detach()[: 3 * B], 60, 5)
+    assert np.array_equal(labels.numpy(), z["km_labels"]) and np.allclose(cent.numpy(), z["km_centroids"], rtol=1e-5, atol=1e-6)
+    loss = oh.cld_loss(G, f, B)
+    loss.backward()
+    assert abs(float(loss) - float(z["cld_loss"])) < 1e-5 * abs(float(z["cld_loss"]))
+    assert np.allclose(f.grad.numpy(), z["cld_dx"], rtol=1e-3, atol=1e-6)
+
+
 def test_eval_forward_matches_reference(golden_dir):
     z, sd = _load_step_fixture(golden_dir)
     B, G, N, S, K = (int(v) for v in z["cfg"])
