@@ -291,6 +291,55 @@ def test_fused_step_equals_api_step_and_oracle(golden_dir):
         assert float((lc - ld).abs().max()) <= tol * float(ld.abs().max()), (i, lc, ld)
 
 
+def test_adam_state_dict_carries_step_and_fused_step_rebinds(golden_dir):
+    """Checkpoint resume: facl_b200.optim.Adam keeps its step count in state_dict() like torch.optim.Adam (state[p]["step"]), and a
+    FusedTrainStep bound to an optimiser whose state was replaced by load_state_dict() picks the new moment tensors up (their
+    device pointers are baked into its table).  Two runs -- uninterrupted, and saved / reloaded after step 2 -- must end identical."""
+    from facl_b200.train import FusedTrainStep, TrainStep
+    z, sd0 = load_fixture(golden_dir)
+    B, G, N, S, K = (int(v) for v in z["cfg"])
+    pts = torch.from_numpy(z["points"]).to(DEV)
+    order = z["order"]
+
+    def fresh():
+        opt = make_opt(B, N, S, K)
+        opt.learning_rate = 0.0003
+        net = MODELL.PointNet_Plus_fine(opt, gost=G, sample_num_level1=S, knn_K=K)
+        net.load_state_dict({k: v.clone() for k, v in sd0.items()})
+        tr = TrainStep(opt, num_crop=G, precision="fp32", model=net)
+        return tr, FusedTrainStep(tr, B, G, N, r2=0.06)
+
+    ta, fa = fresh()
+    for _ in range(2):
+        fa.step(pts, order=order)
+    torch.cuda.synchronize()
+    osd = ta.optimizer.state_dict()
+    steps = [int(st["step"]) for st in osd["state"].values()]
+    assert steps and all(s == 2 for s in steps)
+    # the state is interchangeable with torch.optim.Adam
+    ref_opt = torch.optim.Adam(ta.netR.parameters(), lr=3e-4, betas=(0.5, 0.999), eps=1e-6)
+    ref_opt.load_state_dict(osd)
+    msd = {k: v.clone() for k, v in ta.netR.state_dict().items()}
+    # resumed run: new model + optimiser objects, state loaded, then two more steps
+    tb, fb = fresh()
+    tb.netR.load_state_dict(msd)
+    tb.optimizer.load_state_dict(osd)
+    assert tb.optimizer._step == 2
+    for _ in range(2):
+        fa.step(pts, order=order)
+        fb.step(pts, order=order)
+    torch.cuda.synchronize()
+    assert fb.args.step == 4 and tb.optimizer._step == 4
+    sa, sb = ta.netR.state_dict(), tb.netR.state_dict()
+    for k in sa:
+        if sa[k].dtype.is_floating_point and "running_" not in k:
+            # same kernels, same inputs, same optimiser state: only atomic summation order differs between the two runs
+            assert float((sa[k] - sb[k]).abs().max()) <= 2.1 * 3e-4, k
+    ma = ta.optimizer.state[ta.netR.netR_FC[3].weight]["exp_avg"]
+    mb = tb.optimizer.state[tb.netR.netR_FC[3].weight]["exp_avg"]
+    assert float((ma - mb).norm() / ma.norm()) <= 1e-2
+
+
 def test_extract_features_layout(golden_dir):
     from facl_b200.train import extract_features
     z, sd0 = load_fixture(golden_dir)
