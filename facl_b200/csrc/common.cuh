@@ -28,16 +28,6 @@ __device__ __forceinline__ float sqdist_ref(float px, float py, float pz, float 
 
 __device__ __forceinline__ int div_up_dev(int a, int b) { return (a + b - 1) / b; }
 
-// Packed fp32 pair arithmetic (sm_100: FADD2 / FFMA2, one issue slot for two lanes of work).  The statistic loops of the TMEM
-// epilogues are issue-bound; per-channel sum and sum of squares (or sum of products) cost one instruction per element instead of two.
-//   (s0, s1) += (a, b);   (q0, q1) += (a, b) * (c, d)
-__device__ __forceinline__ void sum_and_dot2(float& s0, float& s1, float& q0, float& q1, float a, float b, float c, float d) {
-    asm("{\n\t.reg .b64 v, w, ss, qq;\n\tmov.b64 v, {%4, %5};\n\tmov.b64 w, {%6, %7};\n\tmov.b64 ss, {%0, %1};\n\tmov.b64 qq, {%2, %3};\n\t"
-        "add.rn.f32x2 ss, ss, v;\n\tfma.rn.f32x2 qq, v, w, qq;\n\tmov.b64 {%0, %1}, ss;\n\tmov.b64 {%2, %3}, qq;\n\t}"
-        : "+f"(s0), "+f"(s1), "+f"(q0), "+f"(q1)
-        : "f"(a), "f"(b), "f"(c), "f"(d));
-}
-
 }  // namespace facl
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

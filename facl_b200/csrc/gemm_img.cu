@@ -296,19 +296,11 @@ __global__ void __launch_bounds__(IMG_THREADS, 1) gemm_img_kernel(const GemmPara
                 for (int i = 0; i < 32; ++i) {
                     float val = v[i] + bias;
                     if (has_zin) val = (fmaf(zs0, z[i], zs2) > 0.f) ? val : 0.f;
-                    if (GEN && has_stats && i < nvalid) {
+                    if (has_stats && (!GEN || i < nvalid)) {
                         s0p[i & 3] += val;
                         s1p[i & 3] = fmaf(val, has_zin ? z[i] : val, s1p[i & 3]);
                     }
                     v[i] = val;
-                }
-                if (!GEN && has_stats) {     // whole 32-column chunks: packed pair arithmetic (FADD2 / FFMA2), two independent chains
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        sum_and_dot2(s0p[0], s0p[1], s1p[0], s1p[1], v[i], v[i + 1], has_zin ? z[i] : v[i], has_zin ? z[i + 1] : v[i + 1]);
-                        sum_and_dot2(s0p[2], s0p[3], s1p[2], s1p[3], v[i + 2], v[i + 3], has_zin ? z[i + 2] : v[i + 2],
-                                     has_zin ? z[i + 3] : v[i + 3]);
-                    }
                 }
                 stat0 += (s0p[0] + s0p[1]) + (s0p[2] + s0p[3]);
                 stat1 += (s1p[0] + s1p[1]) + (s1p[2] + s1p[3]);

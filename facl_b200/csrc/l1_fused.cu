@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             a2 = __ldg(p.scale2 + j);
             c2 = fmaf(a2, b2, __ldg(p.shift2 + j));
         }
-        float s_acc = 0.f, q_acc = 0.f, s_acc1 = 0.f, q_acc1 = 0.f, hsum = 0.f;      // (even, odd) rows: packed pair accumulators
+        float s_acc = 0.f, q_acc = 0.f, hsum = 0.f;
         long long nrows = 0;
         int it = 0;
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -403,7 +403,10 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                     tmem_ld_wait();
                     if (STAT == 1) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) sum_and_dot2(s_acc, s_acc1, q_acc, q_acc1, v[i], v[i + 1], v[i], v[i + 1]);
+                        for (int i = 0; i < 32; ++i) {
+                            s_acc += v[i];
+                            q_acc = fmaf(v[i], v[i], q_acc);
+                        }
                     }
                 }
                 tc_fence_before_sync();
@@ -435,8 +438,6 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             // statistics of z2 = acc + b2 from the sums of acc
             const float n = (float)nrows;
             float* st = p.stats + ((long long)(blockIdx.x * 2 + colhalf) * 64 + j) * 2;
-            s_acc += s_acc1;
-            q_acc += q_acc1;
             st[0] = fmaf(n, b2, s_acc);
             st[1] = q_acc + 2.f * b2 * s_acc + n * b2 * b2;
         }
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             const float b3 = __ldg(p.b3 + c);
             const float sgn = (__ldg(p.gamma3 + c) >= 0.f) ? 1.f : -1.f;
             const int K = p.K, groups = TILE / K;
-            float s_acc = 0.f, q_acc = 0.f, s_acc1 = 0.f, q_acc1 = 0.f;
+            float s_acc = 0.f, q_acc = 0.f;
             long long nrows = 0;
             int it = 0;
             for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -462,12 +463,12 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                     tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(256 + 128 * h + q * 32), v);
                     tmem_ld_wait();
                     if (K >= 32) {
-                        if (STAT == 1) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 2) sum_and_dot2(s_acc, s_acc1, q_acc, q_acc1, v[i], v[i + 1], v[i], v[i + 1]);
-                        }
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
+                            if (STAT == 1) {
+                                s_acc += v[i];
+                                q_acc = fmaf(v[i], v[i], q_acc);
+                            }
                             const float sv = v[i] * sgn;
                             barg = (sv > best) ? (q * 32 + i) : barg;
                             best = fmaxf(best, sv);
@@ -507,8 +508,6 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             if (STAT == 1) {
                 const float n = (float)nrows;
                 float* st = p.stats + ((long long)blockIdx.x * 256 + c) * 2;
-                s_acc += s_acc1;
-                q_acc += q_acc1;
                 st[0] = fmaf(n, b3, s_acc);
                 st[1] = q_acc + 2.f * b3 * s_acc + n * b3 * b3;
             }
