@@ -11,7 +11,8 @@ the sm_100a kernels of libfacl_b200.so (tcgen05 GEMMs with fused BatchNorm/ReLU/
   "bf16"      the mixed mode that meets the 2e-2 bound: single bf16 products for net3DV_3 layers 2-3 (32 % of the FLOPs), the
               split products kept for net3DV_1 and the 259-wide first net3DV_3 layer -- measured against the fp64 oracle,
               those layers carry 96 % of the all-bf16 error variance (an error made there is amplified ~12x by the BatchNorms and
-              max-pools downstream): embeddings within 9e-3 instead of 3.1e-2 (4 x 3 x 128) .. 4.4e-2 (8 x 20 x 2048);
+              max-pools downstream): embeddings within 9e-3 instead of 3.1e-2 (4 x 3 x 128) .. 4.4e-2 (8 x 20 x 2048); the net3DV_1
+              BACKWARD runs single bf16 products (gradients are long sums, stage-wise error <= 1e-2);
   "bf16_fast" every layer except the 4-wide first one and the head in single bf16 products (what autocast-style bf16 of the
               reference's modules computes: the same 3e-2 .. 4.5e-2 on the embeddings); fastest, outside the 2e-2 bound.
 `bf16_split_layers` overrides which of the seven conv/linear+BN layers keep the split products in the bf16 modes.

@@ -222,7 +222,8 @@ typedef struct facl_encoder_dims {
 } facl_encoder_dims;
 
 #define FACL_ENC_FUSED_L1 1   /* net3DV_1 as the fused tcgen05 kernels (csrc/l1_fused.cu) instead of per-layer GEMMs */
-#define FACL_ENC_SPLIT_LAYER(l) (1 << (8 + (l)))   /* bf16 mode (nsplit 1): layer l (0..8) keeps the bf16x3 split products */
+#define FACL_ENC_SPLIT_LAYER(l) (1 << (8 + (l)))   /* bf16 mode (nsplit 1): layer l (0..8) keeps the bf16x3 split products in the FORWARD */
+#define FACL_ENC_SPLIT_BACKWARD 2                  /* bf16 mode: the backward honours the FACL_ENC_SPLIT_LAYER mask too (default: single products) */
 
 /* Work buffers are owned by the caller: query the count / name / size, allocate each (256-byte aligned device
  * memory) and pass the pointer table.  Buffers flagged "backward only" may be NULL for forward-only use. */
