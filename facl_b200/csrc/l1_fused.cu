@@ -1219,16 +1219,20 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
         if (ptid < BT) xnext = __ldg(xg + ptid);
         float hsum = 0.f;
         int s = 0, ph = 0;
+        PROF_DECL(5)
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             float4* xtile = reinterpret_cast<float4*>(xs + s * BT * 16);
             mbar_wait(&x_free[s], ph ^ 1);                        // the dh1 consumers of the tile that used this x slot are done
+            PROF_MARK(0)
             if (ptid < BT) {
                 xtile[ptid] = xnext;
                 if (it + 1 < my_tiles) xnext = __ldg(xg + (long long)(it + 1) * BT + ptid);
             }
             named_bar_sync(1, 128);
+            PROF_MARK(1)
             mbar_wait(&st_empty[s], ph ^ 1);
+            PROF_MARK(2)
             // h1 image of this stage: hi at +IMG64, lo at +3*IMG64
             float acc = 0.f;
             uint8_t* img = stg + s * D_STAGE_BYTES + IMG64;
@@ -1244,11 +1248,18 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
                 store_img8(img, nhl, 2 * IMG64, ch, half * 4 + q, v);
             }
             hsum += acc;
+            PROF_MARK(3)
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&h1_full[s]);
+            PROF_MARK(4)
             if (++s == D_STAGES) { s = 0; ph ^= 1; }
         }
+#ifdef FACL_PROFILE_ROLES
+        if (blockIdx.x == 1 && ptid == 0)
+            printf("pass D h1 producer, cycles/tile: wait x_free %lld | x tile + bar %lld | wait st_empty %lld | produce %lld | fence+arrive %lld\n",
+                   prof_[0] / my_tiles, prof_[1] / my_tiles, prof_[2] / my_tiles, prof_[3] / my_tiles, prof_[4] / my_tiles);
+#endif
         atomicAdd(p.hsum + ch, hsum);
     } else {
         // ---- dh1 consumers (thread = channel i, hi or lo part): + q2, ReLU1 mask by recomputation, BN1 backward sums,
@@ -1262,12 +1273,14 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
         const bool live = (part == 0) || (nhl == 2);             // bf16 mode has no lo part: lanes 64..127 are meaningless
         float s_acc = 0.f, ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
         int s = 0;
+        PROF_DECL(3)
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
             const float4* xtile = reinterpret_cast<const float4*>(xs + s * BT * 16) + colhalf * 32;
             const uint8_t* h1img = stg + s * D_STAGE_BYTES + IMG64;      // bf16(h1) of this tile: non-zero <=> ReLU1 active
             mbar_wait(&dh_full[b], u);
+            PROF_MARK(0)
             tc_fence_after_sync();
             float g[32];
             tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 * b + colhalf * 32), g);
@@ -1281,6 +1294,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
                 tmem_ld_wait();
             }
             tc_fence_before_sync();
+            PROF_MARK(1)
             if (live) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -1302,8 +1316,14 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
                 mbar_arrive(&dh_empty[b]);
                 mbar_arrive(&x_free[s]);
             }
+            PROF_MARK(2)
             if (++s == D_STAGES) s = 0;
         }
+#ifdef FACL_PROFILE_ROLES
+        if (blockIdx.x == 1 && (warp == 0 || warp == 2) && lane == 0)
+            printf("pass D dh1 consumer (quarter %d), cycles/tile: wait dh_full %lld | TMEM loads %lld | mask+sums+arrive %lld\n", quarter,
+                   prof_[0] / my_tiles, prof_[1] / my_tiles, prof_[2] / my_tiles);
+#endif
         // z1 = w.x + b1 is affine in x, so sum dh1' z1 follows from A = sum dh1' x^T and sum dh1'
         const float q_acc = fmaf(w.x, ax, fmaf(w.y, ay, fmaf(w.z, az, fmaf(w.w, aw, b1 * s_acc))));
         const long long slot = (long long)(blockIdx.x * 4 + part * 2 + colhalf) * 64 + i;

@@ -3,7 +3,7 @@ set -u
 OUT=gpurun_out; TAG=${1:-r2c6}; mkdir -p $OUT
 timeout 1200 python -m pytest tests -m gpu -q -rf > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; grep -E "passed|failed|error" $OUT/${TAG}_tests.log | tail -3
 grep -E "^FAILED|^ERROR" $OUT/${TAG}_tests.log | head -20
-bash tools/role_profile.sh $TAG 2>&1 | grep -E "==|MMA thread|dh2 consumer|pass D mma|fwd pass B" | awk '!seen[$3$4$5]++' | head -12
+bash tools/role_profile.sh $TAG 2>&1 | grep -E "==|MMA thread|dh2 consumer|pass D|fwd pass B" | awk '!seen[$3$4$5]++' | head -12
 for PREC in fp32 bf16_fast; do
 timeout 600 python bench.py --precision $PREC --steps 30 --warmup 5 --no-cpu-baseline --no-cfg3 > $OUT/${TAG}_bench_$PREC.json 2> $OUT/${TAG}_bench_$PREC.err; echo "bench $PREC rc=$?"
 python - <<PY
