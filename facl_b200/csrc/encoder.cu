@@ -226,9 +226,13 @@ int check_dims(const facl_encoder_dims* d) {
 
 }  // namespace
 
+// stages: 1 = everything up to the cloud embeddings x (and x_nor / code), 2 = the head on the sequence features -> x_global, 3 = both.
+// A sharded caller starts the all-gather of x after stage 1; the sequence half of the head then runs beside the collective.
 int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, const float* xt, const float* centres,
-                    void* const* bufs, float* x, float* xg, float* x_nor, float* code, cudaStream_t st) {
+                    void* const* bufs, float* x, float* xg, float* x_nor, float* code, int stages, cudaStream_t st) {
     RUN(check_dims(d));
+    if ((stages & 3) == 0) return (int)cudaErrorInvalidValue;
+    const bool stage_x = (stages & 1) != 0, stage_g = (stages & 2) != 0;
     const int M = d->M, S = d->S, K = d->K, G = d->G, B = M / G, ns = mode_of(d), tr = d->training;
     const long long R3 = (long long)M * S, R1 = R3 * K, MB = M + B;
     if (R1 > 2147483647LL) return (int)cudaErrorInvalidValue;
@@ -239,6 +243,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     float* stats = tr ? F(B_STATS) : nullptr;
     uint8_t* wp = reinterpret_cast<uint8_t*>(bufs[B_WPACK]);
 
+    if (stage_x) {
     // constant vectors: L3 input transform for the 3 centre-xyz channels (identity, no ReLU), zero lower bounds
     RUN(encoder_const_vectors_launch(vec, st));
     // operand images of the current weights
@@ -256,6 +261,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
         }
         RUN(pack_table_launch(tbl, st));
     }
+    }
 
     auto finalize = [&](int layer, int slot_i, int Nd, double n) {
         Slot s = bn_slot(bufs, slot_i);
@@ -264,6 +270,7 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
                                   L.running_var, BN_EPS, BN_MOM, tr, s.mean, s.rstd, s.scale, s.shift, st);
     };
 
+    auto trunk = [&]() -> int {
     if (d->flags & FACL_ENC_FUSED_L1) {
         // ---- L1 fused: three launches, no per-row activation ever reaches HBM (l1_fused.cu) -------------------------
         if ((R1 % 128) != 0 || 128 % K != 0) return (int)cudaErrorInvalidValue;
@@ -376,8 +383,12 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
     }
     // ---- sequence aggregation: max over the G views (cn3d_model_conbag.py:225-226) ---------------------------
     RUN(seq_pool_launch(F(B_PALL), MB, p->layer[5].gamma, C_FEAT, G, B, F(B_PALL) + M, MB, U(B_ARGG), st));
+    return 0;
+    };
+    if (stage_x) RUN(trunk());
     // ---- head netR_FC on the M cloud features, then on the B sequence features (two BN batches) --------------
     for (int half = 0; half < 2; ++half) {
+        if (half == 0 ? !stage_x : !stage_g) continue;
         const int Nd = half == 0 ? M : B;
         const long long off = half == 0 ? 0 : M;
         Slot s5 = bn_slot(bufs, 5);
@@ -405,8 +416,8 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
         RUN(launch_gemm_tc(h, st));
     }
     // ---- x_nor = normalize(x), code = mapping(x_nor) (cn3d_model_conbag.py:231-232) ---------------------------
-    if (x_nor) RUN(l2_normalize_launch(x, M, C_EMB, x_nor, st));
-    if (code) {
+    if (x_nor && stage_x) RUN(l2_normalize_launch(x, M, C_EMB, x_nor, st));
+    if (code && stage_x) {
         if (!x_nor) return (int)cudaErrorInvalidValue;
         GemmParams g = gemm_base(C_MAP, M, C_EMB, layer_nsplit(ns, 8));
         g.tag = 24;
@@ -421,11 +432,13 @@ int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, co
 
 // stages: 1 = head + net3DV_3 (every gradient except net3DV_1's is final afterwards), 2 = net3DV_1, 3 = both.  The split lets a
 // data-parallel caller start the all-reduce of the large gradients while the net3DV_1 backward (43 % of the step) still runs.
+// Stage 1 itself splits into 4 = the SEQUENCE half of the head (needs dxg only) and 8 = the cloud half of the head + net3DV_3
+// (needs the final dx): the sharded caller runs 4 beside the reduce-scatter of the key-side gradients that completes dx.
 int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, const float* xt, void* const* bufs, const float* dx,
                      const float* dxg, const facl_encoder_grads* gr, int stages, cudaStream_t st) {
     RUN(check_dims(d));
-    if (!d->training || (stages & 3) == 0) return (int)cudaErrorInvalidValue;
-    const bool stage_hi = (stages & 1) != 0, stage_l1 = (stages & 2) != 0;
+    if (!d->training || (stages & 15) == 0) return (int)cudaErrorInvalidValue;
+    const bool head_g = (stages & (1 | 4)) != 0, head_x = (stages & (1 | 8)) != 0, stage_hi = head_x, stage_l1 = (stages & 2) != 0;
     // The FACL_ENC_SPLIT_LAYER mask of the bf16 mixed mode protects the FORWARD: an operand-rounding error made in net3DV_1 or the 259-wide
     // layer is amplified ~12x by the BatchNorms / max-pools downstream and lands in the embeddings.  The backward has no such
     // amplifier -- every weight gradient is a sum over 10^5..10^7 rows in which independent roundings average out -- so in bf16
@@ -444,7 +457,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
     float* stats = F(B_STATS);
     uint8_t* wt = reinterpret_cast<uint8_t*>(bufs[B_WPACKT]);
 
-    if (stage_hi) {
+    if (head_g) {
     // (the transposed weight images for the data-gradient GEMMs were packed by the training-mode forward)
     // weight gradients are accumulated with atomics (split-K): start from zero; biases in front of a BN get 0
     for (int l = 0; l < 7; ++l) {
@@ -453,12 +466,13 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
     }
     FACL_CHECK(cudaMemsetAsync(gr->dfc3_w, 0, sizeof(float) * C_EMB * C_FEAT, st));
 
-    // upstream gradients -> channel-major [512][M | B]
+    // upstream gradients -> channel-major [512][M | B]; the sequence columns first
     FACL_CHECK(cudaMemsetAsync(F(B_DXT), 0, sizeof(float) * C_EMB * MB, st));
-    if (dx) RUN(transpose_launch(dx, C_EMB, F(B_DXT), MB, M, C_EMB, st));
     if (dxg) RUN(transpose_launch(dxg, C_EMB, F(B_DXT) + M, MB, B, C_EMB, st));
+    }
+    if (head_x) {
+    if (dx) RUN(transpose_launch(dx, C_EMB, F(B_DXT), MB, M, C_EMB, st));
     RUN(rowstats_launch(F(B_DXT), nullptr, MB, C_EMB, (int)MB, 0, gr->dfc3_b, st));   // netR_FC.3.bias: sum over both batches
-
     }
     auto wgrad = [&](int layer, int Md, int Nd, int Kd, const OperandSrc& a, const OperandSrc& b, float* out) {
         GemmParams g = gemm_base(Md, Nd, Kd, layer_nsplit(ns, layer));
@@ -490,7 +504,9 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
 
     // ---- head -------------------------------------------------------------------------------------------------
     Slot s5 = bn_slot(bufs, 5);
-    for (int half = 0; half < 2 && stage_hi; ++half) {
+    // the sequence half (1) first: it does not need dx; the BatchNorm gradients of netR_FC.1 accumulate over the two halves
+    for (int half = 1; half >= 0; --half) {
+        if (half == 1 ? !head_g : !head_x) continue;
         const int Nd = half == 0 ? M : B;
         const long long off = half == 0 ? 0 : M;
         Slot s6 = bn_slot(bufs, 6 + half);
@@ -521,7 +537,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
         RUN(img_wgrad(7, C_EMB, C_FEAT, hi.dx, hi.h7, gr->dfc3_w));
         // grad wrt relu(bn(z7)), masked -> dh7, sums for BN(netR_FC.1)
         RUN(img_dgrad(7, C_FEAT, C_EMB, wt + wpackt_offset(7), hi.dx, F(B_Z7) + off, s6.scale, s6.shift, F(B_DH7) + off, true));
-        RUN(bwd_finalize(6, 6 + half, C_FEAT, Nd, (double)Nd, gemm_tc_ctas_per_mtile(C_FEAT, Nd), half));
+        RUN(bwd_finalize(6, 6 + half, C_FEAT, Nd, (double)Nd, gemm_tc_ctas_per_mtile(C_FEAT, Nd), half == 0 ? 1 : 0));
         // netR_FC.0: dW = dz7 * relu(bn6(pooled))^T ; data grad masked by the pooled feature's ReLU
         RUN(act_image_launch(src2(F(B_DH7) + off, F(B_Z7) + off, MB, s6.c0, s6.c1, s6.c2), 0, C_FEAT, Nd, nullptr, 0, layer_nhl(ns, 6),
                              hi.dz, TAG_IMAGE, st));
@@ -668,7 +684,7 @@ int facl_encoder_buffer_backward_only(int i) { return i >= FIRST_BWD_BUF ? 1 : 0
 int facl_encoder_forward(const facl_encoder_dims* dims, const facl_encoder_params* params, const float* xt, const float* centres,
                          void* const* buffers, float* x, float* x_global, float* x_nor, float* code, void* stream) {
     if (!dims || !params || !xt || !centres || !buffers || !x || !x_global) return (int)cudaErrorInvalidValue;
-    return encoder_forward(dims, params, xt, centres, buffers, x, x_global, x_nor, code, reinterpret_cast<cudaStream_t>(stream));
+    return encoder_forward(dims, params, xt, centres, buffers, x, x_global, x_nor, code, 3, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int facl_encoder_backward(const facl_encoder_dims* dims, const facl_encoder_params* params, const float* xt, void* const* buffers,

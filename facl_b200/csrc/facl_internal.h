@@ -112,6 +112,8 @@ struct facl_encoder_params;
 struct facl_encoder_grads;
 namespace facl {
 // encoder.cu
+int encoder_forward(const facl_encoder_dims* d, const facl_encoder_params* p, const float* xt, const float* centres, void* const* bufs,
+                    float* x, float* xg, float* x_nor, float* code, int stages, cudaStream_t st);
 int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, const float* xt, void* const* bufs, const float* dx,
                      const float* dxg, const facl_encoder_grads* gr, int stages, cudaStream_t st);
 // train_step.cu

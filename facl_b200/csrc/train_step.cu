@@ -75,7 +75,7 @@ int facl_train_step(const facl_train_step_args* a, void* stream) {
     const int phases = a->phases ? a->phases : FACL_PHASE_ALL;
     const int Bglob = a->B_global > 0 ? a->B_global : Bl;
     int rc;
-    if (phases & FACL_PHASE_FORWARD) {
+    if (phases & (FACL_PHASE_FORWARD | FACL_PHASE_FORWARD_X)) {
         const float* batch = a->points_bgnd;
         if (a->points_host) {   // end-to-end path: the batch starts in pinned host memory
             FACL_CHECK(cudaMemcpyAsync(a->staging, a->points_host, sizeof(float) * 4 * (size_t)M * N, cudaMemcpyHostToDevice, st));
@@ -85,8 +85,12 @@ int facl_train_step(const facl_train_step_args* a, void* stream) {
         if ((rc = gmajor_launch(batch, a->clouds, Bl, G, N, st))) return rc;
         if ((rc = group_launch(a->clouds, M, N, 4, S, K, a->r2, a->xt, nullptr, st))) return rc;
         if ((rc = centres_launch(a->clouds, M, N, S, a->centres, st))) return rc;
-        if ((rc = facl_encoder_forward(d, a->params, a->xt, a->centres, a->enc_buffers, a->x, a->x_global, nullptr, nullptr, stream)))
+        if ((rc = encoder_forward(d, a->params, a->xt, a->centres, a->enc_buffers, a->x, a->x_global, nullptr, nullptr,
+                                  (phases & FACL_PHASE_FORWARD) ? 3 : 1, st)))
             return rc;
+    }
+    if ((phases & FACL_PHASE_FORWARD_G) && !(phases & FACL_PHASE_FORWARD)) {
+        if ((rc = encoder_forward(d, a->params, a->xt, a->centres, a->enc_buffers, a->x, a->x_global, nullptr, nullptr, 2, st))) return rc;
     }
     if (phases & FACL_PHASE_LOSS) {
         // single GPU: keys == x and both gradient roles are summed into dx; sharded: dkeys is a separate buffer that the
@@ -113,7 +117,11 @@ int facl_train_step(const facl_train_step_args* a, void* stream) {
         FACL_LAUNCH_OK(launch_pdl(add2_kernel, dim3(1), dim3(1), 0, st, a->loss2, a->loss2 + 2));
         FACL_CHECK_LAUNCH();
     }
-    if (phases & (FACL_PHASE_BACKWARD | FACL_PHASE_BACKWARD_HEAD)) {
+    if ((phases & FACL_PHASE_BACKWARD_HEAD_G) && !(phases & (FACL_PHASE_BACKWARD | FACL_PHASE_BACKWARD_HEAD))) {
+        // the sequence half of the head needs dx_global only: it runs before dx += dx_extra, beside the caller's reduce-scatter
+        if ((rc = encoder_backward(d, a->params, a->xt, a->enc_buffers, nullptr, a->dx_global, a->grads, 4, st))) return rc;
+    }
+    if (phases & (FACL_PHASE_BACKWARD | FACL_PHASE_BACKWARD_HEAD | FACL_PHASE_BACKWARD_HEAD_X)) {
         if (a->dx_extra) {
             long long n = (long long)M * 512;
             count_launch();
@@ -126,6 +134,7 @@ int facl_train_step(const facl_train_step_args* a, void* stream) {
         // gradients on a side stream, and issues L1 -- the collective hides under passes C / D
         int stages = (phases & FACL_PHASE_BACKWARD) ? 3 : 0;
         if (phases & FACL_PHASE_BACKWARD_HEAD) stages |= 1;
+        else if (phases & FACL_PHASE_BACKWARD_HEAD_X) stages |= 8;
         if (phases & FACL_PHASE_BACKWARD_L1) stages |= 2;
         if (stages && (rc = encoder_backward(d, a->params, a->xt, a->enc_buffers, a->dx, a->dx_global, a->grads, stages, st))) return rc;
     }

@@ -8,9 +8,11 @@ SURVEY.md section 8e:
     the sequence max-pool, cn3d_model_conbag.py:225); rank r owns samples [r*Bl, (r+1)*Bl) and encodes them locally
     with per-rank BatchNorm statistics (what nn.DataParallel does);
   * forward exchange: all-gather of the per-rank view embeddings x_r (G*Bl, 512) -> keys (R*G*Bl, 512), rank-major.
-    Every rank evaluates the two losses for ITS anchors against ALL keys (global negatives);
+    Every rank evaluates the two losses for ITS anchors against ALL keys (global negatives).  The gather is asynchronous:
+    the head on the sequence features (x_global, which no other rank needs) runs beside it;
   * backward exchange: the key-side gradient dkeys (R*G*Bl, 512) is sum-reduce-scattered back to the owners, so the
-    gradient flows through the gather (the reference's helper is @no_grad);
+    gradient flows through the gather (the reference's helper is @no_grad).  Asynchronous as well: the sequence half of the
+    head backward needs dx_global only and runs beside it;
   * parameter gradients (+ the loss values) live in one flat buffer, reduced as TWO buckets: everything except
     net3DV_1's gradients (99 % of the bytes) is all-reduced asynchronously as soon as the net3DV_3 backward has produced
     it and hides under the net3DV_1 backward; the small rest follows.  Then every rank applies the same Adam step.
@@ -23,6 +25,7 @@ import torch.distributed as dist
 from .train import FusedTrainStep
 
 PHASE_FORWARD, PHASE_LOSS, PHASE_BACKWARD, PHASE_UPDATE, PHASE_BACKWARD_HEAD, PHASE_BACKWARD_L1 = 1, 2, 4, 8, 16, 32   # FACL_PHASE_*
+PHASE_FORWARD_X, PHASE_FORWARD_G, PHASE_BACKWARD_HEAD_G, PHASE_BACKWARD_HEAD_X = 64, 128, 256, 512
 
 
 def key_index(g, n, G, Bl):
@@ -66,8 +69,8 @@ class DistributedFusedTrainStep(FusedTrainStep):
                 dist.broadcast(p.data, src=0)
 
     # ---- optional timeline: CUDA events on the compute stream at every phase / collective boundary (bench.py --dist-timeline) ----
-    PHASE_NAMES = ["forward", "all_gather(x)", "losses", "reduce_scatter(dkeys)", "backward head+net3DV_3", "backward net3DV_1",
-                   "all_reduce(small) + wait(big)", "adam + loss D2H"]
+    PHASE_NAMES = ["forward to x", "head(x_global) + wait all_gather(x)", "losses", "head backward (sequence half) + wait reduce_scatter(dkeys)",
+                   "backward head (cloud half) + net3DV_3", "backward net3DV_1", "all_reduce(small) + wait(big)", "adam + loss D2H"]
 
     def enable_timeline(self, on=True):
         self._tl = [] if on else None
@@ -103,22 +106,28 @@ class DistributedFusedTrainStep(FusedTrainStep):
         pf_slot = self._begin_step(batch, order, want_host_loss)
         self._cur = []
         self._mark()
-        self._call(PHASE_FORWARD)
+        self._call(PHASE_FORWARD_X)                                             # ... -> cloud embeddings x
         self._mark()
         if multi:
-            dist.all_gather_into_tensor(self.keys, self.x)
+            ag = dist.all_gather_into_tensor(self.keys, self.x, async_op=True)  # NCCL's stream; the sequence head runs beside it
         else:
             self.keys.copy_(self.x)
+        self._call(PHASE_FORWARD_G)                                             # head on the sequence features -> x_global
+        if multi:
+            ag.wait()
         self._mark()
-        self._call(PHASE_LOSS)                                                 # losses, dx / dkeys
+        self._call(PHASE_LOSS)                                                  # losses, dx / dkeys
         self._mark()
         if multi:
-            dist.reduce_scatter_tensor(self.dkeys_loc, self.dkeys, op=dist.ReduceOp.SUM)
+            rs = dist.reduce_scatter_tensor(self.dkeys_loc, self.dkeys, op=dist.ReduceOp.SUM, async_op=True)
         else:
             self.dkeys_loc.copy_(self.dkeys)
         self.flat[0:3].copy_(self.loss2)                                        # this rank's loss shares ride in the small bucket
+        self._call(PHASE_BACKWARD_HEAD_G)                                       # sequence half of the head: needs dx_global only
+        if multi:
+            rs.wait()
         self._mark()
-        self._call(PHASE_BACKWARD_HEAD)                                         # head + net3DV_3: 99 % of the gradient bytes are final
+        self._call(PHASE_BACKWARD_HEAD_X)                                       # dx += dkeys_loc; cloud half + net3DV_3: 99 % of the gradient bytes are final
         big = None
         if multi and self.overlap:
             # asynchronous: NCCL's stream waits for the kernels issued so far and reduces the large bucket while the

@@ -321,6 +321,12 @@ typedef struct facl_train_step_args {
 #define FACL_PHASE_ALL 15
 #define FACL_PHASE_BACKWARD_HEAD 16  /* first half of BACKWARD: dx += dx_extra; head + net3DV_3 -> all gradients but net3DV_1's */
 #define FACL_PHASE_BACKWARD_L1 32    /* second half of BACKWARD: net3DV_1 (the all-reduce of the rest can run beside it) */
+/* finer cuts for a sharded caller that hides its two embedding exchanges as well (facl_b200/dist.py):
+ *   FORWARD = FORWARD_X then FORWARD_G;  BACKWARD_HEAD = BACKWARD_HEAD_G then BACKWARD_HEAD_X */
+#define FACL_PHASE_FORWARD_X 64        /* FORWARD up to the cloud embeddings x (the all-gather of x can start) */
+#define FACL_PHASE_FORWARD_G 128       /* the head on the sequence features -> x_global */
+#define FACL_PHASE_BACKWARD_HEAD_G 256 /* sequence half of the head backward: needs dx_global only (runs beside the reduce-scatter of dkeys) */
+#define FACL_PHASE_BACKWARD_HEAD_X 512 /* dx += dx_extra; cloud half of the head backward + net3DV_3 */
 
 FACL_API int facl_gmajor(const float* points_bgnd, float* clouds, int B, int G, int N, void* stream);
 FACL_API int facl_train_step(const facl_train_step_args* args, void* stream);
