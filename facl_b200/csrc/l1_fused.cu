@@ -574,7 +574,7 @@ struct L1BwdParams {
     float* amat;              // [2*grid][64][4] per-CTA sum dh1' x^T
     float* stats;             // [2*grid][64][2]: pass C (sum dh2', sum dh2' z2); pass D (sum dh1', sum dh1' z1)
     // optional test hooks (pass C): the ReLU decisions of the recomputed forward, so a checker can impose them
-    unsigned char* dbg_mask1; // [R/64][64][64]  h1 > 0
+    unsigned char* dbg_mask1; // [R/64][64][64]  h1 > 0 as pass D sees it (the only place the ReLU1 mask enters the backward)
     unsigned char* dbg_mask2; // [R/64][64][64]  h2 > 0
 };
 
@@ -823,13 +823,6 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             __syncwarp();
             if (lane == 0) mbar_arrive(h1_full);
             PROF_MARK(3)
-            if (p.dbg_mask1) {
-                for (int r = 0; r < 32; ++r) {
-                    float4 x = xtile[half * 32 + r];
-                    float v = fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf))));
-                    p.dbg_mask1[((t0 + it) * 64 + ch) * 64 + half * 32 + r] = v > 0.f ? 1 : 0;
-                }
-            }
         }
 #ifdef FACL_PROFILE_ROLES
         if (blockIdx.x == 1 && ptid == 0)
@@ -1062,7 +1055,8 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
 // pass D   (14 warps)
 // warps 0-7   : dh1 consumers: TMEM lane quarter = warp % 4, column half = warp / 4
 // warps 8-11  : x -> h1 image producers          warp 12 : MMA issuer          warp 13 : bulk-TMA loader of dh2' tiles
-// TMEM columns: DH1[b] 0..127 / 128..255 (column halves = B_hi / B_lo products), [dW2s ; H1] 256
+// TMEM columns: DH1[b] 0..127 / 128..255 (column halves = B_hi / B_lo products), [dW2s ; H1] 256, z1'[b] 320 / 384,
+//               A tiles (E0 W2)^T 448, P2 480
 //
 // Every product here has only 64 real output rows, so the M = 128 instruction is fed STACKED operands instead of padding:
 //  * a weight image is stored [hi 64 rows | lo 64 rows]; read as one 128-row A tile, lanes 0..63 receive A_hi * B and lanes
@@ -1074,6 +1068,8 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
 constexpr int D_THREADS = 14 * 32;
 constexpr int D_STAGES = 3;
 constexpr int D_STAGE_BYTES = 4 * IMG64;
+constexpr int D_XS = 4;                   // x ring (fp32 rows for the consumers + K = 16 rows for the z1' instruction): deeper than the
+                                          // stage ring, because x of tile t+1 is written while tile t-4's consumers may still read theirs
 
 __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParams p) {
     pdl_prologue();
@@ -1083,11 +1079,15 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
     uint8_t* ews = smem;                       // diag(e0) W2: hi 8 KB | lo 8 KB
     uint8_t* p2s = ews + 16384;                // P2:          hi 8 KB | lo 8 KB
     uint8_t* stg = p2s + 16384;                // D_STAGES x [dh2'_hi | h1_hi | dh2'_lo | h1_lo]
-    uint8_t* xs = stg + D_STAGES * D_STAGE_BYTES;   // D_STAGES x 64 rows x 16 B
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + D_STAGES * BT * 16);
+    uint8_t* w1a = stg + D_STAGES * D_STAGE_BYTES;  // layer-0 operand: 128 rows (channel, twice) x K = 16, see below
+    uint8_t* x16s = w1a + 16384;               // D_XS x 64 rows x K = 16 (128-byte rows, two chunks used)
+    uint8_t* xs = x16s + D_XS * IMG64;         // D_XS x 64 rows x 16 B
+    uint8_t* exch = xs + D_XS * BT * 16;       // row swap between the hi / lo consumer warps: 4 pairs x 2 buffers x 2 directions x 2 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(exch + 32768);
     uint64_t *h1_full = bars, *in_full = bars + 3, *st_empty = bars + 6, *dh_full = bars + 9, *dh_empty = bars + 11,
-             *x_free = bars + 13, *w_bar = bars + 16, *fin_bar = bars + 17;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+             *w_bar = bars + 13, *fin_bar = bars + 14, *d1_full = bars + 15, *d1_empty = bars + 17, *x_free = bars + 19,
+             *x16_full = bars + 19 + D_XS, *img_free = bars + 19 + 2 * D_XS, *a_ready = bars + 22 + 2 * D_XS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23 + 2 * D_XS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = p.R / BT;
@@ -1099,19 +1099,44 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
             mbar_init(&h1_full[i], 4);
             mbar_init(&in_full[i], 1);
             mbar_init(&st_empty[i], 1);
+            mbar_init(&img_free[i], 8);
+        }
+        for (int i = 0; i < D_XS; ++i) {
             mbar_init(&x_free[i], 8);
+            mbar_init(&x16_full[i], 2);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&dh_full[i], 1);
             mbar_init(&dh_empty[i], 8);
+            mbar_init(&d1_full[i], 1);
+            mbar_init(&d1_empty[i], 4);
         }
         mbar_init(w_bar, 1);
         mbar_init(fin_bar, 1);
+        mbar_init(a_ready, 4);
         mbar_fence_init();
     }
     if (warp == 12) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
+    }
+    if (warp >= 8 && warp < 12) {
+        // Layer 0 on the tensor pipe: z1' = s1 (W1 x + b1) + t1 is ONE K = 16 instruction per tile.  With W = s1 W1 and b = s1 b1 + t1
+        // split into bf16 hi + lo, the operand rows are
+        //     A[ch] = [ Wh0..3 | Wh0..3 | Wl0..3 | bh bl 0 0 ]        B[row] = [ xh0..3 | xl0..3 | xh0..3 | 1 1 0 0 ]
+        // so that A.B = Wh.xh + Wh.xl + Wl.xh + bh + bl: the same three error-compensated products as every other layer, in both
+        // precision modes.  Rows 64..127 of A repeat rows 0..63: TMEM lanes 64..127 then hold a second copy of z1', which the producer
+        // warps of the upper lane quarters read.
+        const int row = (warp - 8) * 32 + lane, ch = row & 63;
+        const float s1 = __ldg(p.scale1 + ch), t1 = __ldg(p.shift1 + ch);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + ch);
+        const float v[8] = {s1 * w.x, s1 * w.y, s1 * w.z, s1 * w.w, fmaf(s1, __ldg(p.b1 + ch), t1), 0.f, 0.f, 0.f};
+        uint4 h, l;
+        split_bf16x8(v, h, l);
+        // h = [Wh0 Wh1 | Wh2 Wh3 | bh 0 | 0 0], l likewise
+        *reinterpret_cast<uint4*>(w1a + sw128_offset((uint32_t)row, 0)) = make_uint4(h.x, h.y, h.x, h.y);
+        *reinterpret_cast<uint4*>(w1a + sw128_offset((uint32_t)row, 1)) = make_uint4(l.x, l.y, (h.z & 0xFFFFu) | (l.z << 16), 0u);
+        fence_proxy_async_smem();
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -1123,9 +1148,35 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
     // B images are [hi | lo] (2 * IMG64 apart): one N = 128 instruction gives the products with both halves (columns 0..63 / 64..127)
     const int nB = (nhl == 2) ? 2 * BT : BT;
     const uint32_t idesc_mn2 = umma_idesc_bf16(128, nB) | UMMA_B_MN_MAJOR;
-    const uint32_t idesc_dg2 = umma_idesc_bf16(128, nB) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;
     (void)idesc_mn; (void)idesc_dg;
 
+    // The two constant A operands of the dh1 product, (E0 W2)^T and P2 (each [hi 64 rows ; lo 64 rows] x K = 64), live in tensor memory
+    // (columns 448 / 480): this pass is bound by shared-memory bandwidth -- per 64-row tile the instructions fetched 136 KB of operands
+    // next to ~90 KB of CUDA-core traffic at 128 B / cycle -- and an A tile in TMEM is not fetched at all.
+    const uint32_t ew_t = tmem_base + 448, p2_t = tmem_base + 480;
+    if (warp < 4) {
+        mbar_wait(w_bar, 0);
+        const int m = warp * 32 + lane, ci = m & 63, hl = m >> 6;
+        const bool real = (hl == 0) || (nhl == 2);                 // bf16 mode: no lo rows, lanes 64..127 get zeros
+        uint32_t u[32];
+        const uint8_t* img = ews + hl * 8192;                      // stored [j][i]; the A tile wants lane = i, K = j
+#pragma unroll
+        for (int j2 = 0; j2 < 32; ++j2) {
+            uint32_t v = 0u;
+            if (real) {
+                const uint32_t e0 = *reinterpret_cast<const unsigned short*>(img + sw128_offset((uint32_t)(2 * j2), (uint32_t)(ci >> 3)) + (ci & 7) * 2);
+                const uint32_t e1 = *reinterpret_cast<const unsigned short*>(img + sw128_offset((uint32_t)(2 * j2 + 1), (uint32_t)(ci >> 3)) + (ci & 7) * 2);
+                v = e0 | (e1 << 16);
+            }
+            u[j2] = v;
+        }
+        tmem_st32(ew_t + ((uint32_t)(warp * 32) << 16), u);
+        tmem_put_a_tile(p2_t + ((uint32_t)(warp * 32) << 16), real ? p2s + hl * 8192 : nullptr, ci);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+    }
     if (warp == 12) {
         if (elect_one_sync()) {
             mbar_arrive_expect_tx(w_bar, 2 * 8192u * nhl);
@@ -1136,19 +1187,33 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
                 tma_bulk_g2s(p2s + 8192, p.p2_img + 16384, 8192, w_bar);
             }
             mbar_wait(w_bar, 0);
+            mbar_wait(a_ready, 0);
+            tc_fence_after_sync();
             const bool split = nhl == 2;
-            const UDesc ew_mn = udesc_mn(smem_u32(ews), 8192, 1024);                 // (E0 W2) read transposed, [hi ; lo] rows stacked
-            const UDesc p2_k = udesc_k(smem_u32(p2s));                               // [P2_hi ; P2_lo] stacked
             const UDesc stg_mn = udesc_mn(smem_u32(stg), 2 * IMG64, 1024);           // a stage image with its lo half as the second N block
             const UDesc stg_k = udesc_k(smem_u32(stg));
             constexpr uint32_t STG = D_STAGE_BYTES / 16, I64 = IMG64 / 16;
+            const UDesc w1a_k = udesc_k(smem_u32(w1a));
+            const UDesc x16_k = udesc_k(smem_u32(x16s));
             int s = 0, ph = 0;
+            int sa = 0, pha = 0;                      // stage / phase of the tile whose z1' is issued (one tile ahead)
+            // z1'(tile j) -> TMEM columns 320 + 64 (j & 1): lanes = channel (twice), columns = the 64 rows
+            auto issue_z1 = [&](int j) {
+                mbar_wait(&x16_full[sa], pha);
+                mbar_wait(&d1_empty[j & 1], ((j >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                umma_ss(tmem_base + 320 + 64 * (j & 1), w1a_k, 0, x16_k, (uint32_t)sa * I64, idesc_kk, 0u);
+                umma_commit(&d1_full[j & 1]);
+                if (++sa == D_XS) { sa = 0; pha ^= 1; }
+            };
+            if (my_tiles > 0) issue_z1(0);
 #ifdef FACL_PROFILE_ROLES
             long long pw_h1 = 0, pw_in = 0, pw_dh = 0, pw_issue = 0, pt0 = clock64();
 #endif
 #pragma unroll 1
             for (int it = 0; it < my_tiles; ++it) {
                 const int b = it & 1, u = (it >> 1) & 1;
+                if (it + 1 < my_tiles) issue_z1(it + 1);
 #ifdef FACL_PROFILE_ROLES
                 long long c0 = clock64();
 #endif
@@ -1169,9 +1234,9 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
                 const uint32_t so = (uint32_t)s * STG;            // stage: [dh2'_hi | h1_hi | dh2'_lo | h1_lo], 8 KB each
                 // dh1[i][r] = sum_j (e0 W2)[j][i] dh2'[j][r] + sum_i' P2[i][i'] h1[i'][r];  lanes 0..63 hi part, 64..127 lo part
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_ss(tmem_base + 128 * b, ew_mn, ks * 128, stg_mn, so + ks * 128, idesc_dg2, ks > 0 ? 1u : 0u);
+                for (int ks = 0; ks < 4; ++ks) umma_ts(tmem_base + 128 * b, ew_t + ks * 8, stg_mn, so + ks * 128, idesc_mn2, ks > 0 ? 1u : 0u);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_ss(tmem_base + 128 * b, p2_k, ks * 2, stg_mn, so + I64 + ks * 128, idesc_mn2, 1u);
+                for (int ks = 0; ks < 4; ++ks) umma_ts(tmem_base + 128 * b, p2_t + ks * 8, stg_mn, so + I64 + ks * 128, idesc_mn2, 1u);
                 umma_commit(&dh_full[b]);
                 // [dW2s ; H1] += [dh2' ; h1] h1^T  (reduction over the 64 rows): A = the 128-row tile at the stage start, B = h1
 #pragma unroll
@@ -1210,39 +1275,58 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
             }
         }
     } else if (warp >= 8) {
+        // ---- h1 producers: x tile (fp32 for the consumers, K = 16 bf16 rows for the z1' instruction) one tile ahead; then
+        //      h1 = relu(z1') from TMEM -> bf16 hi / lo image of the stage ----
         const int ptid = (warp - 8) * 32 + lane, ch = ptid & 63, half = ptid >> 6;
-        const float s1 = __ldg(p.scale1 + ch), t1 = __ldg(p.shift1 + ch);
-        const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + ch);
-        const float wx = s1 * w.x, wy = s1 * w.y, wz = s1 * w.z, ww = s1 * w.w, bf = fmaf(s1, __ldg(p.b1 + ch), t1);
         const float4* xg = reinterpret_cast<const float4*>(p.xt) + t0 * BT;
         float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ptid < BT) xnext = __ldg(xg + ptid);
+        if (ptid < BT && my_tiles > 0) xnext = __ldg(xg + ptid);
         float hsum = 0.f;
         int s = 0, ph = 0;
+        int sa = 0, pha = 0;
+        auto put_x = [&](int j) {                                 // warps 8, 9: rows of tile j -> slot sa
+            mbar_wait(&x_free[sa], pha ^ 1);                      // the dh1 consumers of the tile that used this x slot are done
+            reinterpret_cast<float4*>(xs + sa * BT * 16)[ptid] = xnext;
+            const float xv[8] = {xnext.x, xnext.y, xnext.z, xnext.w, 1.f, 0.f, 0.f, 0.f};
+            uint4 h, l;
+            split_bf16x8(xv, h, l);
+            uint8_t* x16 = x16s + sa * IMG64;
+            *reinterpret_cast<uint4*>(x16 + sw128_offset((uint32_t)ptid, 0)) = make_uint4(h.x, h.y, l.x, l.y);
+            *reinterpret_cast<uint4*>(x16 + sw128_offset((uint32_t)ptid, 1)) = make_uint4(h.x, h.y, h.z | (h.z << 16), 0u);
+            if (j + 1 < my_tiles) xnext = __ldg(xg + (long long)(j + 1) * BT + ptid);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x16_full[sa]);
+            if (++sa == D_XS) { sa = 0; pha ^= 1; }
+        };
+        if (ptid < BT && my_tiles > 0) put_x(0);
         PROF_DECL(5)
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
-            float4* xtile = reinterpret_cast<float4*>(xs + s * BT * 16);
-            mbar_wait(&x_free[s], ph ^ 1);                        // the dh1 consumers of the tile that used this x slot are done
+            const int b = it & 1, u = (it >> 1) & 1;
+            if (ptid < BT && it + 1 < my_tiles) put_x(it + 1);
             PROF_MARK(0)
-            if (ptid < BT) {
-                xtile[ptid] = xnext;
-                if (it + 1 < my_tiles) xnext = __ldg(xg + (long long)(it + 1) * BT + ptid);
-            }
-            named_bar_sync(1, 128);
+            mbar_wait(&d1_full[b], u);
+            tc_fence_after_sync();
+            float z[32];
+            tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(320 + 64 * b + half * 32), z);
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d1_empty[b]);
             PROF_MARK(1)
-            mbar_wait(&st_empty[s], ph ^ 1);
+            mbar_wait(&st_empty[s], ph ^ 1);                      // the Gram instructions that read this stage are done
+            mbar_wait(&img_free[s], ph ^ 1);                      // ... and so are the consumers that take the ReLU1 mask from its h1 image
             PROF_MARK(2)
             // h1 image of this stage: hi at +IMG64, lo at +3*IMG64
             float acc = 0.f;
             uint8_t* img = stg + s * D_STAGE_BYTES + IMG64;
-#pragma unroll 2
+#pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    float4 x = xtile[half * 32 + q * 8 + e];
-                    v[e] = fmaxf(fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf)))), 0.f);
+                    v[e] = fmaxf(z[q * 8 + e], 0.f);
                     acc += v[e];
                 }
                 store_img8(img, nhl, 2 * IMG64, ch, half * 4 + q, v);
@@ -1253,78 +1337,132 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
             __syncwarp();
             if (lane == 0) mbar_arrive(&h1_full[s]);
             PROF_MARK(4)
+            if (p.dbg_mask1) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) p.dbg_mask1[((t0 + it) * 64 + ch) * 64 + half * 32 + r] = z[r] > 0.f ? 1 : 0;
+            }
             if (++s == D_STAGES) { s = 0; ph ^= 1; }
         }
 #ifdef FACL_PROFILE_ROLES
         if (blockIdx.x == 1 && ptid == 0)
-            printf("pass D h1 producer, cycles/tile: wait x_free %lld | x tile + bar %lld | wait st_empty %lld | produce %lld | fence+arrive %lld\n",
+            printf("pass D h1 producer, cycles/tile: x tile ahead %lld | wait d1_full + ld %lld | wait st_empty %lld | produce %lld | fence+arrive %lld\n",
                    prof_[0] / my_tiles, prof_[1] / my_tiles, prof_[2] / my_tiles, prof_[3] / my_tiles, prof_[4] / my_tiles);
 #endif
         atomicAdd(p.hsum + ch, hsum);
     } else {
-        // ---- dh1 consumers (thread = channel i, hi or lo part): + q2, ReLU1 mask by recomputation, BN1 backward sums,
-        //      A = sum dh1' x^T.  All of these are sums over rows, so the hi and lo parts are reduced as separate partials. ----
+        // ---- dh1 consumers (thread = channel i): + q2, ReLU1 mask from the h1 image, BN1 backward sums, A = sum dh1' x^T.
+        //      The A_hi products of a channel sit in TMEM lanes 0..63 and the A_lo products in lanes 64..127, i.e. in DIFFERENT warps
+        //      (quarter q and q + 2).  The two warps of such a pair swap half of their 32 rows through shared memory, so each one
+        //      holds the COMPLETE dh1 of 16 rows and does the per-element work only for those (in bf16 mode, where there is no lo
+        //      part, the upper warp simply takes over half of the lower warp's rows). ----
         const int quarter = warp & 3, colhalf = warp >> 2;
         const int part = quarter >> 1;                           // 0: lanes 0..63 (A_hi products), 1: lanes 64..127 (A_lo)
         const int i = (quarter & 1) * 32 + lane;
-        const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + i);
-        const float b1 = __ldg(p.b1 + i);
-        const float q2 = part == 0 ? __ldg(p.q2 + i) : 0.f;
-        const bool live = (part == 0) || (nhl == 2);             // bf16 mode has no lo part: lanes 64..127 are meaningless
+        const int pair = (quarter & 1) + 2 * colhalf;
+        const float q2 = __ldg(p.q2 + i);
+        const bool have = (part == 0) || (nhl == 2);             // bf16 mode has no lo part: lanes 64..127 are meaningless
         float s_acc = 0.f, ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
-        int s = 0;
-        PROF_DECL(3)
+        int s = 0, sx = 0;
+        PROF_DECL(7)
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
-            const float4* xtile = reinterpret_cast<const float4*>(xs + s * BT * 16) + colhalf * 32;
+            const float4* xtile = reinterpret_cast<const float4*>(xs + sx * BT * 16) + colhalf * 32 + part * 16;
             const uint8_t* h1img = stg + s * D_STAGE_BYTES + IMG64;      // bf16(h1) of this tile: non-zero <=> ReLU1 active
+            uint8_t* ex = exch + pair * 8192 + (it & 1) * 4096;          // [direction][4 row groups][32 lanes] float4, double-buffered
             mbar_wait(&dh_full[b], u);
             PROF_MARK(0)
             tc_fence_after_sync();
-            float g[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 * b + colhalf * 32), g);
-            if (nhl == 2) {
-                float gl[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 * b + 64 + colhalf * 32), gl);
+            // Every shared-memory load below is issued well before its first use (the ReLU1 bits while the accumulator loads are in
+            // flight, the first eight x rows before the row swap, the other eight before the first eight are consumed): with one exposed
+            // LDS round trip per row the consumers spent 40 % of their time on the short scoreboard (ncu source page).
+            float g[32], gl[32];
+            if (have) {
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 * b + colhalf * 32), g);
+                if (nhl == 2) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 * b + 64 + colhalf * 32), gl);
+            }
+            const uint4 hb0 = *reinterpret_cast<const uint4*>(h1img + sw128_offset((uint32_t)i, (uint32_t)(colhalf * 4 + part * 2)));
+            const uint4 hb1 = *reinterpret_cast<const uint4*>(h1img + sw128_offset((uint32_t)i, (uint32_t)(colhalf * 4 + part * 2 + 1)));
+            float4 xq[4][4];                                              // x rows in groups of four, one group ahead of its use
+            if (have) {
                 tmem_ld_wait();
+                if (nhl == 2) {
 #pragma unroll
-                for (int r = 0; r < 32; ++r) g[r] += gl[r];
+                    for (int r = 0; r < 32; ++r) g[r] += gl[r];
+                }
             } else {
-                tmem_ld_wait();
+#pragma unroll
+                for (int r = 0; r < 32; ++r) g[r] = 0.f;
             }
             tc_fence_before_sync();
+            PROF_MARK(3)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xq[0][e] = xtile[e];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dh_empty[b]);                     // the accumulator is in registers now
+            // rows 0..15 of the column half belong to the lower warp, rows 16..31 to the upper one
+            if (have) {
+#pragma unroll
+                for (int r4 = 0; r4 < 4; ++r4) {
+                    const int k = r4 * 4;
+                    const float4 snd = part ? make_float4(g[k], g[k + 1], g[k + 2], g[k + 3])
+                                            : make_float4(g[16 + k], g[17 + k], g[18 + k], g[19 + k]);
+                    *reinterpret_cast<float4*>(ex + part * 2048 + (r4 * 32 + lane) * 16) = snd;
+                }
+            }
+            float gv[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) gv[r] = part ? g[16 + r] : g[r];
+            PROF_MARK(4)
+            named_bar_sync(2 + pair, 64);
+            PROF_MARK(5)
+            float4 rc[4];
+            const bool recv = (part == 1) || (nhl == 2);
+            if (recv) {
+#pragma unroll
+                for (int r4 = 0; r4 < 4; ++r4) rc[r4] = *reinterpret_cast<const float4*>(ex + (1 - part) * 2048 + (r4 * 32 + lane) * 16);
+            }
+            if (recv) {
+#pragma unroll
+                for (int r4 = 0; r4 < 4; ++r4) {
+                    gv[r4 * 4] += rc[r4].x; gv[r4 * 4 + 1] += rc[r4].y; gv[r4 * 4 + 2] += rc[r4].z; gv[r4 * 4 + 3] += rc[r4].w;
+                }
+            }
             PROF_MARK(1)
-            if (live) {
+            const uint32_t hw[8] = {hb0.x, hb0.y, hb0.z, hb0.w, hb1.x, hb1.y, hb1.z, hb1.w};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint4 hb = *reinterpret_cast<const uint4*>(h1img + sw128_offset((uint32_t)i, (uint32_t)(colhalf * 4 + q)));
-                    const uint32_t hw[4] = {hb.x, hb.y, hb.z, hb.w};
+            for (int j = 0; j < 4; ++j) {
+                if (j < 3) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int r = q * 8 + e;
-                        const uint32_t bits = (e & 1) ? (hw[e >> 1] >> 16) : (hw[e >> 1] & 0xFFFFu);
-                        const float4 x = xtile[r];
-                        const float v = bits ? g[r] + q2 : 0.f;
-                        s_acc += v;
-                        ax = fmaf(v, x.x, ax); ay = fmaf(v, x.y, ay); az = fmaf(v, x.z, az); aw = fmaf(v, x.w, aw);
-                    }
+                    for (int e = 0; e < 4; ++e) xq[j + 1][e] = xtile[(j + 1) * 4 + e];
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int r = j * 4 + e;
+                    const uint32_t bits = (r & 1) ? (hw[r >> 1] >> 16) : (hw[r >> 1] & 0xFFFFu);
+                    const float4 x = xq[j][e];
+                    const float v = bits ? gv[r] + q2 : 0.f;
+                    s_acc += v;
+                    ax = fmaf(v, x.x, ax); ay = fmaf(v, x.y, ay); az = fmaf(v, x.z, az); aw = fmaf(v, x.w, aw);
                 }
             }
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(&dh_empty[b]);
-                mbar_arrive(&x_free[s]);
+                mbar_arrive(&x_free[sx]);
+                mbar_arrive(&img_free[s]);
             }
             PROF_MARK(2)
             if (++s == D_STAGES) s = 0;
+            if (++sx == D_XS) sx = 0;
         }
 #ifdef FACL_PROFILE_ROLES
         if (blockIdx.x == 1 && (warp == 0 || warp == 2) && lane == 0)
-            printf("pass D dh1 consumer (quarter %d), cycles/tile: wait dh_full %lld | TMEM loads %lld | mask+sums+arrive %lld\n", quarter,
-                   prof_[0] / my_tiles, prof_[1] / my_tiles, prof_[2] / my_tiles);
+            printf("pass D dh1 consumer (quarter %d), cycles/tile: wait dh_full %lld | TMEM loads %lld | x prefetch + send %lld | pair barrier %lld | receive %lld | mask+sums+arrive %lld\n", quarter,
+                   prof_[0] / my_tiles, prof_[3] / my_tiles, prof_[4] / my_tiles, prof_[5] / my_tiles, prof_[1] / my_tiles, prof_[2] / my_tiles);
 #endif
         // z1 = w.x + b1 is affine in x, so sum dh1' z1 follows from A = sum dh1' x^T and sum dh1'
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + i);
+        const float b1 = __ldg(p.b1 + i);
         const float q_acc = fmaf(w.x, ax, fmaf(w.y, ay, fmaf(w.z, az, fmaf(w.w, aw, b1 * s_acc))));
         const long long slot = (long long)(blockIdx.x * 4 + part * 2 + colhalf) * 64 + i;
         p.stats[slot * 2 + 0] = s_acc;
@@ -1503,7 +1641,7 @@ __global__ void __launch_bounds__(1024) l1_gamma0_fix_kernel(const float4* __res
 }
 
 size_t l1_bwd_c_smem() { return 16384 + 65536 + 16384 + 2 * IMG64 + 4 * IMG64 + 65536 + 2 * BT * 16 + 256 + 1024; }
-size_t l1_bwd_d_smem() { return 16384 + 16384 + D_STAGES * D_STAGE_BYTES + 16384 + D_STAGES * BT * 16 + 256 + 1024; }
+size_t l1_bwd_d_smem() { return 16384 + 16384 + D_STAGES * D_STAGE_BYTES + 16384 + D_XS * IMG64 + D_XS * BT * 16 + 32768 + 512 + 1024; }
 
 // sum x (4) and sum x x^T (10 unique) over all rows, in double
 __global__ void __launch_bounds__(256) l1_moments_kernel(const float4* __restrict__ xt, long long R, double* __restrict__ out) {
@@ -1701,7 +1839,7 @@ int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, c
     p.arg = arg; p.dpooled = dpooled; p.ldp = ldp; p.c3_0 = c3_0;
     p.kshift = K == 64 ? 0 : (K == 128 ? 1 : 2);
     p.dh2 = reinterpret_cast<uint8_t*>(dh2); p.dw3 = dw3; p.gram = nullptr; p.hsum = nullptr; p.stats = stats;
-    p.dbg_mask1 = g_dbg_mask1; p.dbg_mask2 = g_dbg_mask2;
+    p.dbg_mask2 = g_dbg_mask2;
     ScopedTimer timer(TAG_L1_PASS_C, st);
     count_launch();
     FACL_LAUNCH_OK(launch_pdl(l1_bwd_c_kernel, dim3(l1_bwd_grid(R)), dim3(C_THREADS), l1_bwd_c_smem(), st, p));
@@ -1732,6 +1870,7 @@ int l1_bwd_d_launch(const float* xt, long long R, int nsplit, const float* w1, c
     p.e0w2_img = reinterpret_cast<const uint8_t*>(e0w2_img); p.p2_img = reinterpret_cast<const uint8_t*>(p2_img); p.q2 = q2;
     p.dh2 = reinterpret_cast<uint8_t*>(const_cast<void*>(dh2)); p.dw2s = dw2s; p.gram = gram; p.hsum = hsum; p.amat = amat;
     p.stats = stats;
+    p.dbg_mask1 = g_dbg_mask1;
     ScopedTimer timer(TAG_L1_PASS_D, st);
     count_launch();
     FACL_LAUNCH_OK(launch_pdl(l1_bwd_d_kernel, dim3(l1_bwd_grid(R)), dim3(D_THREADS), l1_bwd_d_smem(), st, p));
