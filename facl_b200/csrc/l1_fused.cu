@@ -16,6 +16,7 @@
 // (max_k relu(a z_k + b) = relu(a * (a >= 0 ? max z : min z) + b), so pooling can precede BN3.)
 #include <stdio.h>
 #include <string.h>
+#include <type_traits>
 
 #include "common.cuh"
 #include "facl_internal.h"
@@ -1356,14 +1357,18 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
         //      holds the COMPLETE dh1 of 16 rows and does the per-element work only for those (in bf16 mode, where there is no lo
         //      part, the upper warp simply takes over half of the lower warp's rows). ----
         const int quarter = warp & 3, colhalf = warp >> 2;
-        const int part = quarter >> 1;                           // 0: lanes 0..63 (A_hi products), 1: lanes 64..127 (A_lo)
+        const int part_rt = quarter >> 1;                        // 0: lanes 0..63 (A_hi products), 1: lanes 64..127 (A_lo)
         const int i = (quarter & 1) * 32 + lane;
         const int pair = (quarter & 1) + 2 * colhalf;
         const float q2 = __ldg(p.q2 + i);
-        const bool have = (part == 0) || (nhl == 2);             // bf16 mode has no lo part: lanes 64..127 are meaningless
+        // (bf16 mode has no lo part: lanes 64..127 are meaningless and are not read)
         float s_acc = 0.f, ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
         int s = 0, sx = 0;
         PROF_DECL(7)
+        // the loop is instantiated once per lane half: with `part` a compile-time constant the row selection below is register naming
+        auto run = [&](auto part_c) {
+        constexpr int part = decltype(part_c)::value;
+        const bool have = (part == 0) || (nhl == 2);
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             const int b = it & 1, u = (it >> 1) & 1;
@@ -1455,6 +1460,9 @@ __global__ void __launch_bounds__(D_THREADS, 1) l1_bwd_d_kernel(const L1BwdParam
             if (++s == D_STAGES) s = 0;
             if (++sx == D_XS) sx = 0;
         }
+        };
+        if (part_rt == 0) run(std::integral_constant<int, 0>{}); else run(std::integral_constant<int, 1>{});
+        const int part = part_rt;
 #ifdef FACL_PROFILE_ROLES
         if (blockIdx.x == 1 && (warp == 0 || warp == 2) && lane == 0)
             printf("pass D dh1 consumer (quarter %d), cycles/tile: wait dh_full %lld | TMEM loads %lld | x prefetch + send %lld | pair barrier %lld | receive %lld | mask+sums+arrive %lld\n", quarter,
