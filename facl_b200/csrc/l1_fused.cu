@@ -642,8 +642,12 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * BT * 16);
     uint64_t *h1_full = bars, *h1_empty = bars + 1, *d2_full = bars + 2, *d2_empty = bars + 4, *h2_full = bars + 6,
              *h2_empty = bars + 8, *sp_full = bars + 10, *sp_empty = bars + 11, *dh_full = bars + 12, *dh_empty = bars + 13,
-             *a_ready = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+             *a_ready = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17, *fw_full = bars + 18, *fw_empty = bars + 22;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+    // The lo rows of the stacked A operands ([hi 64 rows ; lo 64 rows]) leave their products in TMEM lanes 64..127, which the dh2
+    // consumers (lanes 0..63) cannot read.  Four Sp-producer warps that own those lanes forward them through shared memory (the W2
+    // staging area is free once its A tiles are in tensor memory), 4 KB per consumer warp and tile.
+    uint8_t* fwd = w2s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = p.R / BT;
@@ -658,7 +662,11 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             mbar_init(&d2_empty[i], 4);        // the h2 producers read z2 (the dh2 consumers take mask and z2 from the h2 image)
         }
         mbar_init(dh_full, 1);
-        mbar_init(dh_empty, 4);
+        mbar_init(dh_empty, nhl == 2 ? 8 : 4);     // the dh2 consumers + (bf16x3) the warps that forward the lo lanes
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&fw_full[i], 1);
+            mbar_init(&fw_empty[i], 1);
+        }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&h2_full[i], 4);
             mbar_init(&h2_empty[i], 5);        // tcgen05.commit of the MMAs that read the stage + the four dh2 consumer warps
@@ -681,7 +689,6 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc_mn = umma_idesc_bf16(128, BT) | UMMA_B_MN_MAJOR;                      // weights x activation image
-    const uint32_t idesc_dg = umma_idesc_bf16(128, BT) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;    // W3^T x Sp
     const uint32_t idesc_kk = umma_idesc_bf16(128, 64);                                        // reduction over rows
     const int nB = (nhl == 2) ? 2 * BT : BT;                                                   // [hi | lo] stacked B operand
     const uint32_t idesc_mn2 = umma_idesc_bf16(128, nB) | UMMA_B_MN_MAJOR;
@@ -705,7 +712,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             mbar_wait(a_ready, 0);                  // W2 / P3 A tiles are in tensor memory
             tc_fence_after_sync();
             const uint32_t w2_hi = tmem_base + 384, w2_lo = tmem_base + 416;
-            const uint32_t p3_hi = tmem_base + 448, p3_lo = tmem_base + 480;
+            const uint32_t p3_hi = tmem_base + 448;      // lanes 0..63 P3_hi, lanes 64..127 P3_lo
             // operand descriptors, built once; all per-instruction offsets below are immediates in 16-byte units
             const UDesc h1_mn = udesc_mn(smem_u32(h1s), 8192, 1024);            // h1 [64 ch][64 rows] as B of W2 h1 (reduction over channels)
             const UDesc h2_k = udesc_k(smem_u32(h2s));                           // h2 stage 0, K-major: B of Sp h2^T (reduction over rows)
@@ -768,14 +775,11 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 for (int ks = 0; ks < 16; ++ks) {   // dh2 = W3^T Sp: reduction over the 256 channels
                     const uint32_t wa = (ks >> 3) * 2048 + (ks & 7) * 128;
                     umma_ss(tmem_base + 128, w3_mn, wa, sp_mn, ks * 128, idesc_dg2, ks > 0 ? 1u : 0u);
-                    if (split) umma_ss(tmem_base + 128, w3_mn, wa + 1024, sp_mn, ks * 128, idesc_dg, 1u);
                 }
                 umma_commit(sp_empty);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {    // dh2 += P3 h2: A_hi x [h2_hi | h2_lo], then A_lo x h2_hi
+                for (int ks = 0; ks < 4; ++ks)      // dh2 += P3 h2: [P3_hi ; P3_lo] x [h2_hi | h2_lo]
                     umma_ts(tmem_base + 128, p3_hi + ks * 8, h2_mn, st + ks * 128, idesc_mn2, 1u);
-                    if (split) umma_ts(tmem_base + 128, p3_lo + ks * 8, h2_mn, st + ks * 128, idesc_mn, 1u);
-                }
                 umma_commit(dh_full);
                 umma_commit(&h2_empty[b]);
                 PROF_MARK(7)
@@ -790,9 +794,12 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         }
     } else if (warp == 10 || warp == 11 || warp == 14 || warp == 15) {
         // ---- x -> h1 producers ----
-        if (warp >= 14) {      // warps 14, 15 own TMEM lanes 64..127: the unused rows of the four A tiles are zero
+        if (warp >= 14) {      // warps 14, 15 own TMEM lanes 64..127: P3_lo below P3_hi (stacked A operand), zeros under the W2 tiles
+            if (nhl == 2) mbar_wait(w_bar, 0);
 #pragma unroll 1
-            for (int tile = 0; tile < 4; ++tile) tmem_put_a_tile(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 384 + 32 * tile, nullptr, 0);
+            for (int tile = 0; tile < 4; ++tile)
+                tmem_put_a_tile(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 384 + 32 * tile, (tile == 2 && nhl == 2) ? p3s + 8192 : nullptr,
+                                (warp & 1) * 32 + lane);
             tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
@@ -936,6 +943,18 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&h2_empty[b]);   // the h2 stage may be refilled: the MMA stream and these four warps have read it
+            if (nhl == 2) {                             // + A_lo B_hi, forwarded from TMEM lanes 64..127
+                const int fpair = lg + 2 * colhalf;
+                mbar_wait(&fw_full[fpair], it & 1);
+                const uint8_t* src = fwd + fpair * 4096 + lane * 16;
+#pragma unroll
+                for (int r4 = 0; r4 < 8; ++r4) {
+                    const float4 f = *reinterpret_cast<const float4*>(src + r4 * 512);
+                    g[4 * r4] += f.x; g[4 * r4 + 1] += f.y; g[4 * r4 + 2] += f.z; g[4 * r4 + 3] += f.w;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&fw_empty[fpair]);
+            }
             uint8_t* out = p.dh2 + (t0 + it) * (2 * IMG64);
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
@@ -976,6 +995,27 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         const float* dpp = p.dpooled + (long long)c * p.ldp + (t0 >> ksh);
         const unsigned char* argp = p.arg + (long long)c * p.ldp + (t0 >> ksh);
         uint8_t* row_hi = sps + c * 128;
+        // warps 2, 3, 6, 7 own TMEM lanes 64..127: after Sp(it) is out they forward the A_lo B_hi half of dh2(it - 1) to the consumer
+        // warp with the same (channel group, column half)
+        const bool forwarder = (nhl == 2) && (warp & 2);
+        const int fpair = (warp & 1) + 2 * (warp >> 2);
+        auto forward_lo = [&](int t) {
+            mbar_wait(dh_full, t & 1);
+            tc_fence_after_sync();
+            float f[32];
+            tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(128 + (warp >> 2) * 32), f);
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dh_empty);
+            mbar_wait(&fw_empty[fpair], (t & 1) ^ 1);
+            uint8_t* dst = fwd + fpair * 4096 + lane * 16;
+#pragma unroll
+            for (int r4 = 0; r4 < 8; ++r4)
+                *reinterpret_cast<float4*>(dst + r4 * 512) = make_float4(f[4 * r4], f[4 * r4 + 1], f[4 * r4 + 2], f[4 * r4 + 3]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fw_full[fpair]);
+        };
         int prev = -1;
         float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
         uchar4 a4 = make_uchar4(0, 0, 0, 0);
@@ -1026,7 +1066,9 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             __syncwarp();
             if (lane == 0) mbar_arrive(sp_full);
             PROF_MARK(2)
+            if (forwarder && it > 0) forward_lo(it - 1);
         }
+        if (forwarder) forward_lo(my_tiles - 1);
 #ifdef FACL_PROFILE_ROLES
         if (blockIdx.x == 1 && warp == 0 && lane == 0)
             printf("pass C Sp producer, cycles/tile: loads+convert %lld | wait sp_empty %lld | write+fence+arrive %lld\n", prof_[0] / my_tiles,
