@@ -630,7 +630,7 @@ int encoder_backward(const facl_encoder_dims* d, const facl_encoder_params* p, c
         RUN(l1_bwd_c_launch(xt, R1, l1_nsplit(ns), L0.w, L0.b, s0.scale, s0.shift, wp + wpack_offset(1), L1.b, s1.scale, s1.shift,
                             wp + wpack_offset(2), imgs, acc + L1S_Q3, U(B_ARG3), F(B_DP3), R3, s2.c0, bufs[B_DH2], gr->dw[2], stats, K, st));
         RUN(l1_gamma0_fix_launch(xt, R1, l1_nsplit(ns), L0.w, L0.b, s0.scale, s0.shift, L1.w, L1.b, s1.scale, bufs[B_DH2], stats, st));
-        RUN(bwd_finalize(1, 1, 64, (int)R1, (double)R1, P, 0));
+        RUN(bwd_finalize(1, 1, 64, (int)R1, (double)R1, 2 * P, 0));
         RUN(l1_fin_launch(L2.w, 256, s2.c1, L2.b, s2.c2, acc + L1S_H2, acc + L1S_S2, nullptr, nullptr, gr->dw[2], 1, st));
         RUN(l1_prep_launch(L1.w, 64, s1.c1, L1.b, s1.c2, s1.c0, imgs + 32768, acc + L1S_Q2, imgs + 65536, st));
         RUN(l1_bwd_d_launch(xt, R1, l1_nsplit(ns), L0.w, L0.b, s0.scale, s0.shift, imgs + 65536, imgs + 32768, acc + L1S_Q2, bufs[B_DH2],

@@ -609,6 +609,28 @@ __device__ __forceinline__ float produce_h1_tile64(const float4* xtile, uint8_t*
     return acc;
 }
 
+// the per-element part of the dh2 role for 16 rows of channel j (two 8-row chunks starting at `chunk0`): + q3, ReLU2 mask taken from
+// the bf16 h2 image (hh / hl = its hi / lo words), BN2-backward sums, masked gradient -> bf16 hi / lo image in HBM
+__device__ __forceinline__ void dh2_rows16(const float (&gv)[16], const uint4 (&hh)[2], const uint4 (&hl)[2], uint8_t* out, int nhl, int j,
+                                           int chunk0, float q3, float c2, float& s_acc, float& q_acc) {
+#pragma unroll
+    for (int g8 = 0; g8 < 2; ++g8) {
+        const uint32_t hw[4] = {hh[g8].x, hh[g8].y, hh[g8].z, hh[g8].w}, lw[4] = {hl[g8].x, hl[g8].y, hl[g8].z, hl[g8].w};
+        float v8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t hb = (e & 1) ? (hw[e >> 1] & 0xFFFF0000u) : (hw[e >> 1] << 16);     // bf16 -> fp32 bits
+            const uint32_t lb = (e & 1) ? (lw[e >> 1] & 0xFFFF0000u) : (lw[e >> 1] << 16);
+            const float h2v = __uint_as_float(hb) + __uint_as_float(lb);
+            const float v = hb ? gv[g8 * 8 + e] + q3 : 0.f;                  // bf16(h2) != 0  <=>  ReLU2 active
+            s_acc += v;
+            q_acc = fmaf(v, h2v - c2, q_acc);
+            v8[e] = v;
+        }
+        store_img8(out, nhl, IMG64, j, chunk0 + g8, v8);
+    }
+}
+
 // --------------------------------------------------------------------------------------------------------------------
 // pass C   (22 warps)
 // warps 0-7         : Sp producers (thread = channel c): one bf16 hi/lo pair per tile; flush dW3s at the end
@@ -631,23 +653,26 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
+    if (((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) > 768u) __trap();         // C_ALIGN_SLACK (defined with the launcher)
     const int nhl = p.nhl;
     uint8_t* w2s = smem;                       // hi 8 KB | lo 8 KB
     uint8_t* w3s = w2s + 16384;                // [half][hi 16 KB | lo 16 KB]
     uint8_t* p3s = w3s + 65536;                // hi 8 KB | lo 8 KB
-    uint8_t* h1s = p3s + 16384;                // hi 8 KB | lo 8 KB (single stage)
-    uint8_t* h2s = h1s + 2 * IMG64;            // 2 stages x (hi | lo)
+    uint8_t* h1s = p3s + 16384;                // 2 stages x (hi 8 KB | lo 8 KB): with one stage, h1(t + 1) could not be produced before
+                                               // z2(t) had read h1(t), and the 64-row recompute sat on the critical chain of the tile
+    uint8_t* h2s = h1s + 2 * 2 * IMG64;        // 2 stages x (hi | lo)
     uint8_t* sps = h2s + 2 * 2 * IMG64;        // Sp [256 c][64 r]: hi 32 KB | lo 32 KB
     uint8_t* xs = sps + 65536;                 // 2 stages x 64 rows x 16 B
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * BT * 16);
-    uint64_t *h1_full = bars, *h1_empty = bars + 1, *d2_full = bars + 2, *d2_empty = bars + 4, *h2_full = bars + 6,
+    uint64_t *h1_full = bars + 18, *h1_empty = bars + 20, *d2_full = bars + 2, *d2_empty = bars + 4, *h2_full = bars + 6,
              *h2_empty = bars + 8, *sp_full = bars + 10, *sp_empty = bars + 11, *dh_full = bars + 12, *dh_empty = bars + 13,
-             *a_ready = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17, *fw_full = bars + 18, *fw_empty = bars + 22;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+             *a_ready = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
     // The lo rows of the stacked A operands ([hi 64 rows ; lo 64 rows]) leave their products in TMEM lanes 64..127, which the dh2
-    // consumers (lanes 0..63) cannot read.  Four Sp-producer warps that own those lanes forward them through shared memory (the W2
-    // staging area is free once its A tiles are in tensor memory), 4 KB per consumer warp and tile.
-    uint8_t* fwd = w2s;
+    // consumers (warps of lanes 0..63) cannot read.  Four Sp-producer warps own those lanes: each is paired with the consumer warp of
+    // the same (channel group, column half), the two swap half of their 32 rows through shared memory (as in pass D) and each
+    // does the per-element work and the global stores of 16 rows.  The W2 / P3 staging areas are free once their A tiles are in
+    // tensor memory: they are the two buffers of the swap (4 pairs x [consumer -> partner 2 KB | partner -> consumer 2 KB]).
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = p.R / BT;
@@ -655,23 +680,20 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     const int my_tiles = (int)((ntiles - t0 < p.tiles_per_cta) ? (ntiles - t0) : p.tiles_per_cta);   // > 0 by the launch
 
     if (threadIdx.x == 0) {
-        mbar_init(h1_full, 4);
-        mbar_init(h1_empty, 1);
         for (int i = 0; i < 2; ++i) {
+            mbar_init(&h1_full[i], 4);
+            mbar_init(&h1_empty[i], 1);
             mbar_init(&d2_full[i], 1);
             mbar_init(&d2_empty[i], 4);        // the h2 producers read z2 (the dh2 consumers take mask and z2 from the h2 image)
         }
         mbar_init(dh_full, 1);
         mbar_init(dh_empty, nhl == 2 ? 8 : 4);     // the dh2 consumers + (bf16x3) the warps that forward the lo lanes
-        for (int i = 0; i < 4; ++i) {
-            mbar_init(&fw_full[i], 1);
-            mbar_init(&fw_empty[i], 1);
-        }
+
         for (int i = 0; i < 2; ++i) {
             mbar_init(&h2_full[i], 4);
-            mbar_init(&h2_empty[i], 5);        // tcgen05.commit of the MMAs that read the stage + the four dh2 consumer warps
+            mbar_init(&h2_empty[i], 9);        // tcgen05.commit of the MMAs that read the stage + the eight warps of the dh2 role
         }
-        mbar_init(sp_full, 8);
+        mbar_init(sp_full, 4);                 // warps 0, 1, 4, 5 write Sp (two channels per thread); 2, 3, 6, 7 are the dh2 partners
         mbar_init(sp_empty, 1);
         mbar_init(a_ready, 4);
         mbar_init(w_bar, 1);
@@ -725,21 +747,22 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             PROF_DECL(8)
             auto issue_z2 = [&](int it) {          // z2(it) = W2 h1(it): plain 3-term form, double-buffered accumulator
                 const int b = it & 1, u = (it >> 1) & 1;
-                mbar_wait(h1_full, it & 1);
+                mbar_wait(&h1_full[b], u);
                 PROF_MARK(3)
                 mbar_wait(&d2_empty[b], u ^ 1);
                 PROF_MARK(4)
                 tc_fence_after_sync();
                 const uint32_t d = tmem_base + 64 * b;
+                const uint32_t hs = (uint32_t)b * (2 * IMG64 / 16);                  // h1 stage offset
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    umma_ts(d, w2_hi + ks * 8, h1_mn, ks * 128, idesc_mn, ks > 0 ? 1u : 0u);
+                    umma_ts(d, w2_hi + ks * 8, h1_mn, hs + ks * 128, idesc_mn, ks > 0 ? 1u : 0u);
                     if (split) {
-                        umma_ts(d, w2_hi + ks * 8, h1_mn, LO64 + ks * 128, idesc_mn, 1u);
-                        umma_ts(d, w2_lo + ks * 8, h1_mn, ks * 128, idesc_mn, 1u);
+                        umma_ts(d, w2_hi + ks * 8, h1_mn, hs + LO64 + ks * 128, idesc_mn, 1u);
+                        umma_ts(d, w2_lo + ks * 8, h1_mn, hs + ks * 128, idesc_mn, 1u);
                     }
                 }
-                umma_commit(h1_empty);
+                umma_commit(&h1_empty[b]);
                 umma_commit(&d2_full[b]);
                 PROF_MARK(5)
             };
@@ -823,13 +846,13 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             }
             named_bar_sync(1, 128);
             PROF_MARK(0)
-            mbar_wait(h1_empty, (it & 1) ^ 1);
+            mbar_wait(&h1_empty[it & 1], ((it >> 1) & 1) ^ 1);
             PROF_MARK(1)
-            produce_h1_tile64(xtile, h1s, nhl, ch, half, wx, wy, wz, ww, bf);
+            produce_h1_tile64(xtile, h1s + (it & 1) * 2 * IMG64, nhl, ch, half, wx, wy, wz, ww, bf);
             PROF_MARK(2)
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(h1_full);
+            if (lane == 0) mbar_arrive(&h1_full[it & 1]);
             PROF_MARK(3)
         }
 #ifdef FACL_PROFILE_ROLES
@@ -885,6 +908,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         // ---- dh2 consumers (thread = channel j): + q3, ReLU2 mask, BN2 backward sums, masked gradient image -> HBM ----
         const int lg = warp & 1, colhalf = (warp >= 20) ? 1 : 0;
         const int j = lg * 32 + lane;
+        const int pair = lg + 2 * colhalf;
         if (warp < 18) {       // warps 16, 17 own TMEM lanes 0..63: rows of W2 (hi, lo) and P3 (hi, lo) -> A tiles at columns 384..511
             mbar_wait(w_bar, 0);
 #pragma unroll 1
@@ -930,49 +954,36 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             __syncwarp();
             if (lane == 0) mbar_arrive(dh_empty);
             PROF_MARK(3)
-            // this thread's 32 rows of h2 (4 chunks of 8, hi and lo) into registers at once, so that the stage can be handed back to
+            // this thread's 16 rows of h2 (2 chunks of 8, hi and lo) into registers at once, so that the stage can be handed back to
             // the h2 producers before the arithmetic and the global stores below (holding it through them stalled the producers of
             // tile it + 2, measured)
             const uint8_t* h2img = h2s + b * 2 * IMG64;
-            uint4 hh[4], hl[4];
+            uint4 hh[2], hl[2];
 #pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
+            for (int g8 = 0; g8 < 2; ++g8) {
                 const uint32_t hoff = sw128_offset((uint32_t)j, (uint32_t)(colhalf * 4 + g8));
                 hh[g8] = *reinterpret_cast<const uint4*>(h2img + hoff);
                 hl[g8] = (nhl == 2) ? *reinterpret_cast<const uint4*>(h2img + IMG64 + hoff) : make_uint4(0u, 0u, 0u, 0u);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&h2_empty[b]);   // the h2 stage may be refilled: the MMA stream and these four warps have read it
-            if (nhl == 2) {                             // + A_lo B_hi, forwarded from TMEM lanes 64..127
-                const int fpair = lg + 2 * colhalf;
-                mbar_wait(&fw_full[fpair], it & 1);
-                const uint8_t* src = fwd + fpair * 4096 + lane * 16;
+            if (lane == 0) mbar_arrive(&h2_empty[b]);   // the h2 stage may be refilled once the MMA stream and the eight warps have read it
+            // rows 16..31 go to the partner warp; its A_lo B_hi half of rows 0..15 (TMEM lanes 64..127) comes back
+            uint8_t* ex = ((it & 1) ? p3s : w2s) + pair * 4096 + lane * 16;
 #pragma unroll
-                for (int r4 = 0; r4 < 8; ++r4) {
-                    const float4 f = *reinterpret_cast<const float4*>(src + r4 * 512);
-                    g[4 * r4] += f.x; g[4 * r4 + 1] += f.y; g[4 * r4 + 2] += f.z; g[4 * r4 + 3] += f.w;
+            for (int r4 = 0; r4 < 4; ++r4)
+                *reinterpret_cast<float4*>(ex + r4 * 512) = make_float4(g[16 + 4 * r4], g[17 + 4 * r4], g[18 + 4 * r4], g[19 + 4 * r4]);
+            named_bar_sync(2 + pair, 64);
+            float gv[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) gv[r] = g[r];
+            if (nhl == 2) {
+#pragma unroll
+                for (int r4 = 0; r4 < 4; ++r4) {
+                    const float4 f = *reinterpret_cast<const float4*>(ex + 2048 + r4 * 512);
+                    gv[4 * r4] += f.x; gv[4 * r4 + 1] += f.y; gv[4 * r4 + 2] += f.z; gv[4 * r4 + 3] += f.w;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&fw_empty[fpair]);
             }
-            uint8_t* out = p.dh2 + (t0 + it) * (2 * IMG64);
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-                const uint32_t hw[4] = {hh[g8].x, hh[g8].y, hh[g8].z, hh[g8].w}, lw[4] = {hl[g8].x, hl[g8].y, hl[g8].z, hl[g8].w};
-                float v8[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int i = g8 * 8 + e;
-                    const uint32_t hb = (e & 1) ? (hw[e >> 1] & 0xFFFF0000u) : (hw[e >> 1] << 16);     // bf16 -> fp32 bits
-                    const uint32_t lb = (e & 1) ? (lw[e >> 1] & 0xFFFF0000u) : (lw[e >> 1] << 16);
-                    const float h2v = __uint_as_float(hb) + __uint_as_float(lb);
-                    const float v = hb ? g[i] + q3 : 0.f;                    // bf16(h2) != 0  <=>  ReLU2 active
-                    s_acc += v;
-                    q_acc = fmaf(v, h2v - c2, q_acc);
-                    v8[e] = v;
-                }
-                store_img8(out, nhl, IMG64, j, colhalf * 4 + g8, v8);
-            }
+            dh2_rows16(gv, hh, hl, p.dh2 + (t0 + it) * (2 * IMG64), nhl, j, colhalf * 4, q3, c2, s_acc, q_acc);
             PROF_MARK(4)
         }
 #ifdef FACL_PROFILE_ROLES
@@ -981,99 +992,161 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                    prof_[2] / my_tiles, prof_[3] / my_tiles, prof_[4] / my_tiles);
 #endif
         q_acc = (a2 != 0.f) ? q_acc / a2 + b2 * s_acc : 0.f;
-        float* st = p.stats + ((long long)(blockIdx.x * 2 + colhalf) * 64 + j) * 2;
+        float* st = p.stats + ((long long)(blockIdx.x * 4 + colhalf) * 64 + j) * 2;
         st[0] = s_acc;
         st[1] = q_acc;
     } else if (warp < 8) {
-        // ---- Sp producers (thread = channel c): k0 dP at the max-pool winner, everything else stays zero ----
+        // ---- warps 0, 1, 4, 5: Sp producers (thread = channels c and c + 64): k0 dP at the max-pool winner, everything else stays
+        //      zero.  warps 2, 3, 6, 7: partners of the dh2 consumer warps.  All eight flush dW3s at the end. ----
         const int h = warp >> 2, lq = warp & 3;
         const int c = h * 128 + lq * 32 + lane;
-        const float k0 = __ldg(p.c3_0 + c);
         // K = 64: group == tile.  K = 128 / 256: the group of tile t is t >> kshift and its winner (position 0..K-1 inside the
         // group) lies in this tile iff (position >> 6) == (t & kmask); the other tiles of the group get a zero column
         const int ksh = p.kshift, kmask = (1 << ksh) - 1;
-        const float* dpp = p.dpooled + (long long)c * p.ldp + (t0 >> ksh);
-        const unsigned char* argp = p.arg + (long long)c * p.ldp + (t0 >> ksh);
-        uint8_t* row_hi = sps + c * 128;
-        // warps 2, 3, 6, 7 own TMEM lanes 64..127: after Sp(it) is out they forward the A_lo B_hi half of dh2(it - 1) to the consumer
-        // warp with the same (channel group, column half)
-        const bool forwarder = (nhl == 2) && (warp & 2);
-        const int fpair = (warp & 1) + 2 * (warp >> 2);
-        auto forward_lo = [&](int t) {
-            mbar_wait(dh_full, t & 1);
-            tc_fence_after_sync();
-            float f[32];
-            tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(128 + (warp >> 2) * 32), f);
-            tmem_ld_wait();
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dh_empty);
-            mbar_wait(&fw_empty[fpair], (t & 1) ^ 1);
-            uint8_t* dst = fwd + fpair * 4096 + lane * 16;
-#pragma unroll
-            for (int r4 = 0; r4 < 8; ++r4)
-                *reinterpret_cast<float4*>(dst + r4 * 512) = make_float4(f[4 * r4], f[4 * r4 + 1], f[4 * r4 + 2], f[4 * r4 + 3]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&fw_full[fpair]);
-        };
-        int prev = -1;
-        float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        uchar4 a4 = make_uchar4(0, 0, 0, 0);
-        float dcur = 0.f;
-        int acur = 0;
-        PROF_DECL(3)
-#pragma unroll 1
-        for (int it = 0; it < my_tiles; ++it) {
-            float val;
-            int r;
-            if (ksh == 0) {
-                if ((it & 3) == 0) {
-                    if (it + 4 <= my_tiles) {
-                        d4 = __ldg(reinterpret_cast<const float4*>(dpp + it));
-                        a4 = __ldg(reinterpret_cast<const uchar4*>(argp + it));
-                    } else {
-                        d4.x = __ldg(dpp + it);
-                        a4.x = __ldg(argp + it);
-                        if (it + 1 < my_tiles) { d4.y = __ldg(dpp + it + 1); a4.y = __ldg(argp + it + 1); }
-                        if (it + 2 < my_tiles) { d4.z = __ldg(dpp + it + 2); a4.z = __ldg(argp + it + 2); }
-                    }
-                }
-                const int sel = it & 3;
-                val = k0 * (sel == 0 ? d4.x : sel == 1 ? d4.y : sel == 2 ? d4.z : d4.w);
-                r = (sel == 0 ? a4.x : sel == 1 ? a4.y : sel == 2 ? a4.z : a4.w) & 63;
-            } else {
-                if ((it & kmask) == 0) {
-                    dcur = __ldg(dpp + (it >> ksh));
-                    acur = __ldg(argp + (it >> ksh));
-                }
-                r = acur & 63;
-                val = ((acur >> 6) == (it & kmask)) ? k0 * dcur : 0.f;
-            }
-            const __nv_bfloat16 vh = __float2bfloat16_rn(val);
-            const __nv_bfloat16 vl = __float2bfloat16_rn(val - __bfloat162float(vh));
-            const int off = ((((r >> 3) ^ (c & 7)) << 4) | ((r & 7) << 1));
-            PROF_MARK(0)
-            mbar_wait(sp_empty, (it & 1) ^ 1);
-            PROF_MARK(1)
-            if (prev >= 0) {
-                *reinterpret_cast<unsigned short*>(row_hi + prev) = 0;
-                *reinterpret_cast<unsigned short*>(row_hi + 32768 + prev) = 0;
-            }
-            *reinterpret_cast<unsigned short*>(row_hi + off) = __bfloat16_as_ushort(vh);
-            if (nhl == 2) *reinterpret_cast<unsigned short*>(row_hi + 32768 + off) = __bfloat16_as_ushort(vl);
-            prev = off;
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sp_full);
-            PROF_MARK(2)
-            if (forwarder && it > 0) forward_lo(it - 1);
+        // warps 2, 3, 6, 7 own TMEM lanes 64..127 and are the partners of the dh2 consumer warps (see the top of the kernel): after
+        // Sp(it) is out they take rows 16..31 of dh2(it - 1) for channel j of their (channel group, column half)
+        const bool partner = (warp & 2) != 0;
+        const int pj = (warp & 1) * 32 + lane, pcol = warp >> 2, ppair = (warp & 1) + 2 * pcol;
+        float pq3 = 0.f, pc2 = 0.f, ps_acc = 0.f, pq_acc = 0.f;
+        if (partner) {
+            const float a2 = __ldg(p.scale2 + pj);
+            pc2 = fmaf(a2, __ldg(p.b2 + pj), __ldg(p.shift2 + pj));
+            pq3 = __ldg(p.q3 + pj);
         }
-        if (forwarder) forward_lo(my_tiles - 1);
+        auto partner_rows = [&](int t) {
+            uint8_t* ex = ((t & 1) ? p3s : w2s) + ppair * 4096 + lane * 16;
+            float gv[16];
+            if (nhl == 2) {
+                mbar_wait(dh_full, t & 1);
+                tc_fence_after_sync();
+                float f[32];
+                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(128 + pcol * 32), f);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dh_empty);
+#pragma unroll
+                for (int r4 = 0; r4 < 4; ++r4)
+                    *reinterpret_cast<float4*>(ex + 2048 + r4 * 512) = make_float4(f[4 * r4], f[4 * r4 + 1], f[4 * r4 + 2], f[4 * r4 + 3]);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) gv[r] = f[16 + r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) gv[r] = 0.f;
+            }
+            named_bar_sync(2 + ppair, 64);                 // the consumer warp waited for dh_full(t): h2(t) is complete as well
+#pragma unroll
+            for (int r4 = 0; r4 < 4; ++r4) {
+                const float4 f4 = *reinterpret_cast<const float4*>(ex + r4 * 512);
+                gv[4 * r4] += f4.x; gv[4 * r4 + 1] += f4.y; gv[4 * r4 + 2] += f4.z; gv[4 * r4 + 3] += f4.w;
+            }
+            const uint8_t* h2img = h2s + (t & 1) * 2 * IMG64;
+            uint4 hh[2], hl[2];
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+                const uint32_t hoff = sw128_offset((uint32_t)pj, (uint32_t)(pcol * 4 + 2 + g8));
+                hh[g8] = *reinterpret_cast<const uint4*>(h2img + hoff);
+                hl[g8] = (nhl == 2) ? *reinterpret_cast<const uint4*>(h2img + IMG64 + hoff) : make_uint4(0u, 0u, 0u, 0u);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h2_empty[t & 1]);
+            dh2_rows16(gv, hh, hl, p.dh2 + (t0 + t) * (2 * IMG64), nhl, pj, pcol * 4 + 2, pq3, pc2, ps_acc, pq_acc);
+        };
+        if (partner) {
+#pragma unroll 1
+            for (int it = 0; it < my_tiles; ++it) partner_rows(it);
+            const float a2 = __ldg(p.scale2 + pj), b2 = __ldg(p.b2 + pj);
+            float* st = p.stats + ((long long)(blockIdx.x * 4 + 2 + pcol) * 64 + pj) * 2;
+            st[0] = ps_acc;
+            st[1] = (a2 != 0.f) ? pq_acc / a2 + b2 * ps_acc : 0.f;
+        } else {
+            struct SpChannel {
+                float k0;
+                const float* dpp;
+                const unsigned char* argp;
+                uint8_t* row_hi;
+                int prev;
+                float4 d4;
+                uchar4 a4;
+                float dcur;
+                int acur;
+            } sc[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int cq = c + 64 * q;
+                sc[q].k0 = __ldg(p.c3_0 + cq);
+                sc[q].dpp = p.dpooled + (long long)cq * p.ldp + (t0 >> ksh);
+                sc[q].argp = p.arg + (long long)cq * p.ldp + (t0 >> ksh);
+                sc[q].row_hi = sps + cq * 128;
+                sc[q].prev = -1;
+                sc[q].d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                sc[q].a4 = make_uchar4(0, 0, 0, 0);
+                sc[q].dcur = 0.f;
+                sc[q].acur = 0;
+            }
+            PROF_DECL(3)
+#pragma unroll 1
+            for (int it = 0; it < my_tiles; ++it) {
+                __nv_bfloat16 vh[2], vl[2];
+                int off[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    SpChannel& S = sc[q];
+                    float val;
+                    int r;
+                    if (ksh == 0) {
+                        if ((it & 3) == 0) {
+                            if (it + 4 <= my_tiles) {
+                                S.d4 = __ldg(reinterpret_cast<const float4*>(S.dpp + it));
+                                S.a4 = __ldg(reinterpret_cast<const uchar4*>(S.argp + it));
+                            } else {
+                                S.d4.x = __ldg(S.dpp + it);
+                                S.a4.x = __ldg(S.argp + it);
+                                if (it + 1 < my_tiles) { S.d4.y = __ldg(S.dpp + it + 1); S.a4.y = __ldg(S.argp + it + 1); }
+                                if (it + 2 < my_tiles) { S.d4.z = __ldg(S.dpp + it + 2); S.a4.z = __ldg(S.argp + it + 2); }
+                            }
+                        }
+                        const int sel = it & 3;
+                        val = S.k0 * (sel == 0 ? S.d4.x : sel == 1 ? S.d4.y : sel == 2 ? S.d4.z : S.d4.w);
+                        r = (sel == 0 ? S.a4.x : sel == 1 ? S.a4.y : sel == 2 ? S.a4.z : S.a4.w) & 63;
+                    } else {
+                        if ((it & kmask) == 0) {
+                            S.dcur = __ldg(S.dpp + (it >> ksh));
+                            S.acur = __ldg(S.argp + (it >> ksh));
+                        }
+                        r = S.acur & 63;
+                        val = ((S.acur >> 6) == (it & kmask)) ? S.k0 * S.dcur : 0.f;
+                    }
+                    vh[q] = __float2bfloat16_rn(val);
+                    vl[q] = __float2bfloat16_rn(val - __bfloat162float(vh[q]));
+                    const int cq = c + 64 * q;
+                    off[q] = ((((r >> 3) ^ (cq & 7)) << 4) | ((r & 7) << 1));
+                }
+                PROF_MARK(0)
+                mbar_wait(sp_empty, (it & 1) ^ 1);
+                PROF_MARK(1)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    SpChannel& S = sc[q];
+                    if (S.prev >= 0) {
+                        *reinterpret_cast<unsigned short*>(S.row_hi + S.prev) = 0;
+                        *reinterpret_cast<unsigned short*>(S.row_hi + 32768 + S.prev) = 0;
+                    }
+                    *reinterpret_cast<unsigned short*>(S.row_hi + off[q]) = __bfloat16_as_ushort(vh[q]);
+                    if (nhl == 2) *reinterpret_cast<unsigned short*>(S.row_hi + 32768 + off[q]) = __bfloat16_as_ushort(vl[q]);
+                    S.prev = off[q];
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sp_full);
+                PROF_MARK(2)
+            }
 #ifdef FACL_PROFILE_ROLES
-        if (blockIdx.x == 1 && warp == 0 && lane == 0)
-            printf("pass C Sp producer, cycles/tile: loads+convert %lld | wait sp_empty %lld | write+fence+arrive %lld\n", prof_[0] / my_tiles,
-                   prof_[1] / my_tiles, prof_[2] / my_tiles);
+            if (blockIdx.x == 1 && warp == 0 && lane == 0)
+                printf("pass C Sp producer, cycles/tile: loads+convert %lld | wait sp_empty %lld | write+fence+arrive %lld\n", prof_[0] / my_tiles,
+                       prof_[1] / my_tiles, prof_[2] / my_tiles);
 #endif
+        }
         // dW3s of this CTA's rows sits in TMEM: add it to the global gradient
         mbar_wait(fin_bar, 0);
         tc_fence_after_sync();
@@ -1690,7 +1763,10 @@ __global__ void __launch_bounds__(1024) l1_gamma0_fix_kernel(const float4* __res
     }
 }
 
-size_t l1_bwd_c_smem() { return 16384 + 65536 + 16384 + 2 * IMG64 + 4 * IMG64 + 65536 + 2 * BT * 16 + 256 + 1024; }
+// (the last term is the slack for aligning the dynamic window to 1 KB; the window starts right behind the 1 KB the driver reserves,
+//  so none of it is used in practice, and the kernel traps if more than this were needed)
+constexpr uint32_t C_ALIGN_SLACK = 768;
+size_t l1_bwd_c_smem() { return 16384 + 65536 + 16384 + 4 * IMG64 + 4 * IMG64 + 65536 + 2 * BT * 16 + 256 + C_ALIGN_SLACK; }
 size_t l1_bwd_d_smem() { return 16384 + 16384 + D_STAGES * D_STAGE_BYTES + 16384 + D_XS * IMG64 + D_XS * BT * 16 + 32768 + 512 + 1024; }
 
 // sum x (4) and sum x x^T (10 unique) over all rows, in double
@@ -1870,7 +1946,7 @@ int l1_fin_launch(const float* W, int C, const float* d, const float* bias, cons
     return (int)cudaGetLastError();
 }
 
-// pass C (K = 64): dw3 is accumulated with atomics (zero-initialised by the caller); stats [2*grid][64][2]
+// pass C: dw3 is accumulated with atomics (zero-initialised by the caller); stats [4*grid][64][2]
 int l1_bwd_c_launch(const float* xt, long long R, int nsplit, const float* w1, const float* b1, const float* scale1,
                     const float* shift1, const void* w2_img, const float* b2, const float* scale2, const float* shift2,
                     const void* w3_img, const void* p3_img, const float* q3, const unsigned char* arg, const float* dpooled,
