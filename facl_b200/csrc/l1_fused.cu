@@ -153,11 +153,15 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
     uint8_t* h1s = w3s + (PASS_B ? 65536 : 16384);         // pass A: leave 16 KB readable behind W2 (M=128 reads 128 rows)
     uint8_t* h2s = h1s + 2 * 2 * ACT_BYTES;                // 2 stages x (hi|lo)
     uint8_t* xs = h2s + (PASS_B ? 2 * 2 * ACT_BYTES : 0);  // 2 stages x 128 rows x 16 B
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * TILE * 16);
+    // pass A runs layer 0 on the tensor pipe (TCZ1, see pass D): operand rows [Wh | Wh | Wl | bh bl 0 0] x [xh | xl | xh | 1 1 0 0], K = 16
+    constexpr bool TCZ1 = !PASS_B;
+    uint8_t* w1a = xs + 2 * TILE * 16;                     // 128 rows (channel, twice) x 128 B            (pass A)
+    uint8_t* x16s = w1a + (TCZ1 ? 16384 : 0);              // 2 stages x 128 rows x 128 B                    (pass A)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(x16s + (TCZ1 ? 2 * 16384 : 0));
     uint64_t *h1_full = bars, *h1_empty = bars + 2, *d2_full = bars + 4, *d2_empty = bars + 6, *h2_full = bars + 8,
              *h2_empty = bars + 10, *d3_full = bars + 12, *d3_empty = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17,
-             *a_ready = bars + 18;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+             *a_ready = bars + 18, *x16_full = bars + 19, *d1_full = bars + 21, *d1_empty = bars + 22;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = p.R / TILE;
@@ -176,17 +180,32 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
         mbar_init(w_bar, 1);
         mbar_init(fin_bar, 1);
         mbar_init(a_ready, 4);
+        mbar_init(&x16_full[0], 4);
+        mbar_init(&x16_full[1], 4);
+        mbar_init(d1_full, 1);
+        mbar_init(d1_empty, NPW);
         mbar_fence_init();
     }
     if (warp == 16) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
+    if (TCZ1 && warp < 4) {
+        const int row = warp * 32 + lane, ch = row & 63;
+        const float s1 = __ldg(p.scale1 + ch), t1 = __ldg(p.shift1 + ch);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + ch);
+        const float v[8] = {s1 * w.x, s1 * w.y, s1 * w.z, s1 * w.w, fmaf(s1, __ldg(p.b1 + ch), t1), 0.f, 0.f, 0.f};
+        uint4 h, l;
+        split_bf16x8(v, h, l);
+        *reinterpret_cast<uint4*>(w1a + sw128_offset((uint32_t)row, 0)) = make_uint4(h.x, h.y, h.x, h.y);
+        *reinterpret_cast<uint4*>(w1a + sw128_offset((uint32_t)row, 1)) = make_uint4(l.x, l.y, (h.z & 0xFFFFu) | (l.z << 16), 0u);
+        fence_proxy_async_smem();
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM columns.  pass A: D2[b] at 128*b (b = 0,1), W2 A tiles (hi, lo) at 256 / 288.  pass B: D2 at 0 (single: its consumers
+    // TMEM columns.  pass A: D2[b] at 128*b (b = 0,1), W2 A tiles (hi, lo) at 256 / 288, z1' (layer 0, 128 rows) at 320..447.  pass B: D2 at 0 (single: its consumers
     // copy it out at once), H2 Gram accumulator at 128..255 (lanes 0..63 h2_hi rows, 64..127 h2_lo rows; columns 0..63 x h2_hi,
     // 64..127 x h2_lo), D3[half] at 256 + 128*half
     const uint32_t idesc = umma_idesc_bf16(128, TILE) | UMMA_B_MN_MAJOR;
@@ -253,7 +272,24 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             };
             int it = 0;
             long long t = blockIdx.x;
-            if (t < ntiles) issue_mma2(0);
+            if (TCZ1) {
+                // pass A: z1'(it + 1) is issued before z2(it) so that the producers turn it into h1(it + 1) while z2(it) runs
+                const UDesc w1a_k = udesc_k(smem_u32(w1a));
+                const UDesc x16_k = udesc_k(smem_u32(x16s));
+                auto issue_z1 = [&](int j) {
+                    mbar_wait(&x16_full[j & 1], (j >> 1) & 1);
+                    mbar_wait(d1_empty, (j & 1) ^ 1);                     // the producers have copied z1'(j - 1) out
+                    tc_fence_after_sync();
+                    umma_ss(tmem_base + 320, w1a_k, 0, x16_k, (uint32_t)(j & 1) * (16384 / 16), idesc_kk2, 0u);
+                    umma_commit(d1_full);
+                };
+                if (t < ntiles) issue_z1(0);
+                for (; t < ntiles; t += gridDim.x, ++it) {
+                    if (t + gridDim.x < ntiles) issue_z1(it + 1);
+                    issue_mma2(it);
+                }
+            }
+            if (!TCZ1 && t < ntiles) issue_mma2(0);
             for (; t < ntiles; t += gridDim.x, ++it) {
                 if (t + gridDim.x < ntiles) issue_mma2(it + 1);
                 if (PASS_B) {
@@ -285,6 +321,79 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
         }
     } else if (PASS_B ? (warp == 10 || warp == 11 || warp == 14 || warp == 15) : (warp < 8 || warp >= 17)) {
         // ======================= producers: x -> h1 = relu(bn1(W1 x + b1)), thread = (channel, row quarter) ===============
+        if constexpr (TCZ1) {
+            // ---- pass A: h1 = relu(z1') with z1' read from tensor memory.  TMEM lane quarter = warp % 4: quarters 0, 1 hold channels
+            //      0..63 and take rows 0..63 of the tile, quarters 2, 3 hold the second copy and take rows 64..127; the four warps of a
+            //      quarter split its 64 rows.  Warps 0..3 also write the K = 16 operand rows of the NEXT tile. ----
+            const int quarter = warp & 3;
+            const int kq = warp < 8 ? (warp >> 2) : 2 + ((warp - 17) >> 2);
+            const int ch = (quarter & 1) * 32 + lane;
+            const int rowbase = (quarter >> 1) * 64 + kq * 16;
+            const bool writer = warp < 4;
+            const int wrow = warp * 32 + lane;
+            float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (writer && (long long)blockIdx.x < ntiles) xnext = __ldg(reinterpret_cast<const float4*>(p.xt) + (long long)blockIdx.x * TILE + wrow);
+            auto put_x = [&](int j, long long tj) {                 // rows of tile j (global tile index tj) -> slot j & 1
+                const float xv[8] = {xnext.x, xnext.y, xnext.z, xnext.w, 1.f, 0.f, 0.f, 0.f};
+                uint4 h, l;
+                split_bf16x8(xv, h, l);
+                uint8_t* x16 = x16s + (j & 1) * 16384;
+                *reinterpret_cast<uint4*>(x16 + sw128_offset((uint32_t)wrow, 0)) = make_uint4(h.x, h.y, l.x, l.y);
+                *reinterpret_cast<uint4*>(x16 + sw128_offset((uint32_t)wrow, 1)) = make_uint4(h.x, h.y, h.z | (h.z << 16), 0u);
+                if (tj + gridDim.x < ntiles) xnext = __ldg(reinterpret_cast<const float4*>(p.xt) + (tj + gridDim.x) * TILE + wrow);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&x16_full[j & 1]);
+            };
+            if (writer && (long long)blockIdx.x < ntiles) put_x(0, blockIdx.x);
+            int it = 0;
+#ifdef FACL_PROFILE_ROLES
+            long long prof_wait = 0, prof_comp = 0, prof_fence = 0;
+#endif
+            for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int b = it & 1, u = (it >> 1) & 1;
+#ifdef FACL_PROFILE_ROLES
+                long long c0 = clock64();
+#endif
+                mbar_wait(d1_full, it & 1);
+                tc_fence_after_sync();
+                float z[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(320 + rowbase), z);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d1_empty);
+                // z1'(it) is complete, so the slot of tile it - 1 is free: the operand rows of tile it + 1 go there
+                if (writer && t + gridDim.x < ntiles) put_x(it + 1, t + gridDim.x);
+                mbar_wait(&h1_empty[b], u ^ 1);
+#ifdef FACL_PROFILE_ROLES
+                long long c1 = clock64();
+#endif
+                uint8_t* img = h1s + b * 2 * ACT_BYTES;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = fmaxf(z[q * 8 + e], 0.f);
+                    store_act8(img, nhl, ch, rowbase / 8 + q, v);
+                }
+#ifdef FACL_PROFILE_ROLES
+                long long c2 = clock64();
+#endif
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&h1_full[b]);
+#ifdef FACL_PROFILE_ROLES
+                long long c3 = clock64();
+                prof_wait += c1 - c0; prof_comp += c2 - c1; prof_fence += c3 - c2;
+#endif
+            }
+#ifdef FACL_PROFILE_ROLES
+            if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 24))
+                printf("fwd pass_b=0 producer warp %d: tiles %d wait %lld compute %lld fence %lld (cycles per tile)\n", warp, it,
+                       prof_wait / it, prof_comp / it, prof_fence / it);
+#endif
+        } else {
         const int pw = !PASS_B ? (warp < 8 ? warp : warp - 9) : (warp == 10) ? 0 : (warp == 11) ? 1 : (warp == 14) ? 2 : 3;
         const int ptid = pw * 32 + lane;          // 0 .. 32 NPW - 1
         const int ch = ptid & 63, part = ptid >> 6;
@@ -341,6 +450,7 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             printf("fwd pass_b=%d producer warp %d: tiles %d wait %lld compute %lld fence %lld (cycles per tile)\n", (int)PASS_B, pw, it,
                    prof_wait / it, prof_comp / it, prof_fence / it);
 #endif
+        }
         if (PASS_B && GRAM && nhl == 2) {
             // these warps sit on TMEM lanes 64..127: the h2_lo rows of the stacked Gram accumulator
             mbar_wait(fin_bar, 0);
@@ -1837,7 +1947,8 @@ __global__ void l1_bn1_kernel(const double* __restrict__ mom, double n, const fl
 }
 
 size_t l1_smem_bytes(bool pass_b) {
-    size_t b = 16384 + (pass_b ? 65536 : 16384) + 2 * 2 * ACT_BYTES + (pass_b ? 2 * 2 * ACT_BYTES : 0) + 2 * TILE * 16 + 256;
+    size_t b = 16384 + (pass_b ? 65536 : 16384) + 2 * 2 * ACT_BYTES + (pass_b ? 2 * 2 * ACT_BYTES : 0) + 2 * TILE * 16 + 256 +
+               (pass_b ? 0 : 3 * 16384);
     return b + 1024;
 }
 
