@@ -435,7 +435,10 @@ def run_ours(args):
                     share_of_step=top["ms_per_step"] / (ms / args.steps),
                     note=f"algorithmic FLOPs; the {cfg['precision']} mode issues {split:.0f} bf16 products per FLOP, so its ceiling is "
                          f"{peaks['tensor_sustained'] / split:.0f} TFLOP/s (frac_of_mode_ceiling)",
-                    frac_of_mode_ceiling=achieved * split / peaks["tensor_sustained"])
+                    frac_of_mode_ceiling=achieved * split / peaks["tensor_sustained"],
+                    limiter="shared-memory bandwidth, not the tensor pipe: on these 64-wide tiles a 128 x N x 16 tcgen05.mma fetches 8192/N + 64 B of "
+                            "operands per cycle of math; pass C moves 312 KB of operands + ~130 KB of role traffic per 64-row tile at 128 B/cycle/SM "
+                            "= 3 450 of its ~4 600 cycles (profiles/r2_role_profile.md)")
     else:
         nbytes = hbm_bytes.get(top["tag"], 0)
         achieved = nbytes / (top["ms_per_step"] * 1e-3) / 1e9
