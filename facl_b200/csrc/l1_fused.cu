@@ -701,24 +701,6 @@ __device__ __forceinline__ void store_img8(uint8_t* img, int nhl, int img_bytes,
     }
 }
 
-// producer shared by both backward passes: thread = channel (2 threads per channel, 32 rows each); returns sum of h1
-__device__ __forceinline__ float produce_h1_tile64(const float4* xtile, uint8_t* img, int nhl, int ch, int half, float wx, float wy,
-                                                   float wz, float ww, float bf) {
-    float acc = 0.f;
-#pragma unroll 2
-    for (int q = 0; q < 4; ++q) {
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float4 x = xtile[half * 32 + q * 8 + e];
-            v[e] = fmaxf(fmaf(wx, x.x, fmaf(wy, x.y, fmaf(wz, x.z, fmaf(ww, x.w, bf)))), 0.f);
-            acc += v[e];
-        }
-        store_img8(img, nhl, IMG64, ch, half * 4 + q, v);
-    }
-    return acc;
-}
-
 // the per-element part of the dh2 role for 16 rows of channel j (two 8-row chunks starting at `chunk0`): + q3, ReLU2 mask taken from
 // the bf16 h2 image (hh / hl = its hi / lo words), BN2-backward sums, masked gradient -> bf16 hi / lo image in HBM
 __device__ __forceinline__ void dh2_rows16(const float (&gv)[16], const uint4 (&hh)[2], const uint4 (&hl)[2], uint8_t* out, int nhl, int j,
@@ -774,15 +756,19 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     uint8_t* sps = h2s + 2 * 2 * IMG64;        // Sp [256 c][64 r]: hi 32 KB | lo 32 KB
     uint8_t* xs = sps + 65536;                 // 2 stages x 64 rows x 16 B
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * BT * 16);
-    uint64_t *h1_full = bars + 18, *h1_empty = bars + 20, *d2_full = bars + 2, *d2_empty = bars + 4, *h2_full = bars + 6,
+    uint64_t *h1_full = bars + 18, *h1_empty = bars + 20, *x16_full = bars + 22, *d1_full = bars + 24, *d2_full = bars + 2, *d2_empty = bars + 4, *h2_full = bars + 6,
              *h2_empty = bars + 8, *sp_full = bars + 10, *sp_empty = bars + 11, *dh_full = bars + 12, *dh_empty = bars + 13,
              *a_ready = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+    // Layer 0 runs on the tensor pipe as in passes A and D: z1'(t) is ONE K = 16 instruction into the columns of D2[t & 1] (z2(t) overwrites
+    // them only after the h1 producers have read z1'), its A tile (W1 folded with BN1, [hi | hi | lo | bias] K slots, rows 64..127 a copy
+    // of rows 0..63) sits in tensor memory columns 480..487 and its B tiles (the x rows of a tile as K = 16 bf16) in the P3 staging area.
+    uint8_t* x16s = p3s;                       // 2 x 64 rows x 128 B (after the A tiles are in tensor memory)
     // The lo rows of the stacked A operands ([hi 64 rows ; lo 64 rows]) leave their products in TMEM lanes 64..127, which the dh2
     // consumers (warps of lanes 0..63) cannot read.  Four Sp-producer warps own those lanes: each is paired with the consumer warp of
     // the same (channel group, column half), the two swap half of their 32 rows through shared memory (as in pass D) and each
-    // does the per-element work and the global stores of 16 rows.  The W2 / P3 staging areas are free once their A tiles are in
-    // tensor memory: they are the two buffers of the swap (4 pairs x [consumer -> partner 2 KB | partner -> consumer 2 KB]).
+    // does the per-element work and the global stores of 16 rows.  The W2 staging area is free once its A tiles are in tensor memory:
+    // it is the buffer of the swap (4 pairs x [consumer -> partner 2 KB | partner -> consumer 2 KB], a second barrier after the reads).
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = p.R / BT;
@@ -793,6 +779,8 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
         for (int i = 0; i < 2; ++i) {
             mbar_init(&h1_full[i], 4);
             mbar_init(&h1_empty[i], 1);
+            mbar_init(&x16_full[i], 2);
+            mbar_init(&d1_full[i], 1);
             mbar_init(&d2_full[i], 1);
             mbar_init(&d2_empty[i], 4);        // the h2 producers read z2 (the dh2 consumers take mask and z2 from the h2 image)
         }
@@ -825,6 +813,16 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     const int nB = (nhl == 2) ? 2 * BT : BT;                                                   // [hi | lo] stacked B operand
     const uint32_t idesc_mn2 = umma_idesc_bf16(128, nB) | UMMA_B_MN_MAJOR;
     const uint32_t idesc_dg2 = umma_idesc_bf16(128, nB) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;
+    // this warp's 32 lanes of the layer-0 A tile (row = channel `ch`): K slots [Wh0..3 | Wh0..3 | Wl0..3 | bh bl 0 0], two bf16 per column
+    auto put_w1a = [&](int ch) {
+        const float s1 = __ldg(p.scale1 + ch), t1 = __ldg(p.shift1 + ch);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + ch);
+        const float v[8] = {s1 * w.x, s1 * w.y, s1 * w.z, s1 * w.w, fmaf(s1, __ldg(p.b1 + ch), t1), 0.f, 0.f, 0.f};
+        uint4 h, l;
+        split_bf16x8(v, h, l);
+        const uint32_t u[8] = {h.x, h.y, h.x, h.y, l.x, l.y, (h.z & 0xFFFFu) | (l.z << 16), 0u};
+        tmem_st8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 480, u);
+    };
 
     if (warp == 18) {
         // one elected thread issues every bulk copy, tcgen05.mma and tcgen05.commit of the CTA (elect.sync: see umma.cuh, lean issue path)
@@ -876,6 +874,19 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 umma_commit(&d2_full[b]);
                 PROF_MARK(5)
             };
+            // z1'(j) = W1' x(j) into D2[j & 1]: two tiles ahead of Sp h2^T, one ahead of z2 (the producers need it to make h1(j))
+            const uint32_t w1a_t = tmem_base + 480;
+            const UDesc x16_k = udesc_k(smem_u32(x16s));
+            auto issue_z1 = [&](int j) {
+                const int b = j & 1, u = (j >> 1) & 1;
+                mbar_wait(&x16_full[b], u);
+                mbar_wait(&d2_empty[b], u ^ 1);                    // z2(j - 2) has been copied out of these columns
+                tc_fence_after_sync();
+                umma_ts(tmem_base + 64 * b, w1a_t, x16_k, (uint32_t)b * (IMG64 / 16), idesc_kk, 0u);
+                umma_commit(&d1_full[b]);
+            };
+            issue_z1(0);
+            if (my_tiles > 1) issue_z1(1);
             issue_z2(0);
 #pragma unroll 1
             for (int it = 0; it < my_tiles; ++it) {
@@ -901,6 +912,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 }
                 PROF_MARK(2)
                 if (it + 1 < my_tiles) issue_z2(it + 1);
+                if (it + 2 < my_tiles) issue_z1(it + 2);
                 mbar_wait(dh_empty, (it & 1) ^ 1);
                 PROF_MARK(6)
                 tc_fence_after_sync();
@@ -933,41 +945,65 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             for (int tile = 0; tile < 4; ++tile)
                 tmem_put_a_tile(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 384 + 32 * tile, (tile == 2 && nhl == 2) ? p3s + 8192 : nullptr,
                                 (warp & 1) * 32 + lane);
+            put_w1a((warp & 1) * 32 + lane);
             tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready);
         }
         const int pw = (warp == 10) ? 0 : (warp == 11) ? 1 : (warp == 14) ? 2 : 3;
-        const int ptid = pw * 32 + lane, ch = ptid & 63, half = ptid >> 6;
-        const float s1 = __ldg(p.scale1 + ch), t1 = __ldg(p.shift1 + ch);
-        const float4 w = __ldg(reinterpret_cast<const float4*>(p.w1) + ch);
-        const float wx = s1 * w.x, wy = s1 * w.y, wz = s1 * w.z, ww = s1 * w.w, bf = fmaf(s1, __ldg(p.b1 + ch), t1);
+        const int ptid = pw * 32 + lane, ch = ptid & 63, half = ptid >> 6;      // TMEM lane 64 + ch: the second copy of the channels
+        const bool writer = ptid < BT;                                           // warps 10, 11: one x row each
         const float4* xg = reinterpret_cast<const float4*>(p.xt) + t0 * BT;
-        float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ptid < BT) xnext = __ldg(xg + ptid);
+        auto put_x = [&](int j, float4 x) {                                      // rows of tile j -> K = 16 operand rows, slot j & 1
+            const float xv[8] = {x.x, x.y, x.z, x.w, 1.f, 0.f, 0.f, 0.f};
+            uint4 h, l;
+            split_bf16x8(xv, h, l);
+            uint8_t* x16 = x16s + (j & 1) * IMG64;
+            *reinterpret_cast<uint4*>(x16 + sw128_offset((uint32_t)ptid, 0)) = make_uint4(h.x, h.y, l.x, l.y);
+            *reinterpret_cast<uint4*>(x16 + sw128_offset((uint32_t)ptid, 1)) = make_uint4(h.x, h.y, h.z | (h.z << 16), 0u);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x16_full[j & 1]);
+        };
+        if (writer) {
+            mbar_wait(a_ready, 0);                                               // the P3 staging area has been copied to tensor memory
+            put_x(0, __ldg(xg + ptid));
+            if (my_tiles > 1) put_x(1, __ldg(xg + BT + ptid));
+        }
         PROF_DECL(4)
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
-            float4* xtile = reinterpret_cast<float4*>(xs + (it & 1) * BT * 16);
-            if (ptid < BT) {
-                xtile[ptid] = xnext;
-                if (it + 1 < my_tiles) xnext = __ldg(xg + (long long)(it + 1) * BT + ptid);
-            }
-            named_bar_sync(1, 128);
+            const int b = it & 1, u = (it >> 1) & 1;
+            float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (writer && it + 2 < my_tiles) xn = __ldg(xg + (long long)(it + 2) * BT + ptid);
+            mbar_wait(&d1_full[b], u);
+            tc_fence_after_sync();
+            float z[32];
+            tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(64 * b + half * 32), z);
+            tmem_ld_wait();
+            tc_fence_before_sync();
             PROF_MARK(0)
-            mbar_wait(&h1_empty[it & 1], ((it >> 1) & 1) ^ 1);
+            if (writer && it + 2 < my_tiles) put_x(it + 2, xn);                  // z1'(it) is complete: its operand slot is free
+            mbar_wait(&h1_empty[b], u ^ 1);
             PROF_MARK(1)
-            produce_h1_tile64(xtile, h1s + (it & 1) * 2 * IMG64, nhl, ch, half, wx, wy, wz, ww, bf);
+            uint8_t* img = h1s + b * 2 * IMG64;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(z[q * 8 + e], 0.f);
+                store_img8(img, nhl, IMG64, ch, half * 4 + q, v);
+            }
             PROF_MARK(2)
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&h1_full[it & 1]);
+            if (lane == 0) mbar_arrive(&h1_full[b]);
             PROF_MARK(3)
         }
 #ifdef FACL_PROFILE_ROLES
         if (blockIdx.x == 1 && ptid == 0)
-            printf("pass C h1 producer, cycles/tile: x tile + bar %lld | wait h1_empty %lld | produce %lld | fence+arrive %lld\n",
+            printf("pass C h1 producer, cycles/tile: wait z1 + ld %lld | x16 + wait h1_empty %lld | relu + store %lld | fence+arrive %lld\n",
                    prof_[0] / my_tiles, prof_[1] / my_tiles, prof_[2] / my_tiles, prof_[3] / my_tiles);
 #endif
     } else if (warp == 8 || warp == 9 || warp == 12 || warp == 13) {
@@ -1027,6 +1063,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 const uint8_t* img = (tile < 2 ? w2s : p3s) + (tile & 1) * 8192;
                 tmem_put_a_tile(tmem_base + ((uint32_t)(lg * 32) << 16) + 384 + 32 * tile, img, j);
             }
+            put_w1a(j);
             tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
@@ -1078,7 +1115,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             __syncwarp();
             if (lane == 0) mbar_arrive(&h2_empty[b]);   // the h2 stage may be refilled once the MMA stream and the eight warps have read it
             // rows 16..31 go to the partner warp; its A_lo B_hi half of rows 0..15 (TMEM lanes 64..127) comes back
-            uint8_t* ex = ((it & 1) ? p3s : w2s) + pair * 4096 + lane * 16;
+            uint8_t* ex = w2s + pair * 4096 + lane * 16;
 #pragma unroll
             for (int r4 = 0; r4 < 4; ++r4)
                 *reinterpret_cast<float4*>(ex + r4 * 512) = make_float4(g[16 + 4 * r4], g[17 + 4 * r4], g[18 + 4 * r4], g[19 + 4 * r4]);
@@ -1093,6 +1130,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                     gv[4 * r4] += f.x; gv[4 * r4 + 1] += f.y; gv[4 * r4 + 2] += f.z; gv[4 * r4 + 3] += f.w;
                 }
             }
+            named_bar_sync(2 + pair, 64);                 // both warps have read: the (single) swap buffer may be rewritten
             dh2_rows16(gv, hh, hl, p.dh2 + (t0 + it) * (2 * IMG64), nhl, j, colhalf * 4, q3, c2, s_acc, q_acc);
             PROF_MARK(4)
         }
@@ -1124,7 +1162,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             pq3 = __ldg(p.q3 + pj);
         }
         auto partner_rows = [&](int t) {
-            uint8_t* ex = ((t & 1) ? p3s : w2s) + ppair * 4096 + lane * 16;
+            uint8_t* ex = w2s + ppair * 4096 + lane * 16;
             float gv[16];
             if (nhl == 2) {
                 mbar_wait(dh_full, t & 1);
@@ -1150,6 +1188,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 const float4 f4 = *reinterpret_cast<const float4*>(ex + r4 * 512);
                 gv[4 * r4] += f4.x; gv[4 * r4 + 1] += f4.y; gv[4 * r4 + 2] += f4.z; gv[4 * r4 + 3] += f4.w;
             }
+            named_bar_sync(2 + ppair, 64);
             const uint8_t* h2img = h2s + (t & 1) * 2 * IMG64;
             uint4 hh[2], hl[2];
 #pragma unroll

@@ -226,6 +226,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&u)[32
         "r"(u[31])
         : "memory");
 }
+// 8-column variant (a 128 x 16 bf16 A tile: two bf16 per column)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&u)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]),
+                 "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
