@@ -725,19 +725,24 @@ __device__ __forceinline__ void dh2_rows16(const float (&gv)[16], const uint4 (&
 
 // --------------------------------------------------------------------------------------------------------------------
 // pass C   (22 warps)
-// warps 0-7         : Sp producers (thread = channel c): one bf16 hi/lo pair per tile; flush dW3s at the end
+// warps 0,1,4,5     : Sp producers (thread = channels c and c + 64): one bf16 hi/lo pair per channel and tile
+// warps 2,3,6,7     : partners of the dh2 consumers: they own TMEM lanes 64..127, where the A_lo products of dh2 land (see below)
+//                     (all of warps 0-7 flush dW3s at the end)
 // warps 8,9,12,13   : z2 -> h2 image (thread = channel j, TMEM lanes 0..63)
-// warps 10,11,14,15 : x -> h1 image producers
+// warps 10,11,14,15 : h1 image producers: relu(z1') read from tensor memory (layer 0 is one K = 16 instruction per tile); warps 10, 11
+//                     also write the K = 16 operand rows of the tile two ahead
 // warps 16,17,20,21 : dh2 consumers (thread = channel j): + q3, ReLU2 mask, BN2-backward sums, image -> HBM
 // warp 18           : MMA issuer (warp 19 idles)
-// TMEM columns: D2[b] 0/64, DH2 128..255 ([hi | lo] column halves), DW3s[h] 256/320, A tiles W2_hi / W2_lo / P3_hi / P3_lo at
-// 384 / 416 / 448 / 480
+// TMEM columns: D2[b] 0/64 (z1'(t), then z2(t)), DH2 128..255 ([B_hi | B_lo] column halves), DW3s[h] 256/320, A tiles W2_hi 384, W2_lo 416,
+//               [P3_hi ; P3_lo] 448, W1' (layer 0, K = 16) 480..487
 // (H2 = sum h2 h2^T and s2, which dW3 also needs, were accumulated by pass B of the forward)
 //
 // tcgen05.mma time on these narrow tiles is set by the operand bytes it pulls from shared memory (the 4 KB A tile above
-// all), not by the math, so the bf16x3 scheme is issued as TWO instructions per k-step instead of three: the B images
-// are stored [hi | lo], and one N = 128 instruction against A_hi yields A_hi B_hi (columns 0..63) and A_hi B_lo (columns
-// 64..127); A_lo B_hi is added onto columns 0..63.  A consumer thread adds its two column halves in registers.
+// all), not by the math.  For dh2 the bf16x3 scheme is ONE instruction per k-step: the B images are stored [hi | lo] and the A
+// operand is stacked [A_hi 64 rows ; A_lo 64 rows], so an M = 128, N = 128 instruction yields A_hi B_hi | A_hi B_lo in lanes
+// 0..63 and A_lo B_hi (| A_lo B_lo, unused) in lanes 64..127.  A consumer thread adds its two column halves in registers; the
+// lane-64..127 half is read by the partner warp, and the two warps swap half of their rows through shared memory so that each
+// finishes 16 complete rows.  (z2 and dW3s use the plain 3-term form: their accumulators have no columns to spare.)
 // --------------------------------------------------------------------------------------------------------------------
 constexpr int C_THREADS = 22 * 32;
 
@@ -1318,8 +1323,11 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
 
 // --------------------------------------------------------------------------------------------------------------------
 // pass D   (14 warps)
-// warps 0-7   : dh1 consumers: TMEM lane quarter = warp % 4, column half = warp / 4
-// warps 8-11  : x -> h1 image producers          warp 12 : MMA issuer          warp 13 : bulk-TMA loader of dh2' tiles
+// warps 0-7   : dh1 consumers: TMEM lane quarter = warp % 4, column half = warp / 4; the warps of quarters q and q + 2 (A_hi / A_lo products
+//               of the same channels) swap half of their rows through shared memory and each finishes 16 complete rows
+// warps 8-11  : h1 image producers: relu(z1') read from tensor memory (layer 0 is one K = 16 instruction per tile); warps 8, 9 also write
+//               the fp32 x rows (for the consumers) and the K = 16 operand rows of the next tile
+// warp 12     : MMA issuer          warp 13 : bulk-TMA loader of dh2' tiles
 // TMEM columns: DH1[b] 0..127 / 128..255 (column halves = B_hi / B_lo products), [dW2s ; H1] 256, z1'[b] 320 / 384,
 //               A tiles (E0 W2)^T 448, P2 480
 //
