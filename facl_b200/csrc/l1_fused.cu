@@ -254,14 +254,18 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             const UDesc h2_mn = udesc_mn(smem_u32(h2s), H2_LBO, ACT_SBO);            // stage b 32 KB further, lo 8 KB further
             const UDesc h2_k = udesc_k(smem_u32(h2s));                               // a 64-row block [hi ; lo] as a K-major tile
             constexpr uint32_t STAGE = 2 * ACT_BYTES / 16;
+            PROF_DECL(8)
             auto issue_mma2 = [&](int it) {
                 const int b = it & 1, u = (it >> 1) & 1;
+                PROF_MARK(7)
                 mbar_wait(&h1_full[b], u);
+                PROF_MARK(0)
                 if (PASS_B) {
                     if (it > 0) mbar_wait(&d2_empty[(it - 1) & 1], ((it - 1) >> 1) & 1);      // the one D2 has been copied out
                 } else {
                     mbar_wait(&d2_empty[b], u ^ 1);
                 }
+                PROF_MARK(1)
                 tc_fence_after_sync();
                 if (W2_TMEM)
                     mma_tmem_weight_act(tmem_base + 128 * b, w2_t, w2_t + 32, h1_mn, b * STAGE, ACT_BYTES / 16, split, idesc);
@@ -269,6 +273,7 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                     mma_weight_act(tmem_base, w2_k, 0, 8192 / 16, h1_mn, b * STAGE, ACT_BYTES / 16, split, idesc);
                 umma_commit(&h1_empty[b]);
                 umma_commit(&d2_full[b]);
+                PROF_MARK(2)
             };
             int it = 0;
             long long t = blockIdx.x;
@@ -294,12 +299,16 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                 if (t + gridDim.x < ntiles) issue_mma2(it + 1);
                 if (PASS_B) {
                     const int b = it & 1, u = (it >> 1) & 1;
+                    PROF_MARK(7)
                     mbar_wait(&h2_full[b], u);
+                    PROF_MARK(3)
                     for (int h = 0; h < 2; ++h) {
                         mbar_wait(&d3_empty[h], (it & 1) ^ 1);
+                        PROF_MARK(4)
                         tc_fence_after_sync();
                         mma_weight_act(tmem_base + 256 + 128 * h, w3_k, h * (32768 / 16), 16384 / 16, h2_mn, b * STAGE, H2_LO / 16, split, idesc);
                         umma_commit(&d3_full[h]);
+                        PROF_MARK(5)
                     }
                     if (GRAM) {
                         // H2 += h2 h2^T, reduction over the tile's rows.  A 64-row block [hi 64 ch ; lo 64 ch] is used as the 128-row A
@@ -315,8 +324,15 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                         }
                     }
                     umma_commit(&h2_empty[b]);
+                    PROF_MARK(6)
                 }
             }
+#ifdef FACL_PROFILE_ROLES
+            if (PASS_B && blockIdx.x == 1 && it > 0)
+                printf("fwd pass B MMA thread, cycles/tile: wait h1_full %lld | wait d2_empty %lld | issue z2 %lld | wait h2_full %lld | wait d3_empty %lld | "
+                       "issue z3 %lld | issue Gram %lld | other %lld\n", prof_[0] / it, prof_[1] / it, prof_[2] / it, prof_[3] / it, prof_[4] / it,
+                       prof_[5] / it, prof_[6] / it, prof_[7] / it);
+#endif
             if (PASS_B && GRAM) umma_commit(fin_bar);
         }
     } else if (PASS_B ? (warp == 10 || warp == 11 || warp == 14 || warp == 15) : (warp < 8 || warp >= 17)) {
@@ -568,11 +584,7 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                 tc_fence_after_sync();
                 float best = -INFINITY;
                 int barg = 0;
-#pragma unroll 1
-                for (int q = 0; q < TILE / 32; ++q) {
-                    float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(256 + 128 * h + q * 32), v);
-                    tmem_ld_wait();
+                auto process = [&](const float (&v)[32], int q) {
                     if (K >= 32) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
@@ -610,11 +622,30 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                             }
                         }
                     }
-                }
-                nrows += TILE;
+                };
+                // The four 32-column chunks of the accumulator are read one AHEAD of their use (two register buffers), and the accumulator
+                // is handed back as soon as the last chunk is in registers: the z3 instructions of the next tile waited ~2000 of 4900
+                // cycles per tile for this role, which had been paying a tcgen05.ld round trip plus the arithmetic of every chunk in
+                // sequence while holding the (single) accumulator (role accounting, profiles/r2_role_profile.md).
+                static_assert(TILE == 128, "four chunks");
+                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(256 + 128 * h);
+                float va[32], vb[32];
+                tmem_ld32(taddr, va);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 32, vb);
+                process(va, 0);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 64, va);
+                process(vb, 1);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 96, vb);
+                process(va, 2);
+                tmem_ld_wait();
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d3_empty[h]);
+                process(vb, 3);
+                nrows += TILE;
             }
             if (STAT == 1) {
                 const float n = (float)nrows;
