@@ -575,6 +575,7 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
             const int c = h * 128 + lq * 32 + lane;
             const float b3 = __ldg(p.b3 + c);
             const float sgn = (__ldg(p.gamma3 + c) >= 0.f) ? 1.f : -1.f;
+            const bool allpos = __all_sync(0xffffffffu, sgn > 0.f);
             const int K = p.K, groups = TILE / K;
             float s_acc = 0.f, q_acc = 0.f;
             long long nrows = 0;
@@ -584,7 +585,10 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                 tc_fence_after_sync();
                 float best = -INFINITY;
                 int barg = 0;
-                auto process = [&](const float (&v)[32], int q) {
+                // POS: every channel of this warp takes the MAXIMUM (BatchNorm weight >= 0, the usual case): the per-element sign multiply
+                // is skipped.  The z3 consumers share their issue slots with the h1 producers and are the period of this pass.
+                auto chunk = [&](auto pos_c, const float (&v)[32], int q) {
+                    constexpr bool POS = decltype(pos_c)::value;
                     if (K >= 32) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
@@ -592,7 +596,7 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                                 s_acc += v[i];
                                 q_acc = fmaf(v[i], v[i], q_acc);
                             }
-                            const float sv = v[i] * sgn;
+                            const float sv = POS ? v[i] : v[i] * sgn;
                             barg = (sv > best) ? (q * 32 + i) : barg;
                             best = fmaxf(best, sv);
                         }
@@ -610,7 +614,7 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                                 s_acc += v[i];
                                 q_acc = fmaf(v[i], v[i], q_acc);
                             }
-                            const float sv = v[i] * sgn;
+                            const float sv = POS ? v[i] : v[i] * sgn;
                             barg = (sv > best) ? i : barg;
                             best = fmaxf(best, sv);
                             if (((i + 1) & (K - 1)) == 0) {
@@ -623,29 +627,17 @@ __global__ void __launch_bounds__(PASS_B ? NTHREADS_B : NTHREADS_A, 1) l1_fwd_ke
                         }
                     }
                 };
-                // The four 32-column chunks of the accumulator are read one AHEAD of their use (two register buffers), and the accumulator
-                // is handed back as soon as the last chunk is in registers: the z3 instructions of the next tile waited ~2000 of 4900
-                // cycles per tile for this role, which had been paying a tcgen05.ld round trip plus the arithmetic of every chunk in
-                // sequence while holding the (single) accumulator (role accounting, profiles/r2_role_profile.md).
-                static_assert(TILE == 128, "four chunks");
-                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(256 + 128 * h);
-                float va[32], vb[32];
-                tmem_ld32(taddr, va);
-                tmem_ld_wait();
-                tmem_ld32(taddr + 32, vb);
-                process(va, 0);
-                tmem_ld_wait();
-                tmem_ld32(taddr + 64, va);
-                process(vb, 1);
-                tmem_ld_wait();
-                tmem_ld32(taddr + 96, vb);
-                process(va, 2);
-                tmem_ld_wait();
+#pragma unroll 1
+                for (int q = 0; q < TILE / 32; ++q) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(256 + 128 * h + q * 32), v);
+                    tmem_ld_wait();
+                    if (allpos) chunk(std::true_type{}, v, q); else chunk(std::false_type{}, v, q);
+                }
+                nrows += TILE;
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d3_empty[h]);
-                process(vb, 3);
-                nrows += TILE;
             }
             if (STAT == 1) {
                 const float n = (float)nrows;
