@@ -781,13 +781,14 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     uint8_t* h1s = p3s + 16384;                // 2 stages x (hi 8 KB | lo 8 KB): with one stage, h1(t + 1) could not be produced before
                                                // z2(t) had read h1(t), and the 64-row recompute sat on the critical chain of the tile
     uint8_t* h2s = h1s + 2 * 2 * IMG64;        // 2 stages x (hi | lo)
-    uint8_t* sps = h2s + 2 * 2 * IMG64;        // Sp [256 c][64 r]: hi 32 KB | lo 32 KB
+    uint8_t* sps = h2s + 2 * 2 * IMG64;        // Sp [256 c][64 r]: hi 32 KB | lo 32 KB; in bf16 mode (no lo part) two STAGES of 32 KB, so that
+                                               // Sp(t + 1) is written while W3^T Sp(t) still reads Sp(t)
     uint8_t* xs = sps + 65536;                 // 2 stages x 64 rows x 16 B
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * BT * 16);
     uint64_t *h1_full = bars + 18, *h1_empty = bars + 20, *x16_full = bars + 22, *d1_full = bars + 24, *d2_full = bars + 2, *d2_empty = bars + 4, *h2_full = bars + 6,
-             *h2_empty = bars + 8, *sp_full = bars + 10, *sp_empty = bars + 11, *dh_full = bars + 12, *dh_empty = bars + 13,
+             *h2_empty = bars + 8, *sp_full = bars + 10, *sp_empty = bars + 26, *dh_full = bars + 12, *dh_empty = bars + 13,
              *a_ready = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
     // Layer 0 runs on the tensor pipe as in passes A and D: z1'(t) is ONE K = 16 instruction into the columns of D2[t & 1] (z2(t) overwrites
     // them only after the h1 producers have read z1'), its A tile (W1 folded with BN1, [hi | hi | lo | bias] K slots, rows 64..127 a copy
     // of rows 0..63) sits in tensor memory columns 480..487 and its B tiles (the x rows of a tile as K = 16 bf16) in the P3 staging area.
@@ -819,8 +820,10 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
             mbar_init(&h2_full[i], 4);
             mbar_init(&h2_empty[i], 9);        // tcgen05.commit of the MMAs that read the stage + the eight warps of the dh2 role
         }
-        mbar_init(sp_full, 4);                 // warps 0, 1, 4, 5 write Sp (two channels per thread); 2, 3, 6, 7 are the dh2 partners
-        mbar_init(sp_empty, 1);
+        for (int i = 0; i < 2; ++i) {          // bf16 mode: the unused lo half of the Sp image is a second stage (see `sps`)
+            mbar_init(&sp_full[i], 4);         // warps 0, 1, 4, 5 write Sp (two channels per thread); 2, 3, 6, 7 are the dh2 partners
+            mbar_init(&sp_empty[i], 1);
+        }
         mbar_init(a_ready, 4);
         mbar_init(w_bar, 1);
         mbar_init(fin_bar, 1);
@@ -921,9 +924,11 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 const int b = it & 1, u = (it >> 1) & 1;
                 const uint32_t st = (uint32_t)b * (2 * IMG64 / 16);               // h2 stage offset
                 const uint32_t acc0 = it == 0 ? 0u : 1u;
+                const int ss = split ? 0 : b, sp_par = split ? (it & 1) : u;      // Sp stage / phase
+                const uint32_t so = (uint32_t)ss * (32768 / 16);
                 mbar_wait(&h2_full[b], u);
                 PROF_MARK(0)
-                mbar_wait(sp_full, it & 1);
+                mbar_wait(&sp_full[ss], sp_par);
                 PROF_MARK(1)
                 tc_fence_after_sync();
 #pragma unroll
@@ -931,7 +936,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                     const uint32_t d = tmem_base + 256 + 64 * h;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        umma_ss(d, sp_k, h * 1024 + ks * 2, h2_k, st + ks * 2, idesc_kk, ks > 0 ? 1u : acc0);
+                        umma_ss(d, sp_k, so + h * 1024 + ks * 2, h2_k, st + ks * 2, idesc_kk, ks > 0 ? 1u : acc0);
                         if (split) {
                             umma_ss(d, sp_k, h * 1024 + ks * 2, h2_k, st + LO64 + ks * 2, idesc_kk, 1u);
                             umma_ss(d, sp_k, 2048 + h * 1024 + ks * 2, h2_k, st + ks * 2, idesc_kk, 1u);
@@ -947,9 +952,9 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
 #pragma unroll
                 for (int ks = 0; ks < 16; ++ks) {   // dh2 = W3^T Sp: reduction over the 256 channels
                     const uint32_t wa = (ks >> 3) * 2048 + (ks & 7) * 128;
-                    umma_ss(tmem_base + 128, w3_mn, wa, sp_mn, ks * 128, idesc_dg2, ks > 0 ? 1u : 0u);
+                    umma_ss(tmem_base + 128, w3_mn, wa, sp_mn, so + ks * 128, idesc_dg2, ks > 0 ? 1u : 0u);
                 }
-                umma_commit(sp_empty);
+                umma_commit(&sp_empty[ss]);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)      // dh2 += P3 h2: [P3_hi ; P3_lo] x [h2_hi | h2_lo]
                     umma_ts(tmem_base + 128, p3_hi + ks * 8, h2_mn, st + ks * 128, idesc_mn2, 1u);
@@ -1242,7 +1247,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 const float* dpp;
                 const unsigned char* argp;
                 uint8_t* row_hi;
-                int prev;
+                int prev[2];
                 float4 d4;
                 uchar4 a4;
                 float dcur;
@@ -1255,7 +1260,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                 sc[q].dpp = p.dpooled + (long long)cq * p.ldp + (t0 >> ksh);
                 sc[q].argp = p.arg + (long long)cq * p.ldp + (t0 >> ksh);
                 sc[q].row_hi = sps + cq * 128;
-                sc[q].prev = -1;
+                sc[q].prev[0] = sc[q].prev[1] = -1;
                 sc[q].d4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 sc[q].a4 = make_uchar4(0, 0, 0, 0);
                 sc[q].dcur = 0.f;
@@ -1300,22 +1305,25 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
                     off[q] = ((((r >> 3) ^ (cq & 7)) << 4) | ((r & 7) << 1));
                 }
                 PROF_MARK(0)
-                mbar_wait(sp_empty, (it & 1) ^ 1);
+                const int ss = (nhl == 2) ? 0 : (it & 1);                       // Sp stage (bf16 mode: two)
+                mbar_wait(&sp_empty[ss], ((nhl == 2) ? (it & 1) : ((it >> 1) & 1)) ^ 1);
                 PROF_MARK(1)
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     SpChannel& S = sc[q];
-                    if (S.prev >= 0) {
-                        *reinterpret_cast<unsigned short*>(S.row_hi + S.prev) = 0;
-                        *reinterpret_cast<unsigned short*>(S.row_hi + 32768 + S.prev) = 0;
+                    uint8_t* row = S.row_hi + ss * 32768;
+                    const int pv = ss ? S.prev[1] : S.prev[0];
+                    if (pv >= 0) {
+                        *reinterpret_cast<unsigned short*>(row + pv) = 0;
+                        if (nhl == 2) *reinterpret_cast<unsigned short*>(row + 32768 + pv) = 0;
                     }
-                    *reinterpret_cast<unsigned short*>(S.row_hi + off[q]) = __bfloat16_as_ushort(vh[q]);
-                    if (nhl == 2) *reinterpret_cast<unsigned short*>(S.row_hi + 32768 + off[q]) = __bfloat16_as_ushort(vl[q]);
-                    S.prev = off[q];
+                    *reinterpret_cast<unsigned short*>(row + off[q]) = __bfloat16_as_ushort(vh[q]);
+                    if (nhl == 2) *reinterpret_cast<unsigned short*>(row + 32768 + off[q]) = __bfloat16_as_ushort(vl[q]);
+                    if (ss) S.prev[1] = off[q]; else S.prev[0] = off[q];
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(sp_full);
+                if (lane == 0) mbar_arrive(&sp_full[ss]);
                 PROF_MARK(2)
             }
 #ifdef FACL_PROFILE_ROLES
