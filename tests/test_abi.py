@@ -33,3 +33,18 @@ def test_no_cpu_fallback():
     from facl_b200 import ops
     with pytest.raises(_lib.FaclError):
         ops.group_points_raw(torch.zeros(1, 64, 4), 8, 8, 0.1)
+
+
+def test_phase_constants_match_the_header():
+    """facl_b200/dist.py issues facl_train_step in phases: its constants must be the FACL_PHASE_* macros of the header, and the
+    finer cuts must be disjoint bits (the C side tests them with `&`)."""
+    from facl_b200 import dist
+    text = open(os.path.join(ROOT, "include", "facl_b200.h")).read()
+    macros = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+FACL_PHASE_(\w+)\s+(\d+)", text)}
+    names = ["FORWARD", "LOSS", "BACKWARD", "UPDATE", "BACKWARD_HEAD", "BACKWARD_L1", "FORWARD_X", "FORWARD_G", "BACKWARD_HEAD_G",
+             "BACKWARD_HEAD_X"]
+    for n in names:
+        assert macros[n] == getattr(dist, "PHASE_" + n), n
+    bits = [macros[n] for n in names]
+    assert all(b & (b - 1) == 0 for b in bits) and len(set(bits)) == len(bits)
+    assert macros["ALL"] == macros["FORWARD"] | macros["LOSS"] | macros["BACKWARD"] | macros["UPDATE"]
