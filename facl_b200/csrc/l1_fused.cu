@@ -773,7 +773,6 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer (LDS/STS, not generic LD/ST)
-    if (((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) > 768u) __trap();         // C_ALIGN_SLACK (defined with the launcher)
     const int nhl = p.nhl;
     uint8_t* w2s = smem;                       // hi 8 KB | lo 8 KB
     uint8_t* w3s = w2s + 16384;                // [half][hi 16 KB | lo 16 KB]
@@ -783,8 +782,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
     uint8_t* h2s = h1s + 2 * 2 * IMG64;        // 2 stages x (hi | lo)
     uint8_t* sps = h2s + 2 * 2 * IMG64;        // Sp [256 c][64 r]: hi 32 KB | lo 32 KB; in bf16 mode (no lo part) two STAGES of 32 KB, so that
                                                // Sp(t + 1) is written while W3^T Sp(t) still reads Sp(t)
-    uint8_t* xs = sps + 65536;                 // 2 stages x 64 rows x 16 B
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * BT * 16);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sps + 65536);
     uint64_t *h1_full = bars + 18, *h1_empty = bars + 20, *x16_full = bars + 22, *d1_full = bars + 24, *d2_full = bars + 2, *d2_empty = bars + 4, *h2_full = bars + 6,
              *h2_empty = bars + 8, *sp_full = bars + 10, *sp_empty = bars + 26, *dh_full = bars + 12, *dh_empty = bars + 13,
              *a_ready = bars + 14, *w_bar = bars + 16, *fin_bar = bars + 17;
@@ -1951,10 +1949,7 @@ __global__ void __launch_bounds__(1024) l1_gamma0_fix_kernel(const float4* __res
     }
 }
 
-// (the last term is the slack for aligning the dynamic window to 1 KB; the window starts right behind the 1 KB the driver reserves,
-//  so none of it is used in practice, and the kernel traps if more than this were needed)
-constexpr uint32_t C_ALIGN_SLACK = 768;
-size_t l1_bwd_c_smem() { return 16384 + 65536 + 16384 + 4 * IMG64 + 4 * IMG64 + 65536 + 2 * BT * 16 + 256 + C_ALIGN_SLACK; }
+size_t l1_bwd_c_smem() { return 16384 + 65536 + 16384 + 4 * IMG64 + 4 * IMG64 + 65536 + 256 + 1024; }
 size_t l1_bwd_d_smem() { return 16384 + 16384 + D_STAGES * D_STAGE_BYTES + 16384 + D_XS * IMG64 + D_XS * BT * 16 + 32768 + 512 + 1024; }
 
 // sum x (4) and sum x x^T (10 unique) over all rows, in double
