@@ -705,8 +705,8 @@ struct L1BwdParams {
     const uint8_t* p2_img;    // packed image of P2
     const float* q2;          // [64]
     float* dw2s;              // [64][64] += dh2' h1^T (atomic)
-    float* amat;              // [2*grid][64][4] per-CTA sum dh1' x^T
-    float* stats;             // [2*grid][64][2]: pass C (sum dh2', sum dh2' z2); pass D (sum dh1', sum dh1' z1)
+    float* amat;              // [4*grid][64][4] per-CTA (consumer warp group) sum dh1' x^T
+    float* stats;             // [4*grid][64][2]: pass C (sum dh2', sum dh2' z2); pass D (sum dh1', sum dh1' z1)
     // optional test hooks (pass C): the ReLU decisions of the recomputed forward, so a checker can impose them
     unsigned char* dbg_mask1; // [R/64][64][64]  h1 > 0 as pass D sees it (the only place the ReLU1 mask enters the backward)
     unsigned char* dbg_mask2; // [R/64][64][64]  h2 > 0
@@ -1363,7 +1363,8 @@ __global__ void __launch_bounds__(C_THREADS, 1) l1_bwd_c_kernel(const L1BwdParam
 // Every product here has only 64 real output rows, so the M = 128 instruction is fed STACKED operands instead of padding:
 //  * a weight image is stored [hi 64 rows | lo 64 rows]; read as one 128-row A tile, lanes 0..63 receive A_hi * B and lanes
 //    64..127 A_lo * B -- the bf16x3 scheme needs two instructions (B_hi, B_lo) instead of three, and because everything
-//    the consumers derive from dh1 is a SUM over rows, the two lane halves are simply reduced as separate partials;
+//    the consumers derive from dh1 is a SUM over rows, the two lane halves could be reduced as separate partials; since round 2 the two
+//    warps that hold the halves of the same channels swap half of their rows instead, and each finishes 16 complete rows;
 //  * dh2' and h1 of a tile sit next to each other in a stage ([dh2'_hi | h1_hi | dh2'_lo | h1_lo]), so one 128-row A tile
 //    against B = h1 yields dh2' h1^T (lanes 0..63) and h1 h1^T (lanes 64..127) at once.
 // --------------------------------------------------------------------------------------------------------------------
